@@ -1,0 +1,51 @@
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Definitions of the golden cases shared by ``make_golden.py`` (which runs the real reference) and the tests (which run
+the oracle and the CUDA path on the same seeded inputs).  Inputs follow SURVEY.md section 8(d): standardised
+WeatherBench-shaped fields, LR = randn, SR = bicubic x4 of LR.
+"""
+import torch
+import torch.nn.functional as F
+
+from .weights import seeded_randn
+
+LINEAR_1000 = {"schedule": "linear", "n_timestep": 1000, "linear_start": 1e-6, "linear_end": 1e-2}
+
+
+def unet_cfg(height, width, inner=64, c_img=1, attn_res=(16,), mults=(1, 2, 4, 8, 8), res_blocks=2, in_channel=None):
+    return {
+        "in_channel": 5 * c_img if in_channel is None else in_channel, "out_channel": c_img, "norm_groups": 32,
+        "inner_channel": inner, "channel_mults": list(mults), "attn_res": list(attn_res), "res_blocks": res_blocks,
+        "dropout": 0.0, "image_height": height, "image_width": width, "image_channels": c_img,
+    }
+
+
+def fields(tag, batch, c_img, height, width, seed, scale=4):
+    """LR, SR(bicubic), HR synthetic fields."""
+    lr = seeded_randn(tag + ".lr", (batch, c_img, height // scale, width // scale), seed)
+    sr = F.interpolate(lr, scale_factor=scale, mode="bicubic")
+    hr = sr + 0.3 * seeded_randn(tag + ".hr", (batch, c_img, height, width), seed)
+    return lr, sr, hr
+
+
+def short_schedule(T):
+    return {"schedule": "linear", "n_timestep": T, "linear_start": 1e-6, "linear_end": 1e-2}
+
+
+# name -> spec.  'small' cases run in well under a second on CPU; 'full' ones are Cfg-A at 128x256.
+CASES = {
+    # one denoiser call
+    "resdiff_step_small": dict(kind="resdiff_step", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=11, level=(0.83, 0.31)),
+    "resdiff_step_full_b1": dict(kind="resdiff_step", cfg=unet_cfg(128, 256), batch=1, seed=12, level=(0.645,)),
+    "resdiff_step_full_b2": dict(kind="resdiff_step", cfg=unet_cfg(128, 256), batch=2, seed=13, level=(0.9, 0.2)),
+    # short reverse chains with injected noise
+    "resdiff_chain_small": dict(kind="resdiff_chain", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=21, T=4),
+    "resdiff_chain_full_b1": dict(kind="resdiff_chain", cfg=unet_cfg(128, 256), batch=1, seed=22, T=3),
+    # training loss (dropout 0, injected t / level / noise)
+    "resdiff_loss_small": dict(kind="resdiff_loss", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=31, t=400),
+    # priors and the RRDB-conditioned variant
+    "simple_cnn": dict(kind="simple_cnn", batch=2, seed=41, lr_hw=(8, 16)),
+    "rrdb_small": dict(kind="rrdb", batch=1, seed=42, lr_hw=(8, 16)),
+    "srdiff_step_small": dict(kind="srdiff_step", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=1), batch=2, seed=43,
+                              level=(0.7, 0.4)),
+}

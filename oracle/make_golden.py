@@ -1,0 +1,175 @@
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Generates tests/golden/*.npz by running the REAL reference (imported from /root/reference through
+oracle/ref_shims.py) on the seeded cases of oracle/cases.py.  Run in the build container:
+
+    python -m oracle.make_golden            # all cases
+    python -m oracle.make_golden NAME ...   # selected cases
+
+The fixtures store inputs and reference outputs (small fields only); weights are re-derived from the seed
+(oracle/weights.py), with a checksum stored to detect RNG drift.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import ref_shims
+from .cases import CASES, LINEAR_1000, fields, short_schedule
+from .schedule import BUFFER_NAMES
+from .weights import fill_module, seeded_randn
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _checksum(module):
+    with torch.no_grad():
+        return np.array([float(sum(p.double().sum() for p in module.parameters())),
+                         float(sum(p.double().abs().sum() for p in module.parameters()))])
+
+
+def _unet(ref, cfg, srdiff=False):
+    cls = ref.SRDiffUNet if srdiff else ref.ResDiffUNet
+    net = cls(in_channel=cfg["in_channel"], out_channel=cfg["out_channel"], norm_groups=cfg["norm_groups"],
+              inner_channel=cfg["inner_channel"], channel_mults=cfg["channel_mults"], attn_res=cfg["attn_res"],
+              res_blocks=cfg["res_blocks"], dropout=cfg["dropout"], image_height=cfg["image_height"],
+              image_width=cfg["image_width"], image_channels=cfg["image_channels"])
+    return net.eval()
+
+
+class _InjectedNoise:
+    """Replaces torch.randn / torch.randn_like by an iterator over a pre-generated tensor."""
+
+    def __init__(self, noise):
+        self.noise, self.i = noise, 0
+
+    def __enter__(self):
+        self._randn, self._randn_like = torch.randn, torch.randn_like
+
+        def nxt(*a, **k):
+            out = self.noise[self.i].clone()
+            self.i += 1
+            return out
+
+        torch.randn, torch.randn_like = nxt, nxt
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn, torch.randn_like = self._randn, self._randn_like
+
+
+def run_case(ref, name, spec):
+    kind, seed, b = spec["kind"], spec["seed"], spec["batch"]
+    out = {}
+    with torch.no_grad():
+        if kind == "resdiff_step":
+            cfg = spec["cfg"]
+            net = fill_module(_unet(ref, cfg), seed)
+            _, sr, _ = fields(name, b, cfg["image_channels"], cfg["image_height"], cfg["image_width"], seed)
+            x_t = seeded_randn(name + ".xt", sr.shape, seed)
+            level = torch.tensor(spec["level"], dtype=torch.float32).view(b, 1)
+            out.update(cond=sr, x_t=x_t, level=level, eps=net(torch.cat([sr, x_t], 1), level), wsum=_checksum(net))
+        elif kind == "resdiff_chain":
+            cfg, T = spec["cfg"], spec["T"]
+            net = fill_module(_unet(ref, cfg), seed)
+            diff = ref.ResDiffDiffusion(net, image_height=cfg["image_height"], image_width=cfg["image_width"],
+                                        channels=cfg["image_channels"], conditional=True)
+            diff.set_new_noise_schedule(short_schedule(T), "cpu")
+            _, sr, _ = fields(name, b, cfg["image_channels"], cfg["image_height"], cfg["image_width"], seed)
+            noise = seeded_randn(name + ".noise", (T + 1,) + tuple(sr.shape), seed)
+            with _InjectedNoise(noise) as inj:
+                res = diff.super_resolution({"SR": sr})
+                assert inj.i == T, inj.i          # 1 randn + (T-1) randn_like
+            out.update(cond=sr, noise=noise, sr_out=res, wsum=_checksum(net))
+        elif kind == "resdiff_loss":
+            cfg, t = spec["cfg"], spec["t"]
+            net = fill_module(_unet(ref, cfg), seed)
+            diff = ref.ResDiffDiffusion(net, image_height=cfg["image_height"], image_width=cfg["image_width"],
+                                        channels=cfg["image_channels"], conditional=True)
+            diff.set_new_noise_schedule(LINEAR_1000, "cpu")
+            diff.set_loss("cpu")
+            _, sr, hr = fields(name, b, cfg["image_channels"], cfg["image_height"], cfg["image_width"], seed)
+            noise = seeded_randn(name + ".noise", sr.shape, seed)
+            sap = diff.sqrt_alphas_cumprod_prev
+            u = np.random.RandomState(seed).uniform(sap[t - 1], sap[t], size=b)
+            level = torch.FloatTensor(u)
+            # inject t and the continuous level through numpy's global RNG entry points (resdiff_diffusion.py:128-135)
+            _ri, _un = np.random.randint, np.random.uniform
+            np.random.randint = lambda *a, **k: t
+            np.random.uniform = lambda *a, **k: u
+            try:
+                loss = diff.p_losses({"HR": hr, "SR": sr}, noise=noise)
+            finally:
+                np.random.randint, np.random.uniform = _ri, _un
+            out.update(hr=hr, sr=sr, noise=noise, level=level, loss=loss.reshape(1), wsum=_checksum(net))
+        elif kind == "simple_cnn":
+            net = fill_module(ref.SimpleCNN(scale_factor=4, channels=1).eval(), seed)
+            lr = seeded_randn(name + ".lr", (b, 1) + tuple(spec["lr_hw"]), seed)
+            out.update(lr=lr, out=net(lr), wsum=_checksum(net))
+        elif kind == "rrdb":
+            net = fill_module(ref.RRDBNet(1, 1, 64, 17, 32).eval(), seed)
+            lr = seeded_randn(name + ".lr", (b, 1) + tuple(spec["lr_hw"]), seed)
+            sr_img, feas = net(lr, True)
+            out.update(lr=lr, sr_img=sr_img, feas=torch.stack(feas, 0), wsum=_checksum(net))
+        elif kind == "srdiff_step":
+            cfg = spec["cfg"]
+            net = fill_module(_unet(ref, cfg, srdiff=True), seed)
+            rrdb = fill_module(ref.RRDBNet(1, 1, 64, 17, 32).eval(), seed + 1)
+            lr, sr, _ = fields(name, b, 1, cfg["image_height"], cfg["image_width"], seed)
+            _, feas = rrdb(lr, True)
+            x_t = seeded_randn(name + ".xt", sr.shape, seed)
+            level = torch.tensor(spec["level"], dtype=torch.float32).view(b, 1)
+            out.update(lr=lr, x_t=x_t, level=level, eps=net((feas, x_t), level), wsum=_checksum(net))
+        else:
+            raise KeyError(kind)
+    return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()}
+
+
+def schedule_fixture(ref):
+    """Reference schedule buffers for a handful of schedules (diffusion.py:49-96)."""
+    out = {}
+    dummy = torch.nn.Identity()
+    for tag, opt in {
+        "linear1000": LINEAR_1000, "linear50": short_schedule(50),
+        "quad20": {"schedule": "quad", "n_timestep": 20, "linear_start": 1e-4, "linear_end": 2e-2},
+        "cosine20": {"schedule": "cosine", "n_timestep": 20, "linear_start": 1e-4, "linear_end": 2e-2},
+        "warmup10_40": {"schedule": "warmup10", "n_timestep": 40, "linear_start": 1e-4, "linear_end": 2e-2},
+        "warmup50_40": {"schedule": "warmup50", "n_timestep": 40, "linear_start": 1e-4, "linear_end": 2e-2},
+        "const20": {"schedule": "const", "n_timestep": 20, "linear_start": 1e-4, "linear_end": 2e-2},
+        "jsd20": {"schedule": "jsd", "n_timestep": 20, "linear_start": 1e-4, "linear_end": 2e-2},
+    }.items():
+        diff = ref.ResDiffDiffusion(dummy, image_height=8, image_width=8, channels=1)
+        diff.set_new_noise_schedule(opt, "cpu")
+        for n in BUFFER_NAMES:
+            out["%s.%s" % (tag, n)] = getattr(diff, n).numpy()
+        out["%s.sqrt_alphas_cumprod_prev" % tag] = np.asarray(diff.sqrt_alphas_cumprod_prev)
+    return out
+
+
+def main(argv):
+    ref = ref_shims.import_reference()
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    names = argv or (list(CASES) + ["schedule", "manifest"])
+    for name in names:
+        if name == "schedule":
+            data = schedule_fixture(ref)
+        elif name == "manifest":
+            # state_dict key/shape manifests: the drop-in contract for checkpoints
+            from .cases import unet_cfg
+            data = {}
+            for tag, net in {"resdiff": _unet(ref, unet_cfg(128, 256)), "srdiff": _unet(ref, unet_cfg(128, 256, in_channel=1), srdiff=True),
+                             "rrdb": ref.RRDBNet(1, 1, 64, 17, 32), "simple_cnn": ref.SimpleCNN(4, 1)}.items():
+                sd = net.state_dict()
+                data[tag + ".keys"] = np.array(list(sd.keys()))
+                data[tag + ".shapes"] = np.array([",".join(map(str, v.shape)) for v in sd.values()])
+        else:
+            data = run_case(ref, name, CASES[name])
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, **data)
+        print("wrote", path, {k: v.shape for k, v in data.items() if hasattr(v, "shape")} if name not in ("schedule", "manifest") else "")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count() or 1)
+    main(sys.argv[1:])

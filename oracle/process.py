@@ -1,0 +1,91 @@
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+fp32 torch-CPU restatement of the diffusion process around the denoiser: the reverse chain and the training loss.
+Noise is always INJECTED (a pre-generated tensor), never drawn here, so that runs are comparable across devices.
+"""
+import numpy as np
+import torch
+
+from . import nets
+from .schedule import ddpm_tables
+
+
+def _tables(schedule_opt):
+    t32, sqrt_abar_prev = ddpm_tables(schedule_opt)
+    return {k: torch.from_numpy(v) for k, v in t32.items()}, sqrt_abar_prev
+
+
+def p_sample_step(denoise, tab, sqrt_abar_prev, x, t, z, clip=True):
+    """diffusion.py:144-192.  ``denoise(x_t, level)`` -> eps_hat.  z is the injected noise for this step (ignored
+    at t == 0, where the reference uses zeros)."""
+    b = x.shape[0]
+    level = torch.full((b, 1), float(np.float32(sqrt_abar_prev[t + 1])), dtype=torch.float32)  # :159-160
+    eps = denoise(x, level)
+    x0 = tab["sqrt_recip_alphas_cumprod"][t] * x - tab["sqrt_recipm1_alphas_cumprod"][t] * eps   # :124-125
+    if clip:
+        x0 = x0.clamp(-1.0, 1.0)                                                                 # :168-169
+    mean = tab["posterior_mean_coef1"][t] * x0 + tab["posterior_mean_coef2"][t] * x            # :139-140
+    logvar = tab["posterior_log_variance_clipped"][t]
+    noise = z if t > 0 else torch.zeros_like(x)                                                 # :191
+    return mean + noise * (0.5 * logvar).exp(), eps
+
+
+def resdiff_chain(sd, cfg, schedule_opt, cond, noise, return_eps=False):
+    """resdiff/resdiff_diffusion.py:58-108 (conditional branch).  ``noise``: [T+1,B,C,H,W]; noise[0] is the initial
+    image (the reference's ``torch.randn(shape)`` at :83), noise[1+k] the k-th ``randn_like`` (steps t=T-1..1)."""
+    tab, sap = _tables(schedule_opt)
+    T = int(schedule_opt["n_timestep"])
+    img = noise[0].clone()
+    eps_all = []
+
+    def denoise(x, level):
+        return nets.resdiff_unet(sd, torch.cat([cond, x], dim=1), level, cfg)
+
+    k = 1
+    for t in reversed(range(T)):
+        img, eps = p_sample_step(denoise, tab, sap, img, t, noise[k] if t > 0 else None)
+        k += 1
+        if return_eps:
+            eps_all.append(eps)
+    out = img + cond                                                                             # :94
+    return (out, eps_all) if return_eps else out
+
+
+def srdiff_chain(unet_sd, rrdb_sd, cfg, schedule_opt, lr, sr_up, noise, return_eps=False):
+    """srdiff/srdiff_diffusion.py:77-159: RRDB features once, then T steps of the SRDiff UNet."""
+    tab, sap = _tables(schedule_opt)
+    T = int(schedule_opt["n_timestep"])
+    _, feas = nets.rrdb_net(rrdb_sd, lr)
+    img = noise[0].clone()
+    eps_all = []
+
+    def denoise(x, level):
+        return nets.srdiff_unet(unet_sd, feas, x, level, cfg)
+
+    k = 1
+    for t in reversed(range(T)):
+        img, eps = p_sample_step(denoise, tab, sap, img, t, noise[k] if t > 0 else None)
+        k += 1
+        if return_eps:
+            eps_all.append(eps)
+    out = img + sr_up
+    return (out, eps_all) if return_eps else out
+
+
+def q_sample(x0, a, noise):
+    """diffusion.py:209-228: a*x0 + sqrt(1-a^2)*noise with a of shape (B,1,1,1)."""
+    return a * x0 + (1 - a ** 2).sqrt() * noise
+
+
+def resdiff_p_losses(sd, cfg, hr, sr, level, noise, loss_type="l1"):
+    """resdiff/resdiff_diffusion.py:111-152 with the random draws (t, continuous level, noise) injected:
+    ``level`` (B,) is the already-drawn continuous sqrt(alpha_bar).  Returns the SUM-reduced loss (diffusion.py:105-108)
+    and eps_hat.  Dropout is not modelled (tests use dropout = 0)."""
+    x0 = hr - sr
+    x_noisy = q_sample(x0, level.view(-1, 1, 1, 1), noise)
+    eps = nets.resdiff_unet(sd, torch.cat([sr, x_noisy], dim=1), level.view(-1, 1), cfg)
+    if loss_type == "l1":
+        loss = (noise - eps).abs().sum()
+    else:
+        loss = ((noise - eps) ** 2).sum()
+    return loss, eps

@@ -1,0 +1,106 @@
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Analysis shims that let the REAL reference (``/root/reference``, read-only, present only in the build container)
+be imported on a CPU-only machine without its missing third-party packages.  Used by ``make_golden.py`` and by the
+"oracle vs live reference" tests (which skip when ``/root/reference`` is absent, e.g. on the GPU box).
+
+1. ``pytorch_wavelets.DWTForward(J, wave='haar', mode=...)`` stand-in (package pinned at 1.3.0 in the reference's
+   requirements.txt:6, not installable here).  Haar analysis on 2x2 blocks ``a b / c d``:
+       LL = (a+b+c+d)/2, yh[:,:,0] = LH = (a+b-c-d)/2, yh[:,:,1] = HL = (a-b+c-d)/2, yh[:,:,2] = HH = (a-b-c+d)/2
+   (pywt 'haar': dec_lo = [1,1]/sqrt2, dec_hi = [-1,1]/sqrt2; pytorch_wavelets correlates with the reversed filters,
+   so high-pass = (even - odd)/sqrt2; rows then columns; band order LH, HL, HH).  This convention is restated from
+   the published package, NOT verified against it -- the one un-verifiable assumption of the oracle.
+   Known answer: [[1,2],[3,4]] -> LL 5, LH -2, HL -1, HH 0.
+2. ``matplotlib.pyplot`` stub (imported, unused, at resdiff/fd_info_spliter.py:105).
+3. CPU only: ``nn.Module.cuda()`` / ``.to('cuda')`` become no-ops (resdiff/unet.py:129,
+   guided_cross_attention.py:19).
+"""
+import os
+import sys
+import types
+
+import torch
+from torch import nn
+
+REFERENCE_ROOT = os.environ.get("WSR_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "models", "diffusion_models"))
+
+
+class _HaarDWTForward(nn.Module):
+    def __init__(self, J=1, wave="haar", mode="symmetric"):
+        super().__init__()
+        assert wave == "haar"
+        self.J = J
+
+    def forward(self, x):
+        highs = []
+        ll = x
+        for _ in range(self.J):
+            a = ll[:, :, 0::2, 0::2]
+            b = ll[:, :, 0::2, 1::2]
+            c = ll[:, :, 1::2, 0::2]
+            d = ll[:, :, 1::2, 1::2]
+            highs.append(torch.stack([(a + b - c - d) / 2, (a - b + c - d) / 2, (a - b - c + d) / 2], dim=2))
+            ll = (a + b + c + d) / 2
+        return ll, highs
+
+
+_installed = False
+
+
+def install():
+    """Idempotently install the shims and put the reference on sys.path."""
+    global _installed
+    if _installed:
+        return
+    if not reference_available():
+        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+    pw = types.ModuleType("pytorch_wavelets")
+    pw.DWTForward = _HaarDWTForward
+    sys.modules.setdefault("pytorch_wavelets", pw)
+    if "matplotlib" not in sys.modules:
+        try:
+            import matplotlib.pyplot  # noqa: F401
+        except Exception:
+            mpl = types.ModuleType("matplotlib")
+            plt = types.ModuleType("matplotlib.pyplot")
+            mpl.pyplot = plt
+            sys.modules["matplotlib"] = mpl
+            sys.modules["matplotlib.pyplot"] = plt
+    if not torch.cuda.is_available():
+        nn.Module.cuda = lambda self, device=None: self
+        _orig_to = nn.Module.to
+
+        def _to(self, *args, **kwargs):
+            args = tuple(a for a in args if not (isinstance(a, str) and a.startswith("cuda")))
+            if isinstance(kwargs.get("device"), str) and kwargs["device"].startswith("cuda"):
+                kwargs.pop("device")
+            if not args and not kwargs:
+                return self
+            return _orig_to(self, *args, **kwargs)
+
+        nn.Module.to = _to
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    _installed = True
+
+
+def import_reference():
+    """Returns a namespace with the reference classes on the hot path."""
+    install()
+    ns = types.SimpleNamespace()
+    from models.diffusion_models.resdiff.unet import UNet as ResDiffUNet
+    from models.diffusion_models.resdiff.resdiff_diffusion import ResDiffDiffusion
+    from models.diffusion_models.srdiff.unet import UNet as SRDiffUNet
+    from models.diffusion_models.srdiff.srdiff_diffusion import SRDiffDiffusion
+    from models.rrdb_encoder.RRDBNet import RRDBNet
+    from models.simple_cnn.Simple_CNN import SimpleCNN
+    from models.diffusion_models import networks
+    from models.diffusion_models.sheduler import make_beta_schedule
+    ns.ResDiffUNet, ns.ResDiffDiffusion = ResDiffUNet, ResDiffDiffusion
+    ns.SRDiffUNet, ns.SRDiffDiffusion = SRDiffUNet, SRDiffDiffusion
+    ns.RRDBNet, ns.SimpleCNN, ns.networks, ns.make_beta_schedule = RRDBNet, SimpleCNN, networks, make_beta_schedule
+    return ns

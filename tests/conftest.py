@@ -1,0 +1,46 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def load_golden(name):
+    import torch
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return {k: (torch.from_numpy(z[k]) if z[k].dtype.kind == "f" else z[k]) for k in z.files}
+
+
+def manifest(tag, cfg=None):
+    """(name, shape) list of the reference state_dict for model ``tag`` (tests/golden/manifest.npz, Cfg-A at 128x256);
+    the only shape that depends on the image size is fd_spliter.noise_func = Linear(inner, image_width)."""
+    m = load_golden("manifest")
+    keys = [str(k) for k in m[tag + ".keys"]]
+    shapes = [tuple(int(x) for x in str(s).split(",")) if str(s) else () for s in m[tag + ".shapes"]]
+    out = []
+    for k, s in zip(keys, shapes):
+        if cfg is not None and k.startswith("fd_spliter.noise_func."):
+            s = (cfg["image_width"],) + tuple(s[1:])
+        out.append((k, s))
+    return out
+
+
+def rel_l2(a, b):
+    a = a.double().flatten()
+    b = b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return load_golden

@@ -1,0 +1,103 @@
+"""CPU tests: the oracle (oracle/) against the fixtures produced by the REAL reference (oracle/make_golden.py).
+This is what pins the oracle; the CUDA parity tests (-m gpu) then compare against the same fixtures and the oracle.
+Tolerance: fp32 restatement of fp32 code on the same CPU -> rel-L2 <= 1e-5 (reduction order differs slightly)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, manifest, rel_l2
+from oracle import nets, process, schedule
+from oracle.cases import CASES, LINEAR_1000, short_schedule
+from oracle.weights import seeded_state_dict
+
+TOL = 1e-5
+
+
+def _sd(tag, seed, cfg=None):
+    return seeded_state_dict(manifest(tag, cfg), seed)
+
+
+def _wsum(sd):
+    return np.array([float(sum(v.double().sum() for v in sd.values())), float(sum(v.double().abs().sum() for v in sd.values()))])
+
+
+def test_schedule_tables_match_reference():
+    g = load_golden("schedule")
+    opts = {
+        "linear1000": LINEAR_1000, "linear50": short_schedule(50),
+        "quad20": {"schedule": "quad", "n_timestep": 20, "linear_start": 1e-4, "linear_end": 2e-2},
+        "cosine20": {"schedule": "cosine", "n_timestep": 20, "linear_start": 1e-4, "linear_end": 2e-2},
+        "warmup10_40": {"schedule": "warmup10", "n_timestep": 40, "linear_start": 1e-4, "linear_end": 2e-2},
+        "warmup50_40": {"schedule": "warmup50", "n_timestep": 40, "linear_start": 1e-4, "linear_end": 2e-2},
+        "const20": {"schedule": "const", "n_timestep": 20, "linear_start": 1e-4, "linear_end": 2e-2},
+        "jsd20": {"schedule": "jsd", "n_timestep": 20, "linear_start": 1e-4, "linear_end": 2e-2},
+    }
+    for tag, opt in opts.items():
+        with np.errstate(divide="ignore", invalid="ignore"):
+            tabs, sap = schedule.ddpm_tables(opt)
+        for n in schedule.BUFFER_NAMES:
+            ref = g["%s.%s" % (tag, n)].numpy()
+            np.testing.assert_array_equal(np.isfinite(tabs[n]), np.isfinite(ref), err_msg=tag + n)
+            fin = np.isfinite(ref)
+            np.testing.assert_allclose(tabs[n][fin], ref[fin], rtol=2e-6, atol=1e-30, err_msg=tag + "." + n)
+        np.testing.assert_allclose(sap, g["%s.sqrt_alphas_cumprod_prev" % tag].numpy(), rtol=1e-12)
+    # known answers quoted in SURVEY.md 8(a.1)
+    tabs, sap = schedule.ddpm_tables(LINEAR_1000)
+    assert abs(sap[1000] - 0.08138) < 1e-4
+    assert abs(tabs["posterior_log_variance_clipped"][0] + 46.05) < 1e-2
+    assert tabs["posterior_mean_coef1"][0] == 1.0 and tabs["posterior_mean_coef2"][0] == 0.0
+
+
+def test_haar_known_answer():
+    x = torch.tensor([[1.0, 2.0], [3.0, 4.0]]).view(1, 1, 2, 2)
+    assert float(nets.haar_detail_sums(x, 1)[0]) == pytest.approx(-2 - 1 + 0)
+
+
+@pytest.mark.parametrize("name", ["resdiff_step_small", "resdiff_step_full_b1", "resdiff_step_full_b2"])
+def test_resdiff_step(name):
+    g, spec = load_golden(name), CASES[name]
+    sd = _sd("resdiff", spec["seed"], spec["cfg"])
+    np.testing.assert_allclose(_wsum(sd), g["wsum"].numpy(), rtol=1e-9)
+    with torch.no_grad():
+        eps = nets.resdiff_unet(sd, torch.cat([g["cond"], g["x_t"]], 1), g["level"], spec["cfg"])
+    assert rel_l2(eps, g["eps"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["resdiff_chain_small", "resdiff_chain_full_b1"])
+def test_resdiff_chain(name):
+    g, spec = load_golden(name), CASES[name]
+    sd = _sd("resdiff", spec["seed"], spec["cfg"])
+    with torch.no_grad():
+        out = process.resdiff_chain(sd, spec["cfg"], short_schedule(spec["T"]), g["cond"], g["noise"])
+    assert rel_l2(out, g["sr_out"]) < TOL
+
+
+def test_resdiff_loss():
+    g, spec = load_golden("resdiff_loss_small"), CASES["resdiff_loss_small"]
+    sd = _sd("resdiff", spec["seed"], spec["cfg"])
+    with torch.no_grad():
+        loss, _ = process.resdiff_p_losses(sd, spec["cfg"], g["hr"], g["sr"], g["level"], g["noise"])
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < TOL
+
+
+def test_simple_cnn():
+    g, spec = load_golden("simple_cnn"), CASES["simple_cnn"]
+    with torch.no_grad():
+        out = nets.simple_cnn(_sd("simple_cnn", spec["seed"]), g["lr"])
+    assert rel_l2(out, g["out"]) < TOL
+
+
+def test_rrdb():
+    g, spec = load_golden("rrdb_small"), CASES["rrdb_small"]
+    with torch.no_grad():
+        sr_img, feas = nets.rrdb_net(_sd("rrdb", spec["seed"]), g["lr"])
+    assert rel_l2(sr_img, g["sr_img"]) < TOL
+    assert rel_l2(torch.stack(feas, 0), g["feas"]) < TOL
+
+
+def test_srdiff_step():
+    g, spec = load_golden("srdiff_step_small"), CASES["srdiff_step_small"]
+    with torch.no_grad():
+        _, feas = nets.rrdb_net(_sd("rrdb", spec["seed"] + 1), g["lr"])
+        eps = nets.srdiff_unet(_sd("srdiff", spec["seed"], spec["cfg"]), feas, g["x_t"], g["level"], spec["cfg"])
+    assert rel_l2(eps, g["eps"]) < TOL
