@@ -1,0 +1,204 @@
+/*
+ * wsr.h -- C ABI of the B200-native diffusion super-resolution hot path (libwsr.so).
+ *
+ * The reference (jellikus/Super-Resolution-Enhancement-of-Weather-Data-Using-Diffusion-Models) is pure Python/PyTorch
+ * and has NO plugin / FFI / operator ABI of its own: its seam is the Python class registry
+ * models/diffusion_models/networks.py:116-134.  This header is therefore the boundary a maintainer of the
+ * reference would bind with ctypes; every entry point names the reference code whose arithmetic
+ * it replaces.  All pointers are DEVICE pointers unless stated otherwise, all sizes are explicit, outputs and
+ * workspaces are caller-owned, `stream` is a cudaStream_t passed as void*.  No torch types, no hidden allocation,
+ * no exceptions.  Every function returns 0 on success and a negative WSR_E_* code on failure;
+ * wsr_last_error() returns a thread-local description of the last failure.
+ *
+ * Activations are NHWC ("pixels x channels") with an explicit channel pitch `ld` (elements between consecutive
+ * pixels), so a tensor may be a channel slice of a wider buffer (skip-concat without copies, RRDB dense blocks).
+ * Conv weights are packed [tap][Cout][Cin] (tap = ky*KW + kx) in the activation dtype.
+ */
+#ifndef WSR_H_
+#define WSR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WSR_OK 0
+#define WSR_E_INVALID (-1)     /* invalid argument                      */
+#define WSR_E_UNSUPPORTED (-2) /* shape / dtype not supported by kernel */
+#define WSR_E_CUDA (-3)        /* CUDA runtime / driver error           */
+
+#define WSR_F32 0
+#define WSR_BF16 1
+
+#define WSR_ACT_NONE 0
+#define WSR_ACT_LRELU02 1 /* LeakyReLU(0.2), rrdb_encoder/RRDBNet.py:31,103 */
+#define WSR_ACT_RELU 2    /* simple_cnn/Simple_CNN.py:17-19                 */
+#define WSR_ACT_SWISH 3   /* nn_modules/functional_layers.py:44-47          */
+#define WSR_ACT_MISH 4    /* nn_modules/functional_layers.py:49-52          */
+
+const char* wsr_last_error(void);
+int wsr_version(void);
+/* 1 when the current device is compute capability 10.x (tcgen05 path usable). */
+int wsr_device_is_sm100(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Convolution.  Replaces nn.Conv2d call sites: nn_modules/resnet.py:24,51,78-79; functional_layers.py:64,79;
+ * resdiff/unet.py:68; guided_cross_attention.py:20-22; fd_info_spliter.py:35; RRDBNet.py:27-36,93-97;
+ * Simple_CNN.py:16-20.
+ *
+ *   y[n,oh,ow,co] = ( act( sum_{tap,ci} w[tap][co][ci] * X[n, ih, iw, ci]
+ *                          + sum_{ci2} w2[co][ci2] * x2[n,oh,ow,ci2]          (optional fused 1x1 "res_conv")
+ *                          + bias[co] + rowvec[n*rowvec_ld + co] ) ) * out_scale
+ *                   + res[n,oh,ow,co] * res_scale + res2[n,oh,ow,co] * res2_scale
+ *
+ * X is x, or its nearest-neighbour x2 upsampling when `upsample` != 0 (functional_layers.py:62-67); zero padding
+ * (ksize-1)/2; stride 1 or 2.  H, W are the dimensions of x; the output is (H*up/stride, W*up/stride).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;  int x_dtype;  int N, H, W, Cin;  int x_ld;
+  const void* w;                                   /* [ksize*ksize][w_rows][Cin], dtype = x_dtype          */
+  int w_rows;                                      /* rows per tap in w / w2 (>= Cout, zero padded); 0 = Cout */
+  int ksize, stride, upsample;
+  int Cout;
+  const void* x2; int Cin2; int x2_ld;             /* optional second K segment (1x1), dtype = x_dtype     */
+  const void* w2;                                  /* [Cout][Cin2]                                         */
+  const float* bias;                               /* [Cout] or NULL                                       */
+  const float* rowvec; int rowvec_ld;              /* [N][rowvec_ld] or NULL (time embedding)              */
+  int act;
+  float out_scale;
+  const void* res;  int res_dtype;  int res_ld;  float res_scale;
+  const void* res2; int res2_dtype; int res2_ld; float res2_scale;
+  void* y; int y_dtype; int y_ld;
+} WsrConvDesc;
+
+/* fp32-accumulate SIMT implicit GEMM; any dtype, any channel count.  This is the "fp32 check mode" kernel. */
+int wsr_conv_simt(const WsrConvDesc* d, void* stream);
+/* tcgen05/TMEM implicit GEMM fed by TMA; bf16 operands, fp32 accumulation.  Requires x_dtype = BF16, Cin % 64 == 0,
+ * Cin2 % 64 == 0, Cout % 16 == 0, W a power of two (>= 2), pitches % 8 == 0, 16-byte aligned bases. */
+int wsr_conv_tc(const WsrConvDesc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Batched GEMM  D[b][m][n] = alpha * sum_k A[b][m][k] * B[b][n][k] (+ bias[n]) (+ res[b][m][n]),
+ * used for the attention products (nn_modules/resnet.py:90-97, guided_cross_attention.py:34-41) and the linear
+ * layers.  Element strides are explicit; the tcgen05 version requires unit k-stride for both operands.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* a; int a_dtype; int64_t a_sb, a_sm, a_sk;
+  const void* b; int b_dtype; int64_t b_sb, b_sn, b_sk;
+  void* d; int d_dtype; int64_t d_sb, d_sm, d_sn;
+  const void* res; int res_dtype; int64_t res_sb, res_sm, res_sn;
+  const float* bias;
+  int batch, M, N, K;
+  float alpha;
+} WsrGemmDesc;
+
+int wsr_gemm_simt(const WsrGemmDesc* d, void* stream);
+int wsr_gemm_tc(const WsrGemmDesc* d, void* stream);
+
+/* ConvTranspose2d(k=8, s=4, p=2) of srdiff/unet.py:43-45,118.  x NHWC (N,H,W,Cin); w packed [ky*8+kx][Cout][Cin];
+ * y NHWC (N,4H,4W,Cout). */
+int wsr_conv_transpose_k8s4(const void* x, int x_dtype, int N, int H, int W, int Cin, int x_ld, const void* w,
+                            const float* bias, int Cout, void* y, int y_dtype, int y_ld, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * GroupNorm (eps, affine) + activation.  Replaces nn.GroupNorm + Swish of nn_modules/resnet.py:21-22,77 and
+ * guided_cross_attention.py:19.  Two kernels: per-(image, channel) sums, then normalise (+act).
+ * stats: double [N][C][2] = (sum, sum of squares); wsr_gn_stats ACCUMULATES (zero it first with wsr_fill_zero).
+ * ------------------------------------------------------------------------------------------------------------- */
+int wsr_gn_stats(const void* x, int x_dtype, int N, int HW, int C, int x_ld, double* stats, void* stream);
+int wsr_gn_apply(const void* x, int x_dtype, int N, int HW, int C, int x_ld, const double* stats,
+                 const float* gamma, const float* beta, int groups, float eps, int act, void* y, int y_dtype,
+                 int y_ld, void* stream);
+int wsr_fill_zero(void* p, int64_t bytes, void* stream);
+
+/* Row softmax: p[r][:] = softmax(scale * s[r][:]) over `cols`, rows = batch*Nq (resnet.py:92-95). */
+int wsr_softmax_rows(const void* s, int s_dtype, int64_t rows, int cols, int64_t s_ld, float scale, void* p,
+                     int p_dtype, int64_t p_ld, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Layout / packing helpers.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* fp32 NCHW -> NHWC slice (dst pitch ld, already offset to the first channel). */
+int wsr_nchw_to_nhwc(const float* src, int N, int C, int H, int W, void* dst, int dst_dtype, int dst_ld, void* stream);
+int wsr_nhwc_to_nchw(const void* src, int src_dtype, int src_ld, int N, int C, int H, int W, float* dst, void* stream);
+/* OIHW fp32 -> [tap][Cout_pad][Cin_pad] (zero padded). */
+int wsr_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int KH, int KW, void* dst, int dst_dtype,
+                         int Cout_pad, int Cin_pad, void* stream);
+/* ConvTranspose2d weight (Cin, Cout, KH, KW) fp32 -> [tap][Cout][Cin]. */
+int wsr_pack_convT_weight(const float* w_iohw, int Cin, int Cout, int KH, int KW, void* dst, int dst_dtype, void* stream);
+/* dst[i] = (T) src[i] */
+int wsr_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* nearest x2 upsample of an NHWC tensor (functional_layers.py:62). */
+int wsr_upsample2x(const void* x, int dtype, int N, int H, int W, int C, int x_ld, void* y, int y_ld, void* stream);
+/* y[...] = a*x + b*z elementwise on NHWC slices (C channels), used for "x + cond" (srdiff/unet.py:126-127). */
+int wsr_axpby(const void* x, int x_dtype, int x_ld, float a, const void* z, int z_dtype, int z_ld, float b, void* y,
+              int y_dtype, int y_ld, int64_t pixels, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Noise-level embedding.  Replaces PositionalEncoding + noise_level_mlp (functional_layers.py:33-41,
+ * resdiff/unet.py:46-53,135; Mish variant srdiff/unet.py:49-54) and the 27 FeatureWiseAffine linears
+ * (nn_modules/resnet.py:145-157) plus fd_spliter.noise_func (fd_info_spliter.py:24,43).
+ *   level [R] -> temb [R][inner] -> proj [R][P] = temb @ Wcat^T + bcat       (Wcat: [P][inner], all linears stacked)
+ * R is the number of rows: the batch in training, or T (all time steps, precomputed once) in sampling.
+ * ------------------------------------------------------------------------------------------------------------- */
+int wsr_noise_embed(const float* level, int R, int inner, const float* w1, const float* b1, const float* w2,
+                    const float* b2, int act, float* temb, void* stream);
+int wsr_linear_rows(const float* x, int R, int K, const float* w, const float* bias, int P, float* y, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * FD_Info_Spliter (resdiff/fd_info_spliter.py:37-117) and the Haar queries (resdiff/unet.py:124-132).
+ * ------------------------------------------------------------------------------------------------------------- */
+/* Condition-only branch, hoisted out of the T-step loop.  cond: fp32 NCHW (B,C,H,W).  Reproduces the 4-D fftn over
+ * (B,C,H,W), the ResSE-derived sigma, the Gaussian high-pass on the unshifted spectrum, x_lf and x_hf.
+ * Outputs lf, hf: fp32 NCHW (B,C,H,W).  work: caller scratch of wsr_fd_precompute_workspace_bytes(). */
+int64_t wsr_fd_precompute_workspace_bytes(int B, int C, int H, int W);
+int wsr_fd_precompute(const float* cond, int B, int C, int H, int W, const float* sigma_fc0, const float* sigma_fc2,
+                      const float* hf_fc0, const float* hf_fc2, const float* ct_w, const float* ct_b, int out_ch,
+                      float* lf, float* hf, void* work, void* stream);
+/* Per-step gate (fd_info_spliter.py:43-47): ne = noise_func(t_emb) is passed in as ne_rows[r][W] (a slice of the
+ * wsr_linear_rows output, pitch ne_ld); gate[b][c][w] = ne[w] * (1 + sigmoid(fc2 relu(fc0 mean_w ne))[c]).
+ * row_index: device int* giving the row r of ne_rows to use for every b (sampling: the current step), or NULL for r=b. */
+int wsr_fd_gate(const float* ne_rows, int ne_ld, const int* row_index, int B, int C, int W, const float* fc0,
+                const float* fc2, int hidden, float* gate, void* stream);
+/* Stem input assembly: writes NHWC channels [x, cond, x*gate, lf, hf] (5*C, fd_info_spliter.py:117), zero-pads up
+ * to Cpad channels.  x, cond, lf, hf: fp32 NCHW. */
+int wsr_stem_assemble(const float* x, const float* cond, const float* gate, const float* lf, const float* hf, int B,
+                      int C, int H, int W, void* y, int y_dtype, int Cpad, void* stream);
+/* Haar detail-band sums for `levels` levels: out[j] fp32 NCHW (B,C,H>>(j+1),W>>(j+1)) packed back to back in `out`;
+ * ll_work: scratch of B*C*H*W/4*... floats (>= B*C*H*W/2 floats). */
+int wsr_haar_detail_sums(const float* img, int B, int C, int H, int W, int levels, float* out, float* ll_work, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * DDPM process kernels (models/diffusion_models/diffusion.py).
+ * ------------------------------------------------------------------------------------------------------------- */
+/* Fused reverse step (diffusion.py:124-125,139-141,168-169,191-192):
+ *   x0 = clamp(c_recip[t]*x - c_recipm1[t]*eps, -1, 1); mean = coef1[t]*x0 + coef2[t]*x;
+ *   x_out = mean + (t>0 ? z * exp(0.5*logvar[t]) : 0)
+ * tables: float [5][T] = (sqrt_recip, sqrt_recipm1, coef1, coef2, logvar).  t_dev: device int* (current step; the
+ * kernel does NOT modify it).  z: injected noise (fp32, same shape) or NULL to draw it in-kernel (Philox4x32-10,
+ * key = seed, counter = (t, element)).  With z != NULL the step's noise is read at z + (T - t) * z_step_stride, i.e.
+ * z may be the whole injected chain [T+1][n] of the parity tests (stride n) or a single tensor (stride 0).
+ * eps may be fp32 or bf16 (NHWC with C==1 equals NCHW).  x_out may alias x. */
+int wsr_sampler_step(const float* x, const void* eps, int eps_dtype, const float* z, int64_t z_step_stride,
+                     uint64_t seed, const float* tables, int T, const int* t_dev, int clip, float* x_out, int64_t n,
+                     void* stream);
+/* out[b][:] = table[r][:] for b < B, r = *row_index (one row of the per-time-step projection table broadcast to the
+ * batch; lets a captured CUDA graph follow the device-side step counter). */
+int wsr_broadcast_row(const float* table, int P, const int* row_index, int B, float* out, void* stream);
+/* *t_dev += delta (single thread) -- keeps the step counter on the device so a CUDA graph can be replayed. */
+int wsr_step_counter_add(int* t_dev, int delta, void* stream);
+/* Standard normal fill with the same Philox stream layout as wsr_sampler_step (counter word = `tag`). */
+int wsr_randn(float* out, int64_t n, uint64_t seed, uint32_t tag, void* stream);
+/* q_sample (diffusion.py:209-228): x_noisy = a[b]*(hr-sr) + sqrt(1-a[b]^2)*noise, per-sample a; fp32 NCHW. */
+int wsr_q_sample(const float* hr, const float* sr, const float* noise, const float* a, int B, int64_t per_sample,
+                 float* x_noisy, void* stream);
+/* Sum-reduced L1 / L2 loss between noise and eps_hat (diffusion.py:105-108): *loss += sum |noise-eps|^p.
+ * Also writes dloss/deps * scale into grad (or NULL): -sign(noise-eps)*scale (L1), -2(noise-eps)*scale (L2). */
+int wsr_noise_loss(const float* noise, const float* eps, int64_t n, int l2, double* loss, float* grad, float scale,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WSR_H_ */

@@ -1,0 +1,73 @@
+// common.cuh -- shared helpers for libwsr (error reporting, dtype access, launch checks).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/wsr.h"
+
+namespace wsr {
+
+void set_error(const char* fmt, ...);
+
+#define WSR_REQUIRE(cond, code, ...)                \
+  do {                                              \
+    if (!(cond)) {                                  \
+      ::wsr::set_error(__VA_ARGS__);                \
+      return (code);                                \
+    }                                               \
+  } while (0)
+
+#define WSR_CUDA_OK(expr)                                                                       \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      ::wsr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return WSR_E_CUDA;                                                                        \
+    }                                                                                           \
+  } while (0)
+
+#define WSR_LAUNCH_OK() WSR_CUDA_OK(cudaGetLastError())
+
+static inline bool valid_dtype(int dt) { return dt == WSR_F32 || dt == WSR_BF16; }
+static inline int dtype_size(int dt) { return dt == WSR_BF16 ? 2 : 4; }
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// runtime-dtype scalar access (used in epilogues where the dtype is a kernel argument)
+__device__ __forceinline__ float ld_dt(const void* p, int64_t i, int dt) {
+  return dt == WSR_BF16 ? __bfloat162float(((const __nv_bfloat16*)p)[i]) : ((const float*)p)[i];
+}
+__device__ __forceinline__ void st_dt(void* p, int64_t i, int dt, float v) {
+  if (dt == WSR_BF16) ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
+  else ((float*)p)[i] = v;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case WSR_ACT_LRELU02: return v > 0.f ? v : 0.2f * v;
+    case WSR_ACT_RELU: return v > 0.f ? v : 0.f;
+    case WSR_ACT_SWISH: return v / (1.f + __expf(-v));
+    case WSR_ACT_MISH: {
+      float sp = v > 20.f ? v : log1pf(__expf(v));
+      return v * tanhf(sp);
+    }
+    default: return v;
+  }
+}
+
+// Dispatch a templated launcher on a runtime dtype.
+#define WSR_DISPATCH_DTYPE(dt, T, ...)                 \
+  do {                                                 \
+    if ((dt) == WSR_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else { using T = float; __VA_ARGS__; }             \
+  } while (0)
+
+}  // namespace wsr

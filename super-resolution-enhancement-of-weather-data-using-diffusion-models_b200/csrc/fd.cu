@@ -1,0 +1,336 @@
+// fd.cu -- FD_Info_Spliter (resdiff/fd_info_spliter.py:37-117) and the Haar query images (resdiff/unet.py:124-132).
+//
+// The condition-only branch (4-D FFT, sigma, Gaussian high-pass, LF / HF feature maps) depends only on the condition,
+// so it is computed ONCE per batch here instead of once per reverse step.  The transform is a direct
+// separable DFT in double precision (one pass per axis, 2*(B+C+H+W) complex MACs per element): the whole batch costs a
+// few milliseconds once per 1000 steps, and it reproduces the reference's transform over ALL FOUR axes (B, C, H, W).
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace wsr {
+
+// twiddle table tw[j] = exp(-2*pi*i*j/L), double
+__global__ void twiddle_kernel(double2* tw, int L) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= L) return;
+  double s, c;
+  sincospi(-2.0 * (double)j / (double)L, &s, &c);
+  tw[j] = make_double2(c, s);
+}
+
+// One DFT pass along an axis of length L and element stride S:  out[o, k, i] = scale * sum_n in[o, n, i] * tw[(k*n)%L]^(sign)
+// index space: total = outer * L * S, element e -> (o, k, i)
+__global__ void dft_axis_kernel(const float2* __restrict__ in, float2* __restrict__ out, const double2* __restrict__ tw,
+                                int L, int64_t S, int64_t total, int inverse, double scale) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  int64_t i = e % S;
+  int64_t r = e / S;
+  int k = (int)(r % L);
+  int64_t o = r / L;
+  const float2* src = in + o * L * S + i;
+  double re = 0.0, im = 0.0;
+  int idx = 0;
+  for (int n = 0; n < L; ++n) {
+    double2 w = tw[idx];
+    if (inverse) w.y = -w.y;
+    float2 v = src[(int64_t)n * S];
+    re += (double)v.x * w.x - (double)v.y * w.y;
+    im += (double)v.x * w.y + (double)v.y * w.x;
+    idx += k;
+    if (idx >= L) idx -= L;
+  }
+  out[e] = make_float2((float)(re * scale), (float)(im * scale));
+}
+
+__global__ void real_to_complex_kernel(const float* __restrict__ x, float2* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_float2(x[i], 0.f);
+}
+
+// per (b, c): mean of Re and Im over HW, optionally weighted by the high-pass H_b -> means[(b*2C) + c], [(b*2C) + C + c]
+__global__ void __launch_bounds__(256) spec_mean_kernel(const float2* __restrict__ spec, int C, int H, int W,
+                                                        const float* __restrict__ sigma, double* __restrict__ means) {
+  __shared__ double sre[256], sim[256];
+  const int bc = blockIdx.x;
+  const int b = bc / C, c = bc % C;
+  const float2* p = spec + (int64_t)bc * H * W;
+  double re = 0.0, im = 0.0;
+  float inv2s2 = 0.f;
+  if (sigma) { float s = sigma[b]; inv2s2 = 1.f / (2.f * s * s); }
+  for (int i = threadIdx.x; i < H * W; i += 256) {
+    float2 v = p[i];
+    float hp = 1.f;
+    if (sigma) {
+      float u = (float)(i / W) - 0.5f * H, vv = (float)(i % W) - 0.5f * W;
+      hp = 1.f - expf(-(u * u + vv * vv) * inv2s2);
+    }
+    re += (double)(v.x * hp);
+    im += (double)(v.y * hp);
+  }
+  sre[threadIdx.x] = re; sim[threadIdx.x] = im;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { sre[threadIdx.x] += sre[threadIdx.x + s]; sim[threadIdx.x] += sim[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    means[(int64_t)b * 2 * C + c] = sre[0] / (double)(H * W);
+    means[(int64_t)b * 2 * C + C + c] = sim[0] / (double)(H * W);
+  }
+}
+
+// ResSE squeeze-excite vector: se[b][ch] = sigmoid(fc2 * relu(fc0 * mean[b]))  (fd_info_spliter.py:135-146), ch < C2
+__device__ void res_se_vec(const double* mean, int C2, const float* fc0, const float* fc2, int hidden, float* se) {
+  float hid[64];
+  for (int h = 0; h < hidden; ++h) {
+    float a = 0.f;
+    for (int c = 0; c < C2; ++c) a = fmaf(fc0[h * C2 + c], (float)mean[c], a);
+    hid[h] = a > 0.f ? a : 0.f;
+  }
+  for (int c = 0; c < C2; ++c) {
+    float a = 0.f;
+    for (int h = 0; h < hidden; ++h) a = fmaf(fc2[c * hidden + h], hid[h], a);
+    se[c] = 1.f / (1.f + expf(-a));
+  }
+}
+
+// sigma[b] = min(| mean_ch( mean_hw(x_fd) * (1 + se) ) | + l/2, l - 10)       (fd_info_spliter.py:70-73)
+__global__ void fd_sigma_kernel(const double* __restrict__ means, int B, int C, const float* fc0, const float* fc2,
+                                int H, int W, float* __restrict__ sigma) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int C2 = 2 * C, hidden = C2 / 2;
+  float se[64];
+  res_se_vec(means + (int64_t)b * C2, C2, fc0, fc2, hidden, se);
+  float acc = 0.f;
+  for (int c = 0; c < C2; ++c) acc += (float)means[(int64_t)b * C2 + c] * (1.f + se[c]);
+  float l = (float)min(H, W);
+  sigma[b] = fminf(fabsf(acc / (float)C2) + 0.5f * l, l - 10.f);
+}
+
+__global__ void fd_se2_kernel(const double* __restrict__ means, int B, int C, const float* fc0, const float* fc2,
+                              float* __restrict__ se2) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int C2 = 2 * C;
+  float se[64];
+  res_se_vec(means + (int64_t)b * C2, C2, fc0, fc2, C2 / 2, se);
+  for (int c = 0; c < C2; ++c) se2[(int64_t)b * C2 + c] = se[c];
+}
+
+// apply the high-pass in place and emit lf = cond * (ct_b + sum_ch ct_w[o][ch] * F_ch * (1 + se2[ch]))
+__global__ void fd_filter_lf_kernel(float2* __restrict__ spec, const float* __restrict__ cond, const float* __restrict__ sigma,
+                                    const float* __restrict__ se2, const float* __restrict__ ct_w, const float* __restrict__ ct_b,
+                                    int B, int C, int H, int W, float* __restrict__ lf) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*H*W
+  int64_t HW = (int64_t)H * W;
+  if (i >= (int64_t)B * HW) return;
+  int b = (int)(i / HW);
+  int p = (int)(i - (int64_t)b * HW);
+  float s = sigma[b];
+  float u = (float)(p / W) - 0.5f * H, v = (float)(p % W) - 0.5f * W;
+  float hp = 1.f - expf(-(u * u + v * v) / (2.f * s * s));
+  float fre[32], fim[32];
+  for (int c = 0; c < C; ++c) {
+    float2 q = spec[((int64_t)b * C + c) * HW + p];
+    q.x *= hp; q.y *= hp;
+    spec[((int64_t)b * C + c) * HW + p] = q;
+    fre[c] = q.x * (1.f + se2[(int64_t)b * 2 * C + c]);
+    fim[c] = q.y * (1.f + se2[(int64_t)b * 2 * C + C + c]);
+  }
+  for (int o = 0; o < C; ++o) {
+    float a = ct_b[o];
+    for (int c = 0; c < C; ++c) a = fmaf(ct_w[o * 2 * C + c], fre[c], a);
+    for (int c = 0; c < C; ++c) a = fmaf(ct_w[o * 2 * C + C + c], fim[c], a);
+    lf[((int64_t)b * C + o) * HW + p] = cond[((int64_t)b * C + o) * HW + p] * a;
+  }
+}
+
+__global__ void complex_abs_kernel(const float2* __restrict__ in, float* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { float2 v = in[i]; out[i] = sqrtf(v.x * v.x + v.y * v.y); }
+}
+
+// per-step gate
+__global__ void fd_gate_kernel(const float* __restrict__ ne_rows, int ne_ld, const int* __restrict__ row_index, int C, int W,
+                               const float* __restrict__ fc0, const float* __restrict__ fc2, int hidden, float* __restrict__ gate) {
+  __shared__ float red[8];
+  __shared__ float se[32];
+  const int b = blockIdx.x;
+  const int r = row_index ? *row_index : b;
+  const float* ne = ne_rows + (int64_t)r * ne_ld;
+  float acc = 0.f;
+  for (int w = threadIdx.x; w < W; w += blockDim.x) acc += ne[w];
+  // block reduce (blockDim = 256)
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    for (int i = 0; i < 8; ++i) m += red[i];
+    m /= (float)W;
+    float hid[32];
+    for (int h = 0; h < hidden; ++h) {
+      float a = 0.f;
+      for (int c = 0; c < C; ++c) a = fmaf(fc0[h * C + c], m, a);
+      hid[h] = a > 0.f ? a : 0.f;
+    }
+    for (int c = 0; c < C; ++c) {
+      float a = 0.f;
+      for (int h = 0; h < hidden; ++h) a = fmaf(fc2[c * hidden + h], hid[h], a);
+      se[c] = 1.f / (1.f + expf(-a));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
+    int c = i / W, w = i - c * W;
+    gate[((int64_t)b * C + c) * W + w] = ne[w] * (1.f + se[c]);
+  }
+}
+
+template <typename T>
+__global__ void stem_assemble_kernel(const float* __restrict__ x, const float* __restrict__ cond, const float* __restrict__ gate,
+                                     const float* __restrict__ lf, const float* __restrict__ hf, int C, int H, int W,
+                                     T* __restrict__ y, int Cpad, int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*H*W*Cpad, channel fastest
+  if (i >= total) return;
+  int ch = (int)(i % Cpad);
+  int64_t pix = i / Cpad;
+  int64_t HW = (int64_t)H * W;
+  int64_t b = pix / HW;
+  int64_t p = pix - b * HW;
+  float v = 0.f;
+  if (ch < 5 * C) {
+    int k = ch / C, c = ch - k * C;
+    int64_t src = (b * C + c) * HW + p;
+    switch (k) {
+      case 0: v = x[src]; break;
+      case 1: v = cond[src]; break;
+      case 2: v = x[src] * gate[(b * C + c) * W + (p % W)]; break;
+      case 3: v = lf[src]; break;
+      default: v = hf[src]; break;
+    }
+  }
+  stf<T>(y + i, v);
+}
+
+__global__ void haar_level_kernel(const float* __restrict__ ll, int h, int w, float* __restrict__ detail, float* __restrict__ ll_next, int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over BC * h/2 * w/2
+  if (i >= total) return;
+  int w2 = w / 2, h2 = h / 2;
+  int x = (int)(i % w2);
+  int64_t r = i / w2;
+  int y = (int)(r % h2);
+  int64_t bc = r / h2;
+  const float* p = ll + (bc * h + 2 * y) * w + 2 * x;
+  float a = p[0], b = p[1], c = p[w], d = p[w + 1];
+  detail[i] = (3.f * a - b - c - d) * 0.5f;
+  ll_next[i] = (a + b + c + d) * 0.5f;
+}
+
+}  // namespace wsr
+
+using namespace wsr;
+static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+static inline int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
+
+extern "C" int64_t wsr_fd_precompute_workspace_bytes(int B, int C, int H, int W) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return -1;
+  int64_t n = (int64_t)B * C * H * W;
+  int64_t maxL = B > C ? B : C; if (H > maxL) maxL = H; if (W > maxL) maxL = W;
+  return 2 * align256(n * 8) + align256(maxL * 16) + align256((int64_t)B * 2 * C * 8) + 2 * align256((int64_t)B * 2 * C * 4) + 1024;
+}
+
+extern "C" int wsr_fd_precompute(const float* cond, int B, int C, int H, int W, const float* sigma_fc0,
+                                 const float* sigma_fc2, const float* hf_fc0, const float* hf_fc2, const float* ct_w,
+                                 const float* ct_b, int out_ch, float* lf, float* hf, void* work, void* stream) {
+  WSR_REQUIRE(cond && sigma_fc0 && sigma_fc2 && hf_fc0 && hf_fc2 && ct_w && ct_b && lf && hf && work, WSR_E_INVALID, "fd_precompute: null pointer");
+  WSR_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, WSR_E_INVALID, "fd_precompute: bad shape");
+  WSR_REQUIRE(out_ch == C, WSR_E_UNSUPPORTED, "fd_precompute: out_channel (%d) must equal image channels (%d)", out_ch, C);
+  WSR_REQUIRE(C <= 32, WSR_E_UNSUPPORTED, "fd_precompute: C=%d > 32", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = (int64_t)B * C * H * W;
+  char* wp = (char*)work;
+  float2* buf0 = (float2*)wp; wp += align256(n * 8);
+  float2* buf1 = (float2*)wp; wp += align256(n * 8);
+  int64_t maxL = B > C ? B : C; if (H > maxL) maxL = H; if (W > maxL) maxL = W;
+  double2* tw = (double2*)wp; wp += align256(maxL * 16);
+  double* means = (double*)wp; wp += align256((int64_t)B * 2 * C * 8);
+  float* sigma = (float*)wp; wp += align256((int64_t)B * 2 * C * 4);
+  float* se2 = (float*)wp;
+
+  real_to_complex_kernel<<<nblk(n, 256), 256, 0, st>>>(cond, buf0, n);
+  WSR_LAUNCH_OK();
+  float2* cur = buf0; float2* nxt = buf1;
+  const int L[4] = {W, H, C, B};
+  const int64_t S[4] = {1, W, (int64_t)H * W, (int64_t)C * H * W};
+  for (int ax = 0; ax < 4; ++ax) {
+    if (L[ax] == 1) continue;
+    twiddle_kernel<<<nblk(L[ax], 128), 128, 0, st>>>(tw, L[ax]);
+    dft_axis_kernel<<<nblk(n, 128), 128, 0, st>>>(cur, nxt, tw, L[ax], S[ax], n, 0, 1.0);
+    WSR_LAUNCH_OK();
+    float2* t = cur; cur = nxt; nxt = t;
+  }
+  // sigma from the unfiltered spectrum
+  spec_mean_kernel<<<B * C, 256, 0, st>>>(cur, C, H, W, nullptr, means);
+  fd_sigma_kernel<<<nblk(B, 64), 64, 0, st>>>(means, B, C, sigma_fc0, sigma_fc2, H, W, sigma);
+  // squeeze-excite of the FILTERED spectrum
+  spec_mean_kernel<<<B * C, 256, 0, st>>>(cur, C, H, W, sigma, means);
+  fd_se2_kernel<<<nblk(B, 64), 64, 0, st>>>(means, B, C, hf_fc0, hf_fc2, se2);
+  fd_filter_lf_kernel<<<nblk((int64_t)B * H * W, 128), 128, 0, st>>>(cur, cond, sigma, se2, ct_w, ct_b, B, C, H, W, lf);
+  WSR_LAUNCH_OK();
+  // inverse transform over all four axes
+  for (int ax = 0; ax < 4; ++ax) {
+    if (L[ax] == 1) continue;
+    twiddle_kernel<<<nblk(L[ax], 128), 128, 0, st>>>(tw, L[ax]);
+    dft_axis_kernel<<<nblk(n, 128), 128, 0, st>>>(cur, nxt, tw, L[ax], S[ax], n, 1, 1.0 / (double)L[ax]);
+    WSR_LAUNCH_OK();
+    float2* t = cur; cur = nxt; nxt = t;
+  }
+  complex_abs_kernel<<<nblk(n, 256), 256, 0, st>>>(cur, hf, n);
+  WSR_LAUNCH_OK();
+  return WSR_OK;
+}
+
+extern "C" int wsr_fd_gate(const float* ne_rows, int ne_ld, const int* row_index, int B, int C, int W, const float* fc0,
+                           const float* fc2, int hidden, float* gate, void* stream) {
+  WSR_REQUIRE(ne_rows && fc0 && fc2 && gate && B > 0 && C > 0 && W > 0 && ne_ld >= W, WSR_E_INVALID, "fd_gate: bad argument");
+  WSR_REQUIRE(C <= 32 && hidden > 0 && hidden <= 32, WSR_E_UNSUPPORTED, "fd_gate: C or hidden > 32");
+  fd_gate_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(ne_rows, ne_ld, row_index, C, W, fc0, fc2, hidden, gate);
+  WSR_LAUNCH_OK();
+  return WSR_OK;
+}
+
+extern "C" int wsr_stem_assemble(const float* x, const float* cond, const float* gate, const float* lf, const float* hf,
+                                 int B, int C, int H, int W, void* y, int y_dtype, int Cpad, void* stream) {
+  WSR_REQUIRE(x && cond && gate && lf && hf && y && valid_dtype(y_dtype), WSR_E_INVALID, "stem_assemble: null pointer");
+  WSR_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && Cpad >= 5 * C, WSR_E_INVALID, "stem_assemble: bad shape");
+  int64_t total = (int64_t)B * H * W * Cpad;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (y_dtype == WSR_BF16) stem_assemble_kernel<__nv_bfloat16><<<nblk(total, 256), 256, 0, st>>>(x, cond, gate, lf, hf, C, H, W, (__nv_bfloat16*)y, Cpad, total);
+  else stem_assemble_kernel<float><<<nblk(total, 256), 256, 0, st>>>(x, cond, gate, lf, hf, C, H, W, (float*)y, Cpad, total);
+  WSR_LAUNCH_OK();
+  return WSR_OK;
+}
+
+extern "C" int wsr_haar_detail_sums(const float* img, int B, int C, int H, int W, int levels, float* out, float* ll_work, void* stream) {
+  WSR_REQUIRE(img && out && ll_work && B > 0 && C > 0 && levels > 0, WSR_E_INVALID, "haar: bad argument");
+  WSR_REQUIRE((H % (1 << levels)) == 0 && (W % (1 << levels)) == 0, WSR_E_UNSUPPORTED, "haar: H, W must be divisible by 2^levels");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* ll = img;
+  int h = H, w = W;
+  float* lw0 = ll_work;
+  float* lw1 = ll_work + (int64_t)B * C * (H / 2) * (W / 2);
+  float* o = out;
+  for (int j = 0; j < levels; ++j) {
+    int64_t total = (int64_t)B * C * (h / 2) * (w / 2);
+    float* nxt = (j % 2 == 0) ? lw0 : lw1;
+    haar_level_kernel<<<nblk(total, 256), 256, 0, st>>>(ll, h, w, o, nxt, total);
+    WSR_LAUNCH_OK();
+    o += total;
+    ll = nxt; h /= 2; w /= 2;
+  }
+  return WSR_OK;
+}

@@ -1,0 +1,629 @@
+// gemm_tc.cu -- tcgen05 / TMEM implicit-GEMM kernel fed by TMA (sm_100a).
+//
+// One persistent, warp-specialised kernel computes  D[rows, cols] = sum over "K blocks" of A_box * B_box^T  with bf16
+// operands and fp32 accumulation in tensor memory.  A "K block" is 64 channels of one filter tap: the activation
+// operand of tap (ky, kx) is simply the NHWC tensor box shifted by (ky-1, kx-1), fetched by a 4-D TMA box load whose
+// out-of-bounds elements are zero-filled by the hardware -- that IS the convolution's zero padding, so no im2col buffer
+// exists anywhere.  The same kernel runs 3x3 / 1x1 convolutions, stride-2 convolutions (four phase-subsampled tensor
+// maps), nearest-x2-upsample + 3x3 (one launch per output phase), a fused second K segment (the ResnetBlock 1x1
+// `res_conv`), and the batched attention products Q*K^T and P*V.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
+// warps 2-5 = epilogue (tcgen05.ld -> bias / time-embedding / activation / residual -> global).  Two accumulator
+// buffers in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// Reference call sites replaced: every nn.Conv2d on the UNet path (nn_modules/resnet.py:24,51,78-79,
+// functional_layers.py:64,79, resdiff/unet.py:68, guided_cross_attention.py:20-22) and the attention einsums
+// (nn_modules/resnet.py:90-97, guided_cross_attention.py:34-41).
+#include <cuda.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace wsr {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes = one swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
+constexpr int kMaxEntries = 12;
+constexpr int kNumAMaps = 5;
+constexpr int kNumBMaps = 2;
+
+struct TcEntry {
+  int16_t amap, bmap;      // tensor-map indices
+  int16_t a_c0;            // first channel coordinate in A
+  int16_t d1, d2;          // coordinate offsets in A dims 1, 2 (w, h)
+  int16_t b_k0;            // first k coordinate in B
+  int16_t b_z;             // B coordinate 2 (filter tap)
+  int16_t nchunks;         // number of 64-channel K blocks
+};
+
+struct TcParams {
+  CUtensorMap amap[kNumAMaps];
+  CUtensorMap bmap[kNumBMaps];
+  TcEntry e[kMaxEntries];
+  int n_entries;
+  int total_kb;                 // sum of nchunks
+  int t1, t2, t3;               // A box extents along dims 1..3; rows_box = t1*t2*t3 <= 128
+  int g1, g2, g3;               // tiles along dims 1..3
+  int nbatch;                   // extra batch dimension (attention GEMMs); 1 for convolutions
+  int a_zmul, b_zmul;           // A coord3 += zb*a_zmul ; B coord2 += zb*b_zmul
+  int n_tiles;                  // tiles along columns
+  int a_bytes;                  // bytes one A box load delivers (rows_box * 128)
+  int M1, M2, M3;               // valid row extents (masking)
+  int Ncols;                    // valid columns
+  void* out; int out_dtype;
+  long long o_s1, o_s2, o_s3, o_sb, o_sc;
+  int mul1, off1, mul2, off2;   // output coordinate = i*mul + off along dims 1, 2
+  const float* bias;
+  const float* rowvec; int rowvec_ld;
+  int act; float out_scale;
+  const void* res; int res_dtype; long long r_s1, r_s2, r_s3, r_sb, r_sc; float res_scale;
+  const void* res2; int res2_dtype; long long q_s1, q_s2, q_s3, q_sb, q_sc; float res2_scale;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory operand descriptor (8-row x 128-byte atoms, 1024 bytes apart)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address
+  d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset
+  d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BLOCK_N> struct TcCfg {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;     // power of two for 32..256
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
+  static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  using Cfg = TcCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = p.g1 * p.g2 * p.g3 * p.nbatch;
+  const int total_tiles = m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < kNumAMaps; ++i) prefetch_tmap(&p.amap[i]);
+    for (int i = 0; i < kNumBMaps; ++i) prefetch_tmap(&p.bmap[i]);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        int mt = tile / p.n_tiles;
+        const int i1 = mt % p.g1; mt /= p.g1;
+        const int i2 = mt % p.g2; mt /= p.g2;
+        const int i3 = mt % p.g3;
+        const int zb = mt / p.g3;
+        const int c1 = i1 * p.t1, c2 = i2 * p.t2, c3 = i3 * p.t3 + zb * p.a_zmul;
+        for (int ei = 0; ei < p.n_entries; ++ei) {
+          const TcEntry e = p.e[ei];
+          for (int c = 0; c < e.nchunks; ++c) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_expect_tx(&full_bar[stage], (uint32_t)(p.a_bytes + Cfg::kBBytes));
+            tma_load_4d(sa, &p.amap[e.amap], &full_bar[stage], e.a_c0 + c * kBlockK, c1 + e.d1, c2 + e.d2, c3);
+            tma_load_3d(sb, &p.bmap[e.bmap], &full_bar[stage], e.b_k0 + c * kBlockK, nt * BLOCK_N, e.b_z + zb * p.b_zmul);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = 0; kb < p.total_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), Cfg::kIdesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == p.total_kb - 1) umma_commit(&tfull_bar[acc]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;          // row of the 128-row tile
+    const int rows_box = p.t1 * p.t2 * p.t3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int nt = tile % p.n_tiles;
+      int mt = tile / p.n_tiles;
+      const int i1 = mt % p.g1; mt /= p.g1;
+      const int i2 = mt % p.g2; mt /= p.g2;
+      const int i3 = mt % p.g3;
+      const int zb = mt / p.g3;
+      // row -> coordinates
+      const int l1 = row % p.t1;
+      const int l2 = (row / p.t1) % p.t2;
+      const int l3 = row / (p.t1 * p.t2);
+      const int r1 = i1 * p.t1 + l1, r2 = i2 * p.t2 + l2, r3 = i3 * p.t3 + l3;
+      const bool row_ok = row < rows_box && r1 < p.M1 && r2 < p.M2 && r3 < p.M3;
+      const long long o1 = (long long)r1 * p.mul1 + p.off1, o2 = (long long)r2 * p.mul2 + p.off2;
+      const long long obase = o1 * p.o_s1 + o2 * p.o_s2 + (long long)r3 * p.o_s3 + (long long)zb * p.o_sb;
+      const long long rbase = o1 * p.r_s1 + o2 * p.r_s2 + (long long)r3 * p.r_s3 + (long long)zb * p.r_sb;
+      const long long qbase = o1 * p.q_s1 + o2 * p.q_s2 + (long long)r3 * p.q_s3 + (long long)zb * p.q_sb;
+      const float* rowvec = p.rowvec ? p.rowvec + (long long)r3 * p.rowvec_ld : nullptr;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + ch * 32), v);
+        const int n0 = nt * BLOCK_N + ch * 32;
+        if (row_ok && n0 < p.Ncols) {
+        const bool full = (n0 + 32 <= p.Ncols);
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]);
+          if (full || n0 + j < p.Ncols) {
+            if (p.bias) x += __ldg(p.bias + n0 + j);
+            if (rowvec) x += __ldg(rowvec + n0 + j);
+          }
+          f[j] = apply_act(x, p.act) * p.out_scale;
+        }
+        const bool vec_ok = full && p.o_sc == 1 && ((obase + n0) & 7) == 0 && (((uintptr_t)p.out) & 15) == 0;
+        if (p.res) {
+          if (full && p.r_sc == 1 && p.res_dtype == WSR_BF16 && ((rbase + n0) & 7) == 0 && (((uintptr_t)p.res) & 15) == 0) {
+            const uint4* rp = (const uint4*)((const __nv_bfloat16*)p.res + rbase + n0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 u = rp[q];
+              const __nv_bfloat162* h = (const __nv_bfloat162*)&u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { float2 t = __bfloat1622float2(h[k]); f[q * 8 + 2 * k] += p.res_scale * t.x; f[q * 8 + 2 * k + 1] += p.res_scale * t.y; }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.Ncols) f[j] += p.res_scale * ld_dt(p.res, rbase + (long long)(n0 + j) * p.r_sc, p.res_dtype);
+          }
+        }
+        if (p.res2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < p.Ncols) f[j] += p.res2_scale * ld_dt(p.res2, qbase + (long long)(n0 + j) * p.q_sc, p.res2_dtype);
+        }
+        if (vec_ok && p.out_dtype == WSR_BF16) {
+          uint4* op = (uint4*)((__nv_bfloat16*)p.out + obase + n0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            __nv_bfloat162* h = (__nv_bfloat162*)&u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[q * 8 + 2 * k], f[q * 8 + 2 * k + 1]);
+            op[q] = u;
+          }
+        } else if (vec_ok && p.out_dtype == WSR_F32) {
+          float4* op = (float4*)((float*)p.out + obase + n0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) op[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < p.Ncols) st_dt(p.out, obase + (long long)(n0 + j) * p.o_sc, p.out_dtype, f[j]);
+        }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// bf16 tensor map, rank `rank`, innermost box 64 elements (128 B) with 128B swizzle
+static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  WSR_REQUIRE(enc != nullptr, WSR_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  WSR_REQUIRE(r == CUDA_SUCCESS, WSR_E_CUDA,
+              "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] strides [%llu %llu %llu] box [%u %u %u %u] base %p",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+              (unsigned long long)(rank > 3 ? dims[3] : 0), (unsigned long long)strides_bytes[0],
+              (unsigned long long)(rank > 2 ? strides_bytes[1] : 0), (unsigned long long)(rank > 3 ? strides_bytes[2] : 0), box[0],
+              box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, base);
+  return WSR_OK;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BLOCK_N>
+static int launch_tc(const TcParams& p, cudaStream_t st) {
+  using Cfg = TcCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    WSR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  int total = p.g1 * p.g2 * p.g3 * p.nbatch * p.n_tiles;
+  int grid = total < sm_count() ? total : sm_count();
+  gemm_tc_kernel<BLOCK_N><<<grid, 192, Cfg::kSmemBytes, st>>>(p);
+  WSR_LAUNCH_OK();
+  return WSR_OK;
+}
+
+static int pick_block_n(int ncols, int m_tiles) {
+  // widest column tile (fewest re-reads of the activation tile, best smem bandwidth per MMA) that still gives at
+  // least one CTA per SM; otherwise the narrowest one, to spread a small problem over more SMs.
+  const int sms = sm_count();
+  const int cand[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cand[i];
+    if (ncols % bn != 0) continue;
+    if (m_tiles * (ncols / bn) >= sms) return bn;
+  }
+  return 64;
+}
+
+int validate_conv_desc(const WsrConvDesc* d);
+int validate_gemm_desc(const WsrGemmDesc* g);
+
+static void choose_tile(int W, int H, int N, int& t1, int& t2, int& t3) {
+  t1 = W < 128 ? W : 128;
+  t2 = 128 / t1; if (t2 > H) t2 = H; if (t2 < 1) t2 = 1;
+  t3 = 128 / (t1 * t2); if (t3 > N) t3 = N; if (t3 < 1) t3 = 1;
+}
+
+}  // namespace wsr
+
+using namespace wsr;
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
+  int rc = validate_conv_desc(d);
+  if (rc) return rc;
+  WSR_REQUIRE(d->x_dtype == WSR_BF16, WSR_E_UNSUPPORTED, "conv_tc: bf16 operands only");
+  WSR_REQUIRE(d->Cin % 64 == 0 && d->x_ld % 8 == 0 && (((uintptr_t)d->x) & 15) == 0 && (((uintptr_t)d->w) & 15) == 0,
+              WSR_E_UNSUPPORTED, "conv_tc: Cin %% 64, pitch %% 8 and 16-byte alignment required (Cin=%d ld=%d)", d->Cin, d->x_ld);
+  if (d->x2)
+    WSR_REQUIRE(d->Cin2 % 64 == 0 && d->x2_ld % 8 == 0 && (((uintptr_t)d->x2) & 15) == 0 && (((uintptr_t)d->w2) & 15) == 0,
+                WSR_E_UNSUPPORTED, "conv_tc: second segment Cin2 %% 64 / alignment");
+  WSR_REQUIRE(!(d->x2 && (d->stride != 1 || d->upsample)), WSR_E_UNSUPPORTED, "conv_tc: second segment needs stride 1, no upsample");
+  cudaStream_t st = (cudaStream_t)stream;
+
+  const int up = d->upsample ? 2 : 1;
+  const int OH = d->H * up / d->stride, OW = d->W * up / d->stride;
+  // grid of GEMM rows: output pixels (stride 1 / 2) or input-resolution pixels per output phase (upsample)
+  const int GH = d->upsample ? d->H : OH, GW = d->upsample ? d->W : OW;
+  const int taps = d->ksize * d->ksize;
+  const int pad = (d->ksize - 1) / 2;
+  const int nphase = d->upsample ? 4 : 1;
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  choose_tile(GW, GH, d->N, p.t1, p.t2, p.t3);
+  WSR_REQUIRE(p.t1 <= 256 && p.t2 <= 256 && p.t3 <= 256, WSR_E_UNSUPPORTED, "conv_tc: tile");
+  p.g1 = cdiv(GW, p.t1); p.g2 = cdiv(GH, p.t2); p.g3 = cdiv(d->N, p.t3);
+  p.nbatch = 1; p.a_zmul = 0; p.b_zmul = 0;
+  p.a_bytes = p.t1 * p.t2 * p.t3 * 128;
+  p.M1 = GW; p.M2 = GH; p.M3 = d->N;
+  p.Ncols = d->Cout;
+  p.out = d->y; p.out_dtype = d->y_dtype;
+  p.o_s1 = d->y_ld; p.o_s2 = (long long)OW * d->y_ld; p.o_s3 = (long long)OH * OW * d->y_ld; p.o_sb = 0; p.o_sc = 1;
+  p.bias = d->bias; p.rowvec = d->rowvec; p.rowvec_ld = d->rowvec_ld;
+  p.act = d->act; p.out_scale = d->out_scale;
+  p.res = d->res; p.res_dtype = d->res_dtype; p.res_scale = d->res_scale;
+  p.r_s1 = d->res_ld; p.r_s2 = (long long)OW * d->res_ld; p.r_s3 = (long long)OH * OW * d->res_ld; p.r_sc = 1;
+  p.res2 = d->res2; p.res2_dtype = d->res2_dtype; p.res2_scale = d->res2_scale;
+  p.q_s1 = d->res2_ld; p.q_s2 = (long long)OW * d->res2_ld; p.q_s3 = (long long)OH * OW * d->res2_ld; p.q_sc = 1;
+
+  const int m_tiles = p.g1 * p.g2 * p.g3;
+  const int bn = pick_block_n(d->Cout, m_tiles);
+
+  // ---- B maps: weights [tap][Cout][Cin]
+  {
+    const int wrows = d->w_rows > 0 ? d->w_rows : d->Cout;
+    WSR_REQUIRE(wrows >= bn || wrows % 64 == 0 || true, WSR_E_INVALID, "conv_tc: w_rows");
+    uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)wrows, (uint64_t)taps};
+    uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cin * wrows * 2};
+    uint32_t box[3] = {64, (uint32_t)bn, 1};
+    rc = encode_map(&p.bmap[0], d->w, 3, dims, str, box);
+    if (rc) return rc;
+    p.bmap[1] = p.bmap[0];
+    if (d->x2) {
+      uint64_t dims2[3] = {(uint64_t)d->Cin2, (uint64_t)wrows, 1};
+      uint64_t str2[2] = {(uint64_t)d->Cin2 * 2, (uint64_t)d->Cin2 * wrows * 2};
+      rc = encode_map(&p.bmap[1], d->w2, 3, dims2, str2, box);
+      if (rc) return rc;
+    }
+  }
+  // ---- A maps
+  const uint32_t abox[4] = {64, (uint32_t)p.t1, (uint32_t)p.t2, (uint32_t)p.t3};
+  const long long ld = d->x_ld;
+  if (d->stride == 1) {
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)d->W * ld * 2, (uint64_t)d->H * d->W * ld * 2};
+    rc = encode_map(&p.amap[0], d->x, 4, dims, str, abox);
+    if (rc) return rc;
+    for (int i = 1; i < kNumAMaps; ++i) p.amap[i] = p.amap[0];
+  } else {
+    // four phase-subsampled views: phase (py, px) starts at pixel (py, px), steps 2 pixels
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W / 2, (uint64_t)d->H / 2, (uint64_t)d->N};
+        uint64_t str[3] = {(uint64_t)ld * 4, (uint64_t)d->W * ld * 4, (uint64_t)d->H * d->W * ld * 2};
+        const __nv_bfloat16* base = (const __nv_bfloat16*)d->x + ((long long)py * d->W + px) * ld;
+        rc = encode_map(&p.amap[py * 2 + px], base, 4, dims, str, abox);
+        if (rc) return rc;
+      }
+    p.amap[4] = p.amap[0];
+  }
+  if (d->x2) {
+    uint64_t dims[4] = {(uint64_t)d->Cin2, (uint64_t)OW, (uint64_t)OH, (uint64_t)d->N};
+    uint64_t str[3] = {(uint64_t)d->x2_ld * 2, (uint64_t)OW * d->x2_ld * 2, (uint64_t)OH * OW * d->x2_ld * 2};
+    rc = encode_map(&p.amap[4], d->x2, 4, dims, str, abox);
+    if (rc) return rc;
+  }
+
+  for (int ph = 0; ph < nphase; ++ph) {
+    const int py = ph >> 1, px = ph & 1;
+    int ne = 0, kb = 0;
+    for (int ky = 0; ky < d->ksize; ++ky)
+      for (int kx = 0; kx < d->ksize; ++kx) {
+        TcEntry& e = p.e[ne++];
+        e.a_c0 = 0; e.b_k0 = 0; e.bmap = 0; e.b_z = (int16_t)(ky * d->ksize + kx);
+        e.nchunks = (int16_t)(d->Cin / 64);
+        if (d->upsample) {
+          // source row = i + floor((py + ky - 1) / 2)
+          int a = py + ky - pad, b = px + kx - pad;
+          e.amap = 0;
+          e.d2 = (int16_t)(a < 0 ? -1 : a / 2);
+          e.d1 = (int16_t)(b < 0 ? -1 : b / 2);
+        } else if (d->stride == 2) {
+          // input row = 2*oy + ky - pad = 2*(oy + off) + phase
+          int a = ky - pad, b = kx - pad;
+          int pa = ((a % 2) + 2) % 2, pb = ((b % 2) + 2) % 2;
+          e.amap = (int16_t)(pa * 2 + pb);
+          e.d2 = (int16_t)((a - pa) / 2);
+          e.d1 = (int16_t)((b - pb) / 2);
+        } else {
+          e.amap = 0; e.d2 = (int16_t)(ky - pad); e.d1 = (int16_t)(kx - pad);
+        }
+        kb += e.nchunks;
+      }
+    if (d->x2) {
+      TcEntry& e = p.e[ne++];
+      e.amap = 4; e.bmap = 1; e.a_c0 = 0; e.b_k0 = 0; e.b_z = 0; e.d1 = 0; e.d2 = 0;
+      e.nchunks = (int16_t)(d->Cin2 / 64);
+      kb += e.nchunks;
+    }
+    p.n_entries = ne; p.total_kb = kb;
+    p.mul1 = d->upsample ? 2 : 1; p.mul2 = p.mul1;
+    p.off1 = d->upsample ? px : 0; p.off2 = d->upsample ? py : 0;
+    p.n_tiles = cdiv(d->Cout, bn);
+    switch (bn) {
+      case 256: rc = launch_tc<256>(p, st); break;
+      case 128: rc = launch_tc<128>(p, st); break;
+      default: rc = launch_tc<64>(p, st); break;
+    }
+    if (rc) return rc;
+  }
+  return WSR_OK;
+}
+
+extern "C" int wsr_gemm_tc(const WsrGemmDesc* g, void* stream) {
+  int rc = validate_gemm_desc(g);
+  if (rc) return rc;
+  WSR_REQUIRE(g->a_dtype == WSR_BF16 && g->b_dtype == WSR_BF16, WSR_E_UNSUPPORTED, "gemm_tc: bf16 operands only");
+  WSR_REQUIRE(g->a_sk == 1 && g->b_sk == 1, WSR_E_UNSUPPORTED, "gemm_tc: both operands must be K-major (unit k stride)");
+  WSR_REQUIRE(g->K % 64 == 0, WSR_E_UNSUPPORTED, "gemm_tc: K=%d must be a multiple of 64", g->K);
+  WSR_REQUIRE(g->a_sm % 8 == 0 && g->b_sn % 8 == 0 && g->a_sb % 8 == 0 && g->b_sb % 8 == 0 && (((uintptr_t)g->a) & 15) == 0 &&
+                  (((uintptr_t)g->b) & 15) == 0,
+              WSR_E_UNSUPPORTED, "gemm_tc: strides must be multiples of 8 elements, bases 16-byte aligned");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.t1 = g->M < 128 ? g->M : 128; p.t2 = 1; p.t3 = 1;
+  p.g1 = cdiv(g->M, p.t1); p.g2 = 1; p.g3 = 1;
+  p.nbatch = g->batch; p.a_zmul = 1; p.b_zmul = 1;
+  p.a_bytes = p.t1 * 128;
+  p.M1 = g->M; p.M2 = 1; p.M3 = 1;
+  p.Ncols = g->N;
+  p.out = g->d; p.out_dtype = g->d_dtype;
+  p.o_s1 = g->d_sm; p.o_s2 = 0; p.o_s3 = 0; p.o_sb = g->d_sb; p.o_sc = g->d_sn;
+  p.mul1 = 1; p.mul2 = 1;
+  p.bias = g->bias; p.act = WSR_ACT_NONE; p.out_scale = g->alpha;
+  p.res = g->res; p.res_dtype = g->res_dtype; p.res_scale = 1.f;
+  p.r_s1 = g->res_sm; p.r_sb = g->res_sb; p.r_sc = g->res_sn;
+  const int m_tiles = p.g1 * g->batch;
+  const int bn = pick_block_n(g->N, m_tiles);
+  {
+    uint64_t dims[4] = {(uint64_t)g->K, (uint64_t)g->M, 1, (uint64_t)g->batch};
+    uint64_t str[3] = {(uint64_t)g->a_sm * 2, (uint64_t)g->a_sm * g->M * 2, (uint64_t)(g->batch > 1 ? g->a_sb : g->a_sm * g->M) * 2};
+    if (g->batch > 1 && g->a_sb == 0) { dims[3] = 1; p.a_zmul = 0; str[2] = str[1]; }
+    uint32_t box[4] = {64, (uint32_t)p.t1, 1, 1};
+    rc = encode_map(&p.amap[0], g->a, 4, dims, str, box);
+    if (rc) return rc;
+    for (int i = 1; i < kNumAMaps; ++i) p.amap[i] = p.amap[0];
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)g->K, (uint64_t)g->N, (uint64_t)g->batch};
+    uint64_t str[2] = {(uint64_t)g->b_sn * 2, (uint64_t)(g->batch > 1 ? g->b_sb : g->b_sn * g->N) * 2};
+    if (g->batch > 1 && g->b_sb == 0) { dims[2] = 1; p.b_zmul = 0; str[1] = (uint64_t)g->b_sn * g->N * 2; }
+    uint32_t box[3] = {64, (uint32_t)bn, 1};
+    rc = encode_map(&p.bmap[0], g->b, 3, dims, str, box);
+    if (rc) return rc;
+    p.bmap[1] = p.bmap[0];
+  }
+  p.n_entries = 1;
+  p.e[0].amap = 0; p.e[0].bmap = 0; p.e[0].a_c0 = 0; p.e[0].b_k0 = 0; p.e[0].b_z = 0; p.e[0].d1 = 0; p.e[0].d2 = 0;
+  WSR_REQUIRE(g->K / 64 <= 32767, WSR_E_UNSUPPORTED, "gemm_tc: K too large");
+  p.e[0].nchunks = (int16_t)(g->K / 64);
+  p.total_kb = g->K / 64;
+  p.n_tiles = cdiv(g->N, bn);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (bn) {
+    case 256: return launch_tc<256>(p, st);
+    case 128: return launch_tc<128>(p, st);
+    default: return launch_tc<64>(p, st);
+  }
+}

@@ -1,0 +1,212 @@
+"""Host-side engine: device buffers, packed weights and typed wrappers over the C ABI (libwsr.so).
+
+PyTorch is used here only as plumbing: it owns device memory (``torch.empty``) and the CUDA stream; every arithmetic
+operation is a call into the hand-written kernels through ``_native.call``.  Activations are NHWC slices (``Act``)
+with an explicit channel pitch so that skip-concatenation and dense blocks never copy.
+
+Precision modes
+---------------
+``bf16``   bf16 activations/weights, tcgen05 tensor-core kernels (``wsr_conv_tc`` / ``wsr_gemm_tc``), fp32 accumulation.
+           Shapes the tensor-core kernel does not take (channel counts that are not multiples of 64, e.g. the 1-channel
+           Haar query convolution) run on the SIMT kernel; with ``strict_tc=True`` that raises instead.
+``fp32``   "fp32 check mode": fp32 activations/weights on the SIMT kernels; matches the reference to ~1e-5.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _native as nat
+
+_DT = {"bf16": (nat.BF16, torch.bfloat16), "fp32": (nat.F32, torch.float32)}
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class Act:
+    """A channel slice [coff, coff+C) of an NHWC buffer (N, H, W, ld)."""
+
+    __slots__ = ("buf", "N", "H", "W", "C", "ld", "coff", "dt")
+
+    def __init__(self, buf, N, H, W, C, ld, coff, dt):
+        self.buf, self.N, self.H, self.W, self.C, self.ld, self.coff, self.dt = buf, N, H, W, C, ld, coff, dt
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr() + self.coff * self.buf.element_size()
+
+    def slice(self, c0, c):
+        assert 0 <= c0 and c0 + c <= self.C
+        return Act(self.buf, self.N, self.H, self.W, c, self.ld, self.coff + c0, self.dt)
+
+    def to_nchw(self, eng):
+        out = torch.empty((self.N, self.C, self.H, self.W), device=self.buf.device, dtype=torch.float32)
+        nat.call("wsr_nhwc_to_nchw", self.ptr, self.dt, self.ld, self.N, self.C, self.H, self.W, out.data_ptr(), eng.stream)
+        return out
+
+
+class PackedConv:
+    """Conv weight packed as [tap][rows][Cin_pad] in the engine dtype, fp32 bias."""
+
+    __slots__ = ("w", "bias", "Cout", "Cin", "Cin_pad", "rows", "k")
+
+
+class Engine:
+    def __init__(self, device, mode="bf16", strict_tc=False):
+        if mode not in _DT:
+            raise ValueError("mode must be 'bf16' or 'fp32', got %r" % (mode,))
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise nat.WsrError("the B200 engine needs a CUDA device; there is no CPU fallback (got %s)" % device)
+        self.mode = mode
+        self.dt, self.tdt = _DT[mode]
+        self.strict_tc = strict_tc
+        self.use_tc = mode == "bf16" and bool(nat.call("wsr_device_is_sm100"))
+        if mode == "bf16" and not self.use_tc and strict_tc:
+            raise nat.WsrError("bf16 tensor-core mode needs an sm_100 device")
+        self.n_tc = 0
+        self.n_simt = 0
+        self._keep = []          # tensors that must outlive async launches
+
+    # ---- plumbing -------------------------------------------------------------------------------------------------
+    @property
+    def stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def empty(self, shape, dtype=None):
+        return torch.empty(shape, device=self.device, dtype=dtype or self.tdt)
+
+    def zeros(self, shape, dtype=None):
+        return torch.zeros(shape, device=self.device, dtype=dtype or self.tdt)
+
+    def new_act(self, N, H, W, C, ld=None, dt=None, zero=False):
+        ld = ld or C
+        tdt = self.tdt if dt is None else (torch.bfloat16 if dt == nat.BF16 else torch.float32)
+        buf = (torch.zeros if zero else torch.empty)((N, H, W, ld), device=self.device, dtype=tdt)
+        return Act(buf, N, H, W, C, ld, 0, self.dt if dt is None else dt)
+
+    def f32(self, t):
+        return t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+
+    # ---- packing ---------------------------------------------------------------------------------------------------
+    def pack_conv(self, weight, bias=None, cin_pad=None, rows=None):
+        """weight: OIHW fp32 parameter."""
+        w = self.f32(weight)
+        Cout, Cin, KH, KW = w.shape
+        pc = PackedConv()
+        pc.Cout, pc.Cin, pc.k = Cout, Cin, KH
+        pc.Cin_pad = cin_pad or Cin
+        pc.rows = rows or Cout
+        pc.w = self.empty((KH * KW, pc.rows, pc.Cin_pad))
+        nat.call("wsr_pack_conv_weight", w.data_ptr(), Cout, Cin, KH, KW, pc.w.data_ptr(), self.dt, pc.rows, pc.Cin_pad, self.stream)
+        pc.bias = None if bias is None else self.f32(bias)
+        self._keep.append(w)
+        return pc
+
+    def pack_rows(self, weight2d):
+        """(rows, K) fp32 matrix -> engine dtype, row-major (K-major operand for the GEMM kernels)."""
+        w = self.f32(weight2d)
+        out = self.empty(tuple(w.shape))
+        nat.call("wsr_cast", w.data_ptr(), nat.F32, out.data_ptr(), self.dt, w.numel(), self.stream)
+        self._keep.append(w)
+        return out
+
+    # ---- ops -------------------------------------------------------------------------------------------------------
+    def _tc_conv_ok(self, x, pc, x2, y):
+        if not self.use_tc:
+            return False
+        ok = (x.dt == nat.BF16 and pc.Cin_pad % 64 == 0 and x.C == pc.Cin_pad and x.ld % 8 == 0 and x.ptr % 16 == 0
+              and x.W >= 1)
+        if x2 is not None:
+            ok = ok and x2.C % 64 == 0 and x2.ld % 8 == 0 and x2.ptr % 16 == 0
+        return ok
+
+    def conv(self, x, pc, y, stride=1, upsample=False, bias=True, rowvec=None, rowvec_ld=0, act=nat.ACT_NONE,
+             out_scale=1.0, res=None, res_scale=1.0, res2=None, res2_scale=1.0, x2=None, w2=None, extra_bias=None,
+             force_simt=False):
+        """y = act(conv(x) [+ conv1x1(x2, w2)] + bias + rowvec) * out_scale + res*res_scale + res2*res2_scale."""
+        d = nat.ConvDesc()
+        d.x, d.x_dtype, d.N, d.H, d.W, d.Cin, d.x_ld = x.ptr, x.dt, x.N, x.H, x.W, pc.Cin_pad, x.ld
+        assert x.C == pc.Cin_pad, (x.C, pc.Cin_pad)
+        d.w, d.w_rows = pc.w.data_ptr(), pc.rows
+        d.ksize, d.stride, d.upsample = pc.k, stride, 1 if upsample else 0
+        d.Cout = pc.Cout
+        assert y.C == pc.Cout, (y.C, pc.Cout)
+        if x2 is not None:
+            assert w2.rows == pc.rows and w2.Cout == pc.Cout and x2.C == w2.Cin_pad
+            d.x2, d.Cin2, d.x2_ld, d.w2 = x2.ptr, x2.C, x2.ld, w2.w.data_ptr()
+        b = extra_bias if extra_bias is not None else (pc.bias if bias else None)
+        d.bias = _ptr(b)
+        d.rowvec, d.rowvec_ld = (rowvec or 0), rowvec_ld
+        d.act, d.out_scale = act, out_scale
+        if res is not None:
+            d.res, d.res_dtype, d.res_ld, d.res_scale = res.ptr, res.dt, res.ld, res_scale
+        if res2 is not None:
+            d.res2, d.res2_dtype, d.res2_ld, d.res2_scale = res2.ptr, res2.dt, res2.ld, res2_scale
+        d.y, d.y_dtype, d.y_ld = y.ptr, y.dt, y.ld
+        if not force_simt and self._tc_conv_ok(x, pc, x2, y):
+            self.n_tc += 1
+            nat.call("wsr_conv_tc", C.byref(d), self.stream)
+        else:
+            if self.strict_tc and not force_simt:
+                raise nat.WsrError("strict_tc: conv Cin=%d Cout=%d k=%d not eligible for the tcgen05 kernel" % (pc.Cin_pad, pc.Cout, pc.k))
+            self.n_simt += 1
+            nat.call("wsr_conv_simt", C.byref(d), self.stream)
+        return y
+
+    def gemm(self, a_ptr, a_dt, a_s, b_ptr, b_dt, b_s, d_ptr, d_dt, d_s, batch, M, N, K, alpha=1.0, bias=None,
+             force_simt=False):
+        """D[b][m][n] = alpha * sum_k A[b][m][k] B[b][n][k] (+bias[n]).  *_s = (batch stride, row stride, k/col stride)."""
+        g = nat.GemmDesc()
+        g.a, g.a_dtype, (g.a_sb, g.a_sm, g.a_sk) = a_ptr, a_dt, a_s
+        g.b, g.b_dtype, (g.b_sb, g.b_sn, g.b_sk) = b_ptr, b_dt, b_s
+        g.d, g.d_dtype, (g.d_sb, g.d_sm, g.d_sn) = d_ptr, d_dt, d_s
+        g.bias = _ptr(bias)
+        g.batch, g.M, g.N, g.K, g.alpha = batch, M, N, K, alpha
+        tc_ok = (self.use_tc and not force_simt and a_dt == nat.BF16 and b_dt == nat.BF16 and a_s[2] == 1 and b_s[2] == 1
+                 and K % 64 == 0 and a_s[1] % 8 == 0 and b_s[1] % 8 == 0 and a_s[0] % 8 == 0 and b_s[0] % 8 == 0
+                 and a_ptr % 16 == 0 and b_ptr % 16 == 0)
+        if tc_ok:
+            self.n_tc += 1
+            nat.call("wsr_gemm_tc", C.byref(g), self.stream)
+        else:
+            if self.strict_tc and not force_simt:
+                raise nat.WsrError("strict_tc: gemm M=%d N=%d K=%d not eligible for the tcgen05 kernel" % (M, N, K))
+            self.n_simt += 1
+            nat.call("wsr_gemm_simt", C.byref(g), self.stream)
+
+    def gn_stats(self, x, stats):
+        nat.call("wsr_gn_stats", x.ptr, x.dt, x.N, x.H * x.W, x.C, x.ld, stats.data_ptr(), self.stream)
+
+    def gn_apply(self, x, stats, gamma, beta, groups, act, y, eps=1e-5):
+        nat.call("wsr_gn_apply", x.ptr, x.dt, x.N, x.H * x.W, x.C, x.ld, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                 groups, eps, act, y.ptr, y.dt, y.ld, self.stream)
+        return y
+
+    def softmax(self, s, s_dt, rows, cols, scale, p, p_dt):
+        nat.call("wsr_softmax_rows", s.data_ptr(), s_dt, rows, cols, cols, scale, p.data_ptr(), p_dt, cols, self.stream)
+
+    def nchw_to_act(self, src, y):
+        src = src.contiguous()
+        N, Cc, H, W = src.shape
+        nat.call("wsr_nchw_to_nhwc", src.data_ptr(), N, Cc, H, W, y.ptr, y.dt, y.ld, self.stream)
+        self._keep_tmp = src
+        return y
+
+    # ---- attention (single head, dense softmax; nn_modules/resnet.py:81-100, guided_cross_attention.py:24-44) --------
+    def attention(self, q, k, vT, o, scores, probs):
+        """q, k: Act (B, H, W, C) row-major pixels x channels; vT: tensor (B, C, Nk) (V transposed, K-major for P*V);
+        o: Act (B, H, W, C).  scores/probs: scratch tensors (B, Nq, Nk)."""
+        B, Nq, Nk, Cc = q.N, q.H * q.W, k.H * k.W, q.C
+        es = q.buf.element_size()
+        s_dt = nat.BF16 if scores.dtype == torch.bfloat16 else nat.F32
+        p_dt = nat.BF16 if probs.dtype == torch.bfloat16 else nat.F32
+        self.gemm(q.ptr, q.dt, (Nq * q.ld, q.ld, 1), k.ptr, k.dt, (Nk * k.ld, k.ld, 1),
+                  scores.data_ptr(), s_dt, (Nq * Nk, Nk, 1), B, Nq, Nk, Cc)
+        self.softmax(scores, s_dt, B * Nq, Nk, 1.0 / math.sqrt(Cc), probs, p_dt)
+        self.gemm(probs.data_ptr(), p_dt, (Nq * Nk, Nk, 1), vT.data_ptr(), self.dt, (Cc * Nk, Nk, 1),
+                  o.ptr, o.dt, (Nq * o.ld, o.ld, 1), B, Nq, Cc, Nk)
+        del es
+        return o

@@ -1,0 +1,203 @@
+"""GaussianDiffusion -- drop-in for the reference's models/diffusion_models/diffusion.py:10-273.
+
+Same constructor, buffers (12 fp32 schedule tables under the reference's names, so checkpoints round-trip),
+attributes (``num_timesteps``, ``sqrt_alphas_cumprod_prev`` as a host numpy array) and methods.  The arithmetic of
+``p_sample`` / ``q_sample`` / the loss runs in the fused CUDA kernels (wsr_sampler_step, wsr_q_sample,
+wsr_noise_loss); the reverse loop keeps the step counter on the device and replays one captured CUDA graph per step
+instead of ~610 eager launches plus a host->device copy (reference diffusion.py:159-160).
+"""
+from abc import abstractmethod
+
+import numpy as np
+import torch
+from torch import nn
+
+from ... import _native as nat
+from .nn_modules.functional_layers import default
+from .sheduler import make_beta_schedule
+
+_TABLE_ORDER = ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+                "posterior_mean_coef2", "posterior_log_variance_clipped")
+
+
+class GaussianDiffusion(nn.Module):
+    def __init__(self, denoise_fn, channels=1, loss_type='l1', conditional=True, schedule_opt=None, image_height=128,
+                 image_width=256, pretrained_model_path=None, lock_weights=True):
+        super().__init__()
+        self.channels = channels
+        self.image_height = image_height
+        self.image_width = image_width
+        self.denoise_fn = denoise_fn
+        self.loss_type = loss_type
+        self.conditional = conditional
+        self.use_cuda_graph = True
+        self.sample_seed = None          # None -> derive from torch's global generator at every loop
+        self._sampler_tables = None
+
+    # ---- schedule (reference :49-96) --------------------------------------------------------------------------------
+    def set_new_noise_schedule(self, schedule_opt, device):
+        betas = make_beta_schedule(schedule=schedule_opt['schedule'], n_timestep=schedule_opt['n_timestep'],
+                                   linear_start=schedule_opt['linear_start'], linear_end=schedule_opt['linear_end'])
+        betas = np.asarray(betas, dtype=np.float64)
+        alphas = 1.0 - betas
+        abar = np.cumprod(alphas, axis=0)
+        abar_prev = np.append(1.0, abar[:-1])
+        self.sqrt_alphas_cumprod_prev = np.sqrt(np.append(1.0, abar))
+        self.num_timesteps = int(betas.shape[0])
+        post_var = betas * (1.0 - abar_prev) / (1.0 - abar)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            tables = {
+                'betas': betas,
+                'alphas_cumprod': abar,
+                'alphas_cumprod_prev': abar_prev,
+                'sqrt_alphas_cumprod': np.sqrt(abar),
+                'sqrt_one_minus_alphas_cumprod': np.sqrt(1.0 - abar),
+                'log_one_minus_alphas_cumprod': np.log(1.0 - abar),
+                'sqrt_recip_alphas_cumprod': np.sqrt(1.0 / abar),
+                'sqrt_recipm1_alphas_cumprod': np.sqrt(1.0 / abar - 1),
+                'posterior_variance': post_var,
+                'posterior_log_variance_clipped': np.log(np.maximum(post_var, 1e-20)),
+                'posterior_mean_coef1': betas * np.sqrt(abar_prev) / (1.0 - abar),
+                'posterior_mean_coef2': (1.0 - abar_prev) * np.sqrt(alphas) / (1.0 - abar),
+            }
+        for name, arr in tables.items():
+            self.register_buffer(name, torch.tensor(arr, dtype=torch.float32, device=device))
+        self._sampler_tables = None
+
+    def _tables_dev(self):
+        """[5][T] fp32 table consumed by wsr_sampler_step + the T noise levels sqrt(abar_prev[t+1]) (:159-160)."""
+        if self._sampler_tables is None or self._sampler_tables[0].device != self.betas.device:
+            tab = torch.stack([getattr(self, n) for n in _TABLE_ORDER], 0).contiguous()
+            levels = torch.tensor(self.sqrt_alphas_cumprod_prev[1:].astype(np.float32), device=self.betas.device)
+            self._sampler_tables = (tab, levels)
+        return self._sampler_tables
+
+    def set_loss(self, device):
+        if self.loss_type not in ('l1', 'l2'):
+            raise NotImplementedError()
+        self.loss_device = device
+
+    # ---- closed-form pieces kept for API compatibility (reference :112-142) -----------------------------------------
+    def predict_start_from_noise(self, x_t, t, noise):
+        return self.sqrt_recip_alphas_cumprod[t] * x_t - self.sqrt_recipm1_alphas_cumprod[t] * noise
+
+    def q_posterior(self, x_start, x_t, t):
+        mean = self.posterior_mean_coef1[t] * x_start + self.posterior_mean_coef2[t] * x_t
+        return mean, self.posterior_log_variance_clipped[t]
+
+    # ---- engine glue ------------------------------------------------------------------------------------------------
+    def _plan(self, batch, device):
+        return self.denoise_fn.plan(batch, device)
+
+    def _set_condition(self, plan, condition_x):
+        plan.set_condition(condition_x)
+
+    def _next_seed(self):
+        if self.sample_seed is not None:
+            return int(self.sample_seed)
+        return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+    @torch.no_grad()
+    def p_sample(self, x, t, clip_denoised=True, condition_x=None):
+        """One reverse step x_t -> x_{t-1} (reference :175-192), generic (un-hoisted) entry."""
+        if condition_x is None:
+            raise NotImplementedError("unconditional sampling is not part of the accelerated path")
+        plan = self._plan(x.shape[0], x.device)
+        self._set_condition(plan, condition_x)
+        tab, levels = self._tables_dev()
+        plan.set_level_table(levels)
+        t_dev = torch.tensor([int(t)], dtype=torch.int32, device=x.device)
+        xb = x.to(torch.float32).contiguous().clone()
+        self._step(plan, xb, t_dev, tab, None, 0, self._next_seed(), clip_denoised)
+        return xb
+
+    def _step(self, plan, x, t_dev, tab, z, z_stride, seed, clip=True):
+        st = plan.eng.stream
+        plan.select_level_row(t_dev)
+        plan.run(x)
+        nat.call("wsr_sampler_step", x.data_ptr(), plan.eps.data_ptr(), nat.F32, 0 if z is None else z.data_ptr(),
+                 z_stride, seed, tab.data_ptr(), self.num_timesteps, t_dev.data_ptr(), 1 if clip else 0, x.data_ptr(),
+                 x.numel(), st)
+        nat.call("wsr_step_counter_add", t_dev.data_ptr(), -1, st)
+
+    @torch.no_grad()
+    def _reverse_loop(self, plan, shape, noise_chain=None, seed=None, steps=None, collect_eps=False):
+        """T reverse steps on the plan's current condition.  noise_chain: optional injected noise [T+1, *shape]
+        (index 0 = initial image, index T-t = noise of step t) for parity runs; otherwise Philox noise from ``seed``.
+        Returns the final x_0 (fp32 NCHW)."""
+        dev = plan.eng.device
+        T = self.num_timesteps
+        tab, levels = self._tables_dev()
+        plan.set_level_table(levels)
+        x = torch.empty(shape, device=dev, dtype=torch.float32)
+        seed = self._next_seed() if seed is None else int(seed)
+        if noise_chain is not None:
+            z = noise_chain.to(device=dev, dtype=torch.float32).contiguous()
+            assert z.shape[0] == T + 1 and tuple(z.shape[1:]) == tuple(shape)
+            x.copy_(z[0])
+            z_stride = x.numel()
+        else:
+            z, z_stride = None, 0
+            nat.call("wsr_randn", x.data_ptr(), x.numel(), seed, 0xFFFFFFFF, plan.eng.stream)
+        t_dev = torch.tensor([T - 1], dtype=torch.int32, device=dev)
+        n_steps = T if steps is None else min(int(steps), T)
+        eps_log = []
+        # first step eagerly (lazy initialisation of kernel attributes happens here), the rest as graph replays
+        self._step(plan, x, t_dev, tab, z, z_stride, seed)
+        if collect_eps:
+            eps_log.append(plan.eps.clone())
+        remaining = n_steps - 1
+        if remaining > 0 and self.use_cuda_graph and not collect_eps:
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._step(plan, x, t_dev, tab, z, z_stride, seed)
+            for _ in range(remaining):
+                graph.replay()
+            self._last_graph = graph
+        else:
+            for _ in range(remaining):
+                self._step(plan, x, t_dev, tab, z, z_stride, seed)
+                if collect_eps:
+                    eps_log.append(plan.eps.clone())
+        if collect_eps:
+            return x, eps_log
+        return x
+
+    @torch.no_grad()
+    def sample(self, batch_size=1, continous=False):
+        return self.p_sample_loop((batch_size, self.channels, self.image_height, self.image_height), continous)
+
+    def q_sample(self, x_start, continuous_sqrt_alpha_cumprod, noise=None):
+        """reference :209-228.  x_start (B,C,H,W), continuous_sqrt_alpha_cumprod (B,1,1,1)."""
+        noise = default(noise, lambda: torch.randn_like(x_start))
+        x0 = x_start.to(torch.float32).contiguous()
+        a = continuous_sqrt_alpha_cumprod.reshape(-1).to(torch.float32).contiguous()
+        nz = noise.to(torch.float32).contiguous()
+        zero = torch.zeros_like(x0)
+        out = torch.empty_like(x0)
+        nat.call("wsr_q_sample", x0.data_ptr(), zero.data_ptr(), nz.data_ptr(), a.data_ptr(), x0.shape[0],
+                 x0[0].numel(), out.data_ptr(), torch.cuda.current_stream(x0.device).cuda_stream)
+        return out
+
+    def _noise_loss(self, noise, eps):
+        """Sum-reduced L1/L2 (reference :98-110) computed by wsr_noise_loss; returns a 0-dim fp32 tensor."""
+        acc = torch.zeros(1, dtype=torch.float64, device=noise.device)
+        nat.call("wsr_noise_loss", noise.data_ptr(), eps.data_ptr(), noise.numel(), 1 if self.loss_type == 'l2' else 0,
+                 acc.data_ptr(), 0, 0.0, torch.cuda.current_stream(noise.device).cuda_stream)
+        return acc.to(torch.float32)[0]
+
+    def forward(self, x, *args, **kwargs):
+        return self.p_losses(x, *args, **kwargs)
+
+    @abstractmethod
+    def p_sample_loop(self, x_in, continous=False) -> torch.Tensor:
+        pass
+
+    @abstractmethod
+    def super_resolution(self, x_in, continous=False) -> torch.Tensor:
+        pass
+
+    @abstractmethod
+    def p_losses(self, x_in, noise=None) -> torch.Tensor:
+        pass

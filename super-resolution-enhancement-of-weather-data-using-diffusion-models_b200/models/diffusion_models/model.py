@@ -1,0 +1,140 @@
+"""DDPM facade -- drop-in for the reference's models/diffusion_models/model.py:13-252 (same methods, same checkpoint
+file names and contents: ``I{iter}_E{epoch}_gen.pth`` = netG.state_dict() on CPU, ``..._opt.pth`` = optimizer state)."""
+import logging
+import os
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from ..base_model import BaseModel
+from . import networks
+
+logger = logging.getLogger('base')
+
+
+class DDPM(BaseModel):
+    def __init__(self, opt):
+        super().__init__(opt)
+        if self.device.type != "cuda":
+            raise RuntimeError("the B200-native path needs a CUDA device and '-gpu <ids>' (no CPU fallback); "
+                               "the reference's quirk 'no -gpu flag => CPU' (config.py:65, base_model.py:17) does not apply")
+        self.netG = self.set_device(networks.define_diffusion(opt))
+        self.schedule_phase = None
+        self.months = []
+        self.set_loss()
+        self.set_new_noise_schedule(opt['model']['beta_schedule']['train'], schedule_phase='train')
+        if self.opt['phase'] == 'train':
+            self.netG.train()
+            if opt['model']['finetune_norm']:
+                optim_params = []
+                for k, v in self.netG.named_parameters():
+                    v.requires_grad = False
+                    if k.find('transformer') >= 0:
+                        v.requires_grad = True
+                        v.data.zero_()
+                        optim_params.append(v)
+            else:
+                optim_params = list(self.netG.parameters())
+            self.optG = torch.optim.Adam(optim_params, lr=opt['train']["optimizer"]["lr"])
+            self.log_dict = OrderedDict()
+        self.load_network()
+        self.print_network()
+
+    def _net(self):
+        return self.netG.module if isinstance(self.netG, nn.DataParallel) else self.netG
+
+    def feed_data(self, data: tuple) -> None:
+        self.data, self.months = self.set_device(data[0]), data[1]
+
+    def optimize_parameters(self):
+        """reference :61-69: zero_grad, loss / numel, backward, Adam step."""
+        self.optG.zero_grad()
+        l_pix = self.netG(self.data)
+        b, c, h, w = self.data['HR'].shape
+        l_pix = l_pix.sum() / int(b * c * h * w)
+        if not l_pix.requires_grad:
+            raise NotImplementedError("the backward pass of the CUDA denoiser is not implemented yet (forward loss = "
+                                      "%.6f); see DESIGN.md 'training scope'" % float(l_pix))
+        l_pix.backward()
+        self.optG.step()
+        self.log_dict['l_pix'] = l_pix.item()
+
+    def generate_sr(self, continous=False):
+        self.netG.eval()
+        with torch.no_grad():
+            self.SR = self._net().super_resolution(self.data, continous)
+            self.SR = self.SR.unsqueeze(0) if len(self.SR.size()) == 3 else self.SR
+        self.netG.train()
+
+    def sample(self, batch_size=1, continous=False):
+        self.netG.eval()
+        with torch.no_grad():
+            self.SR = self._net().sample(batch_size, continous)
+        self.netG.train()
+
+    def set_loss(self):
+        self._net().set_loss(self.device)
+
+    def set_new_noise_schedule(self, schedule_opt, schedule_phase='train'):
+        if self.schedule_phase is None or self.schedule_phase != schedule_phase:
+            self.schedule_phase = schedule_phase
+            self._net().set_new_noise_schedule(schedule_opt, self.device)
+
+    def get_current_log(self):
+        return self.log_dict
+
+    def get_images(self, need_LR=True, sample=False):
+        out = OrderedDict()
+        if sample:
+            out['SAM'] = self.SR.detach().float().cpu()
+        else:
+            out['SR'] = self.SR.detach().float().cpu()
+            out['INF'] = self.data['SR'].detach().float().cpu()
+            out['HR'] = self.data['HR'].detach().float().cpu()
+            if need_LR and 'LR' in self.data:
+                out['LR'] = self.data['LR'].detach().float().cpu()
+            else:
+                out['LR'] = out['INF']
+        return out
+
+    def print_network(self):
+        s, n = self.get_network_description(self.netG)
+        logger.info('Network G structure: {}, with parameters: {:,d}'.format(self._net().__class__.__name__, n))
+        logger.info(s)
+
+    def save_network(self, epoch, iter_step):
+        gen_path = os.path.join(self.opt['path']['checkpoint'], 'I{}_E{}_gen.pth'.format(iter_step, epoch))
+        opt_path = os.path.join(self.opt['path']['checkpoint'], 'I{}_E{}_opt.pth'.format(iter_step, epoch))
+        state = {k: v.cpu() for k, v in self._net().state_dict().items()}
+        torch.save(state, gen_path)
+        torch.save({'epoch': epoch, 'iter': iter_step, 'scheduler': None, 'optimizer': self.optG.state_dict()}, opt_path)
+        logger.info('Saved model in [{:s}] ...'.format(gen_path))
+
+    def load_network(self):
+        load_path = self.opt['path']['resume_state']
+        if load_path is None:
+            return
+        logger.info('Loading pretrained model for G [{:s}] ...'.format(load_path))
+        self._net().load_state_dict(torch.load('{}_gen.pth'.format(load_path), map_location=self.device),
+                                    strict=(not self.opt['model']['finetune_norm']))
+        if self.opt['phase'] == 'train':
+            o = torch.load('{}_opt.pth'.format(load_path), map_location=self.device)
+            self.optG.load_state_dict(o['optimizer'])
+            self.begin_step = o['iter']
+            self.begin_epoch = o['epoch']
+
+    def prepare_to_train(self) -> None:
+        self.set_new_noise_schedule(self.opt['model']['beta_schedule']['train'], schedule_phase='train')
+
+    def prepare_to_eval(self) -> None:
+        self.set_new_noise_schedule(self.opt['model']['beta_schedule']['val'], schedule_phase='val')
+
+    def get_months(self) -> list:
+        return self.months
+
+    def get_loaded_iter(self):
+        return self.begin_step
+
+    def get_loaded_epoch(self):
+        return self.begin_epoch

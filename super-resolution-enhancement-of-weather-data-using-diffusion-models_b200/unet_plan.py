@@ -1,0 +1,469 @@
+"""UNetPlan -- the launch schedule of one denoiser call (reference resdiff/unet.py:121-177, srdiff/unet.py:112-141).
+
+Built once per (UNet module, local batch, precision): packs the reference-layout fp32 parameters into kernel
+layouts, allocates every activation buffer (NHWC, skip tensors written straight into the channel slice of the
+up-block's concat buffer, so ``torch.cat`` never happens), and then replays a fixed sequence of C-ABI calls per step.
+Because the sequence and all pointers are fixed, a whole reverse step can be captured in a CUDA graph (``sampler.py``).
+
+Hoisting -- results identical, work done once instead of T times:
+  * condition-only: FD splitter FFT branch (lf, hf), Haar detail queries and the HF-CA ``q`` convolutions,
+    SRDiff's ``cond_proj`` transposed convolution                       -> ``set_condition``
+  * level-only: positional encoding, noise MLP, the 27 FeatureWiseAffine projections and ``fd_spliter.noise_func``
+    for all T levels                                                    -> ``set_level_table`` (sampling)
+"""
+import math
+
+import torch
+
+from . import _native as nat
+from .engine import Act, Engine
+
+
+class _L:
+    """Plain record."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def _is_res(m):
+    return type(m).__name__ == "ResnetBlocWithAttn"
+
+
+class UNetPlan:
+    def __init__(self, net, batch, device, precision="bf16", strict_tc=False):
+        self.net = net
+        self.B = int(batch)
+        self.eng = Engine(device, precision, strict_tc=strict_tc)
+        self.kind = "resdiff" if hasattr(net, "fd_spliter") else "srdiff"
+        self.C_img = net.image_channels
+        self.H, self.W = net.image_height, net.image_width
+        self.inner = net.inner_channel
+        self.groups = net.norm_groups
+        self.time_act = nat.ACT_MISH if net.time_act == "mish" else nat.ACT_SWISH
+        self._wver = None
+        self._structure()
+        self._buffers()
+        self.refresh_weights()
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # structure: layer records with shapes, projection offsets
+    # ------------------------------------------------------------------------------------------------------------------
+    def _res_record(self, mod, name, cin, cout, h, w):
+        rb = mod.res_block
+        rec = _L(kind="res", mod=mod, name=name, cin=cin, cout=cout, h=h, w=w, attn=mod.with_attn,
+                 has_res_conv=not isinstance(rb.res_conv, torch.nn.Identity), proj_off=self.P)
+        self.P += cout
+        return rec
+
+    def _structure(self):
+        net = self.net
+        self.P = 0                       # width of the concatenated level projection (all FeatureWiseAffine linears)
+        h, w = self.H, self.W
+        downs, feat_shapes = [], []
+        stem = net.downs[0]
+        c = stem.out_channels
+        downs.append(_L(kind="stem", mod=stem, name="downs.0", cin=stem.in_channels, cout=c, h=h, w=w))
+        feat_shapes.append((c, h, w))
+        for i, m in enumerate(list(net.downs)[1:], start=1):
+            if _is_res(m):
+                cout = m.res_block.block1.block[3].out_channels
+                downs.append(self._res_record(m, "downs.%d" % i, c, cout, h, w))
+                c = cout
+            else:
+                h, w = h // 2, w // 2
+                downs.append(_L(kind="down", mod=m, name="downs.%d" % i, cin=c, cout=c, h=h, w=w))
+            feat_shapes.append((c, h, w))
+        mids = [self._res_record(m, "mid.%d" % i, c, c, h, w) for i, m in enumerate(net.mid)]
+        ups = []
+        fs = list(feat_shapes)
+        for i, m in enumerate(net.ups):
+            if _is_res(m):
+                sc, sh, sw = fs.pop()
+                assert (sh, sw) == (h, w)
+                cout = m.res_block.block1.block[3].out_channels
+                rec = self._res_record(m, "ups.%d" % i, c + sc, cout, h, w)
+                rec.cx, rec.cs = c, sc
+                ups.append(rec)
+                c = cout
+            else:
+                ups.append(_L(kind="up", mod=m, name="ups.%d" % i, cin=c, cout=c, h=h * 2, w=w * 2))
+                h, w = h * 2, w * 2
+        self.downs, self.mids, self.ups, self.feat_shapes = downs, mids, ups, feat_shapes
+        self.final_cin = c
+        if self.kind == "resdiff":
+            self.ne_off = self.P         # fd_spliter.noise_func output (W values) lives at the tail of the projection
+            self.P += self.W
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # buffers
+    # ------------------------------------------------------------------------------------------------------------------
+    def _buffers(self):
+        e, B = self.eng, self.B
+        bf = e.mode == "bf16"
+        # concat buffers of the up path: ups res-block j reads cat([x, feats.pop()])
+        up_res = [r for r in self.ups if r.kind == "res"]
+        for r in up_res:
+            r.cat = e.new_act(B, r.h, r.w, r.cx + r.cs)
+        nfeat = len(self.feat_shapes)
+        assert nfeat == len(up_res)
+        feat_dst = [None] * nfeat
+        for j, r in enumerate(up_res):
+            feat_dst[nfeat - 1 - j] = r.cat.slice(r.cx, r.cs)
+        # destination of each layer's main-path output
+        stats_elems = 0
+        max_scores = 0
+
+        def res_scratch(r, y):
+            nonlocal stats_elems, max_scores
+            r.y = y
+            r.a1 = e.new_act(B, r.h, r.w, r.cin)
+            r.hbuf = e.new_act(B, r.h, r.w, r.cout)
+            r.a2 = e.new_act(B, r.h, r.w, r.cout)
+            r.st1 = stats_elems; stats_elems += B * r.cin * 2
+            r.st2 = stats_elems; stats_elems += B * r.cout * 2
+            if r.attn:
+                n = r.h * r.w
+                r.rbuf = e.new_act(B, r.h, r.w, r.cout)
+                r.nbuf = e.new_act(B, r.h, r.w, r.cout)
+                r.qk = e.new_act(B, r.h, r.w, 2 * r.cout)
+                r.vT = e.empty((B, r.cout, n))
+                r.obuf = e.new_act(B, r.h, r.w, r.cout)
+                r.st3 = stats_elems; stats_elems += B * r.cout * 2
+                max_scores = max(max_scores, B * n * n)
+
+        # down path
+        hf_i = 0
+        self.hfca = []
+        for i, r in enumerate(self.downs):
+            if r.kind == "stem":
+                cpad = 64 if bf else r.cin
+                r.cin_pad = max(cpad, r.cin)
+                r.xin = e.new_act(B, r.h, r.w, r.cin_pad, zero=True)
+                r.y = feat_dst[i]
+            elif r.kind == "res":
+                res_scratch(r, feat_dst[i])
+            else:
+                if self.kind == "resdiff":
+                    # main path continues with the plain strided-conv output; the skip is its HF-guided attention
+                    r.y = e.new_act(B, r.h, r.w, r.cout)
+                    n = r.h * r.w
+                    ca = _L(mod=self.net.hf_ca_list[hf_i], c=r.cout, h=r.h, w=r.w, x=r.y, y=feat_dst[i], level=hf_i)
+                    ca.nbuf = e.new_act(B, r.h, r.w, r.cout)
+                    ca.kbuf = e.new_act(B, r.h, r.w, r.cout)
+                    ca.vT = e.empty((B, r.cout, n))
+                    ca.obuf = e.new_act(B, r.h, r.w, r.cout)
+                    ca.q = e.new_act(B, r.h, r.w, r.cout)
+                    ca.qimg = e.new_act(B, r.h, r.w, self.C_img, dt=nat.F32)
+                    ca.st = stats_elems; stats_elems += B * r.cout * 2
+                    max_scores = max(max_scores, B * n * n)
+                    r.ca = ca
+                    self.hfca.append(ca)
+                    hf_i += 1
+                else:
+                    r.y = feat_dst[i]
+        # mid: mid.0 -> temp, mid.1 -> x slot of the first up concat buffer
+        res_scratch(self.mids[0], e.new_act(B, self.mids[0].h, self.mids[0].w, self.mids[0].cout))
+        res_scratch(self.mids[1], up_res[0].cat.slice(0, up_res[0].cx))
+        # up path: each layer writes into the x slot of the next res block's concat buffer
+        for k, r in enumerate(self.ups):
+            nxt = next((q for q in self.ups[k + 1:] if q.kind == "res"), None) if k + 1 < len(self.ups) else None
+            following = self.ups[k + 1] if k + 1 < len(self.ups) else None
+            if following is not None and following.kind == "res":
+                dst = following.cat.slice(0, following.cx)
+            else:
+                dst = e.new_act(B, r.h, r.w, r.cout)
+            if r.kind == "res":
+                res_scratch(r, dst)
+            else:
+                r.y = dst
+            del nxt
+        # fix-up: an Upsample layer is fed by the res block before it (plain buffer) and feeds the next res block
+        # head
+        self.final_a = e.new_act(B, self.H, self.W, self.final_cin)
+        self.st_final = stats_elems; stats_elems += B * self.final_cin * 2
+        self.eps_nhwc = e.new_act(B, self.H, self.W, self.C_img, dt=nat.F32)
+        self.eps = self.eps_nhwc.buf.view(B, self.C_img, self.H, self.W) if self.C_img == 1 else \
+            e.empty((B, self.C_img, self.H, self.W), torch.float32)
+        self.stats = torch.zeros(stats_elems, device=e.device, dtype=torch.float64)
+        self.scores = e.empty((max_scores,), torch.float32) if max_scores else None
+        self.probs = e.empty((max_scores,)) if max_scores else None
+        # level embedding
+        self.cur_proj = e.empty((B, self.P), torch.float32)
+        self.cur_temb = e.empty((B, self.inner), torch.float32)
+        self.levels = e.empty((B,), torch.float32)
+        self.proj_table = None
+        # condition state
+        self.cond = e.empty((B, self.C_img, self.H, self.W), torch.float32)
+        self.x_t = e.empty((B, self.C_img, self.H, self.W), torch.float32)
+        if self.kind == "resdiff":
+            self.lf = e.empty((B, self.C_img, self.H, self.W), torch.float32)
+            self.hf = e.empty((B, self.C_img, self.H, self.W), torch.float32)
+            self.gate = e.empty((B, self.C_img, self.W), torch.float32)
+            nb = nat.call("wsr_fd_precompute_workspace_bytes", B, self.C_img, self.H, self.W)
+            self.fd_work = e.empty((nb,), torch.uint8)
+            tot = sum(B * self.C_img * (self.H >> (j + 1)) * (self.W >> (j + 1)) for j in range(4))
+            self.haar_out = e.empty((tot,), torch.float32)
+            self.haar_work = e.empty((B * self.C_img * self.H * self.W // 2 + 16,), torch.float32)
+        else:
+            self.cond_feat = e.new_act(B, self.H // 4, self.W // 4, self.net.cond_proj.in_channels)
+            self.cond_up = e.new_act(B, self.H, self.W, self.net.cond_proj.out_channels)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # weights
+    # ------------------------------------------------------------------------------------------------------------------
+    def _weights_version(self):
+        return tuple(p._version for p in self.net.parameters()) + tuple(p.data_ptr() for p in self.net.parameters())
+
+    def refresh_weights(self):
+        v = self._weights_version()
+        if v == self._wver:
+            return
+        self._wver = v
+        e = self.eng
+        with torch.no_grad():
+            proj_w, proj_b = [], []
+
+            def pack_res(r):
+                rb = r.mod.res_block
+                gn1, conv1 = rb.block1.block[0], rb.block1.block[3]
+                gn2, conv2 = rb.block2.block[0], rb.block2.block[3]
+                r.g1, r.b1 = e.f32(gn1.weight), e.f32(gn1.bias)
+                r.g2, r.b2 = e.f32(gn2.weight), e.f32(gn2.bias)
+                r.conv1 = e.pack_conv(conv1.weight, conv1.bias)
+                r.conv2 = e.pack_conv(conv2.weight, conv2.bias)
+                if r.has_res_conv:
+                    r.resw = e.pack_conv(rb.res_conv.weight, None)
+                    r.bias2 = e.f32(conv2.bias + rb.res_conv.bias)
+                lin = rb.noise_func.noise_func[0]
+                proj_w.append(e.f32(lin.weight)); proj_b.append(e.f32(lin.bias))
+                if r.attn:
+                    at = r.mod.attn
+                    r.g3, r.b3 = e.f32(at.norm.weight), e.f32(at.norm.bias)
+                    wqkv = at.qkv.weight
+                    cc = r.cout
+                    r.wqk = e.pack_conv(wqkv[:2 * cc], None)
+                    r.wv = e.pack_rows(wqkv[2 * cc:].reshape(cc, cc))
+                    r.wout = e.pack_conv(at.out.weight, at.out.bias)
+
+            for r in self.downs:
+                if r.kind == "stem":
+                    r.conv = e.pack_conv(r.mod.weight, r.mod.bias, cin_pad=r.cin_pad)
+                elif r.kind == "res":
+                    pack_res(r)
+                else:
+                    r.conv = e.pack_conv(r.mod.conv.weight, r.mod.conv.bias)
+                    if self.kind == "resdiff":
+                        ca, m = r.ca, r.ca.mod
+                        ca.g, ca.b = e.f32(m.norm.weight), e.f32(m.norm.bias)
+                        cc = ca.c
+                        ca.wk = e.pack_conv(m.kv.weight[:cc], None)
+                        ca.wv = e.pack_rows(m.kv.weight[cc:].reshape(cc, cc))
+                        ca.wout = e.pack_conv(m.out.weight, m.out.bias)
+                        ca.wq = self._pack_f32_conv(m.q.weight)
+            for r in self.mids:
+                pack_res(r)
+            for r in self.ups:
+                if r.kind == "res":
+                    pack_res(r)
+                else:
+                    r.conv = e.pack_conv(r.mod.conv.weight, r.mod.conv.bias)
+            fc = self.net.final_conv.block
+            self.gf, self.bf_ = e.f32(fc[0].weight), e.f32(fc[0].bias)
+            self.final = e.pack_conv(fc[3].weight, fc[3].bias, rows=64 if e.mode == "bf16" else None)
+            mlp = self.net.noise_level_mlp
+            self.mlp_w1, self.mlp_b1 = e.f32(mlp[1].weight), e.f32(mlp[1].bias)
+            self.mlp_w2, self.mlp_b2 = e.f32(mlp[3].weight), e.f32(mlp[3].bias)
+            if self.kind == "resdiff":
+                fd = self.net.fd_spliter
+                proj_w.append(e.f32(fd.noise_func.weight)); proj_b.append(e.f32(fd.noise_func.bias))
+                self.fd_n0, self.fd_n2 = e.f32(fd.noise_resSE.fc[0].weight), e.f32(fd.noise_resSE.fc[2].weight)
+                self.fd_s0, self.fd_s2 = e.f32(fd.sigma_resSE.fc[0].weight), e.f32(fd.sigma_resSE.fc[2].weight)
+                self.fd_h0, self.fd_h2 = e.f32(fd.HF_guided_resSE.fc[0].weight), e.f32(fd.HF_guided_resSE.fc[2].weight)
+                self.fd_ctw = e.f32(fd.channel_transform.weight.reshape(fd.channel_transform.out_channels, -1))
+                self.fd_ctb = e.f32(fd.channel_transform.bias)
+                self.fd_hidden = self.fd_n0.shape[0]
+            else:
+                cp = self.net.cond_proj
+                self.cp_w = e.empty((64, cp.out_channels, cp.in_channels))
+                w = e.f32(cp.weight)
+                nat.call("wsr_pack_convT_weight", w.data_ptr(), cp.in_channels, cp.out_channels, 8, 8, self.cp_w.data_ptr(), e.dt, e.stream)
+                self.cp_b = e.f32(cp.bias)
+                e._keep.append(w)
+            self.proj_w = torch.cat(proj_w, 0).contiguous()
+            self.proj_b = torch.cat(proj_b, 0).contiguous()
+            assert self.proj_w.shape == (self.P, self.inner), (self.proj_w.shape, self.P)
+        self.proj_table = None
+        torch.cuda.current_stream(e.device).synchronize()
+        e._keep.clear()
+
+    def _pack_f32_conv(self, weight):
+        """fp32-packed conv weight (used for the 1-channel Haar query convolution, kept in fp32 in both modes)."""
+        e = self.eng
+        w = e.f32(weight)
+        Cout, Cin, KH, KW = w.shape
+        from .engine import PackedConv
+        pc = PackedConv()
+        pc.Cout, pc.Cin, pc.k, pc.Cin_pad, pc.rows, pc.bias = Cout, Cin, KH, Cin, Cout, None
+        pc.w = e.empty((KH * KW, Cout, Cin), torch.float32)
+        nat.call("wsr_pack_conv_weight", w.data_ptr(), Cout, Cin, KH, KW, pc.w.data_ptr(), nat.F32, Cout, Cin, e.stream)
+        e._keep.append(w)
+        return pc
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # condition-only and level-only precompute
+    # ------------------------------------------------------------------------------------------------------------------
+    def set_condition(self, cond):
+        """resdiff: cond = x_in['SR'] (B,C,H,W).  srdiff: cond = cat(feas[2::3], 1) (B,384,H/4,W/4)."""
+        e, B = self.eng, self.B
+        st = e.stream
+        if self.kind == "resdiff":
+            self.cond.copy_(cond.to(torch.float32))
+            nat.call("wsr_fd_precompute", self.cond.data_ptr(), B, self.C_img, self.H, self.W, self.fd_s0.data_ptr(),
+                     self.fd_s2.data_ptr(), self.fd_h0.data_ptr(), self.fd_h2.data_ptr(), self.fd_ctw.data_ptr(),
+                     self.fd_ctb.data_ptr(), self.fd_ctw.shape[0], self.lf.data_ptr(), self.hf.data_ptr(),
+                     self.fd_work.data_ptr(), st)
+            nat.call("wsr_haar_detail_sums", self.cond.data_ptr(), B, self.C_img, self.H, self.W, 4, self.haar_out.data_ptr(),
+                     self.haar_work.data_ptr(), st)
+            off = 0
+            for ca in self.hfca:
+                n = B * self.C_img * ca.h * ca.w
+                j = ca.level
+                assert (ca.h, ca.w) == (self.H >> (j + 1), self.W >> (j + 1))
+                nat.call("wsr_nchw_to_nhwc", self.haar_out.data_ptr() + 4 * off, B, self.C_img, ca.h, ca.w, ca.qimg.ptr,
+                         nat.F32, ca.qimg.ld, st)
+                e.conv(ca.qimg, ca.wq, ca.q, bias=False, force_simt=True)
+                off += n
+        else:
+            src = cond.to(torch.float32).contiguous()
+            e.nchw_to_act(src, self.cond_feat)
+            nat.call("wsr_conv_transpose_k8s4", self.cond_feat.ptr, self.cond_feat.dt, B, self.cond_feat.H, self.cond_feat.W,
+                     self.cond_feat.C, self.cond_feat.ld, self.cp_w.data_ptr(), self.cp_b.data_ptr(), self.cond_up.C,
+                     self.cond_up.ptr, self.cond_up.dt, self.cond_up.ld, st)
+
+    def _embed(self, levels, n_rows, temb, proj):
+        st = self.eng.stream
+        nat.call("wsr_noise_embed", levels.data_ptr(), n_rows, self.inner, self.mlp_w1.data_ptr(), self.mlp_b1.data_ptr(),
+                 self.mlp_w2.data_ptr(), self.mlp_b2.data_ptr(), self.time_act, temb.data_ptr(), st)
+        nat.call("wsr_linear_rows", temb.data_ptr(), n_rows, self.inner, self.proj_w.data_ptr(), self.proj_b.data_ptr(),
+                 self.P, proj.data_ptr(), st)
+
+    def set_levels(self, levels):
+        """Per-sample continuous noise levels (B,) -- the training / generic ``forward`` path."""
+        self.levels.copy_(levels.to(torch.float32))
+        self._embed(self.levels, self.B, self.cur_temb, self.cur_proj)
+
+    def set_level_table(self, levels_T):
+        """All T levels of a sampling schedule: proj_table[r] is the projection of level r (computed once)."""
+        e = self.eng
+        lv = levels_T.to(device=e.device, dtype=torch.float32).contiguous()
+        T = lv.numel()
+        self.table_levels = lv
+        self.temb_table = e.empty((T, self.inner), torch.float32)
+        self.proj_table = e.empty((T, self.P), torch.float32)
+        self._embed(lv, T, self.temb_table, self.proj_table)
+
+    def select_level_row(self, row_index_dev):
+        """cur_proj[b] = proj_table[*row_index] for every b (device-side index: CUDA-graph friendly)."""
+        nat.call("wsr_broadcast_row", self.proj_table.data_ptr(), self.P, row_index_dev.data_ptr(), self.B,
+                 self.cur_proj.data_ptr(), self.eng.stream)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # the denoiser
+    # ------------------------------------------------------------------------------------------------------------------
+    def denoise(self, x_t):
+        """Generic entry: x_t (B,C,H,W) fp32 NCHW -> eps_hat (B,C,H,W) fp32 (a fresh tensor)."""
+        self.x_t.copy_(x_t.to(torch.float32))
+        self.run(self.x_t)
+        return self.eps.clone()
+
+    def _stat(self, off, n):
+        return self.stats[off:off + n]
+
+    def _rowvec(self, r):
+        return self.cur_proj.data_ptr() + 4 * r.proj_off
+
+    def _res_block(self, r, x, extra_res=None):
+        e, B, G = self.eng, self.B, self.groups
+        SW = nat.ACT_SWISH
+        s1 = self._stat(r.st1, B * r.cin * 2)
+        e.gn_stats(x, s1)
+        e.gn_apply(x, s1, r.g1, r.b1, G, SW, r.a1)
+        e.conv(r.a1, r.conv1, r.hbuf, rowvec=self._rowvec(r), rowvec_ld=self.P)
+        s2 = self._stat(r.st2, B * r.cout * 2)
+        e.gn_stats(r.hbuf, s2)
+        e.gn_apply(r.hbuf, s2, r.g2, r.b2, G, SW, r.a2)
+        dst = r.rbuf if r.attn else r.y
+        er = None if r.attn else extra_res
+        if r.has_res_conv:
+            e.conv(r.a2, r.conv2, dst, x2=x, w2=r.resw, extra_bias=r.bias2, res2=er)
+        else:
+            e.conv(r.a2, r.conv2, dst, res=x, res2=er)
+        if r.attn:
+            s3 = self._stat(r.st3, B * r.cout * 2)
+            e.gn_stats(r.rbuf, s3)
+            e.gn_apply(r.rbuf, s3, r.g3, r.b3, G, nat.ACT_NONE, r.nbuf)
+            e.conv(r.nbuf, r.wqk, r.qk, bias=False)
+            self._v_transposed(r.wv, r.nbuf, r.vT)
+            n = r.h * r.w
+            e.attention(r.qk.slice(0, r.cout), r.qk.slice(r.cout, r.cout), r.vT, r.obuf,
+                        self.scores[:B * n * n], self.probs[:B * n * n])
+            e.conv(r.obuf, r.wout, r.y, res=r.rbuf, res2=extra_res)
+        return r.y
+
+    def _v_transposed(self, wv, nact, vT):
+        """vT[b][c][pix] = sum_k Wv[c][k] * n[b][pix][k]  (V produced already transposed = K-major for P*V)."""
+        e = self.eng
+        cc, n = wv.shape[0], nact.H * nact.W
+        e.gemm(wv.data_ptr(), e.dt, (0, cc, 1), nact.ptr, nact.dt, (n * nact.ld, nact.ld, 1),
+               vT.data_ptr(), e.dt, (cc * n, n, 1), self.B, cc, n, cc)
+
+    def _hf_ca(self, ca):
+        e, B = self.eng, self.B
+        s = self._stat(ca.st, B * ca.c * 2)
+        e.gn_stats(ca.x, s)
+        e.gn_apply(ca.x, s, ca.g, ca.b, 32, nat.ACT_NONE, ca.nbuf)       # norm_groups fixed at 32 (guided_cross_attention.py:15)
+        e.conv(ca.nbuf, ca.wk, ca.kbuf, bias=False)
+        self._v_transposed(ca.wv, ca.nbuf, ca.vT)
+        n = ca.h * ca.w
+        e.attention(ca.q, ca.kbuf, ca.vT, ca.obuf, self.scores[:B * n * n], self.probs[:B * n * n])
+        e.conv(ca.obuf, ca.wout, ca.y, res=ca.x)
+
+    def run(self, x_t):
+        """One denoiser call on the current condition / level projection.  x_t: fp32 NCHW device tensor (B,C,H,W).
+        Leaves eps_hat in ``self.eps`` (fp32 NCHW)."""
+        e, B = self.eng, self.B
+        st = e.stream
+        nat.call("wsr_fill_zero", self.stats.data_ptr(), self.stats.numel() * 8, st)
+        stem = self.downs[0]
+        if self.kind == "resdiff":
+            nat.call("wsr_fd_gate", self.cur_proj.data_ptr() + 4 * self.ne_off, self.P, 0, B, self.C_img, self.W,
+                     self.fd_n0.data_ptr(), self.fd_n2.data_ptr(), self.fd_hidden, self.gate.data_ptr(), st)
+            nat.call("wsr_stem_assemble", x_t.data_ptr(), self.cond.data_ptr(), self.gate.data_ptr(), self.lf.data_ptr(),
+                     self.hf.data_ptr(), B, self.C_img, self.H, self.W, stem.xin.ptr, stem.xin.dt, stem.xin.ld, st)
+        else:
+            nat.call("wsr_nchw_to_nhwc", x_t.data_ptr(), B, self.C_img, self.H, self.W, stem.xin.ptr, stem.xin.dt, stem.xin.ld, st)
+        x = e.conv(stem.xin, stem.conv, stem.y)
+        for i, r in enumerate(self.downs[1:], start=1):
+            extra = self.cond_up if (self.kind == "srdiff" and i == 2) else None
+            if r.kind == "res":
+                x = self._res_block(r, x, extra_res=extra)
+            else:
+                x = e.conv(x, r.conv, r.y, stride=2, res=extra)
+                if self.kind == "resdiff":
+                    self._hf_ca(r.ca)
+        for r in self.mids:
+            x = self._res_block(r, x)
+        for r in self.ups:
+            if r.kind == "res":
+                x = self._res_block(r, r.cat)
+            else:
+                x = e.conv(x, r.conv, r.y, upsample=True)
+        sf = self._stat(self.st_final, B * self.final_cin * 2)
+        e.gn_stats(x, sf)
+        e.gn_apply(x, sf, self.gf, self.bf_, self.groups, nat.ACT_SWISH, self.final_a)
+        e.conv(self.final_a, self.final, self.eps_nhwc)
+        if self.C_img != 1:
+            nat.call("wsr_nhwc_to_nchw", self.eps_nhwc.ptr, nat.F32, self.eps_nhwc.ld, B, self.C_img, self.H, self.W,
+                     self.eps.data_ptr(), st)
+        return self.eps

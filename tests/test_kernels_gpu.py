@@ -1,0 +1,271 @@
+"""GPU unit tests of the individual kernels, called through the C ABI (ctypes), against plain PyTorch fp32 on the same
+device.  Tolerances: fp32 SIMT kernels 2e-5 rel-L2 (summation order); bf16 tcgen05 kernels are compared with the SIMT
+kernel on the SAME bf16 inputs (both accumulate in fp32) at 2e-3 rel-L2 after bf16 output rounding."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import wsr
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+nat = wsr.pkg.native
+engine_mod = wsr.sub("engine")
+Engine, Act = engine_mod.Engine, engine_mod.Act
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _nhwc(x, eng, ld=None, coff=0, dt=None):
+    """NCHW fp32 tensor -> Act (optionally embedded at channel offset coff of a wider buffer)."""
+    N, C, H, W = x.shape
+    full = eng.new_act(N, H, W, ld or C, dt=dt, zero=True)
+    a = full.slice(coff, C)
+    eng.nchw_to_act(x, a)
+    return a
+
+
+def _ref_conv(x, w, b, stride=1, upsample=False):
+    if upsample:
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+    return F.conv2d(x, w, b, stride=stride, padding=(w.shape[-1] - 1) // 2)
+
+
+CONV_CASES = [
+    # N, Cin, Cout, H, W, k, stride, upsample
+    (2, 64, 64, 16, 32, 3, 1, False),
+    (1, 128, 64, 8, 16, 3, 1, False),
+    (2, 64, 128, 16, 32, 1, 1, False),
+    (2, 64, 64, 16, 32, 3, 2, False),
+    (1, 64, 64, 8, 16, 3, 1, True),
+    (3, 192, 256, 4, 8, 3, 1, False),
+    (2, 64, 64, 2, 4, 3, 1, False),
+    (1, 64, 128, 32, 256, 3, 1, False),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_simt_fp32_vs_torch(case):
+    N, Cin, Cout, H, W, k, stride, up = case
+    torch.manual_seed(0)
+    dev = _dev()
+    eng = Engine(dev, "fp32")
+    x = torch.randn(N, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, k, k, device=dev) / math.sqrt(Cin * k * k)
+    b = torch.randn(Cout, device=dev)
+    ref = _ref_conv(x, w, b, stride, up)
+    pc = eng.pack_conv(w, b)
+    y = eng.new_act(N, ref.shape[2], ref.shape[3], Cout)
+    eng.conv(_nhwc(x, eng), pc, y, stride=stride, upsample=up)
+    assert rel_l2(y.to_nchw(eng), ref) < 2e-5
+
+
+def test_conv_simt_odd_channels_and_epilogue():
+    torch.manual_seed(1)
+    dev = _dev()
+    eng = Engine(dev, "fp32")
+    N, Cin, Cout, H, W = 2, 5, 7, 8, 16
+    x = torch.randn(N, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, 3, 3, device=dev) * 0.2
+    b = torch.randn(Cout, device=dev)
+    rv = torch.randn(N, 11, device=dev)
+    res = torch.randn(N, Cout, H, W, device=dev)
+    x2 = torch.randn(N, 3, H, W, device=dev)
+    w2 = torch.randn(Cout, 3, 1, 1, device=dev)
+    ref = F.leaky_relu(F.conv2d(x, w, b, padding=1) + F.conv2d(x2, w2) + rv[:, 2:2 + Cout, None, None], 0.2) * 0.5 + 0.25 * res
+    y = eng.new_act(N, H, W, Cout, ld=16).slice(4, Cout)
+    eng.conv(_nhwc(x, eng, ld=8, coff=1), eng.pack_conv(w, b), y, rowvec=rv.data_ptr() + 8, rowvec_ld=11,
+             act=nat.ACT_LRELU02, out_scale=0.5, res=_nhwc(res, eng), res_scale=0.25, x2=_nhwc(x2, eng), w2=eng.pack_conv(w2, None))
+    assert rel_l2(y.to_nchw(eng), ref) < 2e-5
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_tc_vs_simt(case):
+    N, Cin, Cout, H, W, k, stride, up = case
+    torch.manual_seed(2)
+    dev = _dev()
+    eng = Engine(dev, "bf16")
+    assert eng.use_tc, "tcgen05 path needs an sm_100 device"
+    x = torch.randn(N, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, k, k, device=dev) / math.sqrt(Cin * k * k)
+    b = torch.randn(Cout, device=dev)
+    rv = torch.randn(N, Cout, device=dev)
+    OH, OW = (H * (2 if up else 1)) // stride, (W * (2 if up else 1)) // stride
+    res = torch.randn(N, Cout, OH, OW, device=dev)
+    pc = eng.pack_conv(w, b)
+    xa, ra = _nhwc(x, eng), _nhwc(res, eng)
+    y_tc = eng.new_act(N, OH, OW, Cout, zero=True)
+    y_si = eng.new_act(N, OH, OW, Cout, dt=nat.F32, zero=True)
+    kw = dict(stride=stride, upsample=up, rowvec=rv.data_ptr(), rowvec_ld=Cout, res=ra)
+    eng.conv(xa, pc, y_tc, **kw)
+    eng.conv(xa, pc, y_si, force_simt=True, **kw)
+    assert eng.n_tc == 1 and eng.n_simt == 1
+    torch.cuda.synchronize()
+    err = rel_l2(y_tc.to_nchw(eng), y_si.to_nchw(eng))
+    assert err < 4e-3, err
+    # and against fp32 torch on the bf16-rounded operands
+    ref = _ref_conv(x.bfloat16().float(), w.bfloat16().float(), b, stride, up) + rv[:, :, None, None] + res.bfloat16().float()
+    assert rel_l2(y_si.to_nchw(eng), ref) < 1e-4
+
+
+def test_conv_tc_second_segment_slices_and_f32_out():
+    """fused 1x1 res_conv segment, channel-slice input/output pitches, fp32 output, Cout=1 with padded weight rows."""
+    torch.manual_seed(3)
+    dev = _dev()
+    eng = Engine(dev, "bf16")
+    N, Cin, Cout, H, W = 2, 128, 128, 16, 32
+    x = torch.randn(N, Cin, H, W, device=dev)
+    x2 = torch.randn(N, 192, H, W, device=dev)
+    w = torch.randn(Cout, Cin, 3, 3, device=dev) / math.sqrt(Cin * 9)
+    w2 = torch.randn(Cout, 192, 1, 1, device=dev) / math.sqrt(192)
+    b = torch.randn(Cout, device=dev)
+    xa = _nhwc(x, eng, ld=Cin + 64, coff=64)
+    x2a = _nhwc(x2, eng)
+    y_tc = eng.new_act(N, H, W, Cout + 64, zero=True).slice(64, Cout)
+    y_si = eng.new_act(N, H, W, Cout, dt=nat.F32)
+    pc, pc2 = eng.pack_conv(w, b), eng.pack_conv(w2, None)
+    eng.conv(xa, pc, y_tc, x2=x2a, w2=pc2)
+    eng.conv(xa, pc, y_si, x2=x2a, w2=pc2, force_simt=True)
+    assert eng.n_tc == 1
+    assert rel_l2(y_tc.to_nchw(eng), y_si.to_nchw(eng)) < 4e-3
+    # Cout = 1, fp32 output (the UNet head)
+    wf = torch.randn(1, Cin, 3, 3, device=dev) / math.sqrt(Cin * 9)
+    bfin = torch.randn(1, device=dev)
+    pcf = eng.pack_conv(wf, bfin, rows=64)
+    o_tc = eng.new_act(N, H, W, 1, dt=nat.F32)
+    o_si = eng.new_act(N, H, W, 1, dt=nat.F32)
+    eng.conv(xa, pcf, o_tc)
+    eng.conv(xa, pcf, o_si, force_simt=True)
+    assert eng.n_tc == 2
+    assert rel_l2(o_tc.to_nchw(eng), o_si.to_nchw(eng)) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(2, 512, 512, 64), (3, 128, 128, 512), (1, 256, 64, 128), (2, 100, 72, 64)])
+def test_gemm_tc_vs_simt(shape):
+    batch, M, N, K = shape
+    torch.manual_seed(4)
+    dev = _dev()
+    eng = Engine(dev, "bf16")
+    a = (torch.randn(batch, M, K, device=dev) / math.sqrt(K)).bfloat16()
+    b = torch.randn(batch, N, K, device=dev).bfloat16()
+    d_tc = torch.zeros(batch, M, N, device=dev, dtype=torch.float32)
+    d_si = torch.zeros(batch, M, N, device=dev, dtype=torch.float32)
+    for d, force in ((d_tc, False), (d_si, True)):
+        eng.gemm(a.data_ptr(), nat.BF16, (M * K, K, 1), b.data_ptr(), nat.BF16, (N * K, K, 1), d.data_ptr(), nat.F32,
+                 (M * N, N, 1), batch, M, N, K, alpha=0.5, force_simt=force)
+    assert eng.n_tc == 1 and eng.n_simt == 1
+    ref = 0.5 * torch.einsum("bmk,bnk->bmn", a.float(), b.float())
+    assert rel_l2(d_si, ref) < 2e-5
+    assert rel_l2(d_tc, ref) < 2e-5
+
+
+def test_gemm_tc_shared_a_transposed_out():
+    """V^T = Wv * n^T: A shared across the batch (a_sb = 0), output (B, C, pixels)."""
+    torch.manual_seed(5)
+    dev = _dev()
+    eng = Engine(dev, "bf16")
+    B, Cc, n = 2, 128, 512
+    wv = (torch.randn(Cc, Cc, device=dev) / math.sqrt(Cc)).bfloat16()
+    act = torch.randn(B, n, Cc, device=dev).bfloat16()
+    vT = torch.zeros(B, Cc, n, device=dev, dtype=torch.bfloat16)
+    eng.gemm(wv.data_ptr(), nat.BF16, (0, Cc, 1), act.data_ptr(), nat.BF16, (n * Cc, Cc, 1), vT.data_ptr(), nat.BF16,
+             (Cc * n, n, 1), B, Cc, n, Cc)
+    assert eng.n_tc == 1
+    ref = torch.einsum("ck,bpk->bcp", wv.float(), act.float())
+    assert rel_l2(vT.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 64, 16, 32), (2, 768, 4, 8), (1, 192, 8, 16)])
+def test_group_norm(mode, shape):
+    N, Cc, H, W = shape
+    torch.manual_seed(6)
+    dev = _dev()
+    eng = Engine(dev, mode)
+    x = torch.randn(N, Cc, H, W, device=dev) * 2 + 0.5
+    g, b = torch.randn(Cc, device=dev), torch.randn(Cc, device=dev)
+    xa = _nhwc(x, eng)
+    xr = xa.to_nchw(eng)
+    ref = F.group_norm(xr, 32, g, b, eps=1e-5)
+    ref = ref * torch.sigmoid(ref)
+    stats = torch.zeros(N * Cc * 2, device=dev, dtype=torch.float64)
+    eng.gn_stats(xa, stats)
+    y = eng.gn_apply(xa, stats, g, b, 32, nat.ACT_SWISH, eng.new_act(N, H, W, Cc))
+    assert rel_l2(y.to_nchw(eng), ref) < (2e-5 if mode == "fp32" else 4e-3)
+
+
+def test_softmax_rows():
+    torch.manual_seed(7)
+    dev = _dev()
+    eng = Engine(dev, "fp32")
+    s = torch.randn(37, 513, device=dev) * 4
+    p = torch.empty_like(s)
+    eng.softmax(s, nat.F32, 37, 513, 0.3, p, nat.F32)
+    assert rel_l2(p, torch.softmax(s * 0.3, -1)) < 1e-5
+
+
+def test_sampler_step_and_randn():
+    from oracle.schedule import ddpm_tables
+    from oracle.cases import LINEAR_1000
+    dev = _dev()
+    tabs, _ = ddpm_tables(LINEAR_1000)
+    order = ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2",
+             "posterior_log_variance_clipped")
+    tab = torch.stack([torch.from_numpy(tabs[k]) for k in order]).to(dev).contiguous()
+    torch.manual_seed(8)
+    n = 4096 + 3
+    x, eps, z = torch.randn(n, device=dev), torch.randn(n, device=dev), torch.randn(n, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    for t in (999, 500, 1, 0):
+        t_dev = torch.tensor([t], dtype=torch.int32, device=dev)
+        out = torch.empty_like(x)
+        nat.call("wsr_sampler_step", x.data_ptr(), eps.data_ptr(), nat.F32, z.data_ptr(), 0, 0, tab.data_ptr(), 1000,
+                 t_dev.data_ptr(), 1, out.data_ptr(), n, st)
+        x0 = (tab[0, t] * x - tab[1, t] * eps).clamp(-1, 1)
+        ref = tab[2, t] * x0 + tab[3, t] * x + (z * (0.5 * tab[4, t]).exp() if t > 0 else 0)
+        assert rel_l2(out, ref) < 1e-6
+    r = torch.empty(1 << 20, device=dev)
+    nat.call("wsr_randn", r.data_ptr(), r.numel(), 1234, 7, st)
+    assert abs(float(r.mean())) < 5e-3 and abs(float(r.std()) - 1) < 5e-3
+    r2 = torch.empty_like(r)
+    nat.call("wsr_randn", r2.data_ptr(), r2.numel(), 1234, 8, st)
+    assert abs(float((r * r2).mean())) < 5e-3
+
+
+def test_noise_embed_and_fd_and_haar_vs_oracle():
+    """level embedding, FD splitter precompute (4-D FFT over B,C,H,W) and Haar queries against the CPU oracle."""
+    from oracle import nets
+    from oracle.weights import seeded_randn
+    dev = _dev()
+    U = wsr.sub("models.diffusion_models.resdiff.unet").UNet
+    from oracle.cases import unet_cfg
+    from oracle.weights import fill_module
+    for c_img, B in ((1, 3), (3, 2)):
+        cfg = unet_cfg(32, 64, attn_res=(4,), c_img=c_img)
+        net = fill_module(U(in_channel=cfg["in_channel"], out_channel=c_img, norm_groups=32, inner_channel=64,
+                            channel_mults=cfg["channel_mults"], attn_res=cfg["attn_res"], res_blocks=2, dropout=0,
+                            image_height=32, image_width=64, image_channels=c_img, precision="fp32"), 5).to(dev)
+        sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+        cond = seeded_randn("c", (B, c_img, 32, 64), 1)
+        x_t = seeded_randn("x", (B, c_img, 32, 64), 2)
+        level = torch.linspace(0.2, 0.9, B).view(B, 1)
+        pl = net.plan(B, dev)
+        pl.set_condition(cond.to(dev))
+        pl.set_levels(level.view(B).to(dev))
+        t_ref = nets.noise_level_mlp(sd, level, 64)
+        assert rel_l2(pl.cur_temb.cpu(), t_ref.view(B, 64)) < 1e-5
+        ref = nets.fd_info_spliter(sd, "fd_spliter.", torch.cat([cond, x_t], 1), t_ref, c_img, 32, 64)
+        # channels: [x, cnn_x, denoise_x, lf, hf]
+        assert rel_l2(pl.lf.cpu(), ref[:, 3 * c_img:4 * c_img]) < 2e-5
+        assert rel_l2(pl.hf.cpu(), ref[:, 4 * c_img:5 * c_img]) < 2e-5
+        qs = nets.haar_detail_sums(cond, 4)
+        off = 0
+        for q in qs:
+            got = pl.haar_out[off:off + q.numel()].view(q.shape).cpu()
+            assert rel_l2(got, q) < 1e-6
+            off += q.numel()
