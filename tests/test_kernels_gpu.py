@@ -12,6 +12,10 @@ from conftest import rel_l2
 
 pytestmark = pytest.mark.gpu
 
+# the PyTorch side must be a true fp32 reference: no TF32 in cuDNN / cuBLAS
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 nat = wsr.pkg.native
 engine_mod = wsr.sub("engine")
 Engine, Act = engine_mod.Engine, engine_mod.Act
@@ -78,7 +82,7 @@ def test_conv_simt_odd_channels_and_epilogue():
     x2 = torch.randn(N, 3, H, W, device=dev)
     w2 = torch.randn(Cout, 3, 1, 1, device=dev)
     ref = F.leaky_relu(F.conv2d(x, w, b, padding=1) + F.conv2d(x2, w2) + rv[:, 2:2 + Cout, None, None], 0.2) * 0.5 + 0.25 * res
-    y = eng.new_act(N, H, W, Cout, ld=16).slice(4, Cout)
+    y = eng.new_act(N, H, W, 16).slice(4, Cout)
     eng.conv(_nhwc(x, eng, ld=8, coff=1), eng.pack_conv(w, b), y, rowvec=rv.data_ptr() + 8, rowvec_ld=11,
              act=nat.ACT_LRELU02, out_scale=0.5, res=_nhwc(res, eng), res_scale=0.25, x2=_nhwc(x2, eng), w2=eng.pack_conv(w2, None))
     assert rel_l2(y.to_nchw(eng), ref) < 2e-5
