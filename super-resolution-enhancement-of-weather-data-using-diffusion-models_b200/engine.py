@@ -69,8 +69,30 @@ class Engine:
         self.n_tc = 0
         self.n_simt = 0
         self._keep = []          # tensors that must outlive async launches
+        self.prof = None         # list of (name, flops, bytes, start_event, end_event) when profiling
 
     # ---- plumbing -------------------------------------------------------------------------------------------------
+    def call(self, name, *args, flops=0, nbytes=0, tag=None):
+        """nat.call with optional per-launch CUDA-event timing (bench.py roofline pass)."""
+        if self.prof is None:
+            return nat.call(name, *args)
+        s = torch.cuda.Event(enable_timing=True)
+        t = torch.cuda.Event(enable_timing=True)
+        s.record(torch.cuda.current_stream(self.device))
+        rc = nat.call(name, *args)
+        t.record(torch.cuda.current_stream(self.device))
+        self.prof.append((tag or name, flops, nbytes, s, t))
+        return rc
+
+    def prof_summary(self):
+        """name -> [launches, ms, flops, bytes] from the recorded events (synchronises)."""
+        torch.cuda.synchronize(self.device)
+        out = {}
+        for name, fl, nb, s, t in self.prof:
+            r = out.setdefault(name, [0, 0.0, 0, 0])
+            r[0] += 1; r[1] += s.elapsed_time(t); r[2] += fl; r[3] += nb
+        return out
+
     @property
     def stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -146,14 +168,19 @@ class Engine:
         if res2 is not None:
             d.res2, d.res2_dtype, d.res2_ld, d.res2_scale = res2.ptr, res2.dt, res2.ld, res2_scale
         d.y, d.y_dtype, d.y_ld = y.ptr, y.dt, y.ld
+        up = 2 if upsample else 1
+        opix = x.N * (x.H * up // stride) * (x.W * up // stride)
+        flops = 2 * opix * pc.Cout * (pc.k * pc.k * pc.Cin + (x2.C if x2 is not None else 0))
+        es = 2 if x.dt == nat.BF16 else 4
+        nbytes = x.N * x.H * x.W * x.C * es + opix * pc.Cout * (2 if y.dt == nat.BF16 else 4) + pc.w.numel() * es
         if not force_simt and self._tc_conv_ok(x, pc, x2, y):
             self.n_tc += 1
-            nat.call("wsr_conv_tc", C.byref(d), self.stream)
+            self.call("wsr_conv_tc", C.byref(d), self.stream, flops=flops, nbytes=nbytes, tag="conv_tc")
         else:
             if self.strict_tc and not force_simt:
                 raise nat.WsrError("strict_tc: conv Cin=%d Cout=%d k=%d not eligible for the tcgen05 kernel" % (pc.Cin_pad, pc.Cout, pc.k))
             self.n_simt += 1
-            nat.call("wsr_conv_simt", C.byref(d), self.stream)
+            self.call("wsr_conv_simt", C.byref(d), self.stream, flops=flops, nbytes=nbytes, tag="conv_simt")
         return y
 
     def gemm(self, a_ptr, a_dt, a_s, b_ptr, b_dt, b_s, d_ptr, d_dt, d_s, batch, M, N, K, alpha=1.0, bias=None,
@@ -168,25 +195,29 @@ class Engine:
         tc_ok = (self.use_tc and not force_simt and a_dt == nat.BF16 and b_dt == nat.BF16 and a_s[2] == 1 and b_s[2] == 1
                  and K % 64 == 0 and a_s[1] % 8 == 0 and b_s[1] % 8 == 0 and a_s[0] % 8 == 0 and b_s[0] % 8 == 0
                  and a_ptr % 16 == 0 and b_ptr % 16 == 0)
+        flops = 2 * batch * M * N * K
         if tc_ok:
             self.n_tc += 1
-            nat.call("wsr_gemm_tc", C.byref(g), self.stream)
+            self.call("wsr_gemm_tc", C.byref(g), self.stream, flops=flops, tag="gemm_tc")
         else:
             if self.strict_tc and not force_simt:
                 raise nat.WsrError("strict_tc: gemm M=%d N=%d K=%d not eligible for the tcgen05 kernel" % (M, N, K))
             self.n_simt += 1
-            nat.call("wsr_gemm_simt", C.byref(g), self.stream)
+            self.call("wsr_gemm_simt", C.byref(g), self.stream, flops=flops, tag="gemm_simt")
 
     def gn_stats(self, x, stats):
-        nat.call("wsr_gn_stats", x.ptr, x.dt, x.N, x.H * x.W, x.C, x.ld, stats.data_ptr(), self.stream)
+        self.call("wsr_gn_stats", x.ptr, x.dt, x.N, x.H * x.W, x.C, x.ld, stats.data_ptr(), self.stream,
+                  nbytes=x.N * x.H * x.W * x.C * (2 if x.dt == nat.BF16 else 4))
 
     def gn_apply(self, x, stats, gamma, beta, groups, act, y, eps=1e-5):
-        nat.call("wsr_gn_apply", x.ptr, x.dt, x.N, x.H * x.W, x.C, x.ld, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                 groups, eps, act, y.ptr, y.dt, y.ld, self.stream)
+        self.call("wsr_gn_apply", x.ptr, x.dt, x.N, x.H * x.W, x.C, x.ld, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                  groups, eps, act, y.ptr, y.dt, y.ld, self.stream,
+                  nbytes=2 * x.N * x.H * x.W * x.C * (2 if x.dt == nat.BF16 else 4))
         return y
 
     def softmax(self, s, s_dt, rows, cols, scale, p, p_dt):
-        nat.call("wsr_softmax_rows", s.data_ptr(), s_dt, rows, cols, cols, scale, p.data_ptr(), p_dt, cols, self.stream)
+        self.call("wsr_softmax_rows", s.data_ptr(), s_dt, rows, cols, cols, scale, p.data_ptr(), p_dt, cols, self.stream,
+                  nbytes=rows * cols * ((2 if s_dt == nat.BF16 else 4) + (2 if p_dt == nat.BF16 else 4)))
 
     def nchw_to_act(self, src, y):
         src = src.contiguous()

@@ -115,54 +115,41 @@ class GaussianDiffusion(nn.Module):
         st = plan.eng.stream
         plan.select_level_row(t_dev)
         plan.run(x)
-        nat.call("wsr_sampler_step", x.data_ptr(), plan.eps.data_ptr(), nat.F32, 0 if z is None else z.data_ptr(),
-                 z_stride, seed, tab.data_ptr(), self.num_timesteps, t_dev.data_ptr(), 1 if clip else 0, x.data_ptr(),
-                 x.numel(), st)
-        nat.call("wsr_step_counter_add", t_dev.data_ptr(), -1, st)
+        plan.eng.call("wsr_sampler_step", x.data_ptr(), plan.eps.data_ptr(), nat.F32, 0 if z is None else z.data_ptr(),
+                      z_stride, seed, tab.data_ptr(), self.num_timesteps, t_dev.data_ptr(), 1 if clip else 0, x.data_ptr(),
+                      x.numel(), st, nbytes=x.numel() * (16 if z is not None else 12))
+        plan.eng.call("wsr_step_counter_add", t_dev.data_ptr(), -1, st)
+
+    @torch.no_grad()
+    def begin_loop(self, plan, shape, noise_chain=None, seed=None):
+        """Set up a reverse loop on the plan's current condition and return its state object (see ReverseLoop)."""
+        return ReverseLoop(self, plan, shape, noise_chain, seed)
 
     @torch.no_grad()
     def _reverse_loop(self, plan, shape, noise_chain=None, seed=None, steps=None, collect_eps=False):
         """T reverse steps on the plan's current condition.  noise_chain: optional injected noise [T+1, *shape]
         (index 0 = initial image, index T-t = noise of step t) for parity runs; otherwise Philox noise from ``seed``.
         Returns the final x_0 (fp32 NCHW)."""
-        dev = plan.eng.device
-        T = self.num_timesteps
-        tab, levels = self._tables_dev()
-        plan.set_level_table(levels)
-        x = torch.empty(shape, device=dev, dtype=torch.float32)
-        seed = self._next_seed() if seed is None else int(seed)
-        if noise_chain is not None:
-            z = noise_chain.to(device=dev, dtype=torch.float32).contiguous()
-            assert z.shape[0] == T + 1 and tuple(z.shape[1:]) == tuple(shape)
-            x.copy_(z[0])
-            z_stride = x.numel()
-        else:
-            z, z_stride = None, 0
-            nat.call("wsr_randn", x.data_ptr(), x.numel(), seed, 0xFFFFFFFF, plan.eng.stream)
-        t_dev = torch.tensor([T - 1], dtype=torch.int32, device=dev)
-        n_steps = T if steps is None else min(int(steps), T)
+        loop = self.begin_loop(plan, shape, noise_chain, seed)
+        n_steps = self.num_timesteps if steps is None else min(int(steps), self.num_timesteps)
         eps_log = []
         # first step eagerly (lazy initialisation of kernel attributes happens here), the rest as graph replays
-        self._step(plan, x, t_dev, tab, z, z_stride, seed)
+        loop.step()
         if collect_eps:
             eps_log.append(plan.eps.clone())
         remaining = n_steps - 1
         if remaining > 0 and self.use_cuda_graph and not collect_eps:
-            torch.cuda.synchronize(dev)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                self._step(plan, x, t_dev, tab, z, z_stride, seed)
+            loop.capture()
             for _ in range(remaining):
-                graph.replay()
-            self._last_graph = graph
+                loop.replay()
         else:
             for _ in range(remaining):
-                self._step(plan, x, t_dev, tab, z, z_stride, seed)
+                loop.step()
                 if collect_eps:
                     eps_log.append(plan.eps.clone())
         if collect_eps:
-            return x, eps_log
-        return x
+            return loop.x, eps_log
+        return loop.x
 
     @torch.no_grad()
     def sample(self, batch_size=1, continous=False):
@@ -201,3 +188,44 @@ class GaussianDiffusion(nn.Module):
     @abstractmethod
     def p_losses(self, x_in, noise=None) -> torch.Tensor:
         pass
+
+
+class ReverseLoop:
+    """State of one reverse (p_sample) loop: the image x (updated in place), the device-side step counter and the
+    captured CUDA graph of one step.  ``step()`` launches one step eagerly, ``capture()`` records the same launches
+    into a graph, ``replay()`` replays it -- the step index lives on the device, so every replay advances the chain."""
+
+    def __init__(self, diffusion, plan, shape, noise_chain=None, seed=None):
+        self.diffusion, self.plan = diffusion, plan
+        dev = plan.eng.device
+        T = diffusion.num_timesteps
+        self.tab, levels = diffusion._tables_dev()
+        plan.set_level_table(levels)
+        self.x = torch.empty(shape, device=dev, dtype=torch.float32)
+        self.seed = diffusion._next_seed() if seed is None else int(seed)
+        if noise_chain is not None:
+            self.z = noise_chain.to(device=dev, dtype=torch.float32).contiguous()
+            assert self.z.shape[0] == T + 1 and tuple(self.z.shape[1:]) == tuple(shape)
+            self.x.copy_(self.z[0])
+            self.z_stride = self.x.numel()
+        else:
+            self.z, self.z_stride = None, 0
+            nat.call("wsr_randn", self.x.data_ptr(), self.x.numel(), self.seed, 0xFFFFFFFF, plan.eng.stream)
+        self.t_dev = torch.tensor([T - 1], dtype=torch.int32, device=dev)
+        self.graph = None
+
+    def reset_counter(self, t=None):
+        self.t_dev.fill_(self.diffusion.num_timesteps - 1 if t is None else int(t))
+
+    def step(self):
+        self.diffusion._step(self.plan, self.x, self.t_dev, self.tab, self.z, self.z_stride, self.seed)
+
+    def capture(self):
+        torch.cuda.synchronize(self.plan.eng.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.step()
+        return self.graph
+
+    def replay(self):
+        self.graph.replay()

@@ -365,8 +365,8 @@ class UNetPlan:
 
     def select_level_row(self, row_index_dev):
         """cur_proj[b] = proj_table[*row_index] for every b (device-side index: CUDA-graph friendly)."""
-        nat.call("wsr_broadcast_row", self.proj_table.data_ptr(), self.P, row_index_dev.data_ptr(), self.B,
-                 self.cur_proj.data_ptr(), self.eng.stream)
+        self.eng.call("wsr_broadcast_row", self.proj_table.data_ptr(), self.P, row_index_dev.data_ptr(), self.B,
+                      self.cur_proj.data_ptr(), self.eng.stream)
 
     # ------------------------------------------------------------------------------------------------------------------
     # the denoiser
@@ -434,15 +434,15 @@ class UNetPlan:
         Leaves eps_hat in ``self.eps`` (fp32 NCHW)."""
         e, B = self.eng, self.B
         st = e.stream
-        nat.call("wsr_fill_zero", self.stats.data_ptr(), self.stats.numel() * 8, st)
+        e.call("wsr_fill_zero", self.stats.data_ptr(), self.stats.numel() * 8, st)
         stem = self.downs[0]
         if self.kind == "resdiff":
-            nat.call("wsr_fd_gate", self.cur_proj.data_ptr() + 4 * self.ne_off, self.P, 0, B, self.C_img, self.W,
+            e.call("wsr_fd_gate", self.cur_proj.data_ptr() + 4 * self.ne_off, self.P, 0, B, self.C_img, self.W,
                      self.fd_n0.data_ptr(), self.fd_n2.data_ptr(), self.fd_hidden, self.gate.data_ptr(), st)
-            nat.call("wsr_stem_assemble", x_t.data_ptr(), self.cond.data_ptr(), self.gate.data_ptr(), self.lf.data_ptr(),
+            e.call("wsr_stem_assemble", x_t.data_ptr(), self.cond.data_ptr(), self.gate.data_ptr(), self.lf.data_ptr(),
                      self.hf.data_ptr(), B, self.C_img, self.H, self.W, stem.xin.ptr, stem.xin.dt, stem.xin.ld, st)
         else:
-            nat.call("wsr_nchw_to_nhwc", x_t.data_ptr(), B, self.C_img, self.H, self.W, stem.xin.ptr, stem.xin.dt, stem.xin.ld, st)
+            e.call("wsr_nchw_to_nhwc", x_t.data_ptr(), B, self.C_img, self.H, self.W, stem.xin.ptr, stem.xin.dt, stem.xin.ld, st)
         x = e.conv(stem.xin, stem.conv, stem.y)
         for i, r in enumerate(self.downs[1:], start=1):
             extra = self.cond_up if (self.kind == "srdiff" and i == 2) else None
@@ -464,6 +464,6 @@ class UNetPlan:
         e.gn_apply(x, sf, self.gf, self.bf_, self.groups, nat.ACT_SWISH, self.final_a)
         e.conv(self.final_a, self.final, self.eps_nhwc)
         if self.C_img != 1:
-            nat.call("wsr_nhwc_to_nchw", self.eps_nhwc.ptr, nat.F32, self.eps_nhwc.ld, B, self.C_img, self.H, self.W,
+            e.call("wsr_nhwc_to_nchw", self.eps_nhwc.ptr, nat.F32, self.eps_nhwc.ld, B, self.C_img, self.H, self.W,
                      self.eps.data_ptr(), st)
         return self.eps

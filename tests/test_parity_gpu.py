@@ -1,9 +1,8 @@
 """GPU parity tests proper: the CUDA path (through the reference-facing classes and the C ABI) against the golden
 fixtures produced by the REAL reference (tests/golden, oracle/make_golden.py) and against the CPU oracle.
 
-Tolerances (BASELINE.json north_star): per-step noise prediction rel-L2 <= 2e-2 in bf16, and in the fp32 check mode
-<= 1e-4 here (the north star's 1e-5 is the target; fp32 summation-order differences over ~60 stacked convolutions with
-K up to 9216 measure ~2e-6..3e-5)."""
+Tolerances (BASELINE.json north_star): per-step noise prediction rel-L2 <= 2e-2 in bf16 and <= 1e-5 in the fp32 check
+mode (measured on B200: 6e-3..7e-3 and 8e-7..2e-6)."""
 import pytest
 import torch
 
@@ -14,7 +13,7 @@ from oracle.weights import fill_module
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 1e-4, "bf16": 2e-2}
+TOL = {"fp32": 1e-5, "bf16": 2e-2}
 
 
 def _resdiff(cfg, seed, precision):
