@@ -255,6 +255,14 @@ def run_ours(args):
         "whole_step_frac_of_sustained": global_batch / world * FLOPS_PER_SAMPLE_STEP / (ms_per_step * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
     }
     if args.profile_ops and rank == 0:
+        plan.eng.prof, plan.eng.prof_detail = [], True
+        loop.step()
+        detail = plan.eng.prof_summary()
+        plan.eng.prof, plan.eng.prof_detail = None, False
+        print("# per-shape breakdown of the tensor-core launches (B=%d): name launches ms TFLOP/s" % B, file=sys.stderr)
+        for name, (n, ms, fl, nb) in sorted(detail.items(), key=lambda kv: -kv[1][1]):
+            if name.startswith("conv_tc") or name.startswith("gemm_tc"):
+                print("#   %-40s %3d %8.3f %8.1f" % (name, n, ms, fl / (ms * 1e-3) / 1e12 if ms > 0 else 0), file=sys.stderr)
         rows = sorted(summ.items(), key=lambda kv: -kv[1][1])
         print("# per-op breakdown of one eager step (B=%d): name launches ms TFLOP/s GB/s" % B, file=sys.stderr)
         for name, (n, ms, fl, nb) in rows:

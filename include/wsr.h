@@ -96,6 +96,13 @@ typedef struct {
 int wsr_gemm_simt(const WsrGemmDesc* d, void* stream);
 int wsr_gemm_tc(const WsrGemmDesc* d, void* stream);
 
+/* Fused single-head attention O = softmax(scale * Q K^T) V on tcgen05/TMEM; the (Nq x Nk) score matrix stays on chip.
+ * Replaces nn_modules/resnet.py:90-97 and resdiff/guided_cross_attention.py:34-41 (scale = 1/sqrt(C)).
+ * q (B,Nq,d) pitch q_ld; k (B,Nk,d) pitch k_ld; vT (B,d,Nk) = V transposed, dense; o (B,Nq,d) pitch o_ld; all bf16.
+ * Requires d in {64,128}, Nq % 128 == 0, Nk % 128 == 0, pitches % 8 == 0, 16-byte aligned bases. */
+int wsr_attention_tc(const void* q, int q_ld, const void* k, int k_ld, const void* vT, void* o, int o_ld, int B, int Nq,
+                     int Nk, int d, float scale, void* stream);
+
 /* ConvTranspose2d(k=8, s=4, p=2) of srdiff/unet.py:43-45,118.  x NHWC (N,H,W,Cin); w packed [ky*8+kx][Cout][Cin];
  * y NHWC (N,4H,4W,Cout). */
 int wsr_conv_transpose_k8s4(const void* x, int x_dtype, int N, int H, int W, int Cin, int x_ld, const void* w,

@@ -58,6 +58,7 @@ SIGNATURES = {
     "wsr_conv_tc": [C.POINTER(ConvDesc), _P],
     "wsr_gemm_simt": [C.POINTER(GemmDesc), _P],
     "wsr_gemm_tc": [C.POINTER(GemmDesc), _P],
+    "wsr_attention_tc": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "wsr_conv_transpose_k8s4": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P],
     "wsr_gn_stats": [_P, _I, _I, _I, _I, _I, _P, _P],
     "wsr_gn_apply": [_P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _F, _I, _P, _I, _I, _P],

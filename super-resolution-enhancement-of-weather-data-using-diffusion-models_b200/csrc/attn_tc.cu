@@ -1,0 +1,303 @@
+// attn_tc.cu -- fused single-head attention  O = softmax(scale * Q K^T) V  on tcgen05 / TMEM (sm_100a).
+//
+// Replaces the reference's materialised attention (nn_modules/resnet.py:90-97, guided_cross_attention.py:34-41:
+// einsum -> (B,N,N) fp32 matrix -> .contiguous() -> /sqrt(C) -> softmax -> einsum), whose N = 8192 instance writes
+// 268 MB per sample per step.  Here the score matrix never leaves the SM.
+//
+// One CTA owns 128 query rows and streams the keys in blocks of 128, TWO passes over the keys:
+//   pass A:  S = Q K^T (tcgen05.mma into TMEM), row maxima only (no exponentials)
+//   pass B:  S again, P = exp2((S - max) * scale*log2e) -> bf16 -> swizzled smem, O += P V (tcgen05.mma), row sums
+// Knowing the exact row maximum before pass B removes the online-softmax rescaling of the O accumulator (and the
+// dependency it creates between softmax and the previous P*V); the extra Q K^T is cheap because for d = 64 the kernel is
+// bound by the exponentials (128x128 per block on the SFUs), not by the tensor pipe.
+// V is consumed TRANSPOSED (vT: B x d x Nk, produced that way by the K/V projection GEMM) so that both operands of P*V
+// are K-major and can be fed by plain 128B-swizzled TMA boxes.
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-5 softmax + epilogue
+// (thread = query row; tcgen05.ld 32x32b gives each thread 32 consecutive keys of its row).
+#include <string.h>
+
+#include "tc_common.cuh"
+
+namespace wsr {
+
+constexpr int kBQ = 128;     // queries per CTA
+constexpr int kBK = 128;     // keys per block
+
+template <int D> struct AttnCfg {
+  static constexpr int kChunks = D / 64;                  // 64-channel K chunks of Q / K
+  static constexpr int kQBytes = kChunks * 16384;
+  static constexpr int kKBytes = kChunks * 16384;         // one key block [128 keys][D]
+  static constexpr int kVAtom = D * 128;                  // [D rows][64 keys] bf16
+  static constexpr int kVBytes = 2 * kVAtom;              // one key block of V^T
+  static constexpr int kPBytes = 2 * 16384;               // [128 q][128 keys] bf16 as two 64-key atoms
+  static constexpr int kKStages = D == 64 ? 3 : 2;
+  static constexpr int kVStages = D == 64 ? 3 : 2;
+  static constexpr int kSmemData = kQBytes + kKStages * kKBytes + kVStages * kVBytes + 2 * kPBytes;
+  static constexpr int kSmemBytes = kSmemData + 1024 + 256;
+  static constexpr uint32_t kIdescQK = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBK >> 3) << 17) | ((uint32_t)(kBQ >> 4) << 24);
+  static constexpr uint32_t kIdescPV = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(kBQ >> 4) << 24);
+};
+
+struct AttnParams {
+  CUtensorMap qmap, kmap, vmap;
+  void* o; long long o_sb; int o_ld;      // output (B, Nq, d) bf16
+  int nblocks;                            // Nk / 128
+  float c;                                // scale * log2(e)
+};
+
+template <int D>
+__global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
+  using Cfg = AttnCfg<D>;
+  constexpr int KS = Cfg::kKStages, VS = Cfg::kVStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::kQBytes;
+  uint8_t* sV = sK + KS * Cfg::kKBytes;
+  uint8_t* sP = sV + VS * Cfg::kVBytes;
+  uint64_t* bars = (uint64_t*)(smem + Cfg::kSmemData);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* k_full = q_full + 1;           // KS
+  uint64_t* k_empty = k_full + KS;         // KS
+  uint64_t* v_full = k_empty + KS;         // VS
+  uint64_t* v_empty = v_full + VS;         // VS
+  uint64_t* s_full = v_empty + VS;         // 2
+  uint64_t* s_empty = s_full + 2;          // 2
+  uint64_t* p_full = s_empty + 2;          // 2
+  uint64_t* p_empty = p_full + 2;          // 2
+  uint64_t* o_full = p_empty + 2;          // 1
+  uint32_t* tmem_slot = (uint32_t*)(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kBQ;
+  const int b = blockIdx.y;
+  const int NB = p.nblocks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.qmap); prefetch_tmap(&p.kmap); prefetch_tmap(&p.vmap);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1); }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;            // 2 x 128 columns
+  const uint32_t tmem_O = tmem_base + 256;      // D columns
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Cfg::kQBytes);
+      for (int c = 0; c < Cfg::kChunks; ++c) tma_load_3d(sQ + c * 16384, &p.qmap, q_full, c * 64, q0, b);
+      int vj = 0;
+      for (int g = 0; g < 2 * NB; ++g) {
+        const int j = g < NB ? g : g - NB;
+        const int ks = g % KS; const uint32_t kph = (uint32_t)(g / KS) & 1;
+        mbar_wait(&k_empty[ks], kph ^ 1);
+        mbar_expect_tx(&k_full[ks], Cfg::kKBytes);
+        for (int c = 0; c < Cfg::kChunks; ++c) tma_load_3d(sK + ks * Cfg::kKBytes + c * 16384, &p.kmap, &k_full[ks], c * 64, j * kBK, b);
+        if (g >= NB) {
+          const int vs = vj % VS; const uint32_t vph = (uint32_t)(vj / VS) & 1;
+          mbar_wait(&v_empty[vs], vph ^ 1);
+          mbar_expect_tx(&v_full[vs], Cfg::kVBytes);
+          tma_load_3d(sV + vs * Cfg::kVBytes, &p.vmap, &v_full[vs], j * kBK, 0, b);
+          tma_load_3d(sV + vs * Cfg::kVBytes + Cfg::kVAtom, &p.vmap, &v_full[vs], j * kBK + 64, 0, b);
+          ++vj;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      const uint32_t q_addr = smem_u32(sQ);
+      auto issue_qk = [&](int g) {
+        const int ks = g % KS; const uint32_t kph = (uint32_t)(g / KS) & 1;
+        const int sb = g & 1; const uint32_t sph = (uint32_t)(g >> 1) & 1;
+        mbar_wait(&s_empty[sb], sph ^ 1);
+        mbar_wait(&k_full[ks], kph);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK + ks * Cfg::kKBytes);
+#pragma unroll
+        for (int c = 0; c < Cfg::kChunks; ++c)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem_S + (uint32_t)(sb * kBK), make_smem_desc(q_addr + c * 16384 + kk * 32),
+                      make_smem_desc(k_addr + c * 16384 + kk * 32), Cfg::kIdescQK, (c | kk) != 0 ? 1u : 0u);
+        umma_commit(&k_empty[ks]);
+        umma_commit(&s_full[sb]);
+      };
+      // pass A: scores only
+      for (int g = 0; g < NB; ++g) issue_qk(g);
+      // pass B: scores one block ahead of P*V
+      issue_qk(NB);
+      for (int j = 0; j < NB; ++j) {
+        if (j + 1 < NB) issue_qk(NB + j + 1);
+        const int pb = j & 1; const uint32_t pph = (uint32_t)(j >> 1) & 1;
+        const int vs = j % VS; const uint32_t vph = (uint32_t)(j / VS) & 1;
+        mbar_wait(&p_full[pb], pph);
+        mbar_wait(&v_full[vs], vph);
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(sP + pb * Cfg::kPBytes);
+        const uint32_t v_addr = smem_u32(sV + vs * Cfg::kVBytes);
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem_O, make_smem_desc(p_addr + a * 16384 + kk * 32), make_smem_desc(v_addr + a * Cfg::kVAtom + kk * 32),
+                      Cfg::kIdescPV, (j | a | kk) != 0 ? 1u : 0u);
+        umma_commit(&p_empty[pb]);
+        umma_commit(&v_empty[vs]);
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    // ===================== softmax + epilogue (warps 2..5, thread = query row) =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
+    float mx = -INFINITY;
+    // pass A: row maximum of the raw scores
+    for (int g = 0; g < NB; ++g) {
+      const int sb = g & 1; const uint32_t sph = (uint32_t)(g >> 1) & 1;
+      mbar_wait(&s_full[sb], sph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_sel + (uint32_t)(sb * kBK + ch * 32), v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[sb]);
+    }
+    const float mc = mx * p.c;
+    float lsum = 0.f;
+    // pass B: probabilities -> smem (K-major, 128B swizzle), row sums
+    for (int j = 0; j < NB; ++j) {
+      const int g = NB + j;
+      const int sb = g & 1; const uint32_t sph = (uint32_t)(g >> 1) & 1;
+      const int pb = j & 1; const uint32_t pph = (uint32_t)(j >> 1) & 1;
+      mbar_wait(&s_full[sb], sph);
+      mbar_wait(&p_empty[pb], pph ^ 1);
+      tc_fence_after();
+      uint8_t* prow = sP + pb * Cfg::kPBytes + row * 128;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_sel + (uint32_t)(sb * kBK + ch * 32), v);
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { e[i] = exp2f(fmaf(__uint_as_float(v[i]), p.c, -mc)); lsum += e[i]; }
+        uint8_t* atom = prow + (ch >> 1) * 16384;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          __nv_bfloat162* h = (__nv_bfloat162*)&u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(e[q * 8 + 2 * k], e[q * 8 + 2 * k + 1]);
+          const int cc = (ch & 1) * 4 + q;
+          *(uint4*)(atom + ((cc ^ (row & 7)) << 4)) = u;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&s_empty[sb]); mbar_arrive(&p_full[pb]); }
+    }
+    // epilogue: O / l -> bf16 -> global (row = D*2 contiguous bytes)
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = 1.f / lsum;
+    __nv_bfloat16* orow = (__nv_bfloat16*)p.o + (long long)b * p.o_sb + (long long)(q0 + row) * p.o_ld;
+#pragma unroll 1
+    for (int ch = 0; ch < D / 32; ++ch) {
+      uint32_t v[32];
+      tmem_ld32(tmem_O + lane_sel + (uint32_t)(ch * 32), v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u;
+        __nv_bfloat162* h = (__nv_bfloat162*)&u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          h[k] = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 2 * k]) * inv, __uint_as_float(v[q * 8 + 2 * k + 1]) * inv);
+        *(uint4*)(orow + ch * 32 + q * 8) = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+template <int D>
+static int launch_attn(const AttnParams& p, int B, int Nq, cudaStream_t st) {
+  using Cfg = AttnCfg<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    WSR_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid(Nq / kBQ, B);
+  attn_tc_kernel<D><<<grid, 192, Cfg::kSmemBytes, st>>>(p);
+  WSR_LAUNCH_OK();
+  return WSR_OK;
+}
+
+}  // namespace wsr
+
+using namespace wsr;
+
+extern "C" int wsr_attention_tc(const void* q, int q_ld, const void* k, int k_ld, const void* vT, void* o, int o_ld, int B,
+                                int Nq, int Nk, int d, float scale, void* stream) {
+  WSR_REQUIRE(q && k && vT && o, WSR_E_INVALID, "attention_tc: null pointer");
+  WSR_REQUIRE(B > 0 && B <= 65535 && Nq > 0 && Nk > 0, WSR_E_INVALID, "attention_tc: bad shape");
+  WSR_REQUIRE(d == 64 || d == 128, WSR_E_UNSUPPORTED, "attention_tc: head dim %d (only 64, 128)", d);
+  WSR_REQUIRE(Nq % kBQ == 0 && Nk % kBK == 0, WSR_E_UNSUPPORTED, "attention_tc: Nq, Nk must be multiples of 128 (got %d, %d)", Nq, Nk);
+  WSR_REQUIRE(q_ld % 8 == 0 && k_ld % 8 == 0 && o_ld % 8 == 0 && q_ld >= d && k_ld >= d && o_ld >= d, WSR_E_UNSUPPORTED, "attention_tc: pitches");
+  WSR_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)vT | (uintptr_t)o) & 15) == 0, WSR_E_UNSUPPORTED, "attention_tc: 16-byte alignment");
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  {
+    uint64_t dims[3] = {(uint64_t)d, (uint64_t)Nq, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)q_ld * 2, (uint64_t)Nq * q_ld * 2};
+    uint32_t box[3] = {64, (uint32_t)kBQ, 1};
+    if ((rc = encode_map(&p.qmap, q, 3, dims, str, box))) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)d, (uint64_t)Nk, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)k_ld * 2, (uint64_t)Nk * k_ld * 2};
+    uint32_t box[3] = {64, (uint32_t)kBK, 1};
+    if ((rc = encode_map(&p.kmap, k, 3, dims, str, box))) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)Nk, (uint64_t)d, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)Nk * 2, (uint64_t)d * Nk * 2};
+    uint32_t box[3] = {64, (uint32_t)d, 1};
+    if ((rc = encode_map(&p.vmap, vT, 3, dims, str, box))) return rc;
+  }
+  p.o = o; p.o_sb = (long long)Nq * o_ld; p.o_ld = o_ld;
+  p.nblocks = Nk / kBK;
+  p.c = scale * 1.4426950408889634f;
+  cudaStream_t st = (cudaStream_t)stream;
+  return d == 64 ? launch_attn<64>(p, B, Nq, st) : launch_attn<128>(p, B, Nq, st);
+}

@@ -18,7 +18,7 @@
 #include <cuda.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace wsr {
 
@@ -61,86 +61,6 @@ struct TcParams {
   const void* res; int res_dtype; long long r_s1, r_s2, r_s3, r_sb, r_sc; float res_scale;
   const void* res2; int res2_dtype; long long q_s1, q_s2, q_s3, q_sb, q_sc; float res2_scale;
 };
-
-// ------------------------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-// K-major, 128-byte-swizzled shared-memory operand descriptor (8-row x 128-byte atoms, 1024 bytes apart)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address
-  d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset
-  d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
-  return d;
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 template <int BLOCK_N> struct TcCfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
@@ -281,13 +201,35 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         const bool full = (n0 + 32 <= p.Ncols);
         float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]);
-          if (full || n0 + j < p.Ncols) {
-            if (p.bias) x += __ldg(p.bias + n0 + j);
-            if (rowvec) x += __ldg(rowvec + n0 + j);
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (full) {
+          // 32 consecutive columns: bias / time-embedding row as independent 16-byte loads (same address in every
+          // lane -> one broadcast transaction each), issued back to back
+          if (p.bias) {
+            const float4* b4 = (const float4*)(p.bias + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { float4 t = __ldg(b4 + q); f[4 * q] += t.x; f[4 * q + 1] += t.y; f[4 * q + 2] += t.z; f[4 * q + 3] += t.w; }
           }
-          f[j] = apply_act(x, p.act) * p.out_scale;
+          if (rowvec) {
+            const float4* r4 = (const float4*)(rowvec + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { float4 t = __ldg(r4 + q); f[4 * q] += t.x; f[4 * q + 1] += t.y; f[4 * q + 2] += t.z; f[4 * q + 3] += t.w; }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < p.Ncols) {
+              if (p.bias) f[j] += __ldg(p.bias + n0 + j);
+              if (rowvec) f[j] += __ldg(rowvec + n0 + j);
+            }
+        }
+        if (p.act != WSR_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+        }
+        if (p.out_scale != 1.f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
         }
         const bool vec_ok = full && p.o_sc == 1 && ((obase + n0) & 7) == 0 && (((uintptr_t)p.out) & 15) == 0;
         if (p.res) {
@@ -366,7 +308,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // bf16 tensor map, rank `rank`, innermost box 64 elements (128 B) with 128B swizzle
-static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box) {
   EncodeTiledFn enc = get_encode();
   WSR_REQUIRE(enc != nullptr, WSR_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -385,7 +327,7 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t
   return WSR_OK;
 }
 
-static int sm_count() {
+int sm_count() {
   static int n = 0;
   if (!n) {
     int dev = 0;
@@ -449,6 +391,8 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
     WSR_REQUIRE(d->Cin2 % 64 == 0 && d->x2_ld % 8 == 0 && (((uintptr_t)d->x2) & 15) == 0 && (((uintptr_t)d->w2) & 15) == 0,
                 WSR_E_UNSUPPORTED, "conv_tc: second segment Cin2 %% 64 / alignment");
   WSR_REQUIRE(!(d->x2 && (d->stride != 1 || d->upsample)), WSR_E_UNSUPPORTED, "conv_tc: second segment needs stride 1, no upsample");
+  WSR_REQUIRE((((uintptr_t)d->bias) & 15) == 0 && (((uintptr_t)d->rowvec) & 15) == 0 && (d->rowvec == nullptr || d->rowvec_ld % 4 == 0),
+              WSR_E_UNSUPPORTED, "conv_tc: bias / rowvec must be 16-byte aligned, rowvec_ld %% 4 == 0");
   cudaStream_t st = (cudaStream_t)stream;
 
   const int up = d->upsample ? 2 : 1;
@@ -577,6 +521,7 @@ extern "C" int wsr_gemm_tc(const WsrGemmDesc* g, void* stream) {
   WSR_REQUIRE(g->a_dtype == WSR_BF16 && g->b_dtype == WSR_BF16, WSR_E_UNSUPPORTED, "gemm_tc: bf16 operands only");
   WSR_REQUIRE(g->a_sk == 1 && g->b_sk == 1, WSR_E_UNSUPPORTED, "gemm_tc: both operands must be K-major (unit k stride)");
   WSR_REQUIRE(g->K % 64 == 0, WSR_E_UNSUPPORTED, "gemm_tc: K=%d must be a multiple of 64", g->K);
+  WSR_REQUIRE((((uintptr_t)g->bias) & 15) == 0, WSR_E_UNSUPPORTED, "gemm_tc: bias must be 16-byte aligned");
   WSR_REQUIRE(g->a_sm % 8 == 0 && g->b_sn % 8 == 0 && g->a_sb % 8 == 0 && g->b_sb % 8 == 0 && (((uintptr_t)g->a) & 15) == 0 &&
                   (((uintptr_t)g->b) & 15) == 0,
               WSR_E_UNSUPPORTED, "gemm_tc: strides must be multiples of 8 elements, bases 16-byte aligned");

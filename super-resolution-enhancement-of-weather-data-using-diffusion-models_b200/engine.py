@@ -70,6 +70,8 @@ class Engine:
         self.n_simt = 0
         self._keep = []          # tensors that must outlive async launches
         self.prof = None         # list of (name, flops, bytes, start_event, end_event) when profiling
+        self.prof_detail = False
+        self.no_fused_attention = False
 
     # ---- plumbing -------------------------------------------------------------------------------------------------
     def call(self, name, *args, flops=0, nbytes=0, tag=None):
@@ -136,8 +138,12 @@ class Engine:
         return out
 
     # ---- ops -------------------------------------------------------------------------------------------------------
-    def _tc_conv_ok(self, x, pc, x2, y):
+    def _tc_conv_ok(self, x, pc, x2, y, bias=None, rowvec=0, rowvec_ld=0):
         if not self.use_tc:
+            return False
+        if bias is not None and bias.data_ptr() % 16:
+            return False
+        if rowvec and (rowvec % 16 or rowvec_ld % 4):
             return False
         ok = (x.dt == nat.BF16 and pc.Cin_pad % 64 == 0 and x.C == pc.Cin_pad and x.ld % 8 == 0 and x.ptr % 16 == 0
               and x.W >= 1)
@@ -173,9 +179,11 @@ class Engine:
         flops = 2 * opix * pc.Cout * (pc.k * pc.k * pc.Cin + (x2.C if x2 is not None else 0))
         es = 2 if x.dt == nat.BF16 else 4
         nbytes = x.N * x.H * x.W * x.C * es + opix * pc.Cout * (2 if y.dt == nat.BF16 else 4) + pc.w.numel() * es
-        if not force_simt and self._tc_conv_ok(x, pc, x2, y):
+        if not force_simt and self._tc_conv_ok(x, pc, x2, y, b, rowvec or 0, rowvec_ld):
             self.n_tc += 1
-            self.call("wsr_conv_tc", C.byref(d), self.stream, flops=flops, nbytes=nbytes, tag="conv_tc")
+            self.call("wsr_conv_tc", C.byref(d), self.stream, flops=flops, nbytes=nbytes,
+                      tag="conv_tc" if not self.prof_detail else "conv_tc %4d->%4d k%d s%d%s %dx%d" % (
+                          pc.Cin_pad + (x2.C if x2 is not None else 0), pc.Cout, pc.k, stride, "u" if upsample else " ", x.H, x.W))
         else:
             if self.strict_tc and not force_simt:
                 raise nat.WsrError("strict_tc: conv Cin=%d Cout=%d k=%d not eligible for the tcgen05 kernel" % (pc.Cin_pad, pc.Cout, pc.k))
@@ -198,7 +206,8 @@ class Engine:
         flops = 2 * batch * M * N * K
         if tc_ok:
             self.n_tc += 1
-            self.call("wsr_gemm_tc", C.byref(g), self.stream, flops=flops, tag="gemm_tc")
+            self.call("wsr_gemm_tc", C.byref(g), self.stream, flops=flops,
+                      tag="gemm_tc" if not self.prof_detail else "gemm_tc M%d N%d K%d" % (M, N, K))
         else:
             if self.strict_tc and not force_simt:
                 raise nat.WsrError("strict_tc: gemm M=%d N=%d K=%d not eligible for the tcgen05 kernel" % (M, N, K))
@@ -231,6 +240,14 @@ class Engine:
         """q, k: Act (B, H, W, C) row-major pixels x channels; vT: tensor (B, C, Nk) (V transposed, K-major for P*V);
         o: Act (B, H, W, C).  scores/probs: scratch tensors (B, Nq, Nk)."""
         B, Nq, Nk, Cc = q.N, q.H * q.W, k.H * k.W, q.C
+        if (self.use_tc and not self.no_fused_attention and Cc in (64, 128) and Nq % 128 == 0 and Nk % 128 == 0
+                and q.dt == nat.BF16 and k.dt == nat.BF16 and o.dt == nat.BF16 and q.ld % 8 == 0 and k.ld % 8 == 0
+                and o.ld % 8 == 0 and q.ptr % 16 == 0 and k.ptr % 16 == 0 and o.ptr % 16 == 0):
+            self.n_tc += 1
+            self.call("wsr_attention_tc", q.ptr, q.ld, k.ptr, k.ld, vT.data_ptr(), o.ptr, o.ld, B, Nq, Nk, Cc,
+                      1.0 / math.sqrt(Cc), self.stream, flops=4 * B * Nq * Nk * Cc,
+                      tag="attn_tc" if not self.prof_detail else "attn_tc N%d d%d" % (Nk, Cc))
+            return o
         es = q.buf.element_size()
         s_dt = nat.BF16 if scores.dtype == torch.bfloat16 else nat.F32
         p_dt = nat.BF16 if probs.dtype == torch.bfloat16 else nat.F32

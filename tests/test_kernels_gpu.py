@@ -273,3 +273,34 @@ def test_noise_embed_and_fd_and_haar_vs_oracle():
             got = pl.haar_out[off:off + q.numel()].view(q.shape).cpu()
             assert rel_l2(got, q) < 1e-6
             off += q.numel()
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 32, 64), (1, 32, 64, 128), (3, 8, 16, 64), (1, 64, 128, 64)])
+def test_attention_tc_fused_vs_torch(shape):
+    """fused tcgen05 attention (scores stay on chip) against fp32 torch on the same bf16 operands."""
+    B, H, W, d = shape
+    n = H * W
+    torch.manual_seed(9)
+    dev = _dev()
+    eng = Engine(dev, "bf16")
+    q = torch.randn(B, d, H, W, device=dev) * 1.5
+    k = torch.randn(B, d, H, W, device=dev) * 1.5
+    v = torch.randn(B, d, H, W, device=dev)
+    qa, ka = _nhwc(q, eng), _nhwc(k, eng, ld=2 * d, coff=d)
+    vT = v.reshape(B, d, n).bfloat16().contiguous()
+    o = eng.new_act(B, H, W, d, zero=True)
+    scores = torch.empty(B * n * n, device=dev, dtype=torch.float32)
+    probs = torch.empty(B * n * n, device=dev, dtype=torch.bfloat16)
+    eng.attention(qa, ka, vT, o, scores, probs)
+    assert eng.n_tc == 1 and eng.n_simt == 0          # one fused launch
+    qf = qa.to_nchw(eng).reshape(B, d, n)
+    kf = ka.to_nchw(eng).reshape(B, d, n)
+    s = torch.einsum("bcq,bck->bqk", qf, kf) / math.sqrt(d)
+    ref = torch.einsum("bqk,bck->bcq", torch.softmax(s, -1), vT.float()).reshape(B, d, H, W)
+    err = rel_l2(o.to_nchw(eng), ref)
+    assert err < 1e-2, err
+    # and the unfused path (GEMM -> softmax -> GEMM) agrees as well
+    eng.no_fused_attention = True
+    o2 = eng.new_act(B, H, W, d, zero=True)
+    eng.attention(qa, ka, vT, o2, scores, probs)
+    assert rel_l2(o2.to_nchw(eng), ref) < 1e-2
