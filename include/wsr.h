@@ -70,6 +70,9 @@ typedef struct {
   const void* res;  int res_dtype;  int res_ld;  float res_scale;
   const void* res2; int res2_dtype; int res2_ld; float res2_scale;
   void* y; int y_dtype; int y_ld;
+  /* optional fused GroupNorm statistics of the OUTPUT: per-(image, channel) sum and sum of squares of y (taken from the
+   * fp32 epilogue values, before the store rounding) are ACCUMULATED into gn_stats[n*gn_stats_ld + 2*co + {0,1}] (doubles; see wsr_gn_stats).  NULL = off. */
+  double* gn_stats; int gn_stats_ld;
 } WsrConvDesc;
 
 /* fp32-accumulate SIMT implicit GEMM; any dtype, any channel count.  This is the "fp32 check mode" kernel. */
@@ -111,10 +114,13 @@ int wsr_conv_transpose_k8s4(const void* x, int x_dtype, int N, int H, int W, int
 /* ---------------------------------------------------------------------------------------------------------------
  * GroupNorm (eps, affine) + activation.  Replaces nn.GroupNorm + Swish of nn_modules/resnet.py:21-22,77 and
  * guided_cross_attention.py:19.  Two kernels: per-(image, channel) sums, then normalise (+act).
- * stats: double [N][C][2] = (sum, sum of squares); wsr_gn_stats ACCUMULATES (zero it first with wsr_fill_zero).
+ * stats: doubles, stats[n*stats_ld + 2*c + {0,1}] = (sum, sum of squares) of channel c of image n (stats_ld >= 2*C, so
+ * the statistics of a channel slice can live inside those of a wider concat buffer); wsr_gn_stats ACCUMULATES (zero
+ * the buffer first with wsr_fill_zero).  The convolution kernels can produce the same statistics in their epilogue
+ * (WsrConvDesc.gn_stats), which removes this read pass.
  * ------------------------------------------------------------------------------------------------------------- */
-int wsr_gn_stats(const void* x, int x_dtype, int N, int HW, int C, int x_ld, double* stats, void* stream);
-int wsr_gn_apply(const void* x, int x_dtype, int N, int HW, int C, int x_ld, const double* stats,
+int wsr_gn_stats(const void* x, int x_dtype, int N, int HW, int C, int x_ld, double* stats, int stats_ld, void* stream);
+int wsr_gn_apply(const void* x, int x_dtype, int N, int HW, int C, int x_ld, const double* stats, int stats_ld,
                  const float* gamma, const float* beta, int groups, float eps, int act, void* y, int y_dtype,
                  int y_ld, void* stream);
 int wsr_fill_zero(void* p, int64_t bytes, void* stream);
@@ -169,7 +175,8 @@ int wsr_fd_precompute(const float* cond, int B, int C, int H, int W, const float
 int wsr_fd_gate(const float* ne_rows, int ne_ld, const int* row_index, int B, int C, int W, const float* fc0,
                 const float* fc2, int hidden, float* gate, void* stream);
 /* Stem input assembly: writes NHWC channels [x, cond, x*gate, lf, hf] (5*C, fd_info_spliter.py:117), zero-pads up
- * to Cpad channels.  x, cond, lf, hf: fp32 NCHW. */
+ * to Cpad channels.  x, cond, lf, hf: fp32 NCHW.  Only the first roundup(5*C, 8) (bf16) / 5*C (fp32) channels are
+ * written: the caller zero-fills the pad channels of y once. */
 int wsr_stem_assemble(const float* x, const float* cond, const float* gate, const float* lf, const float* hf, int B,
                       int C, int H, int W, void* y, int y_dtype, int Cpad, void* stream);
 /* Haar detail-band sums for `levels` levels: out[j] fp32 NCHW (B,C,H>>(j+1),W>>(j+1)) packed back to back in `out`;

@@ -33,6 +33,7 @@ class ConvDesc(C.Structure):
         ("res", C.c_void_p), ("res_dtype", C.c_int), ("res_ld", C.c_int), ("res_scale", C.c_float),
         ("res2", C.c_void_p), ("res2_dtype", C.c_int), ("res2_ld", C.c_int), ("res2_scale", C.c_float),
         ("y", C.c_void_p), ("y_dtype", C.c_int), ("y_ld", C.c_int),
+        ("gn_stats", C.c_void_p), ("gn_stats_ld", C.c_int),
     ]
 
 
@@ -60,8 +61,8 @@ SIGNATURES = {
     "wsr_gemm_tc": [C.POINTER(GemmDesc), _P],
     "wsr_attention_tc": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "wsr_conv_transpose_k8s4": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P],
-    "wsr_gn_stats": [_P, _I, _I, _I, _I, _I, _P, _P],
-    "wsr_gn_apply": [_P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _F, _I, _P, _I, _I, _P],
+    "wsr_gn_stats": [_P, _I, _I, _I, _I, _I, _P, _I, _P],
+    "wsr_gn_apply": [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _I, _F, _I, _P, _I, _I, _P],
     "wsr_fill_zero": [_P, _L, _P],
     "wsr_softmax_rows": [_P, _I, _L, _I, _L, _F, _P, _I, _L, _P],
     "wsr_nchw_to_nhwc": [_P, _I, _I, _I, _I, _P, _I, _I, _P],

@@ -108,7 +108,7 @@ template <> struct VecLoad<__nv_bfloat16, 1> {
 };
 
 template <typename T, int VEC>
-__global__ void gn_stats_kernel(const T* __restrict__ x, int HW, int C, int ld, int CV, int PL, int chunk, double* __restrict__ stats) {
+__global__ void gn_stats_kernel(const T* __restrict__ x, int HW, int C, int ld, int CV, int PL, int chunk, double* __restrict__ stats, int stats_ld) {
   extern __shared__ float sm[];   // [PL][C][2]
   const int n = blockIdx.y;
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
@@ -118,7 +118,17 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, int HW, int C, int ld, 
 #pragma unroll
   for (int i = 0; i < VEC; ++i) { s[i] = 0.f; q[i] = 0.f; }
   const T* base = x + (int64_t)n * HW * ld + cv * VEC;
-  for (int p = p0 + pl; p < p1; p += PL) {
+  int p = p0 + pl;
+  for (; p + 3 * PL < p1; p += 4 * PL) {          // four independent 16-byte loads in flight per thread
+    float v[4][VEC];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) VecLoad<T, VEC>::ld(base + (int64_t)(p + u * PL) * ld, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { s[i] += v[u][i]; q[i] = fmaf(v[u][i], v[u][i], q[i]); }
+  }
+  for (; p < p1; p += PL) {
     float v[VEC];
     VecLoad<T, VEC>::ld(base + (int64_t)p * ld, v);
 #pragma unroll
@@ -133,14 +143,14 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, int HW, int C, int ld, 
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     double a = 0.0, b = 0.0;
     for (int l = 0; l < PL; ++l) { a += (double)sm[(l * C + c) * 2]; b += (double)sm[(l * C + c) * 2 + 1]; }
-    atomicAdd(&stats[((int64_t)n * C + c) * 2 + 0], a);
-    atomicAdd(&stats[((int64_t)n * C + c) * 2 + 1], b);
+    atomicAdd(&stats[(int64_t)n * stats_ld + c * 2 + 0], a);
+    atomicAdd(&stats[(int64_t)n * stats_ld + c * 2 + 1], b);
   }
 }
 
 template <typename TI, typename TO, int VEC>
 __global__ void gn_apply_kernel(const TI* __restrict__ x, int HW, int C, int ld, int CV, int PL, int chunk,
-                                const double* __restrict__ stats, const float* __restrict__ gamma,
+                                const double* __restrict__ stats, int stats_ld, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int groups, float eps, int act, TO* __restrict__ y, int y_ld) {
   extern __shared__ float sm[];   // scale[C], shift[C]
   const int n = blockIdx.y;
@@ -148,7 +158,7 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x, int HW, int C, int ld,
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     int g0 = (c / cpg) * cpg;
     double a = 0.0, b = 0.0;
-    for (int j = 0; j < cpg; ++j) { a += stats[((int64_t)n * C + g0 + j) * 2]; b += stats[((int64_t)n * C + g0 + j) * 2 + 1]; }
+    for (int j = 0; j < cpg; ++j) { a += stats[(int64_t)n * stats_ld + (g0 + j) * 2]; b += stats[(int64_t)n * stats_ld + (g0 + j) * 2 + 1]; }
     double cnt = (double)cpg * HW;
     double mean = a / cnt;
     double var = b / cnt - mean * mean;
@@ -167,7 +177,19 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x, int HW, int C, int ld,
   for (int i = 0; i < VEC; ++i) { sc[i] = sm[cv * VEC + i]; sh[i] = sm[C + cv * VEC + i]; }
   const TI* xb = x + (int64_t)n * HW * ld + cv * VEC;
   TO* yb = y + (int64_t)n * HW * y_ld + cv * VEC;
-  for (int p = p0 + pl; p < p1; p += PL) {
+  int p = p0 + pl;
+  for (; p + 3 * PL < p1; p += 4 * PL) {          // four independent 16-byte loads in flight per thread
+    float v[4][VEC];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) VecLoad<TI, VEC>::ld(xb + (int64_t)(p + u * PL) * ld, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) v[u][i] = apply_act(fmaf(v[u][i], sc[i], sh[i]), act);
+      VecLoad<TO, VEC>::st(yb + (int64_t)(p + u * PL) * y_ld, v[u]);
+    }
+  }
+  for (; p < p1; p += PL) {
     float v[VEC];
     VecLoad<TI, VEC>::ld(xb + (int64_t)p * ld, v);
 #pragma unroll
@@ -452,28 +474,28 @@ extern "C" int wsr_fill_zero(void* p, int64_t bytes, void* stream) {
   return WSR_OK;
 }
 
-extern "C" int wsr_gn_stats(const void* x, int x_dtype, int N, int HW, int C, int x_ld, double* stats, void* stream) {
-  WSR_REQUIRE(x && stats && valid_dtype(x_dtype) && N > 0 && HW > 0 && C > 0 && x_ld >= C, WSR_E_INVALID, "gn_stats: bad argument");
+extern "C" int wsr_gn_stats(const void* x, int x_dtype, int N, int HW, int C, int x_ld, double* stats, int stats_ld, void* stream) {
+  WSR_REQUIRE(x && stats && valid_dtype(x_dtype) && N > 0 && HW > 0 && C > 0 && x_ld >= C && stats_ld >= 2 * C, WSR_E_INVALID, "gn_stats: bad argument");
   GnGeom g = gn_geom(x_dtype, C, x_ld, x_ld, x, x);
   WSR_REQUIRE(g.vec != 0 && g.threads <= 1024, WSR_E_UNSUPPORTED, "gn_stats: C=%d too wide", C);
   dim3 grid((HW + g.chunk - 1) / g.chunk, N);
   size_t smem = (size_t)g.PL * C * 2 * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   if (x_dtype == WSR_BF16) {
-    if (g.vec == 8) gn_stats_kernel<__nv_bfloat16, 8><<<grid, g.threads, smem, st>>>((const __nv_bfloat16*)x, HW, C, x_ld, g.CV, g.PL, g.chunk, stats);
-    else gn_stats_kernel<__nv_bfloat16, 1><<<grid, g.threads, smem, st>>>((const __nv_bfloat16*)x, HW, C, x_ld, g.CV, g.PL, g.chunk, stats);
+    if (g.vec == 8) gn_stats_kernel<__nv_bfloat16, 8><<<grid, g.threads, smem, st>>>((const __nv_bfloat16*)x, HW, C, x_ld, g.CV, g.PL, g.chunk, stats, stats_ld);
+    else gn_stats_kernel<__nv_bfloat16, 1><<<grid, g.threads, smem, st>>>((const __nv_bfloat16*)x, HW, C, x_ld, g.CV, g.PL, g.chunk, stats, stats_ld);
   } else {
-    if (g.vec == 4) gn_stats_kernel<float, 4><<<grid, g.threads, smem, st>>>((const float*)x, HW, C, x_ld, g.CV, g.PL, g.chunk, stats);
-    else gn_stats_kernel<float, 1><<<grid, g.threads, smem, st>>>((const float*)x, HW, C, x_ld, g.CV, g.PL, g.chunk, stats);
+    if (g.vec == 4) gn_stats_kernel<float, 4><<<grid, g.threads, smem, st>>>((const float*)x, HW, C, x_ld, g.CV, g.PL, g.chunk, stats, stats_ld);
+    else gn_stats_kernel<float, 1><<<grid, g.threads, smem, st>>>((const float*)x, HW, C, x_ld, g.CV, g.PL, g.chunk, stats, stats_ld);
   }
   WSR_LAUNCH_OK();
   return WSR_OK;
 }
 
-extern "C" int wsr_gn_apply(const void* x, int x_dtype, int N, int HW, int C, int x_ld, const double* stats,
+extern "C" int wsr_gn_apply(const void* x, int x_dtype, int N, int HW, int C, int x_ld, const double* stats, int stats_ld,
                             const float* gamma, const float* beta, int groups, float eps, int act, void* y,
                             int y_dtype, int y_ld, void* stream) {
-  WSR_REQUIRE(x && y && stats && gamma && beta && valid_dtype(x_dtype) && N > 0 && HW > 0 && C > 0 && x_ld >= C && y_ld >= C,
+  WSR_REQUIRE(x && y && stats && gamma && beta && valid_dtype(x_dtype) && N > 0 && HW > 0 && C > 0 && x_ld >= C && y_ld >= C && stats_ld >= 2 * C,
               WSR_E_INVALID, "gn_apply: bad argument");
   WSR_REQUIRE(groups > 0 && C % groups == 0, WSR_E_INVALID, "gn_apply: C=%d not divisible by groups=%d", C, groups);
   WSR_REQUIRE(y_dtype == x_dtype, WSR_E_UNSUPPORTED, "gn_apply: y_dtype must equal x_dtype");
@@ -482,7 +504,7 @@ extern "C" int wsr_gn_apply(const void* x, int x_dtype, int N, int HW, int C, in
   dim3 grid((HW + g.chunk - 1) / g.chunk, N);
   size_t smem = (size_t)C * 2 * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-#define GN_APPLY(T, V) gn_apply_kernel<T, T, V><<<grid, g.threads, smem, st>>>((const T*)x, HW, C, x_ld, g.CV, g.PL, g.chunk, stats, gamma, beta, groups, eps, act, (T*)y, y_ld)
+#define GN_APPLY(T, V) gn_apply_kernel<T, T, V><<<grid, g.threads, smem, st>>>((const T*)x, HW, C, x_ld, g.CV, g.PL, g.chunk, stats, stats_ld, gamma, beta, groups, eps, act, (T*)y, y_ld)
   if (x_dtype == WSR_BF16) { if (g.vec == 8) GN_APPLY(__nv_bfloat16, 8); else GN_APPLY(__nv_bfloat16, 1); }
   else { if (g.vec == 4) GN_APPLY(float, 4); else GN_APPLY(float, 1); }
 #undef GN_APPLY

@@ -190,30 +190,44 @@ __global__ void fd_gate_kernel(const float* __restrict__ ne_rows, int ne_ld, con
   }
 }
 
+__device__ __forceinline__ float stem_value(const float* x, const float* cond, const float* gate, const float* lf, const float* hf,
+                                           int C, int W, int64_t HW, int64_t b, int64_t p, int ch) {
+  if (ch >= 5 * C) return 0.f;
+  const int k = ch / C, c = ch - k * C;
+  const int64_t src = (b * C + c) * HW + p;
+  switch (k) {
+    case 0: return x[src];
+    case 1: return cond[src];
+    case 2: return x[src] * gate[(b * C + c) * W + (p % W)];
+    case 3: return lf[src];
+    default: return hf[src];
+  }
+}
+
+// one thread per pixel; writes the first `nwrite` channels (a multiple of 8 for bf16) -- the remaining pad channels
+// of the buffer were zeroed at allocation and are never touched again
 template <typename T>
 __global__ void stem_assemble_kernel(const float* __restrict__ x, const float* __restrict__ cond, const float* __restrict__ gate,
                                      const float* __restrict__ lf, const float* __restrict__ hf, int C, int H, int W,
-                                     T* __restrict__ y, int Cpad, int64_t total) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*H*W*Cpad, channel fastest
-  if (i >= total) return;
-  int ch = (int)(i % Cpad);
-  int64_t pix = i / Cpad;
-  int64_t HW = (int64_t)H * W;
-  int64_t b = pix / HW;
-  int64_t p = pix - b * HW;
-  float v = 0.f;
-  if (ch < 5 * C) {
-    int k = ch / C, c = ch - k * C;
-    int64_t src = (b * C + c) * HW + p;
-    switch (k) {
-      case 0: v = x[src]; break;
-      case 1: v = cond[src]; break;
-      case 2: v = x[src] * gate[(b * C + c) * W + (p % W)]; break;
-      case 3: v = lf[src]; break;
-      default: v = hf[src]; break;
+                                     T* __restrict__ y, int Cpad, int nwrite, int64_t npix) {
+  int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const int64_t HW = (int64_t)H * W;
+  const int64_t b = pix / HW, p = pix - b * HW;
+  T* dst = y + pix * Cpad;
+  if constexpr (sizeof(T) == 2) {
+    for (int c0 = 0; c0 < nwrite; c0 += 8) {
+      uint4 u;
+      __nv_bfloat162* h = (__nv_bfloat162*)&u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        h[k] = __floats2bfloat162_rn(stem_value(x, cond, gate, lf, hf, C, W, HW, b, p, c0 + 2 * k),
+                                     stem_value(x, cond, gate, lf, hf, C, W, HW, b, p, c0 + 2 * k + 1));
+      *(uint4*)(dst + c0) = u;
     }
+  } else {
+    for (int c = 0; c < nwrite; ++c) dst[c] = stem_value(x, cond, gate, lf, hf, C, W, HW, b, p, c);
   }
-  stf<T>(y + i, v);
 }
 
 __global__ void haar_level_kernel(const float* __restrict__ ll, int h, int w, float* __restrict__ detail, float* __restrict__ ll_next, int64_t total) {
@@ -307,10 +321,15 @@ extern "C" int wsr_stem_assemble(const float* x, const float* cond, const float*
                                  int B, int C, int H, int W, void* y, int y_dtype, int Cpad, void* stream) {
   WSR_REQUIRE(x && cond && gate && lf && hf && y && valid_dtype(y_dtype), WSR_E_INVALID, "stem_assemble: null pointer");
   WSR_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && Cpad >= 5 * C, WSR_E_INVALID, "stem_assemble: bad shape");
-  int64_t total = (int64_t)B * H * W * Cpad;
+  const int64_t npix = (int64_t)B * H * W;
   cudaStream_t st = (cudaStream_t)stream;
-  if (y_dtype == WSR_BF16) stem_assemble_kernel<__nv_bfloat16><<<nblk(total, 256), 256, 0, st>>>(x, cond, gate, lf, hf, C, H, W, (__nv_bfloat16*)y, Cpad, total);
-  else stem_assemble_kernel<float><<<nblk(total, 256), 256, 0, st>>>(x, cond, gate, lf, hf, C, H, W, (float*)y, Cpad, total);
+  if (y_dtype == WSR_BF16) {
+    int nwrite = (5 * C + 7) / 8 * 8;
+    WSR_REQUIRE(Cpad % 8 == 0 && nwrite <= Cpad && (((uintptr_t)y) & 15) == 0, WSR_E_UNSUPPORTED, "stem_assemble: bf16 needs Cpad %% 8 == 0");
+    stem_assemble_kernel<__nv_bfloat16><<<nblk(npix, 128), 128, 0, st>>>(x, cond, gate, lf, hf, C, H, W, (__nv_bfloat16*)y, Cpad, nwrite, npix);
+  } else {
+    stem_assemble_kernel<float><<<nblk(npix, 128), 128, 0, st>>>(x, cond, gate, lf, hf, C, H, W, (float*)y, Cpad, 5 * C, npix);
+  }
   WSR_LAUNCH_OK();
   return WSR_OK;
 }

@@ -8,14 +8,15 @@
 // maps), nearest-x2-upsample + 3x3 (one launch per output phase), a fused second K segment (the ResnetBlock 1x1
 // `res_conv`), and the batched attention products Q*K^T and P*V.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
-// warps 2-5 = epilogue (tcgen05.ld -> bias / time-embedding / activation / residual -> global).  Two accumulator
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
+// warps 2-9 = epilogue (tcgen05.ld -> bias / time-embedding / activation / residual -> global).  Two accumulator
 // buffers in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // Reference call sites replaced: every nn.Conv2d on the UNet path (nn_modules/resnet.py:24,51,78-79,
 // functional_layers.py:64,79, resdiff/unet.py:68, guided_cross_attention.py:20-22) and the attention einsums
 // (nn_modules/resnet.py:90-97, guided_cross_attention.py:34-41).
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "tc_common.cuh"
@@ -50,6 +51,10 @@ struct TcParams {
   int a_zmul, b_zmul;           // A coord3 += zb*a_zmul ; B coord2 += zb*b_zmul
   int n_tiles;                  // tiles along columns
   int a_bytes;                  // bytes one A box load delivers (rows_box * 128)
+  int dbg;                      // debugging switches (env WSR_TC_DBG): 1 skip epilogue work, 2 skip MMA issue, 4 skip stores only
+  int halo_bo;                  // debugging switch: put (start row & 7) into the descriptor base-offset field
+  int halo_rows;                // halo mode: output rows per tile (1 or 2; 2 = two accumulators share every weight tile)
+  int n_taps, halo_bytes;       // halo mode: e[0..n_taps) are filter taps served from one (t1+2) x 3 halo tile per chunk
   int M1, M2, M3;               // valid row extents (masking)
   int Ncols;                    // valid columns
   void* out; int out_dtype;
@@ -60,43 +65,80 @@ struct TcParams {
   int act; float out_scale;
   const void* res; int res_dtype; long long r_s1, r_s2, r_s3, r_sb, r_sc; float res_scale;
   const void* res2; int res2_dtype; long long q_s1, q_s2, q_s3, q_sb, q_sc; float res2_scale;
+  double* stats; int stats_ld;  // fused GroupNorm statistics of the output (needs t1*t2 % 32 == 0), or nullptr
 };
 
-template <int BLOCK_N> struct TcCfg {
+constexpr int kEpiWarps = 8;                      // two warps per TMEM lane quadrant, each owning half of the columns
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;
+// halo tile of ROWS output rows: (ROWS + 2) x 130 pixels x 128 bytes, rounded up to a multiple of 1024
+constexpr int halo_stage_bytes(int rows) { return ((rows + 2) * 130 * 128 + 1023) / 1024 * 1024; }
+
+template <int BLOCK_N, bool HALO, int ROWS> struct TcCfg {
+  static constexpr int kHaloStage = halo_stage_bytes(ROWS);
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  // classic mode: one ring of {A tile, B tile} stages.  halo mode: a ring of activation halo tiles (one per 64-channel
+  // chunk, shared by the 9 taps) and a separate ring of weight tiles.
   static constexpr int kStages = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
-  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;     // power of two for 32..256
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kAStages = 2;
+  static constexpr int kBStages = BLOCK_N >= 256 ? 3 : (BLOCK_N >= 128 ? (ROWS > 1 ? 4 : 6) : 8);
+  static constexpr int kSmemData = HALO ? kAStages * kHaloStage + kBStages * kBBytes : kStages * (kABytes + kBBytes);
+  static constexpr int kAccCols = ROWS * BLOCK_N;                           // one accumulator set (ROWS output rows)
+  static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;   // power of two for 32..512
+  static_assert(kTmemCols <= 512, "TMEM budget");
+  static constexpr int kSmemBytes = kSmemData + 1024 /*align slack*/ + 512 /*barriers*/;
   // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
   static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 };
 
+struct TileCoord { int nt, i1, i2, i3, zb; };
+
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
+  TileCoord t;
+  t.nt = tile % p.n_tiles;
+  int mt = tile / p.n_tiles;
+  t.i1 = mt % p.g1; mt /= p.g1;
+  t.i2 = mt % p.g2; mt /= p.g2;
+  t.i3 = mt % p.g3;
+  t.zb = mt / p.g3;
+  return t;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------------
-template <int BLOCK_N>
-__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
-  using Cfg = TcCfg<BLOCK_N>;
-  constexpr int kStages = Cfg::kStages;
+template <int BLOCK_N, bool HALO, int ROWS>
+__global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  using Cfg = TcCfg<BLOCK_N, HALO, ROWS>;
+  constexpr int kHaloStage = Cfg::kHaloStage;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = (uint64_t*)(smem + kStages * Cfg::kStageBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* bars = (uint64_t*)(smem + Cfg::kSmemData);
+  // classic: full[kStages], empty[kStages] | halo: fullA[2], emptyA[2], fullB[kBStages], emptyB[kBStages]
+  constexpr int kRingA = HALO ? Cfg::kAStages : Cfg::kStages;
+  constexpr int kRingB = HALO ? Cfg::kBStages : 0;
+  uint64_t* full_a = bars;
+  uint64_t* empty_a = full_a + kRingA;
+  uint64_t* full_b = empty_a + kRingA;
+  uint64_t* empty_b = full_b + kRingB;
+  uint64_t* tfull_bar = empty_b + kRingB;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+  uint8_t* smem_b = smem + Cfg::kAStages * kHaloStage;      // halo mode only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = p.g1 * p.g2 * p.g3 * p.nbatch;
-  const int total_tiles = m_tiles * p.n_tiles;
+  const int total_tiles = p.g1 * p.g2 * p.g3 * p.nbatch * p.n_tiles;
+  // contiguous tile range per CTA: consecutive tiles share the image (register-accumulated GroupNorm statistics) and
+  // neighbouring rows (halo re-reads hit L2)
+  const int tile_begin = (int)((long long)blockIdx.x * total_tiles / gridDim.x);
+  const int tile_end = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kNumAMaps; ++i) prefetch_tmap(&p.amap[i]);
     for (int i = 0; i < kNumBMaps; ++i) prefetch_tmap(&p.bmap[i]);
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int s = 0; s < kRingA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < kRingB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -112,25 +154,51 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        int mt = tile / p.n_tiles;
-        const int i1 = mt % p.g1; mt /= p.g1;
-        const int i2 = mt % p.g2; mt /= p.g2;
-        const int i3 = mt % p.g3;
-        const int zb = mt / p.g3;
-        const int c1 = i1 * p.t1, c2 = i2 * p.t2, c3 = i3 * p.t3 + zb * p.a_zmul;
-        for (int ei = 0; ei < p.n_entries; ++ei) {
-          const TcEntry e = p.e[ei];
-          for (int c = 0; c < e.nchunks; ++c) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * Cfg::kStageBytes;
-            uint8_t* sb = sa + kABytes;
-            mbar_expect_tx(&full_bar[stage], (uint32_t)(p.a_bytes + Cfg::kBBytes));
-            tma_load_4d(sa, &p.amap[e.amap], &full_bar[stage], e.a_c0 + c * kBlockK, c1 + e.d1, c2 + e.d2, c3);
-            tma_load_3d(sb, &p.bmap[e.bmap], &full_bar[stage], e.b_k0 + c * kBlockK, nt * BLOCK_N, e.b_z + zb * p.b_zmul);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const TileCoord t = decode_tile(p, tile);
+        const int c1 = t.i1 * p.t1, c2 = t.i2 * (HALO ? ROWS : p.t2), c3 = t.i3 * p.t3 + t.zb * p.a_zmul;
+        if constexpr (!HALO) {
+          for (int ei = 0; ei < p.n_entries; ++ei) {
+            const TcEntry e = p.e[ei];
+            for (int c = 0; c < e.nchunks; ++c) {
+              mbar_wait(&empty_a[sa], pa ^ 1);
+              uint8_t* st = smem + sa * (kABytes + Cfg::kBBytes);
+              mbar_expect_tx(&full_a[sa], (uint32_t)(p.a_bytes + Cfg::kBBytes));
+              tma_load_4d(st, &p.amap[e.amap], &full_a[sa], e.a_c0 + c * kBlockK, c1 + e.d1, c2 + e.d2, c3);
+              tma_load_3d(st + kABytes, &p.bmap[e.bmap], &full_a[sa], e.b_k0 + c * kBlockK, t.nt * BLOCK_N, e.b_z + t.zb * p.b_zmul);
+              if (++sa == kRingA) { sa = 0; pa ^= 1; }
+            }
+          }
+        } else {
+          // taps e[0 .. n_taps): one halo tile per 64-channel chunk, then one weight tile per tap
+          const int nch = p.e[0].nchunks;
+          for (int c = 0; c < nch; ++c) {
+            mbar_wait(&empty_a[sa], pa ^ 1);
+            mbar_expect_tx(&full_a[sa], (uint32_t)p.halo_bytes);
+            tma_load_4d(smem + sa * kHaloStage, &p.amap[p.e[0].amap], &full_a[sa], c * kBlockK, c1 - 1, c2 - 1, c3);
+            if (++sa == kRingA) { sa = 0; pa ^= 1; }
+            for (int ei = 0; ei < p.n_taps; ++ei) {
+              const TcEntry e = p.e[ei];
+              mbar_wait(&empty_b[sb], pb ^ 1);
+              mbar_expect_tx(&full_b[sb], (uint32_t)Cfg::kBBytes);
+              tma_load_3d(smem_b + sb * Cfg::kBBytes, &p.bmap[e.bmap], &full_b[sb], e.b_k0 + c * kBlockK, t.nt * BLOCK_N, e.b_z);
+              if (++sb == kRingB) { sb = 0; pb ^= 1; }
+            }
+          }
+          // remaining entries (fused 1x1 segment): plain 128-row activation tiles in the same A ring
+          for (int ei = p.n_taps; ei < p.n_entries; ++ei) {
+            const TcEntry e = p.e[ei];
+            for (int c = 0; c < e.nchunks; ++c) {
+              mbar_wait(&empty_a[sa], pa ^ 1);
+              mbar_expect_tx(&full_a[sa], (uint32_t)p.a_bytes);
+              tma_load_4d(smem + sa * kHaloStage, &p.amap[e.amap], &full_a[sa], e.a_c0 + c * kBlockK, c1 + e.d1, c2 + e.d2, c3);
+              if (++sa == kRingA) { sa = 0; pa ^= 1; }
+              mbar_wait(&empty_b[sb], pb ^ 1);
+              mbar_expect_tx(&full_b[sb], (uint32_t)Cfg::kBBytes);
+              tma_load_3d(smem_b + sb * Cfg::kBBytes, &p.bmap[e.bmap], &full_b[sb], e.b_k0 + c * kBlockK, t.nt * BLOCK_N, e.b_z);
+              if (++sb == kRingB) { sb = 0; pb ^= 1; }
+            }
           }
         }
       }
@@ -138,147 +206,252 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int kb = 0; kb < p.total_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t adesc = make_smem_desc(sa);
-          const uint64_t bdesc = make_smem_desc(sa + kABytes);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::kAccCols);
+        if constexpr (!HALO) {
+          for (int kb = 0; kb < p.total_kb; ++kb) {
+            mbar_wait(&full_a[sa], pa);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + sa * (kABytes + Cfg::kBBytes));
+            const uint64_t adesc = make_smem_desc(st);
+            const uint64_t bdesc = make_smem_desc(st + kABytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), Cfg::kIdesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k)   // +32 bytes along K inside the swizzle atom = +2 in the address field
+              if (!(p.dbg & 2)) umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), Cfg::kIdesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_a[sa]);
+            if (kb == p.total_kb - 1) umma_commit(&tfull_bar[acc]);
+            if (++sa == kRingA) { sa = 0; pa ^= 1; }
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == p.total_kb - 1) umma_commit(&tfull_bar[acc]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        } else {
+          int kb = 0;
+          const int nch = p.e[0].nchunks;
+          const int pitch = p.t1 + 2;
+          for (int c = 0; c < nch; ++c) {
+            mbar_wait(&full_a[sa], pa);
+            const uint32_t a_base = smem_u32(smem + sa * kHaloStage);
+            for (int ei = 0; ei < p.n_taps; ++ei, ++kb) {
+              const TcEntry e = p.e[ei];
+              mbar_wait(&full_b[sb], pb);
+              tc_fence_after();
+              // tap (dy, dx) = the 128 consecutive halo rows starting at row (dy+1)*pitch + (dx+1).  The 128B swizzle is a
+              // function of the absolute shared-memory address bits (the halo buffer is 1024-byte aligned, so the
+              // descriptor's base-offset field stays 0), exactly as for the +32-byte K advance below.
+              const int srow = (e.d2 + 1) * pitch + (e.d1 + 1);
+              const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + sb * Cfg::kBBytes));
+              if (!(p.dbg & 2)) {
+#pragma unroll
+                for (int rr = 0; rr < ROWS; ++rr) {     // output row rr of the tile reads halo rows rr .. rr+2
+                  const uint64_t adesc = make_smem_desc(a_base + (uint32_t)(srow + rr * pitch) * 128u);
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k)
+                    umma_bf16(d_tmem + (uint32_t)(rr * BLOCK_N), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), Cfg::kIdesc, (kb | k) != 0 ? 1u : 0u);
+                }
+              }
+              umma_commit(&empty_b[sb]);
+              if (++sb == kRingB) { sb = 0; pb ^= 1; }
+            }
+            umma_commit(&empty_a[sa]);
+            if (++sa == kRingA) { sa = 0; pa ^= 1; }
+          }
+          for (int ei = p.n_taps; ei < p.n_entries; ++ei) {
+            const int n2 = p.e[ei].nchunks;
+            for (int c = 0; c < n2; ++c, ++kb) {
+              mbar_wait(&full_a[sa], pa);
+              mbar_wait(&full_b[sb], pb);
+              tc_fence_after();
+              const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + sb * Cfg::kBBytes));
+#pragma unroll
+              for (int rr = 0; rr < ROWS; ++rr) {       // plain tile: ROWS consecutive 128-row slabs of t1 pixels
+                const uint64_t adesc = make_smem_desc(smem_u32(smem + sa * kHaloStage) + (uint32_t)(rr * p.t1) * 128u);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma_bf16(d_tmem + (uint32_t)(rr * BLOCK_N), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), Cfg::kIdesc, (kb | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(&empty_b[sb]);
+              umma_commit(&empty_a[sa]);
+              if (++sb == kRingB) { sb = 0; pb ^= 1; }
+              if (++sa == kRingA) { sa = 0; pa ^= 1; }
+            }
+          }
+          umma_commit(&tfull_bar[acc]);
         }
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;          // row of the 128-row tile
-    const int rows_box = p.t1 * p.t2 * p.t3;
+    constexpr int kChunksPerWarp = BLOCK_N / 32 / (kEpiWarps / 4);
+    const int ch_begin = ((warp - 2) >> 2) * kChunksPerWarp;
+    const int rows_box = HALO ? p.t1 : p.t1 * p.t2 * p.t3;
+    // GroupNorm statistics accumulated in registers across consecutive tiles of the same (image, column tile):
+    // lane j of this warp owns column n0 + j of every 32-column chunk
+    float st_s[kChunksPerWarp], st_q[kChunksPerWarp];
+#pragma unroll
+    for (int i = 0; i < kChunksPerWarp; ++i) { st_s[i] = 0.f; st_q[i] = 0.f; }
+    int st_img = -1, st_nt = -1;
+    auto flush_stats = [&]() {
+      if (st_img >= 0 && st_img < p.M3) {
+#pragma unroll
+        for (int i = 0; i < kChunksPerWarp; ++i) {
+          const int col = st_nt * BLOCK_N + (ch_begin + i) * 32 + lane;
+          if (col < p.Ncols) {
+            double* sp = p.stats + (long long)st_img * p.stats_ld + (long long)col * 2;
+            atomicAdd(sp, (double)st_s[i]);
+            atomicAdd(sp + 1, (double)st_q[i]);
+          }
+          st_s[i] = 0.f; st_q[i] = 0.f;
+        }
+      }
+    };
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int nt = tile % p.n_tiles;
-      int mt = tile / p.n_tiles;
-      const int i1 = mt % p.g1; mt /= p.g1;
-      const int i2 = mt % p.g2; mt /= p.g2;
-      const int i3 = mt % p.g3;
-      const int zb = mt / p.g3;
+      const TileCoord t = decode_tile(p, tile);
+      const int nt = t.nt, i1 = t.i1, i2 = t.i2, i3 = t.i3, zb = t.zb;
+      if (p.stats != nullptr) {
+        const int img_w = i3 * p.t3 + (HALO ? 0 : (quad * 32) / (p.t1 * p.t2));     // warp-uniform
+        if (img_w != st_img || nt != st_nt) { flush_stats(); st_img = img_w; st_nt = nt; }
+      }
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int rr = 0; rr < ROWS; ++rr) {
       // row -> coordinates
-      const int l1 = row % p.t1;
-      const int l2 = (row / p.t1) % p.t2;
-      const int l3 = row / (p.t1 * p.t2);
-      const int r1 = i1 * p.t1 + l1, r2 = i2 * p.t2 + l2, r3 = i3 * p.t3 + l3;
+      const int l1 = HALO ? row : row % p.t1;
+      const int l2 = HALO ? rr : (row / p.t1) % p.t2;
+      const int l3 = HALO ? 0 : row / (p.t1 * p.t2);
+      const int r1 = i1 * p.t1 + l1, r2 = i2 * (HALO ? ROWS : p.t2) + l2, r3 = i3 * p.t3 + l3;
       const bool row_ok = row < rows_box && r1 < p.M1 && r2 < p.M2 && r3 < p.M3;
       const long long o1 = (long long)r1 * p.mul1 + p.off1, o2 = (long long)r2 * p.mul2 + p.off2;
       const long long obase = o1 * p.o_s1 + o2 * p.o_s2 + (long long)r3 * p.o_s3 + (long long)zb * p.o_sb;
       const long long rbase = o1 * p.r_s1 + o2 * p.r_s2 + (long long)r3 * p.r_s3 + (long long)zb * p.r_sb;
       const long long qbase = o1 * p.q_s1 + o2 * p.q_s2 + (long long)r3 * p.q_s3 + (long long)zb * p.q_sb;
       const float* rowvec = p.rowvec ? p.rowvec + (long long)r3 * p.rowvec_ld : nullptr;
-
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
 #pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+      for (int ci = 0; ci < ((p.dbg & 1) ? 0 : kChunksPerWarp); ++ci) {
+        const int ch = ch_begin + ci;
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + ch * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * Cfg::kAccCols + rr * BLOCK_N + ch * 32), v);
         const int n0 = nt * BLOCK_N + ch * 32;
-        if (row_ok && n0 < p.Ncols) {
-        const bool full = (n0 + 32 <= p.Ncols);
         float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (full) {
-          // 32 consecutive columns: bias / time-embedding row as independent 16-byte loads (same address in every
-          // lane -> one broadcast transaction each), issued back to back
-          if (p.bias) {
-            const float4* b4 = (const float4*)(p.bias + n0);
+        for (int j = 0; j < 32; ++j) f[j] = 0.f;
+        if (row_ok && n0 < p.Ncols) {
+          const bool full = (n0 + 32 <= p.Ncols);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) { float4 t = __ldg(b4 + q); f[4 * q] += t.x; f[4 * q + 1] += t.y; f[4 * q + 2] += t.z; f[4 * q + 3] += t.w; }
-          }
-          if (rowvec) {
-            const float4* r4 = (const float4*)(rowvec + n0);
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (full) {
+            // 32 consecutive columns: bias / time-embedding row as independent 16-byte loads (same address in every
+            // lane -> one broadcast transaction each), issued back to back
+            if (p.bias) {
+              const float4* b4 = (const float4*)(p.bias + n0);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) { float4 t = __ldg(r4 + q); f[4 * q] += t.x; f[4 * q + 1] += t.y; f[4 * q + 2] += t.z; f[4 * q + 3] += t.w; }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + j < p.Ncols) {
-              if (p.bias) f[j] += __ldg(p.bias + n0 + j);
-              if (rowvec) f[j] += __ldg(rowvec + n0 + j);
+              for (int q = 0; q < 8; ++q) { float4 t4 = __ldg(b4 + q); f[4 * q] += t4.x; f[4 * q + 1] += t4.y; f[4 * q + 2] += t4.z; f[4 * q + 3] += t4.w; }
             }
-        }
-        if (p.act != WSR_ACT_NONE) {
+            if (rowvec) {
+              const float4* r4 = (const float4*)(rowvec + n0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-        }
-        if (p.out_scale != 1.f) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
-        }
-        const bool vec_ok = full && p.o_sc == 1 && ((obase + n0) & 7) == 0 && (((uintptr_t)p.out) & 15) == 0;
-        if (p.res) {
-          if (full && p.r_sc == 1 && p.res_dtype == WSR_BF16 && ((rbase + n0) & 7) == 0 && (((uintptr_t)p.res) & 15) == 0) {
-            const uint4* rp = (const uint4*)((const __nv_bfloat16*)p.res + rbase + n0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 u = rp[q];
-              const __nv_bfloat162* h = (const __nv_bfloat162*)&u;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) { float2 t = __bfloat1622float2(h[k]); f[q * 8 + 2 * k] += p.res_scale * t.x; f[q * 8 + 2 * k + 1] += p.res_scale * t.y; }
+              for (int q = 0; q < 8; ++q) { float4 t4 = __ldg(r4 + q); f[4 * q] += t4.x; f[4 * q + 1] += t4.y; f[4 * q + 2] += t4.z; f[4 * q + 3] += t4.w; }
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.Ncols) f[j] += p.res_scale * ld_dt(p.res, rbase + (long long)(n0 + j) * p.r_sc, p.res_dtype);
+              if (n0 + j < p.Ncols) {
+                if (p.bias) f[j] += __ldg(p.bias + n0 + j);
+                if (rowvec) f[j] += __ldg(rowvec + n0 + j);
+              }
           }
-        }
-        if (p.res2) {
+          if (p.act != WSR_ACT_NONE) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + j < p.Ncols) f[j] += p.res2_scale * ld_dt(p.res2, qbase + (long long)(n0 + j) * p.q_sc, p.res2_dtype);
-        }
-        if (vec_ok && p.out_dtype == WSR_BF16) {
-          uint4* op = (uint4*)((__nv_bfloat16*)p.out + obase + n0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 u;
-            __nv_bfloat162* h = (__nv_bfloat162*)&u;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[q * 8 + 2 * k], f[q * 8 + 2 * k + 1]);
-            op[q] = u;
+            for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
           }
-        } else if (vec_ok && p.out_dtype == WSR_F32) {
-          float4* op = (float4*)((float*)p.out + obase + n0);
+          if (p.out_scale != 1.f) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) op[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-        } else {
+            for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
+          }
+          const bool vec_ok = full && p.o_sc == 1 && ((obase + n0) & 7) == 0 && (((uintptr_t)p.out) & 15) == 0;
+          if (p.res) {
+            if (full && p.r_sc == 1 && p.res_dtype == WSR_BF16 && ((rbase + n0) & 7) == 0 && (((uintptr_t)p.res) & 15) == 0) {
+              const uint4* rp = (const uint4*)((const __nv_bfloat16*)p.res + rbase + n0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + j < p.Ncols) st_dt(p.out, obase + (long long)(n0 + j) * p.o_sc, p.out_dtype, f[j]);
-        }
+              for (int q = 0; q < 4; ++q) {
+                uint4 u = rp[q];
+                const __nv_bfloat162* h = (const __nv_bfloat162*)&u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { float2 t2 = __bfloat1622float2(h[k]); f[q * 8 + 2 * k] += p.res_scale * t2.x; f[q * 8 + 2 * k + 1] += p.res_scale * t2.y; }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.Ncols) f[j] += p.res_scale * ld_dt(p.res, rbase + (long long)(n0 + j) * p.r_sc, p.res_dtype);
+            }
+          }
+          if (p.res2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.Ncols) f[j] += p.res2_scale * ld_dt(p.res2, qbase + (long long)(n0 + j) * p.q_sc, p.res2_dtype);
+          }
+          if (p.dbg & 4) {
+          } else if (vec_ok && p.out_dtype == WSR_BF16) {
+            uint4* op = (uint4*)((__nv_bfloat16*)p.out + obase + n0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 u;
+              __nv_bfloat162* h = (__nv_bfloat162*)&u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[q * 8 + 2 * k], f[q * 8 + 2 * k + 1]);
+              op[q] = u;
+            }
+          } else if (vec_ok && p.out_dtype == WSR_F32) {
+            float4* op = (float4*)((float*)p.out + obase + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) op[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.Ncols) st_dt(p.out, obase + (long long)(n0 + j) * p.o_sc, p.out_dtype, f[j]);
+          }
         }
         __syncwarp();
+        if (p.stats != nullptr && n0 < p.Ncols) {
+          // per-channel sum / sum of squares over the warp's 32 rows: transpose-reduce with 31 shuffles per statistic so
+          // that lane j ends up with column n0 + j; masked rows hold zeros
+          float q2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) q2[j] = f[j] * f[j];
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float send_s = upper ? f[i] : f[i + off];
+              const float keep_s = upper ? f[i + off] : f[i];
+              const float send_q = upper ? q2[i] : q2[i + off];
+              const float keep_q = upper ? q2[i + off] : q2[i];
+              f[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+              q2[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < kChunksPerWarp; ++i)
+            if (i == ci) { st_s[i] += f[0]; st_q[i] += q2[0]; }
+        }
+      }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (p.stats != nullptr) flush_stats();
   }
 
   tc_fence_before();
@@ -338,19 +511,30 @@ int sm_count() {
   return n;
 }
 
-template <int BLOCK_N>
-static int launch_tc(const TcParams& p, cudaStream_t st) {
-  using Cfg = TcCfg<BLOCK_N>;
+template <int BLOCK_N, bool HALO, int ROWS>
+static int launch_tc_impl(const TcParams& p, cudaStream_t st) {
+  using Cfg = TcCfg<BLOCK_N, HALO, ROWS>;
   static bool attr_set = false;
   if (!attr_set) {
-    WSR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    WSR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, HALO, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   int total = p.g1 * p.g2 * p.g3 * p.nbatch * p.n_tiles;
   int grid = total < sm_count() ? total : sm_count();
-  gemm_tc_kernel<BLOCK_N><<<grid, 192, Cfg::kSmemBytes, st>>>(p);
+  gemm_tc_kernel<BLOCK_N, HALO, ROWS><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(p);
   WSR_LAUNCH_OK();
   return WSR_OK;
+}
+
+template <int BLOCK_N>
+static int launch_tc(const TcParams& p, cudaStream_t st) {
+  if (p.n_taps > 0) {
+    if constexpr (BLOCK_N <= 128) {
+      if (p.halo_rows == 2) return launch_tc_impl<BLOCK_N, true, 2>(p, st);
+    }
+    return launch_tc_impl<BLOCK_N, true, 1>(p, st);
+  }
+  return launch_tc_impl<BLOCK_N, false, 1>(p, st);
 }
 
 static int pick_block_n(int ncols, int m_tiles) {
@@ -423,6 +607,22 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
 
   const int m_tiles = p.g1 * p.g2 * p.g3;
   const int bn = pick_block_n(d->Cout, m_tiles);
+  // halo mode: when a tile is a segment of ONE image row, the 9 taps are 9 shifted views of a single halo tile, so the
+  // activation operand is fetched once per 64-channel chunk instead of once per tap; with two output rows per tile
+  // (two accumulators) every weight tile is used twice as well.  Both cut the L2 -> SM traffic that bounds these layers.
+  static const bool no_halo = getenv("WSR_NO_HALO") != nullptr;
+  static const int max_rows = getenv("WSR_HALO_ROWS") ? atoi(getenv("WSR_HALO_ROWS")) : 2;
+  const bool halo = !no_halo && d->ksize == 3 && d->stride == 1 && p.t2 == 1 && p.t3 == 1 && p.t1 + 2 <= 130;
+  const int hrows = (halo && bn <= 128 && GH % 2 == 0 && max_rows >= 2) ? 2 : 1;
+  p.n_taps = halo ? taps : 0;
+  p.halo_rows = hrows;
+  p.halo_bytes = (p.t1 + 2) * (hrows + 2) * 128;
+  if (halo) { p.g2 = cdiv(GH, hrows); p.a_bytes = p.t1 * hrows * 128; }
+  const bool fuse_stats = d->gn_stats != nullptr && (halo ? p.t1 % 32 == 0 : (p.t1 * p.t2) % 32 == 0);
+  p.stats = fuse_stats ? d->gn_stats : nullptr;
+  p.stats_ld = d->gn_stats_ld;
+  static const int dbg_flags = getenv("WSR_TC_DBG") ? atoi(getenv("WSR_TC_DBG")) : 0;
+  p.dbg = dbg_flags;
 
   // ---- B maps: weights [tap][Cout][Cin]
   {
@@ -442,12 +642,13 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
     }
   }
   // ---- A maps
-  const uint32_t abox[4] = {64, (uint32_t)p.t1, (uint32_t)p.t2, (uint32_t)p.t3};
+  const uint32_t abox[4] = {64, (uint32_t)p.t1, (uint32_t)(halo ? hrows : p.t2), (uint32_t)p.t3};
   const long long ld = d->x_ld;
   if (d->stride == 1) {
     uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
     uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)d->W * ld * 2, (uint64_t)d->H * d->W * ld * 2};
-    rc = encode_map(&p.amap[0], d->x, 4, dims, str, abox);
+    const uint32_t hbox[4] = {64, (uint32_t)(p.t1 + 2), (uint32_t)(hrows + 2), 1};
+    rc = encode_map(&p.amap[0], d->x, 4, dims, str, halo ? hbox : abox);
     if (rc) return rc;
     for (int i = 1; i < kNumAMaps; ++i) p.amap[i] = p.amap[0];
   } else {
@@ -512,6 +713,8 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
     }
     if (rc) return rc;
   }
+  if (d->gn_stats && !fuse_stats)
+    return wsr_gn_stats(d->y, d->y_dtype, d->N, OH * OW, d->Cout, d->y_ld, d->gn_stats, d->gn_stats_ld, stream);
   return WSR_OK;
 }
 

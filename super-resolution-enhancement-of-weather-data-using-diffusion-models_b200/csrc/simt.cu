@@ -144,6 +144,7 @@ int validate_conv_desc(const WsrConvDesc* d) {
   if (d->res) WSR_REQUIRE(valid_dtype(d->res_dtype) && d->res_ld >= d->Cout, WSR_E_INVALID, "conv: bad residual");
   if (d->res2) WSR_REQUIRE(valid_dtype(d->res2_dtype) && d->res2_ld >= d->Cout, WSR_E_INVALID, "conv: bad residual 2");
   if (d->rowvec) WSR_REQUIRE(d->rowvec_ld >= d->Cout, WSR_E_INVALID, "conv: rowvec pitch");
+  if (d->gn_stats) WSR_REQUIRE(d->gn_stats_ld >= 2 * d->Cout, WSR_E_INVALID, "conv: gn_stats pitch");
   return WSR_OK;
 }
 
@@ -169,7 +170,10 @@ extern "C" int wsr_conv_simt(const WsrConvDesc* d, void* stream) {
   p.OH = p.UH / d->stride; p.OW = p.UW / d->stride;
   p.GH = p.OH; p.GW = p.OW;
   p.out_mul = 1; p.out_py = 0; p.out_px = 0;
-  return launch_conv_simt(p, (cudaStream_t)stream);
+  rc = launch_conv_simt(p, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (d->gn_stats) return wsr_gn_stats(d->y, d->y_dtype, d->N, p.OH * p.OW, d->Cout, d->y_ld, d->gn_stats, d->gn_stats_ld, stream);
+  return WSR_OK;
 }
 
 extern "C" int wsr_conv_transpose_k8s4(const void* x, int x_dtype, int N, int H, int W, int Cin, int x_ld,

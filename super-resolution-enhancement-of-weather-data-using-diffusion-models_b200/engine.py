@@ -25,21 +25,45 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+class StatsArena:
+    """Bump allocator for the per-(image, channel) GroupNorm statistics (doubles).  Offsets are handed out while the
+    plan is being laid out; ``finalize`` allocates the single zero-initialised tensor that is cleared once per step."""
+
+    def __init__(self):
+        self.size = 0
+        self.tensor = None
+
+    def alloc(self, n):
+        off = self.size
+        self.size += n
+        return off
+
+    def finalize(self, device):
+        self.tensor = torch.zeros(max(self.size, 1), device=device, dtype=torch.float64)
+        return self.tensor
+
+
 class Act:
-    """A channel slice [coff, coff+C) of an NHWC buffer (N, H, W, ld)."""
+    """A channel slice [coff, coff+C) of an NHWC buffer (N, H, W, ld).  ``st*`` optionally locate the GroupNorm
+    statistics of these channels: doubles at arena[st_off + n*st_ld + 2*c + {0,1}]."""
 
-    __slots__ = ("buf", "N", "H", "W", "C", "ld", "coff", "dt")
+    __slots__ = ("buf", "N", "H", "W", "C", "ld", "coff", "dt", "st", "st_off", "st_ld")
 
-    def __init__(self, buf, N, H, W, C, ld, coff, dt):
+    def __init__(self, buf, N, H, W, C, ld, coff, dt, st=None, st_off=0, st_ld=0):
         self.buf, self.N, self.H, self.W, self.C, self.ld, self.coff, self.dt = buf, N, H, W, C, ld, coff, dt
+        self.st, self.st_off, self.st_ld = st, st_off, st_ld
 
     @property
     def ptr(self):
         return self.buf.data_ptr() + self.coff * self.buf.element_size()
 
+    @property
+    def stats_ptr(self):
+        return 0 if self.st is None else self.st.tensor.data_ptr() + 8 * self.st_off
+
     def slice(self, c0, c):
         assert 0 <= c0 and c0 + c <= self.C
-        return Act(self.buf, self.N, self.H, self.W, c, self.ld, self.coff + c0, self.dt)
+        return Act(self.buf, self.N, self.H, self.W, c, self.ld, self.coff + c0, self.dt, self.st, self.st_off + 2 * c0, self.st_ld)
 
     def to_nchw(self, eng):
         out = torch.empty((self.N, self.C, self.H, self.W), device=self.buf.device, dtype=torch.float32)
@@ -105,11 +129,15 @@ class Engine:
     def zeros(self, shape, dtype=None):
         return torch.zeros(shape, device=self.device, dtype=dtype or self.tdt)
 
-    def new_act(self, N, H, W, C, ld=None, dt=None, zero=False):
+    def new_act(self, N, H, W, C, ld=None, dt=None, zero=False, stats=None):
+        """stats: a StatsArena to reserve GroupNorm statistics for this buffer (it will be the input of a GroupNorm)."""
         ld = ld or C
         tdt = self.tdt if dt is None else (torch.bfloat16 if dt == nat.BF16 else torch.float32)
         buf = (torch.zeros if zero else torch.empty)((N, H, W, ld), device=self.device, dtype=tdt)
-        return Act(buf, N, H, W, C, ld, 0, self.dt if dt is None else dt)
+        a = Act(buf, N, H, W, C, ld, 0, self.dt if dt is None else dt)
+        if stats is not None:
+            a.st, a.st_off, a.st_ld = stats, stats.alloc(N * ld * 2), ld * 2
+        return a
 
     def f32(self, t):
         return t.detach().to(device=self.device, dtype=torch.float32).contiguous()
@@ -174,6 +202,8 @@ class Engine:
         if res2 is not None:
             d.res2, d.res2_dtype, d.res2_ld, d.res2_scale = res2.ptr, res2.dt, res2.ld, res2_scale
         d.y, d.y_dtype, d.y_ld = y.ptr, y.dt, y.ld
+        if y.st is not None:
+            d.gn_stats, d.gn_stats_ld = y.stats_ptr, y.st_ld       # GroupNorm statistics of y come out of the epilogue
         up = 2 if upsample else 1
         opix = x.N * (x.H * up // stride) * (x.W * up // stride)
         flops = 2 * opix * pc.Cout * (pc.k * pc.k * pc.Cin + (x2.C if x2 is not None else 0))
@@ -214,12 +244,19 @@ class Engine:
             self.n_simt += 1
             self.call("wsr_gemm_simt", C.byref(g), self.stream, flops=flops, tag="gemm_simt")
 
-    def gn_stats(self, x, stats):
-        self.call("wsr_gn_stats", x.ptr, x.dt, x.N, x.H * x.W, x.C, x.ld, stats.data_ptr(), self.stream,
+    def gn_stats(self, x, stats=None, stats_ld=None):
+        """Stand-alone statistics pass (only needed for tensors that were not produced by a convolution)."""
+        sp = x.stats_ptr if stats is None else stats.data_ptr()
+        sl = x.st_ld if stats is None else (stats_ld or 2 * x.C)
+        self.call("wsr_gn_stats", x.ptr, x.dt, x.N, x.H * x.W, x.C, x.ld, sp, sl, self.stream,
                   nbytes=x.N * x.H * x.W * x.C * (2 if x.dt == nat.BF16 else 4))
 
-    def gn_apply(self, x, stats, gamma, beta, groups, act, y, eps=1e-5):
-        self.call("wsr_gn_apply", x.ptr, x.dt, x.N, x.H * x.W, x.C, x.ld, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+    def gn_apply(self, x, gamma, beta, groups, act, y, eps=1e-5, stats=None, stats_ld=None):
+        """y = act(GroupNorm(x)); the statistics come from x's arena slot (filled by the producing convolution)."""
+        sp = x.stats_ptr if stats is None else stats.data_ptr()
+        sl = x.st_ld if stats is None else (stats_ld or 2 * x.C)
+        assert sp, "gn_apply: no statistics attached to the input"
+        self.call("wsr_gn_apply", x.ptr, x.dt, x.N, x.H * x.W, x.C, x.ld, sp, sl, gamma.data_ptr(), beta.data_ptr(),
                   groups, eps, act, y.ptr, y.dt, y.ld, self.stream,
                   nbytes=2 * x.N * x.H * x.W * x.C * (2 if x.dt == nat.BF16 else 4))
         return y

@@ -16,7 +16,7 @@ import math
 import torch
 
 from . import _native as nat
-from .engine import Act, Engine
+from .engine import Act, Engine, StatsArena
 
 
 class _L:
@@ -101,35 +101,32 @@ class UNetPlan:
     def _buffers(self):
         e, B = self.eng, self.B
         bf = e.mode == "bf16"
+        arena = self.arena = StatsArena()
         # concat buffers of the up path: ups res-block j reads cat([x, feats.pop()])
         up_res = [r for r in self.ups if r.kind == "res"]
         for r in up_res:
-            r.cat = e.new_act(B, r.h, r.w, r.cx + r.cs)
+            r.cat = e.new_act(B, r.h, r.w, r.cx + r.cs, stats=arena)
         nfeat = len(self.feat_shapes)
         assert nfeat == len(up_res)
         feat_dst = [None] * nfeat
         for j, r in enumerate(up_res):
             feat_dst[nfeat - 1 - j] = r.cat.slice(r.cx, r.cs)
         # destination of each layer's main-path output
-        stats_elems = 0
         max_scores = 0
 
         def res_scratch(r, y):
-            nonlocal stats_elems, max_scores
+            nonlocal max_scores
             r.y = y
             r.a1 = e.new_act(B, r.h, r.w, r.cin)
-            r.hbuf = e.new_act(B, r.h, r.w, r.cout)
+            r.hbuf = e.new_act(B, r.h, r.w, r.cout, stats=arena)
             r.a2 = e.new_act(B, r.h, r.w, r.cout)
-            r.st1 = stats_elems; stats_elems += B * r.cin * 2
-            r.st2 = stats_elems; stats_elems += B * r.cout * 2
             if r.attn:
                 n = r.h * r.w
-                r.rbuf = e.new_act(B, r.h, r.w, r.cout)
+                r.rbuf = e.new_act(B, r.h, r.w, r.cout, stats=arena)
                 r.nbuf = e.new_act(B, r.h, r.w, r.cout)
                 r.qk = e.new_act(B, r.h, r.w, 2 * r.cout)
                 r.vT = e.empty((B, r.cout, n))
                 r.obuf = e.new_act(B, r.h, r.w, r.cout)
-                r.st3 = stats_elems; stats_elems += B * r.cout * 2
                 max_scores = max(max_scores, B * n * n)
 
         # down path
@@ -146,7 +143,7 @@ class UNetPlan:
             else:
                 if self.kind == "resdiff":
                     # main path continues with the plain strided-conv output; the skip is its HF-guided attention
-                    r.y = e.new_act(B, r.h, r.w, r.cout)
+                    r.y = e.new_act(B, r.h, r.w, r.cout, stats=arena)
                     n = r.h * r.w
                     ca = _L(mod=self.net.hf_ca_list[hf_i], c=r.cout, h=r.h, w=r.w, x=r.y, y=feat_dst[i], level=hf_i)
                     ca.nbuf = e.new_act(B, r.h, r.w, r.cout)
@@ -155,7 +152,6 @@ class UNetPlan:
                     ca.obuf = e.new_act(B, r.h, r.w, r.cout)
                     ca.q = e.new_act(B, r.h, r.w, r.cout)
                     ca.qimg = e.new_act(B, r.h, r.w, self.C_img, dt=nat.F32)
-                    ca.st = stats_elems; stats_elems += B * r.cout * 2
                     max_scores = max(max_scores, B * n * n)
                     r.ca = ca
                     self.hfca.append(ca)
@@ -163,7 +159,7 @@ class UNetPlan:
                 else:
                     r.y = feat_dst[i]
         # mid: mid.0 -> temp, mid.1 -> x slot of the first up concat buffer
-        res_scratch(self.mids[0], e.new_act(B, self.mids[0].h, self.mids[0].w, self.mids[0].cout))
+        res_scratch(self.mids[0], e.new_act(B, self.mids[0].h, self.mids[0].w, self.mids[0].cout, stats=arena))
         res_scratch(self.mids[1], up_res[0].cat.slice(0, up_res[0].cx))
         # up path: each layer writes into the x slot of the next res block's concat buffer
         for k, r in enumerate(self.ups):
@@ -172,7 +168,7 @@ class UNetPlan:
             if following is not None and following.kind == "res":
                 dst = following.cat.slice(0, following.cx)
             else:
-                dst = e.new_act(B, r.h, r.w, r.cout)
+                dst = e.new_act(B, r.h, r.w, r.cout, stats=arena)
             if r.kind == "res":
                 res_scratch(r, dst)
             else:
@@ -181,11 +177,10 @@ class UNetPlan:
         # fix-up: an Upsample layer is fed by the res block before it (plain buffer) and feeds the next res block
         # head
         self.final_a = e.new_act(B, self.H, self.W, self.final_cin)
-        self.st_final = stats_elems; stats_elems += B * self.final_cin * 2
         self.eps_nhwc = e.new_act(B, self.H, self.W, self.C_img, dt=nat.F32)
         self.eps = self.eps_nhwc.buf.view(B, self.C_img, self.H, self.W) if self.C_img == 1 else \
             e.empty((B, self.C_img, self.H, self.W), torch.float32)
-        self.stats = torch.zeros(stats_elems, device=e.device, dtype=torch.float64)
+        self.stats = arena.finalize(e.device)
         self.scores = e.empty((max_scores,), torch.float32) if max_scores else None
         self.probs = e.empty((max_scores,)) if max_scores else None
         # level embedding
@@ -377,22 +372,15 @@ class UNetPlan:
         self.run(self.x_t)
         return self.eps.clone()
 
-    def _stat(self, off, n):
-        return self.stats[off:off + n]
-
     def _rowvec(self, r):
         return self.cur_proj.data_ptr() + 4 * r.proj_off
 
     def _res_block(self, r, x, extra_res=None):
         e, B, G = self.eng, self.B, self.groups
         SW = nat.ACT_SWISH
-        s1 = self._stat(r.st1, B * r.cin * 2)
-        e.gn_stats(x, s1)
-        e.gn_apply(x, s1, r.g1, r.b1, G, SW, r.a1)
+        e.gn_apply(x, r.g1, r.b1, G, SW, r.a1)
         e.conv(r.a1, r.conv1, r.hbuf, rowvec=self._rowvec(r), rowvec_ld=self.P)
-        s2 = self._stat(r.st2, B * r.cout * 2)
-        e.gn_stats(r.hbuf, s2)
-        e.gn_apply(r.hbuf, s2, r.g2, r.b2, G, SW, r.a2)
+        e.gn_apply(r.hbuf, r.g2, r.b2, G, SW, r.a2)
         dst = r.rbuf if r.attn else r.y
         er = None if r.attn else extra_res
         if r.has_res_conv:
@@ -400,9 +388,7 @@ class UNetPlan:
         else:
             e.conv(r.a2, r.conv2, dst, res=x, res2=er)
         if r.attn:
-            s3 = self._stat(r.st3, B * r.cout * 2)
-            e.gn_stats(r.rbuf, s3)
-            e.gn_apply(r.rbuf, s3, r.g3, r.b3, G, nat.ACT_NONE, r.nbuf)
+            e.gn_apply(r.rbuf, r.g3, r.b3, G, nat.ACT_NONE, r.nbuf)
             e.conv(r.nbuf, r.wqk, r.qk, bias=False)
             self._v_transposed(r.wv, r.nbuf, r.vT)
             n = r.h * r.w
@@ -420,9 +406,7 @@ class UNetPlan:
 
     def _hf_ca(self, ca):
         e, B = self.eng, self.B
-        s = self._stat(ca.st, B * ca.c * 2)
-        e.gn_stats(ca.x, s)
-        e.gn_apply(ca.x, s, ca.g, ca.b, 32, nat.ACT_NONE, ca.nbuf)       # norm_groups fixed at 32 (guided_cross_attention.py:15)
+        e.gn_apply(ca.x, ca.g, ca.b, 32, nat.ACT_NONE, ca.nbuf)       # norm_groups fixed at 32 (guided_cross_attention.py:15)
         e.conv(ca.nbuf, ca.wk, ca.kbuf, bias=False)
         self._v_transposed(ca.wv, ca.nbuf, ca.vT)
         n = ca.h * ca.w
@@ -459,9 +443,7 @@ class UNetPlan:
                 x = self._res_block(r, r.cat)
             else:
                 x = e.conv(x, r.conv, r.y, upsample=True)
-        sf = self._stat(self.st_final, B * self.final_cin * 2)
-        e.gn_stats(x, sf)
-        e.gn_apply(x, sf, self.gf, self.bf_, self.groups, nat.ACT_SWISH, self.final_a)
+        e.gn_apply(x, self.gf, self.bf_, self.groups, nat.ACT_SWISH, self.final_a)
         e.conv(self.final_a, self.final, self.eps_nhwc)
         if self.C_img != 1:
             e.call("wsr_nhwc_to_nchw", self.eps_nhwc.ptr, nat.F32, self.eps_nhwc.ld, B, self.C_img, self.H, self.W,

@@ -50,6 +50,14 @@ CONV_CASES = [
     (3, 192, 256, 4, 8, 3, 1, False),
     (2, 64, 64, 2, 4, 3, 1, False),
     (1, 64, 128, 32, 256, 3, 1, False),
+    # tiles that are segments of one image row -> "halo" mode of the tcgen05 kernel (one activation fetch per 9 taps)
+    (2, 128, 64, 5, 128, 3, 1, False),
+    (1, 192, 256, 3, 256, 3, 1, False),
+    (1, 64, 64, 3, 128, 3, 1, True),
+    # even row counts -> two output rows per tile (two TMEM accumulators share each weight tile)
+    (2, 64, 64, 4, 256, 3, 1, False),
+    (1, 128, 128, 6, 128, 3, 1, False),
+    (1, 64, 64, 4, 128, 3, 1, True),
 ]
 
 
@@ -117,12 +125,15 @@ def test_conv_tc_vs_simt(case):
     assert rel_l2(y_si.to_nchw(eng), ref) < 1e-4
 
 
-def test_conv_tc_second_segment_slices_and_f32_out():
-    """fused 1x1 res_conv segment, channel-slice input/output pitches, fp32 output, Cout=1 with padded weight rows."""
+@pytest.mark.parametrize("hw", [(16, 32), (4, 128)])
+def test_conv_tc_second_segment_slices_and_f32_out(hw):
+    """fused 1x1 res_conv segment, channel-slice input/output pitches, fp32 output, Cout=1 with padded weight rows
+    (classic and halo tiles)."""
     torch.manual_seed(3)
     dev = _dev()
     eng = Engine(dev, "bf16")
-    N, Cin, Cout, H, W = 2, 128, 128, 16, 32
+    N, Cin, Cout = 2, 128, 128
+    H, W = hw
     x = torch.randn(N, Cin, H, W, device=dev)
     x2 = torch.randn(N, 192, H, W, device=dev)
     w = torch.randn(Cout, Cin, 3, 3, device=dev) / math.sqrt(Cin * 9)
@@ -199,7 +210,7 @@ def test_group_norm(mode, shape):
     ref = ref * torch.sigmoid(ref)
     stats = torch.zeros(N * Cc * 2, device=dev, dtype=torch.float64)
     eng.gn_stats(xa, stats)
-    y = eng.gn_apply(xa, stats, g, b, 32, nat.ACT_SWISH, eng.new_act(N, H, W, Cc))
+    y = eng.gn_apply(xa, g, b, 32, nat.ACT_SWISH, eng.new_act(N, H, W, Cc), stats=stats)
     assert rel_l2(y.to_nchw(eng), ref) < (2e-5 if mode == "fp32" else 4e-3)
 
 
@@ -304,3 +315,28 @@ def test_attention_tc_fused_vs_torch(shape):
     o2 = eng.new_act(B, H, W, d, zero=True)
     eng.attention(qa, ka, vT, o2, scores, probs)
     assert rel_l2(o2.to_nchw(eng), ref) < 1e-2
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 16, 32, 3, 1, False), (2, 64, 128, 16, 32, 3, 2, False), (1, 64, 64, 8, 16, 3, 1, True),
+                                  (3, 128, 64, 2, 4, 1, 1, False), (2, 64, 64, 6, 256, 3, 1, False), (2, 64, 128, 4, 128, 3, 1, True)])
+def test_conv_tc_fused_gn_stats(case):
+    """GroupNorm statistics produced by the conv epilogue == statistics of the stored output (into a concat slot)."""
+    N, Cin, Cout, H, W, k, stride, up = case
+    torch.manual_seed(10)
+    dev = _dev()
+    eng = Engine(dev, "bf16")
+    arena = engine_mod.StatsArena()
+    OH, OW = (H * (2 if up else 1)) // stride, (W * (2 if up else 1)) // stride
+    cat = eng.new_act(N, OH, OW, Cout + 64, zero=True, stats=arena)
+    arena.finalize(dev)
+    y = cat.slice(64, Cout)
+    x = torch.randn(N, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, k, k, device=dev) / math.sqrt(Cin * k * k)
+    b = torch.randn(Cout, device=dev)
+    eng.conv(_nhwc(x, eng), eng.pack_conv(w, b), y, stride=stride, upsample=up)
+    assert eng.n_tc == 1
+    got = arena.tensor.view(N, Cout + 64, 2)[:, 64:, :]
+    yv = y.to_nchw(eng).double()
+    ref = torch.stack([yv.sum(dim=(2, 3)), (yv * yv).sum(dim=(2, 3))], dim=-1)
+    assert rel_l2(got, ref) < 1e-3      # statistics are taken from the fp32 accumulators, before the bf16 store rounding
+    assert float(arena.tensor.view(N, Cout + 64, 2)[:, :64, :].abs().max()) == 0.0

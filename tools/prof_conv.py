@@ -22,7 +22,9 @@ def main():
     w = torch.randn(Cout, Cin, k, k, device=dev) / math.sqrt(Cin * k * k)
     b = torch.randn(Cout, device=dev)
     pc = eng.pack_conv(w, b)
-    y = eng.new_act(N, H, W, Cout)
+    arena = wsr.sub("engine").StatsArena()
+    y = eng.new_act(N, H, W, Cout, stats=arena if os.environ.get("PROF_STATS") else None)
+    arena.finalize(dev)
     rv = torch.randn(N, Cout, device=dev)
     for _ in range(2):
         eng.conv(x, pc, y, rowvec=rv.data_ptr(), rowvec_ld=Cout)
