@@ -1,0 +1,195 @@
+"""RRDB encoder -- drop-in for the reference's models/rrdb_encoder/RRDBNet.py:11-133 (same class names, constructor
+arguments and state_dict keys).  ``forward(x, get_fea)`` returns ``(sr_image, [18 feature maps])`` like the reference;
+all convolutions run in the CUDA engine:
+
+  * every ResidualDenseBlock owns ONE NHWC buffer of nf + 4*gc channels; conv_k reads the channel prefix and writes its
+    growth slice in place (LeakyReLU fused), so the reference's ``torch.cat`` (:106-110) never materialises;
+  * ``x5 * 0.2 + x`` and the RRDB-level ``out * 0.2 + x`` (:111, :133) are epilogue scale/residual terms;
+  * channel prefixes that are not a multiple of 64 (96, 160) are read as the next multiple of 64 with zero weights, so
+    all 255 dense-block convolutions are eligible for the tcgen05 kernel.
+"""
+import functools
+
+import torch
+from torch import nn
+
+from ... import _native as nat
+from ...engine import Engine
+
+
+def make_layer(block, n_layers, seq=False):
+    layers = [block() for _ in range(n_layers)]
+    return nn.Sequential(*layers) if seq else nn.ModuleList(layers)
+
+
+class ResidualDenseBlock_5C(nn.Module):
+    def __init__(self, nf=64, gc=32, bias=True):
+        super().__init__()
+        self.conv1 = nn.Conv2d(nf, gc, 3, 1, 1, bias=bias)
+        self.conv2 = nn.Conv2d(nf + gc, gc, 3, 1, 1, bias=bias)
+        self.conv3 = nn.Conv2d(nf + 2 * gc, gc, 3, 1, 1, bias=bias)
+        self.conv4 = nn.Conv2d(nf + 3 * gc, gc, 3, 1, 1, bias=bias)
+        self.conv5 = nn.Conv2d(nf + 4 * gc, nf, 3, 1, 1, bias=bias)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
+
+
+class RRDB(nn.Module):
+    def __init__(self, nf, gc=32):
+        super().__init__()
+        self.RDB1 = ResidualDenseBlock_5C(nf, gc)
+        self.RDB2 = ResidualDenseBlock_5C(nf, gc)
+        self.RDB3 = ResidualDenseBlock_5C(nf, gc)
+
+
+class _RRDBPlan:
+    """Buffers + packed weights for one (batch, h, w, precision)."""
+
+    def __init__(self, net, B, h, w, device, precision):
+        self.net, self.B, self.h, self.w = net, B, h, w
+        e = self.eng = Engine(device, precision)
+        nf, gc = net.nf, net.gc
+        self.wide = nf + 4 * gc
+        nb = len(net.RRDB_trunk)
+        self.x0 = e.new_act(B, h, w, net.in_nc, dt=nat.F32)
+        self.first = e.new_act(B, h, w, nf)
+        # dense buffers: one per RDB (zero-initialised: padded reads hit zero weights, the data must stay finite)
+        self.dense = [[e.new_act(B, h, w, self.wide, zero=True) for _ in range(3)] for _ in range(nb)]
+        self.out_last = e.new_act(B, h, w, nf)          # output of the last RRDB
+        self.trunk = e.new_act(B, h, w, nf)
+        self.up1 = e.new_act(B, 2 * h, 2 * w, nf)
+        self.up2 = e.new_act(B, 4 * h, 4 * w, nf)
+        self.hr = e.new_act(B, 4 * h, 4 * w, nf)
+        self.last = e.new_act(B, 4 * h, 4 * w, net.out_nc, dt=nat.F32)
+        self._wver = None
+        self.refresh()
+
+    def refresh(self):
+        v = tuple(p._version for p in self.net.parameters()) + tuple(p.data_ptr() for p in self.net.parameters())
+        if v == self._wver:
+            return
+        self._wver = v
+        e, net = self.eng, self.net
+        bf = e.mode == "bf16"
+
+        def pad64(c):
+            return (c + 63) // 64 * 64 if bf else c
+
+        with torch.no_grad():
+            self.w_first = self._pack_f32(net.conv_first)
+            self.blocks = []
+            for rrdb in net.RRDB_trunk:
+                packs = []
+                for rdb in (rrdb.RDB1, rrdb.RDB2, rrdb.RDB3):
+                    convs = [rdb.conv1, rdb.conv2, rdb.conv3, rdb.conv4, rdb.conv5]
+                    packs.append([e.pack_conv(c.weight, c.bias, cin_pad=min(pad64(c.in_channels), self.wide),
+                                              rows=64 if bf else None) for c in convs])
+                self.blocks.append(packs)
+            self.w_trunk = e.pack_conv(net.trunk_conv.weight, net.trunk_conv.bias)
+            self.w_up1 = e.pack_conv(net.upconv1.weight, net.upconv1.bias)
+            self.w_up2 = e.pack_conv(net.upconv2.weight, net.upconv2.bias)
+            self.w_hr = e.pack_conv(net.HRconv.weight, net.HRconv.bias)
+            self.w_last = e.pack_conv(net.conv_last.weight, net.conv_last.bias, rows=64 if bf else None)
+        torch.cuda.current_stream(e.device).synchronize()
+        e._keep.clear()
+
+    def _pack_f32(self, conv):
+        from ...engine import PackedConv
+        e = self.eng
+        w = e.f32(conv.weight)
+        Cout, Cin, KH, KW = w.shape
+        pc = PackedConv()
+        pc.Cout, pc.Cin, pc.k, pc.Cin_pad, pc.rows = Cout, Cin, KH, Cin, Cout
+        pc.bias = e.f32(conv.bias)
+        pc.w = e.empty((KH * KW, Cout, Cin), torch.float32)
+        nat.call("wsr_pack_conv_weight", w.data_ptr(), Cout, Cin, KH, KW, pc.w.data_ptr(), nat.F32, Cout, Cin, e.stream)
+        e._keep.append(w)
+        return pc
+
+    def run(self, x):
+        """x: LR (B, C, h, w) fp32.  Returns (list of nb+1 feature Acts, fea Act) -- features stay on the device."""
+        e, net = self.eng, self.net
+        nf, gc = net.nf, net.gc
+        LR = nat.ACT_LRELU02
+        xin = x.to(torch.float32).contiguous()
+        ones = torch.ones_like(xin)
+        x01 = torch.empty_like(xin)
+        # x = (x + 1) / 2   (RRDBNet.py:40)
+        nat.call("wsr_axpby", xin.data_ptr(), nat.F32, 1, 0.5, ones.data_ptr(), nat.F32, 1, 0.5, x01.data_ptr(), nat.F32, 1,
+                 xin.numel(), 1, e.stream)
+        e.nchw_to_act(x01, self.x0)
+        nb = len(self.blocks)
+        e.conv(self.x0, self.w_first, self.first, force_simt=True)
+        # the trunk input lives in channel slot [0, nf) of the first dense buffer
+        nat.call("wsr_axpby", self.first.ptr, self.first.dt, self.first.ld, 1.0, self.first.ptr, self.first.dt, self.first.ld, 0.0,
+                 self.dense[0][0].ptr, self.dense[0][0].dt, self.dense[0][0].ld, self.B * self.h * self.w, nf, e.stream)
+        feas = []
+        for i, packs in enumerate(self.blocks):
+            rrdb_in = self.dense[i][0].slice(0, nf)
+            for j, pk in enumerate(packs):
+                D = self.dense[i][j]
+                for k in range(4):
+                    e.conv(D.slice(0, pk[k].Cin_pad), pk[k], D.slice(nf + k * gc, gc), act=LR)
+                xj = D.slice(0, nf)
+                if j < 2:
+                    e.conv(D.slice(0, pk[4].Cin_pad), pk[4], self.dense[i][j + 1].slice(0, nf), out_scale=0.2, res=xj)
+                else:
+                    dst = self.dense[i + 1][0].slice(0, nf) if i + 1 < nb else self.out_last
+                    # (conv5*0.2 + x3)*0.2 + rrdb_in  (RRDBNet.py:111, 133)
+                    e.conv(D.slice(0, pk[4].Cin_pad), pk[4], dst, out_scale=0.04, res=xj, res_scale=0.2, res2=rrdb_in)
+                    feas.append(dst)
+        e.conv(feas[-1], self.w_trunk, self.trunk, res=self.first)            # fea_first + trunk_conv(fea)
+        feas.append(self.trunk)
+        return feas
+
+    def sr_image(self):
+        """The upsampling tail (RRDBNet.py:49-55); only needed when the encoder's own SR output is used."""
+        e = self.eng
+        LR = nat.ACT_LRELU02
+        e.conv(self.trunk, self.w_up1, self.up1, upsample=True, act=LR)
+        e.conv(self.up1, self.w_up2, self.up2, upsample=True, act=LR)
+        e.conv(self.up2, self.w_hr, self.hr, act=LR)
+        e.conv(self.hr, self.w_last, self.last)
+        return self.last.to_nchw(e).clamp(0, 1) * 2 - 1
+
+
+class RRDBNet(nn.Module):
+    def __init__(self, in_nc, out_nc, nf, nb, gc=32, precision="bf16"):
+        super().__init__()
+        self.in_nc, self.out_nc, self.nf, self.gc = in_nc, out_nc, nf, gc
+        block = functools.partial(RRDB, nf=nf, gc=gc)
+        self.conv_first = nn.Conv2d(in_nc, nf, 3, 1, 1, bias=True)
+        self.RRDB_trunk = make_layer(block, nb)
+        self.trunk_conv = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.upconv1 = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.upconv2 = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.HRconv = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.conv_last = nn.Conv2d(nf, out_nc, 3, 1, 1, bias=True)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.2)
+        self.precision = precision
+        self._plans = {}
+
+    def plan(self, x):
+        B, _, h, w = x.shape
+        key = (B, h, w, str(x.device), self.precision)
+        pl = self._plans.get(key)
+        if pl is None:
+            pl = _RRDBPlan(self, B, h, w, x.device, self.precision)
+            self._plans[key] = pl
+        pl.refresh()
+        return pl
+
+    @torch.no_grad()
+    def forward(self, x, get_fea=False):
+        pl = self.plan(x)
+        feas = pl.run(x)
+        out = pl.sr_image()
+        if get_fea:
+            return out, [f.to_nchw(pl.eng) for f in feas]
+        return out
+
+    @torch.no_grad()
+    def features_device(self, x):
+        """Fast path used by SRDiffDiffusion: the 18 feature maps as device-resident NHWC Acts (no NCHW round trip, no
+        SR tail -- the reference discards the SR image on this path, srdiff_diffusion.py:107-108)."""
+        pl = self.plan(x)
+        return pl, pl.run(x)

@@ -1,0 +1,63 @@
+"""train.py -- same command line as the reference's train.py:208-212 (``-c CONFIG -p {train,val} -gpu IDS``).
+
+``-p val`` runs the validation loop (generate_sr per batch, RMSE in standardised units) on the CUDA path.
+``-p train`` builds the optimiser and runs ``optimize_parameters``; the backward pass of the CUDA denoiser is not
+implemented yet, so training stops with an explicit NotImplementedError after the forward loss."""
+import argparse
+import logging
+import os
+import sys
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+import wsr  # noqa: E402
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("-c", "--config", type=str, help="JSON file for configuration")
+    ap.add_argument("-p", "--phase", type=str, choices=["train", "val"], default="train")
+    ap.add_argument("-gpu", "--gpu_ids", type=str, default=None)
+    args = ap.parse_args(argv)
+    logging.basicConfig(level=logging.INFO)
+    log = logging.getLogger("base")
+
+    Config = wsr.sub("configs.config").Config
+    create_model = wsr.sub("models.base_model").create_model
+    data = wsr.sub("data_synthetic")
+    import numpy as np
+    import random
+    random.seed(0); np.random.seed(0); torch.manual_seed(0)                 # training/utils.py:39-50
+    opt = Config(args, experiment=True).params
+    for key in ("resume_state",):
+        if opt["path"].get(key) and not os.path.exists(str(opt["path"][key]) + "_gen.pth"):
+            opt["path"][key] = None
+    pm = opt["model"].get("pretrained_model", {})
+    if pm.get("model_path") and not os.path.exists(pm["model_path"]):
+        pm["model_path"] = None
+    model = create_model(opt, None)
+    if args.phase == "val":
+        model.prepare_to_eval()
+        se, n = 0.0, 0
+        for batch, months in data.batches_from_opt(opt, "val"):
+            model.feed_data((batch, months))
+            model.generate_sr(False)
+            img = model.get_images(need_LR=True)
+            se += float(((img["SR"] - img["HR"]) ** 2).sum()); n += img["SR"].numel()
+        log.info("validation RMSE (standardised units): %.6f", (se / max(n, 1)) ** 0.5)
+        return
+    it = 0
+    for batch, months in data.batches_from_opt(opt, "train"):
+        it += 1
+        model.feed_data((batch, months))
+        model.optimize_parameters()
+        if it % opt["train"]["print_freq"] == 0:
+            log.info("iter %d  l_pix %.6f", it, model.get_current_log()["l_pix"])
+        if it % opt["train"]["save_checkpoint_freq"] == 0:
+            model.save_network(0, it)
+
+
+if __name__ == "__main__":
+    main()

@@ -77,3 +77,50 @@ def test_resdiff_loss_vs_reference():
     rel = abs(float(loss) - float(g["loss"])) / float(g["loss"])
     print("\n[parity] loss rel err = %.3e" % rel)
     assert rel < 1e-4
+
+
+def _manifest_module(tag):
+    from conftest import manifest
+    return manifest(tag)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_rrdb_encoder_vs_reference(precision):
+    g, spec = load_golden("rrdb_small"), CASES["rrdb_small"]
+    R = wsr.sub("models.rrdb_encoder.RRDBNet").RRDBNet
+    net = fill_module(R(1, 1, 64, 17, 32, precision=precision), spec["seed"]).cuda().eval()
+    assert [k for k, _ in _manifest_module("rrdb")] == list(net.state_dict().keys())
+    sr_img, feas = net(g["lr"].cuda(), True)
+    e_f = rel_l2(torch.stack([f.cpu() for f in feas], 0), g["feas"])
+    e_s = rel_l2(sr_img.cpu(), g["sr_img"])
+    print("\n[parity] rrdb %s features rel-L2 = %.3e, sr image rel-L2 = %.3e" % (precision, e_f, e_s))
+    assert e_f < TOL[precision] and e_s < (5e-2 if precision == "bf16" else 1e-4)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_srdiff_step_vs_reference(precision):
+    g, spec = load_golden("srdiff_step_small"), CASES["srdiff_step_small"]
+    cfg = spec["cfg"]
+    U = wsr.sub("models.diffusion_models.srdiff.unet").UNet
+    R = wsr.sub("models.rrdb_encoder.RRDBNet").RRDBNet
+    net = U(in_channel=cfg["in_channel"], out_channel=cfg["out_channel"], norm_groups=32, inner_channel=64,
+            channel_mults=cfg["channel_mults"], attn_res=cfg["attn_res"], res_blocks=2, dropout=0, image_height=32,
+            image_width=64, image_channels=1, precision=precision)
+    net = fill_module(net, spec["seed"]).cuda().eval()
+    rrdb = fill_module(R(1, 1, 64, 17, 32, precision=precision), spec["seed"] + 1).cuda().eval()
+    with torch.no_grad():
+        _, feas = rrdb(g["lr"].cuda(), True)
+        eps = net((feas, g["x_t"].cuda()), g["level"].cuda())
+    err = rel_l2(eps.cpu(), g["eps"])
+    print("\n[parity] srdiff step %s eps rel-L2 = %.3e" % (precision, err))
+    assert err < TOL[precision], err
+
+
+def test_simple_cnn_vs_reference():
+    g, spec = load_golden("simple_cnn"), CASES["simple_cnn"]
+    S = wsr.sub("models.simple_cnn.Simple_CNN").SimpleCNN
+    net = fill_module(S(scale_factor=4, channels=1), spec["seed"]).cuda().eval()
+    out = net(g["lr"].cuda())
+    err = rel_l2(out.cpu(), g["out"])
+    print("\n[parity] simple_cnn rel-L2 = %.3e" % err)
+    assert err < 1e-5
