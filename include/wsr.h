@@ -54,6 +54,9 @@ int wsr_device_is_sm100(void);
  *
  * X is x, or its nearest-neighbour x2 upsampling when `upsample` != 0 (functional_layers.py:62-67); zero padding
  * (ksize-1)/2; stride 1 or 2.  H, W are the dimensions of x; the output is (H*up/stride, W*up/stride).
+ * upsample = 1: w holds the 9 original taps (every output phase evaluates all 9, bit-for-bit the reference's sum).
+ * upsample = 2: w holds the PHASE-MERGED taps [4 phases][2x2][w_rows][Cin] made by wsr_pack_upsample_weight: taps that
+ *               read the same source pixel are pre-summed, 2.25x fewer MACs (weights are summed in fp32, then rounded).
  * ------------------------------------------------------------------------------------------------------------- */
 typedef struct {
   const void* x;  int x_dtype;  int N, H, W, Cin;  int x_ld;
@@ -138,6 +141,10 @@ int wsr_nhwc_to_nchw(const void* src, int src_dtype, int src_ld, int N, int C, i
 /* OIHW fp32 -> [tap][Cout_pad][Cin_pad] (zero padded). */
 int wsr_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int KH, int KW, void* dst, int dst_dtype,
                          int Cout_pad, int Cin_pad, void* stream);
+/* Phase-merged weights of "nearest x2 upsample + conv3x3": OIHW fp32 (Cout,Cin,3,3) -> [phase*4 + a*2 + b][Cout_pad][Cin_pad],
+ * phase = py*2+px; (a, b) index the source offsets {-1,0} (py/px = 0) or {0,+1} (py/px = 1). */
+int wsr_pack_upsample_weight(const float* w_oihw, int Cout, int Cin, void* dst, int dst_dtype, int Cout_pad, int Cin_pad,
+                             void* stream);
 /* ConvTranspose2d weight (Cin, Cout, KH, KW) fp32 -> [tap][Cout][Cin]. */
 int wsr_pack_convT_weight(const float* w_iohw, int Cin, int Cout, int KH, int KW, void* dst, int dst_dtype, void* stream);
 /* dst[i] = (T) src[i] */

@@ -68,6 +68,7 @@ SIGNATURES = {
     "wsr_nchw_to_nhwc": [_P, _I, _I, _I, _I, _P, _I, _I, _P],
     "wsr_nhwc_to_nchw": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "wsr_pack_conv_weight": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P],
+    "wsr_pack_upsample_weight": [_P, _I, _I, _P, _I, _I, _I, _P],
     "wsr_pack_convT_weight": [_P, _I, _I, _I, _I, _P, _I, _P],
     "wsr_cast": [_P, _I, _P, _I, _L, _P],
     "wsr_upsample2x": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P],

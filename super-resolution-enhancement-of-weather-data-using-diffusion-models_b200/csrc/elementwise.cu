@@ -38,6 +38,28 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
   st_dt(dst, i, dt, v);
 }
 
+// merged taps of upsample+conv: row sets  py=0: a=0 -> {ky 0}, a=1 -> {ky 1,2};  py=1: a=0 -> {ky 0,1}, a=1 -> {ky 2}
+__global__ void pack_upsample_weight_kernel(const float* __restrict__ w, int Cout, int Cin, void* dst, int dt, int Cout_pad,
+                                            int Cin_pad, int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int ci = (int)(i % Cin_pad);
+  int64_t r = i / Cin_pad;
+  int co = (int)(r % Cout_pad);
+  int t = (int)(r / Cout_pad);           // phase*4 + a*2 + b
+  int ph = t >> 2, a = (t >> 1) & 1, b = t & 1;
+  int py = ph >> 1, px = ph & 1;
+  float v = 0.f;
+  if (co < Cout && ci < Cin) {
+    int ky0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), ky1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+    int kx0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), kx1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+    const float* wp = w + ((int64_t)co * Cin + ci) * 9;
+    for (int ky = ky0; ky <= ky1; ++ky)
+      for (int kx = kx0; kx <= kx1; ++kx) v += wp[ky * 3 + kx];
+  }
+  st_dt(dst, i, dt, v);
+}
+
 __global__ void pack_convT_weight_kernel(const float* __restrict__ w, int Cin, int Cout, int taps, void* dst, int dt, int64_t total) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // dst index = (t*Cout + co)*Cin + ci
   if (i >= total) return;
@@ -429,6 +451,16 @@ extern "C" int wsr_pack_conv_weight(const float* w, int Cout, int Cin, int KH, i
               WSR_E_INVALID, "pack_conv_weight: bad argument");
   int64_t total = (int64_t)KH * KW * Cout_pad * Cin_pad;
   pack_conv_weight_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, KH * KW, dst, dst_dtype, Cout_pad, Cin_pad, total);
+  WSR_LAUNCH_OK();
+  return WSR_OK;
+}
+
+extern "C" int wsr_pack_upsample_weight(const float* w, int Cout, int Cin, void* dst, int dst_dtype, int Cout_pad, int Cin_pad,
+                                        void* stream) {
+  WSR_REQUIRE(w && dst && valid_dtype(dst_dtype) && Cout > 0 && Cin > 0 && Cout_pad >= Cout && Cin_pad >= Cin, WSR_E_INVALID,
+              "pack_upsample_weight: bad argument");
+  int64_t total = (int64_t)16 * Cout_pad * Cin_pad;
+  pack_upsample_weight_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, dst, dst_dtype, Cout_pad, Cin_pad, total);
   WSR_LAUNCH_OK();
   return WSR_OK;
 }

@@ -583,7 +583,10 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
   const int OH = d->H * up / d->stride, OW = d->W * up / d->stride;
   // grid of GEMM rows: output pixels (stride 1 / 2) or input-resolution pixels per output phase (upsample)
   const int GH = d->upsample ? d->H : OH, GW = d->upsample ? d->W : OW;
-  const int taps = d->ksize * d->ksize;
+  const bool merged = d->upsample == 2;          // phase-merged 2x2 taps (wsr_pack_upsample_weight)
+  WSR_REQUIRE(!merged || d->ksize == 3, WSR_E_UNSUPPORTED, "conv_tc: merged upsample needs ksize 3");
+  const int taps = merged ? 4 : d->ksize * d->ksize;
+  const int wtaps = merged ? 16 : taps;          // taps stored in the weight tensor
   const int pad = (d->ksize - 1) / 2;
   const int nphase = d->upsample ? 4 : 1;
 
@@ -628,7 +631,7 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
   {
     const int wrows = d->w_rows > 0 ? d->w_rows : d->Cout;
     WSR_REQUIRE(wrows >= bn || wrows % 64 == 0 || true, WSR_E_INVALID, "conv_tc: w_rows");
-    uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)wrows, (uint64_t)taps};
+    uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)wrows, (uint64_t)wtaps};
     uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cin * wrows * 2};
     uint32_t box[3] = {64, (uint32_t)bn, 1};
     rc = encode_map(&p.bmap[0], d->w, 3, dims, str, box);
@@ -673,12 +676,18 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
   for (int ph = 0; ph < nphase; ++ph) {
     const int py = ph >> 1, px = ph & 1;
     int ne = 0, kb = 0;
-    for (int ky = 0; ky < d->ksize; ++ky)
-      for (int kx = 0; kx < d->ksize; ++kx) {
+    const int kdim = merged ? 2 : d->ksize;
+    for (int ky = 0; ky < kdim; ++ky)
+      for (int kx = 0; kx < kdim; ++kx) {
         TcEntry& e = p.e[ne++];
         e.a_c0 = 0; e.b_k0 = 0; e.bmap = 0; e.b_z = (int16_t)(ky * d->ksize + kx);
         e.nchunks = (int16_t)(d->Cin / 64);
-        if (d->upsample) {
+        if (merged) {
+          e.amap = 0;
+          e.b_z = (int16_t)(ph * 4 + ky * 2 + kx);
+          e.d2 = (int16_t)((py == 0 ? -1 : 0) + ky);
+          e.d1 = (int16_t)((px == 0 ? -1 : 0) + kx);
+        } else if (d->upsample) {
           // source row = i + floor((py + ky - 1) / 2)
           int a = py + ky - pad, b = px + kx - pad;
           e.amap = 0;

@@ -155,6 +155,29 @@ using namespace wsr;
 extern "C" int wsr_conv_simt(const WsrConvDesc* d, void* stream) {
   int rc = validate_conv_desc(d);
   if (rc) return rc;
+  if (d->upsample == 2) {
+    // phase-merged weights: one launch per output phase, 2x2 taps on the SOURCE grid
+    WSR_REQUIRE(d->ksize == 3 && d->x2 == nullptr, WSR_E_UNSUPPORTED, "conv: merged upsample needs ksize 3, no second segment");
+    for (int ph = 0; ph < 4; ++ph) {
+      const int py = ph >> 1, px = ph & 1;
+      ConvSimtParams q;
+      q.d = *d;
+      q.ntaps = 4;
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          int t = a * 2 + b;
+          q.dy[t] = (py == 0 ? -1 : 0) + a; q.dx[t] = (px == 0 ? -1 : 0) + b;
+          q.wtap[t] = ph * 4 + t;
+        }
+      q.up = 1; q.UH = d->H; q.UW = d->W; q.in_stride = 1;
+      q.GH = d->H; q.GW = d->W; q.OH = 2 * d->H; q.OW = 2 * d->W;
+      q.out_mul = 2; q.out_py = py; q.out_px = px;
+      rc = launch_conv_simt(q, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
+    if (d->gn_stats) return wsr_gn_stats(d->y, d->y_dtype, d->N, 4 * d->H * d->W, d->Cout, d->y_ld, d->gn_stats, d->gn_stats_ld, stream);
+    return WSR_OK;
+  }
   ConvSimtParams p;
   p.d = *d;
   const int up = d->upsample ? 2 : 1;

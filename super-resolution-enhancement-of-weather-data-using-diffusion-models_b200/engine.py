@@ -74,7 +74,10 @@ class Act:
 class PackedConv:
     """Conv weight packed as [tap][rows][Cin_pad] in the engine dtype, fp32 bias."""
 
-    __slots__ = ("w", "bias", "Cout", "Cin", "Cin_pad", "rows", "k")
+    def __init__(self):
+        self.w = self.bias = None
+        self.Cout = self.Cin = self.Cin_pad = self.rows = self.k = 0
+        self.merged_up = False          # True: phase-merged taps of an upsample conv (wsr_pack_upsample_weight)
 
 
 class Engine:
@@ -151,8 +154,25 @@ class Engine:
         pc.Cout, pc.Cin, pc.k = Cout, Cin, KH
         pc.Cin_pad = cin_pad or Cin
         pc.rows = rows or Cout
+        pc.merged_up = False
         pc.w = self.empty((KH * KW, pc.rows, pc.Cin_pad))
         nat.call("wsr_pack_conv_weight", w.data_ptr(), Cout, Cin, KH, KW, pc.w.data_ptr(), self.dt, pc.rows, pc.Cin_pad, self.stream)
+        pc.bias = None if bias is None else self.f32(bias)
+        self._keep.append(w)
+        return pc
+
+    def pack_upsample_conv(self, weight, bias=None):
+        """Weights of 'nearest x2 upsample + conv3x3' (functional_layers.py:62-67).  In bf16 mode the taps that read the
+        same source pixel are pre-summed per output phase (2.25x fewer MACs); the fp32 check mode keeps the 9 exact taps."""
+        if self.mode != "bf16":
+            return self.pack_conv(weight, bias)
+        w = self.f32(weight)
+        Cout, Cin, KH, KW = w.shape
+        assert KH == 3 and KW == 3
+        pc = PackedConv()
+        pc.Cout, pc.Cin, pc.k, pc.Cin_pad, pc.rows, pc.merged_up = Cout, Cin, 3, Cin, Cout, True
+        pc.w = self.empty((16, Cout, Cin))
+        nat.call("wsr_pack_upsample_weight", w.data_ptr(), Cout, Cin, pc.w.data_ptr(), self.dt, Cout, Cin, self.stream)
         pc.bias = None if bias is None else self.f32(bias)
         self._keep.append(w)
         return pc
@@ -187,7 +207,8 @@ class Engine:
         d.x, d.x_dtype, d.N, d.H, d.W, d.Cin, d.x_ld = x.ptr, x.dt, x.N, x.H, x.W, pc.Cin_pad, x.ld
         assert x.C == pc.Cin_pad, (x.C, pc.Cin_pad)
         d.w, d.w_rows = pc.w.data_ptr(), pc.rows
-        d.ksize, d.stride, d.upsample = pc.k, stride, 1 if upsample else 0
+        d.ksize, d.stride, d.upsample = pc.k, stride, (2 if pc.merged_up else 1) if upsample else 0
+        assert upsample or not pc.merged_up
         d.Cout = pc.Cout
         assert y.C == pc.Cout, (y.C, pc.Cout)
         if x2 is not None:

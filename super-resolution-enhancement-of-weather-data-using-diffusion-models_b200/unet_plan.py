@@ -262,7 +262,7 @@ class UNetPlan:
                 if r.kind == "res":
                     pack_res(r)
                 else:
-                    r.conv = e.pack_conv(r.mod.conv.weight, r.mod.conv.bias)
+                    r.conv = e.pack_upsample_conv(r.mod.conv.weight, r.mod.conv.bias)
             fc = self.net.final_conv.block
             self.gf, self.bf_ = e.f32(fc[0].weight), e.f32(fc[0].bias)
             self.final = e.pack_conv(fc[3].weight, fc[3].bias, rows=64 if e.mode == "bf16" else None)

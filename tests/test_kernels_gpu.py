@@ -340,3 +340,26 @@ def test_conv_tc_fused_gn_stats(case):
     ref = torch.stack([yv.sum(dim=(2, 3)), (yv * yv).sum(dim=(2, 3))], dim=-1)
     assert rel_l2(got, ref) < 1e-3      # statistics are taken from the fp32 accumulators, before the bf16 store rounding
     assert float(arena.tensor.view(N, Cout + 64, 2)[:, :64, :].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 8, 16), (1, 128, 128, 4, 128), (1, 64, 128, 16, 32)])
+def test_upsample_conv_merged_taps(case):
+    """phase-merged 2x2 taps (2.25x fewer MACs) == nearest-x2 upsample + conv3x3, on the tcgen05 and the SIMT kernel."""
+    N, Cin, Cout, H, W = case
+    torch.manual_seed(11)
+    dev = _dev()
+    eng = Engine(dev, "bf16")
+    x = torch.randn(N, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, 3, 3, device=dev) / math.sqrt(Cin * 9)
+    b = torch.randn(Cout, device=dev)
+    xa = _nhwc(x, eng)
+    ref = _ref_conv(xa.to_nchw(eng), w, b, 1, True)
+    pm = eng.pack_upsample_conv(w, b)
+    assert pm.merged_up
+    y_tc = eng.new_act(N, 2 * H, 2 * W, Cout)
+    y_si = eng.new_act(N, 2 * H, 2 * W, Cout, dt=nat.F32)
+    eng.conv(xa, pm, y_tc, upsample=True)
+    eng.conv(xa, pm, y_si, upsample=True, force_simt=True)
+    assert eng.n_tc == 1 and eng.n_simt == 1
+    assert rel_l2(y_si.to_nchw(eng), ref) < 5e-3          # weights pre-summed in fp32, then rounded to bf16
+    assert rel_l2(y_tc.to_nchw(eng), y_si.to_nchw(eng)) < 4e-3
