@@ -13,8 +13,9 @@
 // V is consumed TRANSPOSED (vT: B x d x Nk, produced that way by the K/V projection GEMM) so that both operands of P*V
 // are K-major and can be fed by plain 128B-swizzled TMA boxes.
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-5 softmax + epilogue
-// (thread = query row; tcgen05.ld 32x32b gives each thread 32 consecutive keys of its row).
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-9 softmax + epilogue
+// (thread = query row x key half; tcgen05.ld 32x32b gives each thread 32 consecutive keys of its row; two warps per
+// SMSP keep the SFU busy while the other converts / stores).
 #include <string.h>
 
 #include "tc_common.cuh"
@@ -23,6 +24,8 @@ namespace wsr {
 
 constexpr int kBQ = 128;     // queries per CTA
 constexpr int kBK = 128;     // keys per block
+constexpr int kSoftmaxWarps = 8;                        // two warps per TMEM lane quadrant, each owning 64 of the 128 keys
+constexpr int kAttnThreads = 64 + 32 * kSoftmaxWarps;
 
 template <int D> struct AttnCfg {
   static constexpr int kChunks = D / 64;                  // 64-channel K chunks of Q / K
@@ -34,7 +37,7 @@ template <int D> struct AttnCfg {
   static constexpr int kKStages = D == 64 ? 3 : 2;
   static constexpr int kVStages = D == 64 ? 3 : 2;
   static constexpr int kSmemData = kQBytes + kKStages * kKBytes + kVStages * kVBytes + 2 * kPBytes;
-  static constexpr int kSmemBytes = kSmemData + 1024 + 256;
+  static constexpr int kSmemBytes = kSmemData + 1024 + 256 + 1024;   // + align slack + barriers + max/sum exchange
   static constexpr uint32_t kIdescQK = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBK >> 3) << 17) | ((uint32_t)(kBQ >> 4) << 24);
   static constexpr uint32_t kIdescPV = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(kBQ >> 4) << 24);
 };
@@ -47,7 +50,7 @@ struct AttnParams {
 };
 
 template <int D>
-__global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
   using Cfg = AttnCfg<D>;
   constexpr int KS = Cfg::kKStages, VS = Cfg::kVStages;
   extern __shared__ uint8_t smem_raw[];
@@ -68,6 +71,7 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
   uint64_t* p_empty = p_full + 2;          // 2
   uint64_t* o_full = p_empty + 2;          // 1
   uint32_t* tmem_slot = (uint32_t*)(o_full + 1);
+  float* xchg = (float*)(tmem_slot + 2);    // [2 halves][128 rows]: row max / row sum exchange between the two key halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kBQ;
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
     mbar_init(q_full, 1);
     for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
     for (int i = 0; i < VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], kSoftmaxWarps); mbar_init(&p_full[i], kSoftmaxWarps); mbar_init(&p_empty[i], 1); }
     mbar_init(o_full, 1);
     fence_barrier_init();
     fence_proxy_async();
@@ -164,8 +168,9 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
       umma_commit(o_full);
     }
   } else {
-    // ===================== softmax + epilogue (warps 2..5, thread = query row) =====================
+    // ===================== softmax + epilogue (warps 2..9, thread = query row x key half) =====================
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;          // 0: keys [0,64) of every block, 1: keys [64,128)
     const int row = quad * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
     float mx = -INFINITY;
@@ -175,16 +180,26 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
       mbar_wait(&s_full[sb], sph);
       tc_fence_after();
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int c2 = 0; c2 < 2; ++c2) {
         uint32_t v[32];
-        tmem_ld32(tmem_S + lane_sel + (uint32_t)(sb * kBK + ch * 32), v);
+        tmem_ld32(tmem_S + lane_sel + (uint32_t)(sb * kBK + half * 64 + c2 * 32), v);
+        // four independent max chains (a single running max would be a 64-deep dependent chain per block)
+        float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int i = 4; i < 32; i += 4) {
+          m0 = fmaxf(m0, __uint_as_float(v[i])); m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+          m2 = fmaxf(m2, __uint_as_float(v[i + 2])); m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+        }
+        mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
     }
+    xchg[half * 128 + row] = mx;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
+    mx = fmaxf(mx, xchg[(half ^ 1) * 128 + row]);
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
     const float mc = mx * p.c;
     float lsum = 0.f;
     // pass B: probabilities -> smem (K-major, 128B swizzle), row sums
@@ -195,22 +210,25 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
       mbar_wait(&s_full[sb], sph);
       mbar_wait(&p_empty[pb], pph ^ 1);
       tc_fence_after();
-      uint8_t* prow = sP + pb * Cfg::kPBytes + row * 128;
+      uint8_t* atom = sP + pb * Cfg::kPBytes + half * 16384 + row * 128;     // this half = one 64-key atom of P
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int c2 = 0; c2 < 2; ++c2) {
         uint32_t v[32];
-        tmem_ld32(tmem_S + lane_sel + (uint32_t)(sb * kBK + ch * 32), v);
+        tmem_ld32(tmem_S + lane_sel + (uint32_t)(sb * kBK + half * 64 + c2 * 32), v);
         float e[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { e[i] = exp2f(fmaf(__uint_as_float(v[i]), p.c, -mc)); lsum += e[i]; }
-        uint8_t* atom = prow + (ch >> 1) * 16384;
+        for (int i = 0; i < 32; ++i) e[i] = exp2f(fmaf(__uint_as_float(v[i]), p.c, -mc));
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;       // independent partial sums
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) { s0 += e[i]; s1 += e[i + 1]; s2 += e[i + 2]; s3 += e[i + 3]; }
+        lsum += (s0 + s1) + (s2 + s3);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 u;
           __nv_bfloat162* h = (__nv_bfloat162*)&u;
 #pragma unroll
           for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(e[q * 8 + 2 * k], e[q * 8 + 2 * k + 1]);
-          const int cc = (ch & 1) * 4 + q;
+          const int cc = c2 * 4 + q;
           *(uint4*)(atom + ((cc ^ (row & 7)) << 4)) = u;
         }
       }
@@ -219,13 +237,17 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
       __syncwarp();
       if (lane == 0) { mbar_arrive(&s_empty[sb]); mbar_arrive(&p_full[pb]); }
     }
-    // epilogue: O / l -> bf16 -> global (row = D*2 contiguous bytes)
+    xchg[half * 128 + row] = lsum;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
+    lsum += xchg[(half ^ 1) * 128 + row];
+    // epilogue: O / l -> bf16 -> global; the two halves split the D columns
     mbar_wait(o_full, 0);
     tc_fence_after();
     const float inv = 1.f / lsum;
     __nv_bfloat16* orow = (__nv_bfloat16*)p.o + (long long)b * p.o_sb + (long long)(q0 + row) * p.o_ld;
 #pragma unroll 1
-    for (int ch = 0; ch < D / 32; ++ch) {
+    for (int c2 = 0; c2 < D / 64; ++c2) {
+      const int ch = half * (D / 64) + c2;
       uint32_t v[32];
       tmem_ld32(tmem_O + lane_sel + (uint32_t)(ch * 32), v);
 #pragma unroll
@@ -257,7 +279,7 @@ static int launch_attn(const AttnParams& p, int B, int Nq, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(Nq / kBQ, B);
-  attn_tc_kernel<D><<<grid, 192, Cfg::kSmemBytes, st>>>(p);
+  attn_tc_kernel<D><<<grid, kAttnThreads, Cfg::kSmemBytes, st>>>(p);
   WSR_LAUNCH_OK();
   return WSR_OK;
 }

@@ -63,6 +63,14 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+// x * sigmoid(x) with ONE SFU op: sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5 (tanh.approx.f32, rel. error ~2^-11: below the
+// bf16 rounding of the stored result).  Used on bf16 outputs only; fp32 check mode keeps the exact form.
+__device__ __forceinline__ float swish_fast(float v) {
+  float h = 0.5f * v, t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
 // Dispatch a templated launcher on a runtime dtype.
 #define WSR_DISPATCH_DTYPE(dt, T, ...)                 \
   do {                                                 \

@@ -207,7 +207,10 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x, int HW, int C, int ld,
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) v[u][i] = apply_act(fmaf(v[u][i], sc[i], sh[i]), act);
+      for (int i = 0; i < VEC; ++i) {
+        const float t = fmaf(v[u][i], sc[i], sh[i]);
+        v[u][i] = (sizeof(TO) == 2 && act == WSR_ACT_SWISH) ? swish_fast(t) : apply_act(t, act);
+      }
       VecLoad<TO, VEC>::st(yb + (int64_t)(p + u * PL) * y_ld, v[u]);
     }
   }

@@ -80,7 +80,7 @@ template <int BLOCK_N, bool HALO, int ROWS> struct TcCfg {
   // chunk, shared by the 9 taps) and a separate ring of weight tiles.
   static constexpr int kStages = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
   static constexpr int kAStages = 2;
-  static constexpr int kBStages = BLOCK_N >= 256 ? 3 : (BLOCK_N >= 128 ? (ROWS > 1 ? 4 : 6) : 8);
+  static constexpr int kBStages = BLOCK_N >= 256 ? 3 : (BLOCK_N >= 128 ? (ROWS > 1 ? 4 : 6) : (ROWS >= 4 ? 3 : 8));
   static constexpr int kSmemData = HALO ? kAStages * kHaloStage + kBStages * kBBytes : kStages * (kABytes + kBBytes);
   static constexpr int kAccCols = ROWS * BLOCK_N;                           // one accumulator set (ROWS output rows)
   static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;   // power of two for 32..512
@@ -529,6 +529,9 @@ static int launch_tc_impl(const TcParams& p, cudaStream_t st) {
 template <int BLOCK_N>
 static int launch_tc(const TcParams& p, cudaStream_t st) {
   if (p.n_taps > 0) {
+    if constexpr (BLOCK_N <= 64) {
+      if (p.halo_rows == 4) return launch_tc_impl<BLOCK_N, true, 4>(p, st);
+    }
     if constexpr (BLOCK_N <= 128) {
       if (p.halo_rows == 2) return launch_tc_impl<BLOCK_N, true, 2>(p, st);
     }
@@ -614,9 +617,9 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
   // activation operand is fetched once per 64-channel chunk instead of once per tap; with two output rows per tile
   // (two accumulators) every weight tile is used twice as well.  Both cut the L2 -> SM traffic that bounds these layers.
   static const bool no_halo = getenv("WSR_NO_HALO") != nullptr;
-  static const int max_rows = getenv("WSR_HALO_ROWS") ? atoi(getenv("WSR_HALO_ROWS")) : 2;
+  static const int max_rows = getenv("WSR_HALO_ROWS") ? atoi(getenv("WSR_HALO_ROWS")) : 4;
   const bool halo = !no_halo && d->ksize == 3 && d->stride == 1 && p.t2 == 1 && p.t3 == 1 && p.t1 + 2 <= 130;
-  const int hrows = (halo && bn <= 128 && GH % 2 == 0 && max_rows >= 2) ? 2 : 1;
+  const int hrows = (halo && bn <= 64 && GH % 4 == 0 && max_rows >= 4) ? 4 : (halo && bn <= 128 && GH % 2 == 0 && max_rows >= 2) ? 2 : 1;
   p.n_taps = halo ? taps : 0;
   p.halo_rows = hrows;
   p.halo_bytes = (p.t1 + 2) * (hrows + 2) * 128;
