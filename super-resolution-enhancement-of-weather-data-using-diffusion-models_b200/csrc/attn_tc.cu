@@ -13,7 +13,7 @@
 // V is consumed TRANSPOSED (vT: B x d x Nk, produced that way by the K/V projection GEMM) so that both operands of P*V
 // are K-major and can be fed by plain 128B-swizzled TMA boxes.
 //
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-9 softmax + epilogue
+// Warp roles (320 threads): warps 0-7 softmax + epilogue, warp 8 TMA producer, warp 9 TMEM owner + MMA issuer
 // (thread = query row x key half; tcgen05.ld 32x32b gives each thread 32 consecutive keys of its row; two warps per
 // SMSP keep the SFU busy while the other converts / stores).
 #include <string.h>
@@ -73,12 +73,14 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
   uint32_t* tmem_slot = (uint32_t*)(o_full + 1);
   float* xchg = (float*)(tmem_slot + 2);    // [2 halves][128 rows]: row max / row sum exchange between the two key halves
 
+  // warp roles: 0..7 softmax/epilogue, 8 TMA producer, 9 MMA issuer (highest warp id = highest issue priority)
+  constexpr int kProducerWarp = kSoftmaxWarps, kMmaWarp = kSoftmaxWarps + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kBQ;
   const int b = blockIdx.y;
   const int NB = p.nblocks;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     prefetch_tmap(&p.qmap); prefetch_tmap(&p.kmap); prefetch_tmap(&p.vmap);
     mbar_init(q_full, 1);
     for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
   const uint32_t tmem_S = tmem_base;            // 2 x 128 columns
   const uint32_t tmem_O = tmem_base + 256;      // D columns
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       mbar_expect_tx(q_full, Cfg::kQBytes);
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       mbar_wait(q_full, 0);
@@ -168,9 +170,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
       umma_commit(o_full);
     }
   } else {
-    // ===================== softmax + epilogue (warps 2..9, thread = query row x key half) =====================
+    // ===================== softmax + epilogue (warps 0..7, thread = query row x key half) =====================
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;          // 0: keys [0,64) of every block, 1: keys [64,128)
+    const int half = warp >> 2;          // 0: keys [0,64) of every block, 1: keys [64,128)
     const int row = quad * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
     float mx = -INFINITY;
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }

@@ -8,8 +8,8 @@
 // maps), nearest-x2-upsample + 3x3 (one launch per output phase), a fused second K segment (the ResnetBlock 1x1
 // `res_conv`), and the batched attention products Q*K^T and P*V.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
-// warps 2-9 = epilogue (tcgen05.ld -> bias / time-embedding / activation / residual -> global).  Two accumulator
+// Warp roles (320 threads): warps 0-7 = epilogue, warp 8 = TMA producer, warp 9 = TMEM allocator + single-thread
+// tcgen05.mma issuer (tcgen05.ld -> bias / time-embedding / activation / residual -> global).  Two accumulator
 // buffers in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // Reference call sites replaced: every nn.Conv2d on the UNet path (nn_modules/resnet.py:24,51,78-79,
@@ -125,6 +125,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
   uint8_t* smem_b = smem + Cfg::kAStages * kHaloStage;      // halo mode only
 
+  // warp roles: 0..7 epilogue, 8 TMA producer, 9 MMA issuer.  The issue arbiter favours the HIGHEST warp id on an SMSP, so
+  // the two latency-critical single-thread roles get the top ids and are never starved by the epilogue warps.
+  constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.g1 * p.g2 * p.g3 * p.nbatch * p.n_tiles;
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
   const int tile_begin = (int)((long long)blockIdx.x * total_tiles / gridDim.x);
   const int tile_end = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     for (int i = 0; i < kNumAMaps; ++i) prefetch_tmap(&p.amap[i]);
     for (int i = 0; i < kNumBMaps; ++i) prefetch_tmap(&p.bmap[i]);
     for (int s = 0; s < kRingA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
@@ -218,12 +221,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
           for (int kb = 0; kb < p.total_kb; ++kb) {
             mbar_wait(&full_a[sa], pa);
             tc_fence_after();
-            const uint32_t st = smem_u32(smem + sa * (kABytes + Cfg::kBBytes));
-            const uint64_t adesc = make_smem_desc(st);
-            const uint64_t bdesc = make_smem_desc(st + kABytes);
-#pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)   // +32 bytes along K inside the swizzle atom = +2 in the address field
-              if (!(p.dbg & 2)) umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), Cfg::kIdesc, (kb | k) != 0 ? 1u : 0u);
+            const uint32_t a_lo = desc_lo(smem_u32(smem + sa * (kABytes + Cfg::kBBytes)));
+            const uint32_t b_lo = a_lo + (uint32_t)(kABytes >> 4);
+            if (!(p.dbg & 2)) {
+              // +32 bytes along K inside the swizzle atom = +2 in the address field
+              umma_bf16_lo(d_tmem, a_lo, b_lo, Cfg::kIdesc, kb != 0 ? 1u : 0u);
+              umma_bf16_lo(d_tmem, a_lo + 2, b_lo + 2, Cfg::kIdesc, 1u);
+              umma_bf16_lo(d_tmem, a_lo + 4, b_lo + 4, Cfg::kIdesc, 1u);
+              umma_bf16_lo(d_tmem, a_lo + 6, b_lo + 6, Cfg::kIdesc, 1u);
+            }
             umma_commit(&empty_a[sa]);
             if (kb == p.total_kb - 1) umma_commit(&tfull_bar[acc]);
             if (++sa == kRingA) { sa = 0; pa ^= 1; }
@@ -234,7 +240,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
           const int pitch = p.t1 + 2;
           for (int c = 0; c < nch; ++c) {
             mbar_wait(&full_a[sa], pa);
-            const uint32_t a_base = smem_u32(smem + sa * kHaloStage);
+            const uint32_t a_lo0 = desc_lo(smem_u32(smem + sa * kHaloStage));
+            const uint32_t pitch8 = (uint32_t)pitch * 8u;
             for (int ei = 0; ei < p.n_taps; ++ei, ++kb) {
               const TcEntry e = p.e[ei];
               mbar_wait(&full_b[sb], pb);
@@ -242,15 +249,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
               // tap (dy, dx) = the 128 consecutive halo rows starting at row (dy+1)*pitch + (dx+1).  The 128B swizzle is a
               // function of the absolute shared-memory address bits (the halo buffer is 1024-byte aligned, so the
               // descriptor's base-offset field stays 0), exactly as for the +32-byte K advance below.
-              const int srow = (e.d2 + 1) * pitch + (e.d1 + 1);
-              const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + sb * Cfg::kBBytes));
+              const uint32_t t_lo = a_lo0 + (uint32_t)((e.d2 + 1) * pitch + (e.d1 + 1)) * 8u;    // 128-byte rows = 8 address units
+              const uint32_t b_lo = desc_lo(smem_u32(smem_b + sb * Cfg::kBBytes));
               if (!(p.dbg & 2)) {
+                // k outer, row inner: consecutive MMAs accumulate into different TMEM tiles
 #pragma unroll
-                for (int rr = 0; rr < ROWS; ++rr) {     // output row rr of the tile reads halo rows rr .. rr+2
-                  const uint64_t adesc = make_smem_desc(a_base + (uint32_t)(srow + rr * pitch) * 128u);
+                for (int k = 0; k < kBlockK / 16; ++k) {
 #pragma unroll
-                  for (int k = 0; k < kBlockK / 16; ++k)
-                    umma_bf16(d_tmem + (uint32_t)(rr * BLOCK_N), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), Cfg::kIdesc, (kb | k) != 0 ? 1u : 0u);
+                  for (int rr = 0; rr < ROWS; ++rr)       // output row rr of the tile reads halo rows rr .. rr+2
+                    umma_bf16_lo(d_tmem + (uint32_t)(rr * BLOCK_N), t_lo + (uint32_t)rr * pitch8 + (uint32_t)(2 * k), b_lo + (uint32_t)(2 * k),
+                                 Cfg::kIdesc, k != 0 ? 1u : (kb != 0 ? 1u : 0u));
                 }
               }
               umma_commit(&empty_b[sb]);
@@ -265,13 +273,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
               mbar_wait(&full_a[sa], pa);
               mbar_wait(&full_b[sb], pb);
               tc_fence_after();
-              const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + sb * Cfg::kBBytes));
+              const uint32_t a_lo = desc_lo(smem_u32(smem + sa * kHaloStage));
+              const uint32_t b_lo = desc_lo(smem_u32(smem_b + sb * Cfg::kBBytes));
+              const uint32_t slab8 = (uint32_t)p.t1 * 8u;      // plain tile: ROWS consecutive slabs of t1 pixel rows
 #pragma unroll
-              for (int rr = 0; rr < ROWS; ++rr) {       // plain tile: ROWS consecutive 128-row slabs of t1 pixels
-                const uint64_t adesc = make_smem_desc(smem_u32(smem + sa * kHaloStage) + (uint32_t)(rr * p.t1) * 128u);
+              for (int k = 0; k < kBlockK / 16; ++k) {
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k)
-                  umma_bf16(d_tmem + (uint32_t)(rr * BLOCK_N), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), Cfg::kIdesc, (kb | k) != 0 ? 1u : 0u);
+                for (int rr = 0; rr < ROWS; ++rr)
+                  umma_bf16_lo(d_tmem + (uint32_t)(rr * BLOCK_N), a_lo + (uint32_t)rr * slab8 + (uint32_t)(2 * k), b_lo + (uint32_t)(2 * k),
+                               Cfg::kIdesc, k != 0 ? 1u : (kb != 0 ? 1u : 0u));
               }
               umma_commit(&empty_b[sb]);
               umma_commit(&empty_a[sa]);
@@ -284,11 +294,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    // ===================== epilogue (warps 0..7) =====================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;          // row of the 128-row tile
     constexpr int kChunksPerWarp = BLOCK_N / 32 / (kEpiWarps / 4);
-    const int ch_begin = ((warp - 2) >> 2) * kChunksPerWarp;
+    const int ch_begin = (warp >> 2) * kChunksPerWarp;
     const int rows_box = HALO ? p.t1 : p.t1 * p.t2 * p.t3;
     // GroupNorm statistics accumulated in registers across consecutive tiles of the same (image, column tile):
     // lane j of this warp owns column n0 + j of every 32-column chunk
@@ -456,7 +466,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
   }
