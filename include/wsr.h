@@ -85,6 +85,44 @@ int wsr_conv_simt(const WsrConvDesc* d, void* stream);
 int wsr_conv_tc(const WsrConvDesc* d, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Tap-table convolution: the same kernels driven by an explicit list of taps instead of (ksize, stride, upsample).
+ * It expresses every DATA GRADIENT of the path as a forward convolution on flipped / transposed weights (the backward
+ * of nn.Conv2d in `l_pix.backward()`, models/diffusion_models/model.py:67): stride-2 Downsample -> four output-phase
+ * launches of a transposed convolution; "nearest x2 + conv3x3" Upsample -> one 4x4 stride-2 convolution.
+ *   for g in [0,GH) x [0,GW):   y[n, g*out_mul + out_p, co] = epilogue( sum_t sum_ci w[wtap_t][co][ci] * x[n, in_sub*(g + d_t) + p_t, ci] )
+ * x is (N, d->H, d->W, Cin), y is (N, OH, OW, Cout); out-of-range input pixels read as zero.  d->ksize / stride /
+ * upsample are ignored; the epilogue fields (bias, rowvec, act, res, res2, gn_stats) keep their meaning.
+ * ------------------------------------------------------------------------------------------------------------- */
+#define WSR_MAX_TAPS 16
+typedef struct {
+  int GH, GW;                 /* loop grid per image                                              */
+  int in_sub;                 /* 1 or 2: input subsampling factor                                 */
+  int out_mul, out_py, out_px;/* output pixel = g * out_mul + out_p                                */
+  int OH, OW;                 /* output tensor extent                                             */
+  int ntaps;
+  int py[WSR_MAX_TAPS], px[WSR_MAX_TAPS];   /* input phase of the tap (0 <= p < in_sub)             */
+  int dy[WSR_MAX_TAPS], dx[WSR_MAX_TAPS];   /* input offset of the tap on the subsampled grid        */
+  int wtap[WSR_MAX_TAPS];                   /* index of the tap's [w_rows][Cin] matrix inside d->w   */
+} WsrTapTable;
+int wsr_conv_taps_simt(const WsrConvDesc* d, const WsrTapTable* t, void* stream);
+/* tcgen05 version; same operand constraints as wsr_conv_tc; in_sub = 2 needs even H, W. */
+int wsr_conv_taps_tc(const WsrConvDesc* d, const WsrTapTable* t, void* stream);
+
+/* Weight (and bias) gradient of a tap-table convolution (backward of nn.Conv2d w.r.t. weight / bias):
+ *   dw[wtap_t * dw_stap + co * dw_sco + ci * dw_sci] += sum_{n, g} dy[n, g*out_mul + out_p, co] * X[n, in_sub*(g + d_t) + p_t, ci]
+ *   dbias[co] += sum_{n, g} dy[n, g*out_mul + out_p, co]
+ * X = x, or x read through a nearest x2 upsampling when up == 2 (pixel u reads x[u / 2]; t describes the taps on the
+ * upsampled grid).  The explicit dw strides let the result land directly in the reference's OIHW parameter layout. */
+typedef struct {
+  const void* x;  int x_dtype;  int N, H, W, Cin;  int x_ld;
+  const void* dy; int dy_dtype; int Cout; int dy_ld;           /* (N, t->OH, t->OW, Cout) */
+  float* dw; int64_t dw_stap, dw_sco, dw_sci;
+  float* dbias;                                                /* or NULL */
+  int up;                                                      /* 1 or 2 */
+} WsrWgradDesc;
+int wsr_conv_wgrad_simt(const WsrWgradDesc* d, const WsrTapTable* t, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Batched GEMM  D[b][m][n] = alpha * sum_k A[b][m][k] * B[b][n][k] (+ bias[n]) (+ res[b][m][n]),
  * used for the attention products (nn_modules/resnet.py:90-97, guided_cross_attention.py:34-41) and the linear
  * layers.  Element strides are explicit; the tcgen05 version requires unit k-stride for both operands.
@@ -127,10 +165,32 @@ int wsr_gn_apply(const void* x, int x_dtype, int N, int HW, int C, int x_ld, con
                  const float* gamma, const float* beta, int groups, float eps, int act, void* y, int y_dtype,
                  int y_ld, void* stream);
 int wsr_fill_zero(void* p, int64_t bytes, void* stream);
+/* Training-mode Block (nn_modules/resnet.py:21-24: GroupNorm -> Swish -> Dropout -> Conv): wsr_gn_apply followed by
+ * dropout, y *= keep / (1 - p); the keep mask is Philox4x32-10(seed, tag) indexed by the logical element (n*HW + pix)*C + c,
+ * so the backward pass regenerates it. */
+int wsr_gn_apply_dropout(const void* x, int x_dtype, int N, int HW, int C, int x_ld, const double* stats, int stats_ld,
+                         const float* gamma, const float* beta, int groups, float eps, int act, void* y, int y_dtype,
+                         int y_ld, float drop_p, uint64_t drop_seed, uint32_t drop_tag, void* stream);
+/* Backward of GroupNorm + activation (+ dropout).  da = gradient w.r.t. the block output, same dtype as x.
+ *   pass 1: red[n*red_ld + 2c + {0,1}] += (sum_p dz, sum_p dz*xhat), dz = da * drop * act'(z)   (doubles, zeroed by the caller)
+ *   pass 2: dx (=, or += when accumulate) rstd * (dz*gamma - A_g/m - xhat*B_g/m); dgamma += sum_n red1, dbeta += sum_n red0
+ *           (both or neither NULL); colsum[n*colsum_ld + c] = sum_p dx[n,p,c] of THIS contribution (closed form), or NULL. */
+int wsr_gn_bwd_reduce(const void* x, int x_dtype, int N, int HW, int C, int x_ld, const double* stats, int stats_ld,
+                      const float* gamma, const float* beta, int groups, float eps, int act, const void* da, int da_dtype,
+                      int da_ld, float drop_p, uint64_t drop_seed, uint32_t drop_tag, double* red, int red_ld, void* stream);
+int wsr_gn_bwd_apply(const void* x, int x_dtype, int N, int HW, int C, int x_ld, const double* stats, int stats_ld,
+                     const float* gamma, const float* beta, int groups, float eps, int act, const void* da, int da_dtype,
+                     int da_ld, float drop_p, uint64_t drop_seed, uint32_t drop_tag, const double* red, int red_ld, void* dx,
+                     int dx_dtype, int dx_ld, int accumulate, float* dgamma, float* dbeta, float* colsum, int colsum_ld,
+                     void* stream);
 
 /* Row softmax: p[r][:] = softmax(scale * s[r][:]) over `cols`, rows = batch*Nq (resnet.py:92-95). */
 int wsr_softmax_rows(const void* s, int s_dtype, int64_t rows, int cols, int64_t s_ld, float scale, void* p,
                      int p_dtype, int64_t p_ld, void* stream);
+
+/* Softmax backward: ds[r][c] = scale * p[r][c] * (dp[r][c] - sum_c' dp[r][c'] * p[r][c']) (backward of resnet.py:92-95). */
+int wsr_softmax_bwd_rows(const void* p, int p_dtype, const void* dp, int dp_dtype, int64_t rows, int cols, int64_t ld,
+                         float scale, void* ds, int ds_dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Layout / packing helpers.
@@ -166,6 +226,13 @@ int wsr_noise_embed(const float* level, int R, int inner, const float* w1, const
                     const float* b2, int act, float* temb, void* stream);
 int wsr_linear_rows(const float* x, int R, int K, const float* w, const float* bias, int P, float* y, void* stream);
 
+/* Backward of wsr_noise_embed (all four parameter gradients are ACCUMULATED) and of wsr_linear_rows
+ * (dx is written, dw / db are accumulated; any of dx, dw may be NULL). */
+int wsr_noise_embed_bwd(const float* level, int R, int inner, const float* w1, const float* b1, const float* w2, int act,
+                        const float* dtemb, float* dw1, float* db1, float* dw2, float* db2, void* stream);
+int wsr_linear_rows_bwd(const float* x, int R, int K, const float* w, const float* dy, int P, float* dx, float* dw,
+                        float* db, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * FD_Info_Spliter (resdiff/fd_info_spliter.py:37-117) and the Haar queries (resdiff/unet.py:124-132).
  * ------------------------------------------------------------------------------------------------------------- */
@@ -181,6 +248,21 @@ int wsr_fd_precompute(const float* cond, int B, int C, int H, int W, const float
  * row_index: device int* giving the row r of ne_rows to use for every b (sampling: the current step), or NULL for r=b. */
 int wsr_fd_gate(const float* ne_rows, int ne_ld, const int* row_index, int B, int C, int W, const float* fc0,
                 const float* fc2, int hidden, float* gate, void* stream);
+/* Backward of the gate (wsr_fd_gate + stem channel block 2, denoise_x = x * gate).  dxin: gradient of the stem input,
+ * NHWC pitch d_ld, channels [ch0, ch0+C) hold d denoise_x; x: fp32 NCHW x_t; ne_rows as in wsr_fd_gate with r = b.
+ * Writes dne[b*dne_ld + w] and accumulates dfc0 / dfc2 (noise_resSE.fc.{0,2}.weight). */
+int wsr_fd_gate_bwd(const void* dxin, int d_dtype, int d_ld, int ch0, const float* x, const float* ne_rows, int ne_ld, int B,
+                    int C, int H, int W, const float* fc0, const float* fc2, int hidden, float* dne, int dne_ld, float* dfc0,
+                    float* dfc2, void* stream);
+/* Backward of the condition-only branch (wsr_fd_precompute) w.r.t. its 3 parameter groups.  g_lf, g_hf: fp32 NCHW
+ * gradients of the lf / hf stem channels; `work` must be the workspace the forward call left behind (it keeps the
+ * unfiltered spectrum, sigma, the squeeze-excite vectors and the complex inverse transform); `bwork`: scratch of
+ * wsr_fd_backward_workspace_bytes().  All parameter gradients are ACCUMULATED. */
+int64_t wsr_fd_backward_workspace_bytes(int B, int C, int H, int W);
+int wsr_fd_backward(const float* cond, int B, int C, int H, int W, const float* sigma_fc0, const float* sigma_fc2,
+                    const float* hf_fc0, const float* hf_fc2, const float* ct_w, const float* g_lf, const float* g_hf,
+                    const void* work, void* bwork, float* d_sigma_fc0, float* d_sigma_fc2, float* d_hf_fc0, float* d_hf_fc2,
+                    float* d_ct_w, float* d_ct_b, void* stream);
 /* Stem input assembly: writes NHWC channels [x, cond, x*gate, lf, hf] (5*C, fd_info_spliter.py:117), zero-pads up
  * to Cpad channels.  x, cond, lf, hf: fp32 NCHW.  Only the first roundup(5*C, 8) (bf16) / 5*C (fp32) channels are
  * written: the caller zero-fills the pad channels of y once. */
@@ -218,6 +300,11 @@ int wsr_q_sample(const float* hr, const float* sr, const float* noise, const flo
  * Also writes dloss/deps * scale into grad (or NULL): -sign(noise-eps)*scale (L1), -2(noise-eps)*scale (L2). */
 int wsr_noise_loss(const float* noise, const float* eps, int64_t n, int l2, double* loss, float* grad, float scale,
                    void* stream);
+
+/* Adam update over a flat fp32 buffer (torch.optim.Adam semantics; model.py:43-44 uses lr, betas (0.9, 0.999), eps 1e-8,
+ * weight_decay 0); `step` is the 1-based step count used for the bias corrections. */
+int wsr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int step, void* stream);
 
 #ifdef __cplusplus
 }

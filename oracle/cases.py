@@ -43,9 +43,27 @@ CASES = {
     "resdiff_chain_full_b1": dict(kind="resdiff_chain", cfg=unet_cfg(128, 256), batch=1, seed=22, T=3),
     # training loss (dropout 0, injected t / level / noise)
     "resdiff_loss_small": dict(kind="resdiff_loss", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=31, t=400),
+    # one training step: loss / numel -> backward (model.py:61-69); fixture = per-parameter gradient summaries
+    "resdiff_grad_small": dict(kind="resdiff_grad", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=61, t=400),
     # priors and the RRDB-conditioned variant
     "simple_cnn": dict(kind="simple_cnn", batch=2, seed=41, lr_hw=(8, 16)),
     "rrdb_small": dict(kind="rrdb", batch=1, seed=42, lr_hw=(8, 16)),
     "srdiff_step_small": dict(kind="srdiff_step", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=1), batch=2, seed=43,
                               level=(0.7, 0.4)),
 }
+
+
+def grad_summary(named_grads, seed, full_below=4096):
+    """Compact, order-independent description of a set of gradients: per tensor its L2 norm, its dot product with a
+    seeded random probe and its first 8 elements; tensors with fewer than ``full_below`` elements are kept whole."""
+    import numpy as np
+    out = {}
+    for name, g in named_grads:
+        g = g.detach().to(torch.float64).cpu()
+        probe = seeded_randn(name + ".probe", g.shape, seed).to(torch.float64)
+        out["norm/" + name] = np.array(float(g.norm()))
+        out["dot/" + name] = np.array(float((g * probe).sum()))
+        out["head/" + name] = g.flatten()[:8].numpy().copy()
+        if g.numel() < full_below:
+            out["full/" + name] = g.to(torch.float32).numpy().copy()
+    return out

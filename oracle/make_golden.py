@@ -59,8 +59,40 @@ class _InjectedNoise:
         torch.randn, torch.randn_like = self._randn, self._randn_like
 
 
+def run_grad_case(ref, name, spec):
+    """The reference's training step up to the optimizer (model.py:61-68): p_losses -> sum / numel -> backward, with the
+    random draws (t, continuous level, noise) injected and dropout = 0."""
+    from .cases import grad_summary
+    seed, b, cfg, t = spec["seed"], spec["batch"], spec["cfg"], spec["t"]
+    net = fill_module(_unet(ref, cfg), seed).train()
+    diff = ref.ResDiffDiffusion(net, image_height=cfg["image_height"], image_width=cfg["image_width"],
+                                channels=cfg["image_channels"], conditional=True)
+    diff.set_new_noise_schedule(LINEAR_1000, "cpu")
+    diff.set_loss("cpu")
+    _, sr, hr = fields(name, b, cfg["image_channels"], cfg["image_height"], cfg["image_width"], seed)
+    noise = seeded_randn(name + ".noise", sr.shape, seed)
+    sap = diff.sqrt_alphas_cumprod_prev
+    u = np.random.RandomState(seed).uniform(sap[t - 1], sap[t], size=b)
+    _ri, _un = np.random.randint, np.random.uniform
+    np.random.randint = lambda *a, **k: t
+    np.random.uniform = lambda *a, **k: u
+    try:
+        loss = diff.p_losses({"HR": hr, "SR": sr}, noise=noise)
+    finally:
+        np.random.randint, np.random.uniform = _ri, _un
+    l_pix = loss.sum() / int(hr.numel())
+    l_pix.backward()
+    out = dict(hr=hr, sr=sr, noise=noise, level=torch.FloatTensor(u), loss=loss.detach().reshape(1), wsum=_checksum(net))
+    named = [(n, p.grad) for n, p in net.named_parameters() if p.grad is not None]
+    out["names"] = np.array([n for n, _ in named])
+    out.update(grad_summary(named, seed))
+    return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()}
+
+
 def run_case(ref, name, spec):
     kind, seed, b = spec["kind"], spec["seed"], spec["batch"]
+    if kind == "resdiff_grad":
+        return run_grad_case(ref, name, spec)
     out = {}
     with torch.no_grad():
         if kind == "resdiff_step":

@@ -89,3 +89,12 @@ def resdiff_p_losses(sd, cfg, hr, sr, level, noise, loss_type="l1"):
     else:
         loss = ((noise - eps) ** 2).sum()
     return loss, eps
+
+
+def resdiff_param_grads(sd, cfg, hr, sr, level, noise, loss_type="l1"):
+    """The reference's training step up to the optimizer (models/diffusion_models/model.py:61-68): sum-loss / numel ->
+    backward.  Returns (sum-reduced loss, {name: gradient}) for every entry of ``sd`` that received a gradient."""
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    loss, _ = resdiff_p_losses(leaf, cfg, hr, sr, level, noise, loss_type)
+    (loss / hr.numel()).backward()
+    return loss.detach(), {k: v.grad for k, v in leaf.items() if v.grad is not None}

@@ -49,6 +49,31 @@ class GemmDesc(C.Structure):
     ]
 
 
+MAX_TAPS = 16
+
+
+class TapTable(C.Structure):
+    """WsrTapTable (include/wsr.h): explicit tap list of a convolution."""
+    _fields_ = [
+        ("GH", C.c_int), ("GW", C.c_int), ("in_sub", C.c_int),
+        ("out_mul", C.c_int), ("out_py", C.c_int), ("out_px", C.c_int),
+        ("OH", C.c_int), ("OW", C.c_int), ("ntaps", C.c_int),
+        ("py", C.c_int * MAX_TAPS), ("px", C.c_int * MAX_TAPS),
+        ("dy", C.c_int * MAX_TAPS), ("dx", C.c_int * MAX_TAPS),
+        ("wtap", C.c_int * MAX_TAPS),
+    ]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("x_dtype", C.c_int), ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("x_ld", C.c_int),
+        ("dy", C.c_void_p), ("dy_dtype", C.c_int), ("Cout", C.c_int), ("dy_ld", C.c_int),
+        ("dw", C.c_void_p), ("dw_stap", C.c_int64), ("dw_sco", C.c_int64), ("dw_sci", C.c_int64),
+        ("dbias", C.c_void_p),
+        ("up", C.c_int),
+    ]
+
+
 _P, _I, _L, _F, _U64, _U32 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64, C.c_uint32
 
 # name -> argument ctypes (every one returns int unless listed in _RESTYPE)
@@ -86,10 +111,25 @@ SIGNATURES = {
     "wsr_randn": [_P, _L, _U64, _U32, _P],
     "wsr_q_sample": [_P, _P, _P, _P, _I, _L, _P, _P],
     "wsr_noise_loss": [_P, _P, _L, _I, _P, _P, _F, _P],
+    # training step (backward.cu, fd.cu)
+    "wsr_conv_taps_simt": [C.POINTER(ConvDesc), C.POINTER(TapTable), _P],
+    "wsr_conv_taps_tc": [C.POINTER(ConvDesc), C.POINTER(TapTable), _P],
+    "wsr_conv_wgrad_simt": [C.POINTER(WgradDesc), C.POINTER(TapTable), _P],
+    "wsr_gn_apply_dropout": [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _I, _F, _I, _P, _I, _I, _F, _U64, _U32, _P],
+    "wsr_gn_bwd_reduce": [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _I, _F, _I, _P, _I, _I, _F, _U64, _U32, _P, _I, _P],
+    "wsr_gn_bwd_apply": [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _I, _F, _I, _P, _I, _I, _F, _U64, _U32, _P, _I, _P, _I, _I,
+                         _I, _P, _P, _P, _I, _P],
+    "wsr_softmax_bwd_rows": [_P, _I, _P, _I, _L, _I, _L, _F, _P, _I, _P],
+    "wsr_noise_embed_bwd": [_P, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P],
+    "wsr_linear_rows_bwd": [_P, _I, _I, _P, _P, _I, _P, _P, _P, _P],
+    "wsr_fd_gate_bwd": [_P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _P],
+    "wsr_fd_backward_workspace_bytes": [_I, _I, _I, _I],
+    "wsr_fd_backward": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "wsr_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P],
 }
-_RESTYPE = {"wsr_fd_precompute_workspace_bytes": C.c_int64}
+_RESTYPE = {"wsr_fd_precompute_workspace_bytes": C.c_int64, "wsr_fd_backward_workspace_bytes": C.c_int64}
 # functions whose return value is data, not a status
-_NO_STATUS = {"wsr_version", "wsr_device_is_sm100", "wsr_fd_precompute_workspace_bytes"}
+_NO_STATUS = {"wsr_version", "wsr_device_is_sm100", "wsr_fd_precompute_workspace_bytes", "wsr_fd_backward_workspace_bytes"}
 
 _lib = None
 launches = 0          # number of status-returning calls made (bench.py's gpu_launches bookkeeping is done there)

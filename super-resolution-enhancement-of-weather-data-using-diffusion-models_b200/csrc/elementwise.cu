@@ -2,6 +2,7 @@
 // embedding, DDPM process updates.  All are coalesced over the NHWC channel axis and vectorised to 16 bytes where
 // the pitch allows it.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace wsr {
 
@@ -170,10 +171,13 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, int HW, int C, int ld, 
   }
 }
 
-template <typename TI, typename TO, int VEC>
+// DROP: training-mode dropout after the activation (nn_modules/resnet.py:23): y *= mask / (1 - p), mask from Philox
+// (seed, tag, logical element index (n*HW + p)*C + c) so that the backward pass can regenerate it.
+template <typename TI, typename TO, int VEC, bool DROP>
 __global__ void gn_apply_kernel(const TI* __restrict__ x, int HW, int C, int ld, int CV, int PL, int chunk,
                                 const double* __restrict__ stats, int stats_ld, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, int groups, float eps, int act, TO* __restrict__ y, int y_ld) {
+                                const float* __restrict__ beta, int groups, float eps, int act, TO* __restrict__ y, int y_ld,
+                                float drop_p, uint64_t drop_seed, uint32_t drop_tag) {
   extern __shared__ float sm[];   // scale[C], shift[C]
   const int n = blockIdx.y;
   const int cpg = C / groups;
@@ -211,6 +215,12 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x, int HW, int C, int ld,
         const float t = fmaf(v[u][i], sc[i], sh[i]);
         v[u][i] = (sizeof(TO) == 2 && act == WSR_ACT_SWISH) ? swish_fast(t) : apply_act(t, act);
       }
+      if constexpr (DROP) {
+        float m[VEC];
+        dropout_scale<VEC>(drop_seed, drop_tag, ((uint64_t)n * HW + (uint64_t)(p + u * PL)) * C + (uint64_t)cv * VEC, drop_p, m);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[u][i] *= m[i];
+      }
       VecLoad<TO, VEC>::st(yb + (int64_t)(p + u * PL) * y_ld, v[u]);
     }
   }
@@ -218,7 +228,16 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x, int HW, int C, int ld,
     float v[VEC];
     VecLoad<TI, VEC>::ld(xb + (int64_t)p * ld, v);
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) v[i] = apply_act(fmaf(v[i], sc[i], sh[i]), act);
+    for (int i = 0; i < VEC; ++i) {
+      const float t = fmaf(v[i], sc[i], sh[i]);
+      v[i] = (sizeof(TO) == 2 && act == WSR_ACT_SWISH) ? swish_fast(t) : apply_act(t, act);
+    }
+    if constexpr (DROP) {
+      float m[VEC];
+      dropout_scale<VEC>(drop_seed, drop_tag, ((uint64_t)n * HW + (uint64_t)p) * C + (uint64_t)cv * VEC, drop_p, m);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) v[i] *= m[i];
+    }
     VecLoad<TO, VEC>::st(yb + (int64_t)p * y_ld, v);
   }
 }
@@ -334,16 +353,6 @@ __global__ void linear_rows_kernel(const float* __restrict__ x, int K, const flo
 // ------------------------------------------------------------------------------------------------------------------
 // DDPM process
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-    uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-    uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-}
 // four standard normals for element group `grp` of stream (seed, tag)
 __device__ __forceinline__ void randn4(uint64_t seed, uint32_t tag, uint64_t grp, float (&z)[4]) {
   uint32_t c[4] = {(uint32_t)grp, (uint32_t)(grp >> 32), tag, 0x5752u};
@@ -527,24 +536,43 @@ extern "C" int wsr_gn_stats(const void* x, int x_dtype, int N, int HW, int C, in
   return WSR_OK;
 }
 
-extern "C" int wsr_gn_apply(const void* x, int x_dtype, int N, int HW, int C, int x_ld, const double* stats, int stats_ld,
-                            const float* gamma, const float* beta, int groups, float eps, int act, void* y,
-                            int y_dtype, int y_ld, void* stream) {
+static int gn_apply_impl(const void* x, int x_dtype, int N, int HW, int C, int x_ld, const double* stats, int stats_ld,
+                         const float* gamma, const float* beta, int groups, float eps, int act, void* y, int y_dtype,
+                         int y_ld, float drop_p, uint64_t drop_seed, uint32_t drop_tag, void* stream) {
   WSR_REQUIRE(x && y && stats && gamma && beta && valid_dtype(x_dtype) && N > 0 && HW > 0 && C > 0 && x_ld >= C && y_ld >= C && stats_ld >= 2 * C,
               WSR_E_INVALID, "gn_apply: bad argument");
   WSR_REQUIRE(groups > 0 && C % groups == 0, WSR_E_INVALID, "gn_apply: C=%d not divisible by groups=%d", C, groups);
   WSR_REQUIRE(y_dtype == x_dtype, WSR_E_UNSUPPORTED, "gn_apply: y_dtype must equal x_dtype");
+  WSR_REQUIRE(drop_p >= 0.f && drop_p < 1.f, WSR_E_INVALID, "gn_apply: dropout p=%f", (double)drop_p);
   GnGeom g = gn_geom(x_dtype, C, x_ld, y_ld, x, y);
   WSR_REQUIRE(g.vec != 0 && g.threads <= 1024, WSR_E_UNSUPPORTED, "gn_apply: C=%d too wide", C);
   dim3 grid((HW + g.chunk - 1) / g.chunk, N);
   size_t smem = (size_t)C * 2 * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-#define GN_APPLY(T, V) gn_apply_kernel<T, T, V><<<grid, g.threads, smem, st>>>((const T*)x, HW, C, x_ld, g.CV, g.PL, g.chunk, stats, stats_ld, gamma, beta, groups, eps, act, (T*)y, y_ld)
-  if (x_dtype == WSR_BF16) { if (g.vec == 8) GN_APPLY(__nv_bfloat16, 8); else GN_APPLY(__nv_bfloat16, 1); }
-  else { if (g.vec == 4) GN_APPLY(float, 4); else GN_APPLY(float, 1); }
+#define GN_APPLY(T, V, D) gn_apply_kernel<T, T, V, D><<<grid, g.threads, smem, st>>>((const T*)x, HW, C, x_ld, g.CV, g.PL, g.chunk, stats, stats_ld, gamma, beta, groups, eps, act, (T*)y, y_ld, drop_p, drop_seed, drop_tag)
+  if (drop_p > 0.f) {
+    if (x_dtype == WSR_BF16) { if (g.vec == 8) GN_APPLY(__nv_bfloat16, 8, true); else GN_APPLY(__nv_bfloat16, 1, true); }
+    else { if (g.vec == 4) GN_APPLY(float, 4, true); else GN_APPLY(float, 1, true); }
+  } else {
+    if (x_dtype == WSR_BF16) { if (g.vec == 8) GN_APPLY(__nv_bfloat16, 8, false); else GN_APPLY(__nv_bfloat16, 1, false); }
+    else { if (g.vec == 4) GN_APPLY(float, 4, false); else GN_APPLY(float, 1, false); }
+  }
 #undef GN_APPLY
   WSR_LAUNCH_OK();
   return WSR_OK;
+}
+
+extern "C" int wsr_gn_apply(const void* x, int x_dtype, int N, int HW, int C, int x_ld, const double* stats, int stats_ld,
+                            const float* gamma, const float* beta, int groups, float eps, int act, void* y,
+                            int y_dtype, int y_ld, void* stream) {
+  return gn_apply_impl(x, x_dtype, N, HW, C, x_ld, stats, stats_ld, gamma, beta, groups, eps, act, y, y_dtype, y_ld, 0.f, 0, 0, stream);
+}
+
+extern "C" int wsr_gn_apply_dropout(const void* x, int x_dtype, int N, int HW, int C, int x_ld, const double* stats,
+                                    int stats_ld, const float* gamma, const float* beta, int groups, float eps, int act,
+                                    void* y, int y_dtype, int y_ld, float drop_p, uint64_t drop_seed, uint32_t drop_tag,
+                                    void* stream) {
+  return gn_apply_impl(x, x_dtype, N, HW, C, x_ld, stats, stats_ld, gamma, beta, groups, eps, act, y, y_dtype, y_ld, drop_p, drop_seed, drop_tag, stream);
 }
 
 extern "C" int wsr_softmax_rows(const void* s, int s_dtype, int64_t rows, int cols, int64_t s_ld, float scale, void* p,

@@ -120,10 +120,10 @@ __global__ void fd_se2_kernel(const double* __restrict__ means, int B, int C, co
   for (int c = 0; c < C2; ++c) se2[(int64_t)b * C2 + c] = se[c];
 }
 
-// apply the high-pass in place and emit lf = cond * (ct_b + sum_ch ct_w[o][ch] * F_ch * (1 + se2[ch]))
-__global__ void fd_filter_lf_kernel(float2* __restrict__ spec, const float* __restrict__ cond, const float* __restrict__ sigma,
-                                    const float* __restrict__ se2, const float* __restrict__ ct_w, const float* __restrict__ ct_b,
-                                    int B, int C, int H, int W, float* __restrict__ lf) {
+// apply the high-pass (spec -> out) and emit lf = cond * (ct_b + sum_ch ct_w[o][ch] * F_ch * (1 + se2[ch]))
+__global__ void fd_filter_lf_kernel(const float2* __restrict__ spec, float2* __restrict__ out, const float* __restrict__ cond,
+                                    const float* __restrict__ sigma, const float* __restrict__ se2, const float* __restrict__ ct_w,
+                                    const float* __restrict__ ct_b, int B, int C, int H, int W, float* __restrict__ lf) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*H*W
   int64_t HW = (int64_t)H * W;
   if (i >= (int64_t)B * HW) return;
@@ -136,7 +136,7 @@ __global__ void fd_filter_lf_kernel(float2* __restrict__ spec, const float* __re
   for (int c = 0; c < C; ++c) {
     float2 q = spec[((int64_t)b * C + c) * HW + p];
     q.x *= hp; q.y *= hp;
-    spec[((int64_t)b * C + c) * HW + p] = q;
+    out[((int64_t)b * C + c) * HW + p] = q;
     fre[c] = q.x * (1.f + se2[(int64_t)b * 2 * C + c]);
     fim[c] = q.y * (1.f + se2[(int64_t)b * 2 * C + C + c]);
   }
@@ -151,6 +151,156 @@ __global__ void fd_filter_lf_kernel(float2* __restrict__ spec, const float* __re
 __global__ void complex_abs_kernel(const float2* __restrict__ in, float* __restrict__ out, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { float2 v = in[i]; out[i] = sqrtf(v.x * v.x + v.y * v.y); }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward of the condition-only branch w.r.t. sigma_resSE, HF_guided_resSE and channel_transform (the condition itself
+// is data: resdiff_diffusion.py:121, so the spectrum F0 is a constant and only H(sigma), the two squeeze-excite vectors
+// and the 1x1 channel transform carry gradient)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_atomic_add(float v, float* dst, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    atomicAdd(dst, s);
+  }
+}
+
+// ResSE fc backward for one sample: given d_se (gradient w.r.t. the sigmoid output), accumulates dfc0 / dfc2 and returns
+// the gradient w.r.t. the squeezed mean (or skips it when d_mean == nullptr)
+__device__ void res_se_bwd(const double* mean, int C2, const float* fc0, const float* fc2, int hidden, const float* d_se,
+                           float* dfc0, float* dfc2, float* d_mean) {
+  float a1[64], hid[64], da1[64];
+  for (int h = 0; h < hidden; ++h) {
+    float a = 0.f;
+    for (int c = 0; c < C2; ++c) a = fmaf(fc0[h * C2 + c], (float)mean[c], a);
+    a1[h] = a; hid[h] = a > 0.f ? a : 0.f; da1[h] = 0.f;
+  }
+  for (int c = 0; c < C2; ++c) {
+    float a = 0.f;
+    for (int h = 0; h < hidden; ++h) a = fmaf(fc2[c * hidden + h], hid[h], a);
+    const float se = 1.f / (1.f + expf(-a));
+    const float da2 = d_se[c] * se * (1.f - se);
+    for (int h = 0; h < hidden; ++h) { atomicAdd(dfc2 + c * hidden + h, da2 * hid[h]); da1[h] = fmaf(da2, fc2[c * hidden + h], da1[h]); }
+  }
+  for (int h = 0; h < hidden; ++h) if (!(a1[h] > 0.f)) da1[h] = 0.f;
+  for (int c = 0; c < C2; ++c) {
+    float dm = 0.f;
+    for (int h = 0; h < hidden; ++h) { atomicAdd(dfc0 + h * C2 + c, da1[h] * (float)mean[c]); dm = fmaf(da1[h], fc0[h * C2 + c], dm); }
+    if (d_mean) d_mean[c] = dm;
+  }
+}
+
+// grid (ceil(HW/128), B), 128 threads.  Direct part of dL/dF from the lf path, plus d ct_w, d ct_b and d se_h.
+__global__ void __launch_bounds__(128) fd_bwd_lf_kernel(const float2* __restrict__ F0, const float* __restrict__ cond,
+                                                        const float* __restrict__ sigma, const float* __restrict__ se2,
+                                                        const float* __restrict__ ct_w, const float* __restrict__ g_lf, int C, int H,
+                                                        int W, float2* __restrict__ dF, float* d_ctw, float* d_ctb, float* d_seh) {
+  __shared__ float red[4];
+  const int b = blockIdx.y;
+  const int64_t HW = (int64_t)H * W;
+  const int p = blockIdx.x * 128 + threadIdx.x;
+  const bool ok = p < HW;
+  float fre[32], fim[32], dct[32];
+  float hp = 0.f;
+  if (ok) {
+    const float s = sigma[b];
+    const float u = (float)(p / W) - 0.5f * H, v = (float)(p % W) - 0.5f * W;
+    hp = 1.f - expf(-(u * u + v * v) / (2.f * s * s));
+  }
+  for (int c = 0; c < C; ++c) {
+    float2 q = ok ? F0[((int64_t)b * C + c) * HW + p] : make_float2(0.f, 0.f);
+    fre[c] = q.x * hp; fim[c] = q.y * hp;
+    dct[c] = ok ? g_lf[((int64_t)b * C + c) * HW + p] * cond[((int64_t)b * C + c) * HW + p] : 0.f;
+  }
+  for (int o = 0; o < C; ++o) {
+    block_atomic_add(dct[o], d_ctb + o, red);
+    for (int c = 0; c < C; ++c) {
+      block_atomic_add(dct[o] * fre[c] * (1.f + se2[(int64_t)b * 2 * C + c]), d_ctw + o * 2 * C + c, red);
+      block_atomic_add(dct[o] * fim[c] * (1.f + se2[(int64_t)b * 2 * C + C + c]), d_ctw + o * 2 * C + C + c, red);
+    }
+  }
+  for (int c = 0; c < C; ++c) {
+    float dre = 0.f, dim = 0.f;
+    for (int o = 0; o < C; ++o) { dre = fmaf(ct_w[o * 2 * C + c], dct[o], dre); dim = fmaf(ct_w[o * 2 * C + C + c], dct[o], dim); }
+    block_atomic_add(dre * fre[c], d_seh + (int64_t)b * 2 * C + c, red);
+    block_atomic_add(dim * fim[c], d_seh + (int64_t)b * 2 * C + C + c, red);
+    if (ok) dF[((int64_t)b * C + c) * HW + p] = make_float2(dre * (1.f + se2[(int64_t)b * 2 * C + c]), dim * (1.f + se2[(int64_t)b * 2 * C + C + c]));
+  }
+}
+
+__global__ void fd_bwd_se_kernel(const double* __restrict__ meansF, int B, int C, const float* fc0, const float* fc2,
+                                 const float* __restrict__ d_seh, float* dfc0, float* dfc2, float* __restrict__ d_meanF) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int C2 = 2 * C;
+  res_se_bwd(meansF + (int64_t)b * C2, C2, fc0, fc2, C2 / 2, d_seh + (int64_t)b * C2, dfc0, dfc2, d_meanF + (int64_t)b * C2);
+}
+
+// gz = g_hf * z / |z|  (gradient of |z| in torch's complex convention)
+__global__ void fd_bwd_abs_kernel(const float2* __restrict__ z, const float* __restrict__ g_hf, float2* __restrict__ gz, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float2 v = z[i];
+  float a = sqrtf(v.x * v.x + v.y * v.y);
+  float g = a > 0.f ? g_hf[i] / a : 0.f;
+  gz[i] = make_float2(v.x * g, v.y * g);
+}
+
+// one block per sample: d sigma_b = sum_{c,p} (dReF * ReF0 + dImF * ImF0) * dH/dsigma, then the sigma ResSE backward
+__global__ void __launch_bounds__(256) fd_bwd_sigma_kernel(const float2* __restrict__ F0, const float2* __restrict__ dF,
+                                                          const float2* __restrict__ G, const float* __restrict__ d_meanF,
+                                                          const float* __restrict__ sigma, const double* __restrict__ means0, int C,
+                                                          int H, int W, const float* fc0, const float* fc2, float* dfc0, float* dfc2) {
+  __shared__ double red[256];
+  const int b = blockIdx.x;
+  const int64_t HW = (int64_t)H * W;
+  const float s = sigma[b];
+  const float inv2s2 = 1.f / (2.f * s * s), invs3 = 1.f / (s * s * s);
+  double acc = 0.0;
+  for (int64_t p = threadIdx.x; p < HW; p += 256) {
+    const float u = (float)(p / W) - 0.5f * H, v = (float)(p % W) - 0.5f * W;
+    const float D2 = u * u + v * v;
+    const float dHds = -expf(-D2 * inv2s2) * D2 * invs3;
+    float dH = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const int64_t i = ((int64_t)b * C + c) * HW + p;
+      const float2 f = F0[i], d = dF[i], g = G[i];
+      const float dre = d.x + g.x + d_meanF[(int64_t)b * 2 * C + c] / (float)HW;
+      const float dim = d.y + g.y + d_meanF[(int64_t)b * 2 * C + C + c] / (float)HW;
+      dH = fmaf(dre, f.x, dH);
+      dH = fmaf(dim, f.y, dH);
+    }
+    acc += (double)(dH * dHds);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float dsig = (float)red[0];
+    const int C2 = 2 * C;
+    const double* mean = means0 + (int64_t)b * C2;
+    float se[64];
+    res_se_vec(mean, C2, fc0, fc2, C2 / 2, se);
+    float a = 0.f;
+    for (int c = 0; c < C2; ++c) a += (float)mean[c] * (1.f + se[c]);
+    a /= (float)C2;
+    const float l = (float)min(H, W);
+    if (fabsf(a) + 0.5f * l < l - 10.f) {
+      const float dacc = dsig * (a > 0.f ? 1.f : (a < 0.f ? -1.f : 0.f));
+      float d_se[64];
+      for (int c = 0; c < C2; ++c) d_se[c] = dacc * (float)mean[c] / (float)C2;
+      res_se_bwd(mean, C2, fc0, fc2, C2 / 2, d_se, dfc0, dfc2, nullptr);
+    }
+  }
 }
 
 // per-step gate
@@ -250,11 +400,51 @@ using namespace wsr;
 static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 static inline int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
 
+namespace wsr {
+// workspace of wsr_fd_precompute; the first four complex buffers and the small vectors are read back by wsr_fd_backward
+struct FdWork {
+  float2 *buf0, *buf1, *F0, *Z;
+  double2* tw;
+  double *means0, *meansF;
+  float *sigma, *se2;
+};
+static int64_t fd_work_layout(void* work, int B, int C, int H, int W, FdWork* w) {
+  const int64_t n = (int64_t)B * C * H * W;
+  int64_t maxL = B > C ? B : C; if (H > maxL) maxL = H; if (W > maxL) maxL = W;
+  char* wp = (char*)work;
+  char* w0 = wp;
+  FdWork t;
+  t.buf0 = (float2*)wp; wp += align256(n * 8);
+  t.buf1 = (float2*)wp; wp += align256(n * 8);
+  t.F0 = (float2*)wp; wp += align256(n * 8);
+  t.Z = (float2*)wp; wp += align256(n * 8);
+  t.tw = (double2*)wp; wp += align256(maxL * 16);
+  t.means0 = (double*)wp; wp += align256((int64_t)B * 2 * C * 8);
+  t.meansF = (double*)wp; wp += align256((int64_t)B * 2 * C * 8);
+  t.sigma = (float*)wp; wp += align256((int64_t)B * 4);
+  t.se2 = (float*)wp; wp += align256((int64_t)B * 2 * C * 4);
+  if (w) *w = t;
+  return (int64_t)(wp - w0) + 1024;
+}
+
+// 4-D DFT over (B, C, H, W): `cur` holds the input, `nxt` is scratch; returns the buffer that holds the result
+static float2* dft4(float2* cur, float2* nxt, double2* tw, int B, int C, int H, int W, int inverse, bool scale, cudaStream_t st) {
+  const int64_t n = (int64_t)B * C * H * W;
+  const int L[4] = {W, H, C, B};
+  const int64_t S[4] = {1, W, (int64_t)H * W, (int64_t)C * H * W};
+  for (int ax = 0; ax < 4; ++ax) {
+    if (L[ax] == 1) continue;
+    twiddle_kernel<<<nblk(L[ax], 128), 128, 0, st>>>(tw, L[ax]);
+    dft_axis_kernel<<<nblk(n, 128), 128, 0, st>>>(cur, nxt, tw, L[ax], S[ax], n, inverse, scale ? 1.0 / (double)L[ax] : 1.0);
+    float2* t = cur; cur = nxt; nxt = t;
+  }
+  return cur;
+}
+}  // namespace wsr
+
 extern "C" int64_t wsr_fd_precompute_workspace_bytes(int B, int C, int H, int W) {
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return -1;
-  int64_t n = (int64_t)B * C * H * W;
-  int64_t maxL = B > C ? B : C; if (H > maxL) maxL = H; if (W > maxL) maxL = W;
-  return 2 * align256(n * 8) + align256(maxL * 16) + align256((int64_t)B * 2 * C * 8) + 2 * align256((int64_t)B * 2 * C * 4) + 1024;
+  return fd_work_layout(nullptr, B, C, H, W, nullptr);
 }
 
 extern "C" int wsr_fd_precompute(const float* cond, int B, int C, int H, int W, const float* sigma_fc0,
@@ -266,44 +456,68 @@ extern "C" int wsr_fd_precompute(const float* cond, int B, int C, int H, int W, 
   WSR_REQUIRE(C <= 32, WSR_E_UNSUPPORTED, "fd_precompute: C=%d > 32", C);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = (int64_t)B * C * H * W;
-  char* wp = (char*)work;
-  float2* buf0 = (float2*)wp; wp += align256(n * 8);
-  float2* buf1 = (float2*)wp; wp += align256(n * 8);
-  int64_t maxL = B > C ? B : C; if (H > maxL) maxL = H; if (W > maxL) maxL = W;
-  double2* tw = (double2*)wp; wp += align256(maxL * 16);
-  double* means = (double*)wp; wp += align256((int64_t)B * 2 * C * 8);
-  float* sigma = (float*)wp; wp += align256((int64_t)B * 2 * C * 4);
-  float* se2 = (float*)wp;
+  FdWork w;
+  fd_work_layout(work, B, C, H, W, &w);
 
-  real_to_complex_kernel<<<nblk(n, 256), 256, 0, st>>>(cond, buf0, n);
+  real_to_complex_kernel<<<nblk(n, 256), 256, 0, st>>>(cond, w.buf0, n);
   WSR_LAUNCH_OK();
-  float2* cur = buf0; float2* nxt = buf1;
-  const int L[4] = {W, H, C, B};
-  const int64_t S[4] = {1, W, (int64_t)H * W, (int64_t)C * H * W};
-  for (int ax = 0; ax < 4; ++ax) {
-    if (L[ax] == 1) continue;
-    twiddle_kernel<<<nblk(L[ax], 128), 128, 0, st>>>(tw, L[ax]);
-    dft_axis_kernel<<<nblk(n, 128), 128, 0, st>>>(cur, nxt, tw, L[ax], S[ax], n, 0, 1.0);
-    WSR_LAUNCH_OK();
-    float2* t = cur; cur = nxt; nxt = t;
-  }
+  float2* spec = dft4(w.buf0, w.buf1, w.tw, B, C, H, W, 0, false, st);
+  WSR_LAUNCH_OK();
+  WSR_CUDA_OK(cudaMemcpyAsync(w.F0, spec, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
   // sigma from the unfiltered spectrum
-  spec_mean_kernel<<<B * C, 256, 0, st>>>(cur, C, H, W, nullptr, means);
-  fd_sigma_kernel<<<nblk(B, 64), 64, 0, st>>>(means, B, C, sigma_fc0, sigma_fc2, H, W, sigma);
+  spec_mean_kernel<<<B * C, 256, 0, st>>>(w.F0, C, H, W, nullptr, w.means0);
+  fd_sigma_kernel<<<nblk(B, 64), 64, 0, st>>>(w.means0, B, C, sigma_fc0, sigma_fc2, H, W, w.sigma);
   // squeeze-excite of the FILTERED spectrum
-  spec_mean_kernel<<<B * C, 256, 0, st>>>(cur, C, H, W, sigma, means);
-  fd_se2_kernel<<<nblk(B, 64), 64, 0, st>>>(means, B, C, hf_fc0, hf_fc2, se2);
-  fd_filter_lf_kernel<<<nblk((int64_t)B * H * W, 128), 128, 0, st>>>(cur, cond, sigma, se2, ct_w, ct_b, B, C, H, W, lf);
+  spec_mean_kernel<<<B * C, 256, 0, st>>>(w.F0, C, H, W, w.sigma, w.meansF);
+  fd_se2_kernel<<<nblk(B, 64), 64, 0, st>>>(w.meansF, B, C, hf_fc0, hf_fc2, w.se2);
+  fd_filter_lf_kernel<<<nblk((int64_t)B * H * W, 128), 128, 0, st>>>(w.F0, w.buf0, cond, w.sigma, w.se2, ct_w, ct_b, B, C, H, W, lf);
   WSR_LAUNCH_OK();
   // inverse transform over all four axes
-  for (int ax = 0; ax < 4; ++ax) {
-    if (L[ax] == 1) continue;
-    twiddle_kernel<<<nblk(L[ax], 128), 128, 0, st>>>(tw, L[ax]);
-    dft_axis_kernel<<<nblk(n, 128), 128, 0, st>>>(cur, nxt, tw, L[ax], S[ax], n, 1, 1.0 / (double)L[ax]);
-    WSR_LAUNCH_OK();
-    float2* t = cur; cur = nxt; nxt = t;
-  }
-  complex_abs_kernel<<<nblk(n, 256), 256, 0, st>>>(cur, hf, n);
+  float2* z = dft4(w.buf0, w.buf1, w.tw, B, C, H, W, 1, true, st);
+  WSR_LAUNCH_OK();
+  WSR_CUDA_OK(cudaMemcpyAsync(w.Z, z, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+  complex_abs_kernel<<<nblk(n, 256), 256, 0, st>>>(w.Z, hf, n);
+  WSR_LAUNCH_OK();
+  return WSR_OK;
+}
+
+extern "C" int64_t wsr_fd_backward_workspace_bytes(int B, int C, int H, int W) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return -1;
+  const int64_t n = (int64_t)B * C * H * W;
+  int64_t maxL = B > C ? B : C; if (H > maxL) maxL = H; if (W > maxL) maxL = W;
+  return 3 * align256(n * 8) + align256(maxL * 16) + 2 * align256((int64_t)B * 2 * C * 4) + 1024;
+}
+
+extern "C" int wsr_fd_backward(const float* cond, int B, int C, int H, int W, const float* sigma_fc0, const float* sigma_fc2,
+                               const float* hf_fc0, const float* hf_fc2, const float* ct_w, const float* g_lf, const float* g_hf,
+                               const void* work, void* bwork, float* d_sigma_fc0, float* d_sigma_fc2, float* d_hf_fc0,
+                               float* d_hf_fc2, float* d_ct_w, float* d_ct_b, void* stream) {
+  WSR_REQUIRE(cond && sigma_fc0 && sigma_fc2 && hf_fc0 && hf_fc2 && ct_w && g_lf && g_hf && work && bwork && d_sigma_fc0 && d_sigma_fc2 &&
+                  d_hf_fc0 && d_hf_fc2 && d_ct_w && d_ct_b, WSR_E_INVALID, "fd_backward: null pointer");
+  WSR_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && C <= 32, WSR_E_INVALID, "fd_backward: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = (int64_t)B * C * H * W;
+  FdWork w;
+  fd_work_layout(const_cast<void*>(work), B, C, H, W, &w);
+  int64_t maxL = B > C ? B : C; if (H > maxL) maxL = H; if (W > maxL) maxL = W;
+  char* bp = (char*)bwork;
+  float2* dF = (float2*)bp; bp += align256(n * 8);
+  float2* g0 = (float2*)bp; bp += align256(n * 8);
+  float2* g1 = (float2*)bp; bp += align256(n * 8);
+  double2* tw = (double2*)bp; bp += align256(maxL * 16);
+  float* d_seh = (float*)bp; bp += align256((int64_t)B * 2 * C * 4);
+  float* d_meanF = (float*)bp;
+  WSR_CUDA_OK(cudaMemsetAsync(d_seh, 0, (size_t)B * 2 * C * 4, st));
+  dim3 grid((unsigned)(((int64_t)H * W + 127) / 128), B);
+  fd_bwd_lf_kernel<<<grid, 128, 0, st>>>(w.F0, cond, w.sigma, w.se2, ct_w, g_lf, C, H, W, dF, d_ct_w, d_ct_b, d_seh);
+  WSR_LAUNCH_OK();
+  fd_bwd_se_kernel<<<nblk(B, 64), 64, 0, st>>>(w.meansF, B, C, hf_fc0, hf_fc2, d_seh, d_hf_fc0, d_hf_fc2, d_meanF);
+  fd_bwd_abs_kernel<<<nblk(n, 256), 256, 0, st>>>(w.Z, g_hf, g0, n);
+  WSR_LAUNCH_OK();
+  // gradient of ifftn: (1/N) * fftn of the cotangent
+  float2* G = dft4(g0, g1, tw, B, C, H, W, 0, true, st);
+  WSR_LAUNCH_OK();
+  fd_bwd_sigma_kernel<<<B, 256, 0, st>>>(w.F0, dF, G, d_meanF, w.sigma, w.means0, C, H, W, sigma_fc0, sigma_fc2, d_sigma_fc0, d_sigma_fc2);
   WSR_LAUNCH_OK();
   return WSR_OK;
 }

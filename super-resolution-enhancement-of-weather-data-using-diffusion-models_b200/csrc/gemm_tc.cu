@@ -26,7 +26,7 @@ namespace wsr {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes = one swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
-constexpr int kMaxEntries = 12;
+constexpr int kMaxEntries = 18;              // 16 taps (WSR_MAX_TAPS) + fused 1x1 segment + spare
 constexpr int kNumAMaps = 5;
 constexpr int kNumBMaps = 2;
 
@@ -565,6 +565,7 @@ static int pick_block_n(int ncols, int m_tiles) {
 
 int validate_conv_desc(const WsrConvDesc* d);
 int validate_gemm_desc(const WsrGemmDesc* g);
+int validate_taps(const WsrTapTable* t);
 
 static void choose_tile(int W, int H, int N, int& t1, int& t2, int& t3) {
   t1 = W < 128 ? W : 128;
@@ -735,6 +736,102 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
     }
     if (rc) return rc;
   }
+  if (d->gn_stats && !fuse_stats)
+    return wsr_gn_stats(d->y, d->y_dtype, d->N, OH * OW, d->Cout, d->y_ld, d->gn_stats, d->gn_stats_ld, stream);
+  return WSR_OK;
+}
+
+// Tap-table variant (data gradients of the stride-2 / upsample convolutions; see wsr.h).  Classic (non-halo) tiles only.
+extern "C" int wsr_conv_taps_tc(const WsrConvDesc* d, const WsrTapTable* t, void* stream) {
+  int rc = validate_conv_desc(d);
+  if (rc) return rc;
+  rc = validate_taps(t);
+  if (rc) return rc;
+  WSR_REQUIRE(d->x_dtype == WSR_BF16, WSR_E_UNSUPPORTED, "conv_taps_tc: bf16 operands only");
+  WSR_REQUIRE(d->Cin % 64 == 0 && d->x_ld % 8 == 0 && (((uintptr_t)d->x) & 15) == 0 && (((uintptr_t)d->w) & 15) == 0,
+              WSR_E_UNSUPPORTED, "conv_taps_tc: Cin %% 64, pitch %% 8 and 16-byte alignment required (Cin=%d ld=%d)", d->Cin, d->x_ld);
+  WSR_REQUIRE(d->x2 == nullptr, WSR_E_UNSUPPORTED, "conv_taps_tc: no second segment");
+  WSR_REQUIRE((((uintptr_t)d->bias) & 15) == 0 && (((uintptr_t)d->rowvec) & 15) == 0 && (d->rowvec == nullptr || d->rowvec_ld % 4 == 0),
+              WSR_E_UNSUPPORTED, "conv_taps_tc: bias / rowvec must be 16-byte aligned, rowvec_ld %% 4 == 0");
+  WSR_REQUIRE(t->in_sub == 1 || (d->H % 2 == 0 && d->W % 2 == 0), WSR_E_UNSUPPORTED, "conv_taps_tc: in_sub 2 needs even H, W");
+  WSR_REQUIRE(d->gn_stats == nullptr || (t->out_mul == 1 && t->GH == t->OH && t->GW == t->OW), WSR_E_UNSUPPORTED,
+              "conv_taps_tc: fused statistics need a launch that covers the whole output");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int GH = t->GH, GW = t->GW, OH = t->OH, OW = t->OW;
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  choose_tile(GW, GH, d->N, p.t1, p.t2, p.t3);
+  WSR_REQUIRE(p.t1 <= 256 && p.t2 <= 256 && p.t3 <= 256, WSR_E_UNSUPPORTED, "conv_taps_tc: tile");
+  p.g1 = cdiv(GW, p.t1); p.g2 = cdiv(GH, p.t2); p.g3 = cdiv(d->N, p.t3);
+  p.nbatch = 1; p.a_zmul = 0; p.b_zmul = 0;
+  p.a_bytes = p.t1 * p.t2 * p.t3 * 128;
+  p.M1 = GW; p.M2 = GH; p.M3 = d->N;
+  p.Ncols = d->Cout;
+  p.out = d->y; p.out_dtype = d->y_dtype;
+  p.o_s1 = d->y_ld; p.o_s2 = (long long)OW * d->y_ld; p.o_s3 = (long long)OH * OW * d->y_ld; p.o_sb = 0; p.o_sc = 1;
+  p.bias = d->bias; p.rowvec = d->rowvec; p.rowvec_ld = d->rowvec_ld;
+  p.act = d->act; p.out_scale = d->out_scale;
+  p.res = d->res; p.res_dtype = d->res_dtype; p.res_scale = d->res_scale;
+  p.r_s1 = d->res_ld; p.r_s2 = (long long)OW * d->res_ld; p.r_s3 = (long long)OH * OW * d->res_ld; p.r_sc = 1;
+  p.res2 = d->res2; p.res2_dtype = d->res2_dtype; p.res2_scale = d->res2_scale;
+  p.q_s1 = d->res2_ld; p.q_s2 = (long long)OW * d->res2_ld; p.q_s3 = (long long)OH * OW * d->res2_ld; p.q_sc = 1;
+  const int m_tiles = p.g1 * p.g2 * p.g3;
+  const int bn = pick_block_n(d->Cout, m_tiles);
+  p.n_taps = 0; p.halo_rows = 1;
+  const bool fuse_stats = d->gn_stats != nullptr && (p.t1 * p.t2) % 32 == 0;
+  p.stats = fuse_stats ? d->gn_stats : nullptr;
+  p.stats_ld = d->gn_stats_ld;
+
+  int wt_count = 0;
+  for (int i = 0; i < t->ntaps; ++i) if (t->wtap[i] + 1 > wt_count) wt_count = t->wtap[i] + 1;
+  {
+    const int wrows = d->w_rows > 0 ? d->w_rows : d->Cout;
+    uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)wrows, (uint64_t)wt_count};
+    uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cin * wrows * 2};
+    uint32_t box[3] = {64, (uint32_t)bn, 1};
+    rc = encode_map(&p.bmap[0], d->w, 3, dims, str, box);
+    if (rc) return rc;
+    p.bmap[1] = p.bmap[0];
+  }
+  const uint32_t abox[4] = {64, (uint32_t)p.t1, (uint32_t)p.t2, (uint32_t)p.t3};
+  const long long ld = d->x_ld;
+  if (t->in_sub == 1) {
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)d->W * ld * 2, (uint64_t)d->H * d->W * ld * 2};
+    rc = encode_map(&p.amap[0], d->x, 4, dims, str, abox);
+    if (rc) return rc;
+    for (int i = 1; i < kNumAMaps; ++i) p.amap[i] = p.amap[0];
+  } else {
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W / 2, (uint64_t)d->H / 2, (uint64_t)d->N};
+        uint64_t str[3] = {(uint64_t)ld * 4, (uint64_t)d->W * ld * 4, (uint64_t)d->H * d->W * ld * 2};
+        const __nv_bfloat16* base = (const __nv_bfloat16*)d->x + ((long long)py * d->W + px) * ld;
+        rc = encode_map(&p.amap[py * 2 + px], base, 4, dims, str, abox);
+        if (rc) return rc;
+      }
+    p.amap[4] = p.amap[0];
+  }
+  int kb = 0;
+  for (int i = 0; i < t->ntaps; ++i) {
+    TcEntry& e = p.e[i];
+    e.amap = (int16_t)(t->in_sub == 2 ? t->py[i] * 2 + t->px[i] : 0);
+    e.bmap = 0; e.a_c0 = 0; e.b_k0 = 0;
+    e.b_z = (int16_t)t->wtap[i];
+    e.d1 = (int16_t)t->dx[i]; e.d2 = (int16_t)t->dy[i];
+    e.nchunks = (int16_t)(d->Cin / 64);
+    kb += e.nchunks;
+  }
+  p.n_entries = t->ntaps; p.total_kb = kb;
+  p.mul1 = t->out_mul; p.mul2 = t->out_mul; p.off1 = t->out_px; p.off2 = t->out_py;
+  p.n_tiles = cdiv(d->Cout, bn);
+  switch (bn) {
+    case 256: rc = launch_tc<256>(p, st); break;
+    case 128: rc = launch_tc<128>(p, st); break;
+    default: rc = launch_tc<64>(p, st); break;
+  }
+  if (rc) return rc;
   if (d->gn_stats && !fuse_stats)
     return wsr_gn_stats(d->y, d->y_dtype, d->N, OH * OW, d->Cout, d->y_ld, d->gn_stats, d->gn_stats_ld, stream);
   return WSR_OK;

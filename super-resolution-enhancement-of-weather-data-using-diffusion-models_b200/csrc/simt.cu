@@ -199,6 +199,43 @@ extern "C" int wsr_conv_simt(const WsrConvDesc* d, void* stream) {
   return WSR_OK;
 }
 
+namespace wsr {
+int validate_taps(const WsrTapTable* t) {
+  WSR_REQUIRE(t != nullptr, WSR_E_INVALID, "taps: null table");
+  WSR_REQUIRE(t->ntaps > 0 && t->ntaps <= WSR_MAX_TAPS, WSR_E_INVALID, "taps: ntaps=%d", t->ntaps);
+  WSR_REQUIRE(t->in_sub == 1 || t->in_sub == 2, WSR_E_UNSUPPORTED, "taps: in_sub=%d (1 or 2)", t->in_sub);
+  WSR_REQUIRE(t->GH > 0 && t->GW > 0 && t->OH > 0 && t->OW > 0 && t->out_mul >= 1, WSR_E_INVALID, "taps: bad grid");
+  WSR_REQUIRE(t->out_py >= 0 && t->out_px >= 0 && (t->GH - 1) * t->out_mul + t->out_py < t->OH && (t->GW - 1) * t->out_mul + t->out_px < t->OW,
+              WSR_E_INVALID, "taps: output grid exceeds the output tensor");
+  for (int i = 0; i < t->ntaps; ++i)
+    WSR_REQUIRE(t->py[i] >= 0 && t->py[i] < t->in_sub && t->px[i] >= 0 && t->px[i] < t->in_sub && t->wtap[i] >= 0, WSR_E_INVALID,
+                "taps: bad tap %d", i);
+  return WSR_OK;
+}
+}  // namespace wsr
+
+extern "C" int wsr_conv_taps_simt(const WsrConvDesc* d, const WsrTapTable* t, void* stream) {
+  int rc = validate_conv_desc(d);
+  if (rc) return rc;
+  rc = validate_taps(t);
+  if (rc) return rc;
+  ConvSimtParams p;
+  p.d = *d;
+  p.ntaps = t->ntaps;
+  for (int i = 0; i < t->ntaps; ++i) {
+    p.dy[i] = t->in_sub * t->dy[i] + t->py[i];
+    p.dx[i] = t->in_sub * t->dx[i] + t->px[i];
+    p.wtap[i] = t->wtap[i];
+  }
+  p.up = 1; p.UH = d->H; p.UW = d->W; p.in_stride = t->in_sub;
+  p.GH = t->GH; p.GW = t->GW; p.OH = t->OH; p.OW = t->OW;
+  p.out_mul = t->out_mul; p.out_py = t->out_py; p.out_px = t->out_px;
+  rc = launch_conv_simt(p, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (d->gn_stats) return wsr_gn_stats(d->y, d->y_dtype, d->N, t->OH * t->OW, d->Cout, d->y_ld, d->gn_stats, d->gn_stats_ld, stream);
+  return WSR_OK;
+}
+
 extern "C" int wsr_conv_transpose_k8s4(const void* x, int x_dtype, int N, int H, int W, int Cin, int x_ld,
                                        const void* w, const float* bias, int Cout, void* y, int y_dtype, int y_ld,
                                        void* stream) {

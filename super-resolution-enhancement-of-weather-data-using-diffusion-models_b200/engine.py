@@ -201,14 +201,17 @@ class Engine:
 
     def conv(self, x, pc, y, stride=1, upsample=False, bias=True, rowvec=None, rowvec_ld=0, act=nat.ACT_NONE,
              out_scale=1.0, res=None, res_scale=1.0, res2=None, res2_scale=1.0, x2=None, w2=None, extra_bias=None,
-             force_simt=False):
-        """y = act(conv(x) [+ conv1x1(x2, w2)] + bias + rowvec) * out_scale + res*res_scale + res2*res2_scale."""
+             force_simt=False, taps=None):
+        """y = act(conv(x) [+ conv1x1(x2, w2)] + bias + rowvec) * out_scale + res*res_scale + res2*res2_scale.
+        taps: a ``nat.TapTable`` -- run the tap-table variant (``pc.k`` / stride / upsample are then ignored)."""
+        if taps is not None:
+            assert stride == 1 and not upsample and x2 is None
         d = nat.ConvDesc()
         d.x, d.x_dtype, d.N, d.H, d.W, d.Cin, d.x_ld = x.ptr, x.dt, x.N, x.H, x.W, pc.Cin_pad, x.ld
         assert x.C == pc.Cin_pad, (x.C, pc.Cin_pad)
         d.w, d.w_rows = pc.w.data_ptr(), pc.rows
-        d.ksize, d.stride, d.upsample = pc.k, stride, (2 if pc.merged_up else 1) if upsample else 0
-        assert upsample or not pc.merged_up
+        d.ksize, d.stride, d.upsample = (1 if taps is not None else pc.k), stride, (2 if pc.merged_up else 1) if upsample else 0
+        assert upsample or not pc.merged_up or taps is not None
         d.Cout = pc.Cout
         assert y.C == pc.Cout, (y.C, pc.Cout)
         if x2 is not None:
@@ -228,8 +231,25 @@ class Engine:
         up = 2 if upsample else 1
         opix = x.N * (x.H * up // stride) * (x.W * up // stride)
         flops = 2 * opix * pc.Cout * (pc.k * pc.k * pc.Cin + (x2.C if x2 is not None else 0))
+        if taps is not None:
+            opix = x.N * taps.GH * taps.GW
+            flops = 2 * opix * pc.Cout * taps.ntaps * pc.Cin
         es = 2 if x.dt == nat.BF16 else 4
         nbytes = x.N * x.H * x.W * x.C * es + opix * pc.Cout * (2 if y.dt == nat.BF16 else 4) + pc.w.numel() * es
+        if taps is not None:
+            tc = (not force_simt and self._tc_conv_ok(x, pc, x2, y, b, rowvec or 0, rowvec_ld)
+                  and (taps.in_sub == 1 or (x.H % 2 == 0 and x.W % 2 == 0)) and not (y.st is not None and taps.out_mul != 1))
+            if y.st is not None and taps.out_mul != 1:
+                d.gn_stats = 0
+            if tc:
+                self.n_tc += 1
+                self.call("wsr_conv_taps_tc", C.byref(d), C.byref(taps), self.stream, flops=flops, nbytes=nbytes, tag="conv_taps_tc")
+            else:
+                if self.strict_tc and not force_simt:
+                    raise nat.WsrError("strict_tc: taps conv Cin=%d Cout=%d not eligible for the tcgen05 kernel" % (pc.Cin_pad, pc.Cout))
+                self.n_simt += 1
+                self.call("wsr_conv_taps_simt", C.byref(d), C.byref(taps), self.stream, flops=flops, nbytes=nbytes, tag="conv_taps_simt")
+            return y
         if not force_simt and self._tc_conv_ok(x, pc, x2, y, b, rowvec or 0, rowvec_ld):
             self.n_tc += 1
             self.call("wsr_conv_tc", C.byref(d), self.stream, flops=flops, nbytes=nbytes,
@@ -243,9 +263,12 @@ class Engine:
         return y
 
     def gemm(self, a_ptr, a_dt, a_s, b_ptr, b_dt, b_s, d_ptr, d_dt, d_s, batch, M, N, K, alpha=1.0, bias=None,
-             force_simt=False):
-        """D[b][m][n] = alpha * sum_k A[b][m][k] B[b][n][k] (+bias[n]).  *_s = (batch stride, row stride, k/col stride)."""
+             force_simt=False, res=None):
+        """D[b][m][n] = alpha * sum_k A[b][m][k] B[b][n][k] (+bias[n]) (+res[b][m][n]).  *_s = (batch stride, row stride,
+        k/col stride); res = (ptr, dtype, strides) or None."""
         g = nat.GemmDesc()
+        if res is not None:
+            g.res, g.res_dtype, (g.res_sb, g.res_sm, g.res_sn) = res
         g.a, g.a_dtype, (g.a_sb, g.a_sm, g.a_sk) = a_ptr, a_dt, a_s
         g.b, g.b_dtype, (g.b_sb, g.b_sn, g.b_sk) = b_ptr, b_dt, b_s
         g.d, g.d_dtype, (g.d_sb, g.d_sm, g.d_sn) = d_ptr, d_dt, d_s
@@ -281,6 +304,43 @@ class Engine:
                   groups, eps, act, y.ptr, y.dt, y.ld, self.stream,
                   nbytes=2 * x.N * x.H * x.W * x.C * (2 if x.dt == nat.BF16 else 4))
         return y
+
+    # ---- training step ------------------------------------------------------------------------------------------
+    def gn_apply_dropout(self, x, gamma, beta, groups, act, y, p, seed, tag, eps=1e-5):
+        assert x.stats_ptr
+        self.call("wsr_gn_apply_dropout", x.ptr, x.dt, x.N, x.H * x.W, x.C, x.ld, x.stats_ptr, x.st_ld, gamma.data_ptr(),
+                  beta.data_ptr(), groups, eps, act, y.ptr, y.dt, y.ld, float(p), int(seed), int(tag), self.stream,
+                  nbytes=2 * x.N * x.H * x.W * x.C * (2 if x.dt == nat.BF16 else 4))
+        return y
+
+    def gn_bwd(self, x, gamma, beta, groups, act, da, dx, red_ptr, dgamma, dbeta, accumulate=True, colsum=0, colsum_ld=0,
+               drop=(0.0, 0, 0), eps=1e-5):
+        """Backward of y = dropout(act(GroupNorm(x))): da -> dx (accumulated), dgamma / dbeta accumulated;
+        red_ptr: zeroed [N][2C] doubles scratch; colsum: optional [N][colsum_ld] fp32 = per-image column sums of dx."""
+        assert x.stats_ptr and da.dt == x.dt and dx.dt == x.dt
+        common = (x.ptr, x.dt, x.N, x.H * x.W, x.C, x.ld, x.stats_ptr, x.st_ld, gamma.data_ptr(), beta.data_ptr(), groups, eps,
+                  act, da.ptr, da.dt, da.ld, float(drop[0]), int(drop[1]), int(drop[2]), red_ptr, 2 * x.C)
+        nb = x.N * x.H * x.W * x.C * (2 if x.dt == nat.BF16 else 4)
+        self.call("wsr_gn_bwd_reduce", *common, self.stream, nbytes=2 * nb, tag="gn_bwd_reduce")
+        self.call("wsr_gn_bwd_apply", *common, dx.ptr, dx.dt, dx.ld, 1 if accumulate else 0, _ptr(dgamma), _ptr(dbeta),
+                  colsum, colsum_ld, self.stream, nbytes=(4 if accumulate else 3) * nb, tag="gn_bwd_apply")
+
+    def wgrad(self, x, dy, taps, dw, dw_strides, dbias=None, up=1):
+        """dw (fp32 tensor view, strides (tap, co, ci) in elements) += weight gradient; dbias += column sums of dy."""
+        d = nat.WgradDesc()
+        d.x, d.x_dtype, d.N, d.H, d.W, d.Cin, d.x_ld = x.ptr, x.dt, x.N, x.H, x.W, x.C, x.ld
+        d.dy, d.dy_dtype, d.Cout, d.dy_ld = dy.ptr, dy.dt, dy.C, dy.ld
+        d.dw = dw.data_ptr()
+        d.dw_stap, d.dw_sco, d.dw_sci = dw_strides
+        d.dbias = _ptr(dbias)
+        d.up = up
+        self.n_simt += 1
+        self.call("wsr_conv_wgrad_simt", C.byref(d), C.byref(taps), self.stream,
+                  flops=2 * x.N * taps.GH * taps.GW * dy.C * x.C * taps.ntaps, tag="wgrad_simt")
+
+    def softmax_bwd(self, p, p_dt, dp, dp_dt, rows, cols, scale, ds, ds_dt):
+        self.call("wsr_softmax_bwd_rows", p.data_ptr(), p_dt, dp.data_ptr(), dp_dt, rows, cols, cols, scale, ds.data_ptr(), ds_dt,
+                  self.stream)
 
     def softmax(self, s, s_dt, rows, cols, scale, p, p_dt):
         self.call("wsr_softmax_rows", s.data_ptr(), s_dt, rows, cols, cols, scale, p.data_ptr(), p_dt, cols, self.stream,

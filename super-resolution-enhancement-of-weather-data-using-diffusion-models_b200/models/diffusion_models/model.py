@@ -36,7 +36,9 @@ class DDPM(BaseModel):
                         optim_params.append(v)
             else:
                 optim_params = list(self.netG.parameters())
-            self.optG = torch.optim.Adam(optim_params, lr=opt['train']["optimizer"]["lr"])
+            # torch.optim.Adam semantics and state layout, update done by wsr_adam_step (reference model.py:43-44)
+            from ...autograd_glue import FusedAdam
+            self.optG = FusedAdam(optim_params, lr=opt['train']["optimizer"]["lr"])
             self.log_dict = OrderedDict()
         self.load_network()
         self.print_network()
@@ -53,9 +55,6 @@ class DDPM(BaseModel):
         l_pix = self.netG(self.data)
         b, c, h, w = self.data['HR'].shape
         l_pix = l_pix.sum() / int(b * c * h * w)
-        if not l_pix.requires_grad:
-            raise NotImplementedError("the backward pass of the CUDA denoiser is not implemented yet (forward loss = "
-                                      "%.6f); see DESIGN.md 'training scope'" % float(l_pix))
         l_pix.backward()
         self.optG.step()
         self.log_dict['l_pix'] = l_pix.item()

@@ -208,7 +208,9 @@ class UNetPlan:
     # weights
     # ------------------------------------------------------------------------------------------------------------------
     def _weights_version(self):
-        return tuple(p._version for p in self.net.parameters()) + tuple(p.data_ptr() for p in self.net.parameters())
+        from . import autograd_glue
+        return ((autograd_glue.weights_epoch,) + tuple(p._version for p in self.net.parameters())
+                + tuple(p.data_ptr() for p in self.net.parameters()))
 
     def refresh_weights(self):
         v = self._weights_version()
@@ -380,7 +382,7 @@ class UNetPlan:
         SW = nat.ACT_SWISH
         e.gn_apply(x, r.g1, r.b1, G, SW, r.a1)
         e.conv(r.a1, r.conv1, r.hbuf, rowvec=self._rowvec(r), rowvec_ld=self.P)
-        e.gn_apply(r.hbuf, r.g2, r.b2, G, SW, r.a2)
+        self._block2_norm(r)
         dst = r.rbuf if r.attn else r.y
         er = None if r.attn else extra_res
         if r.has_res_conv:
@@ -396,6 +398,10 @@ class UNetPlan:
                         self.scores[:B * n * n], self.probs[:B * n * n])
             e.conv(r.obuf, r.wout, r.y, res=r.rbuf, res2=extra_res)
         return r.y
+
+    def _block2_norm(self, r):
+        """GroupNorm + Swish of block2 (nn_modules/resnet.py:21-22); the training plan adds the dropout of :23 here."""
+        self.eng.gn_apply(r.hbuf, r.g2, r.b2, self.groups, nat.ACT_SWISH, r.a2)
 
     def _v_transposed(self, wv, nact, vT):
         """vT[b][c][pix] = sum_k Wv[c][k] * n[b][pix][k]  (V produced already transposed = K-major for P*V)."""

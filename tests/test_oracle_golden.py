@@ -101,3 +101,25 @@ def test_srdiff_step():
         _, feas = nets.rrdb_net(_sd("rrdb", spec["seed"] + 1), g["lr"])
         eps = nets.srdiff_unet(_sd("srdiff", spec["seed"], spec["cfg"]), feas, g["x_t"], g["level"], spec["cfg"])
     assert rel_l2(eps, g["eps"]) < TOL
+
+
+def test_resdiff_param_grads_match_reference():
+    """Oracle autograd vs the gradient summaries of the real reference's training step (model.py:61-68)."""
+    from oracle.cases import grad_summary
+    g, spec = load_golden("resdiff_grad_small"), CASES["resdiff_grad_small"]
+    sd = _sd("resdiff", spec["seed"], spec["cfg"])
+    np.testing.assert_allclose(_wsum(sd), g["wsum"].numpy(), rtol=1e-9)
+    loss, grads = process.resdiff_param_grads(sd, spec["cfg"], g["hr"], g["sr"], g["level"], g["noise"])
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 1e-5
+    names = [str(n) for n in g["names"]]
+    assert sorted(names) == sorted(grads.keys())
+    summ = grad_summary([(n, grads[n]) for n in names], spec["seed"])
+    # the FFT-branch parameters of FD_Info_Spliter must be live in this case (non-zero reference gradient)
+    for n in ("fd_spliter.sigma_resSE.fc.0.weight", "fd_spliter.HF_guided_resSE.fc.2.weight", "fd_spliter.channel_transform.weight"):
+        assert float(g["norm/" + n]) > 0
+    for n in names:
+        ref_norm = float(g["norm/" + n])
+        assert abs(float(summ["norm/" + n]) - ref_norm) <= 1e-4 * ref_norm + 1e-12, n
+        assert abs(float(summ["dot/" + n]) - float(g["dot/" + n])) <= 2e-4 * ref_norm * np.sqrt(grads[n].numel()) + 1e-12, n
+        if "full/" + n in g:
+            assert rel_l2(grads[n], g["full/" + n]) < 1e-4 or ref_norm < 1e-12, n

@@ -1,0 +1,339 @@
+"""GPU tests of the training step (p_losses -> loss / numel -> backward -> Adam).
+
+Kernel level: every backward kernel is called through the C ABI and compared with torch.autograd (fp32, no TF32) on
+the same inputs.  End to end: the reference-facing classes (ResDiffDiffusion.p_losses -> .backward()) against the
+gradients of the REAL reference (tests/golden/resdiff_grad_small.npz) and of the CPU oracle's autograd, per parameter.
+Tolerances: fp32 check mode rel-L2 <= 2e-4 per tensor (atomics / summation order); bf16 mode <= 6e-2 per tensor and
+<= 2.5e-2 over the whole gradient (bf16 activations and activation gradients, fp32 accumulation)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import wsr
+from conftest import load_golden, rel_l2
+from oracle import process
+from oracle.cases import CASES, LINEAR_1000
+from oracle.weights import fill_module
+
+pytestmark = pytest.mark.gpu
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+nat = wsr.pkg.native
+engine_mod = wsr.sub("engine")
+Engine, Act = engine_mod.Engine, engine_mod.Act
+T = wsr.sub("taps")
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _nhwc(x, eng, ld=None, coff=0, dt=None):
+    N, C, H, W = x.shape
+    full = eng.new_act(N, H, W, ld or C, dt=dt, zero=True)
+    a = full.slice(coff, C)
+    eng.nchw_to_act(x, a)
+    return a
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# convolution gradients
+# ----------------------------------------------------------------------------------------------------------------
+BWD_CASES = [
+    # N, Cin, Cout, H, W, k, stride, upsample
+    (2, 64, 64, 8, 16, 3, 1, False),
+    (2, 64, 128, 8, 16, 1, 1, False),
+    (2, 64, 64, 8, 16, 3, 2, False),
+    (1, 64, 64, 4, 8, 3, 1, True),
+    (2, 5, 64, 8, 16, 3, 1, False),
+    (2, 64, 1, 8, 16, 3, 1, False),
+    (1, 128, 64, 4, 128, 3, 1, False),
+]
+
+
+def _autograd_case(case, dev, seed=0):
+    N, Cin, Cout, H, W, k, stride, up = case
+    torch.manual_seed(seed)
+    x = torch.randn(N, Cin, H, W, device=dev, requires_grad=True)
+    w = (torch.randn(Cout, Cin, k, k, device=dev) / math.sqrt(Cin * k * k)).requires_grad_(True)
+    b = torch.randn(Cout, device=dev, requires_grad=True)
+    xin = F.interpolate(x, scale_factor=2, mode="nearest") if up else x
+    y = F.conv2d(xin, w, b, stride=stride, padding=(k - 1) // 2)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    return x.detach(), w.detach(), dy, x.grad, w.grad, b.grad
+
+
+def _dgrad(eng, case, w, dy_act, dx_act, force_simt=False):
+    N, Cin, Cout, H, W, k, stride, up = case
+    if up:
+        pc = eng.pack_conv(T.upsample_dgrad_weight(w), None)
+        eng.conv(dy_act, pc, dx_act, taps=T.dgrad_upsample_taps(H, W), bias=False, res=dx_act, force_simt=force_simt)
+    elif stride == 2:
+        pc = eng.pack_conv(T.dgrad_weight(w), None)
+        for tp in T.dgrad_down_taps(H, W):
+            eng.conv(dy_act, pc, dx_act, taps=tp, bias=False, res=dx_act, force_simt=force_simt)
+    else:
+        pc = eng.pack_conv(T.dgrad_weight(w), None)
+        eng.conv(dy_act, pc, dx_act, bias=False, res=dx_act, force_simt=force_simt)
+
+
+@pytest.mark.parametrize("case", BWD_CASES)
+def test_conv_backward_fp32_vs_autograd(case):
+    N, Cin, Cout, H, W, k, stride, up = case
+    dev = _dev()
+    eng = Engine(dev, "fp32")
+    x, w, dy, dx_ref, dw_ref, db_ref = _autograd_case(case, dev)
+    dy_act = _nhwc(dy, eng)
+    dx_act = eng.new_act(N, H, W, Cin, zero=True)
+    _dgrad(eng, case, w, dy_act, dx_act)
+    assert rel_l2(dx_act.to_nchw(eng), dx_ref) < 2e-5
+    dw = torch.zeros_like(w)
+    db = torch.zeros(Cout, device=dev)
+    taps = T.forward_upsample_taps(H, W) if up else T.forward_taps(k, stride, H, W)
+    eng.wgrad(_nhwc(x, eng), dy_act, taps, dw, (1, Cin * k * k, k * k), db, 2 if up else 1)
+    assert rel_l2(dw, dw_ref) < 2e-5
+    assert rel_l2(db, db_ref) < 2e-5
+
+
+@pytest.mark.parametrize("case", [c for c in BWD_CASES if c[2] % 64 == 0])
+def test_conv_dgrad_tc_vs_simt(case):
+    """bf16 mode: the data gradient runs on the tcgen05 kernel (tap-table variant for stride 2 / upsample)."""
+    N, Cin, Cout, H, W, k, stride, up = case
+    dev = _dev()
+    eng = Engine(dev, "bf16")
+    assert eng.use_tc
+    x, w, dy, dx_ref, _, _ = _autograd_case(case, dev, seed=1)
+    dy_act = _nhwc(dy, eng)
+    dx_tc = eng.new_act(N, H, W, Cin, zero=True)
+    dx_si = eng.new_act(N, H, W, Cin, dt=nat.F32, zero=True)
+    _dgrad(eng, case, w, dy_act, dx_tc)
+    n_tc = eng.n_tc
+    _dgrad(eng, case, w, dy_act, dx_si, force_simt=True)
+    assert n_tc >= 1 and eng.n_tc == n_tc
+    assert rel_l2(dx_tc.to_nchw(eng), dx_si.to_nchw(eng)) < 4e-3
+    assert rel_l2(dx_tc.to_nchw(eng), dx_ref) < 1.5e-2
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GroupNorm + Swish (+ dropout) backward
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,groups,act", [(64, 32, "swish"), (96, 32, "swish"), (64, 32, "none")])
+def test_gn_backward_vs_autograd(C, groups, act):
+    dev = _dev()
+    eng = Engine(dev, "fp32")
+    torch.manual_seed(3)
+    N, H, W = 2, 8, 16
+    x = (torch.randn(N, C, H, W, device=dev) * 1.5 + 0.3).requires_grad_(True)
+    gamma = (1 + 0.1 * torch.randn(C, device=dev)).requires_grad_(True)
+    beta = (0.1 * torch.randn(C, device=dev)).requires_grad_(True)
+    z = F.group_norm(x, groups, gamma, beta, eps=1e-5)
+    y = z * torch.sigmoid(z) if act == "swish" else z
+    da = torch.randn_like(y)
+    y.backward(da)
+    arena = engine_mod.StatsArena()
+    xa = eng.new_act(N, H, W, C, stats=arena)
+    arena.finalize(dev)
+    eng.nchw_to_act(x.detach(), xa)
+    eng.gn_stats(xa)
+    dx = eng.new_act(N, H, W, C, zero=True)
+    red = torch.zeros(N * 2 * C, device=dev, dtype=torch.float64)
+    dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    colsum = torch.zeros(N, C, device=dev)
+    eng.gn_bwd(xa, gamma.detach(), beta.detach(), groups, nat.ACT_SWISH if act == "swish" else nat.ACT_NONE, _nhwc(da, eng), dx,
+               red.data_ptr(), dg, db, True, colsum.data_ptr(), C)
+    dxn = dx.to_nchw(eng)
+    assert rel_l2(dxn, x.grad) < 2e-5
+    assert rel_l2(dg, gamma.grad) < 2e-5 and rel_l2(db, beta.grad) < 2e-5
+    assert rel_l2(colsum, x.grad.sum(dim=(2, 3))) < 1e-4
+
+
+def test_gn_dropout_forward_backward_consistent():
+    """The backward regenerates the forward's Philox mask: d/dx of sum(y * g) must match a finite-difference-free check --
+    y_drop = y_nodrop * m with m in {0, 1/(1-p)}, and the dx of the dropout path equals the no-dropout dx fed with da * m."""
+    dev = _dev()
+    eng = Engine(dev, "fp32")
+    torch.manual_seed(4)
+    N, C, H, W, p = 2, 64, 8, 16, 0.2
+    x = torch.randn(N, C, H, W, device=dev)
+    gamma, beta = 1 + 0.1 * torch.randn(C, device=dev), 0.1 * torch.randn(C, device=dev)
+    arena = engine_mod.StatsArena()
+    xa = eng.new_act(N, H, W, C, stats=arena)
+    arena.finalize(dev)
+    eng.nchw_to_act(x, xa)
+    eng.gn_stats(xa)
+    y0, y1 = eng.new_act(N, H, W, C), eng.new_act(N, H, W, C)
+    eng.gn_apply(xa, gamma, beta, 32, nat.ACT_SWISH, y0)
+    eng.gn_apply_dropout(xa, gamma, beta, 32, nat.ACT_SWISH, y1, p, 1234, 7)
+    a0, a1 = y0.to_nchw(eng), y1.to_nchw(eng)
+    m = torch.where(a0.abs() > 1e-6, a1 / a0, torch.full_like(a0, float("nan")))
+    valid = ~torch.isnan(m)
+    keep = (m[valid] - 1 / (1 - p)).abs() < 1e-4
+    drop = m[valid].abs() < 1e-6
+    assert bool((keep | drop).all())
+    frac = float(drop.float().mean())
+    assert abs(frac - p) < 0.02, frac
+    mask = torch.where(a1 != 0, torch.full_like(a0, 1 / (1 - p)), torch.zeros_like(a0))
+    da = torch.randn_like(x)
+    outs = []
+    for da_in, drop_arg in ((da, (p, 1234, 7)), (da * mask, (0.0, 0, 0))):
+        dx = eng.new_act(N, H, W, C, zero=True)
+        red = torch.zeros(N * 2 * C, device=dev, dtype=torch.float64)
+        dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+        eng.gn_bwd(xa, gamma, beta, 32, nat.ACT_SWISH, _nhwc(da_in, eng), dx, red.data_ptr(), dg, db, True, 0, 0, drop_arg)
+        outs.append((dx.to_nchw(eng), dg.clone()))
+    assert rel_l2(outs[0][0], outs[1][0]) < 1e-5 and rel_l2(outs[0][1], outs[1][1]) < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# softmax backward, Adam
+# ----------------------------------------------------------------------------------------------------------------
+def test_softmax_backward_vs_autograd():
+    dev = _dev()
+    eng = Engine(dev, "fp32")
+    torch.manual_seed(5)
+    rows, cols, scale = 96, 200, 0.125
+    s = torch.randn(rows, cols, device=dev, requires_grad=True)
+    p = torch.softmax(s * scale, dim=-1)
+    dp = torch.randn_like(p)
+    p.backward(dp)
+    ds = torch.empty_like(s)
+    eng.softmax_bwd(p.detach().contiguous(), nat.F32, dp, nat.F32, rows, cols, scale, ds, nat.F32)
+    assert rel_l2(ds, s.grad) < 1e-5
+
+
+def test_fused_adam_matches_torch_adam():
+    dev = _dev()
+    FusedAdam = wsr.sub("autograd_glue").FusedAdam
+    torch.manual_seed(6)
+    p0 = [torch.randn(257, 33, device=dev), torch.randn(64, device=dev)]
+    a = [torch.nn.Parameter(t.clone()) for t in p0]
+    b = [torch.nn.Parameter(t.clone()) for t in p0]
+    oa, ob = FusedAdam(a, lr=1e-3), torch.optim.Adam(b, lr=1e-3)
+    for step in range(5):
+        gs = [torch.randn_like(t) for t in p0]
+        for pa, pb, g in zip(a, b, gs):
+            pa.grad, pb.grad = g.clone(), g.clone()
+        oa.step(); ob.step()
+    for pa, pb in zip(a, b):
+        assert rel_l2(pa.data, pb.data) < 1e-6
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert sa["state"].keys() == sb["state"].keys()
+    assert rel_l2(sa["state"][0]["exp_avg_sq"], sb["state"][0]["exp_avg_sq"]) < 1e-6
+    assert float(sa["state"][0]["step"]) == float(sb["state"][0]["step"]) == 5.0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the whole training step against the reference
+# ----------------------------------------------------------------------------------------------------------------
+def _build(cfg, seed, precision):
+    U = wsr.sub("models.diffusion_models.resdiff.unet").UNet
+    D = wsr.sub("models.diffusion_models.resdiff.resdiff_diffusion").ResDiffDiffusion
+    net = U(in_channel=cfg["in_channel"], out_channel=cfg["out_channel"], norm_groups=cfg["norm_groups"],
+            inner_channel=cfg["inner_channel"], channel_mults=cfg["channel_mults"], attn_res=cfg["attn_res"],
+            res_blocks=cfg["res_blocks"], dropout=cfg["dropout"], image_height=cfg["image_height"],
+            image_width=cfg["image_width"], image_channels=cfg["image_channels"], precision=precision)
+    net = fill_module(net, seed).to("cuda:0").train()
+    diff = D(net, image_height=cfg["image_height"], image_width=cfg["image_width"], channels=1, conditional=True).cuda()
+    diff.set_new_noise_schedule(LINEAR_1000, "cuda:0")
+    diff.set_loss("cuda:0")
+    return net, diff
+
+
+def _train_backward(diff, g, spec):
+    u = g["level"].numpy().astype(np.float64)
+    ri, un = np.random.randint, np.random.uniform
+    np.random.randint = lambda *a, **k: spec["t"]
+    np.random.uniform = lambda *a, **k: u
+    try:
+        loss = diff.p_losses({"HR": g["hr"].cuda(), "SR": g["sr"].cuda()}, noise=g["noise"].cuda())
+    finally:
+        np.random.randint, np.random.uniform = ri, un
+    l_pix = loss.sum() / int(g["hr"].numel())
+    l_pix.backward()
+    return float(loss)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_training_step_gradients_vs_reference(precision):
+    from oracle.cases import grad_summary
+    from conftest import manifest
+    from oracle.weights import seeded_state_dict
+    g, spec = load_golden("resdiff_grad_small"), CASES["resdiff_grad_small"]
+    cfg = spec["cfg"]
+    net, diff = _build(cfg, spec["seed"], precision)
+    loss = _train_backward(diff, g, spec)
+    rel_loss = abs(loss - float(g["loss"])) / float(g["loss"])
+    sd = seeded_state_dict(manifest("resdiff", cfg), spec["seed"])
+    _, oracle_grads = process.resdiff_param_grads(sd, cfg, g["hr"], g["sr"], g["level"], g["noise"])
+    tol_t, tol_all = (2e-4, 1e-4) if precision == "fp32" else (6e-2, 2.5e-2)
+    named = dict(net.named_parameters())
+    assert sorted(named) == sorted(str(n) for n in g["names"])
+    plan = net.train_plan(g["hr"].shape[0], torch.device("cuda:0"))
+    name_of = {id(p): n for n, p in named.items()}
+    bad, num, den = [], 0.0, 0.0
+    lines = []
+    for p in plan.param_order:                      # completion order of the backward pass: first failure localises a bug
+        n = name_of[id(p)]
+        assert p.grad is not None, n
+        got, ref = p.grad.detach().cpu().double(), oracle_grads[n].double()
+        err = float((got - ref).norm())
+        rn = float(ref.norm())
+        num += err ** 2
+        den += rn ** 2
+        ref_norm = float(g["norm/" + n])
+        assert abs(rn - ref_norm) <= 1e-3 * ref_norm + 1e-12, n          # oracle == reference (pinned on CPU as well)
+        rel = err / max(rn, 1e-30)
+        lines.append("%-60s |g| %.3e  rel %.3e" % (n, rn, rel))
+        # tiny tensors (e.g. squeeze-excite scalars) are judged against the global gradient scale
+        if rel > tol_t and err > tol_t * 1e-3 * math.sqrt(den):
+            bad.append(lines[-1])
+    total = math.sqrt(num / den)
+    print("\n[parity] training step %s: loss rel err %.3e, whole-gradient rel-L2 %.3e, %d / %d tensors above %.0e"
+          % (precision, rel_loss, total, len(bad), len(lines), tol_t))
+    if bad:
+        print("\n".join(bad[:40]))
+    assert rel_loss < (1e-4 if precision == "fp32" else 2e-2)
+    assert not bad, "%d parameter gradients out of tolerance; first (backward order): %s" % (len(bad), bad[0])
+    assert total < tol_all
+    # summaries of the REAL reference's gradients
+    summ = grad_summary([(n, named[n].grad) for n in named], spec["seed"])
+    for n in named:
+        ref_norm = float(g["norm/" + n])
+        tol = 1e-3 if precision == "fp32" else 8e-2
+        if ref_norm > 1e-6 * math.sqrt(den):
+            assert abs(float(summ["norm/" + n]) - ref_norm) <= tol * ref_norm, n
+
+
+def test_optimize_parameters_decreases_loss_and_flat_adam():
+    """Three optimizer steps on a fixed batch through the flat-buffer path: the loss goes down, the parameters move, and
+    the one-launch flat Adam equals per-parameter torch.optim.Adam driven by the same gradients."""
+    g, spec = load_golden("resdiff_grad_small"), CASES["resdiff_grad_small"]
+    cfg = spec["cfg"]
+    FusedAdam = wsr.sub("autograd_glue").FusedAdam
+    net, diff = _build(cfg, spec["seed"], "fp32")
+    plan = net.train_plan(g["hr"].shape[0], torch.device("cuda:0"))
+    opt = FusedAdam(list(diff.parameters()), lr=1e-4)
+    opt.attach_flat(plan)
+    assert plan.parameters_are_flat()
+    shadow = [torch.nn.Parameter(p.detach().clone()) for p in diff.parameters()]
+    ref_opt = torch.optim.Adam(shadow, lr=1e-4)
+    losses = []
+    for it in range(3):
+        opt.zero_grad()
+        losses.append(_train_backward(diff, g, spec))
+        for s, p in zip(shadow, diff.parameters()):
+            s.grad = None if p.grad is None else p.grad.detach().clone()
+        opt.step()
+        ref_opt.step()
+    assert losses[2] < losses[0], losses
+    worst = max(rel_l2(p.detach(), s.detach()) for s, p in zip(shadow, diff.parameters()))
+    print("\n[train] losses %s, flat Adam vs torch Adam worst rel-L2 %.2e" % (losses, worst))
+    assert worst < 1e-5
+    sd = opt.state_dict()
+    assert len(sd["state"]) == len(list(diff.parameters()))
