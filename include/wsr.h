@@ -302,9 +302,10 @@ int wsr_noise_loss(const float* noise, const float* eps, int64_t n, int l2, doub
                    void* stream);
 
 /* Adam update over a flat fp32 buffer (torch.optim.Adam semantics; model.py:43-44 uses lr, betas (0.9, 0.999), eps 1e-8,
- * weight_decay 0); `step` is the 1-based step count used for the bias corrections. */
-int wsr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                  float weight_decay, int step, void* stream);
+ * weight_decay 0); `step` is the 1-based step count used for the bias corrections.  The hyper-parameters are doubles so that
+ * 1 - beta is rounded to fp32 exactly as torch does. */
+int wsr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
+                  double weight_decay, int step, void* stream);
 
 #ifdef __cplusplus
 }

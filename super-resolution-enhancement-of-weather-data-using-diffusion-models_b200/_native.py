@@ -125,7 +125,7 @@ SIGNATURES = {
     "wsr_fd_gate_bwd": [_P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _P],
     "wsr_fd_backward_workspace_bytes": [_I, _I, _I, _I],
     "wsr_fd_backward": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
-    "wsr_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P],
+    "wsr_adam_step": [_P, _P, _P, _P, _L, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _I, _P],
 }
 _RESTYPE = {"wsr_fd_precompute_workspace_bytes": C.c_int64, "wsr_fd_backward_workspace_bytes": C.c_int64}
 # functions whose return value is data, not a status

@@ -429,13 +429,14 @@ __global__ void __launch_bounds__(256) fd_gate_bwd_kernel(const void* dxin, int 
 // Adam (torch.optim.Adam semantics, models/diffusion_models/model.py:43-44: lr, betas (0.9, 0.999), eps 1e-8, wd 0)
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                                 int64_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+                                 int64_t n, float lr, float b1, float b2, float omb1, float omb2, float eps, float wd, float bc1,
+                                 float bc2_sqrt) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gi = g[i];
     const float pi = p[i];
     if (wd != 0.f) gi = fmaf(wd, pi, gi);
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    const float mi = b1 * m[i] + omb1 * gi;          // 1 - beta rounded from double, as torch does
+    const float vi = b2 * v[i] + omb2 * gi * gi;
     m[i] = mi; v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     p[i] = pi - (lr / bc1) * (mi / denom);
@@ -596,14 +597,16 @@ extern "C" int wsr_fd_gate_bwd(const void* dxin, int d_dtype, int d_ld, int ch0,
   return WSR_OK;
 }
 
-extern "C" int wsr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                             float weight_decay, int step, void* stream) {
+extern "C" int wsr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
+                             double weight_decay, int step, void* stream) {
   WSR_REQUIRE(p && g && m && v && n > 0 && step > 0, WSR_E_INVALID, "adam_step: bad argument");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
   unsigned blocks = (unsigned)((n + 255) / 256);
   if (blocks > 2368) blocks = 2368;
-  adam_step_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2));
+  adam_step_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)lr, (float)beta1, (float)beta2, (float)(1.0 - beta1),
+                                                             (float)(1.0 - beta2), (float)eps, (float)weight_decay, (float)bc1,
+                                                             (float)sqrt(bc2));
   WSR_LAUNCH_OK();
   return WSR_OK;
 }

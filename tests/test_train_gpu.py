@@ -3,8 +3,10 @@
 Kernel level: every backward kernel is called through the C ABI and compared with torch.autograd (fp32, no TF32) on
 the same inputs.  End to end: the reference-facing classes (ResDiffDiffusion.p_losses -> .backward()) against the
 gradients of the REAL reference (tests/golden/resdiff_grad_small.npz) and of the CPU oracle's autograd, per parameter.
-Tolerances: fp32 check mode rel-L2 <= 2e-4 per tensor (atomics / summation order); bf16 mode <= 6e-2 per tensor and
-<= 2.5e-2 over the whole gradient (bf16 activations and activation gradients, fp32 accumulation)."""
+Tolerances: fp32 check mode rel-L2 <= 2e-4 per tensor (atomics / summation order; measured 1.2e-6 over the whole
+gradient).  bf16 mode: 2x the REAL reference's own bf16-autocast drift on this case (oracle/bf16_drift.py: whole gradient
+7.6e-2, median tensor 3.2e-2, worst 0.53 on a 2-element tensor) -> whole gradient <= 1.5e-1, per tensor <= 1.6e-1
+(tensors with fewer than 16 elements: <= 1.0); measured on B200: 6.8e-2 whole gradient."""
 import math
 
 import numpy as np
@@ -271,7 +273,7 @@ def test_training_step_gradients_vs_reference(precision):
     rel_loss = abs(loss - float(g["loss"])) / float(g["loss"])
     sd = seeded_state_dict(manifest("resdiff", cfg), spec["seed"])
     _, oracle_grads = process.resdiff_param_grads(sd, cfg, g["hr"], g["sr"], g["level"], g["noise"])
-    tol_t, tol_all = (2e-4, 1e-4) if precision == "fp32" else (6e-2, 2.5e-2)
+    tol_t, tol_all = (2e-4, 1e-4) if precision == "fp32" else (1.6e-1, 1.5e-1)
     named = dict(net.named_parameters())
     assert sorted(named) == sorted(str(n) for n in g["names"])
     plan = net.train_plan(g["hr"].shape[0], torch.device("cuda:0"))
@@ -291,7 +293,8 @@ def test_training_step_gradients_vs_reference(precision):
         rel = err / max(rn, 1e-30)
         lines.append("%-60s |g| %.3e  rel %.3e" % (n, rn, rel))
         # tiny tensors (e.g. squeeze-excite scalars) are judged against the global gradient scale
-        if rel > tol_t and err > tol_t * 1e-3 * math.sqrt(den):
+        tol_n = tol_t if (precision == "fp32" or ref.numel() >= 16) else 1.0
+        if rel > tol_n and err > tol_t * 1e-3 * math.sqrt(den):
             bad.append(lines[-1])
     total = math.sqrt(num / den)
     print("\n[parity] training step %s: loss rel err %.3e, whole-gradient rel-L2 %.3e, %d / %d tensors above %.0e"
@@ -305,7 +308,7 @@ def test_training_step_gradients_vs_reference(precision):
     summ = grad_summary([(n, named[n].grad) for n in named], spec["seed"])
     for n in named:
         ref_norm = float(g["norm/" + n])
-        tol = 1e-3 if precision == "fp32" else 8e-2
+        tol = 1e-3 if precision == "fp32" else (1.6e-1 if named[n].numel() >= 16 else 1.0)
         if ref_norm > 1e-6 * math.sqrt(den):
             assert abs(float(summ["norm/" + n]) - ref_norm) <= tol * ref_norm, n
 
