@@ -326,6 +326,104 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# secondary workload: configs[2], the training step (not the headline metric; `--workload train`)
+# ----------------------------------------------------------------------------------------------------------------------
+def run_train(args):
+    """One training step = q_sample + UNet forward (dropout 0.2) + loss + hand-written backward + bucketed gradient
+    all-reduce + one-launch Adam over the flat parameter buffer, batch 4 per GPU at 128x256 (BASELINE.json configs[2])."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import wsr
+    nat = wsr.pkg.native
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.train_batch
+    U = wsr.sub("models.diffusion_models.resdiff.unet").UNet
+    D = wsr.sub("models.diffusion_models.resdiff.resdiff_diffusion").ResDiffDiffusion
+    glue = wsr.sub("autograd_glue")
+    par = wsr.sub("parallel")
+    networks = wsr.sub("models.diffusion_models.networks")
+    torch.manual_seed(0); np.random.seed(rank)
+    net = U(precision=args.train_precision, **CFG_A)
+    networks.init_weights(net, "orthogonal")
+    net = net.to(dev).train()
+    diff = D(net, image_height=128, image_width=256, channels=1, conditional=True).to(dev)
+    diff.set_new_noise_schedule(LINEAR_1000, dev)
+    diff.set_loss(dev)
+    plan = net.train_plan(B, dev)
+    opt = glue.FusedAdam(list(diff.parameters()), lr=1e-4)
+    opt.attach_flat(plan)
+    reducer = par.FlatGradReducer(plan) if world > 1 else None
+    g = torch.Generator().manual_seed(1234 + rank)
+    lr = torch.randn(B, 1, 32, 64, generator=g)
+    sr = torch.nn.functional.interpolate(lr, scale_factor=4, mode="bicubic").to(dev)
+    hr = sr + 0.3 * torch.randn(sr.shape, generator=g).to(dev)
+    numel = hr.numel() * world
+
+    def step():
+        opt.zero_grad()
+        loss = diff.p_losses({"HR": hr, "SR": sr})
+        (loss.sum() / numel).backward()
+        if reducer is not None:
+            reducer.finish()
+        opt.step()
+        return loss
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = nat.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    launches = nat.launches - l0
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms[0])
+    if args.profile_ops and rank == 0:
+        plan.eng.prof = []
+        step()
+        summ = plan.eng.prof_summary()
+        plan.eng.prof = None
+        tot = sum(v[1] for v in summ.values())
+        print("# per-op breakdown of one training step (B=%d, %s): name launches ms TFLOP/s" % (B, args.train_precision), file=sys.stderr)
+        for name, (n, t, fl, nb) in sorted(summ.items(), key=lambda kv: -kv[1][1]):
+            print("#   %-22s %4d %9.3f %9.1f" % (name, n, t, fl / (t * 1e-3) / 1e12 if t > 0 else 0), file=sys.stderr)
+        print("#   total of timed kernels %.3f ms (wall per step %.3f ms)" % (tot, ms), file=sys.stderr)
+    if rank == 0:
+        peaks, peak_src = _peaks()
+        tfl = 3 * FLOPS_PER_SAMPLE_STEP * B / (ms * 1e-3) / 1e12
+        print(json.dumps({
+            "metric": "ResDiff training step samples/sec (fwd+bwd+allreduce+Adam)", "value": B * world / (ms * 1e-3), "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.train_precision, "data": "synthetic",
+            "config": {"workload": "configs[2]: ResDiff Cfg-A training step, 128x256, dropout 0.2, batch %d per GPU" % B,
+                       "global_batch": B * world, "parallelism": "data-parallel x%d, bucketed gradient all-reduce overlapped with backward" % world},
+            "clocks": clocks, "gpu_launches": launches, "loss": float(loss),
+            "roofline": {"bound": "tensor", "achieved": tfl, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tfl / peaks["bf16_tflops"],
+                         "note": "3 x forward algorithmic FLOPs (SURVEY 8d) / step time, per GPU", "peak_source": peak_src}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -339,11 +437,16 @@ def main():
     ap.add_argument("--e2e-budget", type=float, default=60.0, help="seconds allowed for the end-to-end public-API call")
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--profile-ops", action="store_true")
+    ap.add_argument("--workload", default="sample", choices=["sample", "train"], help="sample = headline metric; train = configs[2]")
+    ap.add_argument("--train-batch", type=int, default=4)
+    ap.add_argument("--train-precision", default="bf16", choices=["bf16", "fp32"])
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train":
+        run_train(args)
     else:
         run_ours(args)
 

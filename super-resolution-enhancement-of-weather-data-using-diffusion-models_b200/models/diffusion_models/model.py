@@ -50,14 +50,34 @@ class DDPM(BaseModel):
         self.data, self.months = self.set_device(data[0]), data[1]
 
     def optimize_parameters(self):
-        """reference :61-69: zero_grad, loss / numel, backward, Adam step."""
+        """reference :61-69: zero_grad, loss / numel, backward, Adam step.  Under ``torch.distributed`` (one process per
+        GPU) every rank holds a shard of the batch: the loss is divided by the GLOBAL element count and the gradients are
+        SUM-all-reduced in buckets while the backward pass is still running (parallel.FlatGradReducer)."""
+        import torch.distributed as dist
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.optG.zero_grad()
-        l_pix = self.netG(self.data)
         b, c, h, w = self.data['HR'].shape
-        l_pix = l_pix.sum() / int(b * c * h * w)
+        reducer = self._grad_reducer(b) if world > 1 else None
+        l_pix = self.netG(self.data)
+        l_pix = l_pix.sum() / int(b * c * h * w * world)
         l_pix.backward()
+        if reducer is not None:
+            reducer.finish()
         self.optG.step()
+        if world > 1:
+            l_pix = l_pix.detach().clone()
+            dist.all_reduce(l_pix)
         self.log_dict['l_pix'] = l_pix.item()
+
+    def _grad_reducer(self, batch):
+        """FlatGradReducer bound to the denoiser's train plan for this local batch size (created once)."""
+        from ...parallel import FlatGradReducer
+        net = self._net().denoise_fn
+        plan = net.train_plan(batch, self.device)
+        red = getattr(plan, "_reducer", None)
+        if red is None:
+            red = plan._reducer = FlatGradReducer(plan)
+        return red
 
     def generate_sr(self, continous=False):
         self.netG.eval()

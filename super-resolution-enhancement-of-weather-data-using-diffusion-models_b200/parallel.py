@@ -117,3 +117,44 @@ class GradBucketer:
     def remove(self):
         for h in self._hooks:
             h.remove()
+
+
+class FlatGradReducer:
+    """Bucketed, overlapped SUM all-reduce over the flat gradient buffer of a ``UNetTrainPlan``.
+
+    The plan lays its parameter gradients out in the order the backward pass finishes them and calls
+    ``on_ready(lo, hi)`` as soon as ``gflat[lo:hi]`` is final; this class cuts that range into ~``bucket_mb`` MB buckets
+    and launches one asynchronous all-reduce per bucket right away, so the exchange of the up-path gradients overlaps
+    the backward of the down path (NCCL orders each collective after the kernels already enqueued on the compute
+    stream).  ``finish()`` (before ``optimizer.step()``) waits for all of them.  Each rank must scale its loss by
+    1 / (GLOBAL number of elements) -- the reference's ``l_pix.sum() / (b*c*h*w)`` over the whole DataParallel batch
+    (models/diffusion_models/model.py:64-66) -- so that the SUM of the per-rank gradients is the reference's gradient.
+    """
+
+    def __init__(self, plan, bucket_mb=32.0, group=None):
+        self.plan, self.group = plan, group
+        self.bucket_elems = max(1, int(bucket_mb * (1 << 20)) // 4)
+        self._pending = []
+        self.launched = []                 # (lo, hi) of every bucket of the last step, for tests / logging
+        plan.on_ready = self._on_ready
+
+    def _on_ready(self, lo, hi):
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return
+        a = lo
+        while a < hi:
+            b = min(hi, a + self.bucket_elems)
+            work = dist.all_reduce(self.plan.gflat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._pending.append(work)
+            self.launched.append((a, b))
+            a = b
+
+    def finish(self):
+        for w in self._pending:
+            w.wait()
+        self._pending.clear()
+        done, self.launched = self.launched, []
+        return done
+
+    def remove(self):
+        self.plan.on_ready = None

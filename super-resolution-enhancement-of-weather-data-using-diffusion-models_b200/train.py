@@ -1,8 +1,9 @@
 """train.py -- same command line as the reference's train.py:208-212 (``-c CONFIG -p {train,val} -gpu IDS``).
 
 ``-p val`` runs the validation loop (generate_sr per batch, RMSE in standardised units) on the CUDA path.
-``-p train`` builds the optimiser and runs ``optimize_parameters``; the backward pass of the CUDA denoiser is not
-implemented yet, so training stops with an explicit NotImplementedError after the forward loss."""
+``-p train`` builds the optimiser and runs ``optimize_parameters`` (forward, hand-written backward, fused Adam).  Under
+``torchrun`` (one process per GPU) the batch is sharded across ranks and the gradients are all-reduced in buckets
+overlapped with the backward pass (parallel.FlatGradReducer); weights start identical on every rank (same seed)."""
 import argparse
 import logging
 import os
@@ -30,6 +31,12 @@ def main(argv=None):
     import numpy as np
     import random
     random.seed(0); np.random.seed(0); torch.manual_seed(0)                 # training/utils.py:39-50
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+        args.gpu_ids = os.environ.get("LOCAL_RANK", "0")
     opt = Config(args, experiment=True).params
     for key in ("resume_state",):
         if opt["path"].get(key) and not os.path.exists(str(opt["path"][key]) + "_gen.pth"):
@@ -49,13 +56,16 @@ def main(argv=None):
         log.info("validation RMSE (standardised units): %.6f", (se / max(n, 1)) ** 0.5)
         return
     it = 0
+    par = wsr.sub("parallel")
     for batch, months in data.batches_from_opt(opt, "train"):
         it += 1
+        if world > 1:
+            batch = par.shard_batch(batch, rank, world)
         model.feed_data((batch, months))
         model.optimize_parameters()
         if it % opt["train"]["print_freq"] == 0:
             log.info("iter %d  l_pix %.6f", it, model.get_current_log()["l_pix"])
-        if it % opt["train"]["save_checkpoint_freq"] == 0:
+        if it % opt["train"]["save_checkpoint_freq"] == 0 and rank == 0:
             model.save_network(0, it)
 
 

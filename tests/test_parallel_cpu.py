@@ -57,7 +57,18 @@ def _worker(rank, world, port, q):
         bucketer.finish()
         (ref(x) - y).abs().sum().div(y.numel()).backward()
         ok_grad = all(torch.allclose(a.grad, b.grad, atol=1e-6) for a, b in zip(model.parameters(), ref.parameters()))
-        q.put((rank, bool(ok_sample), bool(ok_grad), len(bucketer.buckets)))
+        # flat-buffer reducer (the train plan's gradient layout): buckets are launched as ranges become final
+        class _Plan:
+            gflat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+            on_ready = None
+        plan = _Plan()
+        red = par.FlatGradReducer(plan, bucket_mb=4 * 300 / (1 << 20))       # 300-element buckets
+        plan.on_ready(0, 650)
+        plan.on_ready(650, 1000)
+        done = red.finish()
+        ok_flat = torch.allclose(plan.gflat, torch.arange(1000, dtype=torch.float32) * 3) and \
+            done == [(0, 300), (300, 600), (600, 650), (650, 950), (950, 1000)]
+        q.put((rank, bool(ok_sample), bool(ok_grad) and bool(ok_flat), len(bucketer.buckets)))
     finally:
         dist.destroy_process_group()
 
