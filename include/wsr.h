@@ -121,6 +121,13 @@ typedef struct {
   int up;                                                      /* 1 or 2 */
 } WsrWgradDesc;
 int wsr_conv_wgrad_simt(const WsrWgradDesc* d, const WsrTapTable* t, void* stream);
+/* tcgen05 version: the reduction runs over pixels, so both operands are consumed MN-major (channel-contiguous NHWC boxes
+ * loaded by TMA; no transposed copies).  Requires bf16 x / dy, pitches % 8, 16-byte aligned bases, a table that loops
+ * over the whole output (out_mul 1), loop-grid dimensions that form 64-pixel tiles, and dbias == NULL (use
+ * wsr_col_sums).  Partial sums of the K splits are added to dw with fp32 reductions. */
+int wsr_conv_wgrad_tc(const WsrWgradDesc* d, const WsrTapTable* t, void* stream);
+/* out[c] += sum over pixels of x[p][c] (NHWC, pitch x_ld): bias gradients. */
+int wsr_col_sums(const void* x, int x_dtype, int64_t pixels, int C, int x_ld, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Batched GEMM  D[b][m][n] = alpha * sum_k A[b][m][k] * B[b][n][k] (+ bias[n]) (+ res[b][m][n]),

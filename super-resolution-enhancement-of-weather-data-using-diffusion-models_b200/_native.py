@@ -115,6 +115,8 @@ SIGNATURES = {
     "wsr_conv_taps_simt": [C.POINTER(ConvDesc), C.POINTER(TapTable), _P],
     "wsr_conv_taps_tc": [C.POINTER(ConvDesc), C.POINTER(TapTable), _P],
     "wsr_conv_wgrad_simt": [C.POINTER(WgradDesc), C.POINTER(TapTable), _P],
+    "wsr_conv_wgrad_tc": [C.POINTER(WgradDesc), C.POINTER(TapTable), _P],
+    "wsr_col_sums": [_P, _I, _L, _I, _I, _P, _P],
     "wsr_gn_apply_dropout": [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _I, _F, _I, _P, _I, _I, _F, _U64, _U32, _P],
     "wsr_gn_bwd_reduce": [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _I, _F, _I, _P, _I, _I, _F, _U64, _U32, _P, _I, _P],
     "wsr_gn_bwd_apply": [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _I, _F, _I, _P, _I, _I, _F, _U64, _U32, _P, _I, _P, _I, _I,

@@ -50,7 +50,11 @@ struct TcParams {
   int nbatch;                   // extra batch dimension (attention GEMMs); 1 for convolutions
   int a_zmul, b_zmul;           // A coord3 += zb*a_zmul ; B coord2 += zb*b_zmul
   int n_tiles;                  // tiles along columns
-  int a_bytes;                  // bytes one A box load delivers (rows_box * 128)
+  int a_bytes;                  // bytes one A tile load delivers (rows_box * 128, or 8 KB per 64-row block when MN-major)
+  int b_bytes;                  // bytes one B tile load delivers; 0 = BLOCK_N * 128 (K-major box)
+  int a_mn, b_mn;               // operand is MN-major (contiguous along rows / columns, strided along K): loaded as
+                                // [64 MN][64 K] boxes 8 KB apart and consumed through the MN-major UMMA descriptor
+  int a_blk, b_blk;             // number of such 64-wide boxes per tile
   int dbg;                      // debugging switches (env WSR_TC_DBG): 1 skip epilogue work, 2 skip MMA issue, 4 skip stores only
   int halo_bo;                  // debugging switch: put (start row & 7) into the descriptor base-offset field
   int halo_rows;                // halo mode: output rows per tile (1 or 2; 2 = two accumulators share every weight tile)
@@ -167,9 +171,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             for (int c = 0; c < e.nchunks; ++c) {
               mbar_wait(&empty_a[sa], pa ^ 1);
               uint8_t* st = smem + sa * (kABytes + Cfg::kBBytes);
-              mbar_expect_tx(&full_a[sa], (uint32_t)(p.a_bytes + Cfg::kBBytes));
-              tma_load_4d(st, &p.amap[e.amap], &full_a[sa], e.a_c0 + c * kBlockK, c1 + e.d1, c2 + e.d2, c3);
-              tma_load_3d(st + kABytes, &p.bmap[e.bmap], &full_a[sa], e.b_k0 + c * kBlockK, t.nt * BLOCK_N, e.b_z + t.zb * p.b_zmul);
+              mbar_expect_tx(&full_a[sa], (uint32_t)(p.a_bytes + (p.b_bytes ? p.b_bytes : Cfg::kBBytes)));
+              if (!p.a_mn) {
+                tma_load_4d(st, &p.amap[e.amap], &full_a[sa], e.a_c0 + c * kBlockK, c1 + e.d1, c2 + e.d2, c3);
+              } else {
+                for (int j = 0; j < p.a_blk; ++j) tma_load_4d(st + j * 8192, &p.amap[e.amap], &full_a[sa], c1 + 64 * j, e.a_c0 + c * kBlockK, 0, c3);
+              }
+              if (!p.b_mn) {
+                tma_load_3d(st + kABytes, &p.bmap[e.bmap], &full_a[sa], e.b_k0 + c * kBlockK, t.nt * BLOCK_N, e.b_z + t.zb * p.b_zmul);
+              } else {
+                for (int j = 0; j < p.b_blk; ++j)
+                  tma_load_3d(st + kABytes + j * 8192, &p.bmap[e.bmap], &full_a[sa], t.nt * BLOCK_N + 64 * j, e.b_k0 + c * kBlockK, e.b_z + t.zb * p.b_zmul);
+              }
               if (++sa == kRingA) { sa = 0; pa ^= 1; }
             }
           }
@@ -218,17 +231,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::kAccCols);
         if constexpr (!HALO) {
+          // K-major operand: +32 bytes along K inside the swizzle atom = +2 in the address field, LBO unused (1).
+          // MN-major operand: 16 K rows of 128 bytes = +128, LBO = 8 KB (the next 64-wide box).
+          const uint32_t a_st = p.a_mn ? 128u : 2u, b_st = p.b_mn ? 128u : 2u;
+          const uint32_t a_lbo = (p.a_mn ? (8192u >> 4) : 1u) << 16, b_lbo = (p.b_mn ? (8192u >> 4) : 1u) << 16;
+          const uint32_t idesc = Cfg::kIdesc | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16);
           for (int kb = 0; kb < p.total_kb; ++kb) {
             mbar_wait(&full_a[sa], pa);
             tc_fence_after();
-            const uint32_t a_lo = desc_lo(smem_u32(smem + sa * (kABytes + Cfg::kBBytes)));
-            const uint32_t b_lo = a_lo + (uint32_t)(kABytes >> 4);
+            const uint32_t s_lo = (smem_u32(smem + sa * (kABytes + Cfg::kBBytes)) & 0x3FFFFu) >> 4;
+            const uint32_t a_lo = s_lo | a_lbo;
+            const uint32_t b_lo = (s_lo + (uint32_t)(kABytes >> 4)) | b_lbo;
             if (!(p.dbg & 2)) {
-              // +32 bytes along K inside the swizzle atom = +2 in the address field
-              umma_bf16_lo(d_tmem, a_lo, b_lo, Cfg::kIdesc, kb != 0 ? 1u : 0u);
-              umma_bf16_lo(d_tmem, a_lo + 2, b_lo + 2, Cfg::kIdesc, 1u);
-              umma_bf16_lo(d_tmem, a_lo + 4, b_lo + 4, Cfg::kIdesc, 1u);
-              umma_bf16_lo(d_tmem, a_lo + 6, b_lo + 6, Cfg::kIdesc, 1u);
+              umma_bf16_lo(d_tmem, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u);
+              umma_bf16_lo(d_tmem, a_lo + a_st, b_lo + b_st, idesc, 1u);
+              umma_bf16_lo(d_tmem, a_lo + 2 * a_st, b_lo + 2 * b_st, idesc, 1u);
+              umma_bf16_lo(d_tmem, a_lo + 3 * a_st, b_lo + 3 * b_st, idesc, 1u);
             }
             umma_commit(&empty_a[sa]);
             if (kb == p.total_kb - 1) umma_commit(&tfull_bar[acc]);
@@ -841,10 +859,14 @@ extern "C" int wsr_gemm_tc(const WsrGemmDesc* g, void* stream) {
   int rc = validate_gemm_desc(g);
   if (rc) return rc;
   WSR_REQUIRE(g->a_dtype == WSR_BF16 && g->b_dtype == WSR_BF16, WSR_E_UNSUPPORTED, "gemm_tc: bf16 operands only");
-  WSR_REQUIRE(g->a_sk == 1 && g->b_sk == 1, WSR_E_UNSUPPORTED, "gemm_tc: both operands must be K-major (unit k stride)");
+  // operand majorness from the strides: unit k stride = K-major; unit row / column stride = MN-major (transposed operand)
+  const bool a_mn = g->a_sk != 1, b_mn = g->b_sk != 1;
+  WSR_REQUIRE(!a_mn || g->a_sm == 1, WSR_E_UNSUPPORTED, "gemm_tc: A needs a unit stride along k or along m");
+  WSR_REQUIRE(!b_mn || g->b_sn == 1, WSR_E_UNSUPPORTED, "gemm_tc: B needs a unit stride along k or along n");
   WSR_REQUIRE(g->K % 64 == 0, WSR_E_UNSUPPORTED, "gemm_tc: K=%d must be a multiple of 64", g->K);
   WSR_REQUIRE((((uintptr_t)g->bias) & 15) == 0, WSR_E_UNSUPPORTED, "gemm_tc: bias must be 16-byte aligned");
-  WSR_REQUIRE(g->a_sm % 8 == 0 && g->b_sn % 8 == 0 && g->a_sb % 8 == 0 && g->b_sb % 8 == 0 && (((uintptr_t)g->a) & 15) == 0 &&
+  const int64_t a_pitch = a_mn ? g->a_sk : g->a_sm, b_pitch = b_mn ? g->b_sk : g->b_sn;
+  WSR_REQUIRE(a_pitch % 8 == 0 && b_pitch % 8 == 0 && g->a_sb % 8 == 0 && g->b_sb % 8 == 0 && (((uintptr_t)g->a) & 15) == 0 &&
                   (((uintptr_t)g->b) & 15) == 0,
               WSR_E_UNSUPPORTED, "gemm_tc: strides must be multiples of 8 elements, bases 16-byte aligned");
   TcParams p;
@@ -852,7 +874,9 @@ extern "C" int wsr_gemm_tc(const WsrGemmDesc* g, void* stream) {
   p.t1 = g->M < 128 ? g->M : 128; p.t2 = 1; p.t3 = 1;
   p.g1 = cdiv(g->M, p.t1); p.g2 = 1; p.g3 = 1;
   p.nbatch = g->batch; p.a_zmul = 1; p.b_zmul = 1;
-  p.a_bytes = p.t1 * 128;
+  p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
+  p.a_blk = cdiv(p.t1, 64);
+  p.a_bytes = a_mn ? p.a_blk * 8192 : p.t1 * 128;
   p.M1 = g->M; p.M2 = 1; p.M3 = 1;
   p.Ncols = g->N;
   p.out = g->d; p.out_dtype = g->d_dtype;
@@ -863,20 +887,39 @@ extern "C" int wsr_gemm_tc(const WsrGemmDesc* g, void* stream) {
   p.r_s1 = g->res_sm; p.r_sb = g->res_sb; p.r_sc = g->res_sn;
   const int m_tiles = p.g1 * g->batch;
   const int bn = pick_block_n(g->N, m_tiles);
+  p.b_blk = cdiv(bn < g->N ? bn : g->N, 64);
+  p.b_bytes = b_mn ? p.b_blk * 8192 : 0;
   {
-    uint64_t dims[4] = {(uint64_t)g->K, (uint64_t)g->M, 1, (uint64_t)g->batch};
-    uint64_t str[3] = {(uint64_t)g->a_sm * 2, (uint64_t)g->a_sm * g->M * 2, (uint64_t)(g->batch > 1 ? g->a_sb : g->a_sm * g->M) * 2};
+    uint64_t dims[4], str[3];
+    uint32_t box[4];
+    if (!a_mn) {
+      dims[0] = (uint64_t)g->K; dims[1] = (uint64_t)g->M; dims[2] = 1; dims[3] = (uint64_t)g->batch;
+      str[0] = (uint64_t)g->a_sm * 2; str[1] = (uint64_t)g->a_sm * g->M * 2; str[2] = (uint64_t)(g->batch > 1 ? g->a_sb : g->a_sm * g->M) * 2;
+      box[0] = 64; box[1] = (uint32_t)p.t1; box[2] = 1; box[3] = 1;
+    } else {
+      dims[0] = (uint64_t)g->M; dims[1] = (uint64_t)g->K; dims[2] = 1; dims[3] = (uint64_t)g->batch;
+      str[0] = (uint64_t)g->a_sk * 2; str[1] = (uint64_t)g->a_sk * g->K * 2; str[2] = (uint64_t)(g->batch > 1 ? g->a_sb : g->a_sk * g->K) * 2;
+      box[0] = 64; box[1] = 64; box[2] = 1; box[3] = 1;
+    }
     if (g->batch > 1 && g->a_sb == 0) { dims[3] = 1; p.a_zmul = 0; str[2] = str[1]; }
-    uint32_t box[4] = {64, (uint32_t)p.t1, 1, 1};
     rc = encode_map(&p.amap[0], g->a, 4, dims, str, box);
     if (rc) return rc;
     for (int i = 1; i < kNumAMaps; ++i) p.amap[i] = p.amap[0];
   }
   {
-    uint64_t dims[3] = {(uint64_t)g->K, (uint64_t)g->N, (uint64_t)g->batch};
-    uint64_t str[2] = {(uint64_t)g->b_sn * 2, (uint64_t)(g->batch > 1 ? g->b_sb : g->b_sn * g->N) * 2};
-    if (g->batch > 1 && g->b_sb == 0) { dims[2] = 1; p.b_zmul = 0; str[1] = (uint64_t)g->b_sn * g->N * 2; }
-    uint32_t box[3] = {64, (uint32_t)bn, 1};
+    uint64_t dims[3], str[2];
+    uint32_t box[3];
+    if (!b_mn) {
+      dims[0] = (uint64_t)g->K; dims[1] = (uint64_t)g->N; dims[2] = (uint64_t)g->batch;
+      str[0] = (uint64_t)g->b_sn * 2; str[1] = (uint64_t)(g->batch > 1 ? g->b_sb : g->b_sn * g->N) * 2;
+      box[0] = 64; box[1] = (uint32_t)bn; box[2] = 1;
+      if (g->batch > 1 && g->b_sb == 0) { dims[2] = 1; p.b_zmul = 0; str[1] = (uint64_t)g->b_sn * g->N * 2; }
+    } else {
+      dims[0] = (uint64_t)g->N; dims[1] = (uint64_t)g->K; dims[2] = (uint64_t)g->batch;
+      str[0] = (uint64_t)g->b_sk * 2; str[1] = (uint64_t)(g->batch > 1 ? g->b_sb : g->b_sk * g->K) * 2;
+      box[0] = 64; box[1] = 64; box[2] = 1;
+      if (g->batch > 1 && g->b_sb == 0) { dims[2] = 1; p.b_zmul = 0; str[1] = (uint64_t)g->b_sk * g->K * 2; }
+    }
     rc = encode_map(&p.bmap[0], g->b, 3, dims, str, box);
     if (rc) return rc;
     p.bmap[1] = p.bmap[0];

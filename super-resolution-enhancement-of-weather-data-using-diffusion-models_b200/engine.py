@@ -274,9 +274,12 @@ class Engine:
         g.d, g.d_dtype, (g.d_sb, g.d_sm, g.d_sn) = d_ptr, d_dt, d_s
         g.bias = _ptr(bias)
         g.batch, g.M, g.N, g.K, g.alpha = batch, M, N, K, alpha
-        tc_ok = (self.use_tc and not force_simt and a_dt == nat.BF16 and b_dt == nat.BF16 and a_s[2] == 1 and b_s[2] == 1
-                 and K % 64 == 0 and a_s[1] % 8 == 0 and b_s[1] % 8 == 0 and a_s[0] % 8 == 0 and b_s[0] % 8 == 0
-                 and a_ptr % 16 == 0 and b_ptr % 16 == 0)
+        # each operand is either K-major (unit k stride) or MN-major (unit row stride, i.e. a transposed view): the
+        # tcgen05 kernel consumes both directly, the strided dimension must be a multiple of 8 elements
+        def _major_ok(st):
+            return (st[2] == 1 and st[1] % 8 == 0) or (st[1] == 1 and st[2] % 8 == 0)
+        tc_ok = (self.use_tc and not force_simt and a_dt == nat.BF16 and b_dt == nat.BF16 and _major_ok(a_s) and _major_ok(b_s)
+                 and K % 64 == 0 and a_s[0] % 8 == 0 and b_s[0] % 8 == 0 and a_ptr % 16 == 0 and b_ptr % 16 == 0)
         flops = 2 * batch * M * N * K
         if tc_ok:
             self.n_tc += 1
@@ -325,18 +328,44 @@ class Engine:
         self.call("wsr_gn_bwd_apply", *common, dx.ptr, dx.dt, dx.ld, 1 if accumulate else 0, _ptr(dgamma), _ptr(dbeta),
                   colsum, colsum_ld, self.stream, nbytes=(4 if accumulate else 3) * nb, tag="gn_bwd_apply")
 
-    def wgrad(self, x, dy, taps, dw, dw_strides, dbias=None, up=1):
+    def wgrad(self, x, dy, taps, dw, dw_strides, dbias=None, up=1, force_simt=False):
         """dw (fp32 tensor view, strides (tap, co, ci) in elements) += weight gradient; dbias += column sums of dy."""
         d = nat.WgradDesc()
         d.x, d.x_dtype, d.N, d.H, d.W, d.Cin, d.x_ld = x.ptr, x.dt, x.N, x.H, x.W, x.C, x.ld
         d.dy, d.dy_dtype, d.Cout, d.dy_ld = dy.ptr, dy.dt, dy.C, dy.ld
         d.dw = dw.data_ptr()
         d.dw_stap, d.dw_sco, d.dw_sci = dw_strides
-        d.dbias = _ptr(dbias)
         d.up = up
+        flops = 2 * x.N * taps.GH * taps.GW * dy.C * x.C * taps.ntaps
+        if not force_simt and self._tc_wgrad_ok(x, dy, taps, up):
+            d.dbias = 0
+            self.n_tc += 1
+            self.call("wsr_conv_wgrad_tc", C.byref(d), C.byref(taps), self.stream, flops=flops,
+                      tag="wgrad_tc" if not self.prof_detail else "wgrad_tc %4d->%4d t%d %dx%d" % (x.C, dy.C, taps.ntaps, x.H, x.W))
+            if dbias is not None:
+                self.call("wsr_col_sums", dy.ptr, dy.dt, dy.N * dy.H * dy.W, dy.C, dy.ld, dbias.data_ptr(), self.stream,
+                          nbytes=dy.N * dy.H * dy.W * dy.C * 2, tag="col_sums")
+            return
+        if self.strict_tc and not force_simt:
+            raise nat.WsrError("strict_tc: wgrad Cin=%d Cout=%d not eligible for the tcgen05 kernel" % (x.C, dy.C))
+        d.dbias = _ptr(dbias)
         self.n_simt += 1
-        self.call("wsr_conv_wgrad_simt", C.byref(d), C.byref(taps), self.stream,
-                  flops=2 * x.N * taps.GH * taps.GW * dy.C * x.C * taps.ntaps, tag="wgrad_simt")
+        self.call("wsr_conv_wgrad_simt", C.byref(d), C.byref(taps), self.stream, flops=flops, tag="wgrad_simt")
+
+    def _tc_wgrad_ok(self, x, dy, taps, up):
+        if not self.use_tc or x.dt != nat.BF16 or dy.dt != nat.BF16:
+            return False
+        if x.ld % 8 or dy.ld % 8 or x.ptr % 16 or dy.ptr % 16:
+            return False
+        if taps.out_mul != 1 or taps.GH != taps.OH or taps.GW != taps.OW:
+            return False
+        if taps.in_sub == 2 and (x.H % 2 or x.W % 2):
+            return False
+        lw, lh = (x.W, x.H) if up == 2 else (taps.GW, taps.GH)
+        t1 = min(lw, 64)
+        t2 = min(lh, 64 // t1)
+        t3 = min(x.N, 64 // (t1 * t2))
+        return t1 * t2 * t3 == 64
 
     def softmax_bwd(self, p, p_dt, dp, dp_dt, rows, cols, scale, ds, ds_dt):
         self.call("wsr_softmax_bwd_rows", p.data_ptr(), p_dt, dp.data_ptr(), dp_dt, rows, cols, cols, scale, ds.data_ptr(), ds_dt,

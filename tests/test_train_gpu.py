@@ -122,6 +122,64 @@ def test_conv_dgrad_tc_vs_simt(case):
     assert rel_l2(dx_tc.to_nchw(eng), dx_ref) < 1.5e-2
 
 
+WGRAD_TC_CASES = [
+    # N, Cin, Cout, H, W, k, stride, upsample, x_ld (0 = Cin)
+    (2, 64, 64, 8, 16, 3, 1, False, 0),
+    (1, 128, 64, 4, 128, 3, 1, False, 0),
+    (2, 192, 128, 8, 16, 3, 1, False, 0),        # partial Cin tile (192 in a 256-wide tile)
+    (2, 64, 320, 8, 16, 1, 1, False, 0),         # three Cout tiles, the last one half full
+    (2, 64, 64, 16, 32, 3, 2, False, 0),         # Downsample: phase-subsampled X views
+    (2, 64, 64, 8, 16, 3, 1, True, 0),           # Upsample: four dY phase segments per tap
+    (2, 5, 64, 8, 16, 3, 1, False, 64),          # stem: 5 channels inside a 64-channel buffer
+    (8, 512, 512, 2, 4, 3, 1, False, 0),         # deepest level: one 64-pixel tile spans all eight images
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_TC_CASES)
+def test_conv_wgrad_tc_vs_simt(case):
+    """bf16 mode: the weight gradient on tcgen05 (MN-major operands, split-K) against the SIMT kernel on the same bf16
+    inputs, and against autograd."""
+    N, Cin, Cout, H, W, k, stride, up, x_ld = case
+    dev = _dev()
+    eng = Engine(dev, "bf16")
+    assert eng.use_tc
+    x, w, dy, _, dw_ref, db_ref = _autograd_case(case[:8], dev, seed=2)
+    xa = _nhwc(x, eng, ld=x_ld or None)
+    dya = _nhwc(dy, eng)
+    taps = T.forward_upsample_taps(H, W) if up else T.forward_taps(k, stride, H, W)
+    outs = []
+    for force in (False, True):
+        dw = torch.zeros_like(w)
+        db = torch.zeros(Cout, device=dev)
+        n_tc = eng.n_tc
+        eng.wgrad(xa, dya, taps, dw, (1, Cin * k * k, k * k), db, 2 if up else 1, force_simt=force)
+        assert (eng.n_tc == n_tc + 1) == (not force)
+        outs.append((dw, db))
+    assert rel_l2(outs[0][0], outs[1][0]) < 2e-5, rel_l2(outs[0][0], outs[1][0])
+    assert rel_l2(outs[0][1], outs[1][1]) < 2e-5
+    assert rel_l2(outs[0][0], dw_ref) < 8e-3 and rel_l2(outs[0][1], db_ref) < 8e-3
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K,batch", [(128, 128, 64, 2), (256, 64, 128, 3), (64, 192, 256, 1), (512, 512, 64, 2)])
+def test_gemm_tc_transposed_operands(a_mn, b_mn, M, N, K, batch):
+    """Attention backward needs A^T / B^T operands: the tcgen05 GEMM consumes MN-major (transposed) operands directly."""
+    dev = _dev()
+    eng = Engine(dev, "bf16")
+    torch.manual_seed(7)
+    a = torch.randn(batch, M, K, device=dev).to(torch.bfloat16)
+    b = torch.randn(batch, N, K, device=dev).to(torch.bfloat16)
+    ref = torch.matmul(a.float(), b.float().transpose(1, 2))
+    a_st = a.transpose(1, 2).contiguous() if a_mn else a          # stored (batch, K, M): unit stride along m
+    b_st = b.transpose(1, 2).contiguous() if b_mn else b
+    a_s = (M * K, 1, M) if a_mn else (M * K, K, 1)
+    b_s = (N * K, 1, N) if b_mn else (N * K, K, 1)
+    d = torch.zeros(batch, M, N, device=dev, dtype=torch.float32)
+    eng.gemm(a_st.data_ptr(), nat.BF16, a_s, b_st.data_ptr(), nat.BF16, b_s, d.data_ptr(), nat.F32, (M * N, N, 1), batch, M, N, K)
+    assert eng.n_tc == 1 and eng.n_simt == 0
+    assert rel_l2(d, ref) < 1e-5
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # GroupNorm + Swish (+ dropout) backward
 # ----------------------------------------------------------------------------------------------------------------
