@@ -76,6 +76,11 @@ typedef struct {
   /* optional fused GroupNorm statistics of the OUTPUT: per-(image, channel) sum and sum of squares of y (taken from the
    * fp32 epilogue values, before the store rounding) are ACCUMULATED into gn_stats[n*gn_stats_ld + 2*co + {0,1}] (doubles; see wsr_gn_stats).  NULL = off. */
   double* gn_stats; int gn_stats_ld;
+  /* optional fused GroupNorm (+ Swish) of the INPUT (wsr_conv_tc only, layers for which wsr_conv_tc_can_fuse_gn() is 1):
+   * the convolution reads the RAW tensor x and applies a = gn_act(x * scale + shift) on its way into shared memory, with
+   * gn_table[n*gn_table_ld + c] = (scale, shift) pairs (2 floats) from wsr_gn_finalize; zero padding applies to a.  The
+   * optional second segment x2 stays raw.  Replaces the separate GroupNorm+Swish pass of nn_modules/resnet.py:21-22. */
+  const float* gn_table; int gn_table_ld; int gn_act;
 } WsrConvDesc;
 
 /* fp32-accumulate SIMT implicit GEMM; any dtype, any channel count.  This is the "fp32 check mode" kernel. */
@@ -83,6 +88,7 @@ int wsr_conv_simt(const WsrConvDesc* d, void* stream);
 /* tcgen05/TMEM implicit GEMM fed by TMA; bf16 operands, fp32 accumulation.  Requires x_dtype = BF16, Cin % 64 == 0,
  * Cin2 % 64 == 0, Cout % 16 == 0, W a power of two (>= 2), pitches % 8 == 0, 16-byte aligned bases. */
 int wsr_conv_tc(const WsrConvDesc* d, void* stream);
+int wsr_conv_tc_can_fuse_gn(const WsrConvDesc* d);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Tap-table convolution: the same kernels driven by an explicit list of taps instead of (ksize, stride, upsample).
@@ -171,6 +177,10 @@ int wsr_gn_stats(const void* x, int x_dtype, int N, int HW, int C, int x_ld, dou
 int wsr_gn_apply(const void* x, int x_dtype, int N, int HW, int C, int x_ld, const double* stats, int stats_ld,
                  const float* gamma, const float* beta, int groups, float eps, int act, void* y, int y_dtype,
                  int y_ld, void* stream);
+/* table[n*table_ld + c] = (gamma_c * rstd, beta_c - mean * gamma_c * rstd) as float pairs (table_ld counts PAIRS), so that
+ * GroupNorm(x)*gamma+beta = x*scale+shift; consumed by the fused-input mode of wsr_conv_tc (WsrConvDesc.gn_table). */
+int wsr_gn_finalize(const double* stats, int stats_ld, int N, int HW, int C, int groups, float eps, const float* gamma,
+                    const float* beta, float* table, int table_ld, void* stream);
 int wsr_fill_zero(void* p, int64_t bytes, void* stream);
 /* Training-mode Block (nn_modules/resnet.py:21-24: GroupNorm -> Swish -> Dropout -> Conv): wsr_gn_apply followed by
  * dropout, y *= keep / (1 - p); the keep mask is Philox4x32-10(seed, tag) indexed by the logical element (n*HW + pix)*C + c,

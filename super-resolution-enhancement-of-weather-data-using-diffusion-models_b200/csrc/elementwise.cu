@@ -242,6 +242,25 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x, int HW, int C, int ld,
   }
 }
 
+// (scale, shift) per (image, channel): a = x * scale + shift  ==  GroupNorm(x) * gamma + beta
+__global__ void gn_finalize_kernel(const double* __restrict__ stats, int stats_ld, int HW, int C, int groups, float eps,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float2* __restrict__ tab, int tab_ld) {
+  const int n = blockIdx.x;
+  const int cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g0 = (c / cpg) * cpg;
+    double a = 0.0, b = 0.0;
+    for (int j = 0; j < cpg; ++j) { a += stats[(int64_t)n * stats_ld + (g0 + j) * 2]; b += stats[(int64_t)n * stats_ld + (g0 + j) * 2 + 1]; }
+    const double cnt = (double)cpg * HW;
+    const double mean = a / cnt;
+    double var = b / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * rstd;
+    tab[(int64_t)n * tab_ld + c] = make_float2(sc, beta[c] - (float)mean * sc);
+  }
+}
+
 struct GnGeom { int vec, CV, PL, chunk, threads; };
 static GnGeom gn_geom(int dt, int C, int ld, int ld2, const void* p, const void* p2) {
   GnGeom g;
@@ -558,6 +577,16 @@ static int gn_apply_impl(const void* x, int x_dtype, int N, int HW, int C, int x
     else { if (g.vec == 4) GN_APPLY(float, 4, false); else GN_APPLY(float, 1, false); }
   }
 #undef GN_APPLY
+  WSR_LAUNCH_OK();
+  return WSR_OK;
+}
+
+extern "C" int wsr_gn_finalize(const double* stats, int stats_ld, int N, int HW, int C, int groups, float eps, const float* gamma,
+                               const float* beta, float* table, int table_ld, void* stream) {
+  WSR_REQUIRE(stats && gamma && beta && table && N > 0 && HW > 0 && C > 0 && stats_ld >= 2 * C && table_ld >= C, WSR_E_INVALID, "gn_finalize: bad argument");
+  WSR_REQUIRE(groups > 0 && C % groups == 0, WSR_E_INVALID, "gn_finalize: C=%d not divisible by groups=%d", C, groups);
+  gn_finalize_kernel<<<N, C >= 256 ? 256 : ((C + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(stats, stats_ld, HW, C, groups, eps, gamma, beta,
+                                                                                       (float2*)table, table_ld);
   WSR_LAUNCH_OK();
   return WSR_OK;
 }

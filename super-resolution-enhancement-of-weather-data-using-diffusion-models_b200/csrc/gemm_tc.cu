@@ -70,10 +70,19 @@ struct TcParams {
   const void* res; int res_dtype; long long r_s1, r_s2, r_s3, r_sb, r_sc; float res_scale;
   const void* res2; int res2_dtype; long long q_s1, q_s2, q_s3, q_sb, q_sc; float res2_scale;
   double* stats; int stats_ld;  // fused GroupNorm statistics of the output (needs t1*t2 % 32 == 0), or nullptr
+  // fused GroupNorm (+ Swish) of the INPUT (halo mode, FUSE kernels): the activation operand is not fetched by TMA but by
+  // four "transform" warps that read the raw tensor from global memory, apply a = act(x * scale[n][c] + shift[n][c]) and
+  // write the 128B-swizzled tile themselves (out-of-image pixels stay zero = the convolution's padding of the
+  // NORMALISED tensor).  gn_tab: [N][gn_ld] float2 (scale, shift) from wsr_gn_finalize.
+  const void* xg; int xg_ld, xg_H, xg_W;
+  const void* x2g; int x2g_ld;
+  const float2* gn_tab; int gn_ld; int gn_act;
 };
 
 constexpr int kEpiWarps = 8;                      // two warps per TMEM lane quadrant, each owning half of the columns
+constexpr int kXfWarps = 4;                       // transform warps of the fused-GroupNorm kernels
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
+constexpr int kTcThreadsFused = kTcThreads + 32 * kXfWarps;
 // halo tile of ROWS output rows: (ROWS + 2) x 130 pixels x 128 bytes, rounded up to a multiple of 1024
 constexpr int halo_stage_bytes(int rows) { return ((rows + 2) * 130 * 128 + 1023) / 1024 * 1024; }
 
@@ -110,8 +119,9 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
 // ------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------------
-template <int BLOCK_N, bool HALO, int ROWS>
-__global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+template <int BLOCK_N, bool HALO, int ROWS, bool FUSE = false>
+__global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  static_assert(!FUSE || HALO, "the fused-GroupNorm input path exists in halo mode only");
   using Cfg = TcCfg<BLOCK_N, HALO, ROWS>;
   constexpr int kHaloStage = Cfg::kHaloStage;
   extern __shared__ uint8_t smem_raw[];
@@ -126,12 +136,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
   uint64_t* empty_b = full_b + kRingB;
   uint64_t* tfull_bar = empty_b + kRingB;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+  uint64_t* full_raw = tempty_bar + 2;                       // FUSE: TMA landed the raw tile (transform warps wait on it)
+  uint32_t* tmem_slot = (uint32_t*)(full_raw + 2);
   uint8_t* smem_b = smem + Cfg::kAStages * kHaloStage;      // halo mode only
 
   // warp roles: 0..7 epilogue, 8 TMA producer, 9 MMA issuer.  The issue arbiter favours the HIGHEST warp id on an SMSP, so
   // the two latency-critical single-thread roles get the top ids and are never starved by the epilogue warps.
+  // fused kernels: warps 10..13 are the transform warps.  They get the TOP ids: while they work the producer / MMA threads
+  // mostly spin on barriers, and a spinning higher-priority warp on the same scheduler starved them (4x slower transform).
   constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+  constexpr int kXfWarp0 = kEpiWarps + 2;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.g1 * p.g2 * p.g3 * p.nbatch * p.n_tiles;
@@ -143,9 +157,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
   if (warp == kProducerWarp && lane == 0) {
     for (int i = 0; i < kNumAMaps; ++i) prefetch_tmap(&p.amap[i]);
     for (int i = 0; i < kNumBMaps; ++i) prefetch_tmap(&p.bmap[i]);
-    for (int s = 0; s < kRingA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < kRingA; ++s) { mbar_init(&full_a[s], FUSE ? 32 * kXfWarps : 1); mbar_init(&empty_a[s], 1); }
     for (int s = 0; s < kRingB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); mbar_init(&full_raw[a], 1); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -190,10 +204,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
           // taps e[0 .. n_taps): one halo tile per 64-channel chunk, then one weight tile per tap
           const int nch = p.e[0].nchunks;
           for (int c = 0; c < nch; ++c) {
-            mbar_wait(&empty_a[sa], pa ^ 1);
-            mbar_expect_tx(&full_a[sa], (uint32_t)p.halo_bytes);
-            tma_load_4d(smem + sa * kHaloStage, &p.amap[p.e[0].amap], &full_a[sa], c * kBlockK, c1 - 1, c2 - 1, c3);
-            if (++sa == kRingA) { sa = 0; pa ^= 1; }
+            {
+              uint64_t* fb = FUSE ? &full_raw[sa] : &full_a[sa];
+              mbar_wait(&empty_a[sa], pa ^ 1);
+              mbar_expect_tx(fb, (uint32_t)p.halo_bytes);
+              tma_load_4d(smem + sa * kHaloStage, &p.amap[p.e[0].amap], fb, c * kBlockK, c1 - 1, c2 - 1, c3);
+              if (++sa == kRingA) { sa = 0; pa ^= 1; }
+            }
             for (int ei = 0; ei < p.n_taps; ++ei) {
               const TcEntry e = p.e[ei];
               mbar_wait(&empty_b[sb], pb ^ 1);
@@ -206,10 +223,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
           for (int ei = p.n_taps; ei < p.n_entries; ++ei) {
             const TcEntry e = p.e[ei];
             for (int c = 0; c < e.nchunks; ++c) {
-              mbar_wait(&empty_a[sa], pa ^ 1);
-              mbar_expect_tx(&full_a[sa], (uint32_t)p.a_bytes);
-              tma_load_4d(smem + sa * kHaloStage, &p.amap[e.amap], &full_a[sa], e.a_c0 + c * kBlockK, c1 + e.d1, c2 + e.d2, c3);
-              if (++sa == kRingA) { sa = 0; pa ^= 1; }
+              {
+                uint64_t* fb = FUSE ? &full_raw[sa] : &full_a[sa];
+                mbar_wait(&empty_a[sa], pa ^ 1);
+                mbar_expect_tx(fb, (uint32_t)p.a_bytes);
+                tma_load_4d(smem + sa * kHaloStage, &p.amap[e.amap], fb, e.a_c0 + c * kBlockK, c1 + e.d1, c2 + e.d2, c3);
+                if (++sa == kRingA) { sa = 0; pa ^= 1; }
+              }
               mbar_wait(&empty_b[sb], pb ^ 1);
               mbar_expect_tx(&full_b[sb], (uint32_t)Cfg::kBBytes);
               tma_load_3d(smem_b + sb * Cfg::kBBytes, &p.bmap[e.bmap], &full_b[sb], e.b_k0 + c * kBlockK, t.nt * BLOCK_N, e.b_z);
@@ -308,6 +328,82 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             }
           }
           umma_commit(&tfull_bar[acc]);
+        }
+      }
+    }
+  } else if (FUSE && warp >= kXfWarp0 && warp < kXfWarp0 + kXfWarps) {
+    // ===================== transform warps (fused GroupNorm + activation of the input) =====================
+    // The raw halo tile has been landed by TMA (zero-filled outside the image); each thread rewrites IN PLACE the 16-byte
+    // vectors of one logical channel column: a = act(x * scale + shift), leaving out-of-image pixels at zero (the padding
+    // applies to the normalised tensor), then releases the stage to the MMA issuer.  (Fetching the tile with ordinary
+    // loads instead was 4x slower: with 227 KB of shared memory carved out, L1 has almost no lines left for misses in flight.)
+    if constexpr (FUSE) {
+      const int xt = threadIdx.x - 32 * kXfWarp0;           // 0..127
+      const int j = xt & 7;                                 // logical 16-byte column (8 channels) owned by this thread
+      const int r0 = xt >> 3;                               // first tile row; rows advance by 16
+      const int pitch = p.t1 + 2;
+      const int halo_rows = (ROWS + 2) * pitch;
+      int sa = 0; uint32_t pa = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const TileCoord t = decode_tile(p, tile);
+        const int c1 = t.i1 * p.t1, c2 = t.i2 * ROWS, c3 = t.i3;
+        const int nch = p.e[0].nchunks;
+        // valid halo rows / columns of this tile (everything else is padding and stays zero)
+        const int hy_lo = c2 - 1 < 0 ? 1 - c2 : 0, hy_hi = min(ROWS + 2, p.xg_H - (c2 - 1));
+        const int hx_lo = c1 - 1 < 0 ? 1 - c1 : 0, hx_hi = min(pitch, p.xg_W - (c1 - 1));
+        for (int c = 0; c < nch; ++c) {
+          float sc[8], sh[8];
+          {
+            const float4* tp = (const float4*)(p.gn_tab + (long long)c3 * p.gn_ld + c * kBlockK + j * 8);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { float4 v = __ldg(tp + q); sc[2 * q] = v.x; sh[2 * q] = v.y; sc[2 * q + 1] = v.z; sh[2 * q + 1] = v.w; }
+          }
+          mbar_wait(&full_raw[sa], pa);
+          uint8_t* st = smem + sa * kHaloStage;
+          int hy = r0 / pitch, hx = r0 - hy * pitch;
+          constexpr int U = 8;                              // shared-memory loads in flight per thread (their latency is
+                                                            // hundreds of cycles while the tensor core streams operands)
+          for (int rb = r0; rb < halo_rows; rb += 16 * U) {
+            uint4 raw[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int r = rb + 16 * u;
+              ok[u] = r < halo_rows && hy >= hy_lo && hy < hy_hi && hx >= hx_lo && hx < hx_hi;
+              if (ok[u]) raw[u] = *(const uint4*)(st + r * 128 + ((j ^ (r & 7)) << 4));
+              hx += 16;
+              if (hx >= pitch) { hx -= pitch; ++hy; }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (ok[u]) {
+                const int r = rb + 16 * u;
+                const __nv_bfloat162* h = (const __nv_bfloat162*)&raw[u];
+                uint4 o;
+                __nv_bfloat162* oh = (__nv_bfloat162*)&o;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  float2 f = __bfloat1622float2(h[k]);
+                  float a0 = fmaf(f.x, sc[2 * k], sh[2 * k]), a1 = fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1]);
+                  if (p.gn_act == WSR_ACT_SWISH) { a0 = swish_fast(a0); a1 = swish_fast(a1); }
+                  oh[k] = __floats2bfloat162_rn(a0, a1);
+                }
+                *(uint4*)(st + r * 128 + ((j ^ (r & 7)) << 4)) = o;
+              }
+            }
+          }
+          fence_proxy_async();
+          mbar_arrive(&full_a[sa]);
+          if (++sa == kRingA) { sa = 0; pa ^= 1; }
+        }
+        // fused 1x1 segment (ResnetBlock res_conv): the raw x2 tile passes through untouched
+        for (int ei = p.n_taps; ei < p.n_entries; ++ei) {
+          const int n2 = p.e[ei].nchunks;
+          for (int c = 0; c < n2; ++c) {
+            mbar_wait(&full_raw[sa], pa);
+            mbar_arrive(&full_a[sa]);
+            if (++sa == kRingA) { sa = 0; pa ^= 1; }
+          }
         }
       }
     }
@@ -539,23 +635,32 @@ int sm_count() {
   return n;
 }
 
-template <int BLOCK_N, bool HALO, int ROWS>
+template <int BLOCK_N, bool HALO, int ROWS, bool FUSE = false>
 static int launch_tc_impl(const TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N, HALO, ROWS>;
   static bool attr_set = false;
   if (!attr_set) {
-    WSR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, HALO, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    WSR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   int total = p.g1 * p.g2 * p.g3 * p.nbatch * p.n_tiles;
   int grid = total < sm_count() ? total : sm_count();
-  gemm_tc_kernel<BLOCK_N, HALO, ROWS><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(p);
+  gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE><<<grid, FUSE ? kTcThreadsFused : kTcThreads, Cfg::kSmemBytes, st>>>(p);
   WSR_LAUNCH_OK();
   return WSR_OK;
 }
 
 template <int BLOCK_N>
 static int launch_tc(const TcParams& p, cudaStream_t st) {
+  if (p.n_taps > 0 && p.gn_tab != nullptr) {
+    if constexpr (BLOCK_N <= 64) {
+      if (p.halo_rows == 4) return launch_tc_impl<BLOCK_N, true, 4, true>(p, st);
+    }
+    if constexpr (BLOCK_N <= 128) {
+      if (p.halo_rows == 2) return launch_tc_impl<BLOCK_N, true, 2, true>(p, st);
+    }
+    return launch_tc_impl<BLOCK_N, true, 1, true>(p, st);
+  }
   if (p.n_taps > 0) {
     if constexpr (BLOCK_N <= 64) {
       if (p.halo_rows == 4) return launch_tc_impl<BLOCK_N, true, 4>(p, st);
@@ -649,6 +754,15 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
   static const int max_rows = getenv("WSR_HALO_ROWS") ? atoi(getenv("WSR_HALO_ROWS")) : 4;
   const bool halo = !no_halo && d->ksize == 3 && d->stride == 1 && p.t2 == 1 && p.t3 == 1 && p.t1 + 2 <= 130;
   const int hrows = (halo && bn <= 64 && GH % 4 == 0 && max_rows >= 4) ? 4 : (halo && bn <= 128 && GH % 2 == 0 && max_rows >= 2) ? 2 : 1;
+  WSR_REQUIRE(d->gn_table == nullptr || halo, WSR_E_UNSUPPORTED,
+              "conv_tc: the fused GroupNorm input needs a stride-1 3x3 convolution on rows of >= 128 pixels (see wsr_conv_tc_can_fuse_gn)");
+  if (d->gn_table) {
+    WSR_REQUIRE(d->gn_table_ld >= d->Cin && d->gn_table_ld % 2 == 0 && (((uintptr_t)d->gn_table) & 15) == 0, WSR_E_INVALID, "conv_tc: gn_table pitch / alignment");
+    WSR_REQUIRE(d->gn_act == WSR_ACT_NONE || d->gn_act == WSR_ACT_SWISH, WSR_E_UNSUPPORTED, "conv_tc: gn_act must be NONE or SWISH");
+    p.gn_tab = (const float2*)d->gn_table; p.gn_ld = d->gn_table_ld; p.gn_act = d->gn_act;
+    p.xg = d->x; p.xg_ld = d->x_ld; p.xg_H = d->H; p.xg_W = d->W;
+    p.x2g = d->x2; p.x2g_ld = d->x2_ld;
+  }
   p.n_taps = halo ? taps : 0;
   p.halo_rows = hrows;
   p.halo_bytes = (p.t1 + 2) * (hrows + 2) * 128;
@@ -757,6 +871,15 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
   if (d->gn_stats && !fuse_stats)
     return wsr_gn_stats(d->y, d->y_dtype, d->N, OH * OW, d->Cout, d->y_ld, d->gn_stats, d->gn_stats_ld, stream);
   return WSR_OK;
+}
+
+// 1 when wsr_conv_tc would run this descriptor in halo mode, i.e. can take a fused GroupNorm input (gn_table)
+extern "C" int wsr_conv_tc_can_fuse_gn(const WsrConvDesc* d) {
+  if (d == nullptr || d->x_dtype != WSR_BF16 || d->ksize != 3 || d->stride != 1 || d->upsample != 0) return 0;
+  if (d->Cin % 64 != 0 || (d->x2 && d->Cin2 % 64 != 0)) return 0;
+  int t1, t2, t3;
+  choose_tile(d->W, d->H, d->N, t1, t2, t3);
+  return (t2 == 1 && t3 == 1 && t1 + 2 <= 130 && getenv("WSR_NO_HALO") == nullptr) ? 1 : 0;
 }
 
 // Tap-table variant (data gradients of the stride-2 / upsample convolutions; see wsr.h).  Classic (non-halo) tiles only.

@@ -201,9 +201,10 @@ class Engine:
 
     def conv(self, x, pc, y, stride=1, upsample=False, bias=True, rowvec=None, rowvec_ld=0, act=nat.ACT_NONE,
              out_scale=1.0, res=None, res_scale=1.0, res2=None, res2_scale=1.0, x2=None, w2=None, extra_bias=None,
-             force_simt=False, taps=None):
+             force_simt=False, taps=None, gn=None):
         """y = act(conv(x) [+ conv1x1(x2, w2)] + bias + rowvec) * out_scale + res*res_scale + res2*res2_scale.
-        taps: a ``nat.TapTable`` -- run the tap-table variant (``pc.k`` / stride / upsample are then ignored)."""
+        taps: a ``nat.TapTable`` -- run the tap-table variant (``pc.k`` / stride / upsample are then ignored).
+        gn = (table, act): x is the RAW tensor; GroupNorm (+act) is applied inside the tcgen05 kernel (``conv_can_fuse_gn``)."""
         if taps is not None:
             assert stride == 1 and not upsample and x2 is None
         d = nat.ConvDesc()
@@ -228,6 +229,9 @@ class Engine:
         d.y, d.y_dtype, d.y_ld = y.ptr, y.dt, y.ld
         if y.st is not None:
             d.gn_stats, d.gn_stats_ld = y.stats_ptr, y.st_ld       # GroupNorm statistics of y come out of the epilogue
+        if gn is not None:
+            assert taps is None and not force_simt
+            d.gn_table, d.gn_table_ld, d.gn_act = gn[0].data_ptr(), gn[0].shape[1], gn[1]
         up = 2 if upsample else 1
         opix = x.N * (x.H * up // stride) * (x.W * up // stride)
         flops = 2 * opix * pc.Cout * (pc.k * pc.k * pc.Cin + (x2.C if x2 is not None else 0))
@@ -261,6 +265,24 @@ class Engine:
             self.n_simt += 1
             self.call("wsr_conv_simt", C.byref(d), self.stream, flops=flops, nbytes=nbytes, tag="conv_simt")
         return y
+
+    def conv_can_fuse_gn(self, x, pc, stride=1, upsample=False, x2=None):
+        """True when ``conv(x, pc, ..., gn=...)`` is available for this layer (tcgen05 halo mode)."""
+        if not self.use_tc or upsample or stride != 1 or not self._tc_conv_ok(x, pc, x2, None):
+            return False
+        d = nat.ConvDesc()
+        d.x, d.x_dtype, d.N, d.H, d.W, d.Cin, d.x_ld = x.ptr, x.dt, x.N, x.H, x.W, pc.Cin_pad, x.ld
+        d.ksize, d.stride, d.upsample = pc.k, 1, 0
+        if x2 is not None:
+            d.x2, d.Cin2 = x2.ptr, x2.C
+        return bool(nat.call("wsr_conv_tc_can_fuse_gn", C.byref(d)))
+
+    def gn_finalize(self, x, gamma, beta, groups, table, eps=1e-5):
+        """table (N, C, 2) fp32 <- (scale, shift) of GroupNorm(x) from x's statistics slot."""
+        assert x.stats_ptr and table.shape[0] == x.N and table.shape[1] >= x.C
+        self.call("wsr_gn_finalize", x.stats_ptr, x.st_ld, x.N, x.H * x.W, x.C, groups, eps, gamma.data_ptr(), beta.data_ptr(),
+                  table.data_ptr(), table.shape[1], self.stream, tag="wsr_gn_finalize")
+        return table
 
     def gemm(self, a_ptr, a_dt, a_s, b_ptr, b_dt, b_s, d_ptr, d_dt, d_s, batch, M, N, K, alpha=1.0, bias=None,
              force_simt=False, res=None):

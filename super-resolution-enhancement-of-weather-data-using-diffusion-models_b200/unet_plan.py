@@ -42,6 +42,13 @@ class UNetPlan:
         self.groups = net.norm_groups
         self.time_act = nat.ACT_MISH if net.time_act == "mish" else nat.ACT_SWISH
         self._wver = None
+        # GroupNorm + Swish fused into the consuming convolution's operand path (transform warps rewrite the TMA-landed
+        # tile in shared memory; wsr_conv_tc with WsrConvDesc.gn_table).  Correct and tested, but MEASURED SLOWER on B200
+        # than the separate HBM-bound pass: e.g. 64->64 @128x256, B=64: conv 0.27 ms + gn_apply 0.10 ms unfused vs 0.51 ms
+        # fused (four transform warps cannot keep up with the tensor pipe, and their shared-memory traffic competes with
+        # the operand fetch that already bounds these N=64 layers) -- so it is OFF by default (env WSR_FUSE_GN=1 turns it on).
+        import os
+        self.fuse_gn = (getattr(self, "fuse_gn", True) and self.eng.mode == "bf16" and os.environ.get("WSR_FUSE_GN", "0") == "1")
         self._structure()
         self._buffers()
         self.refresh_weights()
@@ -380,15 +387,29 @@ class UNetPlan:
     def _res_block(self, r, x, extra_res=None):
         e, B, G = self.eng, self.B, self.groups
         SW = nat.ACT_SWISH
-        e.gn_apply(x, r.g1, r.b1, G, SW, r.a1)
-        e.conv(r.a1, r.conv1, r.hbuf, rowvec=self._rowvec(r), rowvec_ld=self.P)
-        self._block2_norm(r)
+        if not hasattr(r, "fuse1"):
+            r.fuse1 = self.fuse_gn and e.conv_can_fuse_gn(x, r.conv1)
+            r.fuse2 = self.fuse_gn and e.conv_can_fuse_gn(r.hbuf, r.conv2, x2=x if r.has_res_conv else None)
+            r.tab1 = e.empty((B, r.cin, 2), torch.float32) if r.fuse1 else None
+            r.tab2 = e.empty((B, r.cout, 2), torch.float32) if r.fuse2 else None
+        if r.fuse1:
+            e.gn_finalize(x, r.g1, r.b1, G, r.tab1)
+            e.conv(x, r.conv1, r.hbuf, rowvec=self._rowvec(r), rowvec_ld=self.P, gn=(r.tab1, SW))
+        else:
+            e.gn_apply(x, r.g1, r.b1, G, SW, r.a1)
+            e.conv(r.a1, r.conv1, r.hbuf, rowvec=self._rowvec(r), rowvec_ld=self.P)
         dst = r.rbuf if r.attn else r.y
         er = None if r.attn else extra_res
-        if r.has_res_conv:
-            e.conv(r.a2, r.conv2, dst, x2=x, w2=r.resw, extra_bias=r.bias2, res2=er)
+        if r.fuse2:
+            e.gn_finalize(r.hbuf, r.g2, r.b2, G, r.tab2)
+            a2, gn2 = r.hbuf, (r.tab2, SW)
         else:
-            e.conv(r.a2, r.conv2, dst, res=x, res2=er)
+            self._block2_norm(r)
+            a2, gn2 = r.a2, None
+        if r.has_res_conv:
+            e.conv(a2, r.conv2, dst, x2=x, w2=r.resw, extra_bias=r.bias2, res2=er, gn=gn2)
+        else:
+            e.conv(a2, r.conv2, dst, res=x, res2=er, gn=gn2)
         if r.attn:
             e.gn_apply(r.rbuf, r.g3, r.b3, G, nat.ACT_NONE, r.nbuf)
             e.conv(r.nbuf, r.wqk, r.qk, bias=False)
@@ -449,9 +470,21 @@ class UNetPlan:
                 x = self._res_block(r, r.cat)
             else:
                 x = e.conv(x, r.conv, r.y, upsample=True)
-        e.gn_apply(x, self.gf, self.bf_, self.groups, nat.ACT_SWISH, self.final_a)
-        e.conv(self.final_a, self.final, self.eps_nhwc)
+        self._head(x)
         if self.C_img != 1:
             e.call("wsr_nhwc_to_nchw", self.eps_nhwc.ptr, nat.F32, self.eps_nhwc.ld, B, self.C_img, self.H, self.W,
                      self.eps.data_ptr(), st)
         return self.eps
+
+    def _head(self, x):
+        """final_conv = GroupNorm -> Swish -> conv3x3 (resdiff/unet.py:119, nn_modules/resnet.py:19-28)."""
+        e = self.eng
+        if not hasattr(self, "fuse_final"):
+            self.fuse_final = self.fuse_gn and e.conv_can_fuse_gn(x, self.final)
+            self.tab_final = e.empty((self.B, self.final_cin, 2), torch.float32) if self.fuse_final else None
+        if self.fuse_final:
+            e.gn_finalize(x, self.gf, self.bf_, self.groups, self.tab_final)
+            e.conv(x, self.final, self.eps_nhwc, gn=(self.tab_final, nat.ACT_SWISH))
+        else:
+            e.gn_apply(x, self.gf, self.bf_, self.groups, nat.ACT_SWISH, self.final_a)
+            e.conv(self.final_a, self.final, self.eps_nhwc)

@@ -35,6 +35,7 @@ class UNetTrainPlan(UNetPlan):
         self.drop_seed = 0
         self.on_ready = None           # callback(lo, hi): gflat[lo:hi] is final (launch its all-reduce now)
         self._dw = None
+        self.fuse_gn = False           # the backward pass reads the normalised activations (a1, a2): keep them materialised
         super().__init__(net, batch, device, precision, strict_tc)
         self.eng.no_fused_attention = False
         self._grad_layout()
@@ -489,8 +490,7 @@ class UNetTrainPlan(UNetPlan):
                 self._up_inputs[k] = x
                 x = e.conv(x, r.conv, r.y, upsample=True)
         self._x_last = x
-        e.gn_apply(x, self.gf, self.bf_, self.groups, nat.ACT_SWISH, self.final_a)
-        e.conv(self.final_a, self.final, self.eps_nhwc)
+        self._head(x)
         if self.C_img != 1:
             e.call("wsr_nhwc_to_nchw", self.eps_nhwc.ptr, nat.F32, self.eps_nhwc.ld, B, self.C_img, self.H, self.W,
                    self.eps.data_ptr(), st)

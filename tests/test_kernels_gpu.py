@@ -363,3 +363,52 @@ def test_upsample_conv_merged_taps(case):
     assert eng.n_tc == 1 and eng.n_simt == 1
     assert rel_l2(y_si.to_nchw(eng), ref) < 5e-3          # weights pre-summed in fp32, then rounded to bf16
     assert rel_l2(y_tc.to_nchw(eng), y_si.to_nchw(eng)) < 4e-3
+
+
+FUSE_GN_CASES = [
+    # N, Cin, Cout, H, W, Cin2 (fused 1x1 segment; 0 = none)
+    (2, 64, 64, 8, 256, 0),          # N = 64 tile, four output rows per tile
+    (1, 192, 64, 6, 128, 192),       # two rows per tile fallback (6 % 4 != 0), res_conv segment
+    (2, 128, 128, 4, 128, 0),        # N = 128 tile, two rows per tile
+    (1, 384, 128, 4, 128, 384),
+    (1, 128, 256, 3, 256, 0),        # N = 256 tile, one row per tile, odd row count
+    (2, 64, 1, 4, 256, 0),           # final conv: one output channel
+]
+
+
+@pytest.mark.parametrize("case", FUSE_GN_CASES)
+def test_conv_tc_fused_groupnorm_input(case):
+    """GroupNorm + Swish applied inside the tcgen05 convolution (transform warps write the operand tile) against the
+    two-kernel path (wsr_gn_apply, then wsr_conv_tc) on the same raw tensor: both round the activation to bf16 once, so
+    the results agree to bf16 output rounding."""
+    N, Cin, Cout, H, W, Cin2 = case
+    torch.manual_seed(11)
+    dev = _dev()
+    eng = Engine(dev, "bf16")
+    x = torch.randn(N, Cin, H, W, device=dev) * 1.3 + 0.2
+    w = torch.randn(Cout, Cin, 3, 3, device=dev) / math.sqrt(Cin * 9)
+    b = torch.randn(Cout, device=dev)
+    gamma, beta = 1 + 0.1 * torch.randn(Cin, device=dev), 0.1 * torch.randn(Cin, device=dev)
+    arena = engine_mod.StatsArena()
+    xa = eng.new_act(N, H, W, Cin, stats=arena)
+    arena.finalize(dev)
+    eng.nchw_to_act(x, xa)
+    eng.gn_stats(xa)
+    pc = eng.pack_conv(w, b, rows=64 if Cout < 16 else None)
+    kw = {}
+    if Cin2:
+        x2 = torch.randn(N, Cin2, H, W, device=dev)
+        w2 = torch.randn(Cout, Cin2, 1, 1, device=dev) / math.sqrt(Cin2)
+        kw = dict(x2=_nhwc(x2, eng), w2=eng.pack_conv(w2, None))
+    assert eng.conv_can_fuse_gn(xa, pc, x2=kw.get("x2"))
+    a = eng.new_act(N, H, W, Cin)
+    eng.gn_apply(xa, gamma, beta, 32, nat.ACT_SWISH, a)
+    y_ref = eng.new_act(N, H, W, Cout, dt=nat.F32, zero=True)
+    eng.conv(a, pc, y_ref, **kw)
+    tab = eng.empty((N, Cin, 2), torch.float32)
+    eng.gn_finalize(xa, gamma, beta, 32, tab)
+    y = eng.new_act(N, H, W, Cout, dt=nat.F32, zero=True)
+    eng.conv(xa, pc, y, gn=(tab, nat.ACT_SWISH), **kw)
+    torch.cuda.synchronize()
+    err = rel_l2(y.to_nchw(eng), y_ref.to_nchw(eng))
+    assert err < 2e-3, err
