@@ -81,6 +81,10 @@ typedef struct {
    * gn_table[n*gn_table_ld + c] = (scale, shift) pairs (2 floats) from wsr_gn_finalize; zero padding applies to a.  The
    * optional second segment x2 stays raw.  Replaces the separate GroupNorm+Swish pass of nn_modules/resnet.py:21-22. */
   const float* gn_table; int gn_table_ld; int gn_act;
+  /* optional second packing of a 3x3 weight with Cout <= 64 for the "vertical tap merge" of wsr_conv_tc (rows of >= 128
+   * pixels): [kx][3 * 64 rows][Cin], row block b of slice kx = the 64 (zero-padded) output channels of tap (ky = 2 - b, kx),
+   * dtype = x_dtype (wsr_pack_conv_weight_vmerge).  NULL = not available. */
+  const void* w_vmerge;
 } WsrConvDesc;
 
 /* fp32-accumulate SIMT implicit GEMM; any dtype, any channel count.  This is the "fp32 check mode" kernel. */
@@ -218,6 +222,8 @@ int wsr_nhwc_to_nchw(const void* src, int src_dtype, int src_ld, int N, int C, i
 /* OIHW fp32 -> [tap][Cout_pad][Cin_pad] (zero padded). */
 int wsr_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int KH, int KW, void* dst, int dst_dtype,
                          int Cout_pad, int Cin_pad, void* stream);
+/* OIHW fp32 (Cout <= 64, Cin, 3, 3) -> [kx][3*64][Cin_pad] with row block b = tap (ky = 2 - b, kx), rows >= Cout zero. */
+int wsr_pack_conv_weight_vmerge(const float* w_oihw, int Cout, int Cin, void* dst, int dst_dtype, int Cin_pad, void* stream);
 /* Phase-merged weights of "nearest x2 upsample + conv3x3": OIHW fp32 (Cout,Cin,3,3) -> [phase*4 + a*2 + b][Cout_pad][Cin_pad],
  * phase = py*2+px; (a, b) index the source offsets {-1,0} (py/px = 0) or {0,+1} (py/px = 1). */
 int wsr_pack_upsample_weight(const float* w_oihw, int Cout, int Cin, void* dst, int dst_dtype, int Cout_pad, int Cin_pad,

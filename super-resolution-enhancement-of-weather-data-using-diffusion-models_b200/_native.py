@@ -35,6 +35,7 @@ class ConvDesc(C.Structure):
         ("y", C.c_void_p), ("y_dtype", C.c_int), ("y_ld", C.c_int),
         ("gn_stats", C.c_void_p), ("gn_stats_ld", C.c_int),
         ("gn_table", C.c_void_p), ("gn_table_ld", C.c_int), ("gn_act", C.c_int),
+        ("w_vmerge", C.c_void_p),
     ]
 
 
@@ -97,6 +98,7 @@ SIGNATURES = {
     "wsr_nhwc_to_nchw": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "wsr_pack_conv_weight": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P],
     "wsr_pack_upsample_weight": [_P, _I, _I, _P, _I, _I, _I, _P],
+    "wsr_pack_conv_weight_vmerge": [_P, _I, _I, _P, _I, _I, _P],
     "wsr_pack_convT_weight": [_P, _I, _I, _I, _I, _P, _I, _P],
     "wsr_cast": [_P, _I, _P, _I, _L, _P],
     "wsr_upsample2x": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P],

@@ -39,6 +39,19 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
   st_dt(dst, i, dt, v);
 }
 
+// vertical-tap-merge pack: dst[(kx*192 + b*64 + co)*Cin_pad + ci] = w[co][ci][ky = 2 - b][kx]
+__global__ void pack_conv_weight_vmerge_kernel(const float* __restrict__ w, int Cout, int Cin, void* dst, int dt, int Cin_pad, int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int ci = (int)(i % Cin_pad);
+  int64_t r = i / Cin_pad;
+  int row = (int)(r % 192);
+  int kx = (int)(r / 192);
+  int b = row / 64, co = row % 64;
+  float v = (co < Cout && ci < Cin) ? w[((int64_t)co * Cin + ci) * 9 + (2 - b) * 3 + kx] : 0.f;
+  st_dt(dst, i, dt, v);
+}
+
 // merged taps of upsample+conv: row sets  py=0: a=0 -> {ky 0}, a=1 -> {ky 1,2};  py=1: a=0 -> {ky 0,1}, a=1 -> {ky 2}
 __global__ void pack_upsample_weight_kernel(const float* __restrict__ w, int Cout, int Cin, void* dst, int dt, int Cout_pad,
                                             int Cin_pad, int64_t total) {
@@ -482,6 +495,14 @@ extern "C" int wsr_pack_conv_weight(const float* w, int Cout, int Cin, int KH, i
               WSR_E_INVALID, "pack_conv_weight: bad argument");
   int64_t total = (int64_t)KH * KW * Cout_pad * Cin_pad;
   pack_conv_weight_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, KH * KW, dst, dst_dtype, Cout_pad, Cin_pad, total);
+  WSR_LAUNCH_OK();
+  return WSR_OK;
+}
+
+extern "C" int wsr_pack_conv_weight_vmerge(const float* w, int Cout, int Cin, void* dst, int dst_dtype, int Cin_pad, void* stream) {
+  WSR_REQUIRE(w && dst && valid_dtype(dst_dtype) && Cout > 0 && Cout <= 64 && Cin > 0 && Cin_pad >= Cin, WSR_E_INVALID, "pack_conv_weight_vmerge: bad argument");
+  int64_t total = (int64_t)3 * 192 * Cin_pad;
+  pack_conv_weight_vmerge_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, dst, dst_dtype, Cin_pad, total);
   WSR_LAUNCH_OK();
   return WSR_OK;
 }

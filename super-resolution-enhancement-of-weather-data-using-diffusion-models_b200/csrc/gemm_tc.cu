@@ -28,7 +28,7 @@ constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes =
 constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
 constexpr int kMaxEntries = 18;              // 16 taps (WSR_MAX_TAPS) + fused 1x1 segment + spare
 constexpr int kNumAMaps = 5;
-constexpr int kNumBMaps = 2;
+constexpr int kNumBMaps = 3;                     // [0] conv weights, [1] fused 1x1 segment, [2] vertically merged taps
 
 struct TcEntry {
   int16_t amap, bmap;      // tensor-map indices
@@ -86,19 +86,28 @@ constexpr int kTcThreadsFused = kTcThreads + 32 * kXfWarps;
 // halo tile of ROWS output rows: (ROWS + 2) x 130 pixels x 128 bytes, rounded up to a multiple of 1024
 constexpr int halo_stage_bytes(int rows) { return ((rows + 2) * 130 * 128 + 1023) / 1024 * 1024; }
 
-template <int BLOCK_N, bool HALO, int ROWS> struct TcCfg {
+constexpr int next_pow2(int v) { int p = 32; while (p < v) p *= 2; return p; }
+
+// VM ("vertical tap merge", halo mode, N = 64): a halo row feeds the three output rows above / at / below it through
+// the taps dy = +1, 0, -1.  With the accumulators of consecutive output rows laid out side by side in TMEM, ONE MMA per
+// (halo row, dx) with the weight matrices [dy=+1 | dy=0 | dy=-1] stacked along N (192 columns) updates all three: the
+// 128-pixel activation operand -- whose shared-memory fetch bounds the N = 64 layers -- is read 5 times per 3 output
+// rows instead of 9 times.
+template <int BLOCK_N, bool HALO, int ROWS, bool VM = false> struct TcCfg {
   static constexpr int kHaloStage = halo_stage_bytes(ROWS);
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kBTile = BLOCK_N * kBlockK * 2;                 // one weight tile
+  static constexpr int kBBytes = VM ? 3 * kBTile : kBTile;             // one stage of the weight ring
   // classic mode: one ring of {A tile, B tile} stages.  halo mode: a ring of activation halo tiles (one per 64-channel
   // chunk, shared by the 9 taps) and a separate ring of weight tiles.
   static constexpr int kStages = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
   static constexpr int kAStages = 2;
-  static constexpr int kBStages = BLOCK_N >= 256 ? 3 : (BLOCK_N >= 128 ? (ROWS > 1 ? 4 : 6) : (ROWS >= 4 ? 3 : 8));
+  static constexpr int kBStages = VM ? 2 : (BLOCK_N >= 256 ? 3 : (BLOCK_N >= 128 ? (ROWS > 1 ? 4 : 6) : (ROWS >= 4 ? 3 : 8)));
   static constexpr int kSmemData = HALO ? kAStages * kHaloStage + kBStages * kBBytes : kStages * (kABytes + kBBytes);
   static constexpr int kAccCols = ROWS * BLOCK_N;                           // one accumulator set (ROWS output rows)
-  static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;   // power of two for 32..512
+  static constexpr int kTmemCols = next_pow2(2 * kAccCols);                // power of two for 32..512
   static_assert(kTmemCols <= 512, "TMEM budget");
-  static constexpr int kSmemBytes = kSmemData + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int kBsumBytes = HALO ? 16 * BLOCK_N : 0;                // per epilogue warp: bias + time-embedding row of its columns
+  static constexpr int kSmemBytes = kSmemData + 1024 /*align slack*/ + 512 /*barriers*/ + kBsumBytes;
   // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
   static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 };
@@ -119,10 +128,12 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
 // ------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------------
-template <int BLOCK_N, bool HALO, int ROWS, bool FUSE = false>
+template <int BLOCK_N, bool HALO, int ROWS, bool FUSE = false, bool VM = false>
 __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  // register budget: 10 warps = 3 warps on the fullest scheduler, 16384 / 3 / 32 -> 168 registers per thread at most
   static_assert(!FUSE || HALO, "the fused-GroupNorm input path exists in halo mode only");
-  using Cfg = TcCfg<BLOCK_N, HALO, ROWS>;
+  static_assert(!VM || (HALO && BLOCK_N == 64), "vertical tap merge: halo mode, N = 64");
+  using Cfg = TcCfg<BLOCK_N, HALO, ROWS, VM>;
   constexpr int kHaloStage = Cfg::kHaloStage;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -211,12 +222,22 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
               tma_load_4d(smem + sa * kHaloStage, &p.amap[p.e[0].amap], fb, c * kBlockK, c1 - 1, c2 - 1, c3);
               if (++sa == kRingA) { sa = 0; pa ^= 1; }
             }
+            if constexpr (VM) {
+              // one [3 x 64 rows] box per horizontal offset dx: rows = weights of dy = +1, 0, -1 (wsr vmerge pack)
+              for (int dxi = 0; dxi < 3; ++dxi) {
+                mbar_wait(&empty_b[sb], pb ^ 1);
+                mbar_expect_tx(&full_b[sb], (uint32_t)Cfg::kBBytes);
+                tma_load_3d(smem_b + sb * Cfg::kBBytes, &p.bmap[2], &full_b[sb], c * kBlockK, 0, dxi);
+                if (++sb == kRingB) { sb = 0; pb ^= 1; }
+              }
+            } else {
             for (int ei = 0; ei < p.n_taps; ++ei) {
               const TcEntry e = p.e[ei];
               mbar_wait(&empty_b[sb], pb ^ 1);
               mbar_expect_tx(&full_b[sb], (uint32_t)Cfg::kBBytes);
               tma_load_3d(smem_b + sb * Cfg::kBBytes, &p.bmap[e.bmap], &full_b[sb], e.b_k0 + c * kBlockK, t.nt * BLOCK_N, e.b_z);
               if (++sb == kRingB) { sb = 0; pb ^= 1; }
+            }
             }
           }
           // remaining entries (fused 1x1 segment): plain 128-row activation tiles in the same A ring
@@ -231,7 +252,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
                 if (++sa == kRingA) { sa = 0; pa ^= 1; }
               }
               mbar_wait(&empty_b[sb], pb ^ 1);
-              mbar_expect_tx(&full_b[sb], (uint32_t)Cfg::kBBytes);
+              mbar_expect_tx(&full_b[sb], (uint32_t)Cfg::kBTile);
               tma_load_3d(smem_b + sb * Cfg::kBBytes, &p.bmap[e.bmap], &full_b[sb], e.b_k0 + c * kBlockK, t.nt * BLOCK_N, e.b_z);
               if (++sb == kRingB) { sb = 0; pb ^= 1; }
             }
@@ -280,6 +301,41 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
             mbar_wait(&full_a[sa], pa);
             const uint32_t a_lo0 = desc_lo(smem_u32(smem + sa * kHaloStage));
             const uint32_t pitch8 = (uint32_t)pitch * 8u;
+            if constexpr (VM) {
+              constexpr uint32_t kIdBase = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBlockM >> 4) << 24);
+              for (int dxi = 0; dxi < 3; ++dxi, ++kb) {
+                mbar_wait(&full_b[sb], pb);
+                tc_fence_after();
+                const uint32_t v_lo = a_lo0 + (uint32_t)dxi * 8u;                 // halo column offset dx + 1 = dxi
+                const uint32_t b_lo = desc_lo(smem_u32(smem_b + sb * Cfg::kBBytes));
+                if (!(p.dbg & 2)) {
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k) {
+                    if (kb == 0 && k == 0) {
+                      // very first K step of the tile: every accumulator block starts from zero, which a merged MMA cannot
+                      // express (one accumulate flag per instruction) -> nine plain N = 64 MMAs, first touch overwrites
+#pragma unroll
+                      for (int rr = 0; rr < ROWS; ++rr)
+#pragma unroll
+                        for (int dyi = 0; dyi < 3; ++dyi)      // dy = dyi - 1 reads halo row rr + dyi; weights block 2 - dyi
+                          umma_bf16_lo(d_tmem + (uint32_t)(rr * 64), v_lo + (uint32_t)(rr + dyi) * pitch8, b_lo + (uint32_t)(2 - dyi) * 512u,
+                                       kIdBase | (8u << 17), dyi != 0 ? 1u : 0u);
+                    } else {
+#pragma unroll
+                      for (int hr = 0; hr < ROWS + 2; ++hr) {
+                        // halo row hr feeds output rows hr-2 (dy=+1, block 0), hr-1 (dy=0, block 1), hr (dy=-1, block 2)
+                        const int r_lo = hr - 2 < 0 ? 0 : hr - 2, r_hi = hr < ROWS - 1 ? hr : ROWS - 1;
+                        const int nblk = r_hi - r_lo + 1, blk0 = r_lo - (hr - 2);
+                        umma_bf16_lo(d_tmem + (uint32_t)(r_lo * 64), v_lo + (uint32_t)hr * pitch8 + (uint32_t)(2 * k),
+                                     b_lo + (uint32_t)blk0 * 512u + (uint32_t)(2 * k), kIdBase | ((uint32_t)(nblk * 8) << 17), 1u);
+                      }
+                    }
+                  }
+                }
+                umma_commit(&empty_b[sb]);
+                if (++sb == kRingB) { sb = 0; pb ^= 1; }
+              }
+            } else {
             for (int ei = 0; ei < p.n_taps; ++ei, ++kb) {
               const TcEntry e = p.e[ei];
               mbar_wait(&full_b[sb], pb);
@@ -301,6 +357,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
               }
               umma_commit(&empty_b[sb]);
               if (++sb == kRingB) { sb = 0; pb ^= 1; }
+            }
             }
             umma_commit(&empty_a[sa]);
             if (++sa == kRingA) { sa = 0; pa ^= 1; }
@@ -419,8 +476,38 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
     float st_s[kChunksPerWarp], st_q[kChunksPerWarp];
 #pragma unroll
     for (int i = 0; i < kChunksPerWarp; ++i) { st_s[i] = 0.f; st_q[i] = 0.f; }
+    // kRegStats (the warp owns ONE 32-column chunk, i.e. N = 64): only the FIRST exchange round of the transpose-reduce
+    // runs per output row; its 16 partial sums per statistic are accumulated in registers and the remaining four rounds
+    // run once per image.  (The full per-row reduce was ~half of all issue slots of the N = 64 kernels and left their
+    // epilogue exposed; keeping all 32 columns per thread instead would need 64 more registers than the 168 available.)
+    // (measured on B200: the register-accumulated variant is SLOWER than the per-row reduce -- 0.24 vs 0.21 ms epilogue-only on the
+    // 64->64 layer -- because 32 more live registers push the 168-register epilogue into local-memory spills; kept for reference)
+    constexpr bool kRegStats = false && kChunksPerWarp == 1;
+    float rs_s[kRegStats ? 16 : 1], rs_q[kRegStats ? 16 : 1];
+#pragma unroll
+    for (int j = 0; j < (kRegStats ? 16 : 1); ++j) { rs_s[j] = 0.f; rs_q[j] = 0.f; }
     int st_img = -1, st_nt = -1;
     auto flush_stats = [&]() {
+      if constexpr (kRegStats) {
+        if (st_img >= 0) {
+#pragma unroll
+          for (int off = 8; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float send_s = upper ? rs_s[i] : rs_s[i + off];
+              const float keep_s = upper ? rs_s[i + off] : rs_s[i];
+              const float send_q = upper ? rs_q[i] : rs_q[i + off];
+              const float keep_q = upper ? rs_q[i + off] : rs_q[i];
+              rs_s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+              rs_q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+            }
+          }
+          st_s[0] = rs_s[0]; st_q[0] = rs_q[0];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { rs_s[j] = 0.f; rs_q[j] = 0.f; }
+        }
+      }
       if (st_img >= 0 && st_img < p.M3) {
 #pragma unroll
         for (int i = 0; i < kChunksPerWarp; ++i) {
@@ -434,12 +521,29 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
         }
       }
     };
+    // halo mode (one image per tile): bias[c] + rowvec[image][c] of this warp's columns are staged once per tile in a
+    // private slice of shared memory and re-read as broadcast vectors for every output row (with 227 KB of shared memory
+    // carved out there is almost no L1 left, so the per-row __ldg's of the classic path were L2 round trips)
+    float* bs = (float*)(smem + Cfg::kSmemData + 512) + warp * (32 * kChunksPerWarp);
     int it = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const TileCoord t = decode_tile(p, tile);
       const int nt = t.nt, i1 = t.i1, i2 = t.i2, i3 = t.i3, zb = t.zb;
+      float bs_reg[HALO ? kChunksPerWarp : 1];
+      if constexpr (HALO) {
+#pragma unroll
+        for (int ci = 0; ci < kChunksPerWarp; ++ci) {
+          const int col = nt * BLOCK_N + (ch_begin + ci) * 32 + lane;
+          float vb = 0.f;
+          if (col < p.Ncols) {
+            if (p.bias) vb += __ldg(p.bias + col);
+            if (p.rowvec) vb += __ldg(p.rowvec + (long long)i3 * p.rowvec_ld + col);
+          }
+          bs_reg[ci] = vb;
+        }
+      }
       if (p.stats != nullptr) {
         const int img_w = i3 * p.t3 + (HALO ? 0 : (quad * 32) / (p.t1 * p.t2));     // warp-uniform
         if (img_w != st_img || nt != st_nt) { flush_stats(); st_img = img_w; st_nt = nt; }
@@ -447,6 +551,12 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if constexpr (HALO) {
+        __syncwarp();
+#pragma unroll
+        for (int ci = 0; ci < kChunksPerWarp; ++ci) bs[ci * 32 + lane] = bs_reg[ci];
+        __syncwarp();
+      }
 #pragma unroll 1
       for (int rr = 0; rr < ROWS; ++rr) {
       // row -> coordinates
@@ -473,7 +583,11 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
           const bool full = (n0 + 32 <= p.Ncols);
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (full) {
+          if constexpr (HALO) {
+            const float4* b4 = (const float4*)(bs + ci * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { float4 t4 = b4[q]; f[4 * q] += t4.x; f[4 * q + 1] += t4.y; f[4 * q + 2] += t4.z; f[4 * q + 3] += t4.w; }
+          } else if (full) {
             // 32 consecutive columns: bias / time-embedding row as independent 16-byte loads (same address in every
             // lane -> one broadcast transaction each), issued back to back
             if (p.bias) {
@@ -546,6 +660,21 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
           }
         }
         __syncwarp();
+        if constexpr (kRegStats) {
+          if (p.stats != nullptr && n0 < p.Ncols) {
+            // first round (offset 16): lanes with bit 4 clear keep columns 0..15, the others 16..31
+            const bool upper = (lane & 16) != 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float lo = f[i], hi = f[i + 16];
+              const float send_s = upper ? lo : hi, keep_s = upper ? hi : lo;
+              const float got_s = __shfl_xor_sync(0xffffffffu, send_s, 16);
+              const float got_q = __shfl_xor_sync(0xffffffffu, send_s * send_s, 16);
+              rs_s[i] += keep_s + got_s;
+              rs_q[i] += fmaf(keep_s, keep_s, got_q);
+            }
+          }
+        } else
         if (p.stats != nullptr && n0 < p.Ncols) {
           // per-channel sum / sum of squares over the warp's 32 rows: transpose-reduce with 31 shuffles per statistic so
           // that lane j ends up with column n0 + j; masked rows hold zeros
@@ -635,17 +764,17 @@ int sm_count() {
   return n;
 }
 
-template <int BLOCK_N, bool HALO, int ROWS, bool FUSE = false>
+template <int BLOCK_N, bool HALO, int ROWS, bool FUSE = false, bool VM = false>
 static int launch_tc_impl(const TcParams& p, cudaStream_t st) {
-  using Cfg = TcCfg<BLOCK_N, HALO, ROWS>;
+  using Cfg = TcCfg<BLOCK_N, HALO, ROWS, VM>;
   static bool attr_set = false;
   if (!attr_set) {
-    WSR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    WSR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE, VM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   int total = p.g1 * p.g2 * p.g3 * p.nbatch * p.n_tiles;
   int grid = total < sm_count() ? total : sm_count();
-  gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE><<<grid, FUSE ? kTcThreadsFused : kTcThreads, Cfg::kSmemBytes, st>>>(p);
+  gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE, VM><<<grid, FUSE ? kTcThreadsFused : kTcThreads, Cfg::kSmemBytes, st>>>(p);
   WSR_LAUNCH_OK();
   return WSR_OK;
 }
@@ -662,6 +791,9 @@ static int launch_tc(const TcParams& p, cudaStream_t st) {
     return launch_tc_impl<BLOCK_N, true, 1, true>(p, st);
   }
   if (p.n_taps > 0) {
+    if constexpr (BLOCK_N == 64) {
+      if (p.halo_rows == 3) return launch_tc_impl<BLOCK_N, true, 3, false, true>(p, st);
+    }
     if constexpr (BLOCK_N <= 64) {
       if (p.halo_rows == 4) return launch_tc_impl<BLOCK_N, true, 4>(p, st);
     }
@@ -753,7 +885,10 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
   static const bool no_halo = getenv("WSR_NO_HALO") != nullptr;
   static const int max_rows = getenv("WSR_HALO_ROWS") ? atoi(getenv("WSR_HALO_ROWS")) : 4;
   const bool halo = !no_halo && d->ksize == 3 && d->stride == 1 && p.t2 == 1 && p.t3 == 1 && p.t1 + 2 <= 130;
-  const int hrows = (halo && bn <= 64 && GH % 4 == 0 && max_rows >= 4) ? 4 : (halo && bn <= 128 && GH % 2 == 0 && max_rows >= 2) ? 2 : 1;
+  // vertical tap merge (N = 64, plain 3x3): three output rows per tile, needs the vmerge weight pack (w_vmerge)
+  static const bool no_vm = getenv("WSR_NO_VMERGE") != nullptr;
+  const bool vmerge = halo && bn == 64 && taps == 9 && !d->upsample && d->w_vmerge != nullptr && d->gn_table == nullptr && !no_vm;
+  const int hrows = vmerge ? 3 : (halo && bn <= 64 && GH % 4 == 0 && max_rows >= 4) ? 4 : (halo && bn <= 128 && GH % 2 == 0 && max_rows >= 2) ? 2 : 1;
   WSR_REQUIRE(d->gn_table == nullptr || halo, WSR_E_UNSUPPORTED,
               "conv_tc: the fused GroupNorm input needs a stride-1 3x3 convolution on rows of >= 128 pixels (see wsr_conv_tc_can_fuse_gn)");
   if (d->gn_table) {
@@ -783,6 +918,16 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
     rc = encode_map(&p.bmap[0], d->w, 3, dims, str, box);
     if (rc) return rc;
     p.bmap[1] = p.bmap[0];
+    p.bmap[2] = p.bmap[0];
+    if (vmerge) {
+      // [kx][3 * 64 rows: ky = 2, 1, 0][Cin]
+      uint64_t dimsv[3] = {(uint64_t)d->Cin, 192, 3};
+      uint64_t strv[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cin * 192 * 2};
+      uint32_t boxv[3] = {64, 192, 1};
+      WSR_REQUIRE((((uintptr_t)d->w_vmerge) & 15) == 0, WSR_E_UNSUPPORTED, "conv_tc: w_vmerge alignment");
+      rc = encode_map(&p.bmap[2], d->w_vmerge, 3, dimsv, strv, boxv);
+      if (rc) return rc;
+    }
     if (d->x2) {
       uint64_t dims2[3] = {(uint64_t)d->Cin2, (uint64_t)wrows, 1};
       uint64_t str2[2] = {(uint64_t)d->Cin2 * 2, (uint64_t)d->Cin2 * wrows * 2};

@@ -78,6 +78,7 @@ class PackedConv:
         self.w = self.bias = None
         self.Cout = self.Cin = self.Cin_pad = self.rows = self.k = 0
         self.merged_up = False          # True: phase-merged taps of an upsample conv (wsr_pack_upsample_weight)
+        self.w_vm = None                # vertical-tap-merge packing (3x3, Cout <= 64, bf16 mode): see wsr_conv_tc
 
 
 class Engine:
@@ -157,6 +158,9 @@ class Engine:
         pc.merged_up = False
         pc.w = self.empty((KH * KW, pc.rows, pc.Cin_pad))
         nat.call("wsr_pack_conv_weight", w.data_ptr(), Cout, Cin, KH, KW, pc.w.data_ptr(), self.dt, pc.rows, pc.Cin_pad, self.stream)
+        if self.use_tc and KH == 3 and KW == 3 and Cout <= 64 and pc.Cin_pad % 64 == 0:
+            pc.w_vm = self.empty((3, 192, pc.Cin_pad))
+            nat.call("wsr_pack_conv_weight_vmerge", w.data_ptr(), Cout, Cin, pc.w_vm.data_ptr(), self.dt, pc.Cin_pad, self.stream)
         pc.bias = None if bias is None else self.f32(bias)
         self._keep.append(w)
         return pc
@@ -211,6 +215,8 @@ class Engine:
         d.x, d.x_dtype, d.N, d.H, d.W, d.Cin, d.x_ld = x.ptr, x.dt, x.N, x.H, x.W, pc.Cin_pad, x.ld
         assert x.C == pc.Cin_pad, (x.C, pc.Cin_pad)
         d.w, d.w_rows = pc.w.data_ptr(), pc.rows
+        if pc.w_vm is not None and taps is None and stride == 1 and not upsample:
+            d.w_vmerge = pc.w_vm.data_ptr()
         d.ksize, d.stride, d.upsample = (1 if taps is not None else pc.k), stride, (2 if pc.merged_up else 1) if upsample else 0
         assert upsample or not pc.merged_up or taps is not None
         d.Cout = pc.Cout

@@ -412,3 +412,37 @@ def test_conv_tc_fused_groupnorm_input(case):
     torch.cuda.synchronize()
     err = rel_l2(y.to_nchw(eng), y_ref.to_nchw(eng))
     assert err < 2e-3, err
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 7, 256, 0), (1, 192, 64, 6, 128, 128), (2, 128, 64, 3, 128, 64), (1, 64, 1, 5, 256, 0)])
+def test_conv_tc_vertical_tap_merge_vs_simt(case):
+    """N = 64 layers on rows of >= 128 pixels run the vertically merged schedule (one MMA per halo row feeds three output
+    rows; register-accumulated GroupNorm statistics): against the SIMT kernel on the same bf16 inputs, incl. the fused 1x1
+    segment, partial last tiles (H % 3 != 0) and the statistics."""
+    N, Cin, Cout, H, W, Cin2 = case
+    torch.manual_seed(12)
+    dev = _dev()
+    eng = Engine(dev, "bf16")
+    x = torch.randn(N, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, 3, 3, device=dev) / math.sqrt(Cin * 9)
+    b = torch.randn(Cout, device=dev)
+    pc = eng.pack_conv(w, b, rows=64 if Cout < 16 else None)
+    assert pc.w_vm is not None
+    kw = {}
+    if Cin2:
+        x2 = torch.randn(N, Cin2, H, W, device=dev)
+        w2 = torch.randn(Cout, Cin2, 1, 1, device=dev) / math.sqrt(Cin2)
+        kw = dict(x2=_nhwc(x2, eng), w2=eng.pack_conv(w2, None))
+    res = torch.randn(N, Cout, H, W, device=dev)
+    xa, ra = _nhwc(x, eng), _nhwc(res, eng)
+    arena = engine_mod.StatsArena()
+    y_tc = eng.new_act(N, H, W, Cout, dt=nat.F32, stats=arena)
+    y_si = eng.new_act(N, H, W, Cout, dt=nat.F32, stats=arena)
+    st = arena.finalize(dev)
+    eng.conv(xa, pc, y_tc, res=ra, **kw)
+    eng.conv(xa, pc, y_si, res=ra, force_simt=True, **kw)
+    assert eng.n_tc == 1 and eng.n_simt == 1
+    torch.cuda.synchronize()
+    assert rel_l2(y_tc.to_nchw(eng), y_si.to_nchw(eng)) < 2e-5
+    half = st.numel() // 2
+    assert rel_l2(st[:half], st[half:]) < 1e-5
