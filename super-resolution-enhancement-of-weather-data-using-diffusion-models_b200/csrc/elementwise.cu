@@ -191,21 +191,29 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x, int HW, int C, int ld,
                                 const double* __restrict__ stats, int stats_ld, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int groups, float eps, int act, TO* __restrict__ y, int y_ld,
                                 float drop_p, uint64_t drop_seed, uint32_t drop_tag) {
-  extern __shared__ float sm[];   // scale[C], shift[C]
+  extern __shared__ float sm[];   // scale[C], shift[C], then (mean, rstd) per group
   const int n = blockIdx.y;
   const int cpg = C / groups;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    int g0 = (c / cpg) * cpg;
+  float* gm = sm + 2 * C;
+  // group moments first (one thread per group sums its cpg channel statistics), then per-channel scale / shift: the
+  // per-channel version re-summed the whole group for every channel (2 * cpg double loads each; cpg = 32 at C = 1024)
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     double a = 0.0, b = 0.0;
-    for (int j = 0; j < cpg; ++j) { a += stats[(int64_t)n * stats_ld + (g0 + j) * 2]; b += stats[(int64_t)n * stats_ld + (g0 + j) * 2 + 1]; }
-    double cnt = (double)cpg * HW;
-    double mean = a / cnt;
-    double var = b / cnt - mean * mean;
+    for (int j = 0; j < cpg; ++j) { a += stats[(int64_t)n * stats_ld + (g * cpg + j) * 2]; b += stats[(int64_t)n * stats_ld + (g * cpg + j) * 2 + 1]; }
+    // sums and the E[x^2] - mean^2 cancellation stay in double; the reciprocal square root is taken in fp32 in bf16 mode
+    const double inv_cnt = 1.0 / ((double)cpg * HW);
+    const double mean = a * inv_cnt;
+    double var = b * inv_cnt - mean * mean;
     if (var < 0.0) var = 0.0;
-    float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    float sc = gamma[c] * rstd;
+    gm[2 * g] = (float)mean;
+    gm[2 * g + 1] = sizeof(TI) == 4 ? (float)(1.0 / sqrt(var + (double)eps)) : rsqrtf((float)var + eps);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float sc = gamma[c] * gm[2 * g + 1];
     sm[c] = sc;
-    sm[C + c] = beta[c] - (float)mean * sc;
+    sm[C + c] = beta[c] - gm[2 * g] * sc;
   }
   __syncthreads();
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
@@ -586,8 +594,16 @@ static int gn_apply_impl(const void* x, int x_dtype, int N, int HW, int C, int x
   WSR_REQUIRE(drop_p >= 0.f && drop_p < 1.f, WSR_E_INVALID, "gn_apply: dropout p=%f", (double)drop_p);
   GnGeom g = gn_geom(x_dtype, C, x_ld, y_ld, x, y);
   WSR_REQUIRE(g.vec != 0 && g.threads <= 1024, WSR_E_UNSUPPORTED, "gn_apply: C=%d too wide", C);
+  // small feature maps: shrink the per-block pixel chunk until the grid has ~4 blocks per SM
+  {
+    const int want = (592 + N - 1) / N;                         // blocks per image
+    int chunk = (HW + want - 1) / want;
+    chunk = (chunk + g.PL - 1) / g.PL * g.PL;
+    if (chunk < 4 * g.PL) chunk = 4 * g.PL;
+    if (chunk < g.chunk) g.chunk = chunk;
+  }
   dim3 grid((HW + g.chunk - 1) / g.chunk, N);
-  size_t smem = (size_t)C * 2 * sizeof(float);
+  size_t smem = ((size_t)C * 2 + 2 * groups) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
 #define GN_APPLY(T, V, D) gn_apply_kernel<T, T, V, D><<<grid, g.threads, smem, st>>>((const T*)x, HW, C, x_ld, g.CV, g.PL, g.chunk, stats, stats_ld, gamma, beta, groups, eps, act, (T*)y, y_ld, drop_p, drop_seed, drop_tag)
   if (drop_p > 0.f) {
