@@ -806,16 +806,23 @@ static int launch_tc(const TcParams& p, cudaStream_t st) {
 }
 
 static int pick_block_n(int ncols, int m_tiles) {
-  // widest column tile (fewest re-reads of the activation tile, best smem bandwidth per MMA) that still gives at
-  // least one CTA per SM; otherwise the narrowest one, to spread a small problem over more SMs.
+  // Column-tile width by a small cost model measured on B200: one 128 x BN x 16 MMA costs about (69 + 0.28 * BN) cycles
+  // (the 128-row activation operand fetch is the fixed part), and a launch needs ceil(tiles / SMs) waves.  E.g. the 8x16
+  // level at B = 64 (64 row tiles, Cout = 512): BN = 256 -> 128 tiles = ONE 86%-full wave of 141-cycle MMAs beats
+  // BN = 128 -> 256 tiles = two waves of 105-cycle MMAs.
   const int sms = sm_count();
   const int cand[3] = {256, 128, 64};
+  int best = 64;
+  double best_cost = 1e30;
   for (int i = 0; i < 3; ++i) {
     const int bn = cand[i];
-    if (ncols % bn != 0) continue;
-    if (m_tiles * (ncols / bn) >= sms) return bn;
+    if (ncols % bn != 0 && !(bn == 64)) continue;
+    const int tiles = m_tiles * ((ncols + bn - 1) / bn);
+    const int waves = (tiles + sms - 1) / sms;
+    const double cost = (double)waves * (69.0 + 0.28 * bn);
+    if (cost < best_cost) { best_cost = cost; best = bn; }
   }
-  return 64;
+  return best;
 }
 
 int validate_conv_desc(const WsrConvDesc* d);
