@@ -4,12 +4,17 @@
 // einsum -> (B,N,N) fp32 matrix -> .contiguous() -> /sqrt(C) -> softmax -> einsum), whose N = 8192 instance writes
 // 268 MB per sample per step.  Here the score matrix never leaves the SM.
 //
-// One CTA owns 128 query rows and streams the keys in blocks of 128, TWO passes over the keys:
-//   pass A:  S = Q K^T (tcgen05.mma into TMEM), row maxima only (no exponentials)
-//   pass B:  S again, P = exp2((S - max) * scale*log2e) -> bf16 -> swizzled smem, O += P V (tcgen05.mma), row sums
-// Knowing the exact row maximum before pass B removes the online-softmax rescaling of the O accumulator (and the
-// dependency it creates between softmax and the previous P*V); the extra Q K^T is cheap because for d = 64 the kernel is
-// bound by the exponentials (128x128 per block on the SFUs), not by the tensor pipe.
+// One CTA owns 128 query rows and streams the keys in blocks of 128, in two passes:
+//   pass A:  S = Q K^T (tcgen05.mma into TMEM) for a few SAMPLED key blocks (4, evenly spread), row maxima only
+//   pass B:  S for every block, P = exp2((S - ref) * scale*log2e) -> bf16 -> swizzled smem, O += P V, row sums
+// Softmax is invariant to the shift `ref`, which only has to keep the exponentials inside the floating-point range;
+// it need not be the exact row maximum.  `ref` = the maximum over the sampled keys is an actual score of the row, so
+// nothing that matters can underflow, and a score above it simply gives P > 1 (fp32 sums, bf16 P and the fp32 O
+// accumulator all have 8 exponent bits; the exponent is clamped at +64 as a safety net, which cannot trigger unless a
+// row's scores differ by more than 44 natural units between the sampled and the unsampled keys).  Knowing the shift
+// before pass B removes the online-softmax rescaling of the O accumulator (and the dependency it creates between
+// softmax and the previous P*V); sampling removes 15/16 of the pass-A tensor and TMEM-read work of the N = 8192 layer.
+// Up to 4 key blocks the maximum is exact.
 // V is consumed TRANSPOSED (vT: B x d x Nk, produced that way by the K/V projection GEMM) so that both operands of P*V
 // are K-major and can be fed by plain 128B-swizzled TMA boxes.
 //
@@ -46,6 +51,7 @@ struct AttnParams {
   CUtensorMap qmap, kmap, vmap;
   void* o; long long o_sb; int o_ld;      // output (B, Nq, d) bf16
   int nblocks;                            // Nk / 128
+  int na, stride_a;                       // pass A: na sampled key blocks, block g*stride_a
   float c;                                // scale * log2(e)
 };
 
@@ -78,7 +84,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kBQ;
   const int b = blockIdx.y;
-  const int NB = p.nblocks;
+  const int NB = p.nblocks, NA = p.na;
 
   if (warp == kProducerWarp && lane == 0) {
     prefetch_tmap(&p.qmap); prefetch_tmap(&p.kmap); prefetch_tmap(&p.vmap);
@@ -107,13 +113,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
       mbar_expect_tx(q_full, Cfg::kQBytes);
       for (int c = 0; c < Cfg::kChunks; ++c) tma_load_3d(sQ + c * 16384, &p.qmap, q_full, c * 64, q0, b);
       int vj = 0;
-      for (int g = 0; g < 2 * NB; ++g) {
-        const int j = g < NB ? g : g - NB;
+      for (int g = 0; g < NA + NB; ++g) {
+        const int j = g < NA ? g * p.stride_a : g - NA;
         const int ks = g % KS; const uint32_t kph = (uint32_t)(g / KS) & 1;
         mbar_wait(&k_empty[ks], kph ^ 1);
         mbar_expect_tx(&k_full[ks], Cfg::kKBytes);
         for (int c = 0; c < Cfg::kChunks; ++c) tma_load_3d(sK + ks * Cfg::kKBytes + c * 16384, &p.kmap, &k_full[ks], c * 64, j * kBK, b);
-        if (g >= NB) {
+        if (g >= NA) {
           const int vs = vj % VS; const uint32_t vph = (uint32_t)(vj / VS) & 1;
           mbar_wait(&v_empty[vs], vph ^ 1);
           mbar_expect_tx(&v_full[vs], Cfg::kVBytes);
@@ -145,12 +151,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
         umma_commit(&k_empty[ks]);
         umma_commit(&s_full[sb]);
       };
-      // pass A: scores only
-      for (int g = 0; g < NB; ++g) issue_qk(g);
+      // pass A: scores of the sampled blocks only
+      for (int g = 0; g < NA; ++g) issue_qk(g);
       // pass B: scores one block ahead of P*V
-      issue_qk(NB);
+      issue_qk(NA);
       for (int j = 0; j < NB; ++j) {
-        if (j + 1 < NB) issue_qk(NB + j + 1);
+        if (j + 1 < NB) issue_qk(NA + j + 1);
         const int pb = j & 1; const uint32_t pph = (uint32_t)(j >> 1) & 1;
         const int vs = j % VS; const uint32_t vph = (uint32_t)(j / VS) & 1;
         mbar_wait(&p_full[pb], pph);
@@ -176,8 +182,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
     const int row = quad * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
     float mx = -INFINITY;
-    // pass A: row maximum of the raw scores
-    for (int g = 0; g < NB; ++g) {
+    // pass A: row maximum of the raw scores of the sampled key blocks
+    for (int g = 0; g < NA; ++g) {
       const int sb = g & 1; const uint32_t sph = (uint32_t)(g >> 1) & 1;
       mbar_wait(&s_full[sb], sph);
       tc_fence_after();
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
     float lsum = 0.f;
     // pass B: probabilities -> smem (K-major, 128B swizzle), row sums
     for (int j = 0; j < NB; ++j) {
-      const int g = NB + j;
+      const int g = NA + j;
       const int sb = g & 1; const uint32_t sph = (uint32_t)(g >> 1) & 1;
       const int pb = j & 1; const uint32_t pph = (uint32_t)(j >> 1) & 1;
       mbar_wait(&s_full[sb], sph);
@@ -219,7 +225,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
         tmem_ld32(tmem_S + lane_sel + (uint32_t)(sb * kBK + half * 64 + c2 * 32), v);
         float e[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) e[i] = exp2f(fmaf(__uint_as_float(v[i]), p.c, -mc));
+        for (int i = 0; i < 32; ++i) e[i] = exp2f(fminf(fmaf(__uint_as_float(v[i]), p.c, -mc), 64.f));
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;       // independent partial sums
 #pragma unroll
         for (int i = 0; i < 32; i += 4) { s0 += e[i]; s1 += e[i + 1]; s2 += e[i + 2]; s3 += e[i + 3]; }
@@ -321,6 +327,8 @@ extern "C" int wsr_attention_tc(const void* q, int q_ld, const void* k, int k_ld
   }
   p.o = o; p.o_sb = (long long)Nq * o_ld; p.o_ld = o_ld;
   p.nblocks = Nk / kBK;
+  p.na = p.nblocks < 4 ? p.nblocks : 4;
+  p.stride_a = p.nblocks / p.na;
   p.c = scale * 1.4426950408889634f;
   cudaStream_t st = (cudaStream_t)stream;
   return d == 64 ? launch_attn<64>(p, B, Nq, st) : launch_attn<128>(p, B, Nq, st);

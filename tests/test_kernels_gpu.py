@@ -446,3 +446,36 @@ def test_conv_tc_vertical_tap_merge_vs_simt(case):
     assert rel_l2(y_tc.to_nchw(eng), y_si.to_nchw(eng)) < 2e-5
     half = st.numel() // 2
     assert rel_l2(st[:half], st[half:]) < 1e-5
+
+
+def test_attention_tc_sampled_shift_is_exact_when_the_maximum_is_not_sampled():
+    """The fused attention takes its softmax shift from 4 sampled key blocks.  Softmax is shift-invariant, so rows whose
+    true maximum lies in an UNSAMPLED block (probabilities > 1 before normalisation, here by up to e^25) must still match
+    torch, as must rows dominated by a sampled key."""
+    B, H, W, d = 1, 16, 64, 64           # 1024 keys = 8 blocks; blocks 0, 2, 4, 6 are sampled
+    n = H * W
+    torch.manual_seed(10)
+    dev = _dev()
+    eng = Engine(dev, "bf16")
+    q = torch.randn(B, d, H, W, device=dev)
+    k = torch.randn(B, d, H, W, device=dev) * 0.5
+    v = torch.randn(B, d, H, W, device=dev)
+    kf0 = k.reshape(B, d, n)
+    qf0 = q.reshape(B, d, n)
+    # key 200 (block 1, unsampled) is strongly aligned with queries 0..255; key 700 (block 5) with queries 256..511
+    kf0[:, :, 200] = 6.0 * qf0[:, :, :256].mean(-1) / qf0[:, :, :256].mean(-1).norm() * math.sqrt(d) / 2
+    kf0[:, :, 700] = 12.0 * qf0[:, :, 256:512].mean(-1) / qf0[:, :, 256:512].mean(-1).norm() * math.sqrt(d) / 2
+    qa, ka = _nhwc(q, eng), _nhwc(k, eng)
+    vT = v.reshape(B, d, n).bfloat16().contiguous()
+    o = eng.new_act(B, H, W, d, zero=True)
+    eng.attention(qa, ka, vT, o, None, None)
+    assert eng.n_tc == 1
+    qf = qa.to_nchw(eng).reshape(B, d, n)
+    kf = ka.to_nchw(eng).reshape(B, d, n)
+    s = torch.einsum("bcq,bck->bqk", qf, kf) / math.sqrt(d)
+    spread = float((s.max(-1).values - s[:, :, torch.arange(n, device=dev) // 128 % 2 == 0].max(-1).values).max())
+    assert spread > 5.0, spread            # the case really exercises P > 1
+    ref = torch.einsum("bqk,bck->bcq", torch.softmax(s, -1), vT.float()).reshape(B, d, H, W)
+    out = o.to_nchw(eng)
+    assert torch.isfinite(out).all()
+    assert rel_l2(out, ref) < 1e-2, rel_l2(out, ref)
