@@ -51,20 +51,18 @@ class NoiseLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, noise, eps, l2):
         acc = torch.zeros(1, dtype=torch.float64, device=noise.device)
-        nat.call("wsr_noise_loss", noise.data_ptr(), eps.data_ptr(), noise.numel(), 1 if l2 else 0, acc.data_ptr(), 0, 0.0,
+        grad = torch.empty_like(eps)               # d loss / d eps for an upstream gradient of 1 (same kernel, same pass)
+        nat.call("wsr_noise_loss", noise.data_ptr(), eps.data_ptr(), noise.numel(), 1 if l2 else 0, acc.data_ptr(), grad.data_ptr(), 1.0,
                  torch.cuda.current_stream(noise.device).cuda_stream)
-        ctx.save_for_backward(noise, eps)
-        ctx.l2 = l2
+        ctx.save_for_backward(grad)
         return acc.to(torch.float32)[0]
 
     @staticmethod
     def backward(ctx, go):
-        noise, eps = ctx.saved_tensors
-        grad = torch.empty_like(eps)
-        scratch = torch.zeros(1, dtype=torch.float64, device=noise.device)
-        nat.call("wsr_noise_loss", noise.data_ptr(), eps.data_ptr(), noise.numel(), 1 if ctx.l2 else 0, scratch.data_ptr(),
-                 grad.data_ptr(), float(go), torch.cuda.current_stream(noise.device).cuda_stream)
-        return None, grad, None
+        (grad,) = ctx.saved_tensors
+        # scaling by the 0-dim upstream gradient stays on the device: reading it on the host would stall the launch queue
+        # between the forward and the backward pass
+        return None, grad * go.to(grad.dtype), None
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -110,8 +108,9 @@ class FusedAdam(torch.optim.Optimizer):
             nat.call("wsr_adam_step", f["p"].data_ptr(), plan.gflat.data_ptr(), f["m"].data_ptr(), f["v"].data_ptr(), f["p"].numel(),
                      float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), int(f["step"]),
                      torch.cuda.current_stream(f["p"].device).cuda_stream)
+            step_t = torch.tensor(float(f["step"]))
             for p in plan.param_order:
-                self.state[p]["step"] = torch.tensor(float(f["step"]))
+                self.state[p]["step"] = step_t
             weights_epoch += 1
             return loss
         for group in self.param_groups:

@@ -64,10 +64,12 @@ class DDPM(BaseModel):
         if reducer is not None:
             reducer.finish()
         self.optG.step()
+        l_pix = l_pix.detach().clone()
         if world > 1:
-            l_pix = l_pix.detach().clone()
             dist.all_reduce(l_pix)
-        self.log_dict['l_pix'] = l_pix.item()
+        # the reference stores l_pix.item() here (model.py:69); the device->host read is deferred to get_current_log() so
+        # that the launch queue is not drained after every optimizer step
+        self.log_dict['l_pix'] = l_pix
 
     def _grad_reducer(self, batch):
         """FlatGradReducer bound to the denoiser's train plan for this local batch size (created once)."""
@@ -101,6 +103,9 @@ class DDPM(BaseModel):
             self._net().set_new_noise_schedule(schedule_opt, self.device)
 
     def get_current_log(self):
+        for k, v in list(self.log_dict.items()):
+            if torch.is_tensor(v):
+                self.log_dict[k] = v.item()
         return self.log_dict
 
     def get_images(self, need_LR=True, sample=False):

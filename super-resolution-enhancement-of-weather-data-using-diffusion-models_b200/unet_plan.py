@@ -298,7 +298,8 @@ class UNetPlan:
             self.proj_b = torch.cat(proj_b, 0).contiguous()
             assert self.proj_w.shape == (self.P, self.inner), (self.proj_w.shape, self.P)
         self.proj_table = None
-        torch.cuda.current_stream(e.device).synchronize()
+        # no host synchronisation: the temporaries were consumed by kernels launched on torch's current stream, and the
+        # caching allocator only hands a freed block to later work on that same stream
         e._keep.clear()
 
     def _pack_f32_conv(self, weight):

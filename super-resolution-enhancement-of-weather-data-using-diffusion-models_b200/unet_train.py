@@ -244,7 +244,6 @@ class UNetTrainPlan(UNetPlan):
                 if r.kind == "up":
                     r.dconv = e.pack_conv(T.upsample_dgrad_weight(r.mod.conv.weight), None)
             self.dfinal = dg(self.net.final_conv.block[3].weight)
-        torch.cuda.current_stream(e.device).synchronize()
         e._keep.clear()
 
     # ------------------------------------------------------------------------------------------------------------------
