@@ -178,6 +178,11 @@ def last_error():
     return _load().wsr_last_error().decode()
 
 
+def fn(name):
+    """The raw ctypes entry point (argtypes set), for recorded launch lists."""
+    return getattr(_load(), name)
+
+
 def call(name, *args):
     """Call a status-returning entry point; raise WsrError on failure."""
     global launches

@@ -97,6 +97,9 @@ class Engine:
         self.n_tc = 0
         self.n_simt = 0
         self._keep = []          # tensors that must outlive async launches
+        self._pack_cache = {}    # key -> packed buffers: re-packing after an optimizer step writes the SAME device buffers,
+                                 # so pointers recorded in launch lists stay valid
+        self.rec = None          # when a list: every launch made through call() is appended as (fn, args) for replay()
         self.prof = None         # list of (name, flops, bytes, start_event, end_event) when profiling
         self.prof_detail = False
         self.no_fused_attention = False
@@ -105,7 +108,10 @@ class Engine:
     def call(self, name, *args, flops=0, nbytes=0, tag=None):
         """nat.call with optional per-launch CUDA-event timing (bench.py roofline pass)."""
         if self.prof is None:
-            return nat.call(name, *args)
+            rc = nat.call(name, *args)
+            if self.rec is not None:
+                self.rec.append((nat.fn(name), args, name))
+            return rc
         s = torch.cuda.Event(enable_timing=True)
         t = torch.cuda.Event(enable_timing=True)
         s.record(torch.cuda.current_stream(self.device))
@@ -113,6 +119,26 @@ class Engine:
         t.record(torch.cuda.current_stream(self.device))
         self.prof.append((tag or name, flops, nbytes, s, t))
         return rc
+
+    def replay(self, entries):
+        """Re-issue a recorded launch list: same entry points, same argument objects (device pointers, descriptors and
+        tap tables are fixed per plan; values that change per step -- dropout seeds -- are shared ctypes objects whose
+        .value is updated before the replay).  Entries with fn None are host callbacks (gradient-bucket hooks)."""
+        if self.prof is not None:
+            for fn, args, name in entries:
+                if fn is None:
+                    args()
+                else:
+                    self.call(name, *args)
+            return
+        for fn, args, name in entries:
+            if fn is None:
+                args()
+            else:
+                rc = fn(*args)
+                if rc != 0:
+                    raise nat.WsrError("%s failed (%d) during replay: %s" % (name, rc, nat.last_error()))
+        nat.launches += len(entries)
 
     def prof_summary(self):
         """name -> [launches, ms, flops, bytes] from the recorded events (synchronises)."""
@@ -147,23 +173,41 @@ class Engine:
         return t.detach().to(device=self.device, dtype=torch.float32).contiguous()
 
     # ---- packing ---------------------------------------------------------------------------------------------------
-    def pack_conv(self, weight, bias=None, cin_pad=None, rows=None):
-        """weight: OIHW fp32 parameter."""
+    def _src_key(self, t):
+        return (t.data_ptr(), tuple(t.shape), tuple(t.stride()))
+
+    def pack_conv(self, weight, bias=None, cin_pad=None, rows=None, key=None):
+        """weight: OIHW fp32 parameter (or a tensor derived from one; then pass ``key`` = a stable identity for the cache,
+        e.g. ('dgrad', param.data_ptr()), because a derived temporary has a new address on every call)."""
         w = self.f32(weight)
         Cout, Cin, KH, KW = w.shape
-        pc = PackedConv()
-        pc.Cout, pc.Cin, pc.k = Cout, Cin, KH
-        pc.Cin_pad = cin_pad or Cin
-        pc.rows = rows or Cout
-        pc.merged_up = False
-        pc.w = self.empty((KH * KW, pc.rows, pc.Cin_pad))
+        key = ("conv", key if key is not None else self._src_key(weight), cin_pad, rows)
+        pc = self._pack_cache.get(key)
+        if pc is None:
+            pc = self._pack_cache[key] = PackedConv()
+            pc.Cout, pc.Cin, pc.k = Cout, Cin, KH
+            pc.Cin_pad = cin_pad or Cin
+            pc.rows = rows or Cout
+            pc.merged_up = False
+            pc.w = self.empty((KH * KW, pc.rows, pc.Cin_pad))
+            if self.use_tc and KH == 3 and KW == 3 and Cout <= 64 and pc.Cin_pad % 64 == 0:
+                pc.w_vm = self.empty((3, 192, pc.Cin_pad))
         nat.call("wsr_pack_conv_weight", w.data_ptr(), Cout, Cin, KH, KW, pc.w.data_ptr(), self.dt, pc.rows, pc.Cin_pad, self.stream)
-        if self.use_tc and KH == 3 and KW == 3 and Cout <= 64 and pc.Cin_pad % 64 == 0:
-            pc.w_vm = self.empty((3, 192, pc.Cin_pad))
+        if pc.w_vm is not None:
             nat.call("wsr_pack_conv_weight_vmerge", w.data_ptr(), Cout, Cin, pc.w_vm.data_ptr(), self.dt, pc.Cin_pad, self.stream)
         pc.bias = None if bias is None else self.f32(bias)
         self._keep.append(w)
         return pc
+
+    def static_f32(self, key, value):
+        """fp32 device tensor with a stable address holding ``value`` (a tensor computed on the fly, e.g. a sum of two biases)."""
+        buf = self._pack_cache.get(("f32", key))
+        v = self.f32(value)
+        if buf is None:
+            buf = self._pack_cache[("f32", key)] = v.clone()
+        else:
+            buf.copy_(v)
+        return buf
 
     def pack_upsample_conv(self, weight, bias=None):
         """Weights of 'nearest x2 upsample + conv3x3' (functional_layers.py:62-67).  In bf16 mode the taps that read the
@@ -173,9 +217,12 @@ class Engine:
         w = self.f32(weight)
         Cout, Cin, KH, KW = w.shape
         assert KH == 3 and KW == 3
-        pc = PackedConv()
-        pc.Cout, pc.Cin, pc.k, pc.Cin_pad, pc.rows, pc.merged_up = Cout, Cin, 3, Cin, Cout, True
-        pc.w = self.empty((16, Cout, Cin))
+        key = ("upconv", self._src_key(weight))
+        pc = self._pack_cache.get(key)
+        if pc is None:
+            pc = self._pack_cache[key] = PackedConv()
+            pc.Cout, pc.Cin, pc.k, pc.Cin_pad, pc.rows, pc.merged_up = Cout, Cin, 3, Cin, Cout, True
+            pc.w = self.empty((16, Cout, Cin))
         nat.call("wsr_pack_upsample_weight", w.data_ptr(), Cout, Cin, pc.w.data_ptr(), self.dt, Cout, Cin, self.stream)
         pc.bias = None if bias is None else self.f32(bias)
         self._keep.append(w)
@@ -184,7 +231,10 @@ class Engine:
     def pack_rows(self, weight2d):
         """(rows, K) fp32 matrix -> engine dtype, row-major (K-major operand for the GEMM kernels)."""
         w = self.f32(weight2d)
-        out = self.empty(tuple(w.shape))
+        key = ("rows", self._src_key(weight2d))
+        out = self._pack_cache.get(key)
+        if out is None:
+            out = self._pack_cache[key] = self.empty(tuple(w.shape))
         nat.call("wsr_cast", w.data_ptr(), nat.F32, out.data_ptr(), self.dt, w.numel(), self.stream)
         self._keep.append(w)
         return out
@@ -340,7 +390,8 @@ class Engine:
     def gn_apply_dropout(self, x, gamma, beta, groups, act, y, p, seed, tag, eps=1e-5):
         assert x.stats_ptr
         self.call("wsr_gn_apply_dropout", x.ptr, x.dt, x.N, x.H * x.W, x.C, x.ld, x.stats_ptr, x.st_ld, gamma.data_ptr(),
-                  beta.data_ptr(), groups, eps, act, y.ptr, y.dt, y.ld, float(p), int(seed), int(tag), self.stream,
+                  beta.data_ptr(), groups, eps, act, y.ptr, y.dt, y.ld, float(p), seed if isinstance(seed, C.c_uint64) else int(seed),
+                  int(tag), self.stream,
                   nbytes=2 * x.N * x.H * x.W * x.C * (2 if x.dt == nat.BF16 else 4))
         return y
 
@@ -350,7 +401,8 @@ class Engine:
         red_ptr: zeroed [N][2C] doubles scratch; colsum: optional [N][colsum_ld] fp32 = per-image column sums of dx."""
         assert x.stats_ptr and da.dt == x.dt and dx.dt == x.dt
         common = (x.ptr, x.dt, x.N, x.H * x.W, x.C, x.ld, x.stats_ptr, x.st_ld, gamma.data_ptr(), beta.data_ptr(), groups, eps,
-                  act, da.ptr, da.dt, da.ld, float(drop[0]), int(drop[1]), int(drop[2]), red_ptr, 2 * x.C)
+                  act, da.ptr, da.dt, da.ld, float(drop[0]), drop[1] if isinstance(drop[1], C.c_uint64) else int(drop[1]), int(drop[2]),
+                  red_ptr, 2 * x.C)
         nb = x.N * x.H * x.W * x.C * (2 if x.dt == nat.BF16 else 4)
         self.call("wsr_gn_bwd_reduce", *common, self.stream, nbytes=2 * nb, tag="gn_bwd_reduce")
         self.call("wsr_gn_bwd_apply", *common, dx.ptr, dx.dt, dx.ld, 1 if accumulate else 0, _ptr(dgamma), _ptr(dbeta),

@@ -238,7 +238,7 @@ class UNetPlan:
                 r.conv2 = e.pack_conv(conv2.weight, conv2.bias)
                 if r.has_res_conv:
                     r.resw = e.pack_conv(rb.res_conv.weight, None)
-                    r.bias2 = e.f32(conv2.bias + rb.res_conv.bias)
+                    r.bias2 = e.static_f32(("bias2", conv2.bias.data_ptr()), conv2.bias + rb.res_conv.bias)
                 lin = rb.noise_func.noise_func[0]
                 proj_w.append(e.f32(lin.weight)); proj_b.append(e.f32(lin.bias))
                 if r.attn:
@@ -294,8 +294,8 @@ class UNetPlan:
                 nat.call("wsr_pack_convT_weight", w.data_ptr(), cp.in_channels, cp.out_channels, 8, 8, self.cp_w.data_ptr(), e.dt, e.stream)
                 self.cp_b = e.f32(cp.bias)
                 e._keep.append(w)
-            self.proj_w = torch.cat(proj_w, 0).contiguous()
-            self.proj_b = torch.cat(proj_b, 0).contiguous()
+            self.proj_w = e.static_f32(("proj_w", id(self)), torch.cat(proj_w, 0))
+            self.proj_b = e.static_f32(("proj_b", id(self)), torch.cat(proj_b, 0))
             assert self.proj_w.shape == (self.P, self.inner), (self.proj_w.shape, self.P)
         self.proj_table = None
         # no host synchronisation: the temporaries were consumed by kernels launched on torch's current stream, and the
@@ -308,9 +308,12 @@ class UNetPlan:
         w = e.f32(weight)
         Cout, Cin, KH, KW = w.shape
         from .engine import PackedConv
-        pc = PackedConv()
-        pc.Cout, pc.Cin, pc.k, pc.Cin_pad, pc.rows, pc.bias = Cout, Cin, KH, Cin, Cout, None
-        pc.w = e.empty((KH * KW, Cout, Cin), torch.float32)
+        key = ("f32conv", e._src_key(weight))
+        pc = e._pack_cache.get(key)
+        if pc is None:
+            pc = e._pack_cache[key] = PackedConv()
+            pc.Cout, pc.Cin, pc.k, pc.Cin_pad, pc.rows, pc.bias = Cout, Cin, KH, Cin, Cout, None
+            pc.w = e.empty((KH * KW, Cout, Cin), torch.float32)
         nat.call("wsr_pack_conv_weight", w.data_ptr(), Cout, Cin, KH, KW, pc.w.data_ptr(), nat.F32, Cout, Cin, e.stream)
         e._keep.append(w)
         return pc

@@ -17,7 +17,10 @@ Parameter gradients live in ONE flat fp32 buffer (``gflat``) laid out in the ord
 them, so a data-parallel trainer can all-reduce contiguous buckets while the rest of the backward is still running
 (``on_ready`` callback).  ``param_grads()`` maps every ``nn.Parameter`` to its view of that buffer.
 """
+import ctypes
+import functools
 import math
+import os
 
 import torch
 
@@ -35,6 +38,14 @@ class UNetTrainPlan(UNetPlan):
         self.drop_seed = 0
         self.on_ready = None           # callback(lo, hi): gflat[lo:hi] is final (launch its all-reduce now)
         self._dw = None
+        # Launch lists: a training step issues ~1100 kernel launches whose arguments (device pointers, descriptors, tap
+        # tables) never change, while building them in Python costs ~30 us each -- more than the GPU needs to execute
+        # them at batch 4.  The forward and the backward schedule are therefore RECORDED once (Engine.rec) and replayed
+        # with ~2 us per launch; the only per-step value, the dropout seed, lives in a shared ctypes object.
+        self._seed = ctypes.c_uint64(0)
+        self._lists = {}
+        self._n_bwd = 0
+        self.replay_enabled = os.environ.get("WSR_NO_REPLAY") is None
         self.fuse_gn = False           # the backward pass reads the normalised activations (a1, a2): keep them materialised
         super().__init__(net, batch, device, precision, strict_tc)
         self.eng.no_fused_attention = False
@@ -46,7 +57,7 @@ class UNetTrainPlan(UNetPlan):
     # ------------------------------------------------------------------------------------------------------------------
     def _block2_norm(self, r):
         if self.drop_p > 0.0 and self.train_mode:
-            self.eng.gn_apply_dropout(r.hbuf, r.g2, r.b2, self.groups, nat.ACT_SWISH, r.a2, self.drop_p, self.drop_seed, r.drop_tag)
+            self.eng.gn_apply_dropout(r.hbuf, r.g2, r.b2, self.groups, nat.ACT_SWISH, r.a2, self.drop_p, self._seed, r.drop_tag)
         else:
             self.eng.gn_apply(r.hbuf, r.g2, r.b2, self.groups, nat.ACT_SWISH, r.a2)
 
@@ -192,6 +203,7 @@ class UNetTrainPlan(UNetPlan):
         self.dproj = torch.zeros((B, self.P), device=e.device, dtype=torch.float32)
         self.dtemb = e.empty((B, self.inner), torch.float32)
         self.deps = e.new_act(B, self.H, self.W, self.C_img)
+        self.deps_in = e.empty((B, self.C_img, self.H, self.W), torch.float32)
         self.dxin = e.new_act(B, self.H, self.W, 5 * self.C_img, dt=nat.F32)
         self.g_lf = e.empty((B, self.C_img, self.H, self.W), torch.float32)
         self.g_hf = e.empty((B, self.C_img, self.H, self.W), torch.float32)
@@ -219,7 +231,7 @@ class UNetTrainPlan(UNetPlan):
         e = self.eng
         with torch.no_grad():
             def dg(weight):
-                return e.pack_conv(T.dgrad_weight(weight), None)
+                return e.pack_conv(T.dgrad_weight(weight), None, key=("dgrad",) + e._src_key(weight))
 
             for r in self._res_records():
                 rb = r.mod.res_block
@@ -242,7 +254,7 @@ class UNetTrainPlan(UNetPlan):
                     r.ca.dwout = dg(m.out.weight)
             for r in self.ups:
                 if r.kind == "up":
-                    r.dconv = e.pack_conv(T.upsample_dgrad_weight(r.mod.conv.weight), None)
+                    r.dconv = e.pack_conv(T.upsample_dgrad_weight(r.mod.conv.weight), None, key=("updgrad",) + e._src_key(r.mod.conv.weight))
             self.dfinal = dg(self.net.final_conv.block[3].weight)
         e._keep.clear()
 
@@ -338,7 +350,7 @@ class UNetTrainPlan(UNetPlan):
         else:
             e.call("wsr_axpby", dy.ptr, dy.dt, dy.ld, 1.0, dx.ptr, dx.dt, dx.ld, 1.0, dx.ptr, dx.dt, dx.ld, B * r.h * r.w, r.cout, e.stream)
         # a2 = dropout(swish(GN2(h)));  h = conv1(a1) + bias + proj[b]
-        drop = (self.drop_p, self.drop_seed, r.drop_tag) if self.drop_p > 0.0 else (0.0, 0, 0)
+        drop = (self.drop_p, self._seed, r.drop_tag) if (self.drop_p > 0.0 and self.train_mode) else (0.0, 0, 0)
         self._gn_bwd(r.hbuf, rb.block2.block[0], SW, d_a2, d_h, r.red2, colsum=self.dproj.data_ptr() + 4 * r.proj_off,
                      colsum_ld=self.P, drop=drop, gamma=r.g2, beta=r.b2)
         e.conv(d_h, r.dconv1, d_a1, bias=False)
@@ -364,6 +376,11 @@ class UNetTrainPlan(UNetPlan):
         self._gn_bwd(ca.x, m.norm, nat.ACT_NONE, d_n, dx, ca.red, gamma=ca.g, beta=ca.b, groups=32)
 
     def _ready(self, mark):
+        if self.eng.rec is not None:
+            self.eng.rec.append((None, functools.partial(self._ready_fire, mark), "on_ready"))
+        self._ready_fire(mark)
+
+    def _ready_fire(self, mark):
         if self.on_ready is not None:
             lo = 0 if mark == 0 else self._mark_offsets[mark - 1]
             hi = self._mark_offsets[mark] if mark < len(self._mark_offsets) else self.gflat.numel()
@@ -376,18 +393,40 @@ class UNetTrainPlan(UNetPlan):
     def backward(self, d_eps):
         """d_eps: (B, C_img, H, W) fp32 gradient of the loss w.r.t. ``self.eps``.  Fills ``gflat`` (all parameter
         gradients of this step; the buffer is overwritten, accumulation across steps is the caller's business)."""
+        e = self.eng
+        self.deps_in.copy_(d_eps.to(torch.float32))
+        self._n_bwd += 1
+        key = ("bwd", self.train_mode, self._ptr_sig())
+        if self.replay_enabled and self._lists.get("bwd_key") == key:
+            e.replay(self._lists["bwd"])
+            return self.gflat
+        # the first call creates the activation-gradient buffers lazily (their memsets are not in its launch sequence):
+        # record from the second call on
+        record = self.replay_enabled and self._n_bwd >= 2
+        if record:
+            e.rec = []
+        try:
+            self._backward_body(self.deps_in)
+        finally:
+            lst, e.rec = e.rec, None
+        if record:
+            self._lists["bwd"], self._lists["bwd_key"] = lst, key
+        return self.gflat
+
+    def _ptr_sig(self):
+        return tuple(p.data_ptr() for p in self.param_order)
+
+    def _backward_body(self, d_eps):
         e, B, G = self.eng, self.B, self.G
         st = e.stream
         net = self.net
         SW = nat.ACT_SWISH
-        d_eps = d_eps.to(torch.float32).contiguous()
         e.call("wsr_fill_zero", self.gflat.data_ptr(), self.gflat.numel() * 4, st)
         e.call("wsr_fill_zero", self.red.data_ptr(), self.red.numel() * 8, st)
         e.call("wsr_fill_zero", self.dproj.data_ptr(), self.dproj.numel() * 4, st)
         for g in self._gtensors:
             e.call("wsr_fill_zero", g.data_ptr(), g.numel() * g.element_size(), st)
         e.call("wsr_nchw_to_nhwc", d_eps.data_ptr(), B, self.C_img, self.H, self.W, self.deps.ptr, self.deps.dt, self.deps.ld, st)
-        e._keep_tmp = d_eps
 
         # head: eps = conv(swish(GN(x_last)))
         fc = net.final_conv.block
@@ -457,11 +496,30 @@ class UNetTrainPlan(UNetPlan):
     # ------------------------------------------------------------------------------------------------------------------
     def run(self, x_t):
         """UNetPlan.run plus a record of which buffer fed each layer (the backward pass walks it in reverse)."""
-        e, B = self.eng, self.B
-        st = e.stream
+        e = self.eng
         self.refresh_weights()
         if self.drop_p > 0.0 and self.train_mode:
             self.drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            self._seed.value = self.drop_seed
+        key = ("fwd", x_t.data_ptr(), self.train_mode, self._ptr_sig())
+        if self.replay_enabled and self._lists.get("fwd_key") == key:
+            e.replay(self._lists["fwd"])
+            return self.eps
+        record = self.replay_enabled and self._lists.get("fwd_seen") == key      # second identical call
+        self._lists["fwd_seen"] = key
+        if record:
+            e.rec = []
+        try:
+            self._run_body(x_t)
+        finally:
+            lst, e.rec = e.rec, None
+        if record:
+            self._lists["fwd"], self._lists["fwd_key"] = lst, key
+        return self.eps
+
+    def _run_body(self, x_t):
+        e, B = self.eng, self.B
+        st = e.stream
         e.call("wsr_fill_zero", self.stats.data_ptr(), self.stats.numel() * 8, st)
         stem = self.downs[0]
         e.call("wsr_fd_gate", self.cur_proj.data_ptr() + 4 * self.ne_off, self.P, 0, B, self.C_img, self.W,

@@ -398,3 +398,22 @@ def test_optimize_parameters_decreases_loss_and_flat_adam():
     assert worst < 1e-5
     sd = opt.state_dict()
     assert len(sd["state"]) == len(list(diff.parameters()))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_recorded_launch_lists_reproduce_the_eager_step(precision):
+    """The forward / backward launch lists are recorded on the second call and replayed from the third: the same batch must
+    give the same loss and gradients in all three modes (fp32 atomics reorder -> 1e-5), and the lists must really be used."""
+    g, spec = load_golden("resdiff_grad_small"), CASES["resdiff_grad_small"]
+    net, diff = _build(spec["cfg"], spec["seed"], precision)
+    plan = net.train_plan(g["hr"].shape[0], torch.device("cuda:0"))
+    outs = []
+    for it in range(4):
+        for p in diff.parameters():
+            p.grad = None
+        loss = _train_backward(diff, g, spec)
+        outs.append((loss, plan.gflat.clone()))
+    assert "fwd" in plan._lists and "bwd" in plan._lists and len(plan._lists["bwd"]) > 300
+    for loss, gf in outs[1:]:
+        assert abs(loss - outs[0][0]) <= 1e-6 * abs(outs[0][0])
+        assert rel_l2(gf, outs[0][1]) < (1e-5 if precision == "fp32" else 1e-3)
