@@ -230,6 +230,22 @@ int wsr_pack_upsample_weight(const float* w_oihw, int Cout, int Cin, void* dst, 
                              void* stream);
 /* ConvTranspose2d weight (Cin, Cout, KH, KW) fp32 -> [tap][Cout][Cin]. */
 int wsr_pack_convT_weight(const float* w_iohw, int Cin, int Cout, int KH, int KW, void* dst, int dst_dtype, void* stream);
+/* Batched re-pack: ONE launch refreshes every packed weight of a plan from the fp32 parameters (the training loop calls it
+ * after each optimizer step instead of ~350 per-tensor pack launches).  `jobs_device` is a device array, sorted by
+ * `first_unit` (prefix sum of the jobs' unit counts: Cout_pad*Cin_pad pairs for the weight kinds, Cout elements for COPY).
+ * `transposed` selects the data-gradient weight W'[o][i][ky][kx] = W[i][o][KH-1-ky][KW-1-kx] of the same parameter (Cout/Cin
+ * are the LOGICAL dims of W').  Kinds: CONV = wsr_pack_conv_weight, VMERGE = wsr_pack_conv_weight_vmerge (Cout_pad = 64),
+ * UPSAMPLE = wsr_pack_upsample_weight, UPSAMPLE_DGRAD = the 4x4 stride-2 data-gradient taps of "nearest x2 + conv3x3"
+ * (always transposed), COPY = dst[i] = src[i] (+ src2[i]) fp32/bf16 vector. */
+enum { WSR_PACK_CONV = 0, WSR_PACK_VMERGE = 1, WSR_PACK_UPSAMPLE = 2, WSR_PACK_UPSAMPLE_DGRAD = 3, WSR_PACK_COPY = 4 };
+typedef struct WsrPackJob {
+  const float* src;
+  const float* src2;
+  void* dst;
+  int64_t first_unit;
+  int32_t kind, transposed, dst_dtype, Cout, Cin, taps, Cout_pad, Cin_pad;
+} WsrPackJob;
+int wsr_repack_batch(const WsrPackJob* jobs_device, int njobs, int64_t total_units, void* stream);
 /* dst[i] = (T) src[i] */
 int wsr_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
 /* nearest x2 upsample of an NHWC tensor (functional_layers.py:62). */

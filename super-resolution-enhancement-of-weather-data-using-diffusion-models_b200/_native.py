@@ -18,6 +18,16 @@ class WsrError(RuntimeError):
     pass
 
 
+class PackJob(C.Structure):
+    """WsrPackJob (include/wsr.h): one entry of the batched weight re-pack."""
+    _fields_ = [("src", C.c_void_p), ("src2", C.c_void_p), ("dst", C.c_void_p), ("first_unit", C.c_int64),
+                ("kind", C.c_int32), ("transposed", C.c_int32), ("dst_dtype", C.c_int32), ("Cout", C.c_int32), ("Cin", C.c_int32),
+                ("taps", C.c_int32), ("Cout_pad", C.c_int32), ("Cin_pad", C.c_int32)]
+
+
+PACK_CONV, PACK_VMERGE, PACK_UPSAMPLE, PACK_UPSAMPLE_DGRAD, PACK_COPY = 0, 1, 2, 3, 4
+
+
 class ConvDesc(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("x_dtype", C.c_int), ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("x_ld", C.c_int),
@@ -101,6 +111,7 @@ SIGNATURES = {
     "wsr_pack_conv_weight_vmerge": [_P, _I, _I, _P, _I, _I, _P],
     "wsr_pack_convT_weight": [_P, _I, _I, _I, _I, _P, _I, _P],
     "wsr_cast": [_P, _I, _P, _I, _L, _P],
+    "wsr_repack_batch": [_P, _I, _L, _P],
     "wsr_upsample2x": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P],
     "wsr_axpby": [_P, _I, _I, _F, _P, _I, _I, _F, _P, _I, _I, _L, _I, _P],
     "wsr_noise_embed": [_P, _I, _I, _P, _P, _P, _P, _I, _P, _P],

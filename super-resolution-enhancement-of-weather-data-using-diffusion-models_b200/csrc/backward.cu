@@ -253,6 +253,138 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a, in
   }
 }
 
+// Vectorised versions (16-byte accesses: 8 bf16 / 4 fp32 channels per thread; thread t owns channel vector t % CV and pixel
+// lane t / CV, like gn_apply_kernel).  The scalar kernels above remain for pitches / widths that are not vector-aligned.
+template <typename T, int VEC>
+__device__ __forceinline__ void gn_bwd_dz(const GnBwdArgs& a, int n, int p, int cv, const T* x, const T* da, const float (&mu)[VEC],
+                                          const float (&rs)[VEC], const float (&g)[VEC], const float (&b)[VEC], float (&xh)[VEC],
+                                          float (&dz)[VEC]) {
+  float xv[VEC], dv[VEC];
+  VecLoad<T, VEC>::ld(x + (int64_t)p * a.x_ld, xv);
+  VecLoad<T, VEC>::ld(da + (int64_t)p * a.da_ld, dv);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    xh[i] = (xv[i] - mu[i]) * rs[i];
+    dz[i] = dv[i] * act_grad(fmaf(xh[i], g[i], b[i]), a.act);
+  }
+  if (a.drop_p > 0.f) {
+    float m[VEC];
+    dropout_scale<VEC>(a.drop_seed, a.drop_tag, ((uint64_t)n * a.HW + (uint64_t)p) * a.C + (uint64_t)cv * VEC, a.drop_p, m);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) dz[i] *= m[i];
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(1024) gn_bwd_reduce_vec_kernel(const GnBwdArgs a, int CV, int PL) {
+  extern __shared__ float sm[];   // mean[C], rstd[C], acc[2C]
+  float* mean_s = sm;
+  float* rstd_s = sm + a.C;
+  float* acc = sm + 2 * a.C;
+  const int n = blockIdx.y;
+  gn_channel_moments(a.stats, a.stats_ld, n, a.C, a.groups, a.HW, a.eps, mean_s, rstd_s);
+  for (int c = threadIdx.x; c < 2 * a.C; c += blockDim.x) acc[c] = 0.f;
+  __syncthreads();
+  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+  const int p0 = blockIdx.x * a.chunk, p1 = min(a.HW, p0 + a.chunk);
+  const T* x = (const T*)a.x + (int64_t)n * a.HW * a.x_ld + cv * VEC;
+  const T* da = (const T*)a.da + (int64_t)n * a.HW * a.da_ld + cv * VEC;
+  float mu[VEC], rs[VEC], g[VEC], b[VEC], s0[VEC], s1[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c = cv * VEC + i;
+    mu[i] = mean_s[c]; rs[i] = rstd_s[c]; g[i] = a.gamma[c]; b[i] = a.beta[c]; s0[i] = 0.f; s1[i] = 0.f;
+  }
+  for (int p = p0 + pl; p < p1; p += PL) {
+    float xh[VEC], dz[VEC];
+    gn_bwd_dz<T, VEC>(a, n, p, cv, x, da, mu, rs, g, b, xh, dz);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { s0[i] += dz[i]; s1[i] = fmaf(dz[i], xh[i], s1[i]); }
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    atomicAdd(&acc[2 * (cv * VEC + i)], s0[i]);
+    atomicAdd(&acc[2 * (cv * VEC + i) + 1], s1[i]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * a.C; c += blockDim.x) atomicAdd(&a.red[(int64_t)n * a.red_ld + c], (double)acc[c]);
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(1024) gn_bwd_apply_vec_kernel(const GnBwdArgs a, int accumulate, int CV, int PL) {
+  extern __shared__ float sm[];   // mean[C], rstd[C], ga[C], gb[C]
+  float* mean_s = sm;
+  float* rstd_s = sm + a.C;
+  float* ga = sm + 2 * a.C;
+  float* gb = sm + 3 * a.C;
+  const int n = blockIdx.y;
+  const int cpg = a.C / a.groups;
+  gn_channel_moments(a.stats, a.stats_ld, n, a.C, a.groups, a.HW, a.eps, mean_s, rstd_s);
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    const int g0 = (c / cpg) * cpg;
+    double A = 0.0, Bq = 0.0;
+    for (int j = 0; j < cpg; ++j) {
+      A += (double)a.gamma[g0 + j] * a.red[(int64_t)n * a.red_ld + 2 * (g0 + j)];
+      Bq += (double)a.gamma[g0 + j] * a.red[(int64_t)n * a.red_ld + 2 * (g0 + j) + 1];
+    }
+    const double m = (double)cpg * a.HW;
+    ga[c] = (float)(A / m);
+    gb[c] = (float)(Bq / m);
+  }
+  __syncthreads();
+  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+  const int p0 = blockIdx.x * a.chunk, p1 = min(a.HW, p0 + a.chunk);
+  const T* x = (const T*)a.x + (int64_t)n * a.HW * a.x_ld + cv * VEC;
+  const T* da = (const T*)a.da + (int64_t)n * a.HW * a.da_ld + cv * VEC;
+  T* dx = (T*)a.dx + (int64_t)n * a.HW * a.dx_ld + cv * VEC;
+  float mu[VEC], rs[VEC], g[VEC], b[VEC], A[VEC], Bq[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c = cv * VEC + i;
+    mu[i] = mean_s[c]; rs[i] = rstd_s[c]; g[i] = a.gamma[c]; b[i] = a.beta[c]; A[i] = ga[c]; Bq[i] = gb[c];
+  }
+  for (int p = p0 + pl; p < p1; p += PL) {
+    float xh[VEC], dz[VEC], v[VEC];
+    gn_bwd_dz<T, VEC>(a, n, p, cv, x, da, mu, rs, g, b, xh, dz);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] = rs[i] * (dz[i] * g[i] - A[i] - xh[i] * Bq[i]);
+    T* o = dx + (int64_t)p * a.dx_ld;
+    if (accumulate) {
+      float old[VEC];
+      VecLoad<T, VEC>::ld(o, old);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) v[i] += old[i];
+    }
+    VecLoad<T, VEC>::st(o, v);
+  }
+  if (blockIdx.x == 0) {
+    if (a.colsum) {
+      for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+        const double sx = a.stats[(int64_t)n * a.stats_ld + 2 * c];
+        const double sxh = (sx - (double)a.HW * mean_s[c]) * rstd_s[c];
+        const double v = (double)rstd_s[c] * ((double)a.gamma[c] * a.red[(int64_t)n * a.red_ld + 2 * c] - (double)a.HW * ga[c] - sxh * gb[c]);
+        a.colsum[(int64_t)n * a.colsum_ld + c] = (float)v;
+      }
+    }
+    if (n == 0 && a.dgamma) {
+      for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int i = 0; i < a.N; ++i) { s0 += a.red[(int64_t)i * a.red_ld + 2 * c]; s1 += a.red[(int64_t)i * a.red_ld + 2 * c + 1]; }
+        a.dgamma[c] += (float)s1;
+        a.dbeta[c] += (float)s0;
+      }
+    }
+  }
+}
+
+// vector width usable for (x, da[, dx]): 8 (bf16) / 4 (fp32) when widths, pitches and addresses allow 16-byte accesses
+static int gn_bwd_vec(int dt, int C, int x_ld, int da_ld, int dx_ld, const void* x, const void* da, const void* dx) {
+  const int want = dt == WSR_BF16 ? 8 : 4;
+  const bool ok = C % want == 0 && x_ld % want == 0 && da_ld % want == 0 && dx_ld % want == 0 && (((uintptr_t)x | (uintptr_t)da | (uintptr_t)dx) & 15) == 0 &&
+                  C / want <= 1024;
+  return ok ? want : 1;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // softmax backward: ds[r][c] = scale * p[r][c] * (dp[r][c] - sum_c' dp[r][c'] p[r][c'])
 // ------------------------------------------------------------------------------------------------------------------
@@ -508,10 +640,21 @@ extern "C" int wsr_gn_bwd_reduce(const void* x, int x_dtype, int N, int HW, int 
   int rc = gn_bwd_common(a, x, x_dtype, N, HW, C, x_ld, stats, stats_ld, gamma, beta, groups, eps, act, da, da_dtype, da_ld, drop_p,
                          drop_seed, drop_tag, red, red_ld);
   if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int vec = gn_bwd_vec(x_dtype, C, x_ld, da_ld, x_ld, x, da, x);
+  if (vec > 1 && (size_t)4 * C * sizeof(float) <= 48 * 1024) {
+    const int CV = C / vec, PL = CV >= 256 ? 1 : 256 / CV;
+    if (a.chunk < 4 * PL) a.chunk = 4 * PL < HW ? 4 * PL : HW;
+    dim3 grid((HW + a.chunk - 1) / a.chunk, N);
+    size_t smem = (size_t)4 * C * sizeof(float);
+    if (x_dtype == WSR_BF16) gn_bwd_reduce_vec_kernel<__nv_bfloat16, 8><<<grid, CV * PL, smem, st>>>(a, CV, PL);
+    else gn_bwd_reduce_vec_kernel<float, 4><<<grid, CV * PL, smem, st>>>(a, CV, PL);
+    WSR_LAUNCH_OK();
+    return WSR_OK;
+  }
   dim3 grid((HW + a.chunk - 1) / a.chunk, N);
   const int threads = C >= 256 ? 256 : ((C + 31) / 32) * 32;
   size_t smem = (size_t)2 * C * sizeof(float);
-  cudaStream_t st = (cudaStream_t)stream;
   if (x_dtype == WSR_BF16) gn_bwd_reduce_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(a);
   else gn_bwd_reduce_kernel<float><<<grid, threads, smem, st>>>(a);
   WSR_LAUNCH_OK();
@@ -531,6 +674,18 @@ extern "C" int wsr_gn_bwd_apply(const void* x, int x_dtype, int N, int HW, int C
   WSR_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), WSR_E_INVALID, "gn_bwd_apply: dgamma / dbeta must come together");
   WSR_REQUIRE(colsum == nullptr || colsum_ld >= C, WSR_E_INVALID, "gn_bwd_apply: colsum pitch");
   a.dx = dx; a.dx_ld = dx_ld; a.dgamma = dgamma; a.dbeta = dbeta; a.colsum = colsum; a.colsum_ld = colsum_ld;
+  const int vec = gn_bwd_vec(x_dtype, C, x_ld, da_ld, dx_ld, x, da, dx);
+  if (vec > 1 && (size_t)4 * C * sizeof(float) <= 48 * 1024) {
+    const int CV = C / vec, PL = CV >= 256 ? 1 : 256 / CV;
+    if (a.chunk < 4 * PL) a.chunk = 4 * PL < HW ? 4 * PL : HW;
+    dim3 grid((HW + a.chunk - 1) / a.chunk, N);
+    size_t smem = (size_t)4 * C * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_dtype == WSR_BF16) gn_bwd_apply_vec_kernel<__nv_bfloat16, 8><<<grid, CV * PL, smem, st>>>(a, accumulate, CV, PL);
+    else gn_bwd_apply_vec_kernel<float, 4><<<grid, CV * PL, smem, st>>>(a, accumulate, CV, PL);
+    WSR_LAUNCH_OK();
+    return WSR_OK;
+  }
   dim3 grid((HW + a.chunk - 1) / a.chunk, N);
   const int threads = C >= 256 ? 256 : ((C + 31) / 32) * 32;
   size_t smem = (size_t)4 * C * sizeof(float);

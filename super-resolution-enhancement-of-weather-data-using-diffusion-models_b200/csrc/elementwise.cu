@@ -84,6 +84,73 @@ __global__ void pack_convT_weight_kernel(const float* __restrict__ w, int Cin, i
   st_dt(dst, i, dt, w[((int64_t)ci * Cout + co) * taps + t]);
 }
 
+// One launch re-packs EVERY weight of a plan after an optimizer step (the training loop's refresh): a device-side job
+// table lists (source parameter, destination buffer, layout kind); one thread owns one (row, column) pair of one job
+// and writes all of its taps, so the 36-byte tap vector of the OIHW source is read once and every destination plane is
+// written coalesced along the column index.
+__device__ __forceinline__ int upsample_dgrad_lo(int r) { return r == 0 ? 2 : (r == 1 ? 1 : 0); }          // r = row offset + 1
+__device__ __forceinline__ int upsample_dgrad_hi(int r) { return r == 0 ? 2 : (r == 1 ? 2 : (r == 2 ? 1 : 0)); }
+
+__global__ void repack_batch_kernel(const WsrPackJob* __restrict__ jobs, int njobs, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].first_unit <= i) lo = mid; else hi = mid - 1;
+    }
+    const WsrPackJob j = jobs[lo];
+    int64_t u = i - j.first_unit;
+    if (j.kind == WSR_PACK_COPY) {
+      float v = j.src[u];
+      if (j.src2) v += j.src2[u];
+      st_dt(j.dst, u, j.dst_dtype, v);
+      continue;
+    }
+    const int ci = (int)(u % j.Cin_pad), co = (int)(u / j.Cin_pad);
+    const bool valid = co < j.Cout && ci < j.Cin;
+    const int T = j.taps;
+    const float* wp = j.src + (j.transposed ? ((int64_t)ci * j.Cout + co) : ((int64_t)co * j.Cin + ci)) * T;
+    const int64_t plane = (int64_t)j.Cout_pad * j.Cin_pad;
+    const int64_t o = (int64_t)co * j.Cin_pad + ci;
+    if (j.kind == WSR_PACK_CONV) {
+      for (int t = 0; t < T; ++t) st_dt(j.dst, t * plane + o, j.dst_dtype, valid ? wp[j.transposed ? T - 1 - t : t] : 0.f);
+    } else {
+      float w9[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) w9[t] = valid ? wp[t] : 0.f;
+      if (j.kind == WSR_PACK_VMERGE) {            // dst[(kx*192 + b*64 + co)*Cin_pad + ci] = w'[co][ci][ky = 2-b][kx]
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) {
+            int t = (2 - b) * 3 + kx;
+            st_dt(j.dst, ((int64_t)(kx * 192 + b * 64 + co)) * j.Cin_pad + ci, j.dst_dtype, w9[j.transposed ? 8 - t : t]);
+          }
+      } else if (j.kind == WSR_PACK_UPSAMPLE) {   // see pack_upsample_weight_kernel
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          int ph = t >> 2, a = (t >> 1) & 1, b = t & 1, py = ph >> 1, px = ph & 1;
+          int ky0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), ky1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+          int kx0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), kx1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+          float v = 0.f;
+          for (int ky = ky0; ky <= ky1; ++ky)
+            for (int kx = kx0; kx <= kx1; ++kx) v += w9[ky * 3 + kx];
+          st_dt(j.dst, t * plane + o, j.dst_dtype, v);
+        }
+      } else {                                    // WSR_PACK_UPSAMPLE_DGRAD: 4x4 taps, tap (r, s) = sum of the 3x3 taps reaching it
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          int r = t >> 2, s = t & 3;
+          float v = 0.f;
+          for (int ky = upsample_dgrad_lo(r); ky <= upsample_dgrad_hi(r); ++ky)
+            for (int kx = upsample_dgrad_lo(s); kx <= upsample_dgrad_hi(s); ++kx) v += w9[ky * 3 + kx];
+          st_dt(j.dst, t * plane + o, j.dst_dtype, v);
+        }
+      }
+    }
+  }
+}
+
 __global__ void cast_kernel(const void* src, int sdt, void* dst, int ddt, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) st_dt(dst, i, ddt, ld_dt(src, i, sdt));
@@ -114,35 +181,6 @@ __global__ void axpby_kernel(const void* x, int xdt, int x_ld, float a, const vo
 // GroupNorm: per-(image, channel) sums, then normalise (+ activation)
 // thread layout: blockDim = CV * PL; thread t owns channel vector t % CV and pixel lane t / CV.
 // ------------------------------------------------------------------------------------------------------------------
-template <typename T, int VEC> struct VecLoad;
-template <> struct VecLoad<float, 4> {
-  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) { float4 q = *(const float4*)p; v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
-  static __device__ __forceinline__ void st(float* p, const float (&v)[4]) { *(float4*)p = make_float4(v[0], v[1], v[2], v[3]); }
-};
-template <> struct VecLoad<float, 1> {
-  static __device__ __forceinline__ void ld(const float* p, float (&v)[1]) { v[0] = *p; }
-  static __device__ __forceinline__ void st(float* p, const float (&v)[1]) { *p = v[0]; }
-};
-template <> struct VecLoad<__nv_bfloat16, 8> {
-  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[8]) {
-    uint4 q = *(const uint4*)p;
-    const __nv_bfloat162* h = (const __nv_bfloat162*)&q;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
-  }
-  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[8]) {
-    uint4 q;
-    __nv_bfloat162* h = (__nv_bfloat162*)&q;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    *(uint4*)p = q;
-  }
-};
-template <> struct VecLoad<__nv_bfloat16, 1> {
-  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[1]) { v[0] = __bfloat162float(*p); }
-  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[1]) { *p = __float2bfloat16_rn(v[0]); }
-};
-
 template <typename T, int VEC>
 __global__ void gn_stats_kernel(const T* __restrict__ x, int HW, int C, int ld, int CV, int PL, int chunk, double* __restrict__ stats, int stats_ld) {
   extern __shared__ float sm[];   // [PL][C][2]
@@ -529,6 +567,15 @@ extern "C" int wsr_pack_convT_weight(const float* w, int Cin, int Cout, int KH, 
   WSR_REQUIRE(w && dst && valid_dtype(dst_dtype) && Cout > 0 && Cin > 0 && KH > 0 && KW > 0, WSR_E_INVALID, "pack_convT_weight: bad argument");
   int64_t total = (int64_t)KH * KW * Cout * Cin;
   pack_convT_weight_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, Cin, Cout, KH * KW, dst, dst_dtype, total);
+  WSR_LAUNCH_OK();
+  return WSR_OK;
+}
+
+extern "C" int wsr_repack_batch(const WsrPackJob* jobs_device, int njobs, int64_t total_units, void* stream) {
+  WSR_REQUIRE(jobs_device && njobs > 0 && total_units > 0, WSR_E_INVALID, "repack_batch: bad argument");
+  int64_t blocks = (total_units + 255) / 256;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  repack_batch_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(jobs_device, njobs, total_units);
   WSR_LAUNCH_OK();
   return WSR_OK;
 }

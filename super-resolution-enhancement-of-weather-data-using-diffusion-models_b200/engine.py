@@ -99,6 +99,8 @@ class Engine:
         self._keep = []          # tensors that must outlive async launches
         self._pack_cache = {}    # key -> packed buffers: re-packing after an optimizer step writes the SAME device buffers,
                                  # so pointers recorded in launch lists stay valid
+        self.jobs = None         # when a list: every pack_* call also appends its WsrPackJob description (batched refresh)
+        self.jobs_ok = True      # False once a pack read from a temporary (no stable source address): batching impossible
         self.rec = None          # when a list: every launch made through call() is appended as (fn, args) for replay()
         self.prof = None         # list of (name, flops, bytes, start_event, end_event) when profiling
         self.prof_detail = False
@@ -169,17 +171,39 @@ class Engine:
             a.st, a.st_off, a.st_ld = stats, stats.alloc(N * ld * 2), ld * 2
         return a
 
-    def f32(self, t):
-        return t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+    def f32(self, t, track=True):
+        r = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        if track and self.jobs is not None and r.data_ptr() != t.data_ptr():
+            self.jobs_ok = False     # a converted COPY of a parameter would go stale under the batched refresh
+        return r
 
     # ---- packing ---------------------------------------------------------------------------------------------------
     def _src_key(self, t):
         return (t.data_ptr(), tuple(t.shape), tuple(t.stride()))
 
-    def pack_conv(self, weight, bias=None, cin_pad=None, rows=None, key=None):
+    def _job(self, kind, src, dst, dt, Cout, Cin, taps, Cout_pad, Cin_pad, transposed=0, src2=0, stable=True):
+        if self.jobs is None:
+            return
+        if not stable:
+            self.jobs_ok = False
+        units = Cout if kind == nat.PACK_COPY else Cout_pad * Cin_pad
+        self.jobs.append((kind, src, src2, dst, dt, Cout, Cin, taps, Cout_pad, Cin_pad, transposed, units))
+
+    def job_table(self):
+        """Device copy of the recorded jobs -> (tensor holding the WsrPackJob array, njobs, total units)."""
+        arr = (nat.PackJob * len(self.jobs))()
+        first = 0
+        for a, (kind, src, src2, dst, dt, Cout, Cin, taps, Cout_pad, Cin_pad, transposed, units) in zip(arr, self.jobs):
+            a.src, a.src2, a.dst, a.first_unit = src, src2 or None, dst, first
+            a.kind, a.transposed, a.dst_dtype, a.Cout, a.Cin, a.taps, a.Cout_pad, a.Cin_pad = kind, transposed, dt, Cout, Cin, taps, Cout_pad, Cin_pad
+            first += units
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        return host.to(self.device), len(self.jobs), first
+
+    def pack_conv(self, weight, bias=None, cin_pad=None, rows=None, key=None, src=None, job_kind=None):
         """weight: OIHW fp32 parameter (or a tensor derived from one; then pass ``key`` = a stable identity for the cache,
         e.g. ('dgrad', param.data_ptr()), because a derived temporary has a new address on every call)."""
-        w = self.f32(weight)
+        w = self.f32(weight, track=False)
         Cout, Cin, KH, KW = w.shape
         key = ("conv", key if key is not None else self._src_key(weight), cin_pad, rows)
         pc = self._pack_cache.get(key)
@@ -193,20 +217,43 @@ class Engine:
             if self.use_tc and KH == 3 and KW == 3 and Cout <= 64 and pc.Cin_pad % 64 == 0:
                 pc.w_vm = self.empty((3, 192, pc.Cin_pad))
         nat.call("wsr_pack_conv_weight", w.data_ptr(), Cout, Cin, KH, KW, pc.w.data_ptr(), self.dt, pc.rows, pc.Cin_pad, self.stream)
+        # the batched refresh reads the PARAMETER: either `weight` itself (src None) or the parameter that `weight` is the
+        # data-gradient view of (src = (parameter address, 1))
+        jsrc, jtr = src if src is not None else (w.data_ptr(), 0)
+        stable = src is not None or w.data_ptr() == weight.data_ptr()
+        self._job(nat.PACK_CONV if job_kind is None else job_kind, jsrc, pc.w.data_ptr(), self.dt, Cout, Cin,
+                  9 if job_kind is not None else KH * KW, pc.rows, pc.Cin_pad, jtr, stable=stable)
         if pc.w_vm is not None:
             nat.call("wsr_pack_conv_weight_vmerge", w.data_ptr(), Cout, Cin, pc.w_vm.data_ptr(), self.dt, pc.Cin_pad, self.stream)
+            self._job(nat.PACK_VMERGE, jsrc, pc.w_vm.data_ptr(), self.dt, Cout, Cin, 9, 64, pc.Cin_pad, jtr, stable=stable)
         pc.bias = None if bias is None else self.f32(bias)
         self._keep.append(w)
         return pc
 
-    def static_f32(self, key, value):
-        """fp32 device tensor with a stable address holding ``value`` (a tensor computed on the fly, e.g. a sum of two biases)."""
+    def static_f32(self, key, value, parts=None, addend=None):
+        """fp32 device tensor with a stable address holding ``value`` (a tensor computed on the fly).  For the batched
+        refresh the caller says how ``value`` derives from parameters: ``parts`` = the tensors it is the dim-0 concatenation
+        of, or ``addend`` = (a, b) with value = a + b."""
         buf = self._pack_cache.get(("f32", key))
         v = self.f32(value)
         if buf is None:
             buf = self._pack_cache[("f32", key)] = v.clone()
         else:
             buf.copy_(v)
+        if self.jobs is not None:
+            if addend is not None:
+                a, b = addend
+                ok = a.is_contiguous() and b.is_contiguous() and a.dtype == torch.float32 and b.dtype == torch.float32
+                self._job(nat.PACK_COPY, a.data_ptr(), buf.data_ptr(), nat.F32, a.numel(), 1, 1, 1, 1, 0, src2=b.data_ptr(), stable=ok)
+            elif parts is not None:
+                off = 0
+                for t in parts:
+                    ok = t.is_contiguous() and t.dtype == torch.float32
+                    self._job(nat.PACK_COPY, t.data_ptr(), buf.data_ptr() + 4 * off, nat.F32, t.numel(), 1, 1, 1, 1, 0, stable=ok)
+                    off += t.numel()
+                assert off == buf.numel()
+            else:
+                self.jobs_ok = False
         return buf
 
     def pack_upsample_conv(self, weight, bias=None):
@@ -224,6 +271,7 @@ class Engine:
             pc.Cout, pc.Cin, pc.k, pc.Cin_pad, pc.rows, pc.merged_up = Cout, Cin, 3, Cin, Cout, True
             pc.w = self.empty((16, Cout, Cin))
         nat.call("wsr_pack_upsample_weight", w.data_ptr(), Cout, Cin, pc.w.data_ptr(), self.dt, Cout, Cin, self.stream)
+        self._job(nat.PACK_UPSAMPLE, w.data_ptr(), pc.w.data_ptr(), self.dt, Cout, Cin, 9, Cout, Cin, stable=w.data_ptr() == weight.data_ptr())
         pc.bias = None if bias is None else self.f32(bias)
         self._keep.append(w)
         return pc
@@ -236,6 +284,7 @@ class Engine:
         if out is None:
             out = self._pack_cache[key] = self.empty(tuple(w.shape))
         nat.call("wsr_cast", w.data_ptr(), nat.F32, out.data_ptr(), self.dt, w.numel(), self.stream)
+        self._job(nat.PACK_COPY, w.data_ptr(), out.data_ptr(), self.dt, w.numel(), 1, 1, 1, 1, stable=w.data_ptr() == weight2d.data_ptr())
         self._keep.append(w)
         return out
 

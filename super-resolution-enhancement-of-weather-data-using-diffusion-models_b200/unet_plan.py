@@ -238,7 +238,8 @@ class UNetPlan:
                 r.conv2 = e.pack_conv(conv2.weight, conv2.bias)
                 if r.has_res_conv:
                     r.resw = e.pack_conv(rb.res_conv.weight, None)
-                    r.bias2 = e.static_f32(("bias2", conv2.bias.data_ptr()), conv2.bias + rb.res_conv.bias)
+                    r.bias2 = e.static_f32(("bias2", conv2.bias.data_ptr()), conv2.bias + rb.res_conv.bias,
+                                           addend=(conv2.bias.detach(), rb.res_conv.bias.detach()))
                 lin = rb.noise_func.noise_func[0]
                 proj_w.append(e.f32(lin.weight)); proj_b.append(e.f32(lin.bias))
                 if r.attn:
@@ -291,11 +292,12 @@ class UNetPlan:
                 cp = self.net.cond_proj
                 self.cp_w = e.empty((64, cp.out_channels, cp.in_channels))
                 w = e.f32(cp.weight)
+                e.jobs_ok = False        # no batched kind for the transposed-convolution packing
                 nat.call("wsr_pack_convT_weight", w.data_ptr(), cp.in_channels, cp.out_channels, 8, 8, self.cp_w.data_ptr(), e.dt, e.stream)
                 self.cp_b = e.f32(cp.bias)
                 e._keep.append(w)
-            self.proj_w = e.static_f32(("proj_w", id(self)), torch.cat(proj_w, 0))
-            self.proj_b = e.static_f32(("proj_b", id(self)), torch.cat(proj_b, 0))
+            self.proj_w = e.static_f32(("proj_w", id(self)), torch.cat(proj_w, 0), parts=proj_w)
+            self.proj_b = e.static_f32(("proj_b", id(self)), torch.cat(proj_b, 0), parts=proj_b)
             assert self.proj_w.shape == (self.P, self.inner), (self.proj_w.shape, self.P)
         self.proj_table = None
         # no host synchronisation: the temporaries were consumed by kernels launched on torch's current stream, and the
@@ -315,6 +317,7 @@ class UNetPlan:
             pc.Cout, pc.Cin, pc.k, pc.Cin_pad, pc.rows, pc.bias = Cout, Cin, KH, Cin, Cout, None
             pc.w = e.empty((KH * KW, Cout, Cin), torch.float32)
         nat.call("wsr_pack_conv_weight", w.data_ptr(), Cout, Cin, KH, KW, pc.w.data_ptr(), nat.F32, Cout, Cin, e.stream)
+        e._job(nat.PACK_CONV, w.data_ptr(), pc.w.data_ptr(), nat.F32, Cout, Cin, KH * KW, Cout, Cin, stable=w.data_ptr() == weight.data_ptr())
         e._keep.append(w)
         return pc
 

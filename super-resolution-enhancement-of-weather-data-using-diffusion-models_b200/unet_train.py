@@ -46,6 +46,8 @@ class UNetTrainPlan(UNetPlan):
         self._lists = {}
         self._n_bwd = 0
         self.replay_enabled = os.environ.get("WSR_NO_REPLAY") is None
+        self._jobtab = None            # (device WsrPackJob table, njobs, total units, parameter-address signature)
+        self.batched_refresh = os.environ.get("WSR_NO_BATCHED_REFRESH") is None
         self.fuse_gn = False           # the backward pass reads the normalised activations (a1, a2): keep them materialised
         super().__init__(net, batch, device, precision, strict_tc)
         self.eng.no_fused_attention = False
@@ -159,6 +161,10 @@ class UNetTrainPlan(UNetPlan):
                 p.data = view
         self._pflat = pflat
         self._wver = None
+        # the packed buffers, the job table and the launch lists were keyed on the old parameter addresses
+        self.eng._pack_cache.clear()
+        self._jobtab = None
+        self._lists.clear()
         return pflat
 
     def parameters_are_flat(self):
@@ -179,6 +185,7 @@ class UNetTrainPlan(UNetPlan):
         e, B = self.eng, self.B
         self._gbuf = {}
         self._gtensors = []
+        self._garena = None
         red = self._red_sizes = []
 
         def gn_slot(c):
@@ -216,6 +223,7 @@ class UNetTrainPlan(UNetPlan):
         g = self._gbuf.get(key)
         if g is None:
             g = torch.zeros_like(a.buf)
+            self._garena = None        # a late buffer lives outside the arena: fall back to per-buffer clearing
             self._gbuf[key] = g
             self._gtensors.append(g)
         return Act(g, a.N, a.H, a.W, a.C, a.ld, a.coff, a.dt)
@@ -224,14 +232,36 @@ class UNetTrainPlan(UNetPlan):
     # weights: forward packs + data-gradient packs
     # ------------------------------------------------------------------------------------------------------------------
     def refresh_weights(self):
+        """Re-pack every forward and data-gradient weight from the fp32 parameters.  The first call goes through the
+        per-tensor pack entry points and records a WsrPackJob table; as long as the parameters keep their addresses, later
+        calls (after every optimizer step) are ONE ``wsr_repack_batch`` launch writing the same destination buffers."""
         v = self._weights_version()
         if v == self._wver:
             return
+        e = self.eng
+        sig = tuple(p.data_ptr() for p in self.net.parameters())
+        if self._jobtab is not None and self._jobtab[3] == sig and self.batched_refresh:
+            tab, n, total, _ = self._jobtab
+            e.call("wsr_repack_batch", tab.data_ptr(), n, total, e.stream)
+            self._wver = v
+            self.proj_table = None
+            return
+        e.jobs, e.jobs_ok = [], True
+        try:
+            self._refresh_eager()
+            if e.jobs_ok and e.jobs:
+                self._jobtab = e.job_table() + (sig,)
+            else:
+                self._jobtab = None
+        finally:
+            e.jobs = None
+
+    def _refresh_eager(self):
         super().refresh_weights()
         e = self.eng
         with torch.no_grad():
             def dg(weight):
-                return e.pack_conv(T.dgrad_weight(weight), None, key=("dgrad",) + e._src_key(weight))
+                return e.pack_conv(T.dgrad_weight(weight), None, key=("dgrad",) + e._src_key(weight), src=(weight.data_ptr(), 1))
 
             for r in self._res_records():
                 rb = r.mod.res_block
@@ -254,7 +284,9 @@ class UNetTrainPlan(UNetPlan):
                     r.ca.dwout = dg(m.out.weight)
             for r in self.ups:
                 if r.kind == "up":
-                    r.dconv = e.pack_conv(T.upsample_dgrad_weight(r.mod.conv.weight), None, key=("updgrad",) + e._src_key(r.mod.conv.weight))
+                    w = r.mod.conv.weight
+                    r.dconv = e.pack_conv(T.upsample_dgrad_weight(w), None, key=("updgrad",) + e._src_key(w),
+                                          src=(w.data_ptr(), 1), job_kind=nat.PACK_UPSAMPLE_DGRAD)
             self.dfinal = dg(self.net.final_conv.block[3].weight)
         e._keep.clear()
 
@@ -411,7 +443,26 @@ class UNetTrainPlan(UNetPlan):
             lst, e.rec = e.rec, None
         if record:
             self._lists["bwd"], self._lists["bwd_key"] = lst, key
+        elif self._garena is None and self._gtensors:
+            self._consolidate_gbufs()
         return self.gflat
+
+    def _consolidate_gbufs(self):
+        """After the first backward pass every activation-gradient buffer exists: move them into ONE arena so that the
+        per-step clearing is a single memset instead of ~150."""
+        sizes = [(g.numel() * g.element_size() + 255) // 256 * 256 for g in self._gtensors]
+        arena = torch.zeros((sum(sizes),), device=self.eng.device, dtype=torch.uint8)
+        new, off = {}, 0
+        old_to_new = {}
+        for g, nb in zip(self._gtensors, sizes):
+            v = arena[off:off + g.numel() * g.element_size()].view(g.dtype).view(g.shape)
+            old_to_new[g.data_ptr()] = v
+            off += nb
+        for key, g in self._gbuf.items():
+            new[key] = old_to_new[g.data_ptr()]
+        self._gbuf = new
+        self._gtensors = list(new.values())
+        self._garena = arena
 
     def _ptr_sig(self):
         return tuple(p.data_ptr() for p in self.param_order)
@@ -424,8 +475,11 @@ class UNetTrainPlan(UNetPlan):
         e.call("wsr_fill_zero", self.gflat.data_ptr(), self.gflat.numel() * 4, st)
         e.call("wsr_fill_zero", self.red.data_ptr(), self.red.numel() * 8, st)
         e.call("wsr_fill_zero", self.dproj.data_ptr(), self.dproj.numel() * 4, st)
-        for g in self._gtensors:
-            e.call("wsr_fill_zero", g.data_ptr(), g.numel() * g.element_size(), st)
+        if self._garena is not None:
+            e.call("wsr_fill_zero", self._garena.data_ptr(), self._garena.numel(), st)
+        else:
+            for g in self._gtensors:
+                e.call("wsr_fill_zero", g.data_ptr(), g.numel() * g.element_size(), st)
         e.call("wsr_nchw_to_nhwc", d_eps.data_ptr(), B, self.C_img, self.H, self.W, self.deps.ptr, self.deps.dt, self.deps.ld, st)
 
         # head: eps = conv(swish(GN(x_last)))

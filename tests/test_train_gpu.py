@@ -403,7 +403,10 @@ def test_optimize_parameters_decreases_loss_and_flat_adam():
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_recorded_launch_lists_reproduce_the_eager_step(precision):
     """The forward / backward launch lists are recorded on the second call and replayed from the third: the same batch must
-    give the same loss and gradients in all three modes (fp32 atomics reorder -> 1e-5), and the lists must really be used."""
+    give the same loss and gradients in all three modes, and the lists must really be used.  Tolerance: the GroupNorm /
+    bias reductions use atomics, so the summation order differs from run to run: 1e-5 in fp32; in bf16 a last-bit change
+    of a reduced statistic flips bf16 roundings of whole activation-gradient tensors downstream (measured 1.4e-3 on the whole
+    gradient between two runs of the SAME mode; bf16 eps = 3.9e-3) -> 5e-3."""
     g, spec = load_golden("resdiff_grad_small"), CASES["resdiff_grad_small"]
     net, diff = _build(spec["cfg"], spec["seed"], precision)
     plan = net.train_plan(g["hr"].shape[0], torch.device("cuda:0"))
@@ -416,4 +419,60 @@ def test_recorded_launch_lists_reproduce_the_eager_step(precision):
     assert "fwd" in plan._lists and "bwd" in plan._lists and len(plan._lists["bwd"]) > 300
     for loss, gf in outs[1:]:
         assert abs(loss - outs[0][0]) <= 1e-6 * abs(outs[0][0])
-        assert rel_l2(gf, outs[0][1]) < (1e-5 if precision == "fp32" else 1e-3)
+        assert rel_l2(gf, outs[0][1]) < (1e-5 if precision == "fp32" else 5e-3)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_batched_weight_refresh_is_bit_identical_to_the_per_tensor_packs(precision):
+    """After an optimizer step the plan re-packs all forward and data-gradient weights with ONE wsr_repack_batch launch
+    (job table recorded on the first refresh).  Every destination buffer must equal, bit for bit, what the per-tensor pack
+    entry points produce from the same parameters."""
+    g, spec = load_golden("resdiff_grad_small"), CASES["resdiff_grad_small"]
+    net, diff = _build(spec["cfg"], spec["seed"], precision)
+    plan = net.train_plan(g["hr"].shape[0], torch.device("cuda:0"))
+    opt = wsr.sub("autograd_glue").FusedAdam(list(diff.parameters()), lr=1e-4)
+    opt.attach_flat(plan)
+    plan.refresh_weights()
+    assert plan._jobtab is not None and plan._jobtab[1] > 100
+    cache = plan.eng._pack_cache
+
+    def snapshot():
+        torch.cuda.synchronize()
+        out = {}
+        for k, v in cache.items():
+            if isinstance(v, torch.Tensor):
+                out[k] = v.clone()
+            else:
+                out[(k, "w")] = v.w.clone()
+                if v.w_vm is not None:
+                    out[(k, "vm")] = v.w_vm.clone()
+        return out
+
+    torch.manual_seed(5)
+    with torch.no_grad():
+        for p in diff.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    before = nat.launches
+    plan.refresh_weights()                       # batched
+    assert nat.launches - before == 1
+    batched = snapshot()
+    for v in cache.values():                     # poison, then redo through the per-tensor path
+        (v if isinstance(v, torch.Tensor) else v.w).fill_(7.0)
+    plan.batched_refresh = False
+    plan._wver = None
+    plan.refresh_weights()
+    eager = snapshot()
+    assert batched.keys() == eager.keys() and len(eager) > 100
+    for k in eager:
+        assert torch.equal(batched[k], eager[k]), k
+    # and the poisoned buffers are rewritten completely by the batched path too
+    for v in cache.values():
+        (v if isinstance(v, torch.Tensor) else v.w).fill_(7.0)
+        if not isinstance(v, torch.Tensor) and v.w_vm is not None:
+            v.w_vm.fill_(7.0)
+    plan.batched_refresh = True
+    plan._wver = None
+    plan.refresh_weights()
+    again = snapshot()
+    for k in eager:
+        assert torch.equal(again[k], eager[k]), k
