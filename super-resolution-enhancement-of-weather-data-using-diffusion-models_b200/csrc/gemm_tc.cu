@@ -107,7 +107,12 @@ template <int BLOCK_N, bool HALO, int ROWS, bool VM = false> struct TcCfg {
   static constexpr int kTmemCols = next_pow2(2 * kAccCols);                // power of two for 32..512
   static_assert(kTmemCols <= 512, "TMEM budget");
   static constexpr int kBsumBytes = HALO ? 16 * BLOCK_N : 0;                // per epilogue warp: bias + time-embedding row of its columns
-  static constexpr int kSmemBytes = kSmemData + 1024 /*align slack*/ + 512 /*barriers*/ + kBsumBytes;
+  // per epilogue warp: a 16-row x 64-byte staging buffer through which residual loads and output stores are re-shaped from
+  // "one row per lane" (32 different 128-byte lines per instruction) to "four lanes per row" (8 lines per instruction);
+  // the ROWS = 4 configuration has no shared memory left for it
+  static constexpr int kStgBytes = (HALO && ROWS >= 4) ? 0 : 8 * 1024;
+  static constexpr int kSmemBytes = kSmemData + 1024 /*align slack*/ + 512 /*barriers*/ + kBsumBytes + kStgBytes;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
   // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
   static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 };
@@ -128,12 +133,15 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
 // ------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------------
-template <int BLOCK_N, bool HALO, int ROWS, bool FUSE = false, bool VM = false>
+template <int BLOCK_N, bool HALO, int ROWS, bool FUSE = false, bool VM = false, bool STG = false>
 __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  // STG: the epilogue moves residual loads and output stores through a per-warp shared-memory staging buffer (see TcCfg::kStgBytes);
+  // the host selects it only when stage_preconditions() hold (bf16 output / residual, unit channel stride, 16-byte aligned rows)
   // register budget: 10 warps = 3 warps on the fullest scheduler, 16384 / 3 / 32 -> 168 registers per thread at most
   static_assert(!FUSE || HALO, "the fused-GroupNorm input path exists in halo mode only");
   static_assert(!VM || (HALO && BLOCK_N == 64), "vertical tap merge: halo mode, N = 64");
   using Cfg = TcCfg<BLOCK_N, HALO, ROWS, VM>;
+  static_assert(!STG || Cfg::kStgBytes > 0, "no staging buffer in this configuration");
   constexpr int kHaloStage = Cfg::kHaloStage;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -476,6 +484,11 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
     float st_s[kChunksPerWarp], st_q[kChunksPerWarp];
 #pragma unroll
     for (int i = 0; i < kChunksPerWarp; ++i) { st_s[i] = 0.f; st_q[i] = 0.f; }
+    // STG: statistics are read back from the staged bf16 tile two columns at a time: lane l accumulates columns
+    // 2*(l & 15), +1 over the rows of parity l >> 4 (st_s / st_q hold the even column, st_s1 / st_q1 the odd one)
+    float st_s1[STG ? kChunksPerWarp : 1], st_q1[STG ? kChunksPerWarp : 1];
+#pragma unroll
+    for (int i = 0; i < (STG ? kChunksPerWarp : 1); ++i) { st_s1[i] = 0.f; st_q1[i] = 0.f; }
     // kRegStats (the warp owns ONE 32-column chunk, i.e. N = 64): only the FIRST exchange round of the transpose-reduce
     // runs per output row; its 16 partial sums per statistic are accumulated in registers and the remaining four rounds
     // run once per image.  (The full per-row reduce was ~half of all issue slots of the N = 64 kernels and left their
@@ -506,6 +519,21 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
           st_s[0] = rs_s[0]; st_q[0] = rs_q[0];
 #pragma unroll
           for (int j = 0; j < 16; ++j) { rs_s[j] = 0.f; rs_q[j] = 0.f; }
+        }
+      }
+      if constexpr (STG) {
+        if (st_img >= 0) {
+#pragma unroll
+          for (int i = 0; i < kChunksPerWarp; ++i) {
+            // row parities: lane l + lane l ^ 16; then lane j picks column j = component j & 1 of pair j >> 1
+            const float a0 = st_s[i] + __shfl_xor_sync(0xffffffffu, st_s[i], 16), a1 = st_s1[i] + __shfl_xor_sync(0xffffffffu, st_s1[i], 16);
+            const float b0 = st_q[i] + __shfl_xor_sync(0xffffffffu, st_q[i], 16), b1 = st_q1[i] + __shfl_xor_sync(0xffffffffu, st_q1[i], 16);
+            const float c0 = __shfl_sync(0xffffffffu, a0, lane >> 1), c1 = __shfl_sync(0xffffffffu, a1, lane >> 1);
+            const float d0 = __shfl_sync(0xffffffffu, b0, lane >> 1), d1 = __shfl_sync(0xffffffffu, b1, lane >> 1);
+            st_s[i] = (lane & 1) ? c1 : c0;
+            st_q[i] = (lane & 1) ? d1 : d0;
+            st_s1[i] = 0.f; st_q1[i] = 0.f;
+          }
         }
       }
       if (st_img >= 0 && st_img < p.M3) {
@@ -576,37 +604,43 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * Cfg::kAccCols + rr * BLOCK_N + ch * 32), v);
         const int n0 = nt * BLOCK_N + ch * 32;
-        float f[32];
+        if constexpr (STG) {
+          // ---- staged epilogue: 32 full bf16 columns; residual loads and output stores go through the warp's staging buffer
+          // with four lanes per row (8 lines per instruction instead of 32) ----
+          uint8_t* stg = smem + Cfg::kSmemData + 512 + Cfg::kBsumBytes + warp * 1024;
+          const int my16 = lane & 15;                                   // my row inside a 16-row half
+          const int mysw = (my16 >> 1) & 3;
+          const int sr = lane >> 2, sq = lane & 3;                      // store layout: 8 rows x four 16-byte columns per pass
+          // the residual does not depend on the accumulator: fetch it first so that its latency hides behind the TMEM load
+          uint4 rv[4];
+          if (p.res) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = 0.f;
-        if (row_ok && n0 < p.Ncols) {
-          const bool full = (n0 + 32 <= p.Ncols);
+            for (int hj = 0; hj < 4; ++hj) {
+              const int src = 8 * hj + sr;
+              const long long rb = __shfl_sync(0xffffffffu, rbase, src);
+              const int ok = __shfl_sync(0xffffffffu, (int)row_ok, src);
+              rv[hj] = make_uint4(0u, 0u, 0u, 0u);
+              if (ok) rv[hj] = __ldg((const uint4*)((const __nv_bfloat16*)p.res + rb + n0 + sq * 8));
+            }
+          }
+          float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if constexpr (HALO) {
             const float4* b4 = (const float4*)(bs + ci * 32);
 #pragma unroll
             for (int q = 0; q < 8; ++q) { float4 t4 = b4[q]; f[4 * q] += t4.x; f[4 * q + 1] += t4.y; f[4 * q + 2] += t4.z; f[4 * q + 3] += t4.w; }
-          } else if (full) {
-            // 32 consecutive columns: bias / time-embedding row as independent 16-byte loads (same address in every
-            // lane -> one broadcast transaction each), issued back to back
+          } else {
             if (p.bias) {
               const float4* b4 = (const float4*)(p.bias + n0);
 #pragma unroll
               for (int q = 0; q < 8; ++q) { float4 t4 = __ldg(b4 + q); f[4 * q] += t4.x; f[4 * q + 1] += t4.y; f[4 * q + 2] += t4.z; f[4 * q + 3] += t4.w; }
             }
-            if (rowvec) {
+            if (rowvec && row_ok) {
               const float4* r4 = (const float4*)(rowvec + n0);
 #pragma unroll
               for (int q = 0; q < 8; ++q) { float4 t4 = __ldg(r4 + q); f[4 * q] += t4.x; f[4 * q + 1] += t4.y; f[4 * q + 2] += t4.z; f[4 * q + 3] += t4.w; }
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.Ncols) {
-                if (p.bias) f[j] += __ldg(p.bias + n0 + j);
-                if (rowvec) f[j] += __ldg(rowvec + n0 + j);
-              }
           }
           if (p.act != WSR_ACT_NONE) {
 #pragma unroll
@@ -616,87 +650,193 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
           }
-          const bool vec_ok = full && p.o_sc == 1 && ((obase + n0) & 7) == 0 && (((uintptr_t)p.out) & 15) == 0;
           if (p.res) {
-            if (full && p.r_sc == 1 && p.res_dtype == WSR_BF16 && ((rbase + n0) & 7) == 0 && (((uintptr_t)p.res) & 15) == 0) {
-              const uint4* rp = (const uint4*)((const __nv_bfloat16*)p.res + rbase + n0);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint4 u = rp[q];
-                const __nv_bfloat162* h = (const __nv_bfloat162*)&u;
+            for (int h = 0; h < 2; ++h) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { float2 t2 = __bfloat1622float2(h[k]); f[q * 8 + 2 * k] += p.res_scale * t2.x; f[q * 8 + 2 * k + 1] += p.res_scale * t2.y; }
+              for (int j = 0; j < 2; ++j) {
+                const int r16 = 8 * j + sr;
+                *(uint4*)(stg + r16 * 64 + ((sq ^ ((r16 >> 1) & 3)) << 4)) = rv[2 * h + j];
+              }
+              __syncwarp();
+              if ((lane >> 4) == h) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 u = *(const uint4*)(stg + my16 * 64 + ((q ^ mysw) << 4));
+                  const __nv_bfloat162* hh = (const __nv_bfloat162*)&u;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) { float2 t2 = __bfloat1622float2(hh[k]); f[q * 8 + 2 * k] += p.res_scale * t2.x; f[q * 8 + 2 * k + 1] += p.res_scale * t2.y; }
+                }
+              }
+              __syncwarp();
+            }
+          }
+          uint4 pk[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            __nv_bfloat162* hh = (__nv_bfloat162*)&pk[q];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hh[k] = row_ok ? __floats2bfloat162_rn(f[q * 8 + 2 * k], f[q * 8 + 2 * k + 1]) : __floats2bfloat162_rn(0.f, 0.f);
+          }
+          float cs0 = 0.f, cs1 = 0.f, cq0 = 0.f, cq1 = 0.f;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if ((lane >> 4) == h) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) *(uint4*)(stg + my16 * 64 + ((q ^ mysw) << 4)) = pk[q];
+            }
+            __syncwarp();
+            if (p.stats != nullptr) {
+              // lane l: columns 2*(l & 15), +1 of the rows with parity l >> 4 (rows r and r + 1 sit in different 64-byte halves
+              // of the 128-byte bank window: conflict-free)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = 2 * i + (lane >> 4);
+                const __nv_bfloat162 x2 = *(const __nv_bfloat162*)(stg + r * 64 + ((((lane & 15) >> 2) ^ ((r >> 1) & 3)) << 4) + (lane & 3) * 4);
+                const float2 x = __bfloat1622float2(x2);
+                cs0 += x.x; cq0 = fmaf(x.x, x.x, cq0);
+                cs1 += x.y; cq1 = fmaf(x.y, x.y, cq1);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int src = 16 * h + 8 * j + sr;
+              const long long ob = __shfl_sync(0xffffffffu, obase, src);
+              const int ok = __shfl_sync(0xffffffffu, (int)row_ok, src);
+              const int r16 = 8 * j + sr;
+              const uint4 u = *(const uint4*)(stg + r16 * 64 + ((sq ^ ((r16 >> 1) & 3)) << 4));
+              if (ok && !(p.dbg & 4)) *(uint4*)((__nv_bfloat16*)p.out + ob + n0 + sq * 8) = u;
+            }
+            __syncwarp();
+          }
+          if (p.stats != nullptr) {
+#pragma unroll
+            for (int i = 0; i < kChunksPerWarp; ++i)
+              if (i == ci) { st_s[i] += cs0; st_q[i] += cq0; st_s1[i] += cs1; st_q1[i] += cq1; }
+          }
+        } else {
+          float f[32];
+  #pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = 0.f;
+          if (row_ok && n0 < p.Ncols) {
+            const bool full = (n0 + 32 <= p.Ncols);
+  #pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if constexpr (HALO) {
+              const float4* b4 = (const float4*)(bs + ci * 32);
+  #pragma unroll
+              for (int q = 0; q < 8; ++q) { float4 t4 = b4[q]; f[4 * q] += t4.x; f[4 * q + 1] += t4.y; f[4 * q + 2] += t4.z; f[4 * q + 3] += t4.w; }
+            } else if (full) {
+              // 32 consecutive columns: bias / time-embedding row as independent 16-byte loads (same address in every
+              // lane -> one broadcast transaction each), issued back to back
+              if (p.bias) {
+                const float4* b4 = (const float4*)(p.bias + n0);
+  #pragma unroll
+                for (int q = 0; q < 8; ++q) { float4 t4 = __ldg(b4 + q); f[4 * q] += t4.x; f[4 * q + 1] += t4.y; f[4 * q + 2] += t4.z; f[4 * q + 3] += t4.w; }
+              }
+              if (rowvec) {
+                const float4* r4 = (const float4*)(rowvec + n0);
+  #pragma unroll
+                for (int q = 0; q < 8; ++q) { float4 t4 = __ldg(r4 + q); f[4 * q] += t4.x; f[4 * q + 1] += t4.y; f[4 * q + 2] += t4.z; f[4 * q + 3] += t4.w; }
               }
             } else {
-#pragma unroll
+  #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.Ncols) f[j] += p.res_scale * ld_dt(p.res, rbase + (long long)(n0 + j) * p.r_sc, p.res_dtype);
+                if (n0 + j < p.Ncols) {
+                  if (p.bias) f[j] += __ldg(p.bias + n0 + j);
+                  if (rowvec) f[j] += __ldg(rowvec + n0 + j);
+                }
+            }
+            if (p.act != WSR_ACT_NONE) {
+  #pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+            }
+            if (p.out_scale != 1.f) {
+  #pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
+            }
+            const bool vec_ok = full && p.o_sc == 1 && ((obase + n0) & 7) == 0 && (((uintptr_t)p.out) & 15) == 0;
+            if (p.res) {
+              if (full && p.r_sc == 1 && p.res_dtype == WSR_BF16 && ((rbase + n0) & 7) == 0 && (((uintptr_t)p.res) & 15) == 0) {
+                const uint4* rp = (const uint4*)((const __nv_bfloat16*)p.res + rbase + n0);
+  #pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  uint4 u = rp[q];
+                  const __nv_bfloat162* h = (const __nv_bfloat162*)&u;
+  #pragma unroll
+                  for (int k = 0; k < 4; ++k) { float2 t2 = __bfloat1622float2(h[k]); f[q * 8 + 2 * k] += p.res_scale * t2.x; f[q * 8 + 2 * k + 1] += p.res_scale * t2.y; }
+                }
+              } else {
+  #pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n0 + j < p.Ncols) f[j] += p.res_scale * ld_dt(p.res, rbase + (long long)(n0 + j) * p.r_sc, p.res_dtype);
+              }
+            }
+            if (p.res2) {
+  #pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.Ncols) f[j] += p.res2_scale * ld_dt(p.res2, qbase + (long long)(n0 + j) * p.q_sc, p.res2_dtype);
+            }
+            if (p.dbg & 4) {
+            } else if (vec_ok && p.out_dtype == WSR_BF16) {
+              uint4* op = (uint4*)((__nv_bfloat16*)p.out + obase + n0);
+  #pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 u;
+                __nv_bfloat162* h = (__nv_bfloat162*)&u;
+  #pragma unroll
+                for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[q * 8 + 2 * k], f[q * 8 + 2 * k + 1]);
+                op[q] = u;
+              }
+            } else if (vec_ok && p.out_dtype == WSR_F32) {
+              float4* op = (float4*)((float*)p.out + obase + n0);
+  #pragma unroll
+              for (int q = 0; q < 8; ++q) op[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+            } else {
+  #pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.Ncols) st_dt(p.out, obase + (long long)(n0 + j) * p.o_sc, p.out_dtype, f[j]);
             }
           }
-          if (p.res2) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.Ncols) f[j] += p.res2_scale * ld_dt(p.res2, qbase + (long long)(n0 + j) * p.q_sc, p.res2_dtype);
-          }
-          if (p.dbg & 4) {
-          } else if (vec_ok && p.out_dtype == WSR_BF16) {
-            uint4* op = (uint4*)((__nv_bfloat16*)p.out + obase + n0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 u;
-              __nv_bfloat162* h = (__nv_bfloat162*)&u;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[q * 8 + 2 * k], f[q * 8 + 2 * k + 1]);
-              op[q] = u;
+          __syncwarp();
+          if constexpr (kRegStats) {
+            if (p.stats != nullptr && n0 < p.Ncols) {
+              // first round (offset 16): lanes with bit 4 clear keep columns 0..15, the others 16..31
+              const bool upper = (lane & 16) != 0;
+  #pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float lo = f[i], hi = f[i + 16];
+                const float send_s = upper ? lo : hi, keep_s = upper ? hi : lo;
+                const float got_s = __shfl_xor_sync(0xffffffffu, send_s, 16);
+                const float got_q = __shfl_xor_sync(0xffffffffu, send_s * send_s, 16);
+                rs_s[i] += keep_s + got_s;
+                rs_q[i] += fmaf(keep_s, keep_s, got_q);
+              }
             }
-          } else if (vec_ok && p.out_dtype == WSR_F32) {
-            float4* op = (float4*)((float*)p.out + obase + n0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) op[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.Ncols) st_dt(p.out, obase + (long long)(n0 + j) * p.o_sc, p.out_dtype, f[j]);
-          }
-        }
-        __syncwarp();
-        if constexpr (kRegStats) {
+          } else
           if (p.stats != nullptr && n0 < p.Ncols) {
-            // first round (offset 16): lanes with bit 4 clear keep columns 0..15, the others 16..31
-            const bool upper = (lane & 16) != 0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float lo = f[i], hi = f[i + 16];
-              const float send_s = upper ? lo : hi, keep_s = upper ? hi : lo;
-              const float got_s = __shfl_xor_sync(0xffffffffu, send_s, 16);
-              const float got_q = __shfl_xor_sync(0xffffffffu, send_s * send_s, 16);
-              rs_s[i] += keep_s + got_s;
-              rs_q[i] += fmaf(keep_s, keep_s, got_q);
+            // per-channel sum / sum of squares over the warp's 32 rows: transpose-reduce with 31 shuffles per statistic so
+            // that lane j ends up with column n0 + j; masked rows hold zeros
+            float q2[32];
+  #pragma unroll
+            for (int j = 0; j < 32; ++j) q2[j] = f[j] * f[j];
+  #pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+              const bool upper = (lane & off) != 0;
+  #pragma unroll
+              for (int i = 0; i < off; ++i) {
+                const float send_s = upper ? f[i] : f[i + off];
+                const float keep_s = upper ? f[i + off] : f[i];
+                const float send_q = upper ? q2[i] : q2[i + off];
+                const float keep_q = upper ? q2[i + off] : q2[i];
+                f[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+                q2[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+              }
             }
+  #pragma unroll
+            for (int i = 0; i < kChunksPerWarp; ++i)
+              if (i == ci) { st_s[i] += f[0]; st_q[i] += q2[0]; }
           }
-        } else
-        if (p.stats != nullptr && n0 < p.Ncols) {
-          // per-channel sum / sum of squares over the warp's 32 rows: transpose-reduce with 31 shuffles per statistic so
-          // that lane j ends up with column n0 + j; masked rows hold zeros
-          float q2[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) q2[j] = f[j] * f[j];
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool upper = (lane & off) != 0;
-#pragma unroll
-            for (int i = 0; i < off; ++i) {
-              const float send_s = upper ? f[i] : f[i + off];
-              const float keep_s = upper ? f[i + off] : f[i];
-              const float send_q = upper ? q2[i] : q2[i + off];
-              const float keep_q = upper ? q2[i + off] : q2[i];
-              f[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
-              q2[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < kChunksPerWarp; ++i)
-            if (i == ci) { st_s[i] += f[0]; st_q[i] += q2[0]; }
         }
       }
       }
@@ -764,19 +904,38 @@ int sm_count() {
   return n;
 }
 
-template <int BLOCK_N, bool HALO, int ROWS, bool FUSE = false, bool VM = false>
+template <int BLOCK_N, bool HALO, int ROWS, bool FUSE = false, bool VM = false, bool STG = false>
 static int launch_tc_impl(const TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N, HALO, ROWS, VM>;
   static bool attr_set = false;
   if (!attr_set) {
-    WSR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE, VM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    WSR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE, VM, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   int total = p.g1 * p.g2 * p.g3 * p.nbatch * p.n_tiles;
   int grid = total < sm_count() ? total : sm_count();
-  gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE, VM><<<grid, FUSE ? kTcThreadsFused : kTcThreads, Cfg::kSmemBytes, st>>>(p);
+  gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE, VM, STG><<<grid, FUSE ? kTcThreadsFused : kTcThreads, Cfg::kSmemBytes, st>>>(p);
   WSR_LAUNCH_OK();
   return WSR_OK;
+}
+
+// Preconditions of the staged epilogue (STG kernels): bf16 output (and residual) with unit channel stride, every row start
+// 16-byte aligned, whole 32-column chunks only.
+static bool stage_preconditions(const TcParams& p, int block_n) {
+  auto m8 = [](long long v) { return (v & 7) == 0; };
+  if (p.out_dtype != WSR_BF16 || p.o_sc != 1 || (((uintptr_t)p.out) & 15) != 0 || p.Ncols % block_n != 0 || p.res2 != nullptr) return false;
+  if (!(m8(p.o_s1) && m8(p.o_s2) && m8(p.o_s3) && m8(p.o_sb))) return false;
+  if (p.res) {
+    if (p.res_dtype != WSR_BF16 || p.r_sc != 1 || (((uintptr_t)p.res) & 15) != 0) return false;
+    if (!(m8(p.r_s1) && m8(p.r_s2) && m8(p.r_s3) && m8(p.r_sb))) return false;
+  }
+  return true;
+}
+
+// WSR_STAGE_MASK (debugging / measurement): bit 0 = vertical-tap-merge kernels, bit 1 = other halo kernels, bit 2 = classic
+static int stage_mask() {
+  static const int m = getenv("WSR_NO_STAGE") ? 0 : (getenv("WSR_STAGE_MASK") ? atoi(getenv("WSR_STAGE_MASK")) : 7);
+  return m;
 }
 
 template <int BLOCK_N>
@@ -790,18 +949,24 @@ static int launch_tc(const TcParams& p, cudaStream_t st) {
     }
     return launch_tc_impl<BLOCK_N, true, 1, true>(p, st);
   }
+  const bool sok = stage_preconditions(p, BLOCK_N);
   if (p.n_taps > 0) {
     if constexpr (BLOCK_N == 64) {
-      if (p.halo_rows == 3) return launch_tc_impl<BLOCK_N, true, 3, false, true>(p, st);
+      if (p.halo_rows == 3) {
+        if (sok && (stage_mask() & 1)) return launch_tc_impl<BLOCK_N, true, 3, false, true, true>(p, st);
+        return launch_tc_impl<BLOCK_N, true, 3, false, true>(p, st);
+      }
     }
     if constexpr (BLOCK_N <= 64) {
       if (p.halo_rows == 4) return launch_tc_impl<BLOCK_N, true, 4>(p, st);
     }
+    const bool stg = sok && (stage_mask() & 2);
     if constexpr (BLOCK_N <= 128) {
-      if (p.halo_rows == 2) return launch_tc_impl<BLOCK_N, true, 2>(p, st);
+      if (p.halo_rows == 2) return stg ? launch_tc_impl<BLOCK_N, true, 2, false, false, true>(p, st) : launch_tc_impl<BLOCK_N, true, 2>(p, st);
     }
-    return launch_tc_impl<BLOCK_N, true, 1>(p, st);
+    return stg ? launch_tc_impl<BLOCK_N, true, 1, false, false, true>(p, st) : launch_tc_impl<BLOCK_N, true, 1>(p, st);
   }
+  if (sok && (stage_mask() & 4)) return launch_tc_impl<BLOCK_N, false, 1, false, false, true>(p, st);
   return launch_tc_impl<BLOCK_N, false, 1>(p, st);
 }
 
