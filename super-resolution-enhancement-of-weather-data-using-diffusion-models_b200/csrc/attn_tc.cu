@@ -134,44 +134,50 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
     if (lane == 0) {
       mbar_wait(q_full, 0);
       tc_fence_after();
-      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t q_lo = desc_lo(smem_u32(sQ));
       auto issue_qk = [&](int g) {
         const int ks = g % KS; const uint32_t kph = (uint32_t)(g / KS) & 1;
         const int sb = g & 1; const uint32_t sph = (uint32_t)(g >> 1) & 1;
         mbar_wait(&s_empty[sb], sph ^ 1);
         mbar_wait(&k_full[ks], kph);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + ks * Cfg::kKBytes);
+        // lean issue path (32-bit descriptor low words, see tc_common.cuh): on this single-thread dependent chain every
+        // integer instruction costs ~5 cycles, and rebuilding two 64-bit descriptors per MMA made the ISSUE the bottleneck
+        const uint32_t k_lo = desc_lo(smem_u32(sK + ks * Cfg::kKBytes));
 #pragma unroll
         for (int c = 0; c < Cfg::kChunks; ++c)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_bf16(tmem_S + (uint32_t)(sb * kBK), make_smem_desc(q_addr + c * 16384 + kk * 32),
-                      make_smem_desc(k_addr + c * 16384 + kk * 32), Cfg::kIdescQK, (c | kk) != 0 ? 1u : 0u);
+            umma_bf16_lo(tmem_S + (uint32_t)(sb * kBK), q_lo + (uint32_t)(c * 1024 + kk * 2), k_lo + (uint32_t)(c * 1024 + kk * 2),
+                         Cfg::kIdescQK, (c | kk) != 0 ? 1u : 0u);
         umma_commit(&k_empty[ks]);
         umma_commit(&s_full[sb]);
       };
       // pass A: scores of the sampled blocks only
       for (int g = 0; g < NA; ++g) issue_qk(g);
-      // pass B: scores one block ahead of P*V
+      // pass B: scores TWO blocks ahead of P*V.  P*V(j) can only be issued once softmax(j) has delivered P(j); with the
+      // scores just one block ahead, Q K^T(j+2) sat behind that wait and softmax(j+2) could not start before softmax(j+1)
+      // had finished AND Q K^T(j+2) had run (period = softmax + Q K^T).  The score buffer of block j is free as soon as
+      // softmax(j) has pulled it into registers, so Q K^T(j+2) is issued right after P*V(j): softmax(j+1) overlaps both.
       issue_qk(NA);
+      if (NB > 1) issue_qk(NA + 1);
       for (int j = 0; j < NB; ++j) {
-        if (j + 1 < NB) issue_qk(NA + j + 1);
         const int pb = j & 1; const uint32_t pph = (uint32_t)(j >> 1) & 1;
         const int vs = j % VS; const uint32_t vph = (uint32_t)(j / VS) & 1;
         mbar_wait(&p_full[pb], pph);
         mbar_wait(&v_full[vs], vph);
         tc_fence_after();
-        const uint32_t p_addr = smem_u32(sP + pb * Cfg::kPBytes);
-        const uint32_t v_addr = smem_u32(sV + vs * Cfg::kVBytes);
+        const uint32_t p_lo = desc_lo(smem_u32(sP + pb * Cfg::kPBytes));
+        const uint32_t v_lo = desc_lo(smem_u32(sV + vs * Cfg::kVBytes));
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_bf16(tmem_O, make_smem_desc(p_addr + a * 16384 + kk * 32), make_smem_desc(v_addr + a * Cfg::kVAtom + kk * 32),
-                      Cfg::kIdescPV, (j | a | kk) != 0 ? 1u : 0u);
+            umma_bf16_lo(tmem_O, p_lo + (uint32_t)(a * 1024 + kk * 2), v_lo + (uint32_t)(a * (Cfg::kVAtom >> 4) + kk * 2),
+                         Cfg::kIdescPV, (j | a | kk) != 0 ? 1u : 0u);
         umma_commit(&p_empty[pb]);
         umma_commit(&v_empty[vs]);
+        if (j + 2 < NB) issue_qk(NA + j + 2);
       }
       umma_commit(o_full);
     }
@@ -216,16 +222,24 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
       const int sb = g & 1; const uint32_t sph = (uint32_t)(g >> 1) & 1;
       const int pb = j & 1; const uint32_t pph = (uint32_t)(j >> 1) & 1;
       mbar_wait(&s_full[sb], sph);
-      mbar_wait(&p_empty[pb], pph ^ 1);
       tc_fence_after();
       uint8_t* atom = sP + pb * Cfg::kPBytes + half * 16384 + row * 128;     // this half = one 64-key atom of P
-#pragma unroll 1
+      // both 32-key chunks are fetched up front; once they sit in registers the score buffer goes back to the MMA issuer
+      // (the next Q K^T starts while the exponentials are still being computed), and the fully unrolled body lets the
+      // compiler interleave the MUFU stream of one chunk with the sums / conversions / stores of the other
+      uint32_t v[2][32];
+      tmem_ld32_nowait(tmem_S + lane_sel + (uint32_t)(sb * kBK + half * 64), v[0]);
+      tmem_ld32_nowait(tmem_S + lane_sel + (uint32_t)(sb * kBK + half * 64 + 32), v[1]);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[sb]);
+      mbar_wait(&p_empty[pb], pph ^ 1);
+#pragma unroll
       for (int c2 = 0; c2 < 2; ++c2) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_sel + (uint32_t)(sb * kBK + half * 64 + c2 * 32), v);
         float e[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) e[i] = exp2f(fminf(fmaf(__uint_as_float(v[i]), p.c, -mc), 64.f));
+        for (int i = 0; i < 32; ++i) e[i] = exp2f(fminf(fmaf(__uint_as_float(v[c2][i]), p.c, -mc), 64.f));
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;       // independent partial sums
 #pragma unroll
         for (int i = 0; i < 32; i += 4) { s0 += e[i]; s1 += e[i + 1]; s2 += e[i + 2]; s3 += e[i + 3]; }
@@ -240,10 +254,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
           *(uint4*)(atom + ((cc ^ (row & 7)) << 4)) = u;
         }
       }
-      tc_fence_before();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&s_empty[sb]); mbar_arrive(&p_full[pb]); }
+      if (lane == 0) mbar_arrive(&p_full[pb]);
     }
     xchg[half * 128 + row] = lsum;
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");

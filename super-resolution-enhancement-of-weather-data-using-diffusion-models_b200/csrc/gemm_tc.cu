@@ -617,8 +617,14 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
 #pragma unroll
             for (int hj = 0; hj < 4; ++hj) {
               const int src = 8 * hj + sr;
-              const long long rb = __shfl_sync(0xffffffffu, rbase, src);
-              const int ok = __shfl_sync(0xffffffffu, (int)row_ok, src);
+              long long rb; int ok;
+              if constexpr (HALO) {       // a warp's rows are consecutive pixels of one image row: addresses are linear in the row index
+                rb = rbase + (long long)(src - lane) * p.mul1 * p.r_s1;
+                ok = (quad * 32 + src < rows_box) && (i1 * p.t1 + quad * 32 + src < p.M1) && r2 < p.M2 && r3 < p.M3;
+              } else {
+                rb = __shfl_sync(0xffffffffu, rbase, src);
+                ok = __shfl_sync(0xffffffffu, (int)row_ok, src);
+              }
               rv[hj] = make_uint4(0u, 0u, 0u, 0u);
               if (ok) rv[hj] = __ldg((const uint4*)((const __nv_bfloat16*)p.res + rb + n0 + sq * 8));
             }
@@ -701,8 +707,14 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const int src = 16 * h + 8 * j + sr;
-              const long long ob = __shfl_sync(0xffffffffu, obase, src);
-              const int ok = __shfl_sync(0xffffffffu, (int)row_ok, src);
+              long long ob; int ok;
+              if constexpr (HALO) {
+                ob = obase + (long long)(src - lane) * p.mul1 * p.o_s1;
+                ok = (quad * 32 + src < rows_box) && (i1 * p.t1 + quad * 32 + src < p.M1) && r2 < p.M2 && r3 < p.M3;
+              } else {
+                ob = __shfl_sync(0xffffffffu, obase, src);
+                ok = __shfl_sync(0xffffffffu, (int)row_ok, src);
+              }
               const int r16 = 8 * j + sr;
               const uint4 u = *(const uint4*)(stg + r16 * 64 + ((sq ^ ((r16 >> 1) & 3)) << 4));
               if (ok && !(p.dbg & 4)) *(uint4*)((__nv_bfloat16*)p.out + ob + n0 + sq * 8) = u;

@@ -26,13 +26,14 @@ def main():
     y = eng.new_act(N, H, W, Cout, stats=arena if os.environ.get("PROF_STATS") else None)
     arena.finalize(dev)
     rv = torch.randn(N, Cout, device=dev)
+    res = x if (os.environ.get("PROF_RES") and Cin == Cout) else None
     for _ in range(2):
-        eng.conv(x, pc, y, rowvec=rv.data_ptr(), rowvec_ld=Cout)
+        eng.conv(x, pc, y, rowvec=rv.data_ptr(), rowvec_ld=Cout, res=res)
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(reps):
-        eng.conv(x, pc, y, rowvec=rv.data_ptr(), rowvec_ld=Cout)
+        eng.conv(x, pc, y, rowvec=rv.data_ptr(), rowvec_ld=Cout, res=res)
     e.record()
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / reps
