@@ -154,6 +154,16 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
+def _conv_traffic():
+    """DRAM bytes per gemm_tc_kernel launch (read + write, averaged over the launches of a B=64 sampler step) from the
+    committed ncu pass (profiles/r01c_conv_traffic.json <- profiles/r01c_ncu_launches.csv); None if the file is missing."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01c_conv_traffic.json")) as f:
+            return json.load(f)["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -249,7 +259,9 @@ def run_ours(args):
     step_ms_prof = sum(v[1] for v in summ.values())
     roofline = {
         "bound": "tensor", "kernel": "gemm_tc_kernel (conv_tc launches)", "achieved": conv_tflops, "peak": peaks["bf16_tflops"],
-        "unit": "TFLOP/s", "frac": conv_tflops / peaks["bf16_tflops"], "traffic": None, "peak_source": peak_src + " burst",
+        "unit": "TFLOP/s", "frac": conv_tflops / peaks["bf16_tflops"], "traffic": _conv_traffic(),
+        "traffic_note": "ncu dram__bytes_read+write per gemm_tc_kernel launch, averaged over one B=64 step (profiles/r01c_conv_traffic.json)",
+        "peak_source": peak_src + " burst",
         "launches_per_step": conv[0], "kernel_ms_per_step": conv[1], "kernel_share_of_step": conv[1] / step_ms_prof if step_ms_prof else None,
         "whole_step_tflops": global_batch / world * FLOPS_PER_SAMPLE_STEP / (ms_per_step * 1e-3) / 1e12,
         "whole_step_frac_of_sustained": global_batch / world * FLOPS_PER_SAMPLE_STEP / (ms_per_step * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
