@@ -310,6 +310,12 @@ int wsr_stem_assemble(const float* x, const float* cond, const float* gate, cons
 /* Haar detail-band sums for `levels` levels: out[j] fp32 NCHW (B,C,H>>(j+1),W>>(j+1)) packed back to back in `out`;
  * ll_work: scratch of B*C*H*W/4*... floats (>= B*C*H*W/2 floats). */
 int wsr_haar_detail_sums(const float* img, int B, int C, int H, int W, int levels, float* out, float* ll_work, void* stream);
+/* PhyDiff variant (phydiff/unet.py:265-276): the three detail bands kept apart, out[j] fp32 NCHW (B, 3*C, H>>(j+1), W>>(j+1)) with
+ * channel k*C + c = band k (LH, HL, HH) of image channel c; same packing and scratch as wsr_haar_detail_sums. */
+int wsr_haar_detail_bands(const float* img, int B, int C, int H, int W, int levels, float* out, float* ll_work, void* stream);
+/* PhyDiff stencil channels (phydiff/unet.py:189-196,311-314): F.conv2d(reflect_pad(cond), k) for k = x forward difference,
+ * y forward difference, 5-point Laplacian, each with a (1, C, 3, 3) kernel (sum over channels).  out fp32 NCHW (B, 3, H, W). */
+int wsr_phy_stencils(const float* cond, int B, int C, int H, int W, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * DDPM process kernels (models/diffusion_models/diffusion.py).

@@ -48,6 +48,14 @@ CASES = {
     # priors and the RRDB-conditioned variant
     "simple_cnn": dict(kind="simple_cnn", batch=2, seed=41, lr_hw=(8, 16)),
     "rrdb_small": dict(kind="rrdb", batch=1, seed=42, lr_hw=(8, 16)),
+    # SR3 (plain conditional UNet) and PhyDiff ("ResDiff+Physics": stencil channels + 3-band Haar queries)
+    "sr3_step_small": dict(kind="sr3_step", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=2), batch=2, seed=51, level=(0.77, 0.21)),
+    "sr3_chain_small": dict(kind="sr3_chain", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=2), batch=2, seed=52, T=3),
+    "phydiff_step_small": dict(kind="phydiff_step", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=53, level=(0.6, 0.35)),
+    "phydiff_step_full_b1": dict(kind="phydiff_step", cfg=unet_cfg(128, 256), batch=1, seed=54, level=(0.5,)),
+    "phydiff_step_c3_small": dict(kind="phydiff_step", cfg=unet_cfg(32, 64, c_img=3, attn_res=(4,), in_channel=9), batch=2, seed=56,
+                                  level=(0.9, 0.15)),
+    "phydiff_chain_small": dict(kind="phydiff_chain", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=55, T=3),
     "srdiff_step_small": dict(kind="srdiff_step", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=1), batch=2, seed=43,
                               level=(0.7, 0.4)),
 }

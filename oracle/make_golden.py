@@ -29,9 +29,14 @@ def _checksum(module):
                          float(sum(p.double().abs().sum() for p in module.parameters()))])
 
 
-def _unet(ref, cfg, srdiff=False):
+def _unet(ref, cfg, srdiff=False, arch=None):
     cls = ref.SRDiffUNet if srdiff else ref.ResDiffUNet
-    net = cls(in_channel=cfg["in_channel"], out_channel=cfg["out_channel"], norm_groups=cfg["norm_groups"],
+    extra = {}
+    if arch == "sr3":
+        cls = ref.SR3UNet
+    elif arch == "phydiff":
+        cls, extra = ref.PhyDiffUNet, {"device": "cpu"}
+    net = cls(**extra, in_channel=cfg["in_channel"], out_channel=cfg["out_channel"], norm_groups=cfg["norm_groups"],
               inner_channel=cfg["inner_channel"], channel_mults=cfg["channel_mults"], attn_res=cfg["attn_res"],
               res_blocks=cfg["res_blocks"], dropout=cfg["dropout"], image_height=cfg["image_height"],
               image_width=cfg["image_width"], image_channels=cfg["image_channels"])
@@ -135,6 +140,25 @@ def run_case(ref, name, spec):
             finally:
                 np.random.randint, np.random.uniform = _ri, _un
             out.update(hr=hr, sr=sr, noise=noise, level=level, loss=loss.reshape(1), wsum=_checksum(net))
+        elif kind in ("sr3_step", "phydiff_step"):
+            cfg, arch = spec["cfg"], kind.split("_")[0]
+            net = fill_module(_unet(ref, cfg, arch=arch), seed)
+            _, sr, _ = fields(name, b, cfg["image_channels"], cfg["image_height"], cfg["image_width"], seed)
+            x_t = seeded_randn(name + ".xt", sr.shape, seed)
+            level = torch.tensor(spec["level"], dtype=torch.float32).view(b, 1)
+            out.update(cond=sr, x_t=x_t, level=level, eps=net(torch.cat([sr, x_t], 1), level), wsum=_checksum(net))
+        elif kind in ("sr3_chain", "phydiff_chain"):
+            cfg, T, arch = spec["cfg"], spec["T"], kind.split("_")[0]
+            net = fill_module(_unet(ref, cfg, arch=arch), seed)
+            D = ref.SR3Diffusion if arch == "sr3" else ref.PhyDiffDiffusion
+            diff = D(net, image_height=cfg["image_height"], image_width=cfg["image_width"], channels=cfg["image_channels"], conditional=True)
+            diff.set_new_noise_schedule(short_schedule(T), "cpu")
+            _, sr, _ = fields(name, b, cfg["image_channels"], cfg["image_height"], cfg["image_width"], seed)
+            noise = seeded_randn(name + ".noise", (T + 1,) + tuple(sr.shape), seed)
+            with _InjectedNoise(noise) as inj:
+                res = diff.super_resolution({"SR": sr})
+                assert inj.i == T, inj.i
+            out.update(cond=sr, noise=noise, sr_out=res, wsum=_checksum(net))
         elif kind == "simple_cnn":
             net = fill_module(ref.SimpleCNN(scale_factor=4, channels=1).eval(), seed)
             lr = seeded_randn(name + ".lr", (b, 1) + tuple(spec["lr_hw"]), seed)
@@ -191,6 +215,8 @@ def main(argv):
             from .cases import unet_cfg
             data = {}
             for tag, net in {"resdiff": _unet(ref, unet_cfg(128, 256)), "srdiff": _unet(ref, unet_cfg(128, 256, in_channel=1), srdiff=True),
+                             "sr3": _unet(ref, unet_cfg(128, 256, in_channel=2), arch="sr3"),
+                             "phydiff": _unet(ref, unet_cfg(128, 256), arch="phydiff"),
                              "rrdb": ref.RRDBNet(1, 1, 64, 17, 32), "simple_cnn": ref.SimpleCNN(4, 1)}.items():
                 sd = net.state_dict()
                 data[tag + ".keys"] = np.array(list(sd.keys()))

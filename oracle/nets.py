@@ -235,6 +235,78 @@ def srdiff_unet(sd, feas, x, level, cfg):
     return block(sd, "final_conv.", x, g)
 
 
+def haar_detail_bands(img, levels=4):
+    """phydiff/unet.py:265-276: per level cat([LH, HL, HH], dim=1) of the Haar analysis of the condition (same band
+    convention as haar_detail_sums; PhyDiff keeps the three bands apart, so their ORDER matters here)."""
+    out = []
+    ll = img
+    for _ in range(levels):
+        a = ll[:, :, 0::2, 0::2]
+        b = ll[:, :, 0::2, 1::2]
+        c = ll[:, :, 1::2, 0::2]
+        d = ll[:, :, 1::2, 1::2]
+        out.append(torch.cat([(a + b - c - d) / 2, (a - b + c - d) / 2, (a - b - c + d) / 2], dim=1))
+        ll = (a + b + c + d) / 2
+    return out
+
+
+def phy_stencils(cond):
+    """phydiff/unet.py:189-196,311-314: forward differences in x and y and the 5-point Laplacian of the REFLECT-padded
+    condition; each is a conv2d with a (1, C_img, 3, 3) kernel, i.e. the stencil summed over the image channels.
+    Returns (B, 3, H, W)."""
+    c = cond.shape[1]
+    kx = torch.tensor([[0, 0, 0], [0, -1, 1], [0, 0, 0]], dtype=torch.float32).view(1, 1, 3, 3).repeat(1, c, 1, 1)
+    ky = torch.tensor([[0, 0, 0], [0, -1, 0], [0, 1, 0]], dtype=torch.float32).view(1, 1, 3, 3).repeat(1, c, 1, 1)
+    kxy = torch.tensor([[0, 1, 0], [1, -4, 1], [0, 1, 0]], dtype=torch.float32).view(1, 1, 3, 3).repeat(1, c, 1, 1)
+    padded = F.pad(cond, (1, 1, 1, 1), mode="reflect")
+    return torch.cat([F.conv2d(padded, kx), F.conv2d(padded, ky), F.conv2d(padded, kxy)], dim=1)
+
+
+def _unet_trunk(sd, x, t, g, queries=None):
+    """downs / mid / ups / final_conv shared by the SR3 and PhyDiff UNets; ``queries`` (PhyDiff) = the HF-guided
+    cross-attention query images, one per Downsample (the attended tensor replaces the SKIP only)."""
+    feats = []
+    hf_i = 0
+    for i, kind in enumerate(_layer_kinds(sd, "downs.")):
+        p = "downs.%d." % i
+        if kind == "conv":
+            x = conv(sd, p, x, padding=1)
+        elif kind == "res":
+            x = res_block_with_attn(sd, p, x, t, g)
+        else:
+            x = conv(sd, p + "conv.", x, stride=2, padding=1)
+        if queries is not None and feats and feats[-1].shape[2:] != x.shape[2:]:
+            feats.append(hf_guided_ca(sd, "hf_ca_list.%d." % hf_i, x, queries[hf_i], 32))
+            hf_i += 1
+        else:
+            feats.append(x)
+    for i in range(len(_layer_kinds(sd, "mid."))):            # SR3 has ONE mid block (sr3/unet.py:77-81), PhyDiff two
+        x = res_block_with_attn(sd, "mid.%d." % i, x, t, g)
+    for i, kind in enumerate(_layer_kinds(sd, "ups.")):
+        p = "ups.%d." % i
+        if kind == "res":
+            x = res_block_with_attn(sd, p, torch.cat([x, feats.pop()], dim=1), t, g)
+        else:
+            x = conv(sd, p + "conv.", F.interpolate(x, scale_factor=2, mode="nearest"), padding=1)
+    return block(sd, "final_conv.", x, g)
+
+
+def sr3_unet(sd, x, level, cfg):
+    """sr3/unet.py:100-124 (eval mode).  x = cat([cond, x_t], 1) (B, 2*C_img, H, W); level (B,1)."""
+    t = noise_level_mlp(sd, level, cfg["inner_channel"], swish)
+    return _unet_trunk(sd, x, t, cfg.get("norm_groups", 32))
+
+
+def phydiff_unet(sd, x, level, cfg):
+    """phydiff/unet.py:262-346 (eval mode).  x = cat([cond, x_t], 1); the stem sees cat([x, Kx, Ky, Kxy](cond))."""
+    c_img = cfg["image_channels"]
+    cond = x[:, :c_img]
+    queries = haar_detail_bands(cond, 4)
+    x = torch.cat([x, phy_stencils(cond)], dim=1)
+    t = noise_level_mlp(sd, level, cfg["inner_channel"], swish)
+    return _unet_trunk(sd, x, t, cfg.get("norm_groups", 32), queries)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # priors
 # ----------------------------------------------------------------------------------------------------------------

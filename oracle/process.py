@@ -72,6 +72,27 @@ def srdiff_chain(unet_sd, rrdb_sd, cfg, schedule_opt, lr, sr_up, noise, return_e
     return (out, eps_all) if return_eps else out
 
 
+def cond_chain(unet_fn, sd, cfg, schedule_opt, cond, noise, add_cond, return_eps=False):
+    """Conditional reverse chain of the SR3 (sr3_diffusion.py:49-84, returns the image) and PhyDiff
+    (phydiff_diffusion.py:49-82, returns image + condition) processes; noise layout as in resdiff_chain."""
+    tab, sap = _tables(schedule_opt)
+    T = int(schedule_opt["n_timestep"])
+    img = noise[0].clone()
+    eps_all = []
+
+    def denoise(x, level):
+        return unet_fn(sd, torch.cat([cond, x], dim=1), level, cfg)
+
+    k = 1
+    for t in reversed(range(T)):
+        img, eps = p_sample_step(denoise, tab, sap, img, t, noise[k] if t > 0 else None)
+        k += 1
+        if return_eps:
+            eps_all.append(eps)
+    out = img + cond if add_cond else img
+    return (out, eps_all) if return_eps else out
+
+
 def q_sample(x0, a, noise):
     """diffusion.py:209-228: a*x0 + sqrt(1-a^2)*noise with a of shape (B,1,1,1)."""
     return a * x0 + (1 - a ** 2).sqrt() * noise

@@ -96,11 +96,16 @@ def import_reference():
     from models.diffusion_models.resdiff.resdiff_diffusion import ResDiffDiffusion
     from models.diffusion_models.srdiff.unet import UNet as SRDiffUNet
     from models.diffusion_models.srdiff.srdiff_diffusion import SRDiffDiffusion
+    from models.diffusion_models.sr3.unet import UNet as SR3UNet
+    from models.diffusion_models.sr3.sr3_diffusion import SR3Diffusion
+    from models.diffusion_models.phydiff.unet import UNet as PhyDiffUNet
+    from models.diffusion_models.phydiff.phydiff_diffusion import PhyDiffDiffusion
     from models.rrdb_encoder.RRDBNet import RRDBNet
     from models.simple_cnn.Simple_CNN import SimpleCNN
     from models.diffusion_models import networks
     from models.diffusion_models.sheduler import make_beta_schedule
     ns.ResDiffUNet, ns.ResDiffDiffusion = ResDiffUNet, ResDiffDiffusion
     ns.SRDiffUNet, ns.SRDiffDiffusion = SRDiffUNet, SRDiffDiffusion
+    ns.SR3UNet, ns.SR3Diffusion, ns.PhyDiffUNet, ns.PhyDiffDiffusion = SR3UNet, SR3Diffusion, PhyDiffUNet, PhyDiffDiffusion
     ns.RRDBNet, ns.SimpleCNN, ns.networks, ns.make_beta_schedule = RRDBNet, SimpleCNN, networks, make_beta_schedule
     return ns

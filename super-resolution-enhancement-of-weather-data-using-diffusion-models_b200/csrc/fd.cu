@@ -394,6 +394,52 @@ __global__ void haar_level_kernel(const float* __restrict__ ll, int h, int w, fl
   ll_next[i] = (a + b + c + d) * 0.5f;
 }
 
+// PhyDiff keeps the three detail bands apart (phydiff/unet.py:274-276): bands[b][k*C + c] = band k (LH, HL, HH) of channel c
+__global__ void haar_level_bands_kernel(const float* __restrict__ ll, int C, int h, int w, float* __restrict__ bands,
+                                        float* __restrict__ ll_next, int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*C * h/2 * w/2
+  if (i >= total) return;
+  int w2 = w / 2, h2 = h / 2;
+  int x = (int)(i % w2);
+  int64_t r = i / w2;
+  int y = (int)(r % h2);
+  int64_t bc = r / h2;
+  int64_t b = bc / C; int c = (int)(bc - b * C);
+  const float* p = ll + (bc * h + 2 * y) * w + 2 * x;
+  float a = p[0], bb = p[1], cc = p[w], d = p[w + 1];
+  const int64_t plane = (int64_t)h2 * w2;
+  float* o = bands + (b * 3 * C + c) * plane + (int64_t)y * w2 + x;
+  o[0] = (a + bb - cc - d) * 0.5f;
+  o[(int64_t)C * plane] = (a - bb + cc - d) * 0.5f;
+  o[(int64_t)2 * C * plane] = (a - bb - cc + d) * 0.5f;
+  ll_next[i] = (a + bb + cc + d) * 0.5f;
+}
+
+// PhyDiff stencil channels (phydiff/unet.py:189-196,311-314): x / y forward differences and the 5-point Laplacian of the
+// REFLECT-padded condition, each summed over the image channels.  out: (B, 3, H, W) fp32.
+__global__ void phy_stencils_kernel(const float* __restrict__ cond, int C, int H, int W, float* __restrict__ out, int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B * H * W
+  if (i >= total) return;
+  int x = (int)(i % W);
+  int64_t r = i / W;
+  int y = (int)(r % H);
+  int64_t b = r / H;
+  const int xl = x == 0 ? 1 : x - 1, xr = x == W - 1 ? W - 2 : x + 1;
+  const int yu = y == 0 ? 1 : y - 1, yd = y == H - 1 ? H - 2 : y + 1;
+  float dx = 0.f, dy = 0.f, lap = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float* p = cond + (b * C + c) * (int64_t)H * W;
+    const float v = p[(int64_t)y * W + x], vr = p[(int64_t)y * W + xr], vl = p[(int64_t)y * W + xl];
+    const float vd = p[(int64_t)yd * W + x], vu = p[(int64_t)yu * W + x];
+    dx += vr - v;
+    dy += vd - v;
+    lap += (vu + vl - 4.f * v) + (vr + vd);        // same tap order as the 3x3 cross-correlation (row-major taps)
+  }
+  const int64_t plane = (int64_t)H * W;
+  float* o = out + b * 3 * plane + (int64_t)y * W + x;
+  o[0] = dx; o[plane] = dy; o[2 * plane] = lap;
+}
+
 }  // namespace wsr
 
 using namespace wsr;
@@ -565,5 +611,33 @@ extern "C" int wsr_haar_detail_sums(const float* img, int B, int C, int H, int W
     o += total;
     ll = nxt; h /= 2; w /= 2;
   }
+  return WSR_OK;
+}
+
+extern "C" int wsr_haar_detail_bands(const float* img, int B, int C, int H, int W, int levels, float* out, float* ll_work, void* stream) {
+  WSR_REQUIRE(img && out && ll_work && B > 0 && C > 0 && levels > 0, WSR_E_INVALID, "haar bands: bad argument");
+  WSR_REQUIRE((H % (1 << levels)) == 0 && (W % (1 << levels)) == 0, WSR_E_UNSUPPORTED, "haar bands: H, W must be divisible by 2^levels");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* ll = img;
+  int h = H, w = W;
+  float* lw0 = ll_work;
+  float* lw1 = ll_work + (int64_t)B * C * (H / 2) * (W / 2);
+  float* o = out;
+  for (int j = 0; j < levels; ++j) {
+    int64_t total = (int64_t)B * C * (h / 2) * (w / 2);
+    float* nxt = (j % 2 == 0) ? lw0 : lw1;
+    haar_level_bands_kernel<<<nblk(total, 256), 256, 0, st>>>(ll, C, h, w, o, nxt, total);
+    WSR_LAUNCH_OK();
+    o += 3 * total;
+    ll = nxt; h /= 2; w /= 2;
+  }
+  return WSR_OK;
+}
+
+extern "C" int wsr_phy_stencils(const float* cond, int B, int C, int H, int W, float* out, void* stream) {
+  WSR_REQUIRE(cond && out && B > 0 && C > 0 && H >= 2 && W >= 2, WSR_E_INVALID, "phy_stencils: bad argument (reflect padding needs H, W >= 2)");
+  int64_t total = (int64_t)B * H * W;
+  phy_stencils_kernel<<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(cond, C, H, W, out, total);
+  WSR_LAUNCH_OK();
   return WSR_OK;
 }

@@ -1,6 +1,6 @@
 """Architecture registry -- drop-in for the reference's models/diffusion_models/networks.py:56-169.
 ``define_diffusion(opt)`` maps ``opt['model']['architecture']`` to a (UNet, *Diffusion) pair with the reference's
-constructor arguments.  Accelerated architectures: ``resdiff`` and ``srdiff``; the others raise
+constructor arguments.  Accelerated architectures: ``resdiff``, ``srdiff`` and ``sr3``, ``phydiff`` (8f N1); ``physrdiff`` raises
 NotImplementedError, like an unknown name does in the reference (:133-134).
 
 Extra optional config key (default reproduces the reference): ``model.precision`` = ``"bf16"`` | ``"fp32"``.
@@ -77,8 +77,15 @@ def define_diffusion(opt):
     elif arch == 'srdiff':
         from .srdiff import unet
         from .srdiff.srdiff_diffusion import SRDiffDiffusion as Diffusion
-    elif arch in ('sr3', 'phydiff', 'physrdiff'):
-        raise NotImplementedError('Architecture [{:s}] is outside the accelerated hot path (SURVEY.md 8f).'.format(arch))
+    elif arch == 'sr3':
+        from .sr3 import unet
+        from .sr3.sr3_diffusion import SR3Diffusion as Diffusion
+    elif arch == 'phydiff':
+        from .phydiff import unet
+        from .phydiff.phydiff_diffusion import PhyDiffDiffusion as Diffusion
+    elif arch == 'physrdiff':
+        # the reference's own physrdiff UNet raises AttributeError on its first forward (physrdiff/unet.py:150)
+        raise NotImplementedError('Architecture [{:s}] is broken in the reference itself and outside the accelerated hot path (SURVEY.md 8f).'.format(arch))
     else:
         raise NotImplementedError('Architecture [{:s}] is not implemented.'.format(arch))
 

@@ -1,0 +1,80 @@
+"""PhyDiff ("ResDiff+Physics") noise-prediction UNet -- drop-in for the reference's models/diffusion_models/phydiff/unet.py:
+140-346 (the architecture of the reference's README example and of 30 of its 55 configs).
+
+ResDiff without the FD splitter: the stem sees ``cat([condition, x_t, Kx(c), Ky(c), Kxy(c)])`` where the three fixed
+stencils (x / y forward differences, 5-point Laplacian) act on the REFLECT-padded condition and sum over the image channels
+(:189-196, :311-314), and the HF-guided cross-attention queries are the three Haar detail bands kept apart
+(``wavelet_components = 3``, :265-276).  Everything that depends only on the condition is computed once per batch
+(``UNetPlan.set_condition``, kind 'phydiff').  The reference's ``PhyConv`` / ``K2M`` classes (:11-137) are never
+instantiated by it and are not reproduced.  state_dict: 386 tensors for the canonical config (the stencil kernels are plain
+tensors in the reference, not parameters or buffers).
+"""
+import torch
+from torch import nn
+
+from ....unet_plan import UNetPlan
+from ..nn_modules.functional_layers import PositionalEncoding, Swish
+from ..resdiff.guided_cross_attention import HF_guided_CA
+from ..resdiff.unet import build_unet_body
+
+
+class UNet(nn.Module):
+    def __init__(self, in_channel=9, out_channel=3, inner_channel=32, norm_groups=32, channel_mults=(1, 2, 4, 8, 8),
+                 attn_res=(8,), res_blocks=3, dropout=0, with_noise_level_emb=True, image_width=128, image_height=128,
+                 image_channels=1, device='cuda', precision="bf16"):
+        super().__init__()
+        if not with_noise_level_emb:
+            raise NotImplementedError("with_noise_level_emb=False is never used on the reference's path")
+        if in_channel != 2 * image_channels + 3:
+            raise AssertionError("PhyDiff's stem consumes cat([condition, x_t, 3 stencil maps]): in_channel must be 2 * image_channels + 3")
+        self.noise_level_mlp = nn.Sequential(
+            PositionalEncoding(inner_channel),
+            nn.Linear(inner_channel, inner_channel * 4),
+            Swish(),
+            nn.Linear(inner_channel * 4, inner_channel),
+        )
+        self.image_channels = image_channels
+        self.wavelet_components = 3
+        self.J = 4
+        self.image_height, self.image_width = image_height, image_width
+        self.inner_channel, self.norm_groups, self.dropout = inner_channel, norm_groups, dropout
+        self.hf_ca_list = nn.ModuleList(
+            [HF_guided_CA(inner_channel * (2 ** i), image_channels=image_channels, wavelet_components=self.wavelet_components)
+             for i in range(self.J)])
+        build_unet_body(self, in_channel, out_channel, inner_channel, norm_groups, channel_mults, attn_res, res_blocks,
+                        dropout, inner_channel, image_height)
+        self.precision = precision
+        self.time_act = "swish"
+        self._plans = {}
+        del device
+
+    # ---- engine glue ------------------------------------------------------------------------------------------------
+    def plan(self, batch, device=None, precision=None, strict_tc=False):
+        """The compiled launch schedule for a given local batch size (cached)."""
+        device = device or next(self.parameters()).device
+        key = (batch, str(device), precision or self.precision, strict_tc)
+        pl = self._plans.get(key)
+        if pl is None:
+            pl = UNetPlan(self, batch, device, precision or self.precision, strict_tc=strict_tc)
+            self._plans[key] = pl
+        pl.refresh_weights()
+        return pl
+
+    def _apply(self, fn, *args, **kwargs):
+        self._plans = {}           # .to() / .cuda() re-allocate the parameters: drop plans that point at the old storage
+        return super()._apply(fn, *args, **kwargs)
+
+    def forward(self, x, time):
+        b = x.shape[0]
+        c = self.image_channels
+        if x.shape[1] != 2 * c:
+            raise AssertionError("expected cat([condition, x_t]) with %d channels, got %d" % (2 * c, x.shape[1]))
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("the hand-written backward pass covers the resdiff architecture only (DESIGN.md section 7); "
+                                      "run this architecture under torch.no_grad()")
+        if self.training and self.dropout:
+            raise NotImplementedError("training-mode dropout of this architecture is not implemented in the CUDA path")
+        pl = self.plan(b, x.device)
+        pl.set_condition(x[:, :c])
+        pl.set_levels(time.reshape(b))
+        return pl.denoise(x[:, c:])

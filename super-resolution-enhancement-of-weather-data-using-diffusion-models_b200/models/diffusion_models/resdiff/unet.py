@@ -18,7 +18,7 @@ from .guided_cross_attention import HF_guided_CA
 
 
 def build_unet_body(net, in_channel, out_channel, inner_channel, norm_groups, channel_mults, attn_res, res_blocks,
-                    dropout, noise_level_channel, image_height):
+                    dropout, noise_level_channel, image_height, mid_attn=(True, False)):
     """Down / mid / up module lists shared by the ResDiff and SRDiff UNets (reference resdiff/unet.py:62-119,
     srdiff/unet.py:58-110).  Attention placement is keyed on the image HEIGHT, as in the reference."""
     n_levels = len(channel_mults)
@@ -38,10 +38,10 @@ def build_unet_body(net, in_channel, out_channel, inner_channel, norm_groups, ch
             skip_widths.append(width)
             res //= 2
     net.downs = nn.ModuleList(downs)
+    # mid_attn: one entry per mid block (ResDiff / SRDiff / PhyDiff: attention then plain; SR3: ONE plain block, sr3/unet.py:77-81)
     net.mid = nn.ModuleList([
-        ResnetBlocWithAttn(width, width, noise_level_emb_dim=noise_level_channel, norm_groups=norm_groups, dropout=dropout, with_attn=True),
-        ResnetBlocWithAttn(width, width, noise_level_emb_dim=noise_level_channel, norm_groups=norm_groups, dropout=dropout, with_attn=False),
-    ])
+        ResnetBlocWithAttn(width, width, noise_level_emb_dim=noise_level_channel, norm_groups=norm_groups, dropout=dropout, with_attn=a)
+        for a in mid_attn])
     ups = []
     for lvl in reversed(range(n_levels)):
         out_w = inner_channel * channel_mults[lvl]

@@ -35,7 +35,11 @@ class UNetPlan:
         self.net = net
         self.B = int(batch)
         self.eng = Engine(device, precision, strict_tc=strict_tc)
-        self.kind = "resdiff" if hasattr(net, "fd_spliter") else "srdiff"
+        # resdiff: FD splitter + HF-guided cross attention; phydiff: stencil channels + 3-band HF-CA queries (phydiff/unet.py);
+        # srdiff: RRDB features through cond_proj; sr3: plain conditional UNet on cat([cond, x_t]) (sr3/unet.py)
+        self.kind = ("resdiff" if hasattr(net, "fd_spliter") else "srdiff" if hasattr(net, "cond_proj") else
+                     "phydiff" if hasattr(net, "hf_ca_list") else "sr3")
+        self.has_hfca = self.kind in ("resdiff", "phydiff")
         self.C_img = net.image_channels
         self.H, self.W = net.image_height, net.image_width
         self.inner = net.inner_channel
@@ -148,7 +152,7 @@ class UNetPlan:
             elif r.kind == "res":
                 res_scratch(r, feat_dst[i])
             else:
-                if self.kind == "resdiff":
+                if self.has_hfca:
                     # main path continues with the plain strided-conv output; the skip is its HF-guided attention
                     r.y = e.new_act(B, r.h, r.w, r.cout, stats=arena)
                     n = r.h * r.w
@@ -158,7 +162,7 @@ class UNetPlan:
                     ca.vT = e.empty((B, r.cout, n))
                     ca.obuf = e.new_act(B, r.h, r.w, r.cout)
                     ca.q = e.new_act(B, r.h, r.w, r.cout)
-                    ca.qimg = e.new_act(B, r.h, r.w, self.C_img, dt=nat.F32)
+                    ca.qimg = e.new_act(B, r.h, r.w, self.C_img * (3 if self.kind == "phydiff" else 1), dt=nat.F32)
                     max_scores = max(max_scores, B * n * n)
                     r.ca = ca
                     self.hfca.append(ca)
@@ -166,8 +170,10 @@ class UNetPlan:
                 else:
                     r.y = feat_dst[i]
         # mid: mid.0 -> temp, mid.1 -> x slot of the first up concat buffer
-        res_scratch(self.mids[0], e.new_act(B, self.mids[0].h, self.mids[0].w, self.mids[0].cout, stats=arena))
-        res_scratch(self.mids[1], up_res[0].cat.slice(0, up_res[0].cx))
+        # (SR3 has a single mid block, sr3/unet.py:77-81): the LAST one writes into the first up concat buffer
+        for m in self.mids[:-1]:
+            res_scratch(m, e.new_act(B, m.h, m.w, m.cout, stats=arena))
+        res_scratch(self.mids[-1], up_res[0].cat.slice(0, up_res[0].cx))
         # up path: each layer writes into the x slot of the next res block's concat buffer
         for k, r in enumerate(self.ups):
             nxt = next((q for q in self.ups[k + 1:] if q.kind == "res"), None) if k + 1 < len(self.ups) else None
@@ -207,7 +213,12 @@ class UNetPlan:
             tot = sum(B * self.C_img * (self.H >> (j + 1)) * (self.W >> (j + 1)) for j in range(4))
             self.haar_out = e.empty((tot,), torch.float32)
             self.haar_work = e.empty((B * self.C_img * self.H * self.W // 2 + 16,), torch.float32)
-        else:
+        elif self.kind == "phydiff":
+            tot = sum(B * 3 * self.C_img * (self.H >> (j + 1)) * (self.W >> (j + 1)) for j in range(4))
+            self.haar_out = e.empty((tot,), torch.float32)
+            self.haar_work = e.empty((B * self.C_img * self.H * self.W // 2 + 16,), torch.float32)
+            self.stencils = e.empty((B, 3, self.H, self.W), torch.float32)
+        elif self.kind == "srdiff":
             self.cond_feat = e.new_act(B, self.H // 4, self.W // 4, self.net.cond_proj.in_channels)
             self.cond_up = e.new_act(B, self.H, self.W, self.net.cond_proj.out_channels)
 
@@ -258,7 +269,7 @@ class UNetPlan:
                     pack_res(r)
                 else:
                     r.conv = e.pack_conv(r.mod.conv.weight, r.mod.conv.bias)
-                    if self.kind == "resdiff":
+                    if self.has_hfca:
                         ca, m = r.ca, r.ca.mod
                         ca.g, ca.b = e.f32(m.norm.weight), e.f32(m.norm.bias)
                         cc = ca.c
@@ -288,7 +299,7 @@ class UNetPlan:
                 self.fd_ctw = e.f32(fd.channel_transform.weight.reshape(fd.channel_transform.out_channels, -1))
                 self.fd_ctb = e.f32(fd.channel_transform.bias)
                 self.fd_hidden = self.fd_n0.shape[0]
-            else:
+            elif self.kind == "srdiff":
                 cp = self.net.cond_proj
                 self.cp_w = e.empty((64, cp.out_channels, cp.in_channels))
                 w = e.f32(cp.weight)
@@ -345,6 +356,30 @@ class UNetPlan:
                          nat.F32, ca.qimg.ld, st)
                 e.conv(ca.qimg, ca.wq, ca.q, bias=False, force_simt=True)
                 off += n
+        elif self.kind == "phydiff":
+            # condition-only work of phydiff/unet.py:262-314, done once per batch: stencil channels of the reflect-padded
+            # condition, the 3-band Haar queries and their 1x1 projections; cond and the stencils are written straight into
+            # their channel slices of the stem input [cond | x_t | Kx Ky Kxy]
+            C = self.C_img
+            stem = self.downs[0]
+            self.cond.copy_(cond.to(torch.float32))
+            nat.call("wsr_phy_stencils", self.cond.data_ptr(), B, C, self.H, self.W, self.stencils.data_ptr(), st)
+            e.nchw_to_act(self.cond, stem.xin.slice(0, C))
+            e.nchw_to_act(self.stencils, stem.xin.slice(2 * C, 3))
+            nat.call("wsr_haar_detail_bands", self.cond.data_ptr(), B, C, self.H, self.W, 4, self.haar_out.data_ptr(),
+                     self.haar_work.data_ptr(), st)
+            off = 0
+            for ca in self.hfca:
+                n = B * 3 * C * ca.h * ca.w
+                j = ca.level
+                assert (ca.h, ca.w) == (self.H >> (j + 1), self.W >> (j + 1))
+                nat.call("wsr_nchw_to_nhwc", self.haar_out.data_ptr() + 4 * off, B, 3 * C, ca.h, ca.w, ca.qimg.ptr,
+                         nat.F32, ca.qimg.ld, st)
+                e.conv(ca.qimg, ca.wq, ca.q, bias=False, force_simt=True)
+                off += n
+        elif self.kind == "sr3":
+            self.cond.copy_(cond.to(torch.float32))
+            e.nchw_to_act(self.cond, self.downs[0].xin.slice(0, self.C_img))
         else:
             src = cond.to(torch.float32).contiguous()
             e.nchw_to_act(src, self.cond_feat)
@@ -459,6 +494,9 @@ class UNetPlan:
                      self.fd_n0.data_ptr(), self.fd_n2.data_ptr(), self.fd_hidden, self.gate.data_ptr(), st)
             e.call("wsr_stem_assemble", x_t.data_ptr(), self.cond.data_ptr(), self.gate.data_ptr(), self.lf.data_ptr(),
                      self.hf.data_ptr(), B, self.C_img, self.H, self.W, stem.xin.ptr, stem.xin.dt, stem.xin.ld, st)
+        elif self.kind in ("phydiff", "sr3"):
+            xs = stem.xin.slice(self.C_img, self.C_img)         # channels [C, 2C) of [cond | x_t | ...]
+            e.call("wsr_nchw_to_nhwc", x_t.data_ptr(), B, self.C_img, self.H, self.W, xs.ptr, xs.dt, xs.ld, st)
         else:
             e.call("wsr_nchw_to_nhwc", x_t.data_ptr(), B, self.C_img, self.H, self.W, stem.xin.ptr, stem.xin.dt, stem.xin.ld, st)
         x = e.conv(stem.xin, stem.conv, stem.y)
@@ -468,7 +506,7 @@ class UNetPlan:
                 x = self._res_block(r, x, extra_res=extra)
             else:
                 x = e.conv(x, r.conv, r.y, stride=2, res=extra)
-                if self.kind == "resdiff":
+                if self.has_hfca:
                     self._hf_ca(r.ca)
         for r in self.mids:
             x = self._res_block(r, x)

@@ -31,6 +31,17 @@ def manifest(tag, cfg=None):
     for k, s in zip(keys, shapes):
         if cfg is not None and k.startswith("fd_spliter.noise_func."):
             s = (cfg["image_width"],) + tuple(s[1:])
+        if cfg is not None and cfg.get("image_channels", 1) != 1:
+            # multi-variable configurations: the stem, the HF-CA query projections and the head scale with C_img
+            c = cfg["image_channels"]
+            if k == "downs.0.weight":
+                s = (s[0], cfg["in_channel"]) + tuple(s[2:])
+            elif k.startswith("hf_ca_list.") and k.endswith(".q.weight"):
+                s = (s[0], s[1] * c) + tuple(s[2:])
+            elif k == "final_conv.block.3.weight":
+                s = (cfg["out_channel"],) + tuple(s[1:])
+            elif k == "final_conv.block.3.bias":
+                s = (cfg["out_channel"],)
         out.append((k, s))
     return out
 

@@ -1,6 +1,7 @@
 """CPU tests of the host-side logic: config parser, C-ABI library exports, state_dict compatibility, registry errors,
 schedule buffers of the product GaussianDiffusion vs the reference golden fixture, no-CPU-fallback behaviour."""
 import argparse
+import copy
 import ctypes
 import os
 import re
@@ -57,6 +58,8 @@ def test_invalid_arguments_are_rejected_before_any_launch():
 @pytest.mark.parametrize("tag,modname,cls,kw", [
     ("resdiff", "models.diffusion_models.resdiff.unet", "UNet", dict(in_channel=5)),
     ("srdiff", "models.diffusion_models.srdiff.unet", "UNet", dict(in_channel=1)),
+    ("sr3", "models.diffusion_models.sr3.unet", "UNet", dict(in_channel=2)),
+    ("phydiff", "models.diffusion_models.phydiff.unet", "UNet", dict(in_channel=5)),
 ])
 def test_state_dict_keys_and_shapes_match_reference(tag, modname, cls, kw):
     U = getattr(wsr.sub(modname), cls)
@@ -106,6 +109,16 @@ def test_registry_and_config_parser(tmp_path):
     bad = {"model": {"architecture": "nope"}}
     with pytest.raises(NotImplementedError):
         networks.define_diffusion(bad)
+    for arch, cls, inc in (("sr3", "SR3Diffusion", 2), ("phydiff", "PhyDiffDiffusion", 5)):
+        o2 = copy.deepcopy(opt)
+        o2["model"]["architecture"] = arch
+        o2["model"]["unet"]["in_channel"] = inc
+        m2 = networks.define_diffusion(o2)
+        assert type(m2).__name__ == cls and type(m2.denoise_fn).__module__.endswith(arch + ".unet")
+    o3 = copy.deepcopy(opt)
+    o3["model"]["architecture"] = "physrdiff"               # broken in the reference itself
+    with pytest.raises(NotImplementedError):
+        networks.define_diffusion(o3)
     opt["phase"] = "train"
     m = networks.define_diffusion(opt)                      # builds on CPU: parameters only, orthogonal init
     assert type(m).__name__ == "ResDiffDiffusion" and sum(p.numel() for p in m.parameters()) == 98870734

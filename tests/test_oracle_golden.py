@@ -103,6 +103,39 @@ def test_srdiff_step():
     assert rel_l2(eps, g["eps"]) < TOL
 
 
+@pytest.mark.parametrize("name", ["sr3_step_small", "phydiff_step_small", "phydiff_step_full_b1", "phydiff_step_c3_small"])
+def test_sr3_phydiff_step(name):
+    """the SR3 and PhyDiff ('ResDiff+Physics') denoisers against the real reference."""
+    g, spec = load_golden(name), CASES[name]
+    arch = name.split("_")[0]
+    sd = _sd(arch, spec["seed"], spec["cfg"])
+    np.testing.assert_allclose(_wsum(sd), g["wsum"].numpy(), rtol=1e-9)
+    fn = nets.sr3_unet if arch == "sr3" else nets.phydiff_unet
+    with torch.no_grad():
+        eps = fn(sd, torch.cat([g["cond"], g["x_t"]], 1), g["level"], spec["cfg"])
+    assert rel_l2(eps, g["eps"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["sr3_chain_small", "phydiff_chain_small"])
+def test_sr3_phydiff_chain(name):
+    g, spec = load_golden(name), CASES[name]
+    arch = name.split("_")[0]
+    sd = _sd(arch, spec["seed"], spec["cfg"])
+    fn = nets.sr3_unet if arch == "sr3" else nets.phydiff_unet
+    with torch.no_grad():
+        out = process.cond_chain(fn, sd, spec["cfg"], short_schedule(spec["T"]), g["cond"], g["noise"], add_cond=(arch == "phydiff"))
+    assert rel_l2(out, g["sr_out"]) < TOL
+
+
+def test_phy_stencils_known_answer():
+    """Reflect padding: on a horizontal ramp the x-difference is 1 inside and -1 in the last column (x[W] := x[W-2])."""
+    x = torch.arange(8, dtype=torch.float32).view(1, 1, 1, 8).repeat(1, 1, 4, 1)
+    st = nets.phy_stencils(x)
+    assert torch.equal(st[0, 0, :, :-1], torch.ones(4, 7)) and torch.equal(st[0, 0, :, -1], -torch.ones(4))
+    assert torch.equal(st[0, 1], torch.zeros(4, 8))
+    assert float(st[0, 2, 1, 0]) == 2.0 and float(st[0, 2, 1, 7]) == -2.0 and float(st[0, 2, 1, 3]) == 0.0
+
+
 def test_resdiff_param_grads_match_reference():
     """Oracle autograd vs the gradient summaries of the real reference's training step (model.py:61-68)."""
     from oracle.cases import grad_summary

@@ -124,3 +124,48 @@ def test_simple_cnn_vs_reference():
     err = rel_l2(out.cpu(), g["out"])
     print("\n[parity] simple_cnn rel-L2 = %.3e" % err)
     assert err < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# SR3 and PhyDiff ("ResDiff+Physics")
+# ----------------------------------------------------------------------------------------------------------------
+def _arch_net(arch, cfg, seed, precision):
+    U = wsr.sub("models.diffusion_models.%s.unet" % arch).UNet
+    net = U(in_channel=cfg["in_channel"], out_channel=cfg["out_channel"], norm_groups=cfg["norm_groups"],
+            inner_channel=cfg["inner_channel"], channel_mults=cfg["channel_mults"], attn_res=cfg["attn_res"],
+            res_blocks=cfg["res_blocks"], dropout=cfg["dropout"], image_height=cfg["image_height"],
+            image_width=cfg["image_width"], image_channels=cfg["image_channels"], precision=precision)
+    return fill_module(net, seed).to("cuda:0").eval()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["sr3_step_small", "phydiff_step_small", "phydiff_step_full_b1", "phydiff_step_c3_small"])
+def test_sr3_phydiff_step_vs_reference(name, precision):
+    g, spec = load_golden(name), CASES[name]
+    net = _arch_net(name.split("_")[0], spec["cfg"], spec["seed"], precision)
+    x = torch.cat([g["cond"], g["x_t"]], 1).cuda()
+    with torch.no_grad():
+        eps = net(x, g["level"].cuda())
+    err = rel_l2(eps.cpu(), g["eps"])
+    print("\n[parity] %s %s eps rel-L2 = %.3e" % (name, precision, err))
+    assert err < TOL[precision], err
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["sr3_chain_small", "phydiff_chain_small"])
+def test_sr3_phydiff_chain_vs_reference(name, precision):
+    g, spec = load_golden(name), CASES[name]
+    arch = name.split("_")[0]
+    mod = wsr.sub("models.diffusion_models.%s.%s_diffusion" % (arch, arch))
+    D = mod.SR3Diffusion if arch == "sr3" else mod.PhyDiffDiffusion
+    cfg = spec["cfg"]
+    net = _arch_net(arch, cfg, spec["seed"], precision)
+    diff = D(net, image_height=cfg["image_height"], image_width=cfg["image_width"], channels=cfg["image_channels"],
+             conditional=True).cuda()
+    diff.set_new_noise_schedule(short_schedule(spec["T"]), "cuda:0")
+    for use_graph in (False, True):
+        diff.use_cuda_graph = use_graph
+        out = diff.p_sample_loop(g["cond"].cuda(), noise_chain=g["noise"].cuda())
+        err = rel_l2(out.cpu(), g["sr_out"])
+        print("\n[parity] %s %s graph=%s final-field rel-L2 = %.3e" % (name, precision, use_graph, err))
+        assert err < TOL[precision], err
