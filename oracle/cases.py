@@ -45,6 +45,8 @@ CASES = {
     "resdiff_loss_small": dict(kind="resdiff_loss", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=31, t=400),
     # one training step: loss / numel -> backward (model.py:61-69); fixture = per-parameter gradient summaries
     "resdiff_grad_small": dict(kind="resdiff_grad", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=61, t=400),
+    "phydiff_grad_small": dict(kind="phydiff_grad", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=62, t=350),
+    "sr3_grad_small": dict(kind="sr3_grad", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=2), batch=2, seed=63, t=500),
     # priors and the RRDB-conditioned variant
     "simple_cnn": dict(kind="simple_cnn", batch=2, seed=41, lr_hw=(8, 16)),
     "rrdb_small": dict(kind="rrdb", batch=1, seed=42, lr_hw=(8, 16)),

@@ -69,8 +69,10 @@ def run_grad_case(ref, name, spec):
     random draws (t, continuous level, noise) injected and dropout = 0."""
     from .cases import grad_summary
     seed, b, cfg, t = spec["seed"], spec["batch"], spec["cfg"], spec["t"]
-    net = fill_module(_unet(ref, cfg), seed).train()
-    diff = ref.ResDiffDiffusion(net, image_height=cfg["image_height"], image_width=cfg["image_width"],
+    arch = spec["kind"].split("_")[0]
+    net = fill_module(_unet(ref, cfg, arch=arch), seed).train()
+    D = {"resdiff": ref.ResDiffDiffusion, "phydiff": ref.PhyDiffDiffusion, "sr3": ref.SR3Diffusion}[arch]
+    diff = D(net, image_height=cfg["image_height"], image_width=cfg["image_width"],
                                 channels=cfg["image_channels"], conditional=True)
     diff.set_new_noise_schedule(LINEAR_1000, "cpu")
     diff.set_loss("cpu")
@@ -96,7 +98,7 @@ def run_grad_case(ref, name, spec):
 
 def run_case(ref, name, spec):
     kind, seed, b = spec["kind"], spec["seed"], spec["batch"]
-    if kind == "resdiff_grad":
+    if kind in ("resdiff_grad", "phydiff_grad", "sr3_grad"):
         return run_grad_case(ref, name, spec)
     out = {}
     with torch.no_grad():

@@ -112,6 +112,26 @@ def resdiff_p_losses(sd, cfg, hr, sr, level, noise, loss_type="l1"):
     return loss, eps
 
 
+def arch_p_losses(arch, sd, cfg, hr, sr, level, noise, loss_type="l1"):
+    """p_losses of the 'resdiff' (:111-152), 'phydiff' (phydiff_diffusion.py:98-139; same residual target) and 'sr3'
+    (sr3_diffusion.py:101-137; target = HR itself) processes with the random draws injected."""
+    if arch == "resdiff":
+        return resdiff_p_losses(sd, cfg, hr, sr, level, noise, loss_type)
+    x0 = hr if arch == "sr3" else hr - sr
+    fn = nets.sr3_unet if arch == "sr3" else nets.phydiff_unet
+    x_noisy = q_sample(x0, level.view(-1, 1, 1, 1), noise)
+    eps = fn(sd, torch.cat([sr, x_noisy], dim=1), level.view(-1, 1), cfg)
+    loss = (noise - eps).abs().sum() if loss_type == "l1" else ((noise - eps) ** 2).sum()
+    return loss, eps
+
+
+def arch_param_grads(arch, sd, cfg, hr, sr, level, noise, loss_type="l1"):
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    loss, _ = arch_p_losses(arch, leaf, cfg, hr, sr, level, noise, loss_type)
+    (loss / hr.numel()).backward()
+    return loss.detach(), {k: v.grad for k, v in leaf.items() if v.grad is not None}
+
+
 def resdiff_param_grads(sd, cfg, hr, sr, level, noise, loss_type="l1"):
     """The reference's training step up to the optimizer (models/diffusion_models/model.py:61-68): sum-loss / numel ->
     backward.  Returns (sum-reduced loss, {name: gradient}) for every entry of ``sd`` that received a gradient."""

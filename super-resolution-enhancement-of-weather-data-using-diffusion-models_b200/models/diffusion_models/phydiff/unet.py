@@ -60,6 +60,17 @@ class UNet(nn.Module):
         pl.refresh_weights()
         return pl
 
+    def train_plan(self, batch, device=None, precision=None):
+        """Forward + backward schedule (``UNetTrainPlan``) for a given local batch size (cached)."""
+        from ....unet_train import UNetTrainPlan
+        device = device or next(self.parameters()).device
+        key = ("train", batch, str(device), precision or self.precision)
+        pl = self._plans.get(key)
+        if pl is None:
+            pl = UNetTrainPlan(self, batch, device, precision or self.precision)
+            self._plans[key] = pl
+        return pl
+
     def _apply(self, fn, *args, **kwargs):
         self._plans = {}           # .to() / .cuda() re-allocate the parameters: drop plans that point at the old storage
         return super()._apply(fn, *args, **kwargs)
@@ -70,10 +81,16 @@ class UNet(nn.Module):
         if x.shape[1] != 2 * c:
             raise AssertionError("expected cat([condition, x_t]) with %d channels, got %d" % (2 * c, x.shape[1]))
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("the hand-written backward pass covers the resdiff architecture only (DESIGN.md section 7); "
-                                      "run this architecture under torch.no_grad()")
+            # training step: the autograd node runs the hand-written backward pass (unet_train.py)
+            from ....autograd_glue import DenoiseFn
+            anchor = next(p for p in self.parameters() if p.requires_grad)
+            return DenoiseFn.apply(anchor, self, x, time)
         if self.training and self.dropout:
-            raise NotImplementedError("training-mode dropout of this architecture is not implemented in the CUDA path")
+            pl = self.train_plan(b, x.device)
+            pl.train_mode = True
+            pl.set_condition(x[:, :c])
+            pl.set_levels(time.reshape(b))
+            return pl.denoise(x[:, c:])
         pl = self.plan(b, x.device)
         pl.set_condition(x[:, :c])
         pl.set_levels(time.reshape(b))

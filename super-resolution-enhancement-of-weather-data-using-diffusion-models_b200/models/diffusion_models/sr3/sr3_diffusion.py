@@ -46,4 +46,7 @@ class SR3Diffusion(GaussianDiffusion):
         if not self.conditional:
             raise NotImplementedError("unconditional training is not part of the accelerated path")
         eps = self.denoise_fn(torch.cat([sr32, x_noisy], dim=1), level.view(b, -1))
+        if eps.requires_grad:
+            from ....autograd_glue import NoiseLossFn
+            return NoiseLossFn.apply(noise, eps, self.loss_type == 'l2')
         return self._noise_loss(noise, eps)

@@ -482,12 +482,11 @@ class UNetPlan:
         e.attention(ca.q, ca.kbuf, ca.vT, ca.obuf, self.scores[:B * n * n], self.probs[:B * n * n])
         e.conv(ca.obuf, ca.wout, ca.y, res=ca.x)
 
-    def run(self, x_t):
-        """One denoiser call on the current condition / level projection.  x_t: fp32 NCHW device tensor (B,C,H,W).
-        Leaves eps_hat in ``self.eps`` (fp32 NCHW)."""
+    def _stem_input(self, x_t):
+        """Per-step part of the stem input: ResDiff's noise gate + 5-channel assembly (fd_info_spliter.py:44-47,117), or x_t
+        written into its channel slice next to the condition-only channels (sr3 / phydiff), or x_t alone (srdiff)."""
         e, B = self.eng, self.B
         st = e.stream
-        e.call("wsr_fill_zero", self.stats.data_ptr(), self.stats.numel() * 8, st)
         stem = self.downs[0]
         if self.kind == "resdiff":
             e.call("wsr_fd_gate", self.cur_proj.data_ptr() + 4 * self.ne_off, self.P, 0, B, self.C_img, self.W,
@@ -499,6 +498,15 @@ class UNetPlan:
             e.call("wsr_nchw_to_nhwc", x_t.data_ptr(), B, self.C_img, self.H, self.W, xs.ptr, xs.dt, xs.ld, st)
         else:
             e.call("wsr_nchw_to_nhwc", x_t.data_ptr(), B, self.C_img, self.H, self.W, stem.xin.ptr, stem.xin.dt, stem.xin.ld, st)
+
+    def run(self, x_t):
+        """One denoiser call on the current condition / level projection.  x_t: fp32 NCHW device tensor (B,C,H,W).
+        Leaves eps_hat in ``self.eps`` (fp32 NCHW)."""
+        e, B = self.eng, self.B
+        st = e.stream
+        e.call("wsr_fill_zero", self.stats.data_ptr(), self.stats.numel() * 8, st)
+        stem = self.downs[0]
+        self._stem_input(x_t)
         x = e.conv(stem.xin, stem.conv, stem.y)
         for i, r in enumerate(self.downs[1:], start=1):
             extra = self.cond_up if (self.kind == "srdiff" and i == 2) else None

@@ -32,8 +32,9 @@ from .unet_plan import UNetPlan, _L
 
 class UNetTrainPlan(UNetPlan):
     def __init__(self, net, batch, device, precision="bf16", strict_tc=False):
-        if not hasattr(net, "fd_spliter"):
-            raise NotImplementedError("the training step is implemented for the 'resdiff' architecture only")
+        if hasattr(net, "cond_proj"):
+            raise NotImplementedError("the training step is implemented for the 'resdiff', 'phydiff' and 'sr3' architectures "
+                                      "(srdiff needs the cond_proj transposed-convolution weight gradient, not written yet)")
         self.drop_p = float(getattr(net, "dropout", 0.0) or 0.0)
         self.drop_seed = 0
         self.on_ready = None           # callback(lo, hi): gflat[lo:hi] is final (launch its all-reduce now)
@@ -106,17 +107,19 @@ class UNetTrainPlan(UNetPlan):
             if r.kind == "res":
                 res_params(r)
             else:
-                m = r.ca.mod
-                add(m.out.weight, m.out.bias, m.kv.weight, m.q.weight, m.norm.weight, m.norm.bias)
+                if self.has_hfca:
+                    m = r.ca.mod
+                    add(m.out.weight, m.out.bias, m.kv.weight, m.q.weight, m.norm.weight, m.norm.bias)
                 add(r.mod.conv.weight, r.mod.conv.bias)
         self._marks.append(len(order))
         stem = self.downs[0].mod
-        fd = net.fd_spliter
         add(stem.weight, stem.bias)
-        add(fd.noise_resSE.fc[0].weight, fd.noise_resSE.fc[2].weight, fd.sigma_resSE.fc[0].weight, fd.sigma_resSE.fc[2].weight,
-            fd.HF_guided_resSE.fc[0].weight, fd.HF_guided_resSE.fc[2].weight, fd.channel_transform.weight, fd.channel_transform.bias)
+        fd = getattr(net, "fd_spliter", None)
+        if fd is not None:
+            add(fd.noise_resSE.fc[0].weight, fd.noise_resSE.fc[2].weight, fd.sigma_resSE.fc[0].weight, fd.sigma_resSE.fc[2].weight,
+                fd.HF_guided_resSE.fc[0].weight, fd.HF_guided_resSE.fc[2].weight, fd.channel_transform.weight, fd.channel_transform.bias)
         # the stacked FeatureWiseAffine linears: weights, then biases, in projection order (= rows of proj_w / proj_b)
-        lins = [r.mod.res_block.noise_func.noise_func[0] for r in self._res_records()] + [fd.noise_func]
+        lins = [r.mod.res_block.noise_func.noise_func[0] for r in self._res_records()] + ([fd.noise_func] if fd is not None else [])
         proj_w_first = len(order)
         add(*[l.weight for l in lins])
         proj_b_first = len(order)
@@ -211,11 +214,12 @@ class UNetTrainPlan(UNetPlan):
         self.dtemb = e.empty((B, self.inner), torch.float32)
         self.deps = e.new_act(B, self.H, self.W, self.C_img)
         self.deps_in = e.empty((B, self.C_img, self.H, self.W), torch.float32)
-        self.dxin = e.new_act(B, self.H, self.W, 5 * self.C_img, dt=nat.F32)
-        self.g_lf = e.empty((B, self.C_img, self.H, self.W), torch.float32)
-        self.g_hf = e.empty((B, self.C_img, self.H, self.W), torch.float32)
-        nb = nat.call("wsr_fd_backward_workspace_bytes", B, self.C_img, self.H, self.W)
-        self.fd_bwork = e.empty((nb,), torch.uint8)
+        if self.kind == "resdiff":
+            self.dxin = e.new_act(B, self.H, self.W, 5 * self.C_img, dt=nat.F32)
+            self.g_lf = e.empty((B, self.C_img, self.H, self.W), torch.float32)
+            self.g_hf = e.empty((B, self.C_img, self.H, self.W), torch.float32)
+            nb = nat.call("wsr_fd_backward_workspace_bytes", B, self.C_img, self.H, self.W)
+            self.fd_bwork = e.empty((nb,), torch.uint8)
 
     def G(self, a):
         """Gradient buffer mirroring the activation slice ``a`` (same geometry; created on first use, zeroed per step)."""
@@ -279,9 +283,10 @@ class UNetTrainPlan(UNetPlan):
                     r.dconv = dg(r.mod.weight)
                 elif r.kind == "down":
                     r.dconv = dg(r.mod.conv.weight)
-                    m = r.ca.mod
-                    r.ca.dwk = dg(m.kv.weight[:r.ca.c])
-                    r.ca.dwout = dg(m.out.weight)
+                    if self.has_hfca:
+                        m = r.ca.mod
+                        r.ca.dwk = dg(m.kv.weight[:r.ca.c])
+                        r.ca.dwout = dg(m.out.weight)
             for r in self.ups:
                 if r.kind == "up":
                     w = r.mod.conv.weight
@@ -464,6 +469,29 @@ class UNetTrainPlan(UNetPlan):
         self._gtensors = list(new.values())
         self._garena = arena
 
+    def _fd_bwd(self, dy):
+        """Backward of FD_Info_Spliter (fd_info_spliter.py:37-117) from the gradient of the stem convolution's output."""
+        e, B = self.eng, self.B
+        st = e.stream
+        net = self.net
+        stem = self.downs[0]
+        C = self.C_img
+        e.conv(dy, stem.dconv, self.dxin, bias=False)
+        fd = net.fd_spliter
+        e.call("wsr_fd_gate_bwd", self.dxin.ptr, self.dxin.dt, self.dxin.ld, 2 * C, self.x_t.data_ptr(),
+               self.cur_proj.data_ptr() + 4 * self.ne_off, self.P, B, C, self.H, self.W, self.fd_n0.data_ptr(), self.fd_n2.data_ptr(),
+               self.fd_hidden, self.dproj.data_ptr() + 4 * self.ne_off, self.P, self.gv(fd.noise_resSE.fc[0].weight).data_ptr(),
+               self.gv(fd.noise_resSE.fc[2].weight).data_ptr(), st)
+        e.call("wsr_nhwc_to_nchw", self.dxin.ptr + 4 * 3 * C, nat.F32, self.dxin.ld, B, C, self.H, self.W, self.g_lf.data_ptr(), st)
+        e.call("wsr_nhwc_to_nchw", self.dxin.ptr + 4 * 4 * C, nat.F32, self.dxin.ld, B, C, self.H, self.W, self.g_hf.data_ptr(), st)
+        e.call("wsr_fd_backward", self.cond.data_ptr(), B, C, self.H, self.W, self.fd_s0.data_ptr(), self.fd_s2.data_ptr(),
+               self.fd_h0.data_ptr(), self.fd_h2.data_ptr(), self.fd_ctw.data_ptr(), self.g_lf.data_ptr(), self.g_hf.data_ptr(),
+               self.fd_work.data_ptr(), self.fd_bwork.data_ptr(), self.gv(fd.sigma_resSE.fc[0].weight).data_ptr(),
+               self.gv(fd.sigma_resSE.fc[2].weight).data_ptr(), self.gv(fd.HF_guided_resSE.fc[0].weight).data_ptr(),
+               self.gv(fd.HF_guided_resSE.fc[2].weight).data_ptr(), self.gv(fd.channel_transform.weight).data_ptr(),
+               self.gv(fd.channel_transform.bias).data_ptr(), st)
+
+
     def _ptr_sig(self):
         return tuple(p.data_ptr() for p in self.param_order)
 
@@ -500,7 +528,7 @@ class UNetTrainPlan(UNetPlan):
                 e.conv(G(r.y), r.dconv, G(x), taps=T.dgrad_upsample_taps(x.H, x.W), bias=False, res=G(x))
                 self._wgrad(x, G(r.y), r.mod.conv, T.forward_upsample_taps(x.H, x.W), up=2)
         self._ready(0)
-        for i in (1, 0):
+        for i in range(len(self.mids) - 1, -1, -1):
             self._res_block_bwd(self.mids[i], self._mid_inputs[i])
         for i in range(len(self.downs) - 1, 0, -1):
             r = self.downs[i]
@@ -508,32 +536,21 @@ class UNetTrainPlan(UNetPlan):
             if r.kind == "res":
                 self._res_block_bwd(r, x)
             else:
-                self._hf_ca_bwd(r.ca)
+                if self.has_hfca:
+                    self._hf_ca_bwd(r.ca)
                 dy, dx = G(r.y), G(x)
                 for tp in T.dgrad_down_taps(x.H, x.W):
                     e.conv(dy, r.dconv, dx, taps=tp, bias=False, res=dx)
                 self._wgrad(x, dy, r.mod.conv, T.forward_taps(3, 2, x.H, x.W))
         self._ready(1)
 
-        # stem and FD_Info_Spliter
+        # stem (its input is not a function of any parameter except through ResDiff's FD_Info_Spliter)
         stem = self.downs[0]
         C = self.C_img
         dy = G(stem.y)
-        e.conv(dy, stem.dconv, self.dxin, bias=False)
         self._wgrad(stem.xin, dy, stem.mod, T.forward_taps(3, 1, self.H, self.W))
-        fd = net.fd_spliter
-        e.call("wsr_fd_gate_bwd", self.dxin.ptr, self.dxin.dt, self.dxin.ld, 2 * C, self.x_t.data_ptr(),
-               self.cur_proj.data_ptr() + 4 * self.ne_off, self.P, B, C, self.H, self.W, self.fd_n0.data_ptr(), self.fd_n2.data_ptr(),
-               self.fd_hidden, self.dproj.data_ptr() + 4 * self.ne_off, self.P, self.gv(fd.noise_resSE.fc[0].weight).data_ptr(),
-               self.gv(fd.noise_resSE.fc[2].weight).data_ptr(), st)
-        e.call("wsr_nhwc_to_nchw", self.dxin.ptr + 4 * 3 * C, nat.F32, self.dxin.ld, B, C, self.H, self.W, self.g_lf.data_ptr(), st)
-        e.call("wsr_nhwc_to_nchw", self.dxin.ptr + 4 * 4 * C, nat.F32, self.dxin.ld, B, C, self.H, self.W, self.g_hf.data_ptr(), st)
-        e.call("wsr_fd_backward", self.cond.data_ptr(), B, C, self.H, self.W, self.fd_s0.data_ptr(), self.fd_s2.data_ptr(),
-               self.fd_h0.data_ptr(), self.fd_h2.data_ptr(), self.fd_ctw.data_ptr(), self.g_lf.data_ptr(), self.g_hf.data_ptr(),
-               self.fd_work.data_ptr(), self.fd_bwork.data_ptr(), self.gv(fd.sigma_resSE.fc[0].weight).data_ptr(),
-               self.gv(fd.sigma_resSE.fc[2].weight).data_ptr(), self.gv(fd.HF_guided_resSE.fc[0].weight).data_ptr(),
-               self.gv(fd.HF_guided_resSE.fc[2].weight).data_ptr(), self.gv(fd.channel_transform.weight).data_ptr(),
-               self.gv(fd.channel_transform.bias).data_ptr(), st)
+        if self.kind == "resdiff":
+            self._fd_bwd(dy)
 
         # level embedding: all FeatureWiseAffine linears at once, then the noise MLP
         e.call("wsr_linear_rows_bwd", self.cur_temb.data_ptr(), B, self.inner, self.proj_w.data_ptr(), self.dproj.data_ptr(), self.P,
@@ -576,10 +593,7 @@ class UNetTrainPlan(UNetPlan):
         st = e.stream
         e.call("wsr_fill_zero", self.stats.data_ptr(), self.stats.numel() * 8, st)
         stem = self.downs[0]
-        e.call("wsr_fd_gate", self.cur_proj.data_ptr() + 4 * self.ne_off, self.P, 0, B, self.C_img, self.W,
-               self.fd_n0.data_ptr(), self.fd_n2.data_ptr(), self.fd_hidden, self.gate.data_ptr(), st)
-        e.call("wsr_stem_assemble", x_t.data_ptr(), self.cond.data_ptr(), self.gate.data_ptr(), self.lf.data_ptr(),
-               self.hf.data_ptr(), B, self.C_img, self.H, self.W, stem.xin.ptr, stem.xin.dt, stem.xin.ld, st)
+        self._stem_input(x_t)
         x = e.conv(stem.xin, stem.conv, stem.y)
         self._down_inputs = {}
         for i, r in enumerate(self.downs[1:], start=1):
@@ -588,7 +602,8 @@ class UNetTrainPlan(UNetPlan):
                 x = self._res_block(r, x)
             else:
                 x = e.conv(x, r.conv, r.y, stride=2)
-                self._hf_ca(r.ca)
+                if self.has_hfca:
+                    self._hf_ca(r.ca)
         self._mid_inputs = {}
         for i, r in enumerate(self.mids):
             self._mid_inputs[i] = x

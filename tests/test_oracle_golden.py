@@ -156,3 +156,23 @@ def test_resdiff_param_grads_match_reference():
         assert abs(float(summ["dot/" + n]) - float(g["dot/" + n])) <= 2e-4 * ref_norm * np.sqrt(grads[n].numel()) + 1e-12, n
         if "full/" + n in g:
             assert rel_l2(grads[n], g["full/" + n]) < 1e-4 or ref_norm < 1e-12, n
+
+
+@pytest.mark.parametrize("name", ["phydiff_grad_small", "sr3_grad_small"])
+def test_phydiff_sr3_param_grads_match_reference(name):
+    """Oracle autograd vs the gradient summaries of the real reference's PhyDiff / SR3 training step."""
+    from oracle.cases import grad_summary
+    g, spec = load_golden(name), CASES[name]
+    arch = name.split("_")[0]
+    sd = _sd(arch, spec["seed"], spec["cfg"])
+    np.testing.assert_allclose(_wsum(sd), g["wsum"].numpy(), rtol=1e-9)
+    loss, grads = process.arch_param_grads(arch, sd, spec["cfg"], g["hr"], g["sr"], g["level"], g["noise"])
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 1e-5
+    names = [str(n) for n in g["names"]]
+    assert sorted(names) == sorted(grads.keys())
+    summ = grad_summary([(n, grads[n]) for n in names], spec["seed"])
+    for n in names:
+        ref_norm = float(g["norm/" + n])
+        assert abs(float(summ["norm/" + n]) - ref_norm) <= 1e-4 * ref_norm + 1e-12, n
+        if "full/" + n in g:
+            assert rel_l2(grads[n], g["full/" + n]) < 1e-4 or ref_norm < 1e-12, n

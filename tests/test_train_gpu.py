@@ -291,9 +291,10 @@ def test_fused_adam_matches_torch_adam():
 # ----------------------------------------------------------------------------------------------------------------
 # the whole training step against the reference
 # ----------------------------------------------------------------------------------------------------------------
-def _build(cfg, seed, precision):
-    U = wsr.sub("models.diffusion_models.resdiff.unet").UNet
-    D = wsr.sub("models.diffusion_models.resdiff.resdiff_diffusion").ResDiffDiffusion
+def _build(cfg, seed, precision, arch="resdiff"):
+    U = wsr.sub("models.diffusion_models.%s.unet" % arch).UNet
+    D = getattr(wsr.sub("models.diffusion_models.%s.%s_diffusion" % (arch, arch)),
+                {"resdiff": "ResDiffDiffusion", "phydiff": "PhyDiffDiffusion", "sr3": "SR3Diffusion"}[arch])
     net = U(in_channel=cfg["in_channel"], out_channel=cfg["out_channel"], norm_groups=cfg["norm_groups"],
             inner_channel=cfg["inner_channel"], channel_mults=cfg["channel_mults"], attn_res=cfg["attn_res"],
             res_blocks=cfg["res_blocks"], dropout=cfg["dropout"], image_height=cfg["image_height"],
@@ -320,17 +321,18 @@ def _train_backward(diff, g, spec):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_training_step_gradients_vs_reference(precision):
+@pytest.mark.parametrize("arch", ["resdiff", "phydiff", "sr3"])
+def test_training_step_gradients_vs_reference(arch, precision):
     from oracle.cases import grad_summary
     from conftest import manifest
     from oracle.weights import seeded_state_dict
-    g, spec = load_golden("resdiff_grad_small"), CASES["resdiff_grad_small"]
+    g, spec = load_golden(arch + "_grad_small"), CASES[arch + "_grad_small"]
     cfg = spec["cfg"]
-    net, diff = _build(cfg, spec["seed"], precision)
+    net, diff = _build(cfg, spec["seed"], precision, arch)
     loss = _train_backward(diff, g, spec)
     rel_loss = abs(loss - float(g["loss"])) / float(g["loss"])
-    sd = seeded_state_dict(manifest("resdiff", cfg), spec["seed"])
-    _, oracle_grads = process.resdiff_param_grads(sd, cfg, g["hr"], g["sr"], g["level"], g["noise"])
+    sd = seeded_state_dict(manifest(arch, cfg), spec["seed"])
+    _, oracle_grads = process.arch_param_grads(arch, sd, cfg, g["hr"], g["sr"], g["level"], g["noise"])
     tol_t, tol_all = (2e-4, 1e-4) if precision == "fp32" else (1.6e-1, 1.5e-1)
     named = dict(net.named_parameters())
     assert sorted(named) == sorted(str(n) for n in g["names"])
@@ -355,7 +357,7 @@ def test_training_step_gradients_vs_reference(precision):
         if rel > tol_n and err > tol_t * 1e-3 * math.sqrt(den):
             bad.append(lines[-1])
     total = math.sqrt(num / den)
-    print("\n[parity] training step %s: loss rel err %.3e, whole-gradient rel-L2 %.3e, %d / %d tensors above %.0e"
+    print("\n[parity] training step " + arch + " %s: loss rel err %.3e, whole-gradient rel-L2 %.3e, %d / %d tensors above %.0e"
           % (precision, rel_loss, total, len(bad), len(lines), tol_t))
     if bad:
         print("\n".join(bad[:40]))
