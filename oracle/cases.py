@@ -47,6 +47,7 @@ CASES = {
     "resdiff_grad_small": dict(kind="resdiff_grad", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=61, t=400),
     "phydiff_grad_small": dict(kind="phydiff_grad", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=62, t=350),
     "sr3_grad_small": dict(kind="sr3_grad", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=2), batch=2, seed=63, t=500),
+    "srdiff_grad_small": dict(kind="srdiff_grad", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=1), batch=2, seed=64, t=450),
     # priors and the RRDB-conditioned variant
     "simple_cnn": dict(kind="simple_cnn", batch=2, seed=41, lr_hw=(8, 16)),
     "rrdb_small": dict(kind="rrdb", batch=1, seed=42, lr_hw=(8, 16)),

@@ -70,13 +70,18 @@ def run_grad_case(ref, name, spec):
     from .cases import grad_summary
     seed, b, cfg, t = spec["seed"], spec["batch"], spec["cfg"], spec["t"]
     arch = spec["kind"].split("_")[0]
-    net = fill_module(_unet(ref, cfg, arch=arch), seed).train()
-    D = {"resdiff": ref.ResDiffDiffusion, "phydiff": ref.PhyDiffDiffusion, "sr3": ref.SR3Diffusion}[arch]
+    net = fill_module(_unet(ref, cfg, arch=arch, srdiff=(arch == "srdiff")), seed).train()
+    D = {"resdiff": ref.ResDiffDiffusion, "phydiff": ref.PhyDiffDiffusion, "sr3": ref.SR3Diffusion, "srdiff": ref.SRDiffDiffusion}[arch]
     diff = D(net, image_height=cfg["image_height"], image_width=cfg["image_width"],
                                 channels=cfg["image_channels"], conditional=True)
     diff.set_new_noise_schedule(LINEAR_1000, "cpu")
     diff.set_loss("cpu")
-    _, sr, hr = fields(name, b, cfg["image_channels"], cfg["image_height"], cfg["image_width"], seed)
+    lr, sr, hr = fields(name, b, cfg["image_channels"], cfg["image_height"], cfg["image_width"], seed)
+    if arch == "srdiff":
+        # frozen encoder, as init_rrdb_encoder(lock_weights=True) leaves it (srdiff_diffusion.py:59-75)
+        diff.rrdb_encoder = fill_module(ref.RRDBNet(1, 1, 64, 17, 32).eval(), seed + 1)
+        for p_ in diff.rrdb_encoder.parameters():
+            p_.requires_grad_(False)
     noise = seeded_randn(name + ".noise", sr.shape, seed)
     sap = diff.sqrt_alphas_cumprod_prev
     u = np.random.RandomState(seed).uniform(sap[t - 1], sap[t], size=b)
@@ -84,12 +89,12 @@ def run_grad_case(ref, name, spec):
     np.random.randint = lambda *a, **k: t
     np.random.uniform = lambda *a, **k: u
     try:
-        loss = diff.p_losses({"HR": hr, "SR": sr}, noise=noise)
+        loss = diff.p_losses({"HR": hr, "SR": sr, "LR": lr}, noise=noise)
     finally:
         np.random.randint, np.random.uniform = _ri, _un
     l_pix = loss.sum() / int(hr.numel())
     l_pix.backward()
-    out = dict(hr=hr, sr=sr, noise=noise, level=torch.FloatTensor(u), loss=loss.detach().reshape(1), wsum=_checksum(net))
+    out = dict(hr=hr, sr=sr, lr=lr, noise=noise, level=torch.FloatTensor(u), loss=loss.detach().reshape(1), wsum=_checksum(net))
     named = [(n, p.grad) for n, p in net.named_parameters() if p.grad is not None]
     out["names"] = np.array([n for n, _ in named])
     out.update(grad_summary(named, seed))
@@ -98,7 +103,7 @@ def run_grad_case(ref, name, spec):
 
 def run_case(ref, name, spec):
     kind, seed, b = spec["kind"], spec["seed"], spec["batch"]
-    if kind in ("resdiff_grad", "phydiff_grad", "sr3_grad"):
+    if kind in ("resdiff_grad", "phydiff_grad", "sr3_grad", "srdiff_grad"):
         return run_grad_case(ref, name, spec)
     out = {}
     with torch.no_grad():

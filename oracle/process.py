@@ -125,6 +125,19 @@ def arch_p_losses(arch, sd, cfg, hr, sr, level, noise, loss_type="l1"):
     return loss, eps
 
 
+def srdiff_param_grads(unet_sd, rrdb_sd, cfg, lr, hr, sr, level, noise, loss_type="l1"):
+    """SRDiff training step with the frozen RRDB encoder (srdiff_diffusion.py:161-216, lock_weights=True: no extra RRDB
+    loss term): gradients of the UNet parameters (incl. cond_proj) only."""
+    with torch.no_grad():
+        _, feas = nets.rrdb_net(rrdb_sd, lr)
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in unet_sd.items()}
+    x_noisy = q_sample(hr - sr, level.view(-1, 1, 1, 1), noise)
+    eps = nets.srdiff_unet(leaf, feas, x_noisy, level.view(-1, 1), cfg)
+    loss = (noise - eps).abs().sum() if loss_type == "l1" else ((noise - eps) ** 2).sum()
+    (loss / hr.numel()).backward()
+    return loss.detach(), {k: v.grad for k, v in leaf.items() if v.grad is not None}
+
+
 def arch_param_grads(arch, sd, cfg, hr, sr, level, noise, loss_type="l1"):
     leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
     loss, _ = arch_p_losses(arch, leaf, cfg, hr, sr, level, noise, loss_type)

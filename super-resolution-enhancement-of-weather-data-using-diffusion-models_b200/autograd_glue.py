@@ -18,6 +18,17 @@ weights_epoch = 0          # bumped by every optimizer step that writes paramete
 class DenoiseFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, net, x, time):
+        if isinstance(x, (tuple, list)):
+            # SRDiff: x = (18 RRDB feature maps, x_t); the condition is cat(feas[2::3]) (srdiff/unet.py:117-118)
+            feas, x_t = x
+            b = x_t.shape[0]
+            pl = net.train_plan(b, x_t.device)
+            pl.train_mode = bool(net.training)
+            pl.set_condition(torch.cat(list(feas[2::3]), dim=1))
+            pl.set_levels(time.reshape(b))
+            eps = pl.denoise(x_t)
+            ctx.pl, ctx.net = pl, net
+            return eps
         b, c = x.shape[0], net.image_channels
         pl = net.train_plan(b, x.device)
         pl.train_mode = bool(net.training)

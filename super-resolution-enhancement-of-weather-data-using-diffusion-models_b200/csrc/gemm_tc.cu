@@ -1217,6 +1217,7 @@ extern "C" int wsr_conv_taps_tc(const WsrConvDesc* d, const WsrTapTable* t, void
   if (rc) return rc;
   rc = validate_taps(t);
   if (rc) return rc;
+  WSR_REQUIRE(t->in_sub <= 2, WSR_E_UNSUPPORTED, "conv_taps_tc: in_sub=%d (1 or 2)", t->in_sub);
   WSR_REQUIRE(d->x_dtype == WSR_BF16, WSR_E_UNSUPPORTED, "conv_taps_tc: bf16 operands only");
   WSR_REQUIRE(d->Cin % 64 == 0 && d->x_ld % 8 == 0 && (((uintptr_t)d->x) & 15) == 0 && (((uintptr_t)d->w) & 15) == 0,
               WSR_E_UNSUPPORTED, "conv_taps_tc: Cin %% 64, pitch %% 8 and 16-byte alignment required (Cin=%d ld=%d)", d->Cin, d->x_ld);

@@ -203,7 +203,7 @@ namespace wsr {
 int validate_taps(const WsrTapTable* t) {
   WSR_REQUIRE(t != nullptr, WSR_E_INVALID, "taps: null table");
   WSR_REQUIRE(t->ntaps > 0 && t->ntaps <= WSR_MAX_TAPS, WSR_E_INVALID, "taps: ntaps=%d", t->ntaps);
-  WSR_REQUIRE(t->in_sub == 1 || t->in_sub == 2, WSR_E_UNSUPPORTED, "taps: in_sub=%d (1 or 2)", t->in_sub);
+  WSR_REQUIRE(t->in_sub == 1 || t->in_sub == 2 || t->in_sub == 4, WSR_E_UNSUPPORTED, "taps: in_sub=%d (1, 2; 4 on the SIMT kernels)", t->in_sub);
   WSR_REQUIRE(t->GH > 0 && t->GW > 0 && t->OH > 0 && t->OW > 0 && t->out_mul >= 1, WSR_E_INVALID, "taps: bad grid");
   WSR_REQUIRE(t->out_py >= 0 && t->out_px >= 0 && (t->GH - 1) * t->out_mul + t->out_py < t->OH && (t->GW - 1) * t->out_mul + t->out_px < t->OW,
               WSR_E_INVALID, "taps: output grid exceeds the output tensor");

@@ -243,6 +243,7 @@ extern "C" int wsr_conv_wgrad_tc(const WsrWgradDesc* d, const WsrTapTable* t, vo
   WSR_REQUIRE(d->x && d->dy && d->dw, WSR_E_INVALID, "wgrad_tc: null x/dy/dw");
   int rc = validate_taps(t);
   if (rc) return rc;
+  WSR_REQUIRE(t->in_sub <= 2, WSR_E_UNSUPPORTED, "wgrad_tc: in_sub=%d (1 or 2)", t->in_sub);
   WSR_REQUIRE(d->x_dtype == WSR_BF16 && d->dy_dtype == WSR_BF16, WSR_E_UNSUPPORTED, "wgrad_tc: bf16 operands only");
   WSR_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0 && d->x_ld >= d->Cin && d->dy_ld >= d->Cout, WSR_E_INVALID, "wgrad_tc: bad shape");
   WSR_REQUIRE(d->x_ld % 8 == 0 && d->dy_ld % 8 == 0 && (((uintptr_t)d->x) & 15) == 0 && (((uintptr_t)d->dy) & 15) == 0, WSR_E_UNSUPPORTED,

@@ -488,7 +488,7 @@ class Engine:
             return False
         if taps.out_mul != 1 or taps.GH != taps.OH or taps.GW != taps.OW:
             return False
-        if taps.in_sub == 2 and (x.H % 2 or x.W % 2):
+        if taps.in_sub > 2 or (taps.in_sub == 2 and (x.H % 2 or x.W % 2)):
             return False
         lw, lh = (x.W, x.H) if up == 2 else (taps.GW, taps.GH)
         t1 = min(lw, 64)

@@ -2,7 +2,6 @@
 then T reverse steps of the SRDiff UNet conditioned on 6 of its 18 feature maps."""
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 from .... import _native as nat
 from ...rrdb_encoder.RRDBNet import RRDBNet
@@ -79,5 +78,8 @@ class SRDiffDiffusion(GaussianDiffusion):
         nat.call("wsr_q_sample", hr32.data_ptr(), sr32.data_ptr(), noise.data_ptr(), level.data_ptr(), b,
                  sr32[0].numel(), x_noisy.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
         eps = self.denoise_fn((feas, x_noisy), level.view(b, -1))
-        del rrdb_sr, F
+        del rrdb_sr          # locked encoder: the reference's extra l1(rrdb_sr, HR) term does not apply (:212-214)
+        if eps.requires_grad:
+            from ....autograd_glue import NoiseLossFn
+            return NoiseLossFn.apply(noise, eps, self.loss_type == 'l2')
         return self._noise_loss(noise, eps)

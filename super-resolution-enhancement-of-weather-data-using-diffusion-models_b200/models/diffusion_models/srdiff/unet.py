@@ -44,12 +44,33 @@ class UNet(nn.Module):
         pl.refresh_weights()
         return pl
 
+    def train_plan(self, batch, device=None, precision=None):
+        """Forward + backward schedule (``UNetTrainPlan``) for a given local batch size (cached)."""
+        from ....unet_train import UNetTrainPlan
+        device = device or next(self.parameters()).device
+        key = ("train", batch, str(device), precision or self.precision)
+        pl = self._plans.get(key)
+        if pl is None:
+            pl = UNetTrainPlan(self, batch, device, precision or self.precision)
+            self._plans[key] = pl
+        return pl
+
+    def _apply(self, fn, *args, **kwargs):
+        self._plans = {}           # .to() / .cuda() re-allocate the parameters: drop plans that point at the old storage
+        return super()._apply(fn, *args, **kwargs)
+
     def forward(self, x, time):
-        if self.training and self.dropout:
-            raise NotImplementedError("training-mode dropout is not implemented in the CUDA path yet")
         feas, x_t = x
         b = x_t.shape[0]
-        pl = self.plan(b, x_t.device)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from ....autograd_glue import DenoiseFn
+            anchor = next(p for p in self.parameters() if p.requires_grad)
+            return DenoiseFn.apply(anchor, self, (list(feas), x_t), time)
+        if self.training and self.dropout:
+            pl = self.train_plan(b, x_t.device)
+            pl.train_mode = True
+        else:
+            pl = self.plan(b, x_t.device)
         pl.set_condition(torch.cat(list(feas[2::3]), dim=1))
         pl.set_levels(time.reshape(b))
         return pl.denoise(x_t)

@@ -108,3 +108,23 @@ def upsample_dgrad_weight(weight):
                     acc = acc + w[:, :, ky, kx]
             out[:, :, r + 1, s + 1] = acc.t()
     return out
+
+
+def conv_transpose_k8s4_wgrad_taps(h, w):
+    """Weight gradient of ConvTranspose2d(k=8, s=4, p=2) (srdiff/unet.py:43-45) with input (h, w) and output (4h, 4w):
+        dW[ci][co][ky][kx] = sum_{n,i,j} x[n,ci,i,j] * dY[n,co,4i+ky-2,4j+kx-2]
+    which IS the weight gradient of a stride-4 8x8 convolution whose input is dY and whose output gradient is x -- so the
+    generic tap-table kernel applies with the operand roles swapped (loop grid = the low-resolution grid, in_sub = 4).
+    64 taps = four tables of 16 (two kernel rows each); wtap = ky*8 + kx indexes the reference's weight layout directly."""
+    out = []
+    for q in range(4):
+        taps = []
+        for ky in (2 * q, 2 * q + 1):
+            py = (ky - 2) % 4
+            dy = (ky - 2 - py) // 4
+            for kx in range(8):
+                px = (kx - 2) % 4
+                dx = (kx - 2 - px) // 4
+                taps.append((py, px, dy, dx, ky * 8 + kx))
+        out.append(_table(h, w, h, w, 4, 1, 0, 0, taps))
+    return out

@@ -32,9 +32,6 @@ from .unet_plan import UNetPlan, _L
 
 class UNetTrainPlan(UNetPlan):
     def __init__(self, net, batch, device, precision="bf16", strict_tc=False):
-        if hasattr(net, "cond_proj"):
-            raise NotImplementedError("the training step is implemented for the 'resdiff', 'phydiff' and 'sr3' architectures "
-                                      "(srdiff needs the cond_proj transposed-convolution weight gradient, not written yet)")
         self.drop_p = float(getattr(net, "dropout", 0.0) or 0.0)
         self.drop_seed = 0
         self.on_ready = None           # callback(lo, hi): gflat[lo:hi] is final (launch its all-reduce now)
@@ -114,6 +111,8 @@ class UNetTrainPlan(UNetPlan):
         self._marks.append(len(order))
         stem = self.downs[0].mod
         add(stem.weight, stem.bias)
+        if self.kind == "srdiff":
+            add(net.cond_proj.weight, net.cond_proj.bias)
         fd = getattr(net, "fd_spliter", None)
         if fd is not None:
             add(fd.noise_resSE.fc[0].weight, fd.noise_resSE.fc[2].weight, fd.sigma_resSE.fc[0].weight, fd.sigma_resSE.fc[2].weight,
@@ -551,6 +550,16 @@ class UNetTrainPlan(UNetPlan):
         self._wgrad(stem.xin, dy, stem.mod, T.forward_taps(3, 1, self.H, self.W))
         if self.kind == "resdiff":
             self._fd_bwd(dy)
+        elif self.kind == "srdiff":
+            # cond = cond_proj(cat(feas[2::3])) was added to the output of downs[2] (srdiff/unet.py:118,126-127): its gradient is
+            # the gradient of that output; the RRDB encoder is frozen (lock_weights), so only cond_proj's parameters need it
+            cp = net.cond_proj
+            gy = G(self.downs[2].y)
+            gw = self.gv(cp.weight)
+            co_t = cp.out_channels
+            for tp in T.conv_transpose_k8s4_wgrad_taps(self.cond_feat.H, self.cond_feat.W):
+                e.wgrad(gy, self.cond_feat, tp, gw, (1, co_t * 64, 64), None, 1, force_simt=True)
+            e.call("wsr_col_sums", gy.ptr, gy.dt, B * gy.H * gy.W, gy.C, gy.ld, self.gv(cp.bias).data_ptr(), st)
 
         # level embedding: all FeatureWiseAffine linears at once, then the noise MLP
         e.call("wsr_linear_rows_bwd", self.cur_temb.data_ptr(), B, self.inner, self.proj_w.data_ptr(), self.dproj.data_ptr(), self.P,
@@ -598,10 +607,11 @@ class UNetTrainPlan(UNetPlan):
         self._down_inputs = {}
         for i, r in enumerate(self.downs[1:], start=1):
             self._down_inputs[i] = x
+            extra = self.cond_up if (self.kind == "srdiff" and i == 2) else None
             if r.kind == "res":
-                x = self._res_block(r, x)
+                x = self._res_block(r, x, extra_res=extra)
             else:
-                x = e.conv(x, r.conv, r.y, stride=2)
+                x = e.conv(x, r.conv, r.y, stride=2, res=extra)
                 if self.has_hfca:
                     self._hf_ca(r.ca)
         self._mid_inputs = {}

@@ -176,3 +176,19 @@ def test_phydiff_sr3_param_grads_match_reference(name):
         assert abs(float(summ["norm/" + n]) - ref_norm) <= 1e-4 * ref_norm + 1e-12, n
         if "full/" + n in g:
             assert rel_l2(grads[n], g["full/" + n]) < 1e-4 or ref_norm < 1e-12, n
+
+
+def test_srdiff_param_grads_match_reference():
+    """SRDiff training step with the frozen RRDB encoder: oracle autograd vs the real reference's gradient summaries."""
+    from oracle.cases import grad_summary
+    g, spec = load_golden("srdiff_grad_small"), CASES["srdiff_grad_small"]
+    sd = _sd("srdiff", spec["seed"], spec["cfg"])
+    loss, grads = process.srdiff_param_grads(sd, _sd("rrdb", spec["seed"] + 1), spec["cfg"], g["lr"], g["hr"], g["sr"], g["level"], g["noise"])
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 1e-5
+    names = [str(n) for n in g["names"]]
+    assert sorted(names) == sorted(grads.keys()) and "cond_proj.weight" in names
+    summ = grad_summary([(n, grads[n]) for n in names], spec["seed"])
+    assert float(g["norm/cond_proj.weight"]) > 0
+    for n in names:
+        ref_norm = float(g["norm/" + n])
+        assert abs(float(summ["norm/" + n]) - ref_norm) <= 1e-4 * ref_norm + 1e-12, n

@@ -478,3 +478,61 @@ def test_batched_weight_refresh_is_bit_identical_to_the_per_tensor_packs(precisi
     again = snapshot()
     for k in eager:
         assert torch.equal(again[k], eager[k]), k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_srdiff_training_step_gradients_vs_reference(precision):
+    """SRDiff (RRDB-conditioned) training step: frozen encoder forward, UNet forward + hand-written backward including the
+    cond_proj transposed-convolution weight gradient (expressed as a stride-4 tap-table weight gradient with the operand
+    roles swapped).  Every UNet parameter gradient against the oracle's autograd, which is pinned to the REAL reference's
+    gradient summaries (tests/golden/srdiff_grad_small.npz)."""
+    from conftest import manifest
+    from oracle.weights import seeded_state_dict
+    g, spec = load_golden("srdiff_grad_small"), CASES["srdiff_grad_small"]
+    cfg = spec["cfg"]
+    U = wsr.sub("models.diffusion_models.srdiff.unet").UNet
+    D = wsr.sub("models.diffusion_models.srdiff.srdiff_diffusion").SRDiffDiffusion
+    R = wsr.sub("models.rrdb_encoder.RRDBNet").RRDBNet
+    net = U(in_channel=cfg["in_channel"], out_channel=cfg["out_channel"], norm_groups=32, inner_channel=64,
+            channel_mults=cfg["channel_mults"], attn_res=cfg["attn_res"], res_blocks=2, dropout=0, image_height=32,
+            image_width=64, image_channels=1, precision=precision)
+    net = fill_module(net, spec["seed"]).cuda().train()
+    diff = D(net, image_height=32, image_width=64, channels=1, conditional=True).cuda()
+    diff.rrdb_encoder = fill_module(R(1, 1, 64, 17, 32, precision=precision), spec["seed"] + 1).cuda().eval()
+    for p in diff.rrdb_encoder.parameters():
+        p.requires_grad_(False)
+    diff.set_new_noise_schedule(LINEAR_1000, "cuda:0")
+    diff.set_loss("cuda:0")
+    u = g["level"].numpy().astype(np.float64)
+    ri, un = np.random.randint, np.random.uniform
+    np.random.randint = lambda *a, **k: spec["t"]
+    np.random.uniform = lambda *a, **k: u
+    try:
+        loss = diff.p_losses({"HR": g["hr"].cuda(), "SR": g["sr"].cuda(), "LR": g["lr"].cuda()}, noise=g["noise"].cuda())
+    finally:
+        np.random.randint, np.random.uniform = ri, un
+    (loss.sum() / int(g["hr"].numel())).backward()
+    rel_loss = abs(float(loss) - float(g["loss"])) / float(g["loss"])
+    _, oracle_grads = process.srdiff_param_grads(seeded_state_dict(manifest("srdiff", cfg), spec["seed"]),
+                                                 seeded_state_dict(manifest("rrdb"), spec["seed"] + 1), cfg, g["lr"], g["hr"], g["sr"],
+                                                 g["level"], g["noise"])
+    num = den = 0.0
+    worst = (0.0, "")
+    for n, p in net.named_parameters():
+        assert p.grad is not None, n
+        ref = oracle_grads[n].double()
+        err = float((p.grad.detach().cpu().double() - ref).norm())
+        num += err ** 2
+        den += float(ref.norm()) ** 2
+        ref_norm = float(g["norm/" + n])
+        assert abs(float(ref.norm()) - ref_norm) <= 1e-3 * ref_norm + 1e-12, n
+        if ref.numel() >= 16 and float(ref.norm()) > 0:
+            worst = max(worst, (err / float(ref.norm()), n))
+    total = math.sqrt(num / den)
+    cp = rel_l2(net.cond_proj.weight.grad.cpu(), oracle_grads["cond_proj.weight"])
+    print("\n[parity] srdiff training step %s: loss rel err %.3e, whole-gradient rel-L2 %.3e, cond_proj.weight %.3e, worst tensor %.3e (%s)"
+          % (precision, rel_loss, total, cp, worst[0], worst[1]))
+    assert rel_loss < (1e-4 if precision == "fp32" else 2e-2)
+    assert total < (1e-4 if precision == "fp32" else 1.5e-1)
+    assert cp < (2e-4 if precision == "fp32" else 1.6e-1)
+    assert worst[0] < (2e-4 if precision == "fp32" else 2.5e-1), worst
