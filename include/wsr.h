@@ -318,6 +318,19 @@ int wsr_haar_detail_bands(const float* img, int B, int C, int H, int W, int leve
 int wsr_phy_stencils(const float* cond, int B, int C, int H, int W, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * The steps either side of the sampling loop, fp32 NCHW planes (plane = one (sample, variable) image).
+ * ------------------------------------------------------------------------------------------------------------- */
+/* F.interpolate(x, scale_factor=scale, mode="bicubic") of the collate (data/dataset_builder.py:374-380): A = -0.75,
+ * align_corners=False, border taps clamped.  src (planes, h, w) -> dst (planes, h*scale, w*scale). */
+int wsr_bicubic_upsample(const float* src, int planes, int h, int w, int scale, float* dst, void* stream);
+/* StandardScaling.transform / .revert (data/transforms.py:391-409) with per-plane statistics (the reference picks them per
+ * sample by month and per variable, transforms.py:116-138): inverse = 0: (x - mean) / std; inverse = 1: std * x + mean. */
+int wsr_standard_scale(const float* x, int planes, int64_t hw, const float* mean, const float* stdv, int inverse, float* y, void* stream);
+/* One pass for MAE / MSE / RMSE / MR (training/metrics.py:75-201): acc[0] += sum |d|, acc[1] += sum d^2, acc[2] += sum d (doubles),
+ * d = scale[plane] * (pred - target); scale = per-plane std folds the inverse transform in (the means cancel), or NULL. */
+int wsr_error_sums(const float* pred, const float* target, int planes, int64_t hw, const float* scale, double* acc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * DDPM process kernels (models/diffusion_models/diffusion.py).
  * ------------------------------------------------------------------------------------------------------------- */
 /* Fused reverse step (diffusion.py:124-125,139-141,168-169,191-192):

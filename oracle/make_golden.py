@@ -210,7 +210,46 @@ def schedule_fixture(ref):
     return out
 
 
+def edge_fixture():
+    """collate interpolation, GlobalStandardScaling fit / transform / revert, MAE / MSE / RMSE / MR -- all through
+    the reference's own classes (data/dataset_builder.py:374-380 is a bare F.interpolate call, reproduced verbatim)."""
+    from torch.nn.functional import interpolate
+    edge = ref_shims.import_reference_edge()
+    out = {}
+    lr = seeded_randn("edge.lr", (3, 2, 8, 16), 71)
+    out["lr"] = lr
+    out["sr"] = torch.cat([interpolate(lr[i:i + 1], scale_factor=4, mode="bicubic") for i in range(3)])
+    # two months with different statistics, two fitting batches each
+    stats = {}
+    for month, (mu, sd) in {1: (270.0, 9.0), 7: (291.0, 5.5)}.items():
+        t = edge.transforms.GlobalStandardScaling()
+        batches = [seeded_randn("edge.fit%d.%d" % (month, k), (4, 1, 16, 32), 72) * sd + mu for k in range(2)]
+        for bdata in batches:
+            t._update_parameters(bdata)
+        stats[month] = t
+        out["fit%d" % month] = torch.stack(batches)
+        out["mean%d" % month] = t._mean.reshape(1)
+        out["std%d" % month] = t._std().reshape(1)
+    x = seeded_randn("edge.x", (2, 1, 16, 32), 73) * 7.0 + 280.0
+    out["x"] = x
+    out["x_std1"] = stats[1].transform(x)
+    out["x_back1"] = stats[1].revert(out["x_std1"])
+    pred, target = seeded_randn("edge.pred", (4, 1, 16, 32), 74), seeded_randn("edge.target", (4, 1, 16, 32), 75)
+    out["pred"], out["target"] = pred, target
+    for name in ("MAE", "MSE", "RMSE", "MR"):
+        m = getattr(edge.metrics, name)(device="cpu")
+        m.update(pred[:2], target[:2])
+        m.update(pred[2:], target[2:])
+        out["metric_" + name] = torch.as_tensor(m.compute()).reshape(1).float()
+    return {k: v.detach().cpu().numpy() for k, v in out.items()}
+
+
 def main(argv):
+    if argv == ["edge"]:
+        os.makedirs(GOLDEN_DIR, exist_ok=True)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "edge.npz"), **edge_fixture())
+        print("wrote edge.npz")
+        return
     ref = ref_shims.import_reference()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     names = argv or (list(CASES) + ["schedule", "manifest"])
