@@ -12,7 +12,11 @@ import torch.nn.functional as F
 
 
 def form_batch(lr, hr=None, scale=4):
-    sr = F.interpolate(lr, scale_factor=scale, mode="bicubic")       # dataset_builder.py:377
+    if lr.is_cuda:
+        from .data.dataset_builder import bicubic_sr
+        sr = bicubic_sr(lr, scale)                                   # device-side collate
+    else:
+        sr = F.interpolate(lr, scale_factor=scale, mode="bicubic")   # dataset_builder.py:377 (host data source)
     if hr is None:
         hr = sr.clone()
     return {"HR": hr, "LR": lr, "SR": sr}, [1] * lr.shape[0]

@@ -1,6 +1,6 @@
 """train.py -- same command line as the reference's train.py:208-212 (``-c CONFIG -p {train,val} -gpu IDS``).
 
-``-p val`` runs the validation loop (generate_sr per batch, RMSE in standardised units) on the CUDA path.
+``-p val`` runs the validation loop (generate_sr per batch, MSE / RMSE / MAE / MR on device accumulators) on the CUDA path.
 ``-p train`` builds the optimiser and runs ``optimize_parameters`` (forward, hand-written backward, fused Adam).  Under
 ``torchrun`` (one process per GPU) the batch is sharded across ranks and the gradients are all-reduced in buckets
 overlapped with the backward pass (parallel.FlatGradReducer); weights start identical on every rank (same seed)."""
@@ -46,14 +46,23 @@ def main(argv=None):
         pm["model_path"] = None
     model = create_model(opt, None)
     if args.phase == "val":
+        # reference train.py:132-196 (validate): generate_sr per batch, inverse transform, metric accumulators -- here the
+        # accumulators live on the device (training/metrics.py) and the inverse StandardScaling is folded into the same pass
+        # as a per-(sample, variable) scale, so nothing is copied to the host until the final compute
         model.prepare_to_eval()
-        se, n = 0.0, 0
+        metrics = wsr.sub("training.metrics")
+        vm = metrics.ValidationMetrics(metrics.create_metric_dict(model.device))
+        vm_k = metrics.ValidationMetrics(metrics.create_metric_dict(model.device))
+        sigma_k = float(opt["data"].get("sigma_kelvin", 21.26))          # WeatherBench t2m std (synthetic data has no fitted transform)
         for batch, months in data.batches_from_opt(opt, "val"):
             model.feed_data((batch, months))
             model.generate_sr(False)
-            img = model.get_images(need_LR=True)
-            se += float(((img["SR"] - img["HR"]) ** 2).sum()); n += img["SR"].numel()
-        log.info("validation RMSE (standardised units): %.6f", (se / max(n, 1)) ** 0.5)
+            sr, hr = model.SR, model.data["HR"]
+            vm.update(sr, hr)
+            vm_k.update(sr, hr, scale=torch.full((sr.shape[0] * sr.shape[1],), sigma_k))
+        vm.compute_metrics(); vm_k.compute_metrics()
+        log.info("validation (standardised units)%s", vm.metrics2str())
+        log.info("validation (x sigma = %.2f K)%s", sigma_k, vm_k.metrics2str())
         return
     it = 0
     par = wsr.sub("parallel")
