@@ -38,6 +38,9 @@ CASES = {
     "resdiff_step_small": dict(kind="resdiff_step", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=11, level=(0.83, 0.31)),
     "resdiff_step_full_b1": dict(kind="resdiff_step", cfg=unet_cfg(128, 256), batch=1, seed=12, level=(0.645,)),
     "resdiff_step_full_b2": dict(kind="resdiff_step", cfg=unet_cfg(128, 256), batch=2, seed=13, level=(0.9, 0.2)),
+    # configs[4]-shaped: three variables, wider UNet (inner 128), 8x condition made outside the model
+    "resdiff_step_c3_wide": dict(kind="resdiff_step", cfg=unet_cfg(32, 64, inner=128, c_img=3, attn_res=(4,)), batch=2, seed=14,
+                                 level=(0.55, 0.8)),
     # short reverse chains with injected noise
     "resdiff_chain_small": dict(kind="resdiff_chain", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=21, T=4),
     "resdiff_chain_full_b1": dict(kind="resdiff_chain", cfg=unet_cfg(128, 256), batch=1, seed=22, T=3),

@@ -46,6 +46,18 @@ def manifest(tag, cfg=None):
     return out
 
 
+def module_manifest(arch, cfg):
+    """(name, shape) list taken from the package's own UNet built with ``cfg`` -- for configurations other than the canonical
+    one of manifest.npz (its key / shape equality with the reference is tested on the canonical configuration)."""
+    import wsr
+    U = wsr.sub("models.diffusion_models.%s.unet" % arch).UNet
+    net = U(in_channel=cfg["in_channel"], out_channel=cfg["out_channel"], norm_groups=cfg["norm_groups"],
+            inner_channel=cfg["inner_channel"], channel_mults=cfg["channel_mults"], attn_res=cfg["attn_res"],
+            res_blocks=cfg["res_blocks"], dropout=cfg["dropout"], image_height=cfg["image_height"],
+            image_width=cfg["image_width"], image_channels=cfg["image_channels"])
+    return [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
+
+
 def rel_l2(a, b):
     a = a.double().flatten()
     b = b.double().flatten()

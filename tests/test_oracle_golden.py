@@ -14,6 +14,9 @@ TOL = 1e-5
 
 
 def _sd(tag, seed, cfg=None):
+    if cfg is not None and cfg.get("inner_channel", 64) != 64:
+        from conftest import module_manifest
+        return seeded_state_dict(module_manifest(tag, cfg), seed)
     return seeded_state_dict(manifest(tag, cfg), seed)
 
 
@@ -53,7 +56,7 @@ def test_haar_known_answer():
     assert float(nets.haar_detail_sums(x, 1)[0]) == pytest.approx(-2 - 1 + 0)
 
 
-@pytest.mark.parametrize("name", ["resdiff_step_small", "resdiff_step_full_b1", "resdiff_step_full_b2"])
+@pytest.mark.parametrize("name", ["resdiff_step_small", "resdiff_step_full_b1", "resdiff_step_full_b2", "resdiff_step_c3_wide"])
 def test_resdiff_step(name):
     g, spec = load_golden(name), CASES[name]
     sd = _sd("resdiff", spec["seed"], spec["cfg"])

@@ -26,7 +26,7 @@ def _resdiff(cfg, seed, precision):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("name", ["resdiff_step_small", "resdiff_step_full_b1", "resdiff_step_full_b2"])
+@pytest.mark.parametrize("name", ["resdiff_step_small", "resdiff_step_full_b1", "resdiff_step_full_b2", "resdiff_step_c3_wide"])
 def test_resdiff_step_vs_reference(name, precision):
     g, spec = load_golden(name), CASES[name]
     net = _resdiff(spec["cfg"], spec["seed"], precision)
