@@ -244,11 +244,64 @@ def edge_fixture():
     return {k: v.detach().cpu().numpy() for k, v in out.items()}
 
 
+def store_fixture():
+    """the REAL reference DataHandler (npy_reader, datasets, transforms, dataset_builder) run on the synthetic
+    store of oracle/store.py -- lengths, sample-index time stamps, fitted per-month statistics, the first validation batch,
+    one training item, a batch fetched by date and its inverse transform."""
+    import tempfile
+    from . import store
+    ref = ref_shims.import_reference_data()
+    out = {}
+    with tempfile.TemporaryDirectory() as root:
+        store.write_store(root)
+        spec = store.SPEC
+        dh = ref.dataset_builder.DataHandler(root, list(store.VARIABLES), root, spec["months_subset"], spec["groups"],
+                                             ref.transforms.GlobalStandardScaling, spec["train"][0], spec["train"][1],
+                                             spec["val"][0], spec["val"][1], spec["val_batch_size"], spec["train_batch_size"], False, 0)
+        train_loader, val_loader, metadata, transformer = dh.process_data()
+        train_set, val_set = dh.get_datasets()
+        out["train_len"], out["val_len"] = np.array(len(train_set)), np.array(len(val_set))
+        first = list(train_set.data_groups["lr"].values())[0]
+        probe = np.array([0, 1, 743, 744, 800, len(train_set) - 1])
+        out["probe"] = probe
+        out["probe_stamps"] = np.array([first._sample_index[int(i)] for i in probe]).astype("datetime64[h]").astype(np.int64)
+        for v in store.VARIABLES:
+            for kind in ("lr", "hr"):
+                for month, t in transformer.transformation_dict[v][kind].items():
+                    out["mean.%s.%s.%d" % (v, kind, month)] = t._mean.reshape(1).numpy()
+                    out["std.%s.%s.%d" % (v, kind, month)] = t._std().reshape(1).numpy()
+        batch, months = next(iter(val_loader))
+        for k in ("HR", "LR", "SR"):
+            out["val0." + k] = batch[k].numpy()
+        out["val0.months"] = np.array(months)
+        out["val_batches"] = np.array(len(val_loader))
+        out["train_batches"] = np.array(len(train_loader))
+        item = train_set[800]
+        out["item800.lr"] = torch.cat([v[0] for v in item[0]], 1).numpy()
+        out["item800.hr"] = torch.cat([v[0] for v in item[1]], 1).numpy()
+        out["item800.month"] = np.array(item[0][0][2])
+        by_date, bmonths = dh.get_data_by_date("2000-03-05-07")
+        for k in ("HR", "LR", "SR"):
+            out["date." + k] = by_date[k].numpy()
+        out["date.months"] = np.array(bmonths)
+        inv = transformer.inverse_transform(by_date, bmonths)
+        for k in ("HR", "LR", "SR"):
+            out["date_inv." + k] = inv[k].numpy()
+        out["meta.hr_lat"] = np.asarray(metadata.hr_lat)
+        out["channels.lr"] = np.array(int(train_set.get_channel_count("lr")))
+    return out
+
+
 def main(argv):
     if argv == ["edge"]:
         os.makedirs(GOLDEN_DIR, exist_ok=True)
         np.savez_compressed(os.path.join(GOLDEN_DIR, "edge.npz"), **edge_fixture())
         print("wrote edge.npz")
+        return
+    if argv == ["store"]:
+        os.makedirs(GOLDEN_DIR, exist_ok=True)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "store.npz"), **store_fixture())
+        print("wrote store.npz")
         return
     ref = ref_shims.import_reference()
     os.makedirs(GOLDEN_DIR, exist_ok=True)

@@ -131,3 +131,66 @@ def import_reference():
     ns.SR3UNet, ns.SR3Diffusion, ns.PhyDiffUNet, ns.PhyDiffDiffusion = SR3UNet, SR3Diffusion, PhyDiffUNet, PhyDiffDiffusion
     ns.RRDBNet, ns.SimpleCNN, ns.networks, ns.make_beta_schedule = RRDBNet, SimpleCNN, networks, make_beta_schedule
     return ns
+
+
+class _Interval(tuple):
+    """(begin, end, data) with attribute access, ordered like intervaltree.Interval."""
+
+    def __new__(cls, begin, end, data=None):
+        return super().__new__(cls, (begin, end, data))
+
+    begin = property(lambda self: self[0])
+    end = property(lambda self: self[1])
+    data = property(lambda self: self[2])
+
+
+class _IntervalTree:
+    """The subset of ``intervaltree.IntervalTree`` (3.1.0, requirements.txt) the reference's data/datasets.py uses: slice
+    assignment ``tree[a:b] = data``, overlap query ``tree[a:b]`` (half-open intervals: overlap iff begin < b and end > a),
+    iteration, ``len``, ``items()``."""
+
+    def __init__(self):
+        self._items = set()
+
+    def __setitem__(self, index, data):
+        self._items.add(_Interval(index.start, index.stop, data))
+
+    def __getitem__(self, index):
+        if isinstance(index, slice):
+            return {iv for iv in self._items if iv.begin < index.stop and iv.end > index.start}
+        return {iv for iv in self._items if iv.begin <= index < iv.end}
+
+    def __iter__(self):
+        return iter(self._items)
+
+    def __len__(self):
+        return len(self._items)
+
+    def items(self):
+        return set(self._items)
+
+
+def import_reference_data():
+    """The reference's data pipeline (npy_reader, datasets, transforms, dataset_builder) for SURVEY 8f N3 fixtures.  The one
+    missing dependency that its code path really uses is ``intervaltree`` (a functional stand-in is installed above)."""
+    install()
+    if not isinstance(getattr(sys.modules.get("intervaltree"), "IntervalTree", None), type) or \
+            not hasattr(sys.modules["intervaltree"].IntervalTree, "items"):
+        try:
+            import intervaltree  # noqa: F401
+            real = hasattr(intervaltree.IntervalTree, "items")
+        except Exception:
+            real = False
+        if not real:
+            m = types.ModuleType("intervaltree")
+            m.IntervalTree, m.Interval = _IntervalTree, _Interval
+            sys.modules["intervaltree"] = m
+            for name in ("data.datasets", "data.dataset_builder", "data.transforms"):
+                sys.modules.pop(name, None)          # re-import against the functional stand-in
+    ns = types.SimpleNamespace()
+    import data.npy_reader as npy_reader
+    import data.datasets as datasets
+    import data.transforms as transforms
+    import data.dataset_builder as dataset_builder
+    ns.npy_reader, ns.datasets, ns.transforms, ns.dataset_builder = npy_reader, datasets, transforms, dataset_builder
+    return ns

@@ -31,6 +31,36 @@ def mkdirs(paths) -> None:
         os.makedirs(p, exist_ok=True)
 
 
+class DataConfig:
+    """On-disk store conventions (reference configs/config.py:8-46 + configs/data_config/config.json).  The reference reads
+    them from a JSON file next to its config module; the same keys can be overridden here with ``json_path``."""
+
+    DEFAULTS = {"name": "data_config", "datetime_format": "%Y-%m-%d-%H", "temporal_resolution": {"unit": "h", "value": 1},
+                "directory_name_meta_data": "meta", "file_name_meta_data": "metadata", "file_name_constant_data": "constant",
+                "directory_name_sample_data": "samples", "netcdf_extension": ".nc", "numpy_extension": ".npy"}
+
+    def __init__(self, json_path=None, json_name=None):
+        cfg = dict(self.DEFAULTS)
+        if json_name and not json_path:
+            json_path = os.path.join(os.path.dirname(__file__), "data_config", (json_name[:-5] if json_name.endswith(".json") else json_name) + ".json")
+            if not os.path.exists(json_path):
+                raise FileNotFoundError("Json file with given name does not exist: {}".format(json_path))
+        if json_path:
+            with open(json_path, "r") as fh:
+                cfg.update(json.load(fh))
+        self.config = cfg
+        self.name = cfg["name"]
+        self.datetime_format = cfg["datetime_format"]
+        self.temporal_resolution_unit = cfg["temporal_resolution"]["unit"]
+        self.temporal_resolution_value = cfg["temporal_resolution"]["value"]
+        self.directory_name_meta_data = cfg["directory_name_meta_data"]
+        self.file_name_meta_data = cfg["file_name_meta_data"]
+        self.file_name_constant_data = cfg["file_name_constant_data"]
+        self.directory_name_sample_data = cfg["directory_name_sample_data"]
+        self.netcdf_extension = cfg["netcdf_extension"]
+        self.numpy_extension = cfg["numpy_extension"]
+
+
 class Config:
     def __init__(self, args, experiment=True):
         self.args = args

@@ -4,8 +4,11 @@ consumes is only the batch-dict contract of data/dataset_builder.py:344-382:
 
     {'HR': (B,C,H,W), 'LR': (B,C,H/4,W/4), 'SR': bicubic x4 of LR (B,C,H,W)} fp32 standardised units, + months list
 
-This module produces that contract either from synthetic WeatherBench-shaped fields or from a file of real,
-already standardised fields (``.npz`` / ``.pt`` with arrays ``HR`` and ``LR``)."""
+This module produces that contract from the reference's on-disk store when ``data.dataroot`` is one (``<root>/{lr,hr}/<var>/...``,
+SURVEY 8f N3: ``data.dataset_builder.DataHandler`` + the device loader), else from synthetic WeatherBench-shaped fields or from a
+file of real, already standardised fields (``.npz`` / ``.pt`` with arrays ``HR`` and ``LR``)."""
+import os
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -42,11 +45,59 @@ def file_batches(path, batch):
         yield form_batch(lr[i:i + batch], hr[i:i + batch], hr.shape[-1] // lr.shape[-1])
 
 
+_handlers = {}
+
+
+def is_store(root):
+    return bool(root) and os.path.isdir(os.path.join(root, "lr")) and os.path.isdir(os.path.join(root, "hr"))
+
+
+def store_handler(opt, val_only=False):
+    """The reference's ``DataHandler(...)`` call of train.py:232-238 / sample.py:51-56 for ``opt['data']``; None when
+    ``dataroot`` is not a store directory.  ``val_only`` = sample.py's variant (transforms fitted on the validation range)."""
+    d = opt["data"]
+    root = str(d.get("dataroot", ""))
+    if not is_store(root):
+        return None
+    key = (root, val_only, str(d.get("train_min_date")), str(d.get("train_max_date")), str(d.get("val_min_date")), str(d.get("val_max_date")),
+           str(d.get("months_subset")))
+    if key not in _handlers:
+        from .data.dataset_builder import DataHandler
+        from .data.transforms import get_transformation_by_name
+        groups = d["transform_groups"]
+        groups = list(groups.values()) if isinstance(groups, dict) else groups
+        lo, hi = (d["val_min_date"], d["val_max_date"]) if val_only else (d["train_min_date"], d["train_max_date"])
+        storage = opt.get("path", {}).get("experiments_root") or root
+        if not os.path.isdir(storage) or not os.access(storage, os.W_OK):
+            import tempfile
+            storage = tempfile.mkdtemp(prefix="wsr_meta_")
+        dh = DataHandler(root, d["variables"], storage, d["months_subset"], groups, get_transformation_by_name(d["transformation"]),
+                         lo, hi, d["val_min_date"], d["val_max_date"], d["val_batch_size"], d["batch_size"], d.get("use_shuffle", True),
+                         d.get("num_workers", 4))
+        dh.process_data()
+        _handlers[key] = dh
+    return _handlers[key]
+
+
 def batches_from_opt(opt, phase, n_batches=None):
     d = opt["data"]
     m = opt["model"]["diffusion"]
     bs = d["val_batch_size"] if phase == "val" else d["batch_size"]
     root = str(d.get("dataroot", ""))
+    dh = store_handler(opt)
+    if dh is not None:
+        if phase == "val":
+            return iter(dh.val_loader)
+
+        def epochs():                          # train.py:57-64: epochs over the loader until n_iter batches were served
+            served, limit = 0, (n_batches if n_batches is not None else opt["train"]["n_iter"])
+            while served < limit:
+                for item in dh.train_loader:
+                    if served >= limit:
+                        return
+                    served += 1
+                    yield item
+        return epochs()
     if root.endswith((".npz", ".pt")):
         return file_batches(root, bs)
     n = n_batches if n_batches is not None else (1 if phase == "val" else opt["train"]["n_iter"])

@@ -51,7 +51,21 @@ def main(argv=None):
         opt["model"]["pretrained_model"]["model_path"] = None
     model = create_model(opt, None)
     model.prepare_to_eval()
-    batch, months = next(iter(data.batches_from_opt(opt, "val")))
+    handler = None
+    if data.is_store(str(opt["data"].get("dataroot", ""))):
+        # reference sample.py:45-56,76-79: -d DATE restricts the validation range to that hour and fetches it by date
+        if args.date:
+            from datetime import datetime, timedelta
+            fmt = "%Y-%m-%d-%H"
+            opt["data"]["months_subset"] = [datetime.strptime(args.date, fmt).month]
+            opt["data"]["transform_groups"] = [opt["data"]["months_subset"]]
+            opt["data"]["val_min_date"] = args.date
+            opt["data"]["val_max_date"] = (datetime.strptime(args.date, fmt) + timedelta(hours=1)).strftime(fmt)
+        handler = data.store_handler(opt, val_only=True)
+    if handler is not None and args.date:
+        batch, months = handler.get_data_by_date(args.date)
+    else:
+        batch, months = next(iter(data.batches_from_opt(opt, "val")))
     n_total = batch["SR"].shape[0]
     if world > 1:
         batch = par.shard_batch(batch, rank, world)
@@ -64,6 +78,9 @@ def main(argv=None):
         os.makedirs(args.output_path, exist_ok=True)
         np.save(os.path.join(args.output_path, "sr.npy"), sr.float().cpu().numpy())
         print("saved %s %s" % (os.path.join(args.output_path, "sr.npy"), tuple(sr.shape)))
+        if handler is not None:
+            phys = handler.get_data_transformer().inverse_transform({"SR": sr}, months[:sr.shape[0]] if len(months) >= sr.shape[0] else months)
+            np.save(os.path.join(args.output_path, "sr_physical.npy"), phys["SR"].float().cpu().numpy())
     if world > 1:
         torch.distributed.destroy_process_group()
 

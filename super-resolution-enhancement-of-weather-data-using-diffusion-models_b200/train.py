@@ -54,16 +54,25 @@ def main(argv=None):
         vm = metrics.ValidationMetrics(metrics.create_metric_dict(model.device))
         vm_k = metrics.ValidationMetrics(metrics.create_metric_dict(model.device))
         sigma_k = float(opt["data"].get("sigma_kelvin", 21.26))          # WeatherBench t2m std (synthetic data has no fitted transform)
+        handler = data.store_handler(opt)                                # the reference's on-disk store, when dataroot is one
         for batch, months in data.batches_from_opt(opt, "val"):
             model.feed_data((batch, months))
             model.generate_sr(False)
             sr, hr = model.SR, model.data["HR"]
             vm.update(sr, hr)
-            vm_k.update(sr, hr, scale=torch.full((sr.shape[0] * sr.shape[1],), sigma_k))
+            if handler is not None:
+                # physical units = fitted std of each sample's month and variable (train.py:96-99 inverse_transform, folded in)
+                _, std = handler.get_data_transformer().batch_statistics("hr", months)
+                vm_k.update(sr, hr, scale=std.reshape(-1))
+            else:
+                vm_k.update(sr, hr, scale=torch.full((sr.shape[0] * sr.shape[1],), sigma_k))
         vm.compute_metrics(); vm_k.compute_metrics()
         log.info("validation (standardised units)%s", vm.metrics2str())
-        log.info("validation (x sigma = %.2f K)%s", sigma_k, vm_k.metrics2str())
-        return
+        if handler is not None:
+            log.info("validation (physical units, fitted statistics)%s", vm_k.metrics2str())
+        else:
+            log.info("validation (x sigma = %.2f K)%s", sigma_k, vm_k.metrics2str())
+        return vm.metrics2dict(), vm_k.metrics2dict()
     it = 0
     par = wsr.sub("parallel")
     for batch, months in data.batches_from_opt(opt, "train"):

@@ -49,7 +49,7 @@ def test_standard_scaling_and_batch_inverse():
     assert rel_l2(xs.cpu(), g["x_std1"]) < 1e-6
     assert rel_l2(t.revert(xs).cpu(), g["x_back1"]) < 1e-6
     # batch inverse with per-sample months and two variables vs the reference's per-sample loop (transforms.py:116-138)
-    tdict = {v: {"hr": {1: transforms.StandardScaling(270.0 + i, 9.0 + i), 7: transforms.StandardScaling(291.0 - i, 5.5 + i)}}
+    tdict = {v: {"hr": {1: transforms.StandardScaling.from_stats(270.0 + i, 9.0 + i), 7: transforms.StandardScaling.from_stats(291.0 - i, 5.5 + i)}}
              for i, v in enumerate(["t2m", "z500"])}
     months = [1, 7, 7, 1]
     mean, std = transforms.batch_statistics(tdict, ["t2m", "z500"], "hr", months)
