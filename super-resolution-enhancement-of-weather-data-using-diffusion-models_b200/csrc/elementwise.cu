@@ -233,6 +233,8 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x, int HW, int C, int ld,
   const int n = blockIdx.y;
   const int cpg = C / groups;
   float* gm = sm + 2 * C;
+  pdl_launch_dependents();        // programmatic dependent launch (common.cuh): the statistics come from the preceding convolution
+  pdl_wait();
   // group moments first (one thread per group sums its cpg channel statistics), then per-channel scale / shift: the
   // per-channel version re-summed the whole group for every channel (2 * cpg double loads each; cpg = 32 at C = 1024)
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
@@ -652,7 +654,7 @@ static int gn_apply_impl(const void* x, int x_dtype, int N, int HW, int C, int x
   dim3 grid((HW + g.chunk - 1) / g.chunk, N);
   size_t smem = ((size_t)C * 2 + 2 * groups) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-#define GN_APPLY(T, V, D) gn_apply_kernel<T, T, V, D><<<grid, g.threads, smem, st>>>((const T*)x, HW, C, x_ld, g.CV, g.PL, g.chunk, stats, stats_ld, gamma, beta, groups, eps, act, (T*)y, y_ld, drop_p, drop_seed, drop_tag)
+#define GN_APPLY(T, V, D) WSR_CUDA_OK(launch_pdl(gn_apply_kernel<T, T, V, D>, grid, dim3(g.threads), smem, st, (const T*)x, HW, C, x_ld, g.CV, g.PL, g.chunk, stats, stats_ld, gamma, beta, groups, eps, act, (T*)y, y_ld, drop_p, drop_seed, drop_tag))
   if (drop_p > 0.f) {
     if (x_dtype == WSR_BF16) { if (g.vec == 8) GN_APPLY(__nv_bfloat16, 8, true); else GN_APPLY(__nv_bfloat16, 1, true); }
     else { if (g.vec == 4) GN_APPLY(float, 4, true); else GN_APPLY(float, 1, true); }

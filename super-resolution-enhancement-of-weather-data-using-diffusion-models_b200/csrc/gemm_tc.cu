@@ -190,6 +190,10 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above touched only this CTA's shared / tensor memory and the (kernel-parameter)
+  // tensor maps; from here on the kernel reads what earlier launches produced and overwrites what they may still be reading
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == kProducerWarp) {
     // ===================== TMA producer =====================
@@ -926,8 +930,8 @@ static int launch_tc_impl(const TcParams& p, cudaStream_t st) {
   }
   int total = p.g1 * p.g2 * p.g3 * p.nbatch * p.n_tiles;
   int grid = total < sm_count() ? total : sm_count();
-  gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE, VM, STG><<<grid, FUSE ? kTcThreadsFused : kTcThreads, Cfg::kSmemBytes, st>>>(p);
-  WSR_LAUNCH_OK();
+  WSR_CUDA_OK(launch_pdl(gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE, VM, STG>, dim3(grid), dim3(FUSE ? kTcThreadsFused : kTcThreads),
+                         (size_t)Cfg::kSmemBytes, st, p));
   return WSR_OK;
 }
 
