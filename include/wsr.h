@@ -330,6 +330,14 @@ int wsr_standard_scale(const float* x, int planes, int64_t hw, const float* mean
  * d = scale[plane] * (pred - target); scale = per-plane std folds the inverse transform in (the means cancel), or NULL. */
 int wsr_error_sums(const float* pred, const float* target, int planes, int64_t hw, const float* scale, double* acc, void* stream);
 
+/* Prior pre-training.  image_compare_loss of models/simple_cnn/loss.py:60-76: alpha * fft_mse_loss +
+ * beta * dwt_mse_loss (4 Haar levels) between x and y, fp32 NCHW planes with H, W multiples of 16.  *loss += value (double);
+ * grad (optional, same shape as x) = d loss / d x.  No FFT is executed: see csrc/pretrain.cu. */
+int wsr_image_compare_loss(const float* x, const float* y, int planes, int H, int W, float alpha, float beta, double* loss,
+                           float* grad, void* stream);
+/* Backward of nn.ReLU(inplace=True) (models/simple_cnn/Simple_CNN.py:17,19) from the kept OUTPUT y: dy[i] = 0 where y[i] <= 0. */
+int wsr_relu_mask(const float* y, float* dy, int64_t n, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * DDPM process kernels (models/diffusion_models/diffusion.py).
  * ------------------------------------------------------------------------------------------------------------- */

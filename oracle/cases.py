@@ -53,6 +53,7 @@ CASES = {
     "srdiff_grad_small": dict(kind="srdiff_grad", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=1), batch=2, seed=64, t=450),
     # priors and the RRDB-conditioned variant
     "simple_cnn": dict(kind="simple_cnn", batch=2, seed=41, lr_hw=(8, 16)),
+    "simple_cnn_pretrain": dict(kind="simple_cnn_pretrain", batch=3, seed=43, lr_hw=(8, 16)),
     "rrdb_small": dict(kind="rrdb", batch=1, seed=42, lr_hw=(8, 16)),
     # SR3 (plain conditional UNet) and PhyDiff ("ResDiff+Physics": stencil channels + 3-band Haar queries)
     "sr3_step_small": dict(kind="sr3_step", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=2), batch=2, seed=51, level=(0.77, 0.21)),

@@ -93,3 +93,35 @@ def error_metrics(pairs):
         s_d += float(d.sum())
         n += pred.numel()
     return {"MAE": s_abs / n, "MSE": s_sq / n, "RMSE": (s_sq / n) ** 0.5, "MR": s_d / n}
+
+
+def haar_bands(x, levels=4):
+    """pytorch_wavelets.DWTForward(J, 'haar', 'symmetric') detail bands per level (see oracle/ref_shims.py for the convention):
+    list of (B, C, 3, H / 2^j, W / 2^j)."""
+    out, ll = [], x
+    for _ in range(levels):
+        a, b, c, d = ll[..., 0::2, 0::2], ll[..., 0::2, 1::2], ll[..., 1::2, 0::2], ll[..., 1::2, 1::2]
+        out.append(torch.stack([(a + b - c - d) / 2, (a - b + c - d) / 2, (a - b - c + d) / 2], dim=2))
+        ll = (a + b + c + d) / 2
+    return out
+
+
+def fft_mse_loss(x, y):
+    """models/simple_cnn/loss.py:9-28, as written (real and imaginary parts of the orthonormal FFT)."""
+    fx, fy = torch.fft.fftn(x, dim=(2, 3), norm="ortho"), torch.fft.fftn(y, dim=(2, 3), norm="ortho")
+    return torch.mean((fx.imag - fy.imag) ** 2) + torch.mean((fx.real - fy.real) ** 2)
+
+
+def dwt_mse_loss(x, y, J=4):
+    """models/simple_cnn/loss.py:31-57."""
+    bx, by = haar_bands(x, J), haar_bands(y, J)
+    total = 0.0
+    for i in range(J):
+        for k in range(3):
+            total = total + torch.mean((bx[i][:, :, k] - by[i][:, :, k]) ** 2)
+    return total
+
+
+def image_compare_loss(x, y, alpha=0.2, beta=0.1):
+    """models/simple_cnn/loss.py:60-76."""
+    return alpha * fft_mse_loss(x, y) + beta * dwt_mse_loss(x, y)

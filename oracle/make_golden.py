@@ -170,6 +170,19 @@ def run_case(ref, name, spec):
             net = fill_module(ref.SimpleCNN(scale_factor=4, channels=1).eval(), seed)
             lr = seeded_randn(name + ".lr", (b, 1) + tuple(spec["lr_hw"]), seed)
             out.update(lr=lr, out=net(lr), wsum=_checksum(net))
+        elif kind == "simple_cnn_pretrain":
+            # one pre-training step of the prior (pretrain.py:37-48): image_compare_loss and all parameter gradients
+            from models.simple_cnn.loss import image_compare_loss, fft_mse_loss, dwt_mse_loss
+            net = fill_module(ref.SimpleCNN(scale_factor=4, channels=1).train(), seed)
+            lr, _, hr = fields(name, b, 1, 4 * spec["lr_hw"][0], 4 * spec["lr_hw"][1], seed)
+            with torch.enable_grad():
+                pred = net(lr)
+                loss = image_compare_loss(pred, hr)
+                loss.backward()
+            pred, loss = pred.detach(), loss.detach()
+            out.update(lr=lr, hr=hr, pred=pred, loss=loss.reshape(1), fft=fft_mse_loss(pred, hr).reshape(1), dwt=dwt_mse_loss(pred, hr).reshape(1))
+            for n, prm in net.named_parameters():
+                out["grad." + n] = prm.grad
         elif kind == "rrdb":
             net = fill_module(ref.RRDBNet(1, 1, 64, 17, 32).eval(), seed)
             lr = seeded_randn(name + ".lr", (b, 1) + tuple(spec["lr_hw"]), seed)
