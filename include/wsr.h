@@ -337,6 +337,9 @@ int wsr_image_compare_loss(const float* x, const float* y, int planes, int H, in
                            float* grad, void* stream);
 /* Backward of nn.ReLU(inplace=True) (models/simple_cnn/Simple_CNN.py:17,19) from the kept OUTPUT y: dy[i] = 0 where y[i] <= 0. */
 int wsr_relu_mask(const float* y, float* dy, int64_t n, void* stream);
+/* Backward of LeakyReLU(slope) (models/rrdb_encoder/RRDBNet.py:105-110,49-53) from the kept OUTPUT y on NHWC channel slices
+ * (rows x C, row pitches y_ld / dy_ld): dy[r][c] *= slope where y[r][c] <= 0. */
+int wsr_lrelu_mask(const void* y, int y_dtype, int y_ld, void* dy, int dy_dtype, int dy_ld, int64_t rows, int C, float slope, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * DDPM process kernels (models/diffusion_models/diffusion.py).

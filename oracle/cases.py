@@ -53,6 +53,7 @@ CASES = {
     "srdiff_grad_small": dict(kind="srdiff_grad", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=1), batch=2, seed=64, t=450),
     # priors and the RRDB-conditioned variant
     "simple_cnn": dict(kind="simple_cnn", batch=2, seed=41, lr_hw=(8, 16)),
+    "rrdb_pretrain": dict(kind="rrdb_pretrain", batch=2, seed=47, lr_hw=(8, 16), nb=2),
     "simple_cnn_pretrain": dict(kind="simple_cnn_pretrain", batch=3, seed=43, lr_hw=(8, 16)),
     "rrdb_small": dict(kind="rrdb", batch=1, seed=42, lr_hw=(8, 16)),
     # SR3 (plain conditional UNet) and PhyDiff ("ResDiff+Physics": stencil channels + 3-band Haar queries)
@@ -82,3 +83,13 @@ def grad_summary(named_grads, seed, full_below=4096):
         if g.numel() < full_below:
             out["full/" + name] = g.to(torch.float32).numpy().copy()
     return out
+
+
+def calibrate_rrdb_head(net):
+    """Variance-preserving random weights drive the encoder's raw output far outside [0, 1], where ``clamp(0, 1)`` (RRDBNet.py:56)
+    zeroes almost every gradient.  For the pre-training fixture the last convolution is scaled down and centred so that most
+    of the output sits inside the clamp range while part of it still saturates (both branches of the mask are exercised)."""
+    with torch.no_grad():
+        net.conv_last.weight.mul_(1.0)
+        net.conv_last.bias.fill_(0.5)
+    return net

@@ -14,6 +14,7 @@ import sys
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 from . import ref_shims
 from .cases import CASES, LINEAR_1000, fields, short_schedule
@@ -183,6 +184,21 @@ def run_case(ref, name, spec):
             out.update(lr=lr, hr=hr, pred=pred, loss=loss.reshape(1), fft=fft_mse_loss(pred, hr).reshape(1), dwt=dwt_mse_loss(pred, hr).reshape(1))
             for n, prm in net.named_parameters():
                 out["grad." + n] = prm.grad
+        elif kind == "rrdb_pretrain":
+            # one pre-training step of the encoder (pretrain.py:37-48, criterion = F.l1_loss): all parameter gradients
+            from .cases import grad_summary, calibrate_rrdb_head
+            net = calibrate_rrdb_head(fill_module(ref.RRDBNet(1, 1, 64, spec["nb"], 32).train(), seed))
+            lr, _, hr = fields(name, b, 1, 4 * spec["lr_hw"][0], 4 * spec["lr_hw"][1], seed)
+            lr, hr = lr * 0.5, (hr * 0.25).clamp(-1, 1)
+            with torch.enable_grad():
+                pred = net(lr)
+                loss = F.l1_loss(pred, hr)
+                loss.backward()
+            out.update(lr=lr, hr=hr, pred=pred.detach(), loss=loss.detach().reshape(1),
+                       inside=torch.tensor([float(((pred > -1) & (pred < 1)).float().mean())]))
+            named = [(n, prm.grad) for n, prm in net.named_parameters()]
+            out["names"] = np.array([n for n, _ in named])
+            out.update(grad_summary(named, seed, full_below=128))
         elif kind == "rrdb":
             net = fill_module(ref.RRDBNet(1, 1, 64, 17, 32).eval(), seed)
             lr = seeded_randn(name + ".lr", (b, 1) + tuple(spec["lr_hw"]), seed)

@@ -128,6 +128,7 @@ SIGNATURES = {
     "wsr_error_sums": [_P, _P, _I, _L, _P, _P, _P],
     "wsr_image_compare_loss": [_P, _P, _I, _I, _I, _F, _F, _P, _P, _P],
     "wsr_relu_mask": [_P, _P, _L, _P],
+    "wsr_lrelu_mask": [_P, _I, _I, _P, _I, _I, _L, _I, _F, _P],
     "wsr_sampler_step": [_P, _P, _I, _P, _L, _U64, _P, _I, _P, _I, _P, _L, _P],
     "wsr_broadcast_row": [_P, _I, _P, _I, _P, _P],
     "wsr_step_counter_add": [_P, _I, _P],

@@ -79,9 +79,37 @@ __global__ void relu_mask_kernel(const float* __restrict__ y, float* __restrict_
   if (i < n && !(y[i] > 0.f)) dy[i] = 0.f;
 }
 
+// dy[r][c] *= (y[r][c] > 0 ? 1 : slope) over an NHWC channel slice (rows x C, row pitches y_ld / dy_ld): backward of LeakyReLU from the
+// kept OUTPUT (the sign of a leaky ReLU's output is the sign of its input)
+template <typename TY, typename TD>
+__global__ void lrelu_mask_kernel(const TY* __restrict__ y, int y_ld, TD* __restrict__ dy, int dy_ld, int64_t rows, int C, float slope) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const int64_t r = i / C;
+  const int c = (int)(i - r * C);
+  if (!(ldf<TY>(y + r * y_ld + c) > 0.f)) {
+    TD* p = dy + r * dy_ld + c;
+    stf<TD>(p, ldf<TD>(p) * slope);
+  }
+}
+
 }  // namespace wsr
 
 using namespace wsr;
+
+extern "C" int wsr_lrelu_mask(const void* y, int y_dtype, int y_ld, void* dy, int dy_dtype, int dy_ld, int64_t rows, int C, float slope,
+                              void* stream) {
+  WSR_REQUIRE(y && dy && rows > 0 && C > 0 && y_ld >= C && dy_ld >= C && valid_dtype(y_dtype) && valid_dtype(dy_dtype), WSR_E_INVALID,
+              "lrelu_mask: bad argument");
+  const unsigned blocks = (unsigned)((rows * C + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (y_dtype == WSR_BF16 && dy_dtype == WSR_BF16) lrelu_mask_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)y, y_ld, (__nv_bfloat16*)dy, dy_ld, rows, C, slope);
+  else if (y_dtype == WSR_F32 && dy_dtype == WSR_F32) lrelu_mask_kernel<<<blocks, 256, 0, st>>>((const float*)y, y_ld, (float*)dy, dy_ld, rows, C, slope);
+  else if (y_dtype == WSR_BF16) lrelu_mask_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)y, y_ld, (float*)dy, dy_ld, rows, C, slope);
+  else lrelu_mask_kernel<<<blocks, 256, 0, st>>>((const float*)y, y_ld, (__nv_bfloat16*)dy, dy_ld, rows, C, slope);
+  WSR_LAUNCH_OK();
+  return WSR_OK;
+}
 
 extern "C" int wsr_image_compare_loss(const float* x, const float* y, int planes, int H, int W, float alpha, float beta, double* loss,
                                       float* grad, void* stream) {

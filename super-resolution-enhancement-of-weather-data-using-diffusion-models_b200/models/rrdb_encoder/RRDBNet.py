@@ -139,6 +139,7 @@ class _RRDBPlan:
                     feas.append(dst)
         e.conv(feas[-1], self.w_trunk, self.trunk, res=self.first)            # fea_first + trunk_conv(fea)
         feas.append(self.trunk)
+        self.last_feas = feas
         return feas
 
     def sr_image(self):
@@ -150,6 +151,109 @@ class _RRDBPlan:
         e.conv(self.up2, self.w_hr, self.hr, act=LR)
         e.conv(self.hr, self.w_last, self.last)
         return self.last.to_nchw(e).clamp(0, 1) * 2 - 1
+
+    def sr_image_raw(self):
+        """conv_last output before ``clamp(0, 1) * 2 - 1`` (:55-57), NCHW fp32 -- the pre-training path applies the clamp with
+        differentiable torch ops so that its mask reaches ``backward``."""
+        self.sr_image()
+        return self.last.to_nchw(self.eng)
+
+
+    # ---- pre-training: backward pass (SURVEY 8f N4; reference pretrain.py:45-48 with criterion = F.l1_loss) ------------------
+    def _axpby(self, x, a, z, b, y):
+        nat.call("wsr_axpby", x.ptr, x.dt, x.ld, float(a), z.ptr, z.dt, z.ld, float(b), y.ptr, y.dt, y.ld, y.N * y.H * y.W, y.C, self.eng.stream)
+
+    def _mask(self, y, dy):
+        nat.call("wsr_lrelu_mask", y.ptr, y.dt, y.ld, dy.ptr, dy.dt, dy.ld, y.N * y.H * y.W, y.C, 0.2, self.eng.stream)
+
+    def _dgrad_pack(self, conv, up=False):
+        from ... import taps as T
+        e = self.eng
+        w = conv.weight
+        if up:
+            return e.pack_conv(T.upsample_dgrad_weight(w), None, key=("updgrad", w.data_ptr(), w._version))
+        return e.pack_conv(T.dgrad_weight(w).contiguous(), None, key=("dgrad", w.data_ptr(), w._version))
+
+    def _wgrad(self, conv, x, dy, table, up=1, force_simt=False):
+        for prm in (conv.weight, conv.bias):
+            if prm.grad is None:
+                prm.grad = torch.zeros_like(prm)
+        co, ci, kh, kw = conv.weight.shape
+        xs = x if x.C == ci else x.slice(0, ci)
+        self.eng.wgrad(xs, dy, table, conv.weight.grad, (1, ci * kh * kw, kh * kw), conv.bias.grad, up, force_simt=force_simt)
+
+    @torch.no_grad()
+    def backward(self, d_raw):
+        """Parameter gradients (accumulated into ``p.grad``) from the gradient w.r.t. the RAW ``conv_last`` output (B, out_nc, 4h, 4w)
+        of the forward pass whose activations this plan still holds.  Every convolution: weight / bias gradient (tcgen05 where the
+        shapes allow, SIMT otherwise) + data gradient = the forward kernel on transposed flipped weights; the dense blocks run on ONE
+        (nf + 4 gc)-channel gradient buffer that mirrors the forward concat buffer (growth slices accumulate in place), LeakyReLU
+        masks come from the kept outputs."""
+        from ... import taps as T
+        e, net = self.eng, self.net
+        B, h, w, nf, gc = self.B, self.h, self.w, net.nf, net.gc
+        new = e.new_act
+        t1, t2, t4 = T.forward_taps(3, 1, h, w), T.forward_taps(3, 1, 2 * h, 2 * w), T.forward_taps(3, 1, 4 * h, 4 * w)
+        # ---- tail: conv_last <- lrelu <- HRconv <- lrelu <- upconv2 <- lrelu <- upconv1 (RRDBNet.py:49-55) ----
+        g_last = e.nchw_to_act(d_raw.to(torch.float32).contiguous(), new(B, 4 * h, 4 * w, net.out_nc))
+        self._wgrad(net.conv_last, self.hr, g_last, t4, force_simt=True)
+        g_hr = e.conv(g_last, self._dgrad_pack(net.conv_last), new(B, 4 * h, 4 * w, nf), bias=False, force_simt=True)
+        self._mask(self.hr, g_hr)
+        self._wgrad(net.HRconv, self.up2, g_hr, t4)
+        g_up2 = e.conv(g_hr, self._dgrad_pack(net.HRconv), new(B, 4 * h, 4 * w, nf), bias=False)
+        self._mask(self.up2, g_up2)
+        self._wgrad(net.upconv2, self.up1, g_up2, T.forward_upsample_taps(2 * h, 2 * w), up=2)
+        g_up1 = e.conv(g_up2, self._dgrad_pack(net.upconv2, up=True), new(B, 2 * h, 2 * w, nf), taps=T.dgrad_upsample_taps(2 * h, 2 * w), bias=False)
+        self._mask(self.up1, g_up1)
+        self._wgrad(net.upconv1, self.trunk, g_up1, T.forward_upsample_taps(h, w), up=2)
+        g_fea = e.conv(g_up1, self._dgrad_pack(net.upconv1, up=True), new(B, h, w, nf), taps=T.dgrad_upsample_taps(h, w), bias=False)
+        # ---- fea = fea_first + trunk_conv(last RRDB output) (:46-47) ----
+        last_in = self.out_last
+        self._wgrad(net.trunk_conv, last_in, g_fea, t1)
+        g = e.conv(g_fea, self._dgrad_pack(net.trunk_conv), new(B, h, w, nf), bias=False)       # d / d(last RRDB output)
+        # ---- the trunk, last block first ----
+        Dg = new(B, h, w, self.wide)
+        go, g5, g_sum = new(B, h, w, nf), new(B, h, w, nf), new(B, h, w, nf)
+        for i in range(len(net.RRDB_trunk) - 1, -1, -1):
+            rrdb = net.RRDB_trunk[i]
+            self._axpby(g, 0.2, g, 0.0, go)                       # out = RDB3(...) * 0.2 + x  (:133): gradient into the RDB chain
+            for j, rdb in ((2, rrdb.RDB3), (1, rrdb.RDB2), (0, rrdb.RDB1)):
+                D = self.dense[i][j]
+                self._axpby(go, 0.2, go, 0.0, g5)                 # x5 * 0.2 + x  (:111)
+                self._wgrad(rdb.conv5, D, g5, t1)
+                e.conv(g5, self._dgrad_pack(rdb.conv5), Dg, bias=False)
+                self._axpby(Dg.slice(0, nf), 1.0, go, 1.0, Dg.slice(0, nf))
+                for k in (4, 3, 2, 1):
+                    conv = (rdb.conv1, rdb.conv2, rdb.conv3, rdb.conv4)[k - 1]
+                    cin = nf + (k - 1) * gc
+                    sl = Dg.slice(cin, gc)
+                    self._mask(D.slice(cin, gc), sl)
+                    self._wgrad(conv, D.slice(0, cin), sl, t1)
+                    e.conv(sl, self._dgrad_pack(conv), Dg.slice(0, cin), bias=False, res=Dg.slice(0, cin))
+                self._axpby(Dg.slice(0, nf), 1.0, Dg.slice(0, nf), 0.0, go)          # gradient w.r.t. this RDB's input
+            self._axpby(g, 1.0, go, 1.0, g_sum)                   # direct path + RDB chain
+            g, g_sum = g_sum, g
+        # ---- conv_first: fea_first feeds the trunk and the skip (:42,47) ----
+        self._axpby(g, 1.0, g_fea, 1.0, g)
+        self._wgrad(net.conv_first, self.x0, g, t1, force_simt=True)
+        e._keep.clear()
+
+
+class _RRDBPretrainFn(torch.autograd.Function):
+    """raw conv_last output with a grad_fn: backward() runs ``_RRDBPlan.backward`` (parameter gradients only; the input is data)."""
+
+    @staticmethod
+    def forward(ctx, anchor, net, x):
+        pl = net.plan(x)
+        pl.run(x)
+        raw = pl.sr_image_raw()
+        ctx.pl = pl
+        return raw
+
+    @staticmethod
+    def backward(ctx, d_raw):
+        ctx.pl.backward(d_raw)
+        return None, None, None
 
 
 class RRDBNet(nn.Module):
@@ -178,8 +282,19 @@ class RRDBNet(nn.Module):
         pl.refresh()
         return pl
 
-    @torch.no_grad()
     def forward(self, x, get_fea=False):
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            # pre-training (reference pretrain.py:37-48): the SR image carries the gradient; features come out detached
+            raw = _RRDBPretrainFn.apply(self.conv_first.weight, self, x)
+            out = raw.clamp(0, 1) * 2 - 1
+            if get_fea:
+                pl = self.plan(x)
+                return out, [f.to_nchw(pl.eng) for f in pl.last_feas]
+            return out
+        with torch.no_grad():
+            return self._forward_eval(x, get_fea)
+
+    def _forward_eval(self, x, get_fea=False):
         pl = self.plan(x)
         feas = pl.run(x)
         out = pl.sr_image()

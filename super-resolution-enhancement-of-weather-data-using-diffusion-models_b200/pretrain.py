@@ -4,8 +4,9 @@ SURVEY.md 8f N4).
 ``model.name = "SimpleSR"``: the SimpleCNN prior trained with ``image_compare_loss`` (0.2 * FFT-MSE + 0.1 * 4-level Haar-MSE, ONE
 kernel for value and gradient), hand-written backward through its three convolutions, Adam -- per epoch: a pass over the training
 loader, then validation with the error metrics in physical units (reference ``train`` / ``evaluate``, :19-104; PSNR / SSIM are
-torcheval / skimage wrappers outside the accelerated path).  ``model.name = "RRDBNet"``: validation only; training the encoder
-needs a backward pass through its 255 dense-block convolutions, which is not built (the reference's checkpoints load).
+torcheval / skimage wrappers outside the accelerated path).  ``model.name = "RRDBNet"``: the RRDB encoder trained with ``F.l1_loss``
+on its SR image; its backward pass (``_RRDBPlan.backward``) runs the dense blocks on one gradient buffer that mirrors the forward
+concat buffer.
 Data comes from the on-disk store through ``DataHandler`` (same call as the reference), or synthetic batches when ``dataroot`` is
 not a store."""
 import argparse
@@ -29,7 +30,7 @@ def get_model(opt):
     if m["name"] == "RRDBNet":
         model = wsr.sub("models.rrdb_encoder.RRDBNet").RRDBNet(in_nc=m["in_channel"], out_nc=m["out_channel"], nf=m["hidden_size"],
                                                                nb=m["num_block"], gc=m["hidden_size"] // 2)
-        return model, None
+        return model, torch.nn.functional.l1_loss
     raise ValueError(f"Unknown model name: {m['name']}")
 
 
@@ -101,8 +102,6 @@ def main(argv=None):
         res = evaluate(model, loader("val"), device, transformer)
         log.info("Val " + ", ".join("%s: %.4f" % (k, float(v)) for k, v in res.items()))
         return res
-    if criterion is None:
-        raise NotImplementedError("RRDBNet pre-training is not part of the accelerated path (no backward pass through the dense blocks)")
     oc = opt["train"]["optimizer"]
     FusedAdam = wsr.sub("autograd_glue").FusedAdam
     if oc.get("amsgrad"):

@@ -102,8 +102,76 @@ def test_pretrain_entry_point_on_the_store(tmp_path, caplog):
         cfg.write_text(json.dumps(opt))
         res = pre.main(["-c", str(cfg), "-p", "val", "-gpu", "0"])
         assert set(res) == {"MSE", "RMSE", "MAE", "MR"}
+        opt["train"]["epoch"] = 1
+        cfg.write_text(json.dumps(opt))
+        hist = pre.main(["-c", str(cfg), "-p", "train", "-gpu", "0"])              # encoder pre-training with F.l1_loss
+        assert len(hist) == 1 and hist[0][0] > 0.0
+        opt["train"]["optimizer"]["amsgrad"] = True
+        cfg.write_text(json.dumps(opt))
         with pytest.raises(NotImplementedError):
             pre.main(["-c", str(cfg), "-p", "train", "-gpu", "0"])
     finally:
         os.chdir(cwd)
 
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_rrdb_pretrain_step_vs_reference(precision):
+    """One encoder pre-training step (pretrain.py:37-48, criterion F.l1_loss): all 72 parameter gradients of a 2-block RRDBNet against
+    the REAL reference's summaries (norm / probe per tensor) and against the oracle's autograd (full tensors)."""
+    import math
+    import torch.nn.functional as F
+    from oracle.cases import calibrate_rrdb_head, grad_summary
+    from test_pretrain_cpu import _rrdb_oracle_grads
+    g, spec = load_golden("rrdb_pretrain"), CASES["rrdb_pretrain"]
+    R = wsr.sub("models.rrdb_encoder.RRDBNet").RRDBNet
+    net = calibrate_rrdb_head(fill_module(R(1, 1, 64, spec["nb"], 32, precision=precision), spec["seed"])).cuda().train()
+    pred = net(g["lr"].cuda())
+    assert pred.requires_grad
+    loss = F.l1_loss(pred, g["hr"].cuda())
+    loss.backward()
+    tol_pred, tol_t, tol_all = (1e-5, 2e-4, 1e-4) if precision == "fp32" else (3e-2, 2.5e-1, 8e-2)
+    assert rel_l2(pred.detach().cpu(), g["pred"]) < tol_pred
+    assert float(loss.detach()) == pytest.approx(float(g["loss"]), rel=1e-5 if precision == "fp32" else 2e-2)
+    _, _, oracle = _rrdb_oracle_grads(g, spec)
+    named = dict(net.named_parameters())
+    num = den = 0.0
+    worst = ("", 0.0)
+    gscale = math.sqrt(sum(float(v.double().pow(2).sum()) for v in oracle.values()))
+    for n, ref in oracle.items():
+        got = named[n].grad.detach().cpu()
+        num += float((got.double() - ref.double()).pow(2).sum()); den += float(ref.double().pow(2).sum())
+        err = float((got - ref).norm())
+        rel = err / max(float(ref.norm()), 1e-30)
+        if rel > worst[1] and err > 1e-3 * tol_t * gscale:
+            worst = (n, rel)
+    total = math.sqrt(num / den)
+    print("\n[parity] rrdb pretrain step %s: whole-gradient rel-L2 %.3e, worst tensor %s %.3e" % (precision, total, worst[0], worst[1]))
+    assert total < tol_all and worst[1] < tol_t, worst
+    summ = grad_summary([(n, named[n].grad) for n in oracle], spec["seed"], full_below=128)
+    for n in oracle:
+        ref_norm = float(g["norm/" + n])
+        if ref_norm > 1e-4 * gscale:
+            assert abs(float(summ["norm/" + n]) - ref_norm) <= (2e-3 if precision == "fp32" else 2e-1) * ref_norm, n
+
+
+def test_rrdb_pretraining_reduces_the_loss_and_eval_path_is_unchanged():
+    import torch.nn.functional as F
+    from oracle.cases import calibrate_rrdb_head
+    R = wsr.sub("models.rrdb_encoder.RRDBNet").RRDBNet
+    net = calibrate_rrdb_head(fill_module(R(1, 1, 64, 1, 32, precision="bf16"), 3)).cuda().train()
+    opt = wsr.sub("autograd_glue").FusedAdam(net.parameters(), lr=2e-4)
+    lr = 0.5 * seeded_randn("rp.lr", (4, 1, 16, 32), 9).cuda()
+    hr = wsr.sub("data.dataset_builder").bicubic_sr(lr, 4).clamp(-1, 1)
+    losses = []
+    for _ in range(12):
+        loss = F.l1_loss(net(lr), hr)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert losses[-1] < 0.97 * losses[0] and all(b < a for a, b in zip(losses, losses[1:])), losses
+    net.eval()
+    with torch.no_grad():
+        out, feas = net(lr, True)
+    assert not out.requires_grad and len(feas) == 2 and bool(torch.isfinite(out).all())
