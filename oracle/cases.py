@@ -51,6 +51,8 @@ CASES = {
     "phydiff_grad_small": dict(kind="phydiff_grad", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=62, t=350),
     "sr3_grad_small": dict(kind="sr3_grad", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=2), batch=2, seed=63, t=500),
     "srdiff_grad_small": dict(kind="srdiff_grad", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=1), batch=2, seed=64, t=450),
+    # lock_weights=False: the encoder is trained jointly (extra l1(rrdb_sr, HR) term, gradients through the condition features)
+    "srdiff_joint_grad_small": dict(kind="srdiff_grad", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=1), batch=2, seed=65, t=300, joint=True),
     # priors and the RRDB-conditioned variant
     "simple_cnn": dict(kind="simple_cnn", batch=2, seed=41, lr_hw=(8, 16)),
     "rrdb_pretrain": dict(kind="rrdb_pretrain", batch=2, seed=47, lr_hw=(8, 16), nb=2),

@@ -78,7 +78,12 @@ def run_grad_case(ref, name, spec):
     diff.set_new_noise_schedule(LINEAR_1000, "cpu")
     diff.set_loss("cpu")
     lr, sr, hr = fields(name, b, cfg["image_channels"], cfg["image_height"], cfg["image_width"], seed)
-    if arch == "srdiff":
+    if arch == "srdiff" and spec.get("joint"):
+        # trainable encoder (lock_weights=False): the loss gains l1(rrdb_sr, HR) and the encoder gets gradients (srdiff_diffusion.py:212-214)
+        from .cases import calibrate_rrdb_head
+        diff.rrdb_encoder = calibrate_rrdb_head(fill_module(ref.RRDBNet(1, 1, 64, 17, 32).train(), seed + 1))
+        diff.lock_weights = False
+    elif arch == "srdiff":
         # frozen encoder, as init_rrdb_encoder(lock_weights=True) leaves it (srdiff_diffusion.py:59-75)
         diff.rrdb_encoder = fill_module(ref.RRDBNet(1, 1, 64, 17, 32).eval(), seed + 1)
         for p_ in diff.rrdb_encoder.parameters():
@@ -97,8 +102,10 @@ def run_grad_case(ref, name, spec):
     l_pix.backward()
     out = dict(hr=hr, sr=sr, lr=lr, noise=noise, level=torch.FloatTensor(u), loss=loss.detach().reshape(1), wsum=_checksum(net))
     named = [(n, p.grad) for n, p in net.named_parameters() if p.grad is not None]
+    if spec.get("joint"):
+        named += [("rrdb_encoder." + n, p.grad) for n, p in diff.rrdb_encoder.named_parameters() if p.grad is not None]
     out["names"] = np.array([n for n, _ in named])
-    out.update(grad_summary(named, seed))
+    out.update(grad_summary(named, seed, full_below=128 if spec.get("joint") else 4096))
     return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()}
 
 

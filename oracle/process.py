@@ -138,6 +138,20 @@ def srdiff_param_grads(unet_sd, rrdb_sd, cfg, lr, hr, sr, level, noise, loss_typ
     return loss.detach(), {k: v.grad for k, v in leaf.items() if v.grad is not None}
 
 
+def srdiff_joint_param_grads(unet_sd, rrdb_sd, cfg, lr, hr, sr, level, noise, loss_type="l1"):
+    """SRDiff training step with a TRAINABLE encoder (srdiff_diffusion.py:161-216, lock_weights=False): the loss gains
+    ``F.l1_loss(rrdb_sr, HR)`` (:212-214) and both parameter sets receive gradients.  Returns (loss, unet grads, rrdb grads)."""
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in unet_sd.items()}
+    rleaf = {k: v.detach().clone().requires_grad_(True) for k, v in rrdb_sd.items()}
+    rrdb_sr, feas = nets.rrdb_net(rleaf, lr)
+    x_noisy = q_sample(hr - sr, level.view(-1, 1, 1, 1), noise)
+    eps = nets.srdiff_unet(leaf, feas, x_noisy, level.view(-1, 1), cfg)
+    loss = (noise - eps).abs().sum() if loss_type == "l1" else ((noise - eps) ** 2).sum()
+    loss = loss + (rrdb_sr - hr).abs().mean()
+    (loss / hr.numel()).backward()
+    return loss.detach(), {k: v.grad for k, v in leaf.items() if v.grad is not None}, {k: v.grad for k, v in rleaf.items() if v.grad is not None}
+
+
 def arch_param_grads(arch, sd, cfg, hr, sr, level, noise, loss_type="l1"):
     leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
     loss, _ = arch_p_losses(arch, leaf, cfg, hr, sr, level, noise, loss_type)

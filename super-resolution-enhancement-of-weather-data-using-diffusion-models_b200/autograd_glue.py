@@ -17,14 +17,18 @@ weights_epoch = 0          # bumped by every optimizer step that writes paramete
 
 class DenoiseFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, net, x, time):
+    def forward(ctx, anchor, net, x, time, cond=None):
+        """cond: SRDiff with a trainable encoder -- the condition cat(feas[2::3]) as a tensor ARGUMENT, so that autograd routes
+        its gradient (``UNetTrainPlan.cond_grad``) back into the encoder's backward pass."""
+        ctx.has_cond = cond is not None
         if isinstance(x, (tuple, list)):
             # SRDiff: x = (18 RRDB feature maps, x_t); the condition is cat(feas[2::3]) (srdiff/unet.py:117-118)
             feas, x_t = x
             b = x_t.shape[0]
             pl = net.train_plan(b, x_t.device)
             pl.train_mode = bool(net.training)
-            pl.set_condition(torch.cat(list(feas[2::3]), dim=1))
+            pl.want_cond_grad = cond is not None
+            pl.set_condition(cond.detach() if cond is not None else torch.cat(list(feas[2::3]), dim=1))
             pl.set_levels(time.reshape(b))
             eps = pl.denoise(x_t)
             ctx.pl, ctx.net = pl, net
@@ -55,7 +59,7 @@ class DenoiseFn(torch.autograd.Function):
                 p.grad = g
             else:
                 p.grad.add_(g)
-        return None, None, None, None
+        return None, None, None, None, (pl.cond_grad() if (ctx.has_cond and ctx.needs_input_grad[4]) else None)
 
 
 class NoiseLossFn(torch.autograd.Function):
@@ -122,11 +126,22 @@ class FusedAdam(torch.optim.Optimizer):
             step_t = torch.tensor(float(f["step"]))
             for p in plan.param_order:
                 self.state[p]["step"] = step_t
+            # parameters of the group that are NOT part of the flat plan (e.g. a jointly trained RRDB encoder) step one by one
+            in_plan = f.get("ids")
+            if in_plan is None:
+                in_plan = f["ids"] = {id(p) for p in plan.param_order}
+            self._step_each([p for p in group["params"] if id(p) not in in_plan], group)
             weights_epoch += 1
             return loss
         for group in self.param_groups:
-            b1, b2 = group["betas"]
-            for p in group["params"]:
+            self._step_each(group["params"], group)
+        weights_epoch += 1
+        return loss
+
+    def _step_each(self, params, group):
+        b1, b2 = group["betas"]
+        if True:
+            for p in params:
                 if p.grad is None:
                     continue
                 if p.dtype != torch.float32 or not p.is_contiguous() or not p.is_cuda:
@@ -141,5 +156,3 @@ class FusedAdam(torch.optim.Optimizer):
                 nat.call("wsr_adam_step", p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
                          float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
                          int(st["step"].item()), torch.cuda.current_stream(p.device).cuda_stream)
-        weights_epoch += 1
-        return loss

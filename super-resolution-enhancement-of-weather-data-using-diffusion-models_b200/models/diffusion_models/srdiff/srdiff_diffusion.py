@@ -1,5 +1,6 @@
-"""SRDiffDiffusion -- drop-in for the reference's srdiff/srdiff_diffusion.py:9-219: frozen RRDB encoder once per batch,
-then T reverse steps of the SRDiff UNet conditioned on 6 of its 18 feature maps."""
+"""SRDiffDiffusion -- drop-in for the reference's srdiff/srdiff_diffusion.py:9-219: RRDB encoder once per batch, then T reverse
+steps of the SRDiff UNet conditioned on 6 of its 18 feature maps; training with a frozen (``lock_weights=True``) or a jointly trained
+encoder."""
 import numpy as np
 import torch
 
@@ -62,13 +63,17 @@ class SRDiffDiffusion(GaussianDiffusion):
         return super().p_sample(x, t, clip_denoised=clip_denoised, condition_x=cond)
 
     def p_losses(self, x_in, noise=None):
-        """reference :161-216 (locked encoder: no extra RRDB loss term)."""
+        """reference :161-216.  Locked encoder: the noise loss alone.  ``lock_weights=False``: ``loss + F.l1_loss(rrdb_sr, HR)`` (:212-214)
+        with the gradient flowing into the encoder both through its SR image and through the six condition features."""
         sr_up, lr, hr = x_in['SR'], x_in['LR'], x_in['HR']
-        if self.rrdb_encoder is not None and not self.lock_weights:
-            raise NotImplementedError("joint training of the RRDB encoder (lock_weights=False) is not part of the accelerated path")
         dev = sr_up.device
         b = sr_up.shape[0]
-        rrdb_sr, feas = self.rrdb_encoder(lr, True)
+        joint = (self.rrdb_encoder is not None and not self.lock_weights and torch.is_grad_enabled()
+                 and any(p.requires_grad for p in self.rrdb_encoder.parameters()))
+        if joint:
+            rrdb_sr, feas = self.rrdb_encoder.forward_joint(lr.to(dev))
+        else:
+            rrdb_sr, feas = self.rrdb_encoder(lr, True)
         t = np.random.randint(1, self.num_timesteps + 1)
         level = torch.FloatTensor(np.random.uniform(self.sqrt_alphas_cumprod_prev[t - 1],
                                                     self.sqrt_alphas_cumprod_prev[t], size=b)).to(dev)
@@ -78,8 +83,11 @@ class SRDiffDiffusion(GaussianDiffusion):
         nat.call("wsr_q_sample", hr32.data_ptr(), sr32.data_ptr(), noise.data_ptr(), level.data_ptr(), b,
                  sr32[0].numel(), x_noisy.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
         eps = self.denoise_fn((feas, x_noisy), level.view(b, -1))
-        del rrdb_sr          # locked encoder: the reference's extra l1(rrdb_sr, HR) term does not apply (:212-214)
         if eps.requires_grad:
             from ....autograd_glue import NoiseLossFn
-            return NoiseLossFn.apply(noise, eps, self.loss_type == 'l2')
-        return self._noise_loss(noise, eps)
+            loss = NoiseLossFn.apply(noise, eps, self.loss_type == 'l2')
+        else:
+            loss = self._noise_loss(noise, eps)
+        if self.rrdb_encoder is not None and not self.lock_weights:
+            return loss + torch.nn.functional.l1_loss(rrdb_sr, hr.to(torch.float32))          # reference :212-214
+        return loss

@@ -65,6 +65,8 @@ class UNet(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from ....autograd_glue import DenoiseFn
             anchor = next(p for p in self.parameters() if p.requires_grad)
+            if torch.is_tensor(feas):          # joint training: the condition cat(feas[2::3]) as ONE differentiable tensor
+                return DenoiseFn.apply(anchor, self, ([], x_t), time, feas)
             return DenoiseFn.apply(anchor, self, (list(feas), x_t), time)
         if self.training and self.dropout:
             pl = self.train_plan(b, x_t.device)

@@ -183,9 +183,10 @@ class _RRDBPlan:
         self.eng.wgrad(xs, dy, table, conv.weight.grad, (1, ci * kh * kw, kh * kw), conv.bias.grad, up, force_simt=force_simt)
 
     @torch.no_grad()
-    def backward(self, d_raw):
+    def backward(self, d_raw=None, d_cond=None):
         """Parameter gradients (accumulated into ``p.grad``) from the gradient w.r.t. the RAW ``conv_last`` output (B, out_nc, 4h, 4w)
-        of the forward pass whose activations this plan still holds.  Every convolution: weight / bias gradient (tcgen05 where the
+        and / or w.r.t. the condition cat(feas[2::3]) (B, 6 nf, h, w) that SRDiff's UNet consumes (joint training,
+        srdiff_diffusion.py:212-214), for the forward pass whose activations this plan still holds.  Every convolution: weight / bias gradient (tcgen05 where the
         shapes allow, SIMT otherwise) + data gradient = the forward kernel on transposed flipped weights; the dense blocks run on ONE
         (nf + 4 gc)-channel gradient buffer that mirrors the forward concat buffer (growth slices accumulate in place), LeakyReLU
         masks come from the kept outputs."""
@@ -194,19 +195,31 @@ class _RRDBPlan:
         B, h, w, nf, gc = self.B, self.h, self.w, net.nf, net.gc
         new = e.new_act
         t1, t2, t4 = T.forward_taps(3, 1, h, w), T.forward_taps(3, 1, 2 * h, 2 * w), T.forward_taps(3, 1, 4 * h, 4 * w)
-        # ---- tail: conv_last <- lrelu <- HRconv <- lrelu <- upconv2 <- lrelu <- upconv1 (RRDBNet.py:49-55) ----
-        g_last = e.nchw_to_act(d_raw.to(torch.float32).contiguous(), new(B, 4 * h, 4 * w, net.out_nc))
-        self._wgrad(net.conv_last, self.hr, g_last, t4, force_simt=True)
-        g_hr = e.conv(g_last, self._dgrad_pack(net.conv_last), new(B, 4 * h, 4 * w, nf), bias=False, force_simt=True)
-        self._mask(self.hr, g_hr)
-        self._wgrad(net.HRconv, self.up2, g_hr, t4)
-        g_up2 = e.conv(g_hr, self._dgrad_pack(net.HRconv), new(B, 4 * h, 4 * w, nf), bias=False)
-        self._mask(self.up2, g_up2)
-        self._wgrad(net.upconv2, self.up1, g_up2, T.forward_upsample_taps(2 * h, 2 * w), up=2)
-        g_up1 = e.conv(g_up2, self._dgrad_pack(net.upconv2, up=True), new(B, 2 * h, 2 * w, nf), taps=T.dgrad_upsample_taps(2 * h, 2 * w), bias=False)
-        self._mask(self.up1, g_up1)
-        self._wgrad(net.upconv1, self.trunk, g_up1, T.forward_upsample_taps(h, w), up=2)
-        g_fea = e.conv(g_up1, self._dgrad_pack(net.upconv1, up=True), new(B, h, w, nf), taps=T.dgrad_upsample_taps(h, w), bias=False)
+        nb = len(net.RRDB_trunk)
+        fgrads = {}
+        if d_cond is not None:
+            picked = list(range(nb + 1))[2::3]                   # feature k < nb = output of RRDB k, feature nb = fea_first + trunk
+            dc = e.nchw_to_act(d_cond.to(torch.float32).contiguous(), new(B, h, w, nf * len(picked)))
+            fgrads = {k: dc.slice(n_ * nf, nf) for n_, k in enumerate(picked)}
+        if d_raw is not None:
+            # ---- tail: conv_last <- lrelu <- HRconv <- lrelu <- upconv2 <- lrelu <- upconv1 (RRDBNet.py:49-55) ----
+            g_last = e.nchw_to_act(d_raw.to(torch.float32).contiguous(), new(B, 4 * h, 4 * w, net.out_nc))
+            self._wgrad(net.conv_last, self.hr, g_last, t4, force_simt=True)
+            g_hr = e.conv(g_last, self._dgrad_pack(net.conv_last), new(B, 4 * h, 4 * w, nf), bias=False, force_simt=True)
+            self._mask(self.hr, g_hr)
+            self._wgrad(net.HRconv, self.up2, g_hr, t4)
+            g_up2 = e.conv(g_hr, self._dgrad_pack(net.HRconv), new(B, 4 * h, 4 * w, nf), bias=False)
+            self._mask(self.up2, g_up2)
+            self._wgrad(net.upconv2, self.up1, g_up2, T.forward_upsample_taps(2 * h, 2 * w), up=2)
+            g_up1 = e.conv(g_up2, self._dgrad_pack(net.upconv2, up=True), new(B, 2 * h, 2 * w, nf), taps=T.dgrad_upsample_taps(2 * h, 2 * w), bias=False)
+            self._mask(self.up1, g_up1)
+            self._wgrad(net.upconv1, self.trunk, g_up1, T.forward_upsample_taps(h, w), up=2)
+            g_fea = e.conv(g_up1, self._dgrad_pack(net.upconv1, up=True), new(B, h, w, nf), taps=T.dgrad_upsample_taps(h, w), bias=False)
+            if nb in fgrads:
+                self._axpby(g_fea, 1.0, fgrads[nb], 1.0, g_fea)
+        else:
+            assert nb in fgrads, "nothing to differentiate"
+            g_fea = fgrads[nb]
         # ---- fea = fea_first + trunk_conv(last RRDB output) (:46-47) ----
         last_in = self.out_last
         self._wgrad(net.trunk_conv, last_in, g_fea, t1)
@@ -214,8 +227,10 @@ class _RRDBPlan:
         # ---- the trunk, last block first ----
         Dg = new(B, h, w, self.wide)
         go, g5, g_sum = new(B, h, w, nf), new(B, h, w, nf), new(B, h, w, nf)
-        for i in range(len(net.RRDB_trunk) - 1, -1, -1):
+        for i in range(nb - 1, -1, -1):
             rrdb = net.RRDB_trunk[i]
+            if i in fgrads:
+                self._axpby(g, 1.0, fgrads[i], 1.0, g)            # this block's output is one of the condition features
             self._axpby(g, 0.2, g, 0.0, go)                       # out = RDB3(...) * 0.2 + x  (:133): gradient into the RDB chain
             for j, rdb in ((2, rrdb.RDB3), (1, rrdb.RDB2), (0, rrdb.RDB1)):
                 D = self.dense[i][j]
@@ -256,6 +271,27 @@ class _RRDBPretrainFn(torch.autograd.Function):
         return None, None, None
 
 
+class _RRDBJointFn(torch.autograd.Function):
+    """(raw conv_last output, cat(feas[2::3])) with grad_fns: ONE backward call receives both gradients (joint training of the
+    encoder inside SRDiff, srdiff_diffusion.py:176-214)."""
+
+    @staticmethod
+    def forward(ctx, anchor, net, x):
+        pl = net.plan(x)
+        feas = pl.run(x)
+        raw = pl.sr_image_raw()
+        cond = torch.cat([f.to_nchw(pl.eng) for f in feas[2::3]], dim=1)
+        ctx.pl = pl
+        ctx.set_materialize_grads(False)
+        return raw, cond
+
+    @staticmethod
+    def backward(ctx, d_raw, d_cond):
+        if d_raw is not None or d_cond is not None:
+            ctx.pl.backward(d_raw, d_cond)
+        return None, None, None
+
+
 class RRDBNet(nn.Module):
     def __init__(self, in_nc, out_nc, nf, nb, gc=32, precision="bf16"):
         super().__init__()
@@ -293,6 +329,11 @@ class RRDBNet(nn.Module):
             return out
         with torch.no_grad():
             return self._forward_eval(x, get_fea)
+
+    def forward_joint(self, x):
+        """(sr_image, condition cat(feas[2::3])) -- both differentiable w.r.t. the encoder's parameters."""
+        raw, cond = _RRDBJointFn.apply(self.conv_first.weight, self, x)
+        return raw.clamp(0, 1) * 2 - 1, cond
 
     def _forward_eval(self, x, get_fea=False):
         pl = self.plan(x)

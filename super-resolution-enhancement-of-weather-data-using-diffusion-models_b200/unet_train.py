@@ -26,6 +26,7 @@ import torch
 
 from . import _native as nat
 from . import taps as T
+from . import taps as taps_mod
 from .engine import Act
 from .unet_plan import UNetPlan, _L
 
@@ -292,6 +293,10 @@ class UNetTrainPlan(UNetPlan):
                     r.dconv = e.pack_conv(T.upsample_dgrad_weight(w), None, key=("updgrad",) + e._src_key(w),
                                           src=(w.data_ptr(), 1), job_kind=nat.PACK_UPSAMPLE_DGRAD)
             self.dfinal = dg(self.net.final_conv.block[3].weight)
+            if self.kind == "srdiff":
+                # data gradient of cond_proj (joint training of the encoder): its OIHW weight is the parameter itself
+                cp = self.net.cond_proj
+                self.cond_dgrad_pc = e.pack_conv(cp.weight, None, key=("cond_dgrad",) + e._src_key(cp.weight))
         e._keep.clear()
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -432,7 +437,7 @@ class UNetTrainPlan(UNetPlan):
         e = self.eng
         self.deps_in.copy_(d_eps.to(torch.float32))
         self._n_bwd += 1
-        key = ("bwd", self.train_mode, self._ptr_sig())
+        key = ("bwd", self.train_mode, getattr(self, "want_cond_grad", False), self._ptr_sig())
         if self.replay_enabled and self._lists.get("bwd_key") == key:
             e.replay(self._lists["bwd"])
             return self.gflat
@@ -450,6 +455,26 @@ class UNetTrainPlan(UNetPlan):
         elif self._garena is None and self._gtensors:
             self._consolidate_gbufs()
         return self.gflat
+
+    def _cond_grad_launches(self, gy):
+        """SRDiff with a trainable encoder (``lock_weights=False``, srdiff_diffusion.py:212-214): gradient of the loss w.r.t. the
+        condition cat(feas[2::3]) (B, 384, h, w).  cond_up = ConvTranspose2d(k8, s4, p2)(cond) was added to the output of downs[2], so
+        d cond[n, ci, i, j] = sum_{co, ky, kx} dY[n, co, 4i + ky - 2, 4j + kx - 2] W[ci, co, ky, kx]: a stride-4 8x8 convolution over dY
+        whose OIHW weight IS the transposed convolution's (in, out, 8, 8) parameter, run as four 16-tap launches on the tap tables the
+        weight gradient already uses.  Part of the backward launch sequence (and of its recorded list)."""
+        e = self.eng
+        cp = self.net.cond_proj
+        pc = self.cond_dgrad_pc                      # packed with the other backward weights (refresh_weights)
+        cf = self.cond_feat
+        if getattr(self, "_dcond", None) is None:
+            self._dcond = e.new_act(self.B, cf.H, cf.W, cf.C)
+        for q, tp in enumerate(taps_mod.conv_transpose_k8s4_wgrad_taps(cf.H, cf.W)):
+            e.conv(gy, pc, self._dcond, taps=tp, bias=False, res=self._dcond if q else None, force_simt=True)
+
+    def cond_grad(self):
+        """(B, 384, h, w) fp32 NCHW gradient w.r.t. the condition, computed by the last ``backward`` (``want_cond_grad`` set)."""
+        assert self.kind == "srdiff" and getattr(self, "_dcond", None) is not None
+        return self._dcond.to_nchw(self.eng)
 
     def _consolidate_gbufs(self):
         """After the first backward pass every activation-gradient buffer exists: move them into ONE arena so that the
@@ -560,6 +585,8 @@ class UNetTrainPlan(UNetPlan):
             for tp in T.conv_transpose_k8s4_wgrad_taps(self.cond_feat.H, self.cond_feat.W):
                 e.wgrad(gy, self.cond_feat, tp, gw, (1, co_t * 64, 64), None, 1, force_simt=True)
             e.call("wsr_col_sums", gy.ptr, gy.dt, B * gy.H * gy.W, gy.C, gy.ld, self.gv(cp.bias).data_ptr(), st)
+            if getattr(self, "want_cond_grad", False):
+                self._cond_grad_launches(gy)
 
         # level embedding: all FeatureWiseAffine linears at once, then the noise MLP
         e.call("wsr_linear_rows_bwd", self.cur_temb.data_ptr(), B, self.inner, self.proj_w.data_ptr(), self.dproj.data_ptr(), self.P,

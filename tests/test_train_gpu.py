@@ -536,3 +536,69 @@ def test_srdiff_training_step_gradients_vs_reference(precision):
     assert total < (1e-4 if precision == "fp32" else 1.5e-1)
     assert cp < (2e-4 if precision == "fp32" else 1.6e-1)
     assert worst[0] < (2e-4 if precision == "fp32" else 2.5e-1), worst
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_srdiff_joint_training_step_vs_reference(precision):
+    """SRDiff with a TRAINABLE RRDB-17 encoder (``lock_weights=False``, srdiff_diffusion.py:176-214): loss = noise loss + l1(rrdb_sr, HR);
+    the encoder receives gradients through its SR image and through the six condition features (UNetTrainPlan.cond_grad ->
+    _RRDBPlan.backward).  UNet and encoder gradients against the oracle's autograd, which is pinned to the REAL reference's summaries
+    (tests/golden/srdiff_joint_grad_small.npz); then one optimizer step moves both parameter sets."""
+    from conftest import manifest
+    from oracle.cases import calibrate_rrdb_head
+    from oracle.weights import seeded_state_dict
+    g, spec = load_golden("srdiff_joint_grad_small"), CASES["srdiff_joint_grad_small"]
+    cfg = spec["cfg"]
+    U = wsr.sub("models.diffusion_models.srdiff.unet").UNet
+    D = wsr.sub("models.diffusion_models.srdiff.srdiff_diffusion").SRDiffDiffusion
+    R = wsr.sub("models.rrdb_encoder.RRDBNet").RRDBNet
+    net = U(in_channel=cfg["in_channel"], out_channel=cfg["out_channel"], norm_groups=32, inner_channel=64,
+            channel_mults=cfg["channel_mults"], attn_res=cfg["attn_res"], res_blocks=2, dropout=0, image_height=32,
+            image_width=64, image_channels=1, precision=precision)
+    net = fill_module(net, spec["seed"]).cuda().train()
+    diff = D(net, image_height=32, image_width=64, channels=1, conditional=True, lock_weights=False).cuda()
+    diff.rrdb_encoder = calibrate_rrdb_head(fill_module(R(1, 1, 64, 17, 32, precision=precision), spec["seed"] + 1)).cuda().train()
+    diff.set_new_noise_schedule(LINEAR_1000, "cuda:0")
+    diff.set_loss("cuda:0")
+    u = g["level"].numpy().astype(np.float64)
+    ri, un = np.random.randint, np.random.uniform
+    np.random.randint = lambda *a, **k: spec["t"]
+    np.random.uniform = lambda *a, **k: u
+    try:
+        loss = diff.p_losses({"HR": g["hr"].cuda(), "SR": g["sr"].cuda(), "LR": g["lr"].cuda()}, noise=g["noise"].cuda())
+    finally:
+        np.random.randint, np.random.uniform = ri, un
+    (loss.sum() / int(g["hr"].numel())).backward()
+    rel_loss = abs(float(loss.detach()) - float(g["loss"])) / float(g["loss"])
+    rrdb_sd = seeded_state_dict(manifest("rrdb"), spec["seed"] + 1)
+    rrdb_sd["conv_last.bias"] = torch.full_like(rrdb_sd["conv_last.bias"], 0.5)           # calibrate_rrdb_head
+    _, og_unet, og_rrdb = process.srdiff_joint_param_grads(seeded_state_dict(manifest("srdiff", cfg), spec["seed"]), rrdb_sd, cfg,
+                                                           g["lr"], g["hr"], g["sr"], g["level"], g["noise"])
+    report = {}
+    for tag, mod, oracle, prefix in (("unet", net, og_unet, ""), ("rrdb", diff.rrdb_encoder, og_rrdb, "rrdb_encoder.")):
+        num = den = 0.0
+        worst = (0.0, "")
+        gscale = math.sqrt(sum(float(v.double().pow(2).sum()) for v in oracle.values()))
+        for n, p in mod.named_parameters():
+            assert p.grad is not None, n
+            ref = oracle[n].double()
+            err = float((p.grad.detach().cpu().double() - ref).norm())
+            num += err ** 2
+            den += float(ref.norm()) ** 2
+            ref_norm = float(g["norm/" + prefix + n])
+            assert abs(float(ref.norm()) - ref_norm) <= 2e-3 * ref_norm + 1e-6 * gscale, prefix + n      # oracle == real reference
+            if ref.numel() >= 16 and err > 1e-4 * gscale:
+                worst = max(worst, (err / max(float(ref.norm()), 1e-30), n))
+        report[tag] = (math.sqrt(num / den), worst)
+    print("\n[parity] srdiff JOINT training step %s: loss rel err %.3e, whole-gradient rel-L2 unet %.3e / encoder %.3e, worst %s / %s"
+          % (precision, rel_loss, report["unet"][0], report["rrdb"][0], report["unet"][1], report["rrdb"][1]))
+    assert rel_loss < (1e-4 if precision == "fp32" else 2e-2)
+    for tag in ("unet", "rrdb"):
+        assert report[tag][0] < (2e-4 if precision == "fp32" else 1.5e-1), tag
+        assert report[tag][1][0] < (1e-3 if precision == "fp32" else 3e-1), (tag, report[tag][1])
+    # one optimizer step over BOTH parameter sets (the encoder's parameters are outside the UNet's flat buffer)
+    FusedAdam = wsr.sub("autograd_glue").FusedAdam
+    before_u, before_r = net.cond_proj.weight.detach().clone(), diff.rrdb_encoder.trunk_conv.weight.detach().clone()
+    opt = FusedAdam(list(diff.parameters()), lr=1e-4)
+    opt.step()
+    assert not torch.equal(before_u, net.cond_proj.weight.detach()) and not torch.equal(before_r, diff.rrdb_encoder.trunk_conv.weight.detach())
