@@ -63,6 +63,7 @@ class DDPM(BaseModel):
         l_pix.backward()
         if reducer is not None:
             reducer.finish()
+            self._reduce_outside_plan(reducer)
         self.optG.step()
         l_pix = l_pix.detach().clone()
         if world > 1:
@@ -70,6 +71,21 @@ class DDPM(BaseModel):
         # the reference stores l_pix.item() here (model.py:69); the device->host read is deferred to get_current_log() so
         # that the launch queue is not drained after every optimizer step
         self.log_dict['l_pix'] = l_pix
+
+    def _reduce_outside_plan(self, reducer):
+        """Gradients of trainable parameters that are not part of the denoiser's flat buffer (a jointly trained RRDB encoder,
+        ``lock_weights=False``): one coalesced SUM all-reduce after the backward pass."""
+        import torch.distributed as dist
+        in_plan = {id(p) for p in reducer.plan.param_order} if hasattr(reducer, "plan") else set()
+        rest = [p for p in self._net().parameters() if p.requires_grad and p.grad is not None and id(p) not in in_plan]
+        if not rest:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in rest])
+        dist.all_reduce(flat)
+        off = 0
+        for p in rest:
+            p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+            off += p.numel()
 
     def _grad_reducer(self, batch):
         """FlatGradReducer bound to the denoiser's train plan for this local batch size (created once)."""
