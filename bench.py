@@ -131,9 +131,64 @@ def cpu_reference_steps(n_steps, warmup, seed=0):
     return times, cores
 
 
+def gpu_eager_reference_steps(n_steps, warmup, batch, autocast, seed=0):
+    """OPTIONAL extra arm (``--impl reference --ref-device cuda``, never the default): the same oracle port of the reference's
+    algorithm, but executed by eager PyTorch (cuDNN / cuBLAS, one launch per op, fp32 or bf16 autocast) on cuda:0 at ``batch``
+    samples -- what running the reference's own modules on a B200 amounts to.  Returns seconds per step (CUDA events)."""
+    import torch
+    from oracle import nets, process
+    from oracle.schedule import ddpm_tables
+    from oracle.weights import seeded_randn, seeded_state_dict
+    import numpy as np
+    dev = torch.device("cuda:0")
+    torch.backends.cudnn.benchmark = True                    # the reference sets it (train.py:24-25)
+    man = np.load(os.path.join(ROOT, "tests", "golden", "manifest.npz"))
+    keys = [str(k) for k in man["resdiff.keys"]]
+    shapes = [tuple(int(x) for x in str(s).split(",")) if str(s) else () for s in man["resdiff.shapes"]]
+    sd = {k: v.to(dev) for k, v in seeded_state_dict(zip(keys, shapes), seed).items()}
+    cfg = dict(CFG_A)
+    cfg["dropout"] = 0.0
+    tab32, sap = ddpm_tables(LINEAR_1000)
+    tab = {k: torch.from_numpy(v).to(dev) for k, v in tab32.items()}
+    cond = torch.nn.functional.interpolate(seeded_randn("bench.lr", (batch, 1, 32, 64), 1234), scale_factor=4, mode="bicubic").to(dev)
+    x = seeded_randn("bench.x", (batch, 1, 128, 256), 4321).to(dev)
+    z = seeded_randn("bench.z", (batch, 1, 128, 256), 99).to(dev)
+
+    def denoise(xx, level):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            return nets.resdiff_unet(sd, torch.cat([cond, xx], 1), level.to(dev), cfg).float()
+
+    times = []
+    t = T_FULL - 1
+    with torch.no_grad():
+        for i in range(warmup + n_steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            x, _ = process.p_sample_step(denoise, tab, sap, x, t, z)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warmup:
+                times.append(e0.elapsed_time(e1) * 1e-3)
+            t -= 1
+    return times
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.ref_device == "cuda":
+        times = gpu_eager_reference_steps(args.steps, max(args.warmup, 2), args.ref_batch, args.ref_autocast)
+        ms = 1e3 * sum(times) / len(times)
+        val = args.ref_batch / (T_FULL * ms * 1e-3)
+        print(json.dumps({
+            "impl": "reference", "device": "cuda:0 eager PyTorch (%s)" % ("bf16 autocast" if args.ref_autocast else "fp32"),
+            "metric": "128x256 t2m SR samples/sec (1000-step loop)", "value": val, "unit": "samples/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.ref_autocast else "f32", "data": "synthetic",
+            "config": {"workload": "ResDiff Cfg-A UNet, 128x256, 1000-step DDPM reverse loop; oracle port of the reference run by eager PyTorch",
+                       "batch_per_gpu": args.ref_batch, "T": T_FULL},
+            "note": "extra arm, not the CPU baseline: same algorithm, library kernels (cuDNN / cuBLAS) launched op by op", "gpu_launches": 0}))
         return
     times, cores = cpu_reference_steps(args.steps, args.warmup)
     ms = 1e3 * sum(times) / len(times)
@@ -442,6 +497,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="reference arm: cpu (the contract) or the optional eager-PyTorch-on-GPU arm")
+    ap.add_argument("--ref-batch", type=int, default=8)
+    ap.add_argument("--ref-autocast", action="store_true")
     ap.add_argument("--batch", type=int, default=64, help="batch per GPU (weak) or total (strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-e2e", action="store_true")

@@ -26,7 +26,7 @@ def mish(x):
 def positional_encoding(level, dim):
     """nn_modules/functional_layers.py:33-41.  level (B,1) -> (B,1,dim) (the middle dim is kept)."""
     half = dim // 2
-    k = torch.arange(half, dtype=level.dtype) / half
+    k = torch.arange(half, dtype=level.dtype, device=level.device) / half
     arg = level.unsqueeze(1) * torch.exp(-math.log(1e4) * k.unsqueeze(0))
     return torch.cat([torch.sin(arg), torch.cos(arg)], dim=-1)
 
@@ -135,8 +135,8 @@ def fd_info_spliter(sd, p, x_cat, t_emb, in_ch, height, width):
     denoise_x = x * res_se(sd, p + "noise_resSE.", ne)
     # FFT over ALL FOUR dims (no dim= argument, :61-63)
     n, m = x.shape[-2:]
-    u = torch.arange(n, dtype=torch.float32)[:, None] - n / 2
-    v = torch.arange(m, dtype=torch.float32)[None, :] - m / 2
+    u = torch.arange(n, dtype=torch.float32, device=x.device)[:, None] - n / 2
+    v = torch.arange(m, dtype=torch.float32, device=x.device)[None, :] - m / 2
     spec = torch.fft.fftn(torch.complex(cnn_x, torch.zeros_like(cnn_x)))
     x_fd = torch.cat([spec.real, spec.imag], dim=1)
     ell = min(height, width)
