@@ -207,3 +207,26 @@ def test_month_windows_and_helpers():
     with pytest.raises(AssertionError):
         U.validate_month_subset([0, 13])
     assert U.get_month_idx("2000-07-01-00") == 7
+
+
+@pytest.mark.parametrize("name", ["LocalStandardScaling", "IdentityTransform"])
+def test_loader_per_sample_fallback_transforms(root, name):
+    """Transforms the staged path does not cover (per-grid-point statistics, identity): the loader falls back to the reference's
+    per-sample interface and still yields the collate contract."""
+    builder, transforms = wsr.sub("data.dataset_builder"), wsr.sub("data.transforms")
+    dh = builder.DataHandler(root, ["t2m"], root, [1], [[1]], transforms.get_transformation_by_name(name), "2000-01-01-00", "2000-01-06-00",
+                             "2000-01-06-00", "2000-01-07-00", 4, 4, False, 1, device=None)
+    dh.process_data()
+    loader = dh.val_loader
+    assert loader._bulk == (name == "IdentityTransform")
+    batch, months = next(iter(loader))
+    assert batch["LR"].shape == (4, 1, 8, 16) and batch["HR"].shape == (4, 1, 32, 64) and batch["SR"].shape == (4, 1, 32, 64)
+    assert months == [1, 1, 1, 1]
+    raw = dh.val_dataset.data_groups["hr"]["hr_t2m"].wnpy_reader[np.datetime64("2000-01-06T00")]
+    if name == "IdentityTransform":
+        assert torch.equal(batch["HR"][:1], raw)
+    else:
+        t = dh.get_data_transformer().get_transform("t2m", "hr")[1]
+        assert t._mean.shape == (1, 1, 32, 64) and _close(batch["HR"][:1], (raw - t._mean) / t._std(), 1e-6)
+        inv = dh.get_data_transformer().inverse_transform({"HR": batch["HR"]}, months)
+        assert _close(inv["HR"][:1], raw, 1e-6)
