@@ -475,6 +475,17 @@ def run_train(args):
         for name, (n, t, fl, nb) in sorted(summ.items(), key=lambda kv: -kv[1][1]):
             print("#   %-22s %4d %9.3f %9.1f" % (name, n, t, fl / (t * 1e-3) / 1e12 if t > 0 else 0), file=sys.stderr)
         print("#   total of timed kernels %.3f ms (wall per step %.3f ms)" % (tot, ms), file=sys.stderr)
+        # per-shape detail: the recorded launch lists carry no shape tags, so this one step is issued call by call
+        plan.replay_enabled = False
+        plan.eng.prof, plan.eng.prof_detail = [], True
+        step()
+        detail = plan.eng.prof_summary()
+        plan.eng.prof, plan.eng.prof_detail = None, False
+        plan.replay_enabled = True
+        print("# per-shape breakdown of the tensor-core launches of one training step: name launches ms TFLOP/s", file=sys.stderr)
+        for name, (n, t, fl, nb) in sorted(detail.items(), key=lambda kv: -kv[1][1])[:60]:
+            if name.startswith(("wgrad_tc", "conv_tc", "gemm_tc", "conv_taps")):
+                print("#   %-42s %3d %8.3f %8.1f" % (name, n, t, fl / (t * 1e-3) / 1e12 if t > 0 else 0), file=sys.stderr)
     if rank == 0:
         peaks, peak_src = _peaks()
         tfl = 3 * FLOPS_PER_SAMPLE_STEP * B / (ms * 1e-3) / 1e12

@@ -325,9 +325,22 @@ extern "C" int wsr_conv_wgrad_tc(const WsrWgradDesc* d, const WsrTapTable* t, vo
   p.n_tiles = wg_cdiv(d->Cin, bn);
   const int tiles = p.ntaps * p.m_tiles * p.n_tiles;
   const int total_kb = p.nseg * p.g1 * p.g2 * p.g3;
-  int splits = wg_cdiv(sm_count(), tiles);
-  if (splits > total_kb) splits = total_kb;
-  if (splits < 1) splits = 1;
+  // K splits: one CTA per SM is resident (the operand ring takes most of the shared memory), so the launch runs in
+  // ceil(tiles * splits / SMs) waves of ceil(total_kb / splits) K blocks each, plus a fixed per-CTA cost (prologue, TMEM round
+  // trip, the red.global.add epilogue) of roughly a dozen K blocks.  The former rule ceil(SMs / tiles) overshot one wave by a few
+  // CTAs for most layers (9 taps x 17 splits = 153 CTAs on 148 SMs: a second, almost empty wave doubled the time).
+  int splits = 1;
+  {
+    const int sms = sm_count();
+    double best = 1e30;
+    const int smax = total_kb < 8 * sms ? total_kb : 8 * sms;
+    for (int sp = 1; sp <= smax; ++sp) {
+      const int waves = wg_cdiv(tiles * sp, sms);
+      const double cost = (double)waves * ((double)wg_cdiv(total_kb, sp) + 12.0);
+      if (cost < best) { best = cost; splits = sp; }
+      if (tiles * sp > 4 * sms && wg_cdiv(total_kb, sp) < 12) break;
+    }
+  }
   p.splits = splits;
   cudaStream_t st = (cudaStream_t)stream;
   switch (bn) {
