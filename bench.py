@@ -483,9 +483,11 @@ def run_train(args):
         plan.eng.prof, plan.eng.prof_detail = None, False
         plan.replay_enabled = True
         print("# per-shape breakdown of the tensor-core launches of one training step: name launches ms TFLOP/s", file=sys.stderr)
-        for name, (n, t, fl, nb) in sorted(detail.items(), key=lambda kv: -kv[1][1])[:60]:
+        for name, (n, t, fl, nb) in sorted(detail.items(), key=lambda kv: -kv[1][1])[:90]:
             if name.startswith(("wgrad_tc", "conv_tc", "gemm_tc", "conv_taps")):
                 print("#   %-42s %3d %8.3f %8.1f" % (name, n, t, fl / (t * 1e-3) / 1e12 if t > 0 else 0), file=sys.stderr)
+            elif name.startswith("gn_bwd"):
+                print("#   %-42s %3d %8.3f %8.1f GB/s" % (name, n, t, nb / (t * 1e-3) / 1e9 if t > 0 else 0), file=sys.stderr)
     if rank == 0:
         peaks, peak_src = _peaks()
         tfl = 3 * FLOPS_PER_SAMPLE_STEP * B / (ms * 1e-3) / 1e12

@@ -624,7 +624,7 @@ static int gn_bwd_common(GnBwdArgs& a, const void* x, int x_dtype, int N, int HW
   a.groups = groups; a.eps = eps; a.act = act; a.da = da; a.da_ld = da_ld; a.drop_p = drop_p; a.drop_seed = drop_seed;
   a.drop_tag = drop_tag; a.red = red; a.red_ld = red_ld; a.N = N;
   // pixels per block: enough blocks to fill the machine, at least 8 pixels each
-  int64_t want_blocks = 1184;
+  int64_t want_blocks = 1184;       // measured at B = 4: 592 / 296 / 148 blocks change the step time by < 1 % either way
   int chunk = (int)(((int64_t)N * HW + want_blocks - 1) / want_blocks);
   if (chunk < 8) chunk = 8;
   if (chunk > HW) chunk = HW;

@@ -453,9 +453,10 @@ class Engine:
                   act, da.ptr, da.dt, da.ld, float(drop[0]), drop[1] if isinstance(drop[1], C.c_uint64) else int(drop[1]), int(drop[2]),
                   red_ptr, 2 * x.C)
         nb = x.N * x.H * x.W * x.C * (2 if x.dt == nat.BF16 else 4)
-        self.call("wsr_gn_bwd_reduce", *common, self.stream, nbytes=2 * nb, tag="gn_bwd_reduce")
+        shape = " C%d %dx%d" % (x.C, x.H, x.W) if self.prof_detail else ""
+        self.call("wsr_gn_bwd_reduce", *common, self.stream, nbytes=2 * nb, tag="gn_bwd_reduce" + shape)
         self.call("wsr_gn_bwd_apply", *common, dx.ptr, dx.dt, dx.ld, 1 if accumulate else 0, _ptr(dgamma), _ptr(dbeta),
-                  colsum, colsum_ld, self.stream, nbytes=(4 if accumulate else 3) * nb, tag="gn_bwd_apply")
+                  colsum, colsum_ld, self.stream, nbytes=(4 if accumulate else 3) * nb, tag="gn_bwd_apply" + shape)
 
     def wgrad(self, x, dy, taps, dw, dw_strides, dbias=None, up=1, force_simt=False):
         """dw (fp32 tensor view, strides (tap, co, ci) in elements) += weight gradient; dbias += column sums of dy."""
