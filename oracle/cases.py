@@ -44,6 +44,8 @@ CASES = {
     # short reverse chains with injected noise
     "resdiff_chain_small": dict(kind="resdiff_chain", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=21, T=4),
     "resdiff_chain_full_b1": dict(kind="resdiff_chain", cfg=unet_cfg(128, 256), batch=1, seed=22, T=3),
+    # BASELINE configs[0]: ResDiff Cfg-A, batch 1, 50-step DDPM sampling at 128x256 (the reference's own CPU-runnable case)
+    "resdiff_c1_t50": dict(kind="resdiff_chain", cfg=unet_cfg(128, 256), batch=1, seed=23, T=50, regenerate_noise=True),
     # training loss (dropout 0, injected t / level / noise)
     "resdiff_loss_small": dict(kind="resdiff_loss", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=31, t=400),
     # one training step: loss / numel -> backward (model.py:61-69); fixture = per-parameter gradient summaries

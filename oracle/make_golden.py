@@ -133,7 +133,12 @@ def run_case(ref, name, spec):
             with _InjectedNoise(noise) as inj:
                 res = diff.super_resolution({"SR": sr})
                 assert inj.i == T, inj.i          # 1 randn + (T-1) randn_like
-            out.update(cond=sr, noise=noise, sr_out=res, wsum=_checksum(net))
+            if spec.get("regenerate_noise"):
+                # long chains: the noise is regenerated from its seed by the tests (same torch build on both machines), only the
+                # condition and the reference's final field are stored
+                out.update(cond=sr, sr_out=res, noise_head=noise[:2, :, :, :2, :8].clone(), wsum=_checksum(net))
+            else:
+                out.update(cond=sr, noise=noise, sr_out=res, wsum=_checksum(net))
         elif kind == "resdiff_loss":
             cfg, t = spec["cfg"], spec["t"]
             net = fill_module(_unet(ref, cfg), seed)

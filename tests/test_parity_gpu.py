@@ -56,6 +56,28 @@ def test_resdiff_chain_vs_reference(name, precision):
         assert err < TOL[precision], err
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_baseline_config0_50_step_chain_vs_reference(precision):
+    """BASELINE configs[0]: ResDiff Cfg-A, batch 1, 50-step DDPM sampling at 128x256 -- the final super-resolved field against the REAL
+    reference's CPU run (tests/golden/resdiff_c1_t50.npz; the injected noise chain is regenerated from its seed), as relative L2 and
+    as RMSE in Kelvin (x 21.26 K, the WeatherBench t2m standard deviation)."""
+    from oracle.weights import seeded_randn
+    g, spec = load_golden("resdiff_c1_t50"), CASES["resdiff_c1_t50"]
+    cfg, T = spec["cfg"], spec["T"]
+    noise = seeded_randn("resdiff_c1_t50.noise", (T + 1,) + tuple(g["cond"].shape), spec["seed"])
+    assert torch.equal(noise[:2, :, :, :2, :8], g["noise_head"])               # same generator stream as the fixture's run
+    D = wsr.sub("models.diffusion_models.resdiff.resdiff_diffusion").ResDiffDiffusion
+    net = _resdiff(cfg, spec["seed"], precision)
+    diff = D(net, image_height=128, image_width=256, channels=1, conditional=True).cuda()
+    diff.set_new_noise_schedule(short_schedule(T), "cuda:0")
+    out = diff.p_sample_loop(g["cond"].cuda(), noise_chain=noise.cuda()).cpu()
+    err = rel_l2(out, g["sr_out"])
+    rmse_k = 21.26 * float(((out - g["sr_out"]) ** 2).mean().sqrt())
+    print("\n[parity] configs[0] (B=1, T=50, 128x256) %s: final-field rel-L2 = %.3e, RMSE = %.4f K" % (precision, err, rmse_k))
+    assert err < (1e-4 if precision == "fp32" else 2e-2), err
+    assert rmse_k < (1e-3 if precision == "fp32" else 0.1), rmse_k
+
+
 def test_resdiff_loss_vs_reference():
     import numpy as np
     g, spec = load_golden("resdiff_loss_small"), CASES["resdiff_loss_small"]
