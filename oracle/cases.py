@@ -52,6 +52,7 @@ CASES = {
     "resdiff_grad_small": dict(kind="resdiff_grad", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=61, t=400),
     "phydiff_grad_small": dict(kind="phydiff_grad", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=62, t=350),
     "sr3_grad_small": dict(kind="sr3_grad", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=2), batch=2, seed=63, t=500),
+    "srdiff_chain_small": dict(kind="srdiff_chain", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=1), batch=2, seed=63, T=4),
     "srdiff_grad_small": dict(kind="srdiff_grad", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=1), batch=2, seed=64, t=450),
     # lock_weights=False: the encoder is trained jointly (extra l1(rrdb_sr, HR) term, gradients through the condition features)
     "srdiff_joint_grad_small": dict(kind="srdiff_grad", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=1), batch=2, seed=65, t=300, joint=True),

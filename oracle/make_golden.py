@@ -225,6 +225,20 @@ def run_case(ref, name, spec):
             x_t = seeded_randn(name + ".xt", sr.shape, seed)
             level = torch.tensor(spec["level"], dtype=torch.float32).view(b, 1)
             out.update(lr=lr, x_t=x_t, level=level, eps=net((feas, x_t), level), wsum=_checksum(net))
+        elif kind == "srdiff_chain":
+            # the SRDiff sampling loop with its encoder (srdiff_diffusion.py:77-131): encode LR once, T reverse steps conditioned on
+            # the features, + bicubic
+            cfg, T = spec["cfg"], spec["T"]
+            net = fill_module(_unet(ref, cfg, srdiff=True), seed)
+            diff = ref.SRDiffDiffusion(net, image_height=cfg["image_height"], image_width=cfg["image_width"], channels=1, conditional=True)
+            diff.rrdb_encoder = fill_module(ref.RRDBNet(1, 1, 64, 17, 32).eval(), seed + 1)
+            diff.set_new_noise_schedule(short_schedule(T), "cpu")
+            lr, sr, _ = fields(name, b, 1, cfg["image_height"], cfg["image_width"], seed)
+            noise = seeded_randn(name + ".noise", (T + 1,) + tuple(sr.shape), seed)
+            with _InjectedNoise(noise) as inj:
+                res = diff.super_resolution({"SR": sr, "LR": lr})
+                assert inj.i == T, inj.i
+            out.update(lr=lr, cond=sr, noise=noise, sr_out=res, wsum=_checksum(net))
         else:
             raise KeyError(kind)
     return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()}

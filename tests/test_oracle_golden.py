@@ -195,3 +195,12 @@ def test_srdiff_param_grads_match_reference():
     for n in names:
         ref_norm = float(g["norm/" + n])
         assert abs(float(summ["norm/" + n]) - ref_norm) <= 1e-4 * ref_norm + 1e-12, n
+
+
+def test_srdiff_chain():
+    """The oracle's SRDiff sampling loop (encoder + T reverse steps) against the real reference's run."""
+    g, spec = load_golden("srdiff_chain_small"), CASES["srdiff_chain_small"]
+    with torch.no_grad():
+        out = process.srdiff_chain(_sd("srdiff", spec["seed"], spec["cfg"]), _sd("rrdb", spec["seed"] + 1), spec["cfg"],
+                                   short_schedule(spec["T"]), g["lr"], g["cond"], g["noise"])
+    assert rel_l2(out, g["sr_out"]) < TOL

@@ -138,6 +138,28 @@ def test_srdiff_step_vs_reference(precision):
     assert err < TOL[precision], err
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_srdiff_chain_vs_reference(precision):
+    """SRDiff sampling loop with its RRDB-17 encoder through ``SRDiffDiffusion.super_resolution`` (srdiff_diffusion.py:77-131) against
+    the REAL reference: encoder once per batch, T reverse steps conditioned on six feature maps, + bicubic."""
+    g, spec = load_golden("srdiff_chain_small"), CASES["srdiff_chain_small"]
+    cfg = spec["cfg"]
+    U = wsr.sub("models.diffusion_models.srdiff.unet").UNet
+    D = wsr.sub("models.diffusion_models.srdiff.srdiff_diffusion").SRDiffDiffusion
+    R = wsr.sub("models.rrdb_encoder.RRDBNet").RRDBNet
+    net = U(in_channel=cfg["in_channel"], out_channel=cfg["out_channel"], norm_groups=32, inner_channel=64,
+            channel_mults=cfg["channel_mults"], attn_res=cfg["attn_res"], res_blocks=2, dropout=0, image_height=32,
+            image_width=64, image_channels=1, precision=precision)
+    net = fill_module(net, spec["seed"]).cuda().eval()
+    diff = D(net, image_height=32, image_width=64, channels=1, conditional=True).cuda()
+    diff.rrdb_encoder = fill_module(R(1, 1, 64, 17, 32, precision=precision), spec["seed"] + 1).cuda().eval()
+    diff.set_new_noise_schedule(short_schedule(spec["T"]), "cuda:0")
+    out = diff.p_sample_loop({"SR": g["cond"].cuda(), "LR": g["lr"].cuda()}, noise_chain=g["noise"].cuda())
+    err = rel_l2(out.cpu(), g["sr_out"])
+    print("\n[parity] srdiff chain %s final-field rel-L2 = %.3e" % (precision, err))
+    assert err < TOL[precision], err
+
+
 def test_simple_cnn_vs_reference():
     g, spec = load_golden("simple_cnn"), CASES["simple_cnn"]
     S = wsr.sub("models.simple_cnn.Simple_CNN").SimpleCNN
