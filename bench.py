@@ -6,6 +6,9 @@ batch 64 per GPU, synthetic WeatherBench-shaped fields, random-init weights).
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun for N>1)
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+    python bench.py --impl reference --ref-device cuda [--ref-batch 16] [--ref-autocast]     # optional extra: the same algorithm run
+                                                             # op by op by eager PyTorch on cuda:0 (never the default arm)
+    python bench.py --workload train [--profile-ops]         # configs[2]: the training step
 
 A "step" is ONE reverse (p_sample) step of the loop over the whole local batch: level-projection select, FD gate,
 stem assembly, the UNet (~270 kernel launches, replayed as one CUDA graph), the fused sampler update.  Every one of the

@@ -91,10 +91,9 @@ def grad_summary(named_grads, seed, full_below=4096):
 
 
 def calibrate_rrdb_head(net):
-    """Variance-preserving random weights drive the encoder's raw output far outside [0, 1], where ``clamp(0, 1)`` (RRDBNet.py:56)
-    zeroes almost every gradient.  For the pre-training fixture the last convolution is scaled down and centred so that most
-    of the output sits inside the clamp range while part of it still saturates (both branches of the mask are exercised)."""
+    """Variance-preserving random weights with a near-zero bias put ~99 % of the encoder's raw output outside [0, 1], where
+    ``clamp(0, 1)`` (RRDBNet.py:56) zeroes the gradient.  For the training fixtures the last convolution's bias is centred on the
+    clamp range: ~83 % of the output then sits inside it and ~17 % still saturates (both branches of the mask are exercised)."""
     with torch.no_grad():
-        net.conv_last.weight.mul_(1.0)
         net.conv_last.bias.fill_(0.5)
     return net

@@ -140,19 +140,18 @@ class FusedAdam(torch.optim.Optimizer):
 
     def _step_each(self, params, group):
         b1, b2 = group["betas"]
-        if True:
-            for p in params:
-                if p.grad is None:
-                    continue
-                if p.dtype != torch.float32 or not p.is_contiguous() or not p.is_cuda:
-                    raise nat.WsrError("FusedAdam: parameters must be contiguous fp32 CUDA tensors")
-                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                st = self.state[p]
-                if len(st) == 0:
-                    st["step"] = torch.tensor(0.0)
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["step"] = st["step"] + 1
-                nat.call("wsr_adam_step", p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
-                         float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
-                         int(st["step"].item()), torch.cuda.current_stream(p.device).cuda_stream)
+        for p in params:
+            if p.grad is None:
+                continue
+            if p.dtype != torch.float32 or not p.is_contiguous() or not p.is_cuda:
+                raise nat.WsrError("FusedAdam: parameters must be contiguous fp32 CUDA tensors")
+            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            st = self.state[p]
+            if len(st) == 0:
+                st["step"] = torch.tensor(0.0)
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["step"] = st["step"] + 1
+            nat.call("wsr_adam_step", p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
+                     float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                     int(st["step"].item()), torch.cuda.current_stream(p.device).cuda_stream)
