@@ -37,6 +37,28 @@ CFG_A = dict(in_channel=5, out_channel=1, norm_groups=32, inner_channel=64, chan
              res_blocks=2, dropout=0.2, image_height=128, image_width=256, image_channels=1)
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on stdout when NCCL_DEBUG
+    is set, as it is on the GPU boxes): file descriptor 1 is pointed at stderr for the rest of the run and the JSON line goes to the
+    saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(text):
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(text, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (text + "\n").encode())
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -184,7 +206,7 @@ def run_reference(args):
         times = gpu_eager_reference_steps(args.steps, max(args.warmup, 2), args.ref_batch, args.ref_autocast)
         ms = 1e3 * sum(times) / len(times)
         val = args.ref_batch / (T_FULL * ms * 1e-3)
-        print(json.dumps({
+        _emit(json.dumps({
             "impl": "reference", "device": "cuda:0 eager PyTorch (%s)" % ("bf16 autocast" if args.ref_autocast else "fp32"),
             "metric": "128x256 t2m SR samples/sec (1000-step loop)", "value": val, "unit": "samples/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -206,7 +228,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -390,7 +412,7 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu,
             "tc_launches_per_step": plan.eng.n_tc, "simt_launches_total": plan.eng.n_simt,
         }
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -494,7 +516,7 @@ def run_train(args):
     if rank == 0:
         peaks, peak_src = _peaks()
         tfl = 3 * FLOPS_PER_SAMPLE_STEP * B / (ms * 1e-3) / 1e12
-        print(json.dumps({
+        _emit(json.dumps({
             "metric": "ResDiff training step samples/sec (fwd+bwd+allreduce+Adam)", "value": B * world / (ms * 1e-3), "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.train_precision, "data": "synthetic",
@@ -508,6 +530,7 @@ def run_train(args):
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
