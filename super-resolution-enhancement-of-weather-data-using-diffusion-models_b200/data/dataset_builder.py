@@ -55,8 +55,13 @@ class DeviceBatchLoader:
     device: a CUDA device -> device-resident batches (see the module docstring); None -> host tensors.
     drop_last is always on and the order is a fresh permutation per epoch when ``shuffle`` (reference :139-147)."""
 
-    def __init__(self, dataset, batch_size, shuffle=False, num_workers=4, device=None, scale=4, prefetch=2, seed=0):
+    def __init__(self, dataset, batch_size, shuffle=False, num_workers=4, device=None, scale=4, prefetch=2, seed=0, shard=None):
+        """shard = (rank, world): under one-process-per-GPU data parallelism every rank walks the SAME batch sequence (same seed) but
+        reads, copies and transforms only its contiguous 1 / world slice of each global batch (``batch_size`` stays the GLOBAL size,
+        as in the reference's config; what ``nn.DataParallel`` scattered after loading is never loaded here)."""
         self.dataset, self.batch_size, self.shuffle, self.scale = dataset, int(batch_size), bool(shuffle), scale
+        self.shard = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
+        assert 0 <= self.shard[0] < self.shard[1] and self.batch_size % self.shard[1] == 0, "global batch must divide by the world size"
         self.device = torch.device(device) if device is not None else None
         self.prefetch = max(1, int(prefetch))
         self.workers = max(1, int(num_workers or 1))
@@ -116,12 +121,15 @@ class DeviceBatchLoader:
 
     def _new_bufs(self):
         pin = self.device is not None
-        return {k: torch.empty((self.batch_size,) + self._shapes[k], dtype=torch.float32, pin_memory=pin) for k in ("lr", "hr")}
+        n = self.batch_size // self.shard[1]
+        return {k: torch.empty((n,) + self._shapes[k], dtype=torch.float32, pin_memory=pin) for k in ("lr", "hr")}
 
     # ---- iteration ---------------------------------------------------------------------------------------------------
     def __iter__(self):
         order = self._order()
-        batches = [order[i * self.batch_size:(i + 1) * self.batch_size] for i in range(len(self))]
+        r, w = self.shard
+        per = self.batch_size // w
+        batches = [order[i * self.batch_size + r * per:i * self.batch_size + (r + 1) * per] for i in range(len(self))]
         if not self._bulk:
             for idx in batches:
                 yield form_batch([self.dataset[int(i)] for i in idx], self.scale, self.device)
@@ -197,7 +205,7 @@ def form_batch(samples, scale=4, device=None):
 class DataHandler:
     def __init__(self, dataroot, variables, storage_root, months_subset, groups, transformation, train_min_date=None,
                  train_max_date=None, val_min_date=None, val_max_date=None, val_batch_size=None, train_batch_size=None,
-                 shuffle_data=True, num_workers=None, device="auto"):
+                 shuffle_data=True, num_workers=None, device="auto", shard=None):
         self.metadata = {}
         self.dataroot, self.variables, self.storage_root = dataroot, variables, storage_root
         self.months_subset, self.groups, self.transformation = months_subset, groups, transformation
@@ -211,6 +219,7 @@ class DataHandler:
         if device == "auto":
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
         self.device = device
+        self.shard = shard                 # (rank, world) for the TRAINING loader under torchrun; validation is not sharded
         self._readers = {}
 
     # ---- accessors -----------------------------------------------------------------------------------------------
@@ -299,7 +308,8 @@ class DataHandler:
     def create_train_loader(self, batch_size, use_shuffle, num_workers):
         if self.train_dataset is None:
             raise ValueError("Training dataset is not created. Call create_train_set() first.")
-        self.train_loader = DeviceBatchLoader(self.train_dataset, batch_size, shuffle=use_shuffle, num_workers=num_workers, device=self.device)
+        self.train_loader = DeviceBatchLoader(self.train_dataset, batch_size, shuffle=use_shuffle, num_workers=num_workers, device=self.device,
+                                              shard=self.shard)
         return self.train_loader
 
     def create_val_loader(self, batch_size, use_shuffle, num_workers):

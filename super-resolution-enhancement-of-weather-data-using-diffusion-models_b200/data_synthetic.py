@@ -52,14 +52,14 @@ def is_store(root):
     return bool(root) and os.path.isdir(os.path.join(root, "lr")) and os.path.isdir(os.path.join(root, "hr"))
 
 
-def store_handler(opt, val_only=False):
+def store_handler(opt, val_only=False, shard=None):
     """The reference's ``DataHandler(...)`` call of train.py:232-238 / sample.py:51-56 for ``opt['data']``; None when
     ``dataroot`` is not a store directory.  ``val_only`` = sample.py's variant (transforms fitted on the validation range)."""
     d = opt["data"]
     root = str(d.get("dataroot", ""))
     if not is_store(root):
         return None
-    key = (root, val_only, str(d.get("train_min_date")), str(d.get("train_max_date")), str(d.get("val_min_date")), str(d.get("val_max_date")),
+    key = (root, val_only, shard, str(d.get("train_min_date")), str(d.get("train_max_date")), str(d.get("val_min_date")), str(d.get("val_max_date")),
            str(d.get("months_subset")))
     if key not in _handlers:
         from .data.dataset_builder import DataHandler
@@ -73,18 +73,20 @@ def store_handler(opt, val_only=False):
             storage = tempfile.mkdtemp(prefix="wsr_meta_")
         dh = DataHandler(root, d["variables"], storage, d["months_subset"], groups, get_transformation_by_name(d["transformation"]),
                          lo, hi, d["val_min_date"], d["val_max_date"], d["val_batch_size"], d["batch_size"], d.get("use_shuffle", True),
-                         d.get("num_workers", 4))
+                         d.get("num_workers", 4), shard=shard)
         dh.process_data()
         _handlers[key] = dh
     return _handlers[key]
 
 
-def batches_from_opt(opt, phase, n_batches=None):
+def batches_from_opt(opt, phase, n_batches=None, shard=None):
+    """shard = (rank, world): the store's training loader then yields this rank's slice of every global batch (already sharded);
+    synthetic / file batches are always global and are cut by the caller."""
     d = opt["data"]
     m = opt["model"]["diffusion"]
     bs = d["val_batch_size"] if phase == "val" else d["batch_size"]
     root = str(d.get("dataroot", ""))
-    dh = store_handler(opt)
+    dh = store_handler(opt, shard=shard)
     if dh is not None:
         if phase == "val":
             return iter(dh.val_loader)

@@ -75,9 +75,11 @@ def main(argv=None):
         return vm.metrics2dict(), vm_k.metrics2dict()
     it = 0
     par = wsr.sub("parallel")
-    for batch, months in data.batches_from_opt(opt, "train"):
+    from_store = data.is_store(str(opt["data"].get("dataroot", "")))
+    shard = (rank, world) if (world > 1 and from_store) else None        # the store loader reads only this rank's slice
+    for batch, months in data.batches_from_opt(opt, "train", shard=shard):
         it += 1
-        if world > 1:
+        if world > 1 and shard is None:
             batch = par.shard_batch(batch, rank, world)
         model.feed_data((batch, months))
         model.optimize_parameters()

@@ -230,3 +230,18 @@ def test_loader_per_sample_fallback_transforms(root, name):
         assert t._mean.shape == (1, 1, 32, 64) and _close(batch["HR"][:1], (raw - t._mean) / t._std(), 1e-6)
         inv = dh.get_data_transformer().inverse_transform({"HR": batch["HR"]}, months)
         assert _close(inv["HR"][:1], raw, 1e-6)
+
+
+def test_loader_rank_shards_partition_the_global_batches(handler):
+    """One process per GPU: ranks walk the same (shuffled) batch sequence and each reads only its contiguous slice."""
+    L = wsr.sub("data.dataset_builder").DeviceBatchLoader
+    train_set, _ = handler.get_datasets()
+    full = list(L(train_set, 8, shuffle=True, num_workers=1, device=None, seed=5))
+    parts = [list(L(train_set, 8, shuffle=True, num_workers=1, device=None, seed=5, shard=(r, 4))) for r in range(4)]
+    assert all(len(p) == len(full) == 816 // 8 for p in parts)
+    for i in (0, 7, len(full) - 1):
+        for k in ("HR", "LR", "SR"):
+            assert torch.equal(torch.cat([p[i][0][k] for p in parts]), full[i][0][k]), (i, k)
+        assert sum((p[i][1] for p in parts), []) == full[i][1]
+    with pytest.raises(AssertionError, match="divide"):
+        L(train_set, 6, device=None, shard=(0, 4))
