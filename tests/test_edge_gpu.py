@@ -88,3 +88,37 @@ def test_metric_accumulators_vs_reference_fixture_and_fused_inverse():
     got = vm.compute_metrics()
     for name in ("MAE", "MSE", "RMSE", "MR"):
         assert abs(float(got[name]) - ref[name]) <= 2e-5 * abs(ref[name]) + 1e-6, name
+
+
+def test_edge_kernels_fallback_paths():
+    """Shapes the vectorised kernels do not take (plane sizes that are not multiples of 4, bases that are not 16-byte aligned, a
+    scale other than 4 / 8) run on the scalar kernels with the same results."""
+    torch.manual_seed(11)
+    # generic bicubic kernel (scale 2 and 3)
+    for scale in (2, 3):
+        lr = torch.randn(3, 2, 6, 10)
+        assert rel_l2(builder.bicubic_sr(lr.cuda(), scale).cpu(), edge.collate_sr(lr, scale)) < 1e-6
+    # 5 x 7 planes: hw = 35
+    x = torch.randn(4, 2, 5, 7) * 7 + 280
+    mean, std = torch.tensor([[270.0, 5000.0]] * 4), torch.tensor([[9.0, 300.0]] * 4)
+    back = transforms.transform_batch(transforms.inverse_batch(x.cuda(), mean, std), mean, std).cpu()
+    assert rel_l2(transforms.inverse_batch(x.cuda(), mean, std).cpu(), edge.inverse_tensor(x, mean, std)) < 1e-6 and rel_l2(back, x) < 1e-5
+    # misaligned base: a view that starts one element into its storage
+    flat = torch.randn(2 * 1 * 16 * 32 + 1).cuda()
+    v = flat[1:].view(2, 1, 16, 32)
+    assert v.data_ptr() % 16 != 0
+    m1, s1 = torch.tensor([[1.5], [-2.0]]), torch.tensor([[2.0], [0.5]])
+    assert rel_l2(transforms.inverse_batch(v, m1, s1).cpu(), edge.inverse_tensor(v.cpu(), m1, s1)) < 1e-6
+    # error sums on odd plane sizes and with a misaligned operand
+    pred, target = torch.randn(4, 2, 5, 7), torch.randn(4, 2, 5, 7)
+    ref = edge.error_metrics([(pred, target)])
+    vm = metrics.ValidationMetrics(metrics.create_metric_dict("cuda:0"))
+    vm.update(pred.cuda(), target.cuda())
+    got = vm.compute_metrics()
+    for name in ("MAE", "MSE", "RMSE", "MR"):
+        assert abs(float(got[name]) - ref[name]) <= 1e-5 * abs(ref[name]) + 1e-7, name
+    ref2 = edge.error_metrics([(v.cpu(), torch.zeros_like(v.cpu()))])
+    vm.reset()
+    vm.update(v, torch.zeros_like(v))
+    got2 = vm.compute_metrics()
+    assert abs(float(got2["RMSE"]) - ref2["RMSE"]) <= 1e-5 * ref2["RMSE"]
