@@ -87,14 +87,27 @@ __device__ __forceinline__ void st_dt(void* p, int64_t i, int dt, float v) {
 // 16-byte vector access to VEC consecutive channels, widened to fp32 registers
 template <typename T, int VEC> struct VecLoad;
 template <> struct VecLoad<float, 4> {
+  typedef float4 Raw;
+  static __device__ __forceinline__ Raw ldraw(const float* p) { return *(const float4*)p; }
+  static __device__ __forceinline__ void widen(const Raw& q, float (&v)[4]) { v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
   static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) { float4 q = *(const float4*)p; v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
   static __device__ __forceinline__ void st(float* p, const float (&v)[4]) { *(float4*)p = make_float4(v[0], v[1], v[2], v[3]); }
 };
 template <> struct VecLoad<float, 1> {
+  typedef float Raw;
+  static __device__ __forceinline__ Raw ldraw(const float* p) { return *p; }
+  static __device__ __forceinline__ void widen(const Raw& q, float (&v)[1]) { v[0] = q; }
   static __device__ __forceinline__ void ld(const float* p, float (&v)[1]) { v[0] = *p; }
   static __device__ __forceinline__ void st(float* p, const float (&v)[1]) { *p = v[0]; }
 };
 template <> struct VecLoad<__nv_bfloat16, 8> {
+  typedef uint4 Raw;
+  static __device__ __forceinline__ Raw ldraw(const __nv_bfloat16* p) { return *(const uint4*)p; }
+  static __device__ __forceinline__ void widen(const Raw& q, float (&v)[8]) {
+    const __nv_bfloat162* h = (const __nv_bfloat162*)&q;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
   static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[8]) {
     uint4 q = *(const uint4*)p;
     const __nv_bfloat162* h = (const __nv_bfloat162*)&q;
@@ -110,6 +123,9 @@ template <> struct VecLoad<__nv_bfloat16, 8> {
   }
 };
 template <> struct VecLoad<__nv_bfloat16, 1> {
+  typedef __nv_bfloat16 Raw;
+  static __device__ __forceinline__ Raw ldraw(const __nv_bfloat16* p) { return *p; }
+  static __device__ __forceinline__ void widen(const Raw& q, float (&v)[1]) { v[0] = __bfloat162float(q); }
   static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[1]) { v[0] = __bfloat162float(*p); }
   static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[1]) { *p = __float2bfloat16_rn(v[0]); }
 };

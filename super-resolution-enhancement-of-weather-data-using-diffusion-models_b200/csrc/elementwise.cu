@@ -266,23 +266,27 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x, int HW, int C, int ld,
   TO* yb = y + (int64_t)n * HW * y_ld + cv * VEC;
   int p = p0 + pl;
   for (; p + 3 * PL < p1; p += 4 * PL) {          // four independent 16-byte loads in flight per thread
-    float v[4][VEC];
+    // the loaded vectors stay RAW (4 registers each for bf16) until their turn: widening all four up front cost 32 live fp32
+    // registers, 72 per thread and 3 resident blocks per SM (ncu: 33 % achieved occupancy, 61 % of the DRAM peak)
+    typename VecLoad<TI, VEC>::Raw raw[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) VecLoad<TI, VEC>::ld(xb + (int64_t)(p + u * PL) * ld, v[u]);
+    for (int u = 0; u < 4; ++u) raw[u] = VecLoad<TI, VEC>::ldraw(xb + (int64_t)(p + u * PL) * ld);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
+      float v[VEC];
+      VecLoad<TI, VEC>::widen(raw[u], v);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
-        const float t = fmaf(v[u][i], sc[i], sh[i]);
-        v[u][i] = (sizeof(TO) == 2 && act == WSR_ACT_SWISH) ? swish_fast(t) : apply_act(t, act);
+        const float t = fmaf(v[i], sc[i], sh[i]);
+        v[i] = (sizeof(TO) == 2 && act == WSR_ACT_SWISH) ? swish_fast(t) : apply_act(t, act);
       }
       if constexpr (DROP) {
         float m[VEC];
         dropout_scale<VEC>(drop_seed, drop_tag, ((uint64_t)n * HW + (uint64_t)(p + u * PL)) * C + (uint64_t)cv * VEC, drop_p, m);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) v[u][i] *= m[i];
+        for (int i = 0; i < VEC; ++i) v[i] *= m[i];
       }
-      VecLoad<TO, VEC>::st(yb + (int64_t)(p + u * PL) * y_ld, v[u]);
+      VecLoad<TO, VEC>::st(yb + (int64_t)(p + u * PL) * y_ld, v);
     }
   }
   for (; p < p1; p += PL) {
