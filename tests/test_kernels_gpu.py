@@ -224,6 +224,24 @@ def test_softmax_rows():
     assert rel_l2(p, torch.softmax(s * 0.3, -1)) < 1e-5
 
 
+@pytest.mark.parametrize("cols", [128, 512, 1024])
+def test_softmax_rows_warp_per_row_path(cols):
+    """Row lengths that are multiples of 128 up to 1024 (the sampler's attention shapes) take the one-warp-per-row kernel: fp32 and packed
+    bf16 outputs, a row count that is not a multiple of the 8 rows per block, large logits."""
+    torch.manual_seed(8)
+    dev = _dev()
+    eng = Engine(dev, "fp32")
+    s = torch.randn(37, cols, device=dev) * 6
+    s[3, 5] = 80.0
+    ref = torch.softmax(s * 0.25, -1)
+    p = torch.empty_like(s)
+    eng.softmax(s, nat.F32, 37, cols, 0.25, p, nat.F32)
+    assert rel_l2(p, ref) < 1e-6 and float((p.sum(-1) - 1).abs().max()) < 1e-5
+    pb = torch.empty(37, cols, device=dev, dtype=torch.bfloat16)
+    eng.softmax(s, nat.F32, 37, cols, 0.25, pb, nat.BF16)
+    assert rel_l2(pb.float(), ref) < 4e-3
+
+
 def test_sampler_step_and_randn():
     from oracle.schedule import ddpm_tables
     from oracle.cases import LINEAR_1000
