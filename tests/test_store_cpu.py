@@ -245,3 +245,26 @@ def test_loader_rank_shards_partition_the_global_batches(handler):
         assert sum((p[i][1] for p in parts), []) == full[i][1]
     with pytest.raises(AssertionError, match="divide"):
         L(train_set, 6, device=None, shard=(0, 4))
+
+
+def test_loader_abandoned_iteration_releases_its_reader_thread(handler):
+    """Breaking out of an epoch early (the reference's ``next(iter(val_loader))`` in sample.py:79) must not leave the staging thread
+    blocked: closing the generator stops it."""
+    import threading
+    import time
+    L = wsr.sub("data.dataset_builder").DeviceBatchLoader
+    train_set, _ = handler.get_datasets()
+    before = threading.active_count()
+    it = iter(L(train_set, 8, shuffle=True, num_workers=2, device=None, seed=1))
+    next(it)
+    next(it)
+    it.close()
+    deadline = time.time() + 10
+    while threading.active_count() > before and time.time() < deadline:
+        time.sleep(0.05)
+    assert threading.active_count() <= before
+    # a reader failure surfaces in the consumer instead of hanging it
+    broken = L(train_set, 8, device=None)
+    broken._stage = lambda *a, **k: (_ for _ in ()).throw(OSError("disk gone"))
+    with pytest.raises(OSError, match="disk gone"):
+        next(iter(broken))
