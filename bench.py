@@ -2,7 +2,10 @@
 """bench.py -- headline benchmark of the diffusion super-resolution hot path (BASELINE.json).
 
 Metric: 128x256 t2m super-resolution samples/s for the full 1000-step DDPM reverse loop (ResDiff Cfg-A UNet, bf16,
-batch 64 per GPU, synthetic WeatherBench-shaped fields, random-init weights).
+batch 64 IN TOTAL sharded over the N GPUs = BASELINE.json configs[1] / SURVEY 8(d) C2, i.e. strong scaling; synthetic
+WeatherBench-shaped fields, random-init weights).  The same JSON line carries, as sub-records: ``weak`` (64 samples PER GPU),
+``train`` (configs[2]: the training step, NCCL all-reduce at N > 1), ``configs`` (configs[3] SRDiff + RRDB-17 at B = 32 and
+configs[4] the 3-variable stress model, N = 1), ``eager_gpu_baseline`` (the reference's algorithm in eager PyTorch on the same GPU).
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun for N>1)
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
@@ -118,6 +121,11 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
 # ----------------------------------------------------------------------------------------------------------------------
+def workload_text(global_batch):
+    return ("configs[1]: ResDiff Cfg-A UNet (inner 64, mults 1-2-4-8-8, attn@16) + bicubic prior, t2m 32x64->128x256, "
+            "1000-step DDPM reverse loop, bf16, batch %d in total sharded over the GPUs" % global_batch)
+
+
 def cpu_reference_steps(n_steps, warmup, seed=0):
     """Times reverse steps of the reference algorithm (oracle/ port, fp32 torch-CPU, all host threads) at B=1, 128x256.
     Returns (seconds per step list, cores)."""
@@ -218,12 +226,15 @@ def run_reference(args):
     times, cores = cpu_reference_steps(args.steps, args.warmup)
     ms = 1e3 * sum(times) / len(times)
     val = 1.0 / (T_FULL * ms * 1e-3)
-    sample = "B=1 of the batch, %d reverse steps of the 1000-step chain at 128x256 (oracle port of the reference, fp32 torch-CPU)" % len(times)
+    sample = ("B=1 of the batch of 64, %d reverse steps of the 1000-step chain at 128x256 (oracle port of the reference, fp32 torch-CPU, all "
+              "host threads); samples/s = 1 / (1000 x s per step): the CPU runs the samples of a batch one after the other.  The port computes "
+              "attention without the reference's .contiguous() copies of the (B,N,N) matrices (39%% of the reference's CPU step in the survey), "
+              "so it is FASTER than the reference's own modules would be" % len(times))
     line = {
         "impl": "reference", "metric": "128x256 t2m SR samples/sec (1000-step loop)", "value": val, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ResDiff Cfg-A UNet, 128x256, 1000-step DDPM reverse loop; CPU arm runs batch 1", "T": T_FULL},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_text(64), "global_batch": 64, "T": T_FULL, "cpu_arm": "bounded sample: batch 1 of the 64, fp32"},
         "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -236,218 +247,224 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------------
 def _conv_traffic():
     """DRAM bytes per gemm_tc_kernel launch (read + write, averaged over the launches of a B=64 sampler step) from the
-    committed ncu pass (profiles/r01c_conv_traffic.json <- profiles/r01c_ncu_launches.csv); None if the file is missing."""
-    try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01c_conv_traffic.json")) as f:
-            return json.load(f)["dram_bytes_per_launch"]
-    except Exception:
-        return None
+    committed ncu pass (profiles/*conv_traffic.json, newest round first); None if no file is there."""
+    pdir = os.path.join(ROOT, "profiles")
+    for name in ("r02_conv_traffic.json", "r01c_conv_traffic.json"):
+        try:
+            with open(os.path.join(pdir, name)) as f:
+                return json.load(f)["dram_bytes_per_launch"], name
+        except Exception:
+            continue
+    return None, None
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class _Ctx:
+    """Process-wide state of one bench run (rank, device, barrier helpers)."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, *vals):
+        t = self.torch.tensor([float(v) for v in vals], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def _resdiff(ctx, precision="bf16", **over):
     import wsr
-    nat = wsr.pkg.native
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    n_gpus = world
-    B = args.batch if args.scaling == "weak" else max(1, args.batch // world)
-    global_batch = B * world
-
+    torch = ctx.torch
     U = wsr.sub("models.diffusion_models.resdiff.unet").UNet
     D = wsr.sub("models.diffusion_models.resdiff.resdiff_diffusion").ResDiffDiffusion
     networks = wsr.sub("models.diffusion_models.networks")
+    cfg = dict(CFG_A)
+    cfg.update(over)
     torch.manual_seed(0)
-    net = U(precision="bf16", **CFG_A)
+    net = U(precision=precision, **cfg)
     networks.init_weights(net, "orthogonal")          # the reference's "random-init weights" (networks.py:164-165)
-    net = net.to(dev).eval()
-    diff = D(net, image_height=128, image_width=256, channels=1, conditional=True).to(dev)
-    diff.set_new_noise_schedule(LINEAR_1000, dev)
+    net = net.to(ctx.dev).eval()
+    diff = D(net, image_height=cfg["image_height"], image_width=cfg["image_width"], channels=cfg["image_channels"], conditional=True).to(ctx.dev)
+    diff.set_new_noise_schedule(LINEAR_1000, ctx.dev)
+    return net, diff
 
-    # synthetic WeatherBench-shaped standardised fields (SURVEY 8d): LR randn, SR = bicubic x4, in PINNED host memory
-    g = torch.Generator().manual_seed(1234 + rank)
-    lr = torch.randn(B, 1, 32, 64, generator=g)
-    sr_host = torch.nn.functional.interpolate(lr, scale_factor=4, mode="bicubic").contiguous().pin_memory()
-    out_host = torch.empty_like(sr_host).pin_memory()
 
-    plan = net.plan(B, dev, strict_tc=False)
+def _time_loop(ctx, diff, plan, set_condition, shape, K, warmup, sample_clocks=False):
+    """Precompute (timed separately), W eager warm-up steps, graph capture, K timed graph replays bracketed by barrier + synchronize.
+    Returns dict(ms_per_step, pre_ms, launches_per_step, clocks, loop) -- times are the MAX over ranks."""
+    torch = ctx.torch
+    import wsr
+    nat = wsr.pkg.native
     ev = lambda: torch.cuda.Event(enable_timing=True)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    # ---- once-per-batch precompute (condition-only hoists + level table + initial noise) -------------------------------
-    cond = sr_host.to(dev, non_blocking=True)
-    torch.cuda.synchronize(dev)
+    set_condition()                                   # untimed first call (lazy init)
+    loop = diff.begin_loop(plan, shape, seed=7)
+    torch.cuda.synchronize(ctx.dev)
     e0, e1 = ev(), ev()
-    plan.set_condition(cond)                       # untimed first call (lazy init)
-    loop = diff.begin_loop(plan, tuple(cond.shape), seed=7)
-    torch.cuda.synchronize(dev)
     e0.record()
-    plan.set_condition(cond)
-    loop = diff.begin_loop(plan, tuple(cond.shape), seed=7)
+    set_condition()
+    loop = diff.begin_loop(plan, shape, seed=7)
     e1.record()
-    torch.cuda.synchronize(dev)
-    precompute_ms = e0.elapsed_time(e1)
-
-    # ---- warm-up (eager, also counts launches per step), capture, timed graph replays ----------------------------------
+    torch.cuda.synchronize(ctx.dev)
+    pre_ms = e0.elapsed_time(e1)
     l0 = nat.launches
     loop.step()
     launches_per_step = nat.launches - l0
-    for _ in range(max(0, args.warmup - 1)):
+    for _ in range(max(0, warmup - 1)):
         loop.step()
     loop.capture()
     loop.replay()                                   # one graph warm-up replay
-    K = args.steps
-    if K + args.warmup + 2 > T_FULL:
-        K = T_FULL - args.warmup - 2
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
+    K = min(K, T_FULL - warmup - 2)
+    sampler = ClockSampler(ctx.local) if sample_clocks else None
+    ctx.barrier()
+    if sampler:
+        sampler.start()
     e0, e1 = ev(), ev()
     e0.record()
     for _ in range(K):
         loop.replay()
     e1.record()
-    barrier()
-    clocks = sampler.stop()
-    ms_local = e0.elapsed_time(e1)
-    tmax = torch.tensor([ms_local, precompute_ms], device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_total, pre_ms = float(tmax[0]), float(tmax[1])
-    ms_per_step = ms_total / K
-    value = global_batch / (T_FULL * ms_per_step * 1e-3 + pre_ms * 1e-3)
+    ctx.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_total, pre = ctx.max_over_ranks(e0.elapsed_time(e1), pre_ms)
+    return dict(ms_per_step=ms_total / K, pre_ms=pre, launches_per_step=launches_per_step, clocks=clocks, loop=loop, K=K)
 
-    # ---- roofline pass: one eager step with per-launch CUDA events ------------------------------------------------------
+
+def _synthetic_sr(ctx, B, c=1, lr_hw=(32, 64), scale=4, pinned=True):
+    """Synthetic WeatherBench-shaped standardised fields: LR randn, SR = bicubic upsample, in PINNED host memory."""
+    torch = ctx.torch
+    g = torch.Generator().manual_seed(1234 + ctx.rank)
+    lr = torch.randn(B, c, lr_hw[0], lr_hw[1], generator=g)
+    sr = torch.nn.functional.interpolate(lr, scale_factor=scale, mode="bicubic").contiguous()
+    return lr, (sr.pin_memory() if pinned else sr)
+
+
+def _roofline(ctx, plan, loop, B, ms_per_step, profile_ops):
+    """One eager step with per-launch CUDA events on the launching stream -> the conv_tc (gemm_tc_kernel) roofline record."""
     plan.eng.prof = []
     loop.step()
     summ = plan.eng.prof_summary()
     plan.eng.prof = None
     peaks, peak_src = _peaks()
-    conv = summ.get("conv_tc", [0, 1e-9, 0, 0])
+    conv = summ.get("conv_tc", [0, 1e-9, 0, 0, 0])
     conv_tflops = conv[2] / (conv[1] * 1e-3) / 1e12 if conv[1] > 0 else 0.0
+    conv_xtflops = conv[4] / (conv[1] * 1e-3) / 1e12 if conv[1] > 0 else 0.0
     step_ms_prof = sum(v[1] for v in summ.values())
+    traffic, traffic_src = _conv_traffic()
+    whole = B * FLOPS_PER_SAMPLE_STEP / (ms_per_step * 1e-3) / 1e12
     roofline = {
         "bound": "tensor", "kernel": "gemm_tc_kernel (conv_tc launches)", "achieved": conv_tflops, "peak": peaks["bf16_tflops"],
-        "unit": "TFLOP/s", "frac": conv_tflops / peaks["bf16_tflops"], "traffic": _conv_traffic(),
-        "traffic_note": "ncu dram__bytes_read+write per gemm_tc_kernel launch, averaged over one B=64 step (profiles/r01c_conv_traffic.json)",
+        "unit": "TFLOP/s", "frac": conv_tflops / peaks["bf16_tflops"],
+        "executed_flops_per_step": conv[4], "algorithmic_flops_per_step": conv[2],
+        "achieved_executed": conv_xtflops, "frac_executed": conv_xtflops / peaks["bf16_tflops"],
+        "executed_note": "the four nearest-x2 + 3x3 convolutions run 4 phase-merged taps instead of the reference's 9: 'achieved' counts the "
+                         "reference's FLOPs (SURVEY 8d), 'achieved_executed' what the tensor pipe really did (compare with ncu)",
+        "traffic": traffic, "traffic_note": "ncu dram__bytes_read+write per gemm_tc_kernel launch, averaged over one B=64 step (profiles/%s)" % traffic_src,
         "peak_source": peak_src + " burst",
         "launches_per_step": conv[0], "kernel_ms_per_step": conv[1], "kernel_share_of_step": conv[1] / step_ms_prof if step_ms_prof else None,
-        "whole_step_tflops": global_batch / world * FLOPS_PER_SAMPLE_STEP / (ms_per_step * 1e-3) / 1e12,
-        "whole_step_frac_of_sustained": global_batch / world * FLOPS_PER_SAMPLE_STEP / (ms_per_step * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
+        "whole_step_tflops": whole,
+        "whole_step_frac_of_burst": whole / peaks["bf16_tflops"],
+        "whole_step_frac_of_sustained": whole / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
+        "per_op_ms": {k: round(v[1], 4) for k, v in sorted(summ.items(), key=lambda kv: -kv[1][1])[:8]},
     }
-    if args.profile_ops and rank == 0:
+    if profile_ops and ctx.rank == 0:
         plan.eng.prof, plan.eng.prof_detail = [], True
         loop.step()
         detail = plan.eng.prof_summary()
         plan.eng.prof, plan.eng.prof_detail = None, False
-        print("# per-shape breakdown of the tensor-core launches (B=%d): name launches ms TFLOP/s" % B, file=sys.stderr)
-        for name, (n, ms, fl, nb) in sorted(detail.items(), key=lambda kv: -kv[1][1]):
-            if name.startswith("conv_tc") or name.startswith("gemm_tc"):
-                print("#   %-40s %3d %8.3f %8.1f" % (name, n, ms, fl / (ms * 1e-3) / 1e12 if ms > 0 else 0), file=sys.stderr)
+        print("# per-shape breakdown of the tensor-core launches (B=%d): name launches ms TFLOP/s(algorithmic) TFLOP/s(executed)" % B, file=sys.stderr)
+        for name, (n, ms, fl, nb, xf) in sorted(detail.items(), key=lambda kv: -kv[1][1]):
+            if name.startswith(("conv_tc", "gemm_tc", "attn_tc")):
+                print("#   %-40s %3d %8.3f %8.1f %8.1f" % (name, n, ms, fl / (ms * 1e-3) / 1e12 if ms > 0 else 0, xf / (ms * 1e-3) / 1e12 if ms > 0 else 0), file=sys.stderr)
         rows = sorted(summ.items(), key=lambda kv: -kv[1][1])
         print("# per-op breakdown of one eager step (B=%d): name launches ms TFLOP/s GB/s" % B, file=sys.stderr)
-        for name, (n, ms, fl, nb) in rows:
+        for name, (n, ms, fl, nb, xf) in rows:
             print("#   %-22s %4d %9.3f %9.1f %9.1f" % (name, n, ms, fl / (ms * 1e-3) / 1e12 if ms > 0 else 0, nb / (ms * 1e-3) / 1e9 if ms > 0 else 0), file=sys.stderr)
         print("#   total %.3f ms (graph: %.3f ms/step)" % (step_ms_prof, ms_per_step), file=sys.stderr)
-
-    # ---- end-to-end through the public API with HOST buffers ------------------------------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        budget_s = args.e2e_budget
-        t_e2e = T_FULL
-        est = T_FULL * ms_per_step * 1e-3
-        if est > budget_s:
-            t_e2e = max(10, int(T_FULL * budget_s / est))
-        sched = dict(LINEAR_1000)
-        sched["n_timestep"] = t_e2e
-        diff.set_new_noise_schedule(sched, dev)
-        diff.sample_seed = 11
-        barrier()
-        t0 = time.perf_counter()
-        x_in = {"SR": sr_host.to(dev, non_blocking=True)}
-        res = diff.super_resolution(x_in)
-        out_host.copy_(res, non_blocking=True)
-        torch.cuda.synchronize(dev)
-        el = time.perf_counter() - t0
-        tt = torch.tensor([el], device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        el = float(tt[0])
-        e2e = {"value": global_batch / (el * T_FULL / t_e2e), "unit": "samples/s", "h2d_bytes_per_step": sr_host.numel() * 4,
-               "d2h_bytes_per_step": out_host.numel() * 4, "api": "ResDiffDiffusion.super_resolution({'SR': host tensor}) + .cpu()",
-               "loop_steps_run": t_e2e, "seconds": el,
-               "note": "one public-API call = one whole reverse loop; H2D of the condition and D2H of the result inside the timed region"
-                       + ("" if t_e2e == T_FULL else "; run with a %d-step schedule and scaled to 1000 steps" % t_e2e)}
-        diff.set_new_noise_schedule(LINEAR_1000, dev)
-
-    # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        times, cores = cpu_reference_steps(args.cpu_steps, 1)
-        mean = sum(times) / len(times)
-        cpu = {"value": 1.0 / (T_FULL * mean), "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": "B=1, %d reverse steps at 128x256 of the oracle port (fp32 torch-CPU), %.2f s/step" % (len(times), mean)}
-
-    if rank == 0:
-        line = {
-            "metric": "128x256 t2m SR samples/sec (1000-step loop)", "value": value, "unit": "samples/s", "n_gpus": n_gpus,
-            "steps": K, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "configs[1]: ResDiff Cfg-A UNet (inner 64, mults 1-2-4-8-8, attn@16) + bicubic prior, t2m 32x64->128x256, "
-                                   "1000-step DDPM reverse loop, bf16", "global_batch": global_batch, "batch_per_gpu": B, "T": T_FULL,
-                       "step": "one reverse step over the local batch (CUDA-graph replay)", "precompute_ms_per_batch": pre_ms,
-                       "l2": "per-step activations >> 126 MB L2, no flush needed", "parallelism": "batch-sharded x%d, no collective in the loop" % world},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
-            "roofline": roofline, "cpu_baseline": cpu,
-            "tc_launches_per_step": plan.eng.n_tc, "simt_launches_total": plan.eng.n_simt,
-        }
-        _emit(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    return roofline
 
 
-# ----------------------------------------------------------------------------------------------------------------------
-# secondary workload: configs[2], the training step (not the headline metric; `--workload train`)
-# ----------------------------------------------------------------------------------------------------------------------
-def run_train(args):
-    """One training step = q_sample + UNet forward (dropout 0.2) + loss + hand-written backward + bucketed gradient
-    all-reduce + one-launch Adam over the flat parameter buffer, batch 4 per GPU at 128x256 (BASELINE.json configs[2])."""
+def _e2e(ctx, diff, sr_host, B, ms_per_step, budget_s):
+    """The same metric through the public API with HOST buffers: H2D of the condition, the whole reverse loop and D2H of the result
+    inside the timed region (a shorter schedule, scaled to 1000 steps, when the full loop does not fit the budget)."""
+    torch = ctx.torch
+    out_host = torch.empty_like(sr_host).pin_memory()
+    t_e2e = T_FULL
+    est = T_FULL * ms_per_step * 1e-3
+    if est > budget_s:
+        t_e2e = max(10, int(T_FULL * budget_s / est))
+    sched = dict(LINEAR_1000)
+    sched["n_timestep"] = t_e2e
+    diff.set_new_noise_schedule(sched, ctx.dev)
+    diff.sample_seed = 11
+    ctx.barrier()
+    t0 = time.perf_counter()
+    x_in = {"SR": sr_host.to(ctx.dev, non_blocking=True)}
+    res = diff.super_resolution(x_in)
+    out_host.copy_(res, non_blocking=True)
+    torch.cuda.synchronize(ctx.dev)
+    el = time.perf_counter() - t0
+    (el,) = ctx.max_over_ranks(el)
+    diff.set_new_noise_schedule(LINEAR_1000, ctx.dev)
+    return {"value": B * ctx.world / (el * T_FULL / t_e2e), "unit": "samples/s", "h2d_bytes_per_step": sr_host.numel() * 4,
+            "d2h_bytes_per_step": out_host.numel() * 4, "api": "ResDiffDiffusion.super_resolution({'SR': host tensor}) + .cpu()",
+            "loop_steps_run": t_e2e, "seconds": el,
+            "note": "one public-API call = one whole reverse loop; H2D of the condition and D2H of the result inside the timed region"
+                    + ("" if t_e2e == T_FULL else "; run with a %d-step schedule and scaled to 1000 steps" % t_e2e)}
+
+
+def measure_sampling(ctx, net, diff, B, args, full):
+    """configs[1] at B samples on this GPU.  full: also roofline pass, e2e and clocks (the headline record)."""
+    torch = ctx.torch
+    _, sr_host = _synthetic_sr(ctx, B)
+    plan = net.plan(B, ctx.dev, strict_tc=False)
+    cond = sr_host.to(ctx.dev, non_blocking=True)
+    torch.cuda.synchronize(ctx.dev)
+    r = _time_loop(ctx, diff, plan, lambda: plan.set_condition(cond), tuple(cond.shape), args.steps, args.warmup, sample_clocks=full)
+    ms, pre = r["ms_per_step"], r["pre_ms"]
+    rec = {"batch_per_gpu": B, "global_batch": B * ctx.world, "ms_per_step": ms, "precompute_ms_per_batch": pre,
+           "value": B * ctx.world / (T_FULL * ms * 1e-3 + pre * 1e-3), "unit": "samples/s", "steps": r["K"],
+           "launches_per_step": r["launches_per_step"], "clocks": r["clocks"]}
+    if full:
+        rec["roofline"] = _roofline(ctx, plan, r["loop"], B, ms, args.profile_ops)
+        rec["e2e"] = None if args.no_e2e else _e2e(ctx, diff, sr_host, B, ms, args.e2e_budget)
+        rec["tc_launches_per_step"], rec["simt_launches_total"] = plan.eng.n_tc, plan.eng.n_simt
+    del r["loop"]
+    return rec
+
+
+def measure_train(ctx, args, steps, warmup, profile=False):
+    """configs[2]: one training step = q_sample + UNet forward (dropout 0.2) + loss + hand-written backward + bucketed gradient
+    all-reduce + one-launch Adam over the flat parameter buffer, batch 4 per GPU at 128x256.  Returns the record (ms per step is the
+    max over ranks); for N > 1 also the step time WITHOUT the all-reduce, so its exposed (non-overlapped) part is visible."""
     import numpy as np
-    import torch
-    import torch.distributed as dist
     import wsr
+    torch, dist = ctx.torch, ctx.dist
     nat = wsr.pkg.native
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
     B = args.train_batch
-    U = wsr.sub("models.diffusion_models.resdiff.unet").UNet
-    D = wsr.sub("models.diffusion_models.resdiff.resdiff_diffusion").ResDiffDiffusion
     glue = wsr.sub("autograd_glue")
     par = wsr.sub("parallel")
-    networks = wsr.sub("models.diffusion_models.networks")
-    torch.manual_seed(0); np.random.seed(rank)
-    net = U(precision=args.train_precision, **CFG_A)
-    networks.init_weights(net, "orthogonal")
-    net = net.to(dev).train()
-    diff = D(net, image_height=128, image_width=256, channels=1, conditional=True).to(dev)
-    diff.set_new_noise_schedule(LINEAR_1000, dev)
+    np.random.seed(rank)
+    net, diff = _resdiff(ctx, args.train_precision)
+    net.train()
     diff.set_loss(dev)
     plan = net.train_plan(B, dev)
     opt = glue.FusedAdam(list(diff.parameters()), lr=1e-4)
@@ -459,45 +476,48 @@ def run_train(args):
     hr = sr + 0.3 * torch.randn(sr.shape, generator=g).to(dev)
     numel = hr.numel() * world
 
-    def step():
+    def step(reduce=True):
         opt.zero_grad()
         loss = diff.p_losses({"HR": hr, "SR": sr})
         (loss.sum() / numel).backward()
         if reducer is not None:
-            reducer.finish()
+            if reduce:
+                reducer.finish()
         opt.step()
         return loss
 
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local)
+    def timed(n, reduce=True):
+        if reducer is not None:
+            plan.on_ready = reducer._on_ready if reduce else None
+        for _ in range(warmup):
+            step(reduce)
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = nat.launches
+        e0.record()
+        for _ in range(n):
+            loss = step(reduce)
+        e1.record()
+        ctx.barrier()
+        (ms,) = ctx.max_over_ranks(e0.elapsed_time(e1) / n)
+        return ms, nat.launches - l0, loss
+
+    sampler = ClockSampler(ctx.local)
     sampler.start()
-    l0 = nat.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss = step()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
+    ms, launches, loss = timed(steps)
     clocks = sampler.stop()
-    launches = nat.launches - l0
-    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    ms_noar = None
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms[0])
-    if args.profile_ops and rank == 0:
+        ms_noar, _, _ = timed(steps, reduce=False)
+        plan.on_ready = reducer._on_ready
+    if profile and rank == 0:
         plan.eng.prof = []
         step()
         summ = plan.eng.prof_summary()
         plan.eng.prof = None
         tot = sum(v[1] for v in summ.values())
         print("# per-op breakdown of one training step (B=%d, %s): name launches ms TFLOP/s" % (B, args.train_precision), file=sys.stderr)
-        for name, (n, t, fl, nb) in sorted(summ.items(), key=lambda kv: -kv[1][1]):
+        for name, (n, t, fl, nb, xf) in sorted(summ.items(), key=lambda kv: -kv[1][1]):
             print("#   %-22s %4d %9.3f %9.1f" % (name, n, t, fl / (t * 1e-3) / 1e12 if t > 0 else 0), file=sys.stderr)
         print("#   total of timed kernels %.3f ms (wall per step %.3f ms)" % (tot, ms), file=sys.stderr)
         # per-shape detail: the recorded launch lists carry no shape tags, so this one step is issued call by call
@@ -508,25 +528,178 @@ def run_train(args):
         plan.eng.prof, plan.eng.prof_detail = None, False
         plan.replay_enabled = True
         print("# per-shape breakdown of the tensor-core launches of one training step: name launches ms TFLOP/s", file=sys.stderr)
-        for name, (n, t, fl, nb) in sorted(detail.items(), key=lambda kv: -kv[1][1])[:90]:
-            if name.startswith(("wgrad_tc", "conv_tc", "gemm_tc", "conv_taps")):
+        for name, (n, t, fl, nb, xf) in sorted(detail.items(), key=lambda kv: -kv[1][1])[:90]:
+            if name.startswith(("wgrad_tc", "conv_tc", "gemm_tc", "conv_taps", "attn")):
                 print("#   %-42s %3d %8.3f %8.1f" % (name, n, t, fl / (t * 1e-3) / 1e12 if t > 0 else 0), file=sys.stderr)
             elif name.startswith("gn_bwd"):
                 print("#   %-42s %3d %8.3f %8.1f GB/s" % (name, n, t, nb / (t * 1e-3) / 1e9 if t > 0 else 0), file=sys.stderr)
+    peaks, peak_src = _peaks()
+    tfl = 3 * FLOPS_PER_SAMPLE_STEP * B / (ms * 1e-3) / 1e12
+    return {"workload": "configs[2]: ResDiff Cfg-A training step (q_sample + fwd + bwd + bucketed all-reduce + Adam), 128x256, dropout 0.2",
+            "batch_per_gpu": B, "global_batch": B * world, "ms_per_step": ms, "value": B * world / (ms * 1e-3), "unit": "samples/s",
+            "steps": steps, "dtype": args.train_precision, "gpu_launches": launches, "loss": float(loss), "clocks": clocks,
+            "ms_per_step_without_allreduce": ms_noar, "allreduce_exposed_ms": None if ms_noar is None else max(0.0, ms - ms_noar),
+            "allreduce_bytes": plan.gflat.numel() * 4 if world > 1 else 0,
+            "parallelism": "data-parallel x%d, bucketed NCCL gradient all-reduce overlapped with backward" % world,
+            "tflops": tfl, "frac_of_burst": tfl / peaks["bf16_tflops"],
+            "note": "3 x forward algorithmic FLOPs (SURVEY 8d) / step time, per GPU; peak " + peak_src}
+
+
+def measure_c4(ctx, args):
+    """configs[3]: SRDiff UNet + RRDB-17 encoder (random init), B = 32: encoder once per batch + the reverse loop (graph replays)."""
+    import wsr
+    torch, dev = ctx.torch, ctx.dev
+    U = wsr.sub("models.diffusion_models.srdiff.unet").UNet
+    D = wsr.sub("models.diffusion_models.srdiff.srdiff_diffusion").SRDiffDiffusion
+    networks = wsr.sub("models.diffusion_models.networks")
+    torch.manual_seed(0)
+    cfg = dict(CFG_A)
+    cfg["in_channel"] = 1
+    net = U(precision="bf16", **cfg)
+    networks.init_weights(net, "orthogonal")
+    diff = D(net.to(dev).eval(), image_height=128, image_width=256, channels=1, conditional=True).to(dev)
+    diff.init_rrdb_encoder(None, lock_weights=True)
+    diff.rrdb_encoder.to(dev)
+    diff.set_new_noise_schedule(LINEAR_1000, dev)
+    B = 32
+    lr, sr = _synthetic_sr(ctx, B, pinned=False)
+    lr, sr = lr.to(dev), sr.to(dev)
+    plan = net.plan(B, dev)
+
+    def set_condition():
+        plan.set_condition(diff._condition(lr))          # RRDB-17 encoder forward + cond_proj: once per batch
+
+    r = _time_loop(ctx, diff, plan, set_condition, tuple(sr.shape), args.steps, args.warmup)
+    ms, pre = r["ms_per_step"], r["pre_ms"]
+    fl = B * 192.24e9 / (ms * 1e-3) / 1e12
+    return {"workload": "configs[3]: SRDiff UNet + RRDB-17 encoder (once per batch), 128x256, 1000-step loop, bf16", "batch_per_gpu": B,
+            "ms_per_step": ms, "encoder_and_precompute_ms_per_batch": pre, "value": B / (T_FULL * ms * 1e-3 + pre * 1e-3), "unit": "samples/s",
+            "tflops": fl, "flops_note": "192.24 GF per sample-step as the reference executes it (SURVEY 8d)", "steps": r["K"]}
+
+
+def measure_c5(ctx, args):
+    """configs[4]: 3 variables, inner 128, 16x32 -> 128x256 (8x), B = 8."""
+    torch, dev = ctx.torch, ctx.dev
+    net, diff = _resdiff(ctx, "bf16", image_channels=3, in_channel=15, out_channel=3, inner_channel=128)
+    B = 8
+    _, sr = _synthetic_sr(ctx, B, c=3, lr_hw=(16, 32), scale=8, pinned=False)
+    sr = sr.to(dev)
+    plan = net.plan(B, dev)
+    r = _time_loop(ctx, diff, plan, lambda: plan.set_condition(sr), tuple(sr.shape), args.steps, args.warmup)
+    ms, pre = r["ms_per_step"], r["pre_ms"]
+    fl = B * 781.32e9 / (ms * 1e-3) / 1e12
+    peaks, _ = _peaks()
+    return {"workload": "configs[4]: ResDiff, 3 variables (t2m, z500, t850), inner 128, 16x32 -> 128x256, 1000-step loop, bf16", "batch_per_gpu": B,
+            "ms_per_step": ms, "precompute_ms_per_batch": pre, "value": B / (T_FULL * ms * 1e-3 + pre * 1e-3), "unit": "samples/s",
+            "tflops": fl, "frac_of_burst": fl / peaks["bf16_tflops"], "flops_note": "781.32 GF per sample-step (SURVEY 8d)", "steps": r["K"]}
+
+
+def _free(ctx):
+    import gc
+    gc.collect()
+    ctx.torch.cuda.empty_cache()
+
+
+def run_ours(args):
+    ctx = _Ctx()
+    torch = ctx.torch
+    world, rank = ctx.world, ctx.rank
+    # ---- headline: configs[1] = batch 64 IN TOTAL, sharded over the N GPUs (SURVEY 8d C2: 64 / 32 / 16 / 8 per GPU) -> strong scaling
+    total = args.batch
+    B_strong = max(1, total // world)
+    net, diff = _resdiff(ctx)
+    main = measure_sampling(ctx, net, diff, B_strong if args.scaling == "strong" else total, args, full=True)
+    # ---- the weak-scaling companion (64 samples PER GPU): identical to the headline at N = 1
+    weak = None
+    if world > 1 and args.scaling == "strong" and not args.no_extras:
+        net._plans.clear(); _free(ctx)
+        w = measure_sampling(ctx, net, diff, total, args, full=False)
+        weak = {k: w[k] for k in ("batch_per_gpu", "global_batch", "ms_per_step", "value", "unit", "steps")}
+        weak["scaling"] = "weak"
+    elif args.scaling == "strong":
+        weak = {k: main[k] for k in ("batch_per_gpu", "global_batch", "ms_per_step", "value", "unit", "steps")}
+        weak["scaling"] = "weak"
+        weak["note"] = "N = 1: the weak and the strong configuration coincide"
+    net._plans.clear()
+    del net, diff
+    _free(ctx)
+
+    extras = {}
+    if not args.no_extras:
+        # ---- configs[2]: the training step (NCCL all-reduce path at N > 1); every rank takes part
+        try:
+            extras["train"] = measure_train(ctx, args, steps=max(5, args.steps // 2), warmup=3)
+        except Exception as e:                               # a secondary record must never take the headline down
+            extras["train"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        _free(ctx)
+        if world == 1:
+            for key, fn in (("c4_srdiff_rrdb17_b32", measure_c4), ("c5_3var_inner128_b8", measure_c5)):
+                try:
+                    extras[key] = fn(ctx, args)
+                except Exception as e:
+                    extras[key] = {"error": "%s: %s" % (type(e).__name__, e)}
+                _free(ctx)
+
+    # ---- CPU baseline + the eager-PyTorch-on-this-GPU baseline (rank 0, N=1 only; after every timed region of ours) -----------
+    cpu = eager = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        times, cores = cpu_reference_steps(args.cpu_steps, 1)
+        mean = sum(times) / len(times)
+        cpu = {"value": 1.0 / (T_FULL * mean), "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": "B=1, %d reverse steps at 128x256 of the oracle port (fp32 torch-CPU), %.2f s/step; the port computes attention "
+                         "without the reference's .contiguous() copies of the (B,N,N) matrices (39%% of the reference's CPU step in the survey), "
+                         "so this baseline is FASTER than the reference's own modules would be" % (len(times), mean)}
+        if not args.no_extras:
+            try:
+                rb = 16
+                tms = gpu_eager_reference_steps(3, 2, rb, True)
+                em = sum(tms) / len(tms)
+                eager = {"value": rb / (T_FULL * em), "unit": "samples/s", "ms_per_step": em * 1e3, "batch": rb, "dtype": "bf16 autocast",
+                         "what": "BASELINE.md section 4: the reference's algorithm (oracle port, op by op) run by eager PyTorch (cuDNN / cuBLAS) on "
+                                 "this same B200 -- the 'existing implementation' on this hardware; 3 timed reverse steps",
+                         "speedup_of_ours": main["value"] / (rb / (T_FULL * em))}
+            except Exception as e:
+                eager = {"error": "%s: %s" % (type(e).__name__, e)}
+
     if rank == 0:
+        B = main["batch_per_gpu"]
+        line = {
+            "metric": "128x256 t2m SR samples/sec (1000-step loop)", "value": main["value"], "unit": "samples/s", "n_gpus": world,
+            "steps": main["steps"], "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_text(B * world), "global_batch": B * world, "batch_per_gpu": B, "T": T_FULL,
+                       "step": "one reverse step over the local batch (CUDA-graph replay)", "precompute_ms_per_batch": main["precompute_ms_per_batch"],
+                       "l2": "per-step activations (%.1f GB at this batch) >> 126 MB L2, no flush needed" % (0.47 * B),
+                       "parallelism": "batch-sharded x%d, no collective in the loop" % world},
+            "clocks": main["clocks"], "e2e": main.get("e2e"), "gpu_launches": main["launches_per_step"] * main["steps"],
+            "launches_per_step": main["launches_per_step"], "roofline": main["roofline"], "cpu_baseline": cpu,
+            "tc_launches_per_step": main.get("tc_launches_per_step"), "simt_launches_total": main.get("simt_launches_total"),
+            "weak": weak, "train": extras.get("train"),
+            "configs": {k: v for k, v in extras.items() if k != "train"} or None,
+            "eager_gpu_baseline": eager,
+        }
+        _emit(json.dumps(line))
+    ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# secondary workload: configs[2], the training step (not the headline metric; `--workload train`)
+# ----------------------------------------------------------------------------------------------------------------------
+def run_train(args):
+    ctx = _Ctx()
+    rec = measure_train(ctx, args, steps=args.steps, warmup=args.warmup, profile=args.profile_ops)
+    if ctx.rank == 0:
         peaks, peak_src = _peaks()
-        tfl = 3 * FLOPS_PER_SAMPLE_STEP * B / (ms * 1e-3) / 1e12
         _emit(json.dumps({
-            "metric": "ResDiff training step samples/sec (fwd+bwd+allreduce+Adam)", "value": B * world / (ms * 1e-3), "unit": "samples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": args.train_precision, "data": "synthetic",
-            "config": {"workload": "configs[2]: ResDiff Cfg-A training step, 128x256, dropout 0.2, batch %d per GPU" % B,
-                       "global_batch": B * world, "parallelism": "data-parallel x%d, bucketed gradient all-reduce overlapped with backward" % world},
-            "clocks": clocks, "gpu_launches": launches, "loss": float(loss),
-            "roofline": {"bound": "tensor", "achieved": tfl, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tfl / peaks["bf16_tflops"],
-                         "note": "3 x forward algorithmic FLOPs (SURVEY 8d) / step time, per GPU", "peak_source": peak_src}}))
-    if world > 1:
-        dist.destroy_process_group()
+            "metric": "ResDiff training step samples/sec (fwd+bwd+allreduce+Adam)", "value": rec["value"], "unit": "samples/s",
+            "n_gpus": ctx.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.train_precision, "data": "synthetic",
+            "config": {"workload": rec["workload"], "global_batch": rec["global_batch"], "parallelism": rec["parallelism"]},
+            "clocks": rec["clocks"], "gpu_launches": rec["gpu_launches"], "loss": rec["loss"],
+            "allreduce_exposed_ms": rec["allreduce_exposed_ms"], "ms_per_step_without_allreduce": rec["ms_per_step_without_allreduce"],
+            "roofline": {"bound": "tensor", "achieved": rec["tflops"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": rec["frac_of_burst"],
+                         "note": rec["note"], "peak_source": peak_src}}))
+    ctx.close()
 
 
 def main():
@@ -539,8 +712,9 @@ def main():
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="reference arm: cpu (the contract) or the optional eager-PyTorch-on-GPU arm")
     ap.add_argument("--ref-batch", type=int, default=8)
     ap.add_argument("--ref-autocast", action="store_true")
-    ap.add_argument("--batch", type=int, default=64, help="batch per GPU (weak) or total (strong)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--batch", type=int, default=64, help="TOTAL batch sharded over the GPUs (strong, the default = configs[1]) or batch per GPU (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
+    ap.add_argument("--no-extras", action="store_true", help="headline record only: skip the weak / train / configs[3,4] / eager-GPU sub-records")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-budget", type=float, default=60.0, help="seconds allowed for the end-to-end public-API call")

@@ -89,15 +89,38 @@ class FusedAdam(torch.optim.Optimizer):
         self._flat = None
 
     def attach_flat(self, plan):
-        """Use the train plan's flat parameter / gradient buffers: one kernel launch per step."""
+        """Use the train plan's flat parameter / gradient buffers: one kernel launch per step.  Existing per-parameter state
+        (a loaded checkpoint, or steps already taken one by one) is COPIED into the flat moment buffers, so attaching before or
+        after ``load_state_dict`` keeps the optimizer state."""
         pflat = plan.flatten_parameters()
-        self._flat = dict(plan=plan, p=pflat, m=torch.zeros_like(pflat), v=torch.zeros_like(pflat), step=0)
+        m, v = torch.zeros_like(pflat), torch.zeros_like(pflat)
+        step = 0
+        for p in plan.param_order:
+            st = self.state.get(p)
+            if st:
+                off = plan._goff[id(p)]
+                m[off:off + p.numel()].copy_(st["exp_avg"].reshape(-1))
+                v[off:off + p.numel()].copy_(st["exp_avg_sq"].reshape(-1))
+                step = max(step, int(float(st["step"])))
+        self._flat = dict(plan=plan, p=pflat, m=m, v=v, step=step)
+        step_t = torch.tensor(float(step))
         for p in plan.param_order:
             off = plan._goff[id(p)]
             st = self.state[p]
-            st["step"] = torch.tensor(0.0)
-            st["exp_avg"] = self._flat["m"][off:off + p.numel()].view(p.shape)
-            st["exp_avg_sq"] = self._flat["v"][off:off + p.numel()].view(p.shape)
+            st["step"] = step_t
+            st["exp_avg"] = m[off:off + p.numel()].view(p.shape)
+            st["exp_avg_sq"] = v[off:off + p.numel()].view(p.shape)
+
+    def load_state_dict(self, state_dict):
+        """torch.optim.Optimizer.load_state_dict replaces the state tensors: the per-parameter ``step`` counters are moved back to
+        the host (a CUDA ``step`` would cost one device->host read per parameter per step in ``_step_each``), and an attached
+        flat plan is re-synchronised with the loaded moments instead of silently keeping its zeros."""
+        super().load_state_dict(state_dict)
+        for st in self.state.values():
+            if torch.is_tensor(st.get("step")) and st["step"].is_cuda:
+                st["step"] = st["step"].cpu()
+        if self._flat is not None:
+            self.attach_flat(self._flat["plan"])
 
     def _flat_ok(self):
         f = self._flat

@@ -104,3 +104,26 @@ def batches_from_opt(opt, phase, n_batches=None, shard=None):
         return file_batches(root, bs)
     n = n_batches if n_batches is not None else (1 if phase == "val" else opt["train"]["n_iter"])
     return synthetic_batches(n, bs, m["image_channels"], m["image_height"], m["image_width"])
+
+
+def epoch_batches(opt, remaining, shard=None):
+    """ONE epoch of training batches, at most ``remaining`` of them (reference train.py:57-64: ``for train_data in train_loader``
+    inside ``while curr_iter <= n_iter``).  Store: one pass over the shuffled loader; file: one pass over the file; synthetic
+    fields have no epoch structure, so all remaining batches form one epoch."""
+    d = opt["data"]
+    m = opt["model"]["diffusion"]
+    root = str(d.get("dataroot", ""))
+    dh = store_handler(opt, shard=shard)
+
+    def limited(it):
+        for i, item in enumerate(it):
+            if i >= remaining:
+                return
+            yield item
+    if dh is not None:
+        return limited(dh.train_loader)
+    if root.endswith((".npz", ".pt")):
+        return limited(file_batches(root, d["batch_size"]))
+    # the stream continues where a resumed run left off: the generator is advanced by seeding with the served count
+    seed = 1234 + int(opt["train"]["n_iter"]) - int(remaining)
+    return synthetic_batches(remaining, d["batch_size"], m["image_channels"], m["image_height"], m["image_width"], seed=seed)

@@ -107,8 +107,9 @@ class Engine:
         self.no_fused_attention = False
 
     # ---- plumbing -------------------------------------------------------------------------------------------------
-    def call(self, name, *args, flops=0, nbytes=0, tag=None):
-        """nat.call with optional per-launch CUDA-event timing (bench.py roofline pass)."""
+    def call(self, name, *args, flops=0, nbytes=0, tag=None, xflops=None):
+        """nat.call with optional per-launch CUDA-event timing (bench.py roofline pass).  flops = ALGORITHMIC FLOPs (as the
+        reference executes the op); xflops = FLOPs the kernel actually EXECUTES when they differ (phase-merged upsample taps)."""
         if self.prof is None:
             rc = nat.call(name, *args)
             if self.rec is not None:
@@ -119,7 +120,7 @@ class Engine:
         s.record(torch.cuda.current_stream(self.device))
         rc = nat.call(name, *args)
         t.record(torch.cuda.current_stream(self.device))
-        self.prof.append((tag or name, flops, nbytes, s, t))
+        self.prof.append((tag or name, flops, nbytes, s, t, flops if xflops is None else xflops))
         return rc
 
     def replay(self, entries):
@@ -143,12 +144,12 @@ class Engine:
         nat.launches += len(entries)
 
     def prof_summary(self):
-        """name -> [launches, ms, flops, bytes] from the recorded events (synchronises)."""
+        """name -> [launches, ms, algorithmic flops, bytes, executed flops] from the recorded events (synchronises)."""
         torch.cuda.synchronize(self.device)
         out = {}
-        for name, fl, nb, s, t in self.prof:
-            r = out.setdefault(name, [0, 0.0, 0, 0])
-            r[0] += 1; r[1] += s.elapsed_time(t); r[2] += fl; r[3] += nb
+        for name, fl, nb, s, t, xf in self.prof:
+            r = out.setdefault(name, [0, 0.0, 0, 0, 0])
+            r[0] += 1; r[1] += s.elapsed_time(t); r[2] += fl; r[3] += nb; r[4] += xf
         return out
 
     @property
@@ -340,6 +341,8 @@ class Engine:
         up = 2 if upsample else 1
         opix = x.N * (x.H * up // stride) * (x.W * up // stride)
         flops = 2 * opix * pc.Cout * (pc.k * pc.k * pc.Cin + (x2.C if x2 is not None else 0))
+        # nearest-x2 + 3x3 with phase-merged weights: 4 taps per output pixel are executed instead of 9 (SURVEY 8d asks for both)
+        xflops = 2 * opix * pc.Cout * 4 * pc.Cin if (upsample and pc.merged_up) else flops
         if taps is not None:
             opix = x.N * taps.GH * taps.GW
             flops = 2 * opix * pc.Cout * taps.ntaps * pc.Cin
@@ -361,7 +364,7 @@ class Engine:
             return y
         if not force_simt and self._tc_conv_ok(x, pc, x2, y, b, rowvec or 0, rowvec_ld):
             self.n_tc += 1
-            self.call("wsr_conv_tc", C.byref(d), self.stream, flops=flops, nbytes=nbytes,
+            self.call("wsr_conv_tc", C.byref(d), self.stream, flops=flops, nbytes=nbytes, xflops=xflops,
                       tag="conv_tc" if not self.prof_detail else "conv_tc %4d->%4d k%d s%d%s %dx%d" % (
                           pc.Cin_pad + (x2.C if x2 is not None else 0), pc.Cout, pc.k, stride, "u" if upsample else " ", x.H, x.W))
         else:

@@ -20,6 +20,21 @@ _TABLE_ORDER = ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "pos
                 "posterior_mean_coef2", "posterior_log_variance_clipped")
 
 
+def rank_stream_seed(seed, rank=None):
+    """seed -> a per-rank Philox key: rank 0 (and single-process runs) keep ``seed``; rank r > 0 gets splitmix64(seed + r * golden),
+    so shards of one batch hold independent noise realisations while a single-GPU run with the same seed is unchanged."""
+    if rank is None:
+        import torch.distributed as dist
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    if rank == 0:
+        return int(seed) & ((1 << 62) - 1)
+    m = (1 << 64) - 1
+    z = (int(seed) + int(rank) * 0x9E3779B97F4A7C15) & m
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+    return (z ^ (z >> 31)) & ((1 << 62) - 1)
+
+
 class GaussianDiffusion(nn.Module):
     def __init__(self, denoise_fn, channels=1, loss_type='l1', conditional=True, schedule_opt=None, image_height=128,
                  image_width=256, pretrained_model_path=None, lock_weights=True):
@@ -93,9 +108,11 @@ class GaussianDiffusion(nn.Module):
         plan.set_condition(condition_x)
 
     def _next_seed(self):
-        if self.sample_seed is not None:
-            return int(self.sample_seed)
-        return int(torch.randint(0, 2 ** 62, (1,)).item())
+        """Philox seed of the next loop.  Under ``torch.distributed`` (batch-sharded sampling, parallel.py) every rank must draw
+        DIFFERENT noise for its shard: the Philox counter is the local element index, and torch's default CPU generator starts
+        from the same state in every process, so the rank is folded into the key (``rank_stream_seed``)."""
+        base = int(self.sample_seed) if self.sample_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+        return rank_stream_seed(base)
 
     @torch.no_grad()
     def p_sample(self, x, t, clip_denoised=True, condition_x=None):
@@ -202,7 +219,8 @@ class ReverseLoop:
         self.tab, levels = diffusion._tables_dev()
         plan.set_level_table(levels)
         self.x = torch.empty(shape, device=dev, dtype=torch.float32)
-        self.seed = diffusion._next_seed() if seed is None else int(seed)
+        # an explicit seed is still made rank-distinct: sharded ranks pass the same value (bench.py, sample.py)
+        self.seed = diffusion._next_seed() if seed is None else rank_stream_seed(int(seed))
         if noise_chain is not None:
             self.z = noise_chain.to(device=dev, dtype=torch.float32).contiguous()
             assert self.z.shape[0] == T + 1 and tuple(self.z.shape[1:]) == tuple(shape)

@@ -55,8 +55,9 @@ class DDPM(BaseModel):
         SUM-all-reduced in buckets while the backward pass is still running (parallel.FlatGradReducer)."""
         import torch.distributed as dist
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        self.optG.zero_grad()
         b, c, h, w = self.data['HR'].shape
+        self._attach_flat(b)
+        self.optG.zero_grad()
         reducer = self._grad_reducer(b) if world > 1 else None
         l_pix = self.netG(self.data)
         l_pix = l_pix.sum() / int(b * c * h * w * world)
@@ -86,6 +87,18 @@ class DDPM(BaseModel):
         for p in rest:
             p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
             off += p.numel()
+
+    def _attach_flat(self, batch):
+        """The denoiser's parameters are flattened into the train plan's single buffer on the first step (after load_network), so
+        that the optimizer update is ONE ``wsr_adam_step`` launch instead of one per parameter; a loaded optimizer state is
+        carried over (FusedAdam.attach_flat)."""
+        if getattr(self, "_flat_batch", None) == batch or self.opt['model']['finetune_norm']:
+            return
+        net = self._net().denoise_fn
+        if not hasattr(net, "train_plan"):
+            return
+        self.optG.attach_flat(net.train_plan(batch, self.device))
+        self._flat_batch = batch
 
     def _grad_reducer(self, batch):
         """FlatGradReducer bound to the denoiser's train plan for this local batch size (created once)."""
@@ -159,7 +172,8 @@ class DDPM(BaseModel):
         self._net().load_state_dict(torch.load('{}_gen.pth'.format(load_path), map_location=self.device),
                                     strict=(not self.opt['model']['finetune_norm']))
         if self.opt['phase'] == 'train':
-            o = torch.load('{}_opt.pth'.format(load_path), map_location=self.device)
+            # optimizer state: moments go to the device with load_state_dict; the per-parameter step counters stay on the host
+            o = torch.load('{}_opt.pth'.format(load_path), map_location='cpu')
             self.optG.load_state_dict(o['optimizer'])
             self.begin_step = o['iter']
             self.begin_epoch = o['epoch']

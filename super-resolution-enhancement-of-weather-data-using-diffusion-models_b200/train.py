@@ -45,48 +45,79 @@ def main(argv=None):
     if pm.get("model_path") and not os.path.exists(pm["model_path"]):
         pm["model_path"] = None
     model = create_model(opt, None)
+    if world > 1:
+        # weights were initialised under seed 0 on every rank (identical replicas); from here on each rank must draw its OWN
+        # timestep, noise levels, noise and dropout masks (the reference's single process draws them once for the whole batch)
+        random.seed(rank); np.random.seed(rank); torch.manual_seed(rank); torch.cuda.manual_seed(rank)
     if args.phase == "val":
-        # reference train.py:132-196 (validate): generate_sr per batch, inverse transform, metric accumulators -- here the
-        # accumulators live on the device (training/metrics.py) and the inverse StandardScaling is folded into the same pass
-        # as a per-(sample, variable) scale, so nothing is copied to the host until the final compute
-        model.prepare_to_eval()
-        metrics = wsr.sub("training.metrics")
-        vm = metrics.ValidationMetrics(metrics.create_metric_dict(model.device))
-        vm_k = metrics.ValidationMetrics(metrics.create_metric_dict(model.device))
-        sigma_k = float(opt["data"].get("sigma_kelvin", 21.26))          # WeatherBench t2m std (synthetic data has no fitted transform)
-        handler = data.store_handler(opt)                                # the reference's on-disk store, when dataroot is one
-        for batch, months in data.batches_from_opt(opt, "val"):
-            model.feed_data((batch, months))
-            model.generate_sr(False)
-            sr, hr = model.SR, model.data["HR"]
-            vm.update(sr, hr)
-            if handler is not None:
-                # physical units = fitted std of each sample's month and variable (train.py:96-99 inverse_transform, folded in)
-                _, std = handler.get_data_transformer().batch_statistics("hr", months)
-                vm_k.update(sr, hr, scale=std.reshape(-1))
-            else:
-                vm_k.update(sr, hr, scale=torch.full((sr.shape[0] * sr.shape[1],), sigma_k))
-        vm.compute_metrics(); vm_k.compute_metrics()
-        log.info("validation (standardised units)%s", vm.metrics2str())
-        if handler is not None:
-            log.info("validation (physical units, fitted statistics)%s", vm_k.metrics2str())
-        else:
-            log.info("validation (x sigma = %.2f K)%s", sigma_k, vm_k.metrics2str())
-        return vm.metrics2dict(), vm_k.metrics2dict()
-    it = 0
+        return validate(model, opt, data, log)
+    # reference train.py:55-123: resume from the loaded iteration / epoch, stop at n_iter, validate every val_freq iterations,
+    # checkpoints named by the REAL epoch and iteration
+    curr_iter, curr_epoch = int(model.get_loaded_iter() or 0), int(model.get_loaded_epoch() or 0)
+    n_iter = int(opt["train"]["n_iter"])
+    val_freq = int(opt["train"].get("val_freq") or 0)
+    full_val_freq = int(opt["train"].get("full_val_freq") or 0)
     par = wsr.sub("parallel")
     from_store = data.is_store(str(opt["data"].get("dataroot", "")))
     shard = (rank, world) if (world > 1 and from_store) else None        # the store loader reads only this rank's slice
-    for batch, months in data.batches_from_opt(opt, "train", shard=shard):
-        it += 1
-        if world > 1 and shard is None:
-            batch = par.shard_batch(batch, rank, world)
+    if curr_iter:
+        log.info("resuming at iteration %d, epoch %d", curr_iter, curr_epoch)
+    while curr_iter < n_iter:
+        curr_epoch += 1
+        served = 0
+        for batch, months in data.epoch_batches(opt, n_iter - curr_iter, shard=shard):
+            curr_iter += 1
+            served += 1
+            if world > 1 and shard is None:
+                batch = par.shard_batch(batch, rank, world)
+            model.feed_data((batch, months))
+            model.optimize_parameters()
+            if curr_iter % opt["train"]["print_freq"] == 0:
+                log.info("epoch %d  iter %d  l_pix %.6f", curr_epoch, curr_iter, model.get_current_log()["l_pix"])
+            if val_freq and curr_iter % val_freq == 0:
+                # train.py:79-117: the first validation batch only, the whole loader every full_val_freq iterations
+                model.prepare_to_eval()
+                full = bool(full_val_freq) and curr_iter % full_val_freq == 0
+                validate(model, opt, data, log, max_batches=None if full else 1)
+                model.prepare_to_train()
+            if curr_iter % opt["train"]["save_checkpoint_freq"] == 0 and rank == 0:
+                model.save_network(curr_epoch, curr_iter)
+        if served == 0:
+            break
+    log.info("End of training.")
+    return curr_iter, curr_epoch
+
+
+def validate(model, opt, data, log, max_batches=None):
+    """reference train.py:132-196 (validate): generate_sr per batch, inverse transform, metric accumulators -- here the
+    accumulators live on the device (training/metrics.py) and the inverse StandardScaling is folded into the same pass
+    as a per-(sample, variable) scale, so nothing is copied to the host until the final compute."""
+    model.prepare_to_eval()
+    metrics = wsr.sub("training.metrics")
+    vm = metrics.ValidationMetrics(metrics.create_metric_dict(model.device))
+    vm_k = metrics.ValidationMetrics(metrics.create_metric_dict(model.device))
+    sigma_k = float(opt["data"].get("sigma_kelvin", 21.26))          # WeatherBench t2m std (synthetic data has no fitted transform)
+    handler = data.store_handler(opt)                                # the reference's on-disk store, when dataroot is one
+    for i, (batch, months) in enumerate(data.batches_from_opt(opt, "val")):
+        if max_batches is not None and i >= max_batches:
+            break
         model.feed_data((batch, months))
-        model.optimize_parameters()
-        if it % opt["train"]["print_freq"] == 0:
-            log.info("iter %d  l_pix %.6f", it, model.get_current_log()["l_pix"])
-        if it % opt["train"]["save_checkpoint_freq"] == 0 and rank == 0:
-            model.save_network(0, it)
+        model.generate_sr(False)
+        sr, hr = model.SR, model.data["HR"]
+        vm.update(sr, hr)
+        if handler is not None:
+            # physical units = fitted std of each sample's month and variable (train.py:96-99 inverse_transform, folded in)
+            _, std = handler.get_data_transformer().batch_statistics("hr", months)
+            vm_k.update(sr, hr, scale=std.reshape(-1))
+        else:
+            vm_k.update(sr, hr, scale=torch.full((sr.shape[0] * sr.shape[1],), sigma_k))
+    vm.compute_metrics(); vm_k.compute_metrics()
+    log.info("validation (standardised units)%s", vm.metrics2str())
+    if handler is not None:
+        log.info("validation (physical units, fitted statistics)%s", vm_k.metrics2str())
+    else:
+        log.info("validation (x sigma = %.2f K)%s", sigma_k, vm_k.metrics2str())
+    return vm.metrics2dict(), vm_k.metrics2dict()
 
 
 if __name__ == "__main__":

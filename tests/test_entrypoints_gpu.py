@@ -94,3 +94,46 @@ def test_entry_points_on_the_on_disk_store(tmp_path, caplog):
         assert 150.0 < phys.mean() < 400.0 and abs(sr.mean()) < 20.0
     finally:
         os.chdir(cwd)
+
+
+def test_resume_continues_iterations_epochs_and_adam_state(tmp_path, caplog):
+    """a resumed run starts at the loaded iteration / epoch (reference train.py:55-64 + model.get_loaded_iter/epoch),
+    stops at n_iter, names its checkpoints by the real counters, keeps the Adam moments and step count, and uses the one-launch
+    flat Adam (attach_flat) in the train.py path."""
+    cfgmod = wsr.sub("configs.config")
+    cfg = _small_config(tmp_path, "sr3", 2)
+    opt = json.loads(open(cfg).read())
+    opt["train"].update(n_iter=2, save_checkpoint_freq=2, val_freq=2, full_val_freq=1000)
+    open(cfg, "w").write(json.dumps(opt))
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        train = wsr.sub("train")
+        nat = wsr.pkg.native
+        import logging
+        with caplog.at_level(logging.INFO, logger="base"):
+            assert train.main(["-c", cfg, "-p", "train", "-gpu", "0"]) == (2, 1)
+        assert "validation (standardised units)" in caplog.text          # val_freq validation inside the training loop
+        ck = str(tmp_path / "checkpoint")
+        assert sorted(os.listdir(ck)) == ["I2_E1_gen.pth", "I2_E1_opt.pth"]
+        o1 = torch.load(os.path.join(ck, "I2_E1_opt.pth"), map_location="cpu")
+        st1 = o1["optimizer"]["state"]
+        assert all(float(s["step"]) == 2.0 for s in st1.values())
+        assert any(float(s["exp_avg"].abs().sum()) > 0 for s in st1.values())
+        # resume: two more iterations
+        opt["train"].update(n_iter=4)
+        opt["path"]["resume_state"] = os.path.join(ck, "I2_E1")
+        open(cfg, "w").write(json.dumps(opt))
+        l0 = nat.launches
+        assert train.main(["-c", cfg, "-p", "train", "-gpu", "0"]) == (4, 2)
+        assert "I4_E2_gen.pth" in os.listdir(ck) and "I2_E1_gen.pth" in os.listdir(ck)
+        o2 = torch.load(os.path.join(ck, "I4_E2_opt.pth"), map_location="cpu")
+        st2 = o2["optimizer"]["state"]
+        assert all(float(s["step"]) == 4.0 for s in st2.values())
+        # the loaded moments were carried into the flat buffers (not reset to zero): after two more steps with b2 = 0.999 the second
+        # moment still holds (0.999^2 of) the loaded one
+        k = max(st1, key=lambda i: float(st1[i]["exp_avg_sq"].sum()))
+        assert float(st2[k]["exp_avg_sq"].sum()) > 0.99 * float(st1[k]["exp_avg_sq"].sum())
+        del l0, cfgmod
+    finally:
+        os.chdir(cwd)

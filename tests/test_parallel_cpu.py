@@ -68,7 +68,18 @@ def _worker(rank, world, port, q):
         done = red.finish()
         ok_flat = torch.allclose(plan.gflat, torch.arange(1000, dtype=torch.float32) * 3) and \
             done == [(0, 300), (300, 600), (600, 650), (650, 950), (950, 1000)]
-        q.put((rank, bool(ok_sample), bool(ok_grad) and bool(ok_flat), len(bucketer.buckets)))
+        # per-rank Philox streams: same base seed / same torch generator state on every rank, different keys
+        D = wsr.sub("models.diffusion_models.diffusion")
+        gd = D.GaussianDiffusion(denoise_fn=None)
+        torch.manual_seed(0)
+        drawn = gd._next_seed()
+        gd.sample_seed = 11
+        fixed = gd._next_seed()
+        seeds = [None, None]
+        dist.all_gather_object(seeds, (drawn, fixed, D.rank_stream_seed(7)))
+        ok_seed = (seeds[0][0] != seeds[1][0] and seeds[0][1] != seeds[1][1] and seeds[0][2] != seeds[1][2]
+                   and seeds[0][1] == 11 and seeds[0][2] == 7)
+        q.put((rank, bool(ok_sample), bool(ok_grad) and bool(ok_flat) and bool(ok_seed), len(bucketer.buckets)))
     finally:
         dist.destroy_process_group()
 
@@ -93,3 +104,11 @@ def test_world2_gloo_sharded_sampling_and_grad_allreduce():
         assert ok_sample, "rank %d: sharded sampling mismatch" % rank
         assert ok_grad, "rank %d: all-reduced gradients differ from the single-process reference" % rank
         assert nb >= 2
+
+
+def test_rank_stream_seed_is_identity_on_rank0_and_spreads_other_ranks():
+    D = wsr.sub("models.diffusion_models.diffusion")
+    assert D.rank_stream_seed(1234, rank=0) == 1234
+    keys = {D.rank_stream_seed(1234, rank=r) for r in range(64)}
+    assert len(keys) == 64 and all(0 <= k < 2 ** 62 for k in keys)
+    assert D.rank_stream_seed(1234, rank=3) != D.rank_stream_seed(1235, rank=3)
