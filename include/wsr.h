@@ -164,6 +164,15 @@ int wsr_gemm_tc(const WsrGemmDesc* d, void* stream);
 int wsr_attention_tc(const void* q, int q_ld, const void* k, int k_ld, const void* vT, void* o, int o_ld, int B, int Nq,
                      int Nk, int d, float scale, void* stream);
 
+/* The same product for SHORT key sequences and WIDE heads (the low-resolution levels): SelfAttention at 16x32 / 8x16
+ * (nn_modules/resnet.py:81-100: N = 512 / 128, d = 512) and HF_guided_CA levels 2, 3 (resdiff/guided_cross_attention.py:24-44:
+ * N = 512, d = 256; N = 128, d = 512).  The whole 128 x Nk score block sits in tensor memory: exact single-pass softmax, P in
+ * shared memory, O re-uses the score columns.  Same argument meaning as wsr_attention_tc.
+ * Requires Nq % 128 == 0, 64 <= Nk <= 512 with Nk % 64 == 0, 64 <= d <= 512 with d % 64 == 0 (wsr_attention_small_tc_supported). */
+int wsr_attention_small_tc(const void* q, int q_ld, const void* k, int k_ld, const void* vT, void* o, int o_ld, int B, int Nq,
+                           int Nk, int d, float scale, void* stream);
+int wsr_attention_small_tc_supported(int Nq, int Nk, int d);
+
 /* ConvTranspose2d(k=8, s=4, p=2) of srdiff/unet.py:43-45,118.  x NHWC (N,H,W,Cin); w packed [ky*8+kx][Cout][Cin];
  * y NHWC (N,4H,4W,Cout). */
 int wsr_conv_transpose_k8s4(const void* x, int x_dtype, int N, int H, int W, int Cin, int x_ld, const void* w,
@@ -355,6 +364,18 @@ int wsr_lrelu_mask(const void* y, int y_dtype, int y_ld, void* dy, int dy_dtype,
 int wsr_sampler_step(const float* x, const void* eps, int eps_dtype, const float* z, int64_t z_step_stride,
                      uint64_t seed, const float* tables, int T, const int* t_dev, int clip, float* x_out, int64_t n,
                      void* stream);
+/* The UNet head fused with the reverse step (SURVEY 8b `final_conv_sampler_step`): eps_hat = conv3x3(Swish(GroupNorm(x))) --
+ * `final_conv` of resdiff/unet.py:119,177 (nn_modules/resnet.py:19-28 Block) -- followed, in the same kernel, by the update of
+ * wsr_sampler_step on the fp32 NCHW state.  x: RAW (pre-GroupNorm) NHWC bf16 (B,H,W,Cin) with pitch x_ld; stats: the
+ * per-(image, channel) (sum, sumsq) doubles the producing convolution emitted; w: fp32 [9][Cout][Cin]; eps_out (optional): fp32 NCHW
+ * (B,Cout,H,W); x_state (optional): fp32 NCHW, updated in place with the same Philox stream layout / injected-noise addressing as
+ * wsr_sampler_step.  Requires Cin % 64 == 0, Cout <= 4 (wsr_head_sampler_supported). */
+int wsr_final_conv_sampler_step(const void* x, int x_ld, int B, int H, int W, int Cin, const double* stats, int stats_ld,
+                                const float* gamma, const float* beta, int groups, float gn_eps, const float* w,
+                                const float* bias, int Cout, float* eps_out, float* x_state, const float* z,
+                                int64_t z_step_stride, uint64_t seed, const float* tables, int T, const int* t_dev, int clip,
+                                void* stream);
+int wsr_head_sampler_supported(int Cin, int Cout, int groups);
 /* out[b][:] = table[r][:] for b < B, r = *row_index (one row of the per-time-step projection table broadcast to the
  * batch; lets a captured CUDA graph follow the device-side step counter). */
 int wsr_broadcast_row(const float* table, int P, const int* row_index, int B, float* out, void* stream);

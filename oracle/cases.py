@@ -74,6 +74,32 @@ CASES = {
 }
 
 
+# Benchmark-shaped single steps ("parity on what is benchmarked").  The reference's output is too large to commit whole, so the
+# fixture keeps a strided probe of eps_hat plus per-sample norms; inputs are regenerated from their seeds by the tests (head values are
+# stored to detect RNG drift).  `arch` picks the reference class; `scale` the LR -> condition factor.
+PROBE_CASES = {
+    # BASELINE configs[1] at the benchmark batch: 64 samples, Cfg-A, 128x256 (tile modes / column-tile choice depend on the batch)
+    "resdiff_step_full_b64": dict(kind="step_probe", arch="resdiff", cfg=unet_cfg(128, 256), batch=64, seed=15, scale=4),
+    # BASELINE configs[3]: SRDiff UNet conditioned on the RRDB-17 encoder's features, batch 32, 128x256
+    "srdiff_step_full_b32": dict(kind="step_probe", arch="srdiff", cfg=unet_cfg(128, 256, in_channel=1), batch=32, seed=16, scale=4),
+    # BASELINE configs[4]: 3 variables, inner 128, condition = bicubic x8 of a 16x32 field, batch 8
+    "resdiff_step_c5_full_b8": dict(kind="step_probe", arch="resdiff", cfg=unet_cfg(128, 256, inner=128, c_img=3), batch=8, seed=17, scale=8),
+}
+CASES.update(PROBE_CASES)
+
+
+def probe_levels(batch):
+    """Continuous noise levels sqrt(abar) spread over (0, 1): sample b gets 0.05 + 0.9 * ((7 b) mod batch) / batch."""
+    return [0.05 + 0.9 * ((7 * b) % batch) / batch for b in range(batch)]
+
+
+def probe_summary(eps):
+    """What the fixture keeps of a (B, C, H, W) output: a stride-4 sub-grid, per-sample L2 norms and sums."""
+    e = eps.detach().to(torch.float32)
+    return dict(eps_probe=e[:, :, 1::4, 2::4].contiguous(), eps_norm=e.flatten(1).double().norm(dim=1).float(),
+                eps_sum=e.flatten(1).double().sum(dim=1).float())
+
+
 def grad_summary(named_grads, seed, full_below=4096):
     """Compact, order-independent description of a set of gradients: per tensor its L2 norm, its dot product with a
     seeded random probe and its first 8 elements; tensors with fewer than ``full_below`` elements are kept whole."""

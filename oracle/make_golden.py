@@ -109,8 +109,54 @@ def run_grad_case(ref, name, spec):
     return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()}
 
 
+class _PerSampleHFCA:
+    """Runs the reference's HF_guided_CA.forward (guided_cross_attention.py:24-44) one sample at a time: the module is
+    per-sample independent (GroupNorm, 1x1 convolutions, softmax over that sample's keys), but at level 0 it materialises a
+    (B, 8192, 8192) fp32 matrix several times over -- 17 GB each at the benchmark batch of 64, more than this container holds.
+    The reference's own code runs unmodified on each batch slice."""
+
+    def __enter__(self):
+        import models.diffusion_models.resdiff.guided_cross_attention as m
+        self.cls, self.orig = m.HF_guided_CA, m.HF_guided_CA.forward
+        orig = self.orig
+
+        def forward(mod, input, quary):
+            return torch.cat([orig(mod, input[i:i + 1], quary[i:i + 1]) for i in range(input.shape[0])], 0)
+
+        self.cls.forward = forward
+        return self
+
+    def __exit__(self, *exc):
+        self.cls.forward = self.orig
+
+
+def run_probe_case(ref, name, spec):
+    """One denoiser call at a benchmark shape; keeps a probe of the output (cases.probe_summary)."""
+    from .cases import probe_levels, probe_summary
+    seed, b, cfg, arch = spec["seed"], spec["batch"], spec["cfg"], spec["arch"]
+    c, H, W = cfg["image_channels"], cfg["image_height"], cfg["image_width"]
+    lr, sr, _ = fields(name, b, c, H, W, seed, scale=spec["scale"])
+    x_t = seeded_randn(name + ".xt", sr.shape, seed)
+    level = torch.tensor(probe_levels(b), dtype=torch.float32).view(b, 1)
+    with torch.no_grad():
+        if arch == "srdiff":
+            net = fill_module(_unet(ref, cfg, srdiff=True), seed)
+            rrdb = fill_module(ref.RRDBNet(1, 1, 64, 17, 32).eval(), seed + 1)
+            _, feas = rrdb(lr, True)
+            eps = net((feas, x_t), level)
+        else:
+            net = fill_module(_unet(ref, cfg), seed)
+            with _PerSampleHFCA():
+                eps = net(torch.cat([sr, x_t], 1), level)
+    out = dict(level=level, lr_head=lr[:2, :, :2, :8].clone(), xt_head=x_t[:2, :, :2, :8].clone(), wsum=_checksum(net))
+    out.update(probe_summary(eps))
+    return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()}
+
+
 def run_case(ref, name, spec):
     kind, seed, b = spec["kind"], spec["seed"], spec["batch"]
+    if kind == "step_probe":
+        return run_probe_case(ref, name, spec)
     if kind in ("resdiff_grad", "phydiff_grad", "sr3_grad", "srdiff_grad"):
         return run_grad_case(ref, name, spec)
     out = {}

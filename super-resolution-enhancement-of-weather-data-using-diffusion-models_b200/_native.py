@@ -99,6 +99,8 @@ SIGNATURES = {
     "wsr_gemm_simt": [C.POINTER(GemmDesc), _P],
     "wsr_gemm_tc": [C.POINTER(GemmDesc), _P],
     "wsr_attention_tc": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "wsr_attention_small_tc": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "wsr_attention_small_tc_supported": [_I, _I, _I],
     "wsr_conv_transpose_k8s4": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P],
     "wsr_gn_stats": [_P, _I, _I, _I, _I, _I, _P, _I, _P],
     "wsr_gn_apply": [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _I, _F, _I, _P, _I, _I, _P],
@@ -130,6 +132,8 @@ SIGNATURES = {
     "wsr_relu_mask": [_P, _P, _L, _P],
     "wsr_lrelu_mask": [_P, _I, _I, _P, _I, _I, _L, _I, _F, _P],
     "wsr_sampler_step": [_P, _P, _I, _P, _L, _U64, _P, _I, _P, _I, _P, _L, _P],
+    "wsr_final_conv_sampler_step": [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _I, _F, _P, _P, _I, _P, _P, _P, _L, _U64, _P, _I, _P, _I, _P],
+    "wsr_head_sampler_supported": [_I, _I, _I],
     "wsr_broadcast_row": [_P, _I, _P, _I, _P, _P],
     "wsr_step_counter_add": [_P, _I, _P],
     "wsr_randn": [_P, _L, _U64, _U32, _P],
@@ -155,7 +159,7 @@ SIGNATURES = {
 }
 _RESTYPE = {"wsr_fd_precompute_workspace_bytes": C.c_int64, "wsr_fd_backward_workspace_bytes": C.c_int64}
 # functions whose return value is data, not a status
-_NO_STATUS = {"wsr_version", "wsr_device_is_sm100", "wsr_conv_tc_can_fuse_gn", "wsr_fd_precompute_workspace_bytes", "wsr_fd_backward_workspace_bytes"}
+_NO_STATUS = {"wsr_version", "wsr_device_is_sm100", "wsr_conv_tc_can_fuse_gn", "wsr_attention_small_tc_supported", "wsr_head_sampler_supported", "wsr_fd_precompute_workspace_bytes", "wsr_fd_backward_workspace_bytes"}
 
 _lib = None
 launches = 0          # number of status-returning calls made (bench.py's gpu_launches bookkeeping is done there)

@@ -1,0 +1,241 @@
+// head.cu -- the UNet head and the reverse-step update in ONE kernel (HBM-bound):
+//   eps_hat = conv3x3(Swish(GroupNorm(x)))                  final_conv, resdiff/unet.py:119,177 + nn_modules/resnet.py:19-28
+//   x0 = clamp(c_recip[t] x_t - c_recipm1[t] eps_hat); x_{t-1} = coef1[t] x0 + coef2[t] x_t + sigma_t z      diffusion.py:124-125,139-141,168-169,191-192
+// Round 1 ran this as three launches: gn_apply (read + write of the 64-channel full-resolution tensor), the tcgen05 convolution
+// with Cout padded 1 -> 64 (11 TFLOP/s: 63 of its 64 output columns are zeros) and the sampler step.  A Cout <= 4 convolution is a
+// 9 * Cin-term dot product per pixel, i.e. bandwidth-bound work: here every CTA loads a (4 + 2) x (128 + 2) pixel halo tile of the RAW
+// tensor once, applies GroupNorm + Swish on the way into shared memory (bf16, 16-byte chunks XOR-swizzled by pixel so that
+// neighbouring pixels hit different banks), and each thread accumulates the 9 * Cin products of two pixels in fp32 with the fp32
+// weights broadcast from shared memory; the epilogue is the sampler update, in place on the fp32 NCHW state.  Algorithmic traffic:
+// Cin * 2 bytes per pixel read (+ halo) and 12-16 bytes per pixel-channel for the state update.
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace wsr {
+
+constexpr int kHeadRows = 4, kHeadCols = 128, kHeadThreads = 256;
+constexpr int kHeadMaxCout = 4;
+
+struct HeadParams {
+  const __nv_bfloat16* x; int x_ld;       // raw (pre-GroupNorm) input, NHWC (B, H, W, Cin) bf16
+  int B, H, W, Cin, Cout;
+  const double* stats; int stats_ld; const float* gamma; const float* beta; int groups; float gn_eps;
+  const float* w;                          // fp32 [9][Cout][Cin]
+  const float* bias;                       // [Cout] or null
+  float* eps_out;                          // fp32 NCHW (B, Cout, H, W) or null
+  float* xs;                               // fp32 NCHW state x_t -> x_{t-1} in place, or null (convolution only)
+  const float* z; long long z_stride; unsigned long long seed; const float* tab; int T; const int* t_dev; int clip;
+};
+
+__device__ __forceinline__ void head_randn4(uint64_t seed, uint32_t tag, uint64_t grp, float (&z)[4]) {
+  // identical stream layout to randn4 of elementwise.cu (wsr_sampler_step / wsr_randn): element i = word i & 3 of group i >> 2
+  uint32_t c[4] = {(uint32_t)grp, (uint32_t)(grp >> 32), tag, 0x5752u};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float s = 2.3283064365386963e-10f;
+  float u0 = ((float)c[0] + 0.5f) * s, u1 = ((float)c[1] + 0.5f) * s;
+  float u2 = ((float)c[2] + 0.5f) * s, u3 = ((float)c[3] + 0.5f) * s;
+  float r0 = sqrtf(-2.f * __logf(u0)), r1 = sqrtf(-2.f * __logf(u2));
+  float s0, c0, s1, c1;
+  __sincosf(6.283185307179586f * u1, &s0, &c0);
+  __sincosf(6.283185307179586f * u3, &s1, &c1);
+  z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+}
+
+// shared memory: tile [Cin/64 planes][6 rows][130 cols][64 ch] bf16 | weights fp32 [9][Cout][Cin] | scale[Cin] shift[Cin] | group moments
+template <int COUT>
+__global__ void __launch_bounds__(kHeadThreads) head_sampler_kernel(const HeadParams p) {
+  extern __shared__ __align__(16) uint8_t hsm[];
+  constexpr int TR = kHeadRows + 2, TC = kHeadCols + 2;
+  const int planes = p.Cin >> 6;
+  uint8_t* tile = hsm;
+  float* wsm = (float*)(hsm + (size_t)planes * TR * TC * 128);
+  float* sc = wsm + 9 * COUT * p.Cin;
+  float* sh = sc + p.Cin;
+  float* gm = sh + p.Cin;
+  const int n = blockIdx.y;
+  const int tiles_x = (p.W + kHeadCols - 1) / kHeadCols;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int y0 = ty * kHeadRows, x0 = tx * kHeadCols;
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < 9 * COUT * p.Cin; i += kHeadThreads) wsm[i] = p.w[i];
+  pdl_launch_dependents();
+  pdl_wait();
+  {
+    const int cpg = p.Cin / p.groups;
+    const long long HW = (long long)p.H * p.W;
+    for (int g = tid; g < p.groups; g += kHeadThreads) {
+      double a = 0.0, b = 0.0;
+      for (int j = 0; j < cpg; ++j) { a += p.stats[(long long)n * p.stats_ld + (g * cpg + j) * 2]; b += p.stats[(long long)n * p.stats_ld + (g * cpg + j) * 2 + 1]; }
+      const double inv_cnt = 1.0 / ((double)cpg * (double)HW);
+      const double mean = a * inv_cnt;
+      double var = b * inv_cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      gm[2 * g] = (float)mean;
+      gm[2 * g + 1] = rsqrtf((float)var + p.gn_eps);
+    }
+    __syncthreads();
+    for (int c = tid; c < p.Cin; c += kHeadThreads) {
+      const int g = c / cpg;
+      const float s = p.gamma[c] * gm[2 * g + 1];
+      sc[c] = s;
+      sh[c] = p.beta[c] - gm[2 * g] * s;
+    }
+    __syncthreads();
+  }
+  // ---- halo tile: raw bf16 -> GroupNorm + Swish -> bf16, out-of-image pixels are the convolution's zero padding ----
+  {
+    const int nvec = planes * TR * TC * 8;                 // 16-byte vectors (8 channels)
+    const __nv_bfloat16* xb = p.x + (long long)n * p.H * p.W * p.x_ld;
+    for (int v = tid; v < nvec; v += kHeadThreads) {
+      const int k = v & 7;                                 // 16-byte chunk inside the 64-channel plane
+      int r = v >> 3;
+      const int col = r % TC; r /= TC;
+      const int row = r % TR; const int pl = r / TR;
+      const int gy = y0 + row - 1, gx = x0 + col - 1;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+        const int c0 = pl * 64 + k * 8;
+        const uint4 raw = __ldg((const uint4*)(xb + ((long long)gy * p.W + gx) * p.x_ld + c0));
+        const __nv_bfloat162* h = (const __nv_bfloat162*)&raw;
+        __nv_bfloat162* oh = (__nv_bfloat162*)&o;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __bfloat1622float2(h[q]);
+          const float a0 = swish_fast(fmaf(f.x, sc[c0 + 2 * q], sh[c0 + 2 * q]));
+          const float a1 = swish_fast(fmaf(f.y, sc[c0 + 2 * q + 1], sh[c0 + 2 * q + 1]));
+          oh[q] = __floats2bfloat162_rn(a0, a1);
+        }
+      }
+      *(uint4*)(tile + ((size_t)(pl * TR + row) * TC + col) * 128 + ((k ^ (col & 7)) << 4)) = o;
+    }
+  }
+  __syncthreads();
+  // ---- 9 * Cin products per pixel: thread (r, j) owns pixels (r, j) and (r, j + 64) of the tile ----
+  const int r = tid >> 6, j = tid & 63;
+  float acc[2][COUT];
+#pragma unroll
+  for (int px = 0; px < 2; ++px)
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[px][co] = p.bias ? p.bias[co] : 0.f;
+  for (int pl = 0; pl < planes; ++pl) {
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3, dx = tap - dy * 3;
+      const uint8_t* rowp = tile + ((size_t)(pl * TR + r + dy) * TC) * 128;
+      const int ca = j + dx, cb = j + 64 + dx;
+      const float* wt = wsm + (tap * COUT) * p.Cin + pl * 64;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint4 ua = *(const uint4*)(rowp + (size_t)ca * 128 + ((k ^ (ca & 7)) << 4));
+        const uint4 ub = *(const uint4*)(rowp + (size_t)cb * 128 + ((k ^ (cb & 7)) << 4));
+        float fa[8], fb[8];
+        const uint32_t* wa = (const uint32_t*)&ua;
+        const uint32_t* wb = (const uint32_t*)&ub;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          fa[2 * q] = __uint_as_float(wa[q] << 16); fa[2 * q + 1] = __uint_as_float(wa[q] & 0xffff0000u);
+          fb[2 * q] = __uint_as_float(wb[q] << 16); fb[2 * q + 1] = __uint_as_float(wb[q] & 0xffff0000u);
+        }
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+          const float4 w0 = *(const float4*)(wt + co * p.Cin + k * 8);
+          const float4 w1 = *(const float4*)(wt + co * p.Cin + k * 8 + 4);
+          float a = acc[0][co], b = acc[1][co];
+          a = fmaf(fa[0], w0.x, a); a = fmaf(fa[1], w0.y, a); a = fmaf(fa[2], w0.z, a); a = fmaf(fa[3], w0.w, a);
+          a = fmaf(fa[4], w1.x, a); a = fmaf(fa[5], w1.y, a); a = fmaf(fa[6], w1.z, a); a = fmaf(fa[7], w1.w, a);
+          b = fmaf(fb[0], w0.x, b); b = fmaf(fb[1], w0.y, b); b = fmaf(fb[2], w0.z, b); b = fmaf(fb[3], w0.w, b);
+          b = fmaf(fb[4], w1.x, b); b = fmaf(fb[5], w1.y, b); b = fmaf(fb[6], w1.z, b); b = fmaf(fb[7], w1.w, b);
+          acc[0][co] = a; acc[1][co] = b;
+        }
+      }
+    }
+  }
+  // ---- epilogue: eps_hat (optional) and the reverse-step update of the state, fp32 NCHW ----
+  const int gy = y0 + r;
+  if (gy >= p.H) return;
+  int t = 0;
+  float c_recip = 0.f, c_recipm1 = 0.f, coef1 = 0.f, coef2 = 0.f, sigma = 0.f;
+  const float* zt = nullptr;
+  if (p.xs) {
+    t = *p.t_dev;
+    c_recip = p.tab[t]; c_recipm1 = p.tab[p.T + t]; coef1 = p.tab[2 * p.T + t]; coef2 = p.tab[3 * p.T + t];
+    sigma = t > 0 ? __expf(0.5f * p.tab[4 * p.T + t]) : 0.f;
+    if (p.z) zt = p.z + (long long)(p.T - t) * p.z_stride;
+  }
+#pragma unroll
+  for (int px = 0; px < 2; ++px) {
+    const int gx = x0 + j + 64 * px;
+    if (gx >= p.W) continue;
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+      const long long i = (((long long)n * COUT + co) * p.H + gy) * p.W + gx;
+      const float e = acc[px][co];
+      if (p.eps_out) p.eps_out[i] = e;
+      if (p.xs) {
+        float zz = 0.f;
+        if (t > 0) {
+          if (zt) zz = zt[i];
+          else { float z4[4]; head_randn4(p.seed, (uint32_t)t, (uint64_t)(i >> 2), z4); const int wsel = (int)(i & 3); zz = wsel == 0 ? z4[0] : wsel == 1 ? z4[1] : wsel == 2 ? z4[2] : z4[3]; }
+        }
+        const float xv = p.xs[i];
+        float x0v = c_recip * xv - c_recipm1 * e;
+        if (p.clip) x0v = fminf(1.f, fmaxf(-1.f, x0v));
+        p.xs[i] = coef1 * x0v + coef2 * xv + sigma * zz;
+      }
+    }
+  }
+}
+
+static size_t head_smem_bytes(int Cin, int Cout, int groups) {
+  return (size_t)(Cin / 64) * (kHeadRows + 2) * (kHeadCols + 2) * 128 + (size_t)(9 * Cout * Cin + 2 * Cin + 2 * groups) * 4;
+}
+
+template <int COUT>
+static int launch_head(const HeadParams& p, cudaStream_t st) {
+  const size_t smem = head_smem_bytes(p.Cin, COUT, p.groups);
+  static size_t attr = 0;
+  if (smem > attr) {
+    WSR_CUDA_OK(cudaFuncSetAttribute(head_sampler_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const int tiles = ((p.W + kHeadCols - 1) / kHeadCols) * ((p.H + kHeadRows - 1) / kHeadRows);
+  WSR_CUDA_OK(launch_pdl(head_sampler_kernel<COUT>, dim3(tiles, p.B), dim3(kHeadThreads), smem, st, p));
+  return WSR_OK;
+}
+
+}  // namespace wsr
+
+using namespace wsr;
+
+extern "C" int wsr_head_sampler_supported(int Cin, int Cout, int groups) {
+  if (Cin <= 0 || Cin % 64 != 0 || Cout < 1 || Cout > kHeadMaxCout || groups <= 0 || Cin % groups != 0) return 0;
+  return head_smem_bytes(Cin, Cout, groups) <= 227 * 1024 ? 1 : 0;
+}
+
+extern "C" int wsr_final_conv_sampler_step(const void* x, int x_ld, int B, int H, int W, int Cin, const double* stats, int stats_ld,
+                                           const float* gamma, const float* beta, int groups, float gn_eps, const float* w,
+                                           const float* bias, int Cout, float* eps_out, float* x_state, const float* z,
+                                           int64_t z_step_stride, uint64_t seed, const float* tables, int T, const int* t_dev,
+                                           int clip, void* stream) {
+  WSR_REQUIRE(x && stats && gamma && beta && w, WSR_E_INVALID, "final_conv_sampler_step: null pointer");
+  WSR_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, WSR_E_INVALID, "final_conv_sampler_step: bad shape");
+  WSR_REQUIRE(wsr_head_sampler_supported(Cin, Cout, groups), WSR_E_UNSUPPORTED,
+              "final_conv_sampler_step: needs Cin %% 64 == 0, 1 <= Cout <= 4, Cin %% groups == 0 and the tile in shared memory (Cin=%d Cout=%d)", Cin, Cout);
+  WSR_REQUIRE(x_ld % 8 == 0 && x_ld >= Cin && (((uintptr_t)x) & 15) == 0 && (((uintptr_t)w) & 15) == 0, WSR_E_UNSUPPORTED,
+              "final_conv_sampler_step: pitch / alignment");
+  WSR_REQUIRE(eps_out || x_state, WSR_E_INVALID, "final_conv_sampler_step: no output");
+  WSR_REQUIRE(!x_state || (tables && t_dev && T > 0), WSR_E_INVALID, "final_conv_sampler_step: sampler tables");
+  HeadParams p;
+  p.x = (const __nv_bfloat16*)x; p.x_ld = x_ld; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.stats = stats; p.stats_ld = stats_ld; p.gamma = gamma; p.beta = beta; p.groups = groups; p.gn_eps = gn_eps;
+  p.w = w; p.bias = bias; p.eps_out = eps_out; p.xs = x_state; p.z = z; p.z_stride = z_step_stride; p.seed = seed;
+  p.tab = tables; p.T = T; p.t_dev = t_dev; p.clip = clip;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (Cout) {
+    case 1: return launch_head<1>(p, st);
+    case 2: return launch_head<2>(p, st);
+    case 3: return launch_head<3>(p, st);
+    default: return launch_head<4>(p, st);
+  }
+}

@@ -528,6 +528,15 @@ class Engine:
                       1.0 / math.sqrt(Cc), self.stream, flops=4 * B * Nq * Nk * Cc,
                       tag="attn_tc" if not self.prof_detail else "attn_tc N%d d%d" % (Nk, Cc))
             return o
+        if (self.use_tc and not self.no_fused_attention and q.dt == nat.BF16 and k.dt == nat.BF16 and o.dt == nat.BF16
+                and q.ld % 8 == 0 and k.ld % 8 == 0 and o.ld % 8 == 0 and q.ptr % 16 == 0 and k.ptr % 16 == 0 and o.ptr % 16 == 0
+                and vT.dtype == torch.bfloat16 and nat.call("wsr_attention_small_tc_supported", Nq, Nk, Cc)):
+            # low-resolution levels (N <= 512, d <= 512): whole score block in tensor memory, one launch, nothing in HBM
+            self.n_tc += 1
+            self.call("wsr_attention_small_tc", q.ptr, q.ld, k.ptr, k.ld, vT.data_ptr(), o.ptr, o.ld, B, Nq, Nk, Cc,
+                      1.0 / math.sqrt(Cc), self.stream, flops=4 * B * Nq * Nk * Cc,
+                      tag="attn_small_tc" if not self.prof_detail else "attn_small_tc N%d d%d" % (Nk, Cc))
+            return o
         es = q.buf.element_size()
         s_dt = nat.BF16 if scores.dtype == torch.bfloat16 else nat.F32
         p_dt = nat.BF16 if probs.dtype == torch.bfloat16 else nat.F32

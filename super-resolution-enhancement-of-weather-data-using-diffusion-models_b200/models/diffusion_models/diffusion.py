@@ -131,6 +131,12 @@ class GaussianDiffusion(nn.Module):
     def _step(self, plan, x, t_dev, tab, z, z_stride, seed, clip=True):
         st = plan.eng.stream
         plan.select_level_row(t_dev)
+        if plan.can_fuse_head():
+            # head (GroupNorm + Swish + conv3x3) and the reverse-step update in one HBM-bound kernel
+            feat = plan.run(x, head=False)
+            plan.head_sampler_step(feat, x, tab, self.num_timesteps, t_dev, z, z_stride, seed, clip)
+            plan.eng.call("wsr_step_counter_add", t_dev.data_ptr(), -1, st)
+            return
         plan.run(x)
         plan.eng.call("wsr_sampler_step", x.data_ptr(), plan.eps.data_ptr(), nat.F32, 0 if z is None else z.data_ptr(),
                       z_stride, seed, tab.data_ptr(), self.num_timesteps, t_dev.data_ptr(), 1 if clip else 0, x.data_ptr(),

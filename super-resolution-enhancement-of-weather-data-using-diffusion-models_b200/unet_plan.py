@@ -287,6 +287,8 @@ class UNetPlan:
             fc = self.net.final_conv.block
             self.gf, self.bf_ = e.f32(fc[0].weight), e.f32(fc[0].bias)
             self.final = e.pack_conv(fc[3].weight, fc[3].bias, rows=64 if e.mode == "bf16" else None)
+            # fp32 [9][Cout][Cin] copy of the head's weights for the fused head + reverse-step kernel (wsr_final_conv_sampler_step)
+            self.final_f32 = self._pack_f32_conv(fc[3].weight) if e.mode == "bf16" else None
             mlp = self.net.noise_level_mlp
             self.mlp_w1, self.mlp_b1 = e.f32(mlp[1].weight), e.f32(mlp[1].bias)
             self.mlp_w2, self.mlp_b2 = e.f32(mlp[3].weight), e.f32(mlp[3].bias)
@@ -499,9 +501,32 @@ class UNetPlan:
         else:
             e.call("wsr_nchw_to_nhwc", x_t.data_ptr(), B, self.C_img, self.H, self.W, stem.xin.ptr, stem.xin.dt, stem.xin.ld, st)
 
-    def run(self, x_t):
+    def can_fuse_head(self):
+        """True when the head (GroupNorm + Swish + conv3x3 to <= 4 channels) can run fused with the reverse-step update
+        (wsr_final_conv_sampler_step): bf16 sampling plan, head input produced by a convolution that emitted its statistics."""
+        ok = getattr(self, "_fuse_head", None)
+        if ok is None:
+            import os
+            ok = self._fuse_head = (type(self) is UNetPlan and self.eng.mode == "bf16" and self.eng.use_tc and not self.fuse_gn
+                                    and os.environ.get("WSR_NO_FUSED_HEAD") is None
+                                    and bool(nat.call("wsr_head_sampler_supported", self.final_cin, self.C_img, self.groups)))
+        return ok
+
+    def head_sampler_step(self, feat, x_state, tab, T, t_dev, z, z_stride, seed, clip):
+        """eps_hat = final_conv(feat) and x_state <- reverse-step update, one launch; eps_hat is also left in ``self.eps``."""
+        e = self.eng
+        assert feat.stats_ptr and feat.C == self.final_cin and feat.dt == nat.BF16
+        npix = self.B * self.H * self.W
+        e.call("wsr_final_conv_sampler_step", feat.ptr, feat.ld, self.B, self.H, self.W, feat.C, feat.stats_ptr, feat.st_ld,
+               self.gf.data_ptr(), self.bf_.data_ptr(), self.groups, 1e-5, self.final_f32.w.data_ptr(), self.final.bias.data_ptr(),
+               self.C_img, self.eps.data_ptr(), x_state.data_ptr(), 0 if z is None else z.data_ptr(), z_stride, seed, tab.data_ptr(), T,
+               t_dev.data_ptr(), 1 if clip else 0, e.stream, tag="head_sampler",
+               flops=2 * npix * 9 * feat.C * self.C_img, nbytes=npix * (feat.C * 2 + self.C_img * (16 if z is not None else 12)))
+
+    def run(self, x_t, head=True):
         """One denoiser call on the current condition / level projection.  x_t: fp32 NCHW device tensor (B,C,H,W).
-        Leaves eps_hat in ``self.eps`` (fp32 NCHW)."""
+        Leaves eps_hat in ``self.eps`` (fp32 NCHW).  head=False: stop before ``final_conv`` and return its (raw) input Act --
+        the caller runs the head fused with the sampler update (``head_sampler_step``)."""
         e, B = self.eng, self.B
         st = e.stream
         e.call("wsr_fill_zero", self.stats.data_ptr(), self.stats.numel() * 8, st)
@@ -523,6 +548,8 @@ class UNetPlan:
                 x = self._res_block(r, r.cat)
             else:
                 x = e.conv(x, r.conv, r.y, upsample=True)
+        if not head:
+            return x
         self._head(x)
         if self.C_img != 1:
             e.call("wsr_nhwc_to_nchw", self.eps_nhwc.ptr, nat.F32, self.eps_nhwc.ld, B, self.C_img, self.H, self.W,

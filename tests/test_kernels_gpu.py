@@ -270,6 +270,61 @@ def test_sampler_step_and_randn():
     assert abs(float((r * r2).mean())) < 5e-3
 
 
+@pytest.mark.parametrize("case", [(2, 64, 1, 12, 160), (1, 128, 3, 8, 256), (3, 64, 1, 7, 128), (1, 64, 4, 5, 40)])
+def test_final_conv_sampler_step_fused_vs_torch(case):
+    """wsr_final_conv_sampler_step: GroupNorm + Swish + conv3x3 to <= 4 channels (final_conv, resdiff/unet.py:119,177) fused with the
+    reverse-step update, against fp32 torch (GroupNorm -> x*sigmoid(x) -> conv2d -> the update formula) and against the stand-alone
+    wsr_sampler_step fed with the fused kernel's own eps_hat (injected noise AND the in-kernel Philox stream must match exactly).
+    Sizes exercise partial tiles (H % 4 != 0, W % 128 != 0)."""
+    from oracle.schedule import ddpm_tables
+    from oracle.cases import LINEAR_1000
+    B, Cin, Cout, H, W = case
+    dev = _dev()
+    torch.manual_seed(21)
+    eng = Engine(dev, "bf16")
+    tabs, _ = ddpm_tables(LINEAR_1000)
+    order = ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2",
+             "posterior_log_variance_clipped")
+    tab = torch.stack([torch.from_numpy(tabs[k]) for k in order]).to(dev).contiguous()
+    x = torch.randn(B, Cin, H, W, device=dev) * 1.7 + 0.3
+    xa = _nhwc(x, eng)
+    xq = xa.to_nchw(eng)                                    # the bf16-rounded tensor the kernel reads
+    gamma, beta = 1 + 0.2 * torch.randn(Cin, device=dev), 0.1 * torch.randn(Cin, device=dev)
+    w, bias = torch.randn(Cout, Cin, 3, 3, device=dev) / math.sqrt(9 * Cin), 0.1 * torch.randn(Cout, device=dev)
+    wp = torch.empty(9, Cout, Cin, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    nat.call("wsr_pack_conv_weight", w.contiguous().data_ptr(), Cout, Cin, 3, 3, wp.data_ptr(), nat.F32, Cout, Cin, st)
+    stats = torch.zeros(B, 2 * Cin, device=dev, dtype=torch.float64)
+    nat.call("wsr_gn_stats", xa.ptr, xa.dt, B, H * W, Cin, xa.ld, stats.data_ptr(), 2 * Cin, st)
+    ref_eps = F.conv2d(F.silu(F.group_norm(xq, 32, gamma, beta, 1e-5)), w, bias, padding=1)
+    state0 = torch.randn(B, Cout, H, W, device=dev)
+    z = torch.randn(B, Cout, H, W, device=dev)
+    for t in (999, 1, 0):
+        t_dev = torch.tensor([t], dtype=torch.int32, device=dev)
+        for use_z in (True, False):
+            eps = torch.zeros(B, Cout, H, W, device=dev)
+            state = state0.clone()
+            nat.call("wsr_final_conv_sampler_step", xa.ptr, xa.ld, B, H, W, Cin, stats.data_ptr(), 2 * Cin, gamma.data_ptr(), beta.data_ptr(),
+                     32, 1e-5, wp.data_ptr(), bias.data_ptr(), Cout, eps.data_ptr(), state.data_ptr(), z.data_ptr() if use_z else 0, 0,
+                     4242, tab.data_ptr(), 1000, t_dev.data_ptr(), 1, st)
+            e_eps = rel_l2(eps, ref_eps)
+            assert e_eps < 6e-3, e_eps                       # bf16 rounding of the normalised activation, fp32 weights and sums
+            # the update itself: exact against the stand-alone kernel on the same eps_hat (same injected noise / same Philox words)
+            out2 = torch.empty_like(state0)
+            nat.call("wsr_sampler_step", state0.data_ptr(), eps.data_ptr(), nat.F32, z.data_ptr() if use_z else 0, 0, 4242, tab.data_ptr(),
+                     1000, t_dev.data_ptr(), 1, out2.data_ptr(), state0.numel(), st)
+            assert torch.equal(state, out2) or rel_l2(state, out2) < 1e-6
+            if use_z:
+                x0 = (tab[0, t] * state0 - tab[1, t] * ref_eps).clamp(-1, 1)
+                ref = tab[2, t] * x0 + tab[3, t] * state0 + (z * (0.5 * tab[4, t]).exp() if t > 0 else 0)
+                assert rel_l2(state, ref) < 6e-3
+    # convolution-only mode (no state)
+    eps = torch.zeros(B, Cout, H, W, device=dev)
+    nat.call("wsr_final_conv_sampler_step", xa.ptr, xa.ld, B, H, W, Cin, stats.data_ptr(), 2 * Cin, gamma.data_ptr(), beta.data_ptr(), 32, 1e-5,
+             wp.data_ptr(), 0, Cout, eps.data_ptr(), 0, 0, 0, 0, 0, 0, 0, 0, st)
+    assert rel_l2(eps, ref_eps - bias.view(1, -1, 1, 1)) < 6e-3
+
+
 def test_noise_embed_and_fd_and_haar_vs_oracle():
     """level embedding, FD splitter precompute (4-D FFT over B,C,H,W) and Haar queries against the CPU oracle."""
     from oracle import nets
@@ -333,6 +388,55 @@ def test_attention_tc_fused_vs_torch(shape):
     o2 = eng.new_act(B, H, W, d, zero=True)
     eng.attention(qa, ka, vT, o2, scores, probs)
     assert rel_l2(o2.to_nchw(eng), ref) < 1e-2
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 32, 512), (2, 16, 32, 256), (3, 8, 16, 512), (1, 12, 32, 192), (5, 16, 16, 320)])
+def test_attention_small_tc_fused_vs_torch(shape):
+    """fused low-resolution attention (N <= 512 keys, head dimension up to 512: nn_modules/resnet.py:81-100 at 16x32 / 8x16,
+    guided_cross_attention.py levels 2-3): ONE launch, whole score block in tensor memory, against fp32 torch on the same bf16
+    operands; the operands are channel slices of wider buffers as in the UNet plan (q | k in one 2C-channel tensor)."""
+    B, H, W, d = shape
+    n = H * W
+    torch.manual_seed(10)
+    dev = _dev()
+    eng = Engine(dev, "bf16")
+    # scores with a realistic spread: |s| / sqrt(d) of a few units, so the softmax is far from uniform
+    q = torch.randn(B, d, H, W, device=dev) * 2.0
+    k = torch.randn(B, d, H, W, device=dev) * 2.0
+    v = torch.randn(B, d, H, W, device=dev)
+    qk = eng.new_act(B, H, W, 2 * d, zero=True)
+    qa, ka = qk.slice(0, d), qk.slice(d, d)
+    eng.nchw_to_act(q, qa)
+    eng.nchw_to_act(k, ka)
+    vT = v.reshape(B, d, n).bfloat16().contiguous()
+    o = eng.new_act(B, H, W, d, zero=True)
+    scores = torch.empty(B * n * n, device=dev, dtype=torch.float32)
+    probs = torch.empty(B * n * n, device=dev, dtype=torch.bfloat16)
+    assert nat.call("wsr_attention_small_tc_supported", n, n, d) == 1
+    eng.attention(qa, ka, vT, o, scores, probs)
+    assert eng.n_tc == 1 and eng.n_simt == 0          # one fused launch
+    qf = qa.to_nchw(eng).reshape(B, d, n)
+    kf = ka.to_nchw(eng).reshape(B, d, n)
+    s = torch.einsum("bcq,bck->bqk", qf, kf) / math.sqrt(d)
+    ref = torch.einsum("bqk,bck->bcq", torch.softmax(s, -1), vT.float()).reshape(B, d, H, W)
+    got = o.to_nchw(eng)
+    err = rel_l2(got, ref)
+    assert torch.isfinite(got).all()
+    assert err < 1e-2, err
+    # per image as well (a wrong batch coordinate would hide in the average)
+    for b in range(B):
+        assert rel_l2(got[b], ref[b]) < 1.5e-2
+    # and the unfused path (GEMM -> softmax -> GEMM) agrees
+    eng.no_fused_attention = True
+    o2 = eng.new_act(B, H, W, d, zero=True)
+    eng.attention(qa, ka, vT, o2, scores, probs)
+    assert rel_l2(o2.to_nchw(eng), ref) < 1e-2
+
+
+def test_attention_small_tc_shape_gate():
+    ok = lambda nq, nk, d: nat.call("wsr_attention_small_tc_supported", nq, nk, d)
+    assert ok(512, 512, 512) and ok(128, 128, 512) and ok(512, 512, 256) and ok(256, 64, 64)
+    assert not ok(32, 32, 64) and not ok(512, 1024, 64) and not ok(512, 512, 1024) and not ok(128, 96, 64) and not ok(128, 128, 96)
 
 
 @pytest.mark.parametrize("case", [(2, 64, 64, 16, 32, 3, 1, False), (2, 64, 128, 16, 32, 3, 2, False), (1, 64, 64, 8, 16, 3, 1, True),
