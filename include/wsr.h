@@ -85,6 +85,11 @@ typedef struct {
    * pixels): [kx][3 * 64 rows][Cin], row block b of slice kx = the 64 (zero-padded) output channels of tap (ky = 2 - b, kx),
    * dtype = x_dtype (wsr_pack_conv_weight_vmerge).  NULL = not available. */
   const void* w_vmerge;
+  /* optional split-K workspace of wsr_conv_tc / wsr_conv_taps_tc (caller-owned, splitk_ws_bytes >= 4096 + tiles * splits * 128 *
+   * BN * 4; its first 4096 bytes are counters that MUST be zero before the first use -- the kernels leave them zero).  When a layer's
+   * tiles do not fill the SMs (deep levels at small batch) the K loop of each tile is cut across several CTAs that exchange fp32
+   * partial tiles through this buffer.  One workspace serves all launches of a stream; NULL = never split. */
+  void* splitk_ws; long long splitk_ws_bytes;
 } WsrConvDesc;
 
 /* fp32-accumulate SIMT implicit GEMM; any dtype, any channel count.  This is the "fp32 check mode" kernel. */
@@ -93,6 +98,8 @@ int wsr_conv_simt(const WsrConvDesc* d, void* stream);
  * Cin2 % 64 == 0, Cout % 16 == 0, W a power of two (>= 2), pitches % 8 == 0, 16-byte aligned bases. */
 int wsr_conv_tc(const WsrConvDesc* d, void* stream);
 int wsr_conv_tc_can_fuse_gn(const WsrConvDesc* d);
+/* test introspection: (column-tile width << 8) | K splits chosen by the most recent wsr_conv_tc / wsr_conv_taps_tc call */
+int wsr_debug_last_tc_config(void);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Tap-table convolution: the same kernels driven by an explicit list of taps instead of (ksize, stride, upsample).

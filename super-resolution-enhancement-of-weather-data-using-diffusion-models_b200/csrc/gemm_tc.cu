@@ -16,6 +16,7 @@
 // functional_layers.py:64,79, resdiff/unet.py:68, guided_cross_attention.py:20-22) and the attention einsums
 // (nn_modules/resnet.py:90-97, guided_cross_attention.py:34-41).
 #include <cuda.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -74,6 +75,12 @@ struct TcParams {
   // four "transform" warps that read the raw tensor from global memory, apply a = act(x * scale[n][c] + shift[n][c]) and
   // write the 128B-swizzled tile themselves (out-of-image pixels stay zero = the convolution's padding of the
   // NORMALISED tensor).  gn_tab: [N][gn_ld] float2 (scale, shift) from wsr_gn_finalize.
+  // split-K (SPLIT kernels, classic mode, one work item per CTA): the K blocks of a tile are cut into `ksplit` contiguous ranges of
+  // `kb_split` blocks, CTA (tile, s) accumulates range s; partial tiles go through the fp32 workspace `ws` ([tile][split][128][BN])
+  // and each CTA finishes the 32-column chunks ch with ch % ksplit == s.  ctr: [tile][2] arrival / completion counters, zero
+  // between launches (the last CTA of a tile restores the zeros).
+  int ksplit, kb_split;
+  float* ws; unsigned* ctr;
   const void* xg; int xg_ld, xg_H, xg_W;
   const void* x2g; int x2g_ld;
   const float2* gn_tab; int gn_ld; int gn_act;
@@ -133,8 +140,9 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
 // ------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------------
-template <int BLOCK_N, bool HALO, int ROWS, bool FUSE = false, bool VM = false, bool STG = false>
+template <int BLOCK_N, bool HALO, int ROWS, bool FUSE = false, bool VM = false, bool STG = false, bool SPLIT = false>
 __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  static_assert(!SPLIT || (!HALO && STG), "split-K: classic tiles with the staged epilogue only");
   // STG: the epilogue moves residual loads and output stores through a per-warp shared-memory staging buffer (see TcCfg::kStgBytes);
   // the host selects it only when stage_preconditions() hold (bf16 output / residual, unit channel stride, 16-byte aligned rows)
   // register budget: 10 warps = 3 warps on the fullest scheduler, 16384 / 3 / 32 -> 168 registers per thread at most
@@ -170,8 +178,12 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
   const int total_tiles = p.g1 * p.g2 * p.g3 * p.nbatch * p.n_tiles;
   // contiguous tile range per CTA: consecutive tiles share the image (register-accumulated GroupNorm statistics) and
   // neighbouring rows (halo re-reads hit L2)
-  const int tile_begin = (int)((long long)blockIdx.x * total_tiles / gridDim.x);
-  const int tile_end = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
+  // SPLIT: the grid is exactly (tiles x ksplit) CTAs, CTA = (tile, split)
+  const int split_s = SPLIT ? (int)blockIdx.x % p.ksplit : 0;
+  const int tile_begin = SPLIT ? (int)blockIdx.x / p.ksplit : (int)((long long)blockIdx.x * total_tiles / gridDim.x);
+  const int tile_end = SPLIT ? tile_begin + 1 : (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
+  const int kb0 = SPLIT ? split_s * p.kb_split : 0;
+  const int kb1 = SPLIT ? min(p.total_kb, kb0 + p.kb_split) : p.total_kb;
 
   if (warp == kProducerWarp && lane == 0) {
     for (int i = 0; i < kNumAMaps; ++i) prefetch_tmap(&p.amap[i]);
@@ -203,9 +215,11 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
         const TileCoord t = decode_tile(p, tile);
         const int c1 = t.i1 * p.t1, c2 = t.i2 * (HALO ? ROWS : p.t2), c3 = t.i3 * p.t3 + t.zb * p.a_zmul;
         if constexpr (!HALO) {
+          int kbi = 0;
           for (int ei = 0; ei < p.n_entries; ++ei) {
             const TcEntry e = p.e[ei];
-            for (int c = 0; c < e.nchunks; ++c) {
+            for (int c = 0; c < e.nchunks; ++c, ++kbi) {
+              if constexpr (SPLIT) { if (kbi < kb0 || kbi >= kb1) continue; }
               mbar_wait(&empty_a[sa], pa ^ 1);
               uint8_t* st = smem + sa * (kABytes + Cfg::kBBytes);
               mbar_expect_tx(&full_a[sa], (uint32_t)(p.a_bytes + (p.b_bytes ? p.b_bytes : Cfg::kBBytes)));
@@ -289,20 +303,20 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
           const uint32_t a_st = p.a_mn ? 128u : 2u, b_st = p.b_mn ? 128u : 2u;
           const uint32_t a_lbo = (p.a_mn ? (8192u >> 4) : 1u) << 16, b_lbo = (p.b_mn ? (8192u >> 4) : 1u) << 16;
           const uint32_t idesc = Cfg::kIdesc | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16);
-          for (int kb = 0; kb < p.total_kb; ++kb) {
+          for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(&full_a[sa], pa);
             tc_fence_after();
             const uint32_t s_lo = (smem_u32(smem + sa * (kABytes + Cfg::kBBytes)) & 0x3FFFFu) >> 4;
             const uint32_t a_lo = s_lo | a_lbo;
             const uint32_t b_lo = (s_lo + (uint32_t)(kABytes >> 4)) | b_lbo;
             if (!(p.dbg & 2)) {
-              umma_bf16_lo(d_tmem, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u);
+              umma_bf16_lo(d_tmem, a_lo, b_lo, idesc, kb != kb0 ? 1u : 0u);
               umma_bf16_lo(d_tmem, a_lo + a_st, b_lo + b_st, idesc, 1u);
               umma_bf16_lo(d_tmem, a_lo + 2 * a_st, b_lo + 2 * b_st, idesc, 1u);
               umma_bf16_lo(d_tmem, a_lo + 3 * a_st, b_lo + 3 * b_st, idesc, 1u);
             }
             umma_commit(&empty_a[sa]);
-            if (kb == p.total_kb - 1) umma_commit(&tfull_bar[acc]);
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
             if (++sa == kRingA) { sa = 0; pa ^= 1; }
           }
         } else {
@@ -589,6 +603,33 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
         for (int ci = 0; ci < kChunksPerWarp; ++ci) bs[ci * 32 + lane] = bs_reg[ci];
         __syncwarp();
       }
+      if constexpr (SPLIT) {
+        // phase A: the chunks another split finishes go to the workspace as fp32 partials (each lane writes 128 contiguous bytes of
+        // its own row), then every CTA of the tile waits until all partials are there.  All CTAs of the launch are resident (grid
+        // <= number of SMs, one CTA per SM), so spinning on the arrival counter cannot deadlock.
+        float* wsp = p.ws + ((long long)(tile * p.ksplit + split_s) * kBlockM + row) * BLOCK_N;
+#pragma unroll 1
+        for (int ci = 0; ci < kChunksPerWarp; ++ci) {
+          const int ch = ch_begin + ci;
+          if (ch % p.ksplit == split_s) continue;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * Cfg::kAccCols + ch * 32), v);
+          float4* dst = (float4*)(wsp + ch * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            __stcg(dst + q, make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])));
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        if (threadIdx.x == 0) {
+          atomicAdd(p.ctr + 2 * tile, 1u);
+          unsigned seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.ctr + 2 * tile) : "memory");
+          } while (seen < (unsigned)p.ksplit);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      }
 #pragma unroll 1
       for (int rr = 0; rr < ROWS; ++rr) {
       // row -> coordinates
@@ -605,8 +646,22 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
 #pragma unroll 1
       for (int ci = 0; ci < ((p.dbg & 1) ? 0 : kChunksPerWarp); ++ci) {
         const int ch = ch_begin + ci;
+        if constexpr (SPLIT) { if (ch % p.ksplit != split_s) continue; }
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * Cfg::kAccCols + rr * BLOCK_N + ch * 32), v);
+        if constexpr (SPLIT) {
+          // phase B: this CTA owns the chunk -- add the other splits' partials (L2 reads, never through L1)
+          for (int s2 = 0; s2 < p.ksplit; ++s2) {
+            if (s2 == split_s) continue;
+            const float4* src = (const float4*)(p.ws + ((long long)(tile * p.ksplit + s2) * kBlockM + row) * BLOCK_N + ch * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t4 = __ldcg(src + q);
+              v[4 * q] = __float_as_uint(__uint_as_float(v[4 * q]) + t4.x); v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + t4.y);
+              v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + t4.z); v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + t4.w);
+            }
+          }
+        }
         const int n0 = nt * BLOCK_N + ch * 32;
         if constexpr (STG) {
           // ---- staged epilogue: 32 full bf16 columns; residual loads and output stores go through the warp's staging buffer
@@ -859,6 +914,14 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if constexpr (SPLIT) {
+        // every CTA of the tile has passed the arrival spin before it gets here, so the last one may restore the zeros
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        if (threadIdx.x == 0) {
+          const unsigned done = atomicAdd(p.ctr + 2 * tile + 1, 1u);
+          if (done == (unsigned)p.ksplit - 1) { p.ctr[2 * tile] = 0u; p.ctr[2 * tile + 1] = 0u; __threadfence(); }
+        }
+      }
     }
     if (p.stats != nullptr) flush_stats();
   }
@@ -920,17 +983,21 @@ int sm_count() {
   return n;
 }
 
-template <int BLOCK_N, bool HALO, int ROWS, bool FUSE = false, bool VM = false, bool STG = false>
+template <int BLOCK_N, bool HALO, int ROWS, bool FUSE = false, bool VM = false, bool STG = false, bool SPLIT = false>
 static int launch_tc_impl(const TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N, HALO, ROWS, VM>;
   static bool attr_set = false;
   if (!attr_set) {
-    WSR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE, VM, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    WSR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE, VM, STG, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   int total = p.g1 * p.g2 * p.g3 * p.nbatch * p.n_tiles;
   int grid = total < sm_count() ? total : sm_count();
-  WSR_CUDA_OK(launch_pdl(gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE, VM, STG>, dim3(grid), dim3(FUSE ? kTcThreadsFused : kTcThreads),
+  if (SPLIT) {
+    grid = total * p.ksplit;
+    WSR_REQUIRE(p.ksplit >= 2 && grid <= sm_count() && p.ws != nullptr && p.ctr != nullptr, WSR_E_INVALID, "gemm_tc: split-K launch invariants");
+  }
+  WSR_CUDA_OK(launch_pdl(gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE, VM, STG, SPLIT>, dim3(grid), dim3(FUSE ? kTcThreadsFused : kTcThreads),
                          (size_t)Cfg::kSmemBytes, st, p));
   return WSR_OK;
 }
@@ -982,8 +1049,49 @@ static int launch_tc(const TcParams& p, cudaStream_t st) {
     }
     return stg ? launch_tc_impl<BLOCK_N, true, 1, false, false, true>(p, st) : launch_tc_impl<BLOCK_N, true, 1>(p, st);
   }
+  if constexpr (BLOCK_N >= 128) {
+    if (p.ksplit > 1) {
+      WSR_REQUIRE(sok, WSR_E_INVALID, "gemm_tc: split-K chosen without the staged-epilogue preconditions");
+      return launch_tc_impl<BLOCK_N, false, 1, false, false, true, true>(p, st);
+    }
+  }
   if (sok && (stage_mask() & 4)) return launch_tc_impl<BLOCK_N, false, 1, false, false, true>(p, st);
   return launch_tc_impl<BLOCK_N, false, 1>(p, st);
+}
+
+// Split-K plan for a classic-mode launch whose tiles do not fill the machine (deep UNet levels at small batch: 8 .. 64 row tiles for
+// 148 SMs).  Cost model in cycles per CTA, from the same B200 measurements as pick_block_n: a 128 x BN x 64 K block costs
+// 4 * (69 + 0.28 BN); a split adds the partial-tile round trip through L2 and one inter-CTA wait (~2000 + 8 BN (S-1)/S).  Returns the
+// chosen BN and sets *ksplit (1 = no split).  Split-K needs BN >= 128 (S <= BN / 32 column chunks to distribute), at least 4 K blocks
+// per split, tiles * S <= SMs and the caller's workspace.
+static int g_last_ksplit = 1, g_last_bn = 0;      // introspection for the tests (wsr_debug_last_tc_config)
+
+static int pick_split(int ncols, int m_tiles, int total_kb, long long ws_bytes, int bn_nosplit, int* ksplit) {
+  *ksplit = 1;
+  static const bool off = getenv("WSR_NO_SPLITK") != nullptr;
+  if (off || ws_bytes <= 0) return bn_nosplit;
+  const int sms = sm_count();
+  const double base_tiles = (double)m_tiles * ((ncols + bn_nosplit - 1) / bn_nosplit);
+  const double base = ceil(base_tiles / sms) * total_kb * 4.0 * (69.0 + 0.28 * bn_nosplit);
+  double best = base * 0.85;                       // split only for a clear win
+  int best_bn = bn_nosplit;
+  const int cand_bn[2] = {256, 128};
+  const int cand_s[7] = {2, 3, 4, 5, 6, 7, 8};
+  for (int i = 0; i < 2; ++i) {
+    const int bn = cand_bn[i];
+    if (ncols % bn != 0) continue;
+    const int tiles = m_tiles * (ncols / bn);
+    for (int j = 0; j < 7; ++j) {
+      const int S = cand_s[j];
+      if (S > bn / 32 || tiles * S > sms) continue;
+      const int per = (total_kb + S - 1) / S;
+      if (per < 4 || (S - 1) * per >= total_kb) continue;
+      if ((long long)tiles * S * kBlockM * bn * 4 + 4096 > ws_bytes || tiles * 2 * 4 > 4096) continue;
+      const double cost = per * 4.0 * (69.0 + 0.28 * bn) + 2000.0 + 8.0 * bn * (S - 1) / S;
+      if (cost < best) { best = cost; best_bn = bn; *ksplit = S; }
+    }
+  }
+  return best_bn;
 }
 
 static int pick_block_n(int ncols, int m_tiles) {
@@ -1021,6 +1129,9 @@ static void choose_tile(int W, int H, int N, int& t1, int& t2, int& t3) {
 using namespace wsr;
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+/* (column-tile width << 8) | K splits of the most recent wsr_conv_tc / wsr_conv_taps_tc launch of this process (tests only) */
+extern "C" int wsr_debug_last_tc_config(void) { return (g_last_bn << 8) | g_last_ksplit; }
 
 extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
   int rc = validate_conv_desc(d);
@@ -1066,13 +1177,24 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
   p.q_s1 = d->res2_ld; p.q_s2 = (long long)OW * d->res2_ld; p.q_s3 = (long long)OH * OW * d->res2_ld; p.q_sc = 1;
 
   const int m_tiles = p.g1 * p.g2 * p.g3;
-  const int bn = pick_block_n(d->Cout, m_tiles);
+  int bn = pick_block_n(d->Cout, m_tiles);
   // halo mode: when a tile is a segment of ONE image row, the 9 taps are 9 shifted views of a single halo tile, so the
   // activation operand is fetched once per 64-channel chunk instead of once per tap; with two output rows per tile
   // (two accumulators) every weight tile is used twice as well.  Both cut the L2 -> SM traffic that bounds these layers.
   static const bool no_halo = getenv("WSR_NO_HALO") != nullptr;
   static const int max_rows = getenv("WSR_HALO_ROWS") ? atoi(getenv("WSR_HALO_ROWS")) : 4;
   const bool halo = !no_halo && d->ksize == 3 && d->stride == 1 && p.t2 == 1 && p.t3 == 1 && p.t1 + 2 <= 130;
+  // split-K (classic tiles that do not fill the machine; needs the caller's workspace and the staged-epilogue preconditions)
+  p.ksplit = 1;
+  if (!halo && d->splitk_ws != nullptr && d->gn_table == nullptr && stage_preconditions(p, 128)) {
+    const int kb_est = (merged ? 4 : taps) * (d->Cin / 64) + (d->x2 ? d->Cin2 / 64 : 0);
+    int ks = 1;
+    const int bn2 = pick_split(d->Cout, m_tiles, kb_est, d->splitk_ws_bytes, bn, &ks);
+    if (ks > 1) {
+      bn = bn2; p.ksplit = ks; p.kb_split = (kb_est + ks - 1) / ks;
+      p.ctr = (unsigned*)d->splitk_ws; p.ws = (float*)((uint8_t*)d->splitk_ws + 4096);
+    }
+  }
   // vertical tap merge (N = 64, plain 3x3): three output rows per tile, needs the vmerge weight pack (w_vmerge)
   static const bool no_vm = getenv("WSR_NO_VMERGE") != nullptr;
   const bool vmerge = halo && bn == 64 && taps == 9 && !d->upsample && d->w_vmerge != nullptr && d->gn_table == nullptr && !no_vm;
@@ -1194,6 +1316,8 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
     p.mul1 = d->upsample ? 2 : 1; p.mul2 = p.mul1;
     p.off1 = d->upsample ? px : 0; p.off2 = d->upsample ? py : 0;
     p.n_tiles = cdiv(d->Cout, bn);
+    if (p.ksplit > 1) WSR_REQUIRE(kb == p.total_kb && (p.ksplit - 1) * p.kb_split < kb, WSR_E_INVALID, "conv_tc: split-K plan / K block count mismatch");
+    g_last_ksplit = p.ksplit; g_last_bn = bn;
     switch (bn) {
       case 256: rc = launch_tc<256>(p, st); break;
       case 128: rc = launch_tc<128>(p, st); break;
@@ -1252,8 +1376,18 @@ extern "C" int wsr_conv_taps_tc(const WsrConvDesc* d, const WsrTapTable* t, void
   p.res2 = d->res2; p.res2_dtype = d->res2_dtype; p.res2_scale = d->res2_scale;
   p.q_s1 = d->res2_ld; p.q_s2 = (long long)OW * d->res2_ld; p.q_s3 = (long long)OH * OW * d->res2_ld; p.q_sc = 1;
   const int m_tiles = p.g1 * p.g2 * p.g3;
-  const int bn = pick_block_n(d->Cout, m_tiles);
+  int bn = pick_block_n(d->Cout, m_tiles);
   p.n_taps = 0; p.halo_rows = 1;
+  p.ksplit = 1;
+  if (d->splitk_ws != nullptr && stage_preconditions(p, 128)) {
+    const int kb_est = t->ntaps * (d->Cin / 64);
+    int ks = 1;
+    const int bn2 = pick_split(d->Cout, m_tiles, kb_est, d->splitk_ws_bytes, bn, &ks);
+    if (ks > 1) {
+      bn = bn2; p.ksplit = ks; p.kb_split = (kb_est + ks - 1) / ks;
+      p.ctr = (unsigned*)d->splitk_ws; p.ws = (float*)((uint8_t*)d->splitk_ws + 4096);
+    }
+  }
   const bool fuse_stats = d->gn_stats != nullptr && (p.t1 * p.t2) % 32 == 0;
   p.stats = fuse_stats ? d->gn_stats : nullptr;
   p.stats_ld = d->gn_stats_ld;
@@ -1301,6 +1435,8 @@ extern "C" int wsr_conv_taps_tc(const WsrConvDesc* d, const WsrTapTable* t, void
   p.n_entries = t->ntaps; p.total_kb = kb;
   p.mul1 = t->out_mul; p.mul2 = t->out_mul; p.off1 = t->out_px; p.off2 = t->out_py;
   p.n_tiles = cdiv(d->Cout, bn);
+  if (p.ksplit > 1) WSR_REQUIRE((p.ksplit - 1) * p.kb_split < kb, WSR_E_INVALID, "conv_taps_tc: split-K plan / K block count mismatch");
+  g_last_ksplit = p.ksplit; g_last_bn = bn;
   switch (bn) {
     case 256: rc = launch_tc<256>(p, st); break;
     case 128: rc = launch_tc<128>(p, st); break;

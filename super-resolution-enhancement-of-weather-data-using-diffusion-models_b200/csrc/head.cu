@@ -58,9 +58,34 @@ __global__ void __launch_bounds__(kHeadThreads) head_sampler_kernel(const HeadPa
   const int y0 = ty * kHeadRows, x0 = tx * kHeadCols;
   const int tid = threadIdx.x;
 
-  for (int i = tid; i < 9 * COUT * p.Cin; i += kHeadThreads) wsm[i] = p.w[i];
+  // ---- halo tile loader: raw bf16 -> GroupNorm + Swish -> bf16 (out-of-image pixels = the convolution's zero padding).  The global
+  // loads are issued kU at a time BEFORE their results are needed (a block is one latency chain otherwise: 25 dependent ~1 us round
+  // trips per thread), and the first batch is in flight while the weights / GroupNorm parameters are staged.
+  constexpr int kU = 7;
+  const int nvec = planes * TR * TC * 8;                 // 16-byte vectors (8 channels)
+  const __nv_bfloat16* xb = p.x + (long long)n * p.H * p.W * p.x_ld;
+  uint4 raw[kU];
+  auto locate = [&](int v, int& k, int& col, int& row, int& pl) -> bool {
+    k = v & 7;
+    int r = v >> 3;
+    col = r % TC; r /= TC;
+    row = r % TR; pl = r / TR;
+    const int gy = y0 + row - 1, gx = x0 + col - 1;
+    return v < nvec && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+  };
+  auto issue = [&](int v0) {
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      int k, col, row, pl;
+      raw[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (locate(v0 + u * kHeadThreads, k, col, row, pl))
+        raw[u] = __ldg((const uint4*)(xb + ((long long)(y0 + row - 1) * p.W + (x0 + col - 1)) * p.x_ld + pl * 64 + k * 8));
+    }
+  };
   pdl_launch_dependents();
   pdl_wait();
+  issue(tid);
+  for (int i = tid; i < 9 * COUT * p.Cin; i += kHeadThreads) wsm[i] = p.w[i];
   {
     const int cpg = p.Cin / p.groups;
     const long long HW = (long long)p.H * p.W;
@@ -83,21 +108,21 @@ __global__ void __launch_bounds__(kHeadThreads) head_sampler_kernel(const HeadPa
     }
     __syncthreads();
   }
-  // ---- halo tile: raw bf16 -> GroupNorm + Swish -> bf16, out-of-image pixels are the convolution's zero padding ----
-  {
-    const int nvec = planes * TR * TC * 8;                 // 16-byte vectors (8 channels)
-    const __nv_bfloat16* xb = p.x + (long long)n * p.H * p.W * p.x_ld;
-    for (int v = tid; v < nvec; v += kHeadThreads) {
-      const int k = v & 7;                                 // 16-byte chunk inside the 64-channel plane
-      int r = v >> 3;
-      const int col = r % TC; r /= TC;
-      const int row = r % TR; const int pl = r / TR;
-      const int gy = y0 + row - 1, gx = x0 + col - 1;
+  for (int v0 = tid; v0 < nvec; v0 += kU * kHeadThreads) {
+    uint4 cur[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) cur[u] = raw[u];
+    if (v0 + kU * kHeadThreads < nvec) issue(v0 + kU * kHeadThreads);          // next batch in flight while this one is transformed
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      int k, col, row, pl;
+      const int v = v0 + u * kHeadThreads;
+      const bool inside = locate(v, k, col, row, pl);
+      if (v >= nvec) continue;
       uint4 o = make_uint4(0u, 0u, 0u, 0u);
-      if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+      if (inside) {
         const int c0 = pl * 64 + k * 8;
-        const uint4 raw = __ldg((const uint4*)(xb + ((long long)gy * p.W + gx) * p.x_ld + c0));
-        const __nv_bfloat162* h = (const __nv_bfloat162*)&raw;
+        const __nv_bfloat162* h = (const __nv_bfloat162*)&cur[u];
         __nv_bfloat162* oh = (__nv_bfloat162*)&o;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {

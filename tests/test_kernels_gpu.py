@@ -125,6 +125,66 @@ def test_conv_tc_vs_simt(case):
     assert rel_l2(y_si.to_nchw(eng), ref) < 1e-4
 
 
+SPLITK_CASES = [
+    # N, Cin, Cout, H, W, k, stride, up, Cin2 (fused 1x1 segment), expect a split
+    (8, 512, 512, 8, 16, 3, 1, False, 0, True),        # the 8x16 level at 8 samples per GPU: 8 row tiles for 148 SMs
+    (8, 512, 512, 8, 16, 3, 1, False, 1024, True),     # ... with the ResnetBlock's 1x1 res_conv as a second K segment
+    (8, 1024, 512, 16, 32, 3, 1, False, 0, True),      # the 16x32 level: 32 row tiles
+    (8, 512, 512, 8, 16, 3, 1, True, 0, True),         # nearest-x2 + 3x3 (phase-merged taps, 4 launches)
+    (8, 512, 512, 16, 32, 3, 2, False, 0, True),       # stride 2 (phase-subsampled tensor maps)
+    (3, 192, 256, 4, 8, 3, 1, False, 0, True),         # uneven split of 27 K blocks, partial row tile
+    (64, 512, 512, 8, 16, 3, 1, False, 0, False),      # enough tiles: no split
+]
+
+
+@pytest.mark.parametrize("case", SPLITK_CASES)
+def test_conv_tc_split_k_vs_simt(case):
+    """Split-K of the classic-mode tcgen05 convolution (tiles that do not fill the SMs): fp32 partial tiles through the
+    workspace, distributed fix-up with bias / time-embedding row / residual / GroupNorm statistics in the epilogue; compared
+    with the SIMT kernel on the same bf16 operands, run twice (the arrival counters must be left at zero)."""
+    N, Cin, Cout, H, W, k, stride, up, Cin2, expect = case
+    torch.manual_seed(12)
+    dev = _dev()
+    eng = Engine(dev, "bf16")
+    x = torch.randn(N, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, k, k, device=dev) / math.sqrt(Cin * k * k)
+    b = torch.randn(Cout, device=dev)
+    rv = torch.randn(N, Cout, device=dev)
+    OH, OW = (H * (2 if up else 1)) // stride, (W * (2 if up else 1)) // stride
+    res = torch.randn(N, Cout, OH, OW, device=dev)
+    pc = eng.pack_upsample_conv(w, b) if up else eng.pack_conv(w, b)
+    pc_ref = eng.pack_conv(w, b)
+    xa, ra = _nhwc(x, eng), _nhwc(res, eng)
+    kw = dict(stride=stride, upsample=up, rowvec=rv.data_ptr(), rowvec_ld=Cout, res=ra)
+    kw_ref = dict(kw)
+    if Cin2:
+        x2 = torch.randn(N, Cin2, H, W, device=dev)
+        w2 = torch.randn(Cout, Cin2, 1, 1, device=dev) / math.sqrt(Cin2)
+        kw.update(x2=_nhwc(x2, eng), w2=eng.pack_conv(w2, None))
+        kw_ref.update(x2=kw["x2"], w2=kw["w2"])
+    arena = engine_mod.StatsArena()
+    y_tc = eng.new_act(N, OH, OW, Cout, zero=True, stats=arena)
+    arena.finalize(dev)
+    y_si = eng.new_act(N, OH, OW, Cout, dt=nat.F32, zero=True)
+    eng.conv(xa, pc_ref, y_si, force_simt=True, **kw_ref)
+    ref = y_si.to_nchw(eng)
+    for rep in range(2):
+        arena.tensor.zero_()
+        y_tc.buf.zero_()
+        eng.conv(xa, pc, y_tc, **kw)
+        cfg = nat.call("wsr_debug_last_tc_config")
+        assert ((cfg & 0xff) > 1) == expect, (cfg >> 8, cfg & 0xff)
+        got = y_tc.to_nchw(eng)
+        err = rel_l2(got, ref)
+        assert err < (8e-3 if up else 4e-3), (rep, err)          # merged upsample taps are summed before the bf16 rounding
+        # GroupNorm statistics of the output came out of the (distributed) epilogue
+        st = arena.tensor.view(N, Cout, 2)
+        assert rel_l2(st[..., 0].float(), got.double().sum((2, 3)).float()) < 2e-3
+        assert rel_l2(st[..., 1].float(), (got.double() ** 2).sum((2, 3)).float()) < 2e-3
+    ws = eng.splitk_ws[:4096].view(torch.int32)
+    assert int(ws.abs().sum()) == 0                               # counters restored
+
+
 @pytest.mark.parametrize("hw", [(16, 32), (4, 128)])
 def test_conv_tc_second_segment_slices_and_f32_out(hw):
     """fused 1x1 res_conv segment, channel-slice input/output pitches, fp32 output, Cout=1 with padded weight rows
