@@ -85,8 +85,8 @@ typedef struct {
    * pixels): [kx][3 * 64 rows][Cin], row block b of slice kx = the 64 (zero-padded) output channels of tap (ky = 2 - b, kx),
    * dtype = x_dtype (wsr_pack_conv_weight_vmerge).  NULL = not available. */
   const void* w_vmerge;
-  /* optional split-K workspace of wsr_conv_tc / wsr_conv_taps_tc (caller-owned, splitk_ws_bytes >= 4096 + tiles * splits * 128 *
-   * BN * 4; its first 4096 bytes are counters that MUST be zero before the first use -- the kernels leave them zero).  When a layer's
+  /* optional split-K workspace of wsr_conv_tc / wsr_conv_taps_tc (caller-owned, splitk_ws_bytes >= 32768 + tiles * splits * 128 *
+   * BN * 4; its first 32768 bytes are counters that MUST be zero before the first use -- the kernels leave them zero).  When a layer's
    * tiles do not fill the SMs (deep levels at small batch) the K loop of each tile is cut across several CTAs that exchange fp32
    * partial tiles through this buffer.  One workspace serves all launches of a stream; NULL = never split. */
   void* splitk_ws; long long splitk_ws_bytes;
@@ -100,6 +100,9 @@ int wsr_conv_tc(const WsrConvDesc* d, void* stream);
 int wsr_conv_tc_can_fuse_gn(const WsrConvDesc* d);
 /* test introspection: (column-tile width << 8) | K splits chosen by the most recent wsr_conv_tc / wsr_conv_taps_tc call */
 int wsr_debug_last_tc_config(void);
+/* split-K of the classic-mode tcgen05 convolution is correct but measured no faster than the unsplit kernel on B200, so
+ * it is off unless WSR_SPLITK=1 or this switch is set; returns the previous setting. */
+int wsr_debug_set_splitk(int on);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Tap-table convolution: the same kernels driven by an explicit list of taps instead of (ksize, stride, upsample).
@@ -208,6 +211,10 @@ int wsr_fill_zero(void* p, int64_t bytes, void* stream);
 int wsr_gn_apply_dropout(const void* x, int x_dtype, int N, int HW, int C, int x_ld, const double* stats, int stats_ld,
                          const float* gamma, const float* beta, int groups, float eps, int act, void* y, int y_dtype,
                          int y_ld, float drop_p, uint64_t drop_seed, uint32_t drop_tag, void* stream);
+/* The keep-scale mask (0 or 1/(1-p)) that wsr_gn_apply_dropout / wsr_gn_bwd_* apply for (seed, tag): out is NHWC-dense
+ * (N, HW, C) fp32, element ((n*HW + p)*C + c).  Test infrastructure for the dropout-on gradient parity check: the mask is exported
+ * to the oracle, which multiplies with it where the reference applies nn.Dropout (nn_modules/resnet.py:23). */
+int wsr_dropout_mask(float* out, int N, int HW, int C, float p, uint64_t seed, uint32_t tag, void* stream);
 /* Backward of GroupNorm + activation (+ dropout).  da = gradient w.r.t. the block output, same dtype as x.
  *   pass 1: red[n*red_ld + 2c + {0,1}] += (sum_p dz, sum_p dz*xhat), dz = da * drop * act'(z)   (doubles, zeroed by the caller)
  *   pass 2: dx (=, or += when accumulate) rstd * (dz*gamma - A_g/m - xhat*B_g/m); dgamma += sum_n red1, dbeta += sum_n red0

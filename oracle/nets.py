@@ -49,9 +49,18 @@ def noise_level_mlp(sd, level, inner, act=swish, p="noise_level_mlp."):
     return linear(sd, p + "3.", act(linear(sd, p + "1.", e)))
 
 
-def block(sd, p, x, groups):
-    """nn_modules/resnet.py:19-28 in eval mode (dropout = identity): GN -> Swish -> conv3x3."""
-    return conv(sd, p + "block.3.", swish(group_norm(sd, p + "block.0.", x, groups)), padding=1)
+# Training-mode dropout (nn_modules/resnet.py:23, only block2 has p != 0): an iterator of keep-scale masks (0 or 1/(1-p), shape of
+# the activation), consumed in execution order by every block2; None = eval mode / p = 0.  The GPU tests export the masks the
+# CUDA path used (wsr_dropout_mask) so that both sides apply the SAME mask.
+DROP_MASKS = None
+
+
+def block(sd, p, x, groups, drop=False):
+    """nn_modules/resnet.py:19-28: GN -> Swish -> (Dropout) -> conv3x3."""
+    a = swish(group_norm(sd, p + "block.0.", x, groups))
+    if drop and DROP_MASKS is not None:
+        a = a * next(DROP_MASKS)
+    return conv(sd, p + "block.3.", a, padding=1)
 
 
 def resnet_block(sd, p, x, t_emb, groups):
@@ -59,7 +68,7 @@ def resnet_block(sd, p, x, t_emb, groups):
     b = x.shape[0]
     h = block(sd, p + "block1.", x, groups)
     h = h + linear(sd, p + "noise_func.noise_func.0.", t_emb).view(b, -1, 1, 1)
-    h = block(sd, p + "block2.", h, groups)
+    h = block(sd, p + "block2.", h, groups, drop=True)
     skip = conv(sd, p + "res_conv.", x) if (p + "res_conv.weight") in sd else x
     return h + skip
 

@@ -228,9 +228,23 @@ template <typename TI, typename TO, int VEC, bool DROP>
 __global__ void gn_apply_kernel(const TI* __restrict__ x, int HW, int C, int ld, int CV, int PL, int chunk,
                                 const double* __restrict__ stats, int stats_ld, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int groups, float eps, int act, TO* __restrict__ y, int y_ld,
-                                float drop_p, uint64_t drop_seed, uint32_t drop_tag) {
+                                float drop_p, uint64_t drop_seed, uint32_t drop_tag, int cpi, int nr, int nimg) {
   extern __shared__ float sm[];   // scale[C], shift[C], then (mean, rstd) per group
-  const int n = blockIdx.y;
+  // Block -> (image, pixel chunk).  nr == 0: natural order (blockIdx.x = image * cpi + chunk).  nr > 0: "range-reversed" order.  The
+  // producing convolution is a persistent kernel whose CTA r wrote the r-th of nr contiguous ranges of this tensor front to back, so
+  // when it ends the 126 MB L2 holds the TAIL of every range; walking every range back to front (pass k visits the k-th chunk from the
+  // end of all ranges) reads those tails while they are still cached, and leaves the HEADS of the ranges of the output in L2, which is
+  // where the consuming convolution's CTAs start.  In natural order a tensor larger than the cache streams through it with no hits.
+  int gc = blockIdx.x;
+  if (nr > 0) {
+    const long long T = (long long)cpi * nimg;
+    const int k = blockIdx.x / nr, r = blockIdx.x - k * nr;
+    const long long start = (long long)r * T / nr, end = (long long)(r + 1) * T / nr;
+    if (k >= end - start) return;
+    gc = (int)(end - 1 - k);
+  }
+  const int n = nr > 0 ? gc / cpi : blockIdx.y;
+  const int chunk_idx = nr > 0 ? gc - n * cpi : blockIdx.x;
   const int cpg = C / groups;
   float* gm = sm + 2 * C;
   pdl_launch_dependents();        // programmatic dependent launch (common.cuh): the statistics come from the preceding convolution
@@ -257,7 +271,7 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x, int HW, int C, int ld,
   }
   __syncthreads();
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
-  const int p0 = blockIdx.x * chunk;
+  const int p0 = chunk_idx * chunk;
   const int p1 = min(HW, p0 + chunk);
   float sc[VEC], sh[VEC];
 #pragma unroll
@@ -699,10 +713,25 @@ static int gn_apply_impl(const void* x, int x_dtype, int N, int HW, int C, int x
     if (chunk < 4 * g.PL) chunk = 4 * g.PL;
     if (chunk < g.chunk) g.chunk = chunk;
   }
-  dim3 grid((HW + g.chunk - 1) / g.chunk, N);
+  const int cpi = (HW + g.chunk - 1) / g.chunk;
+  dim3 grid(cpi, N);
+  // range-reversed block order (see the kernel): on for tensors that do not fit the L2 anyway-hit regime, i.e. always harmless;
+  // WSR_GN_ORDER=0 restores the natural order (A/B measurements)
+  static const int order_on = getenv("WSR_GN_ORDER") ? atoi(getenv("WSR_GN_ORDER")) : 1;
+  int nr = 0;
+  if (order_on) {
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    static int cached_sms = 0;
+    if (!cached_sms) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); cached_sms = sms > 0 ? sms : 148; }
+    nr = cached_sms;
+    const long long T = (long long)cpi * N;
+    const long long maxlen = (T + nr - 1) / nr;
+    grid = dim3((unsigned)(maxlen * nr), 1);
+  }
   size_t smem = ((size_t)C * 2 + 2 * groups) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-#define GN_APPLY(T, V, D) WSR_CUDA_OK(launch_pdl(gn_apply_kernel<T, T, V, D>, grid, dim3(g.threads), smem, st, (const T*)x, HW, C, x_ld, g.CV, g.PL, g.chunk, stats, stats_ld, gamma, beta, groups, eps, act, (T*)y, y_ld, drop_p, drop_seed, drop_tag))
+#define GN_APPLY(T, V, D) WSR_CUDA_OK(launch_pdl(gn_apply_kernel<T, T, V, D>, grid, dim3(g.threads), smem, st, (const T*)x, HW, C, x_ld, g.CV, g.PL, g.chunk, stats, stats_ld, gamma, beta, groups, eps, act, (T*)y, y_ld, drop_p, drop_seed, drop_tag, cpi, nr, N))
   if (drop_p > 0.f) {
     if (x_dtype == WSR_BF16) { if (g.vec == 8) GN_APPLY(__nv_bfloat16, 8, true); else GN_APPLY(__nv_bfloat16, 1, true); }
     else { if (g.vec == 4) GN_APPLY(float, 4, true); else GN_APPLY(float, 1, true); }
@@ -736,6 +765,22 @@ extern "C" int wsr_gn_apply_dropout(const void* x, int x_dtype, int N, int HW, i
                                     void* y, int y_dtype, int y_ld, float drop_p, uint64_t drop_seed, uint32_t drop_tag,
                                     void* stream) {
   return gn_apply_impl(x, x_dtype, N, HW, C, x_ld, stats, stats_ld, gamma, beta, groups, eps, act, y, y_dtype, y_ld, drop_p, drop_seed, drop_tag, stream);
+}
+
+__global__ void dropout_mask_kernel(float* out, int64_t total, float p, uint64_t seed, uint32_t tag) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  float m[1];
+  dropout_scale<1>(seed, tag, (uint64_t)e, p, m);
+  out[e] = m[0];
+}
+
+extern "C" int wsr_dropout_mask(float* out, int N, int HW, int C, float p, uint64_t seed, uint32_t tag, void* stream) {
+  WSR_REQUIRE(out && N > 0 && HW > 0 && C > 0 && p >= 0.f && p < 1.f, WSR_E_INVALID, "dropout_mask: bad argument");
+  const int64_t total = (int64_t)N * HW * C;
+  dropout_mask_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(out, total, p, seed, tag);
+  WSR_LAUNCH_OK();
+  return WSR_OK;
 }
 
 extern "C" int wsr_softmax_rows(const void* s, int s_dtype, int64_t rows, int cols, int64_t s_ld, float scale, void* p,

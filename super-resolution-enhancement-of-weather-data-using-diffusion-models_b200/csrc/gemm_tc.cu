@@ -615,18 +615,23 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * Cfg::kAccCols + ch * 32), v);
           float4* dst = (float4*)(wsp + ch * 32);
+          if (!(p.dbg & 16)) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            __stcg(dst + q, make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])));
+            for (int q = 0; q < 8; ++q)
+              __stcg(dst + q, make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])));
+          }
         }
         __threadfence();
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
         if (threadIdx.x == 0) {
-          atomicAdd(p.ctr + 2 * tile, 1u);
+          // one 128-byte line per tile: arrival counter at [tile * 32], completion counter at [tile * 32 + 1]
+          unsigned* arrive = p.ctr + tile * 32;
+          atomicAdd(arrive, 1u);
           unsigned seen;
           do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.ctr + 2 * tile) : "memory");
-          } while (seen < (unsigned)p.ksplit);
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrive) : "memory");
+            if (seen < (unsigned)p.ksplit) __nanosleep(100);
+          } while (seen < (unsigned)p.ksplit && !(p.dbg & 8));
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       }
@@ -651,7 +656,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * Cfg::kAccCols + rr * BLOCK_N + ch * 32), v);
         if constexpr (SPLIT) {
           // phase B: this CTA owns the chunk -- add the other splits' partials (L2 reads, never through L1)
-          for (int s2 = 0; s2 < p.ksplit; ++s2) {
+          for (int s2 = 0; s2 < ((p.dbg & 32) ? 0 : p.ksplit); ++s2) {
             if (s2 == split_s) continue;
             const float4* src = (const float4*)(p.ws + ((long long)(tile * p.ksplit + s2) * kBlockM + row) * BLOCK_N + ch * 32);
 #pragma unroll
@@ -918,8 +923,8 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
         // every CTA of the tile has passed the arrival spin before it gets here, so the last one may restore the zeros
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
         if (threadIdx.x == 0) {
-          const unsigned done = atomicAdd(p.ctr + 2 * tile + 1, 1u);
-          if (done == (unsigned)p.ksplit - 1) { p.ctr[2 * tile] = 0u; p.ctr[2 * tile + 1] = 0u; __threadfence(); }
+          const unsigned done = atomicAdd(p.ctr + tile * 32 + 1, 1u);
+          if (done == (unsigned)p.ksplit - 1) { p.ctr[tile * 32] = 0u; p.ctr[tile * 32 + 1] = 0u; __threadfence(); }
         }
       }
     }
@@ -1064,13 +1069,35 @@ static int launch_tc(const TcParams& p, cudaStream_t st) {
 // 4 * (69 + 0.28 BN); a split adds the partial-tile round trip through L2 and one inter-CTA wait (~2000 + 8 BN (S-1)/S).  Returns the
 // chosen BN and sets *ksplit (1 = no split).  Split-K needs BN >= 128 (S <= BN / 32 column chunks to distribute), at least 4 K blocks
 // per split, tiles * S <= SMs and the caller's workspace.
-static int g_last_ksplit = 1, g_last_bn = 0;      // introspection for the tests (wsr_debug_last_tc_config)
+constexpr int kSplitHeader = 32768;               // bytes of counters at the head of the split-K workspace (one 128-byte line per tile)
+static int g_last_ksplit = 1, g_last_bn = 0;
+static int g_splitk_on = 0;                       // wsr_debug_set_splitk (tests); the environment variable WSR_SPLITK=1 does the same      // introspection for the tests (wsr_debug_last_tc_config)
 
 static int pick_split(int ncols, int m_tiles, int total_kb, long long ws_bytes, int bn_nosplit, int* ksplit) {
   *ksplit = 1;
+  // MEASURED on B200 (tools/prof_conv.py, profiles/r02_splitk_sweep.txt): at the shapes this was built for (8x16 / 16x32 levels at 8
+  // samples per GPU) the kernel time does not depend on how the work is cut -- 512->512 k3 @8x16, B = 8: 24.5 us with 64 CTAs (BN 64),
+  // 29.7 us with 16 CTAs (BN 256), 30.4 / 29.6 / 33.5 us with 2 / 4 / 8 K splits, and the SAME 31.7 us with the MMA issue disabled:
+  // these launches are bound by the latency of the TMA operand fetch (~190 KB in flight per SM / 1.4 .. 5 us), not by the tensor pipe
+  // or the CTA count, and the partial-tile round trip of a split adds 9 + 5 us.  Split-K is therefore OFF unless WSR_SPLITK=1.
+  static const bool env_on = getenv("WSR_SPLITK") != nullptr && atoi(getenv("WSR_SPLITK")) != 0;
   static const bool off = getenv("WSR_NO_SPLITK") != nullptr;
-  if (off || ws_bytes <= 0) return bn_nosplit;
+  static const bool forced = getenv("WSR_SPLITK_FORCE") != nullptr;
+  if ((!env_on && !forced && !g_splitk_on) || off || ws_bytes <= 0) return bn_nosplit;
   const int sms = sm_count();
+  // WSR_SPLITK_FORCE="bn,S": measurement override (tools/prof_conv.py); ignored when the plan is not feasible
+  static const char* force = getenv("WSR_SPLITK_FORCE");
+  if (force) {
+    int fbn = 0, fs = 0;
+    if (sscanf(force, "%d,%d", &fbn, &fs) == 2 && (fbn == 128 || fbn == 256) && ncols % fbn == 0) {
+      const int tiles = m_tiles * (ncols / fbn);
+      const int per = fs > 0 ? (total_kb + fs - 1) / fs : 0;
+      if (fs >= 2 && fs <= fbn / 32 && tiles * fs <= sms && per >= 1 && (fs - 1) * per < total_kb &&
+          (long long)tiles * fs * kBlockM * fbn * 4 + kSplitHeader <= ws_bytes && tiles * 128 <= kSplitHeader) { *ksplit = fs; return fbn; }
+      if (fs == 1) return fbn;
+    }
+    return bn_nosplit;
+  }
   const double base_tiles = (double)m_tiles * ((ncols + bn_nosplit - 1) / bn_nosplit);
   const double base = ceil(base_tiles / sms) * total_kb * 4.0 * (69.0 + 0.28 * bn_nosplit);
   double best = base * 0.85;                       // split only for a clear win
@@ -1086,7 +1113,7 @@ static int pick_split(int ncols, int m_tiles, int total_kb, long long ws_bytes, 
       if (S > bn / 32 || tiles * S > sms) continue;
       const int per = (total_kb + S - 1) / S;
       if (per < 4 || (S - 1) * per >= total_kb) continue;
-      if ((long long)tiles * S * kBlockM * bn * 4 + 4096 > ws_bytes || tiles * 2 * 4 > 4096) continue;
+      if ((long long)tiles * S * kBlockM * bn * 4 + kSplitHeader > ws_bytes || tiles * 128 > kSplitHeader) continue;
       const double cost = per * 4.0 * (69.0 + 0.28 * bn) + 2000.0 + 8.0 * bn * (S - 1) / S;
       if (cost < best) { best = cost; best_bn = bn; *ksplit = S; }
     }
@@ -1132,6 +1159,8 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 /* (column-tile width << 8) | K splits of the most recent wsr_conv_tc / wsr_conv_taps_tc launch of this process (tests only) */
 extern "C" int wsr_debug_last_tc_config(void) { return (g_last_bn << 8) | g_last_ksplit; }
+/* enable (1) / disable (0) the split-K plan of wsr_conv_tc / wsr_conv_taps_tc for this process; returns the previous setting */
+extern "C" int wsr_debug_set_splitk(int on) { const int prev = g_splitk_on; g_splitk_on = on ? 1 : 0; return prev; }
 
 extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
   int rc = validate_conv_desc(d);
@@ -1190,9 +1219,10 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
     const int kb_est = (merged ? 4 : taps) * (d->Cin / 64) + (d->x2 ? d->Cin2 / 64 : 0);
     int ks = 1;
     const int bn2 = pick_split(d->Cout, m_tiles, kb_est, d->splitk_ws_bytes, bn, &ks);
+    bn = bn2;
     if (ks > 1) {
-      bn = bn2; p.ksplit = ks; p.kb_split = (kb_est + ks - 1) / ks;
-      p.ctr = (unsigned*)d->splitk_ws; p.ws = (float*)((uint8_t*)d->splitk_ws + 4096);
+      p.ksplit = ks; p.kb_split = (kb_est + ks - 1) / ks;
+      p.ctr = (unsigned*)d->splitk_ws; p.ws = (float*)((uint8_t*)d->splitk_ws + kSplitHeader);
     }
   }
   // vertical tap merge (N = 64, plain 3x3): three output rows per tile, needs the vmerge weight pack (w_vmerge)
@@ -1383,9 +1413,10 @@ extern "C" int wsr_conv_taps_tc(const WsrConvDesc* d, const WsrTapTable* t, void
     const int kb_est = t->ntaps * (d->Cin / 64);
     int ks = 1;
     const int bn2 = pick_split(d->Cout, m_tiles, kb_est, d->splitk_ws_bytes, bn, &ks);
+    bn = bn2;
     if (ks > 1) {
-      bn = bn2; p.ksplit = ks; p.kb_split = (kb_est + ks - 1) / ks;
-      p.ctr = (unsigned*)d->splitk_ws; p.ws = (float*)((uint8_t*)d->splitk_ws + 4096);
+      p.ksplit = ks; p.kb_split = (kb_est + ks - 1) / ks;
+      p.ctr = (unsigned*)d->splitk_ws; p.ws = (float*)((uint8_t*)d->splitk_ws + kSplitHeader);
     }
   }
   const bool fuse_stats = d->gn_stats != nullptr && (p.t1 * p.t2) % 32 == 0;

@@ -107,7 +107,7 @@ class Engine:
         self.no_fused_attention = False
         # split-K workspace of the tcgen05 convolutions (WsrConvDesc.splitk_ws): counters (zero) + fp32 partial tiles; one per engine =
         # one per stream.  148 CTAs x 128 x 256 x 4 bytes = 19.4 MB is the most a launch can use.
-        self.splitk_ws = torch.zeros(4096 + 148 * 128 * 256 * 4, device=self.device, dtype=torch.uint8) if self.use_tc else None
+        self.splitk_ws = torch.zeros(32768 + 148 * 128 * 256 * 4, device=self.device, dtype=torch.uint8) if self.use_tc else None
 
     # ---- plumbing -------------------------------------------------------------------------------------------------
     def call(self, name, *args, flops=0, nbytes=0, tag=None, xflops=None):

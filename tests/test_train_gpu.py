@@ -321,6 +321,68 @@ def _train_backward(diff, g, spec):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_training_step_gradients_with_dropout_on_vs_oracle(precision):
+    """The REAL training configuration has dropout 0.2 in every block2 (nn_modules/resnet.py:23).  The CUDA path draws its masks from
+    Philox (seed, tag = res-block index, element); the masks are exported (wsr_dropout_mask) and the oracle -- pinned to the reference
+    on the dropout-free fixtures -- applies the SAME masks where the reference applies nn.Dropout, so all 396 parameter gradients can be
+    compared exactly (fp32: 2e-4 per tensor) instead of statistically."""
+    from conftest import manifest
+    from oracle import nets
+    from oracle.weights import seeded_state_dict
+    g, spec = load_golden("resdiff_grad_small"), CASES["resdiff_grad_small"]
+    cfg = dict(spec["cfg"])
+    cfg["dropout"] = 0.2
+    net, diff = _build(cfg, spec["seed"], precision)
+    assert net.training
+    B = g["hr"].shape[0]
+    dev = torch.device("cuda:0")
+    torch.manual_seed(77)
+    loss = _train_backward(diff, g, spec)
+    plan = net.train_plan(B, dev)
+    assert plan.drop_p == 0.2 and plan.drop_seed != 0
+    masks = []
+    frac = []
+    for r in plan._res_records():
+        m = torch.empty(B, r.h * r.w, r.cout, device=dev)
+        nat.call("wsr_dropout_mask", m.data_ptr(), B, r.h * r.w, r.cout, 0.2, plan.drop_seed, r.drop_tag, torch.cuda.current_stream().cuda_stream)
+        masks.append(m.view(B, r.h, r.w, r.cout).permute(0, 3, 1, 2).contiguous().cpu())
+        frac.append(float((masks[-1] == 0).float().mean()))
+    assert len(masks) == 27 or len(masks) == len(plan._res_records())
+    assert abs(sum(frac) / len(frac) - 0.2) < 0.01
+    sd = seeded_state_dict(manifest("resdiff", cfg), spec["seed"])
+    nets.DROP_MASKS = iter(masks)
+    try:
+        ref_loss, oracle_grads = process.arch_param_grads("resdiff", sd, cfg, g["hr"], g["sr"], g["level"], g["noise"])
+        assert next(nets.DROP_MASKS, None) is None                 # every mask consumed, in order
+    finally:
+        nets.DROP_MASKS = None
+    rel_loss = abs(loss - float(ref_loss)) / float(ref_loss)
+    # the masks really changed the problem: the dropout-free reference loss differs
+    assert abs(float(ref_loss) - float(g["loss"])) / float(g["loss"]) > 1e-3
+    named = dict(net.named_parameters())
+    tol_t, tol_all = (2e-4, 1e-4) if precision == "fp32" else (1.6e-1, 1.5e-1)
+    num = den = 0.0
+    bad = []
+    for n, p in named.items():
+        got, ref = p.grad.detach().cpu().double(), oracle_grads[n].double()
+        err, rn = float((got - ref).norm()), float(ref.norm())
+        num += err ** 2
+        den += rn ** 2
+    for n, p in named.items():
+        got, ref = p.grad.detach().cpu().double(), oracle_grads[n].double()
+        err, rn = float((got - ref).norm()), float(ref.norm())
+        tol_n = tol_t if (precision == "fp32" or ref.numel() >= 16) else 1.0
+        if err / max(rn, 1e-30) > tol_n and err > tol_t * 1e-3 * math.sqrt(den):
+            bad.append("%s rel %.3e" % (n, err / max(rn, 1e-30)))
+    total = math.sqrt(num / den)
+    print("\n[parity] training step with dropout 0.2 (exported Philox masks) %s: loss rel err %.3e, whole-gradient rel-L2 %.3e, %d / %d tensors out"
+          % (precision, rel_loss, total, len(bad), len(named)))
+    assert rel_loss < (1e-4 if precision == "fp32" else 2e-2)
+    assert not bad, bad[:10]
+    assert total < tol_all
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("arch", ["resdiff", "phydiff", "sr3"])
 def test_training_step_gradients_vs_reference(arch, precision):
     from oracle.cases import grad_summary
