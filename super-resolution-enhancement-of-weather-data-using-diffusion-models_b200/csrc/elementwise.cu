@@ -715,9 +715,11 @@ static int gn_apply_impl(const void* x, int x_dtype, int N, int HW, int C, int x
   }
   const int cpi = (HW + g.chunk - 1) / g.chunk;
   dim3 grid(cpi, N);
-  // range-reversed block order (see the kernel): on for tensors that do not fit the L2 anyway-hit regime, i.e. always harmless;
-  // WSR_GN_ORDER=0 restores the natural order (A/B measurements)
-  static const int order_on = getenv("WSR_GN_ORDER") ? atoi(getenv("WSR_GN_ORDER")) : 1;
+  // range-reversed block order (see the kernel).  MEASURED on B200 (A/B in one job, profiles/r02_gn_order_ab.txt): no effect -- the 65
+  // gn_apply launches of a B = 64 step take 3.09 ms reversed vs 3.03 ms in natural order, the whole step 16.64 vs 16.56 ms (3.53 vs 3.51
+  // ms at B = 8): the write-back L2 does not keep the producer's tail lines resident the way an LRU read cache would.  OFF unless
+  // WSR_GN_ORDER=1.
+  static const int order_on = getenv("WSR_GN_ORDER") ? atoi(getenv("WSR_GN_ORDER")) : 0;
   int nr = 0;
   if (order_on) {
     int sms = 0, dev = 0;

@@ -87,9 +87,16 @@ struct TcParams {
 };
 
 constexpr int kEpiWarps = 8;                      // two warps per TMEM lane quadrant, each owning half of the columns
-constexpr int kXfWarps = 4;                       // transform warps of the fused-GroupNorm kernels
+// Fused-GroupNorm kernels: 20 warps = 5 warpgroups.  Warpgroups 0-1 = the 8 epilogue warps, warpgroup 2 = TMA producer (warp 8), MMA
+// issuer (warp 9) and two idle warps, warpgroups 3-4 = 8 transform warps.  All warps of a kernel start with the same register
+// count (65536 / 640 -> 96), which neither fits the 168-register staged epilogue nor is needed by the single-thread roles, so the
+// warpgroups re-balance with setmaxnreg right after the common set-up: 168 / 40 / 64 registers (256*168 + 128*40 + 256*64 = 64512).
+// Round 1 ran 4 transform warps at the common 128-register cap: one warp per scheduler could not hide its own latencies
+// (0.30 ms for the transform alone on the 64->64 @128x256 layer) and the epilogue spilled.
+constexpr int kXfWarps = 8;                       // transform warps of the fused-GroupNorm kernels
+constexpr int kXfFirstWarp = 12;
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
-constexpr int kTcThreadsFused = kTcThreads + 32 * kXfWarps;
+constexpr int kTcThreadsFused = 32 * (kXfFirstWarp + kXfWarps);   // 640
 // halo tile of ROWS output rows: (ROWS + 2) x 130 pixels x 128 bytes, rounded up to a multiple of 1024
 constexpr int halo_stage_bytes(int rows) { return ((rows + 2) * 130 * 128 + 1023) / 1024 * 1024; }
 
@@ -172,7 +179,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
   // fused kernels: warps 10..13 are the transform warps.  They get the TOP ids: while they work the producer / MMA threads
   // mostly spin on barriers, and a spinning higher-priority warp on the same scheduler starved them (4x slower transform).
   constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
-  constexpr int kXfWarp0 = kEpiWarps + 2;
+  constexpr int kXfWarp0 = kXfFirstWarp;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.g1 * p.g2 * p.g3 * p.nbatch * p.n_tiles;
@@ -202,6 +209,8 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // FUSE: register re-balancing between the warpgroups (see kXfWarps) -- the setmaxnreg of each role is the FIRST statement of its
+  // branch below, so that the compiler sees which budget governs which code (every warp of a warpgroup executes the same value)
   // programmatic dependent launch: everything above touched only this CTA's shared / tensor memory and the (kernel-parameter)
   // tensor maps; from here on the kernel reads what earlier launches produced and overwrites what they may still be reading
   pdl_launch_dependents();
@@ -209,6 +218,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
 
   if (warp == kProducerWarp) {
     // ===================== TMA producer =====================
+    if constexpr (FUSE) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -288,6 +298,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
+    if constexpr (FUSE) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -414,6 +425,9 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
         }
       }
     }
+  } else if (FUSE && warp > kMmaWarp && warp < kXfWarp0) {
+    // the two spare warps of the producer / MMA warpgroup: give their registers back and leave
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   } else if (FUSE && warp >= kXfWarp0 && warp < kXfWarp0 + kXfWarps) {
     // ===================== transform warps (fused GroupNorm + activation of the input) =====================
     // The raw halo tile has been landed by TMA (zero-filled outside the image); each thread rewrites IN PLACE the 16-byte
@@ -421,9 +435,11 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
     // applies to the normalised tensor), then releases the stage to the MMA issuer.  (Fetching the tile with ordinary
     // loads instead was 4x slower: with 227 KB of shared memory carved out, L1 has almost no lines left for misses in flight.)
     if constexpr (FUSE) {
-      const int xt = threadIdx.x - 32 * kXfWarp0;           // 0..127
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+      constexpr int kXfRows = 4 * kXfWarps;                 // tile rows covered by one pass of the transform warps
+      const int xt = threadIdx.x - 32 * kXfWarp0;           // 0 .. 32 * kXfWarps - 1
       const int j = xt & 7;                                 // logical 16-byte column (8 channels) owned by this thread
-      const int r0 = xt >> 3;                               // first tile row; rows advance by 16
+      const int r0 = xt >> 3;                               // first tile row; rows advance by kXfRows
       const int pitch = p.t1 + 2;
       const int halo_rows = (ROWS + 2) * pitch;
       int sa = 0; uint32_t pa = 0;
@@ -444,23 +460,22 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
           mbar_wait(&full_raw[sa], pa);
           uint8_t* st = smem + sa * kHaloStage;
           int hy = r0 / pitch, hx = r0 - hy * pitch;
-          constexpr int U = 8;                              // shared-memory loads in flight per thread (their latency is
-                                                            // hundreds of cycles while the tensor core streams operands)
-          for (int rb = r0; rb < halo_rows; rb += 16 * U) {
+          constexpr int U = 4;                              // shared-memory loads in flight per thread (64 registers per thread)
+          for (int rb = r0; rb < halo_rows; rb += kXfRows * U) {
             uint4 raw[U];
             bool ok[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-              const int r = rb + 16 * u;
+              const int r = rb + kXfRows * u;
               ok[u] = r < halo_rows && hy >= hy_lo && hy < hy_hi && hx >= hx_lo && hx < hx_hi;
               if (ok[u]) raw[u] = *(const uint4*)(st + r * 128 + ((j ^ (r & 7)) << 4));
-              hx += 16;
+              hx += kXfRows;
               if (hx >= pitch) { hx -= pitch; ++hy; }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
               if (ok[u]) {
-                const int r = rb + 16 * u;
+                const int r = rb + kXfRows * u;
                 const __nv_bfloat162* h = (const __nv_bfloat162*)&raw[u];
                 uint4 o;
                 __nv_bfloat162* oh = (__nv_bfloat162*)&o;
@@ -492,6 +507,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
     }
   } else {
     // ===================== epilogue (warps 0..7) =====================
+    if constexpr (FUSE) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;          // row of the 128-row tile
     constexpr int kChunksPerWarp = BLOCK_N / 32 / (kEpiWarps / 4);
@@ -1028,16 +1044,19 @@ static int stage_mask() {
 
 template <int BLOCK_N>
 static int launch_tc(const TcParams& p, cudaStream_t st) {
+  const bool sok = stage_preconditions(p, BLOCK_N);
   if (p.n_taps > 0 && p.gn_tab != nullptr) {
-    if constexpr (BLOCK_N <= 64) {
-      if (p.halo_rows == 4) return launch_tc_impl<BLOCK_N, true, 4, true>(p, st);
+    // fused GroupNorm input: the same tile shapes as the plain halo kernels (vertical tap merge for N = 64, two rows for N = 128),
+    // staged epilogue whenever its preconditions hold
+    if constexpr (BLOCK_N == 64) {
+      if (p.halo_rows == 3) return sok ? launch_tc_impl<BLOCK_N, true, 3, true, true, true>(p, st) : launch_tc_impl<BLOCK_N, true, 3, true, true>(p, st);
     }
     if constexpr (BLOCK_N <= 128) {
-      if (p.halo_rows == 2) return launch_tc_impl<BLOCK_N, true, 2, true>(p, st);
+      if (p.halo_rows == 2) return sok ? launch_tc_impl<BLOCK_N, true, 2, true, false, true>(p, st) : launch_tc_impl<BLOCK_N, true, 2, true>(p, st);
     }
-    return launch_tc_impl<BLOCK_N, true, 1, true>(p, st);
+    WSR_REQUIRE(p.halo_rows == 1, WSR_E_INVALID, "conv_tc: fused GroupNorm input with %d halo rows", p.halo_rows);
+    return sok ? launch_tc_impl<BLOCK_N, true, 1, true, false, true>(p, st) : launch_tc_impl<BLOCK_N, true, 1, true>(p, st);
   }
-  const bool sok = stage_preconditions(p, BLOCK_N);
   if (p.n_taps > 0) {
     if constexpr (BLOCK_N == 64) {
       if (p.halo_rows == 3) {
@@ -1227,8 +1246,9 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
   }
   // vertical tap merge (N = 64, plain 3x3): three output rows per tile, needs the vmerge weight pack (w_vmerge)
   static const bool no_vm = getenv("WSR_NO_VMERGE") != nullptr;
-  const bool vmerge = halo && bn == 64 && taps == 9 && !d->upsample && d->w_vmerge != nullptr && d->gn_table == nullptr && !no_vm;
-  const int hrows = vmerge ? 3 : (halo && bn <= 64 && GH % 4 == 0 && max_rows >= 4) ? 4 : (halo && bn <= 128 && GH % 2 == 0 && max_rows >= 2) ? 2 : 1;
+  const bool vmerge = halo && bn == 64 && taps == 9 && !d->upsample && d->w_vmerge != nullptr && !no_vm;
+  // (the 4-row tiles have no shared memory left for the staged epilogue and are not built with the fused GroupNorm input)
+  const int hrows = vmerge ? 3 : (halo && bn <= 64 && GH % 4 == 0 && max_rows >= 4 && d->gn_table == nullptr) ? 4 : (halo && bn <= 128 && GH % 2 == 0 && max_rows >= 2) ? 2 : 1;
   WSR_REQUIRE(d->gn_table == nullptr || halo, WSR_E_UNSUPPORTED,
               "conv_tc: the fused GroupNorm input needs a stride-1 3x3 convolution on rows of >= 128 pixels (see wsr_conv_tc_can_fuse_gn)");
   if (d->gn_table) {

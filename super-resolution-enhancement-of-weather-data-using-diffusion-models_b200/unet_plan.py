@@ -507,7 +507,7 @@ class UNetPlan:
         ok = getattr(self, "_fuse_head", None)
         if ok is None:
             import os
-            ok = self._fuse_head = (type(self) is UNetPlan and self.eng.mode == "bf16" and self.eng.use_tc and not self.fuse_gn
+            ok = self._fuse_head = (type(self) is UNetPlan and self.eng.mode == "bf16" and self.eng.use_tc
                                     and os.environ.get("WSR_NO_FUSED_HEAD") is None
                                     and bool(nat.call("wsr_head_sampler_supported", self.final_cin, self.C_img, self.groups)))
         return ok
