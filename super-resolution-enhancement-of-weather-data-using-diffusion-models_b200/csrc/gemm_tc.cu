@@ -90,7 +90,10 @@ constexpr int kEpiWarps = 8;                      // two warps per TMEM lane qua
 // Fused-GroupNorm kernels: 20 warps = 5 warpgroups.  Warpgroups 0-1 = the 8 epilogue warps, warpgroup 2 = TMA producer (warp 8), MMA
 // issuer (warp 9) and two idle warps, warpgroups 3-4 = 8 transform warps.  All warps of a kernel start with the same register
 // count (65536 / 640 -> 96), which neither fits the 168-register staged epilogue nor is needed by the single-thread roles, so the
-// warpgroups re-balance with setmaxnreg right after the common set-up: 168 / 40 / 64 registers (256*168 + 128*40 + 256*64 = 64512).
+// warpgroups re-balance with setmaxnreg at the top of their role branches: 168 / 32 / 56 registers.  The increase can only be served
+// from registers the CTA itself gives back, so the budget is the LAUNCH allocation, not the register file:
+// 256*168 + 128*32 + 256*56 = 61440 = 640 * 96 exactly (a plan that sums to more than the launch allocation deadlocks in the
+// setmaxnreg.inc of the epilogue warps).
 // Round 1 ran 4 transform warps at the common 128-register cap: one warp per scheduler could not hide its own latencies
 // (0.30 ms for the transform alone on the 64->64 @128x256 layer) and the epilogue spilled.
 constexpr int kXfWarps = 8;                       // transform warps of the fused-GroupNorm kernels
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
   // STG: the epilogue moves residual loads and output stores through a per-warp shared-memory staging buffer (see TcCfg::kStgBytes);
   // the host selects it only when stage_preconditions() hold (bf16 output / residual, unit channel stride, 16-byte aligned rows)
   // register budget: 10 warps = 3 warps on the fullest scheduler, 16384 / 3 / 32 -> 168 registers per thread at most
+  static_assert(256 * 168 + 128 * 32 + 256 * 56 <= kTcThreadsFused * 96, "setmaxnreg plan exceeds the launch allocation");
   static_assert(!FUSE || HALO, "the fused-GroupNorm input path exists in halo mode only");
   static_assert(!VM || (HALO && BLOCK_N == 64), "vertical tap merge: halo mode, N = 64");
   using Cfg = TcCfg<BLOCK_N, HALO, ROWS, VM>;
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
 
   if (warp == kProducerWarp) {
     // ===================== TMA producer =====================
-    if constexpr (FUSE) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if constexpr (FUSE) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (lane == 0) {
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    if constexpr (FUSE) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if constexpr (FUSE) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (lane == 0) {
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -427,7 +431,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
     }
   } else if (FUSE && warp > kMmaWarp && warp < kXfWarp0) {
     // the two spare warps of the producer / MMA warpgroup: give their registers back and leave
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
   } else if (FUSE && warp >= kXfWarp0 && warp < kXfWarp0 + kXfWarps) {
     // ===================== transform warps (fused GroupNorm + activation of the input) =====================
     // The raw halo tile has been landed by TMA (zero-filled outside the image); each thread rewrites IN PLACE the 16-byte
@@ -435,7 +439,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
     // applies to the normalised tensor), then releases the stage to the MMA issuer.  (Fetching the tile with ordinary
     // loads instead was 4x slower: with 227 KB of shared memory carved out, L1 has almost no lines left for misses in flight.)
     if constexpr (FUSE) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
       constexpr int kXfRows = 4 * kXfWarps;                 // tile rows covered by one pass of the transform warps
       const int xt = threadIdx.x - 32 * kXfWarp0;           // 0 .. 32 * kXfWarps - 1
       const int j = xt & 7;                                 // logical 16-byte column (8 channels) owned by this thread
@@ -460,7 +464,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
           mbar_wait(&full_raw[sa], pa);
           uint8_t* st = smem + sa * kHaloStage;
           int hy = r0 / pitch, hx = r0 - hy * pitch;
-          constexpr int U = 4;                              // shared-memory loads in flight per thread (64 registers per thread)
+          constexpr int U = 4;                              // shared-memory loads in flight per thread (56 registers per thread)
           for (int rb = r0; rb < halo_rows; rb += kXfRows * U) {
             uint4 raw[U];
             bool ok[U];

@@ -5,9 +5,12 @@
 // with Cout padded 1 -> 64 (11 TFLOP/s: 63 of its 64 output columns are zeros) and the sampler step.  A Cout <= 4 convolution is a
 // 9 * Cin-term dot product per pixel, i.e. bandwidth-bound work: here every CTA loads a (4 + 2) x (128 + 2) pixel halo tile of the RAW
 // tensor once, applies GroupNorm + Swish on the way into shared memory (bf16, 16-byte chunks XOR-swizzled by pixel so that
-// neighbouring pixels hit different banks), and each thread accumulates the 9 * Cin products of two pixels in fp32 with the fp32
-// weights broadcast from shared memory; the epilogue is the sampler update, in place on the fp32 NCHW state.  Algorithmic traffic:
-// Cin * 2 bytes per pixel read (+ halo) and 12-16 bytes per pixel-channel for the state update.
+// neighbouring pixels hit different banks); the 9 * Cin products per pixel run on the warp-level tensor path (mma.sync m16n8k16, bf16
+// operands fetched with ldmatrix from the swizzled tile, the <= 4 output channels padded to n = 8, fp32 accumulation) -- a CUDA-core
+// version of the same loop issued 5x the instructions and was bound by them (0.34 ms at batch 64) -- and the epilogue is the sampler
+// update, in place on the fp32 NCHW state.  tcgen05 is the wrong tool here: its smallest tile (M = 128, N = 16) leaves the kernel
+// bound by the activation-operand fetch exactly as the Cout-padded convolution was.  Algorithmic traffic: Cin * 2 bytes per pixel
+// read (+ halo) and 12-16 bytes per pixel-channel for the state update.
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -41,15 +44,16 @@ __device__ __forceinline__ void head_randn4(uint64_t seed, uint32_t tag, uint64_
   z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
 }
 
-// shared memory: tile [Cin/64 planes][6 rows][130 cols][64 ch] bf16 | weights fp32 [9][Cout][Cin] | scale[Cin] shift[Cin] | group moments
+// shared memory: tile [Cin/64 planes][6 rows][130 cols][64 ch] bf16 | weights bf16 as ldmatrix-ready 8x8 blocks
+// [plane][tap][16-channel step][k half][n = 8 output channels (zero above Cout)][8 channels] | scale[Cin] shift[Cin] | group moments
 template <int COUT>
 __global__ void __launch_bounds__(kHeadThreads) head_sampler_kernel(const HeadParams p) {
   extern __shared__ __align__(16) uint8_t hsm[];
   constexpr int TR = kHeadRows + 2, TC = kHeadCols + 2;
   const int planes = p.Cin >> 6;
   uint8_t* tile = hsm;
-  float* wsm = (float*)(hsm + (size_t)planes * TR * TC * 128);
-  float* sc = wsm + 9 * COUT * p.Cin;
+  __nv_bfloat16* wsm = (__nv_bfloat16*)(hsm + (size_t)planes * TR * TC * 128);
+  float* sc = (float*)(wsm + (size_t)planes * 9 * 4 * 2 * 64);
   float* sh = sc + p.Cin;
   float* gm = sh + p.Cin;
   const int n = blockIdx.y;
@@ -85,7 +89,13 @@ __global__ void __launch_bounds__(kHeadThreads) head_sampler_kernel(const HeadPa
   pdl_launch_dependents();
   pdl_wait();
   issue(tid);
-  for (int i = tid; i < 9 * COUT * p.Cin; i += kHeadThreads) wsm[i] = p.w[i];
+  for (int i = tid; i < planes * 9 * 4 * 2 * 64; i += kHeadThreads) {
+    // i = ((((pl * 9 + tap) * 4 + kc) * 2 + h) * 8 + nn) * 8 + kk  ->  w[tap][nn][pl * 64 + kc * 16 + h * 8 + kk]
+    const int kk = i & 7, nn = (i >> 3) & 7, h = (i >> 6) & 1, kc = (i >> 7) & 3;
+    const int tp = i >> 9, tap = tp % 9, pl = tp / 9;
+    const float v = nn < COUT ? p.w[((long long)tap * COUT + nn) * p.Cin + pl * 64 + kc * 16 + h * 8 + kk] : 0.f;
+    wsm[i] = __float2bfloat16_rn(v);
+  }
   {
     const int cpg = p.Cin / p.groups;
     const long long HW = (long long)p.H * p.W;
@@ -136,46 +146,67 @@ __global__ void __launch_bounds__(kHeadThreads) head_sampler_kernel(const HeadPa
     }
   }
   __syncthreads();
-  // ---- 9 * Cin products per pixel: thread (r, j) owns pixels (r, j) and (r, j + 64) of the tile ----
-  const int r = tid >> 6, j = tid & 63;
-  float acc[2][COUT];
+  // ---- 9 * Cin products per pixel on mma.sync m16n8k16: warp w owns row w >> 1, columns (w & 1) * 64 .. + 63 = four 16-pixel M tiles ----
+  const int warp = tid >> 5, lane = tid & 31;
+  const int r = warp >> 1, cbase = (warp & 1) * 64;
+  float acc[4][4];
 #pragma unroll
-  for (int px = 0; px < 2; ++px)
+  for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[px][co] = p.bias ? p.bias[co] : 0.f;
+    for (int q = 0; q < 4; ++q) acc[mt][q] = 0.f;
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+  const uint32_t wsm_s = (uint32_t)__cvta_generic_to_shared(wsm);
+  // ldmatrix row addresses: A -- lane l supplies pixel (l & 7) + 8 * ((l >> 3) & 1) of the M tile, k half l >> 4;
+  //                         B -- lanes 0..15 supply row (l & 7) of k-half matrix (l >> 3) & 1
+  const int a_px = (lane & 7) + ((lane >> 3) & 1) * 8, a_kh = lane >> 4;
+  const uint32_t b_off = (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * 16);
   for (int pl = 0; pl < planes; ++pl) {
 #pragma unroll 1
     for (int tap = 0; tap < 9; ++tap) {
       const int dy = tap / 3, dx = tap - dy * 3;
-      const uint8_t* rowp = tile + ((size_t)(pl * TR + r + dy) * TC) * 128;
-      const int ca = j + dx, cb = j + 64 + dx;
-      const float* wt = wsm + (tap * COUT) * p.Cin + pl * 64;
+      const uint32_t rowp = tile_s + (uint32_t)(((pl * TR + r + dy) * TC) * 128);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint4 ua = *(const uint4*)(rowp + (size_t)ca * 128 + ((k ^ (ca & 7)) << 4));
-        const uint4 ub = *(const uint4*)(rowp + (size_t)cb * 128 + ((k ^ (cb & 7)) << 4));
-        float fa[8], fb[8];
-        const uint32_t* wa = (const uint32_t*)&ua;
-        const uint32_t* wb = (const uint32_t*)&ub;
+      for (int kc = 0; kc < 4; ++kc) {
+        uint32_t b0, b1;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1)
+                     : "r"(wsm_s + (uint32_t)((((pl * 9 + tap) * 4 + kc) * 2) * 128) + b_off));
+        const int chunk = kc * 2 + a_kh;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          fa[2 * q] = __uint_as_float(wa[q] << 16); fa[2 * q + 1] = __uint_as_float(wa[q] & 0xffff0000u);
-          fb[2 * q] = __uint_as_float(wb[q] << 16); fb[2 * q + 1] = __uint_as_float(wb[q] & 0xffff0000u);
-        }
-#pragma unroll
-        for (int co = 0; co < COUT; ++co) {
-          const float4 w0 = *(const float4*)(wt + co * p.Cin + k * 8);
-          const float4 w1 = *(const float4*)(wt + co * p.Cin + k * 8 + 4);
-          float a = acc[0][co], b = acc[1][co];
-          a = fmaf(fa[0], w0.x, a); a = fmaf(fa[1], w0.y, a); a = fmaf(fa[2], w0.z, a); a = fmaf(fa[3], w0.w, a);
-          a = fmaf(fa[4], w1.x, a); a = fmaf(fa[5], w1.y, a); a = fmaf(fa[6], w1.z, a); a = fmaf(fa[7], w1.w, a);
-          b = fmaf(fb[0], w0.x, b); b = fmaf(fb[1], w0.y, b); b = fmaf(fb[2], w0.z, b); b = fmaf(fb[3], w0.w, b);
-          b = fmaf(fb[4], w1.x, b); b = fmaf(fb[5], w1.y, b); b = fmaf(fb[6], w1.z, b); b = fmaf(fb[7], w1.w, b);
-          acc[0][co] = a; acc[1][co] = b;
+        for (int mt = 0; mt < 4; ++mt) {
+          const int col = cbase + mt * 16 + a_px + dx;
+          uint32_t a0, a1, a2, a3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                       : "r"(rowp + (uint32_t)(col * 128 + ((chunk ^ (col & 7)) << 4))));
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                       : "+f"(acc[mt][0]), "+f"(acc[mt][1]), "+f"(acc[mt][2]), "+f"(acc[mt][3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
         }
       }
     }
   }
+  // accumulator (m16n8): lane l holds pixels l >> 2 (c0, c1) and (l >> 2) + 8 (c2, c3) of each M tile for output channels 2 (l & 3), + 1.
+  // Re-distribute so that lane l owns pixels l and l + 32 of the warp's 64 (all output channels): pixel P = mt * 16 + q sits in
+  // lane (q & 7) * 4 + (co >> 1), register (q >> 3) * 2 + (co & 1) of M tile mt.
+  float outv[2][COUT];
+  {
+    const int q = lane & 15, want_hi = q >> 3, want_mt = lane >> 4;
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+      const int src = (q & 7) * 4 + (co >> 1);
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        float v = 0.f;
+#pragma unroll
+        for (int m2 = 0; m2 < 2; ++m2)
+#pragma unroll
+          for (int hi = 0; hi < 2; ++hi) {
+            const float cand = __shfl_sync(0xffffffffu, acc[px * 2 + m2][hi * 2 + (co & 1)], src);
+            if (m2 == want_mt && hi == want_hi) v = cand;
+          }
+        outv[px][co] = v + (p.bias ? p.bias[co] : 0.f);
+      }
+    }
+  }
+  const int j = cbase + lane;                      // tile column of this lane's first pixel; the second one is j + 32
   // ---- epilogue: eps_hat (optional) and the reverse-step update of the state, fp32 NCHW ----
   const int gy = y0 + r;
   if (gy >= p.H) return;
@@ -190,12 +221,12 @@ __global__ void __launch_bounds__(kHeadThreads) head_sampler_kernel(const HeadPa
   }
 #pragma unroll
   for (int px = 0; px < 2; ++px) {
-    const int gx = x0 + j + 64 * px;
+    const int gx = x0 + j + 32 * px;
     if (gx >= p.W) continue;
 #pragma unroll
     for (int co = 0; co < COUT; ++co) {
       const long long i = (((long long)n * COUT + co) * p.H + gy) * p.W + gx;
-      const float e = acc[px][co];
+      const float e = outv[px][co];
       if (p.eps_out) p.eps_out[i] = e;
       if (p.xs) {
         float zz = 0.f;
@@ -213,7 +244,8 @@ __global__ void __launch_bounds__(kHeadThreads) head_sampler_kernel(const HeadPa
 }
 
 static size_t head_smem_bytes(int Cin, int Cout, int groups) {
-  return (size_t)(Cin / 64) * (kHeadRows + 2) * (kHeadCols + 2) * 128 + (size_t)(9 * Cout * Cin + 2 * Cin + 2 * groups) * 4;
+  (void)Cout;
+  return (size_t)(Cin / 64) * (kHeadRows + 2) * (kHeadCols + 2) * 128 + (size_t)(Cin / 64) * 9 * 4 * 2 * 128 + (size_t)(2 * Cin + 2 * groups) * 4;
 }
 
 template <int COUT>

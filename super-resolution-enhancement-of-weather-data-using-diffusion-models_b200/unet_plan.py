@@ -475,6 +475,28 @@ class UNetPlan:
         e.gemm(wv.data_ptr(), e.dt, (0, cc, 1), nact.ptr, nact.dt, (n * nact.ld, nact.ld, 1),
                vT.data_ptr(), e.dt, (cc * n, n, 1), self.B, cc, n, cc)
 
+    def _side_stream(self):
+        """The HF-guided cross-attention branches (resdiff/unet.py:156-163: they only produce the SKIP tensors; the main path continues
+        with the un-attended x) run on a second stream, forked after each Downsample and joined before the up path: the N = 8192 /
+        2048 attention launches then overlap the deep levels of the down path, whose kernels leave most SMs idle at small batch.
+        Works eagerly and inside a captured CUDA graph (event fork / join).  Only when every branch launch is a fused kernel -- the
+        unfused fallback shares the score scratch with the main path's self-attention -- and not while per-launch timing is on."""
+        if not self.has_hfca or self.eng.prof is not None:
+            return None
+        ok = getattr(self, "_side_ok", None)
+        if ok is None:
+            import os
+            e = self.eng
+            ok = e.use_tc and e.mode == "bf16" and not e.no_fused_attention and os.environ.get("WSR_NO_SIDE_STREAM") is None
+            for ca in self.hfca:
+                n = ca.h * ca.w
+                fused_long = ca.c in (64, 128) and n % 128 == 0
+                fused_small = bool(nat.call("wsr_attention_small_tc_supported", n, n, ca.c))
+                ok = ok and (fused_long or fused_small)
+            self._side_ok = ok
+            self._side = torch.cuda.Stream(device=e.device) if ok else None
+        return self._side if ok else None
+
     def _hf_ca(self, ca):
         e, B = self.eng, self.B
         e.gn_apply(ca.x, ca.g, ca.b, 32, nat.ACT_NONE, ca.nbuf)       # norm_groups fixed at 32 (guided_cross_attention.py:15)
@@ -530,6 +552,7 @@ class UNetPlan:
         e, B = self.eng, self.B
         st = e.stream
         e.call("wsr_fill_zero", self.stats.data_ptr(), self.stats.numel() * 8, st)
+        main, side = torch.cuda.current_stream(e.device), self._side_stream()
         stem = self.downs[0]
         self._stem_input(x_t)
         x = e.conv(stem.xin, stem.conv, stem.y)
@@ -540,9 +563,22 @@ class UNetPlan:
             else:
                 x = e.conv(x, r.conv, r.y, stride=2, res=extra)
                 if self.has_hfca:
-                    self._hf_ca(r.ca)
+                    if side is None:
+                        self._hf_ca(r.ca)
+                    else:
+                        # fork: the branch only reads r.y (complete on the main stream at this point) and writes its own scratch and
+                        # the skip slot of an up-path concat buffer, which nothing touches before the join below
+                        ev = torch.cuda.Event()
+                        ev.record(main)
+                        side.wait_event(ev)
+                        with torch.cuda.stream(side):
+                            self._hf_ca(r.ca)
         for r in self.mids:
             x = self._res_block(r, x)
+        if side is not None:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            main.wait_event(ev)            # join: the up path consumes the skips written by the branch
         for r in self.ups:
             if r.kind == "res":
                 x = self._res_block(r, r.cat)
