@@ -381,15 +381,17 @@ int wsr_sampler_step(const float* x, const void* eps, int eps_dtype, const float
 /* The UNet head fused with the reverse step (SURVEY 8b `final_conv_sampler_step`): eps_hat = conv3x3(Swish(GroupNorm(x))) --
  * `final_conv` of resdiff/unet.py:119,177 (nn_modules/resnet.py:19-28 Block) -- followed, in the same kernel, by the update of
  * wsr_sampler_step on the fp32 NCHW state.  x: RAW (pre-GroupNorm) NHWC bf16 (B,H,W,Cin) with pitch x_ld; stats: the
- * per-(image, channel) (sum, sumsq) doubles the producing convolution emitted; w: fp32 [9][Cout][Cin]; eps_out (optional): fp32 NCHW
+ * per-(image, channel) (sum, sumsq) doubles the producing convolution emitted; w: the bf16 blocks made by wsr_pack_head_weight from
+ * the fp32 [9][Cout][Cin] packing ((Cin / 64) * 9216 bytes); eps_out (optional): fp32 NCHW
  * (B,Cout,H,W); x_state (optional): fp32 NCHW, updated in place with the same Philox stream layout / injected-noise addressing as
  * wsr_sampler_step.  Requires Cin % 64 == 0, Cout <= 4 (wsr_head_sampler_supported). */
 int wsr_final_conv_sampler_step(const void* x, int x_ld, int B, int H, int W, int Cin, const double* stats, int stats_ld,
-                                const float* gamma, const float* beta, int groups, float gn_eps, const float* w,
+                                const float* gamma, const float* beta, int groups, float gn_eps, const void* w,
                                 const float* bias, int Cout, float* eps_out, float* x_state, const float* z,
                                 int64_t z_step_stride, uint64_t seed, const float* tables, int T, const int* t_dev, int clip,
                                 void* stream);
 int wsr_head_sampler_supported(int Cin, int Cout, int groups);
+int wsr_pack_head_weight(const float* w_tap_cout_cin, int Cout, int Cin, void* dst, void* stream);
 /* out[b][:] = table[r][:] for b < B, r = *row_index (one row of the per-time-step projection table broadcast to the
  * batch; lets a captured CUDA graph follow the device-side step counter). */
 int wsr_broadcast_row(const float* table, int P, const int* row_index, int B, float* out, void* stream);

@@ -455,42 +455,58 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
         const int hy_lo = c2 - 1 < 0 ? 1 - c2 : 0, hy_hi = min(ROWS + 2, p.xg_H - (c2 - 1));
         const int hx_lo = c1 - 1 < 0 ? 1 - c1 : 0, hx_hi = min(pitch, p.xg_W - (c1 - 1));
         for (int c = 0; c < nch; ++c) {
-          float sc[8], sh[8];
+          // PACKED bf16x2 arithmetic: a = fma(x, scale, shift), swish(a) = h * tanh(h) + h with h = a / 2 -- four FMA-pipe and one SFU
+          // instruction per PAIR of channels.  The fp32 version of this loop (unpack, 2 FFMA, 2 x (FMUL, MUFU, FFMA), pack per pair;
+          // ~100 instructions per 16-byte vector with the address / predicate code) ran at ~0.15 instructions per clock per warp: the
+          // per-pair dependency chains did not fit the transform warps' 56 registers side by side, and the transform, not the tensor
+          // pipe, set the pace of the fused layers (ncu: issue 40 %, tensor 17 %, SFU 15 %; profiles/r02_ncu_fused_gn_fp32_transform.txt).
+          // Rounding: scale / shift and the intermediate a are rounded to bf16 (the unfused pass rounds only its output), i.e. about one
+          // extra bf16 rounding per activation -- inside the 2e-2 budget of the bf16 mode (tests/test_parity_*_gpu.py run with the fusion).
+          uint32_t sc2[4], sh2[4];
           {
             const float4* tp = (const float4*)(p.gn_tab + (long long)c3 * p.gn_ld + c * kBlockK + j * 8);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { float4 v = __ldg(tp + q); sc[2 * q] = v.x; sh[2 * q] = v.y; sc[2 * q + 1] = v.z; sh[2 * q + 1] = v.w; }
+            for (int q = 0; q < 4; ++q) {
+              const float4 v = __ldg(tp + q);                 // (scale, shift) of channels 2q, 2q + 1
+              __nv_bfloat162 s2 = __floats2bfloat162_rn(v.x, v.z), h2 = __floats2bfloat162_rn(v.y, v.w);
+              sc2[q] = *(uint32_t*)&s2; sh2[q] = *(uint32_t*)&h2;
+            }
           }
           mbar_wait(&full_raw[sa], pa);
-          uint8_t* st = smem + sa * kHaloStage;
+          const uint32_t st_s = smem_u32(smem + sa * kHaloStage);
           int hy = r0 / pitch, hx = r0 - hy * pitch;
-          constexpr int U = 4;                              // shared-memory loads in flight per thread (56 registers per thread)
+          constexpr int U = 4;                              // shared-memory loads in flight per thread
+          const bool swish = p.gn_act == WSR_ACT_SWISH;
           for (int rb = r0; rb < halo_rows; rb += kXfRows * U) {
-            uint4 raw[U];
+            uint32_t raw[U][4];
+            uint32_t addr[U];
             bool ok[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
               const int r = rb + kXfRows * u;
               ok[u] = r < halo_rows && hy >= hy_lo && hy < hy_hi && hx >= hx_lo && hx < hx_hi;
-              if (ok[u]) raw[u] = *(const uint4*)(st + r * 128 + ((j ^ (r & 7)) << 4));
+              addr[u] = st_s + (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
+              if (ok[u]) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(raw[u][0]), "=r"(raw[u][1]), "=r"(raw[u][2]), "=r"(raw[u][3]) : "r"(addr[u]));
               hx += kXfRows;
               if (hx >= pitch) { hx -= pitch; ++hy; }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
               if (ok[u]) {
-                const int r = rb + kXfRows * u;
-                const __nv_bfloat162* h = (const __nv_bfloat162*)&raw[u];
-                uint4 o;
-                __nv_bfloat162* oh = (__nv_bfloat162*)&o;
+                uint32_t o[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  float2 f = __bfloat1622float2(h[k]);
-                  float a0 = fmaf(f.x, sc[2 * k], sh[2 * k]), a1 = fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1]);
-                  if (p.gn_act == WSR_ACT_SWISH) { a0 = swish_fast(a0); a1 = swish_fast(a1); }
-                  oh[k] = __floats2bfloat162_rn(a0, a1);
+                  uint32_t a;
+                  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(a) : "r"(raw[u][k]), "r"(sc2[k]), "r"(sh2[k]));
+                  if (swish) {
+                    uint32_t h, t;
+                    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(h) : "r"(a), "r"(0x3f003f00u));      // 0.5, 0.5
+                    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t) : "r"(h));
+                    asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(a) : "r"(h), "r"(t));
+                  }
+                  o[k] = a;
                 }
-                *(uint4*)(st + r * 128 + ((j ^ (r & 7)) << 4)) = o;
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr[u]), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
               }
             }
           }

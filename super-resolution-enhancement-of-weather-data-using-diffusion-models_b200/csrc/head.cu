@@ -23,7 +23,7 @@ struct HeadParams {
   const __nv_bfloat16* x; int x_ld;       // raw (pre-GroupNorm) input, NHWC (B, H, W, Cin) bf16
   int B, H, W, Cin, Cout;
   const double* stats; int stats_ld; const float* gamma; const float* beta; int groups; float gn_eps;
-  const float* w;                          // fp32 [9][Cout][Cin]
+  const uint4* w;                          // bf16, ldmatrix-ready blocks (wsr_pack_head_weight), (Cin / 64) * 9 * 4 * 2 * 128 bytes
   const float* bias;                       // [Cout] or null
   float* eps_out;                          // fp32 NCHW (B, Cout, H, W) or null
   float* xs;                               // fp32 NCHW state x_t -> x_{t-1} in place, or null (convolution only)
@@ -89,13 +89,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_sampler_kernel(const HeadPa
   pdl_launch_dependents();
   pdl_wait();
   issue(tid);
-  for (int i = tid; i < planes * 9 * 4 * 2 * 64; i += kHeadThreads) {
-    // i = ((((pl * 9 + tap) * 4 + kc) * 2 + h) * 8 + nn) * 8 + kk  ->  w[tap][nn][pl * 64 + kc * 16 + h * 8 + kk]
-    const int kk = i & 7, nn = (i >> 3) & 7, h = (i >> 6) & 1, kc = (i >> 7) & 3;
-    const int tp = i >> 9, tap = tp % 9, pl = tp / 9;
-    const float v = nn < COUT ? p.w[((long long)tap * COUT + nn) * p.Cin + pl * 64 + kc * 16 + h * 8 + kk] : 0.f;
-    wsm[i] = __float2bfloat16_rn(v);
-  }
+  for (int i = tid; i < planes * 9 * 4 * 2 * 8; i += kHeadThreads) ((uint4*)wsm)[i] = __ldg(p.w + i);
   {
     const int cpg = p.Cin / p.groups;
     const long long HW = (long long)p.H * p.W;
@@ -243,6 +237,15 @@ __global__ void __launch_bounds__(kHeadThreads) head_sampler_kernel(const HeadPa
   }
 }
 
+// fp32 [9][Cout][Cin] (wsr_pack_conv_weight layout) -> bf16 blocks [plane][tap][16-channel step][k half][n = 8][8 channels], rows n >= Cout zero
+__global__ void pack_head_weight_kernel(const float* __restrict__ w, int Cout, int Cin, __nv_bfloat16* __restrict__ dst, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int kk = i & 7, nn = (i >> 3) & 7, h = (i >> 6) & 1, kc = (i >> 7) & 3;
+  const int tp = i >> 9, tap = tp % 9, pl = tp / 9;
+  dst[i] = __float2bfloat16_rn(nn < Cout ? w[((long long)tap * Cout + nn) * Cin + pl * 64 + kc * 16 + h * 8 + kk] : 0.f);
+}
+
 static size_t head_smem_bytes(int Cin, int Cout, int groups) {
   (void)Cout;
   return (size_t)(Cin / 64) * (kHeadRows + 2) * (kHeadCols + 2) * 128 + (size_t)(Cin / 64) * 9 * 4 * 2 * 128 + (size_t)(2 * Cin + 2 * groups) * 4;
@@ -270,8 +273,16 @@ extern "C" int wsr_head_sampler_supported(int Cin, int Cout, int groups) {
   return head_smem_bytes(Cin, Cout, groups) <= 227 * 1024 ? 1 : 0;
 }
 
+extern "C" int wsr_pack_head_weight(const float* w, int Cout, int Cin, void* dst, void* stream) {
+  WSR_REQUIRE(w && dst && Cout >= 1 && Cout <= kHeadMaxCout && Cin > 0 && Cin % 64 == 0, WSR_E_INVALID, "pack_head_weight: bad argument");
+  const int total = (Cin / 64) * 9 * 4 * 2 * 64;
+  pack_head_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, (__nv_bfloat16*)dst, total);
+  WSR_LAUNCH_OK();
+  return WSR_OK;
+}
+
 extern "C" int wsr_final_conv_sampler_step(const void* x, int x_ld, int B, int H, int W, int Cin, const double* stats, int stats_ld,
-                                           const float* gamma, const float* beta, int groups, float gn_eps, const float* w,
+                                           const float* gamma, const float* beta, int groups, float gn_eps, const void* w,
                                            const float* bias, int Cout, float* eps_out, float* x_state, const float* z,
                                            int64_t z_step_stride, uint64_t seed, const float* tables, int T, const int* t_dev,
                                            int clip, void* stream) {
@@ -286,7 +297,7 @@ extern "C" int wsr_final_conv_sampler_step(const void* x, int x_ld, int B, int H
   HeadParams p;
   p.x = (const __nv_bfloat16*)x; p.x_ld = x_ld; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.stats = stats; p.stats_ld = stats_ld; p.gamma = gamma; p.beta = beta; p.groups = groups; p.gn_eps = gn_eps;
-  p.w = w; p.bias = bias; p.eps_out = eps_out; p.xs = x_state; p.z = z; p.z_stride = z_step_stride; p.seed = seed;
+  p.w = (const uint4*)w; p.bias = bias; p.eps_out = eps_out; p.xs = x_state; p.z = z; p.z_stride = z_step_stride; p.seed = seed;
   p.tab = tables; p.T = T; p.t_dev = t_dev; p.clip = clip;
   cudaStream_t st = (cudaStream_t)stream;
   switch (Cout) {

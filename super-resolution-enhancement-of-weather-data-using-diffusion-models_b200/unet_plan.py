@@ -289,6 +289,13 @@ class UNetPlan:
             self.final = e.pack_conv(fc[3].weight, fc[3].bias, rows=64 if e.mode == "bf16" else None)
             # fp32 [9][Cout][Cin] copy of the head's weights for the fused head + reverse-step kernel (wsr_final_conv_sampler_step)
             self.final_f32 = self._pack_f32_conv(fc[3].weight) if e.mode == "bf16" else None
+            if self.final_f32 is not None and nat.call("wsr_head_sampler_supported", self.final_cin, self.C_img, self.groups):
+                # ldmatrix-ready bf16 blocks of the head's weights for wsr_final_conv_sampler_step
+                key = ("headw", fc[3].weight.data_ptr())
+                self.final_hw = e._pack_cache.get(key)
+                if self.final_hw is None:
+                    self.final_hw = e._pack_cache[key] = e.empty((self.final_cin // 64) * 9 * 4 * 2 * 64, torch.bfloat16)
+                nat.call("wsr_pack_head_weight", self.final_f32.w.data_ptr(), self.C_img, self.final_cin, self.final_hw.data_ptr(), e.stream)
             mlp = self.net.noise_level_mlp
             self.mlp_w1, self.mlp_b1 = e.f32(mlp[1].weight), e.f32(mlp[1].bias)
             self.mlp_w2, self.mlp_b2 = e.f32(mlp[3].weight), e.f32(mlp[3].bias)
@@ -540,7 +547,7 @@ class UNetPlan:
         assert feat.stats_ptr and feat.C == self.final_cin and feat.dt == nat.BF16
         npix = self.B * self.H * self.W
         e.call("wsr_final_conv_sampler_step", feat.ptr, feat.ld, self.B, self.H, self.W, feat.C, feat.stats_ptr, feat.st_ld,
-               self.gf.data_ptr(), self.bf_.data_ptr(), self.groups, 1e-5, self.final_f32.w.data_ptr(), self.final.bias.data_ptr(),
+               self.gf.data_ptr(), self.bf_.data_ptr(), self.groups, 1e-5, self.final_hw.data_ptr(), self.final.bias.data_ptr(),
                self.C_img, self.eps.data_ptr(), x_state.data_ptr(), 0 if z is None else z.data_ptr(), z_stride, seed, tab.data_ptr(), T,
                t_dev.data_ptr(), 1 if clip else 0, e.stream, tag="head_sampler",
                flops=2 * npix * 9 * feat.C * self.C_img, nbytes=npix * (feat.C * 2 + self.C_img * (16 if z is not None else 12)))

@@ -364,6 +364,9 @@ def test_final_conv_sampler_step_fused_vs_torch(case):
     wp = torch.empty(9, Cout, Cin, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     nat.call("wsr_pack_conv_weight", w.contiguous().data_ptr(), Cout, Cin, 3, 3, wp.data_ptr(), nat.F32, Cout, Cin, st)
+    wp32 = wp
+    wp = torch.empty((Cin // 64) * 9 * 4 * 2 * 64, device=dev, dtype=torch.bfloat16)
+    nat.call("wsr_pack_head_weight", wp32.data_ptr(), Cout, Cin, wp.data_ptr(), st)
     stats = torch.zeros(B, 2 * Cin, device=dev, dtype=torch.float64)
     nat.call("wsr_gn_stats", xa.ptr, xa.dt, B, H * W, Cin, xa.ld, stats.data_ptr(), 2 * Cin, st)
     ref_eps = F.conv2d(F.silu(F.group_norm(xq, 32, gamma, beta, 1e-5)), w, bias, padding=1)
@@ -571,9 +574,8 @@ FUSE_GN_CASES = [
 @pytest.mark.parametrize("out_bf16", [False, True])
 @pytest.mark.parametrize("case", FUSE_GN_CASES + [(2, 64, 64, 7, 256, 0), (1, 128, 64, 5, 128, 128), (3, 192, 128, 6, 256, 0)])
 def test_conv_tc_fused_groupnorm_input(case, out_bf16):
-    """GroupNorm + Swish applied inside the tcgen05 convolution (transform warps write the operand tile) against the
-    two-kernel path (wsr_gn_apply, then wsr_conv_tc) on the same raw tensor: both round the activation to bf16 once, so
-    the results agree to bf16 output rounding."""
+    """GroupNorm + Swish applied inside the tcgen05 convolution (transform warps rewrite the operand tile in shared memory)
+    against the two-kernel path (wsr_gn_apply, then wsr_conv_tc) on the same raw tensor."""
     N, Cin, Cout, H, W, Cin2 = case
     torch.manual_seed(11)
     dev = _dev()
@@ -614,7 +616,9 @@ def test_conv_tc_fused_groupnorm_input(case, out_bf16):
     torch.cuda.synchronize()
     got, ref = y.to_nchw(eng), y_ref.to_nchw(eng)
     err = rel_l2(got, ref)
-    assert err < (6e-3 if out_bf16 else 2e-3), err
+    # the fused transform works in packed bf16x2 arithmetic (scale / shift and the pre-activation are rounded to bf16; see gemm_tc.cu):
+    # about one extra bf16 rounding per activation relative to the two-kernel path
+    assert err < (8e-3 if out_bf16 else 5e-3), err
     if out_bf16:
         st = arena2.tensor.view(N, Cout, 2) / 2              # two launches accumulated into the same slot
         assert rel_l2(st[..., 0].float(), got.double().sum((2, 3)).float()) < 3e-3
