@@ -81,6 +81,7 @@ struct TcParams {
   // between launches (the last CTA of a tile restores the zeros).
   int ksplit, kb_split;
   float* ws; unsigned* ctr;
+  int prefetch;                 // halo mode: L2-prefetch the halo box two loads ahead (see the producer)
   const void* xg; int xg_ld, xg_H, xg_W;
   const void* x2g; int x2g_ld;
   const float2* gn_tab; int gn_ld; int gn_act;
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
   if (warp == kProducerWarp && lane == 0) {
     for (int i = 0; i < kNumAMaps; ++i) prefetch_tmap(&p.amap[i]);
     for (int i = 0; i < kNumBMaps; ++i) prefetch_tmap(&p.bmap[i]);
-    for (int s = 0; s < kRingA; ++s) { mbar_init(&full_a[s], FUSE ? 32 * kXfWarps : 1); mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < kRingA; ++s) { mbar_init(&full_a[s], FUSE ? kXfWarps : 1); mbar_init(&empty_a[s], 1); }
     for (int s = 0; s < kRingB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); mbar_init(&full_raw[a], 1); }
     fence_barrier_init();
@@ -260,6 +261,17 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
               mbar_wait(&empty_a[sa], pa ^ 1);
               mbar_expect_tx(fb, (uint32_t)p.halo_bytes);
               tma_load_4d(smem + sa * kHaloStage, &p.amap[p.e[0].amap], fb, c * kBlockK, c1 - 1, c2 - 1, c3);
+              if (p.prefetch) {
+                // the box that will land in this stage the NEXT time round (two halo loads ahead) goes to L2 now: with the transform
+                // between load and MMA a stage is refilled only after load + transform + MMA of its previous content, so the refill
+                // latency is on the critical path and should be an L2 hit, not an HBM round trip
+                const int idx = c + kRingA;
+                const int t2i = tile + idx / nch, c2i = idx % nch;
+                if (t2i < tile_end) {
+                  const TileCoord u = decode_tile(p, t2i);
+                  tma_prefetch_4d(&p.amap[p.e[0].amap], c2i * kBlockK, u.i1 * p.t1 - 1, u.i2 * ROWS - 1, u.i3 * p.t3 + u.zb * p.a_zmul);
+                }
+              }
               if (++sa == kRingA) { sa = 0; pa ^= 1; }
             }
             if constexpr (VM) {
@@ -510,8 +522,10 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
               }
             }
           }
+          // one arrival per WARP (256 per-thread arrivals on one shared-memory word serialise: ~1-2 us per stage)
           fence_proxy_async();
-          mbar_arrive(&full_a[sa]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_a[sa]);
           if (++sa == kRingA) { sa = 0; pa ^= 1; }
         }
         // fused 1x1 segment (ResnetBlock res_conv): the raw x2 tile passes through untouched
@@ -519,7 +533,8 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
           const int n2 = p.e[ei].nchunks;
           for (int c = 0; c < n2; ++c) {
             mbar_wait(&full_raw[sa], pa);
-            mbar_arrive(&full_a[sa]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_a[sa]);
             if (++sa == kRingA) { sa = 0; pa ^= 1; }
           }
         }
@@ -1280,6 +1295,11 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
   }
   p.n_taps = halo ? taps : 0;
   p.halo_rows = hrows;
+  {
+    // WSR_HALO_PREFETCH: 0 = never, 1 = fused-GroupNorm kernels only (default), 2 = every halo kernel
+    static const int pf = getenv("WSR_HALO_PREFETCH") ? atoi(getenv("WSR_HALO_PREFETCH")) : 1;
+    p.prefetch = halo && (pf >= 2 || (pf == 1 && d->gn_table != nullptr)) ? 1 : 0;
+  }
   p.halo_bytes = (p.t1 + 2) * (hrows + 2) * 128;
   if (halo) { p.g2 = cdiv(GH, hrows); p.a_bytes = p.t1 * hrows * 128; }
   const bool fuse_stats = d->gn_stats != nullptr && (halo ? p.t1 % 32 == 0 : (p.t1 * p.t2) % 32 == 0);
