@@ -181,6 +181,10 @@ int wsr_attention_tc(const void* q, int q_ld, const void* k, int k_ld, const voi
  * Requires Nq % 128 == 0, 64 <= Nk <= 512 with Nk % 64 == 0, 64 <= d <= 512 with d % 64 == 0 (wsr_attention_small_tc_supported). */
 int wsr_attention_small_tc(const void* q, int q_ld, const void* k, int k_ld, const void* vT, void* o, int o_ld, int B, int Nq,
                            int Nk, int d, float scale, void* stream);
+/* ... with V as it leaves the q | k | v projection convolution: (B, Nk, d) pixels x channels with pitch v_ld (an MN-major tcgen05
+ * operand; no V^T GEMM).  Same shape requirements; v_ld % 8 == 0. */
+int wsr_attention_small_nhwc_tc(const void* q, int q_ld, const void* k, int k_ld, const void* v, int v_ld, void* o, int o_ld, int B,
+                                int Nq, int Nk, int d, float scale, void* stream);
 int wsr_attention_small_tc_supported(int Nq, int Nk, int d);
 
 /* ConvTranspose2d(k=8, s=4, p=2) of srdiff/unet.py:43-45,118.  x NHWC (N,H,W,Cin); w packed [ky*8+kx][Cout][Cin];

@@ -103,6 +103,7 @@ SIGNATURES = {
     "wsr_gemm_tc": [C.POINTER(GemmDesc), _P],
     "wsr_attention_tc": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "wsr_attention_small_tc": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "wsr_attention_small_nhwc_tc": [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P],
     "wsr_attention_small_tc_supported": [_I, _I, _I],
     "wsr_conv_transpose_k8s4": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P],
     "wsr_gn_stats": [_P, _I, _I, _I, _I, _I, _P, _I, _P],

@@ -13,7 +13,10 @@
 //   phase 3  O[128 x d] = P V               O re-uses the TMEM columns of S (dead once P is written); V^T tiles streamed by TMA
 //   phase 4  O / rowsum -> bf16 -> global
 //
-// V is consumed TRANSPOSED (vT: B x d x Nk, produced that way by the K/V projection GEMM), so both P*V operands are K-major.
+// V comes either TRANSPOSED (vT: B x d x Nk, K-major like P) or -- v_mn -- as it leaves the q/k/v projection convolution,
+// pixels x channels (B x Nk x d with a pitch): tcgen05 takes such an MN-major B operand directly (instruction-descriptor bit 16; a TMA
+// box of [64 channels][64 keys] with the 128B swizzle is the canonical MN-major tile: 1 KB between 8-key atoms, 8 KB to the next 64
+// channels), so the sampling plan needs no V^T GEMM at all: one convolution produces q | k | v.
 // Shared memory is time-multiplexed: the phase-1 ring occupies the bytes that later hold P (<= 128 KB) and the V^T ring (3 x 32 KB).
 // Warp roles (320 threads): warps 0-7 softmax + epilogue (thread = query row x column half), warp 8 TMA producer, warp 9 TMEM
 // owner + single-thread MMA issuer.
@@ -41,6 +44,7 @@ struct AttnSmallParams {
   int kpieces, kbox;                      // Nk = kpieces * kbox, kbox <= 256 (one MMA / one TMA box per piece)
   int vpieces, vbox;                      // d = vpieces * vbox, vbox <= 256
   int stages1, stage1_bytes;              // phase-1 ring
+  int v_mn;                               // 1: V is (B, Nk, d) pixels x channels (MN-major B operand), 0: V^T (B, d, Nk)
   float c;                                // scale * log2(e)
 };
 
@@ -107,14 +111,23 @@ __global__ void __launch_bounds__(kSmThreads, 1) attn_small_tc_kernel(const __gr
           const int vs = idx % kSmVStages; const uint32_t ph = (uint32_t)(idx / kSmVStages) & 1;
           mbar_wait(&v_empty[vs], ph ^ 1);
           mbar_expect_tx(&v_full[vs], (uint32_t)(p.vbox * 128));
-          tma_load_3d(sV + vs * kSmVStage, &p.vmap, &v_full[vs], j * 64, h * p.vbox, b);
+          if (!p.v_mn) {
+            tma_load_3d(sV + vs * kSmVStage, &p.vmap, &v_full[vs], j * 64, h * p.vbox, b);
+          } else {
+            for (int jb = 0; jb < (p.vbox >> 6); ++jb)       // [64 channels][64 keys] boxes, 8 KB apart
+              tma_load_3d(sV + vs * kSmVStage + jb * 8192, &p.vmap, &v_full[vs], h * p.vbox + jb * 64, j * 64, b);
+          }
         }
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.kbox >> 3) << 17) | ((uint32_t)(kSmQ >> 4) << 24);
-      const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.vbox >> 3) << 17) | ((uint32_t)(kSmQ >> 4) << 24);
+      const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.vbox >> 3) << 17) | ((uint32_t)(kSmQ >> 4) << 24) |
+                                ((uint32_t)p.v_mn << 16);
+      // K-major V^T: +32 bytes per 16-key step, LBO unused; MN-major V: 16 key rows of 128 bytes per step, LBO = 8 KB (next 64 channels)
+      const uint32_t v_step = p.v_mn ? 128u : 2u;
+      const uint32_t v_lbo = p.v_mn ? ((8192u >> 4) << 16) : (1u << 16);
       const uint32_t kpiece_units = (uint32_t)(p.kbox * 128) >> 4;
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % S1; const uint32_t ph = (uint32_t)(c / S1) & 1;
@@ -140,10 +153,10 @@ __global__ void __launch_bounds__(kSmThreads, 1) attn_small_tc_kernel(const __gr
           const int vs = idx % kSmVStages; const uint32_t ph = (uint32_t)(idx / kSmVStages) & 1;
           mbar_wait(&v_full[vs], ph);
           tc_fence_after();
-          const uint32_t v_lo = desc_lo(smem_u32(sV + vs * kSmVStage));
+          const uint32_t v_lo = ((smem_u32(sV + vs * kSmVStage) & 0x3FFFFu) >> 4) | v_lbo;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_bf16_lo(tmem_base + (uint32_t)(h * p.vbox), p_lo + (uint32_t)(kk * 2), v_lo + (uint32_t)(kk * 2), idesc_pv, (j | kk) != 0 ? 1u : 0u);
+            umma_bf16_lo(tmem_base + (uint32_t)(h * p.vbox), p_lo + (uint32_t)(kk * 2), v_lo + (uint32_t)kk * v_step, idesc_pv, (j | kk) != 0 ? 1u : 0u);
           umma_commit(&v_empty[vs]);
         }
       }
@@ -250,8 +263,24 @@ extern "C" int wsr_attention_small_tc_supported(int Nq, int Nk, int d) {
   return 1;
 }
 
+static int attention_small_impl(const void* q, int q_ld, const void* k, int k_ld, const void* vT, int v_ld, void* o, int o_ld, int B,
+                                int Nq, int Nk, int d, float scale, void* stream);
+
 extern "C" int wsr_attention_small_tc(const void* q, int q_ld, const void* k, int k_ld, const void* vT, void* o, int o_ld, int B,
                                       int Nq, int Nk, int d, float scale, void* stream) {
+  return attention_small_impl(q, q_ld, k, k_ld, vT, 0, o, o_ld, B, Nq, Nk, d, scale, stream);
+}
+
+extern "C" int wsr_attention_small_nhwc_tc(const void* q, int q_ld, const void* k, int k_ld, const void* v, int v_ld, void* o, int o_ld,
+                                           int B, int Nq, int Nk, int d, float scale, void* stream) {
+  WSR_REQUIRE(v_ld % 8 == 0 && v_ld >= d, WSR_E_UNSUPPORTED, "attention_small_nhwc_tc: v pitch");
+  WSR_REQUIRE(d > 0 && (d / ((d + 255) / 256)) % 64 == 0, WSR_E_UNSUPPORTED, "attention_small_nhwc_tc: d=%d (the channel pieces must be multiples of 64)", d);
+  return attention_small_impl(q, q_ld, k, k_ld, v, v_ld, o, o_ld, B, Nq, Nk, d, scale, stream);
+}
+
+// v_ld == 0: vT is V transposed (B, d, Nk); v_ld > 0: V as (B, Nk, d) with pitch v_ld
+static int attention_small_impl(const void* q, int q_ld, const void* k, int k_ld, const void* vT, int v_ld, void* o, int o_ld, int B,
+                                int Nq, int Nk, int d, float scale, void* stream) {
   WSR_REQUIRE(q && k && vT && o, WSR_E_INVALID, "attention_small_tc: null pointer");
   WSR_REQUIRE(B > 0 && B <= 65535 && Nq > 0 && Nk > 0, WSR_E_INVALID, "attention_small_tc: bad shape");
   WSR_REQUIRE(wsr_attention_small_tc_supported(Nq, Nk, d), WSR_E_UNSUPPORTED,
@@ -280,10 +309,16 @@ extern "C" int wsr_attention_small_tc(const void* q, int q_ld, const void* k, in
     uint32_t box[3] = {64, (uint32_t)p.kbox, 1};
     if ((rc = encode_map(&p.kmap, k, 3, dims, str, box))) return rc;
   }
-  {
+  p.v_mn = v_ld > 0 ? 1 : 0;
+  if (!p.v_mn) {
     uint64_t dims[3] = {(uint64_t)Nk, (uint64_t)d, (uint64_t)B};
     uint64_t str[2] = {(uint64_t)Nk * 2, (uint64_t)d * Nk * 2};
     uint32_t box[3] = {64, (uint32_t)p.vbox, 1};
+    if ((rc = encode_map(&p.vmap, vT, 3, dims, str, box))) return rc;
+  } else {
+    uint64_t dims[3] = {(uint64_t)d, (uint64_t)Nk, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)v_ld * 2, (uint64_t)Nk * v_ld * 2};
+    uint32_t box[3] = {64, 64, 1};
     if ((rc = encode_map(&p.vmap, vT, 3, dims, str, box))) return rc;
   }
   p.o = o; p.o_sb = (long long)Nq * o_ld; p.o_ld = o_ld;

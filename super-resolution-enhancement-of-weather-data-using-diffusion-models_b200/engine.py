@@ -521,10 +521,23 @@ class Engine:
         return y
 
     # ---- attention (single head, dense softmax; nn_modules/resnet.py:81-100, guided_cross_attention.py:24-44) --------
-    def attention(self, q, k, vT, o, scores, probs):
+    def small_attention_takes_nhwc_v(self, Nq, Nk, Cc):
+        """True when the fused low-resolution attention kernel can consume V as pixels x channels (no V^T GEMM)."""
+        return (self.use_tc and not self.no_fused_attention and bool(nat.call("wsr_attention_small_tc_supported", Nq, Nk, Cc))
+                and (Cc // ((Cc + 255) // 256)) % 64 == 0)
+
+    def attention(self, q, k, vT, o, scores, probs, v=None):
         """q, k: Act (B, H, W, C) row-major pixels x channels; vT: tensor (B, C, Nk) (V transposed, K-major for P*V);
-        o: Act (B, H, W, C).  scores/probs: scratch tensors (B, Nq, Nk)."""
+        o: Act (B, H, W, C).  scores/probs: scratch tensors (B, Nq, Nk).  v: alternatively V as an Act (pixels x channels, e.g. a slice
+        of the q | k | v projection) -- only for shapes with ``small_attention_takes_nhwc_v``."""
         B, Nq, Nk, Cc = q.N, q.H * q.W, k.H * k.W, q.C
+        if v is not None:
+            assert vT is None and self.small_attention_takes_nhwc_v(Nq, Nk, Cc) and v.dt == nat.BF16 and v.ld % 8 == 0 and v.ptr % 16 == 0
+            self.n_tc += 1
+            self.call("wsr_attention_small_nhwc_tc", q.ptr, q.ld, k.ptr, k.ld, v.ptr, v.ld, o.ptr, o.ld, B, Nq, Nk, Cc,
+                      1.0 / math.sqrt(Cc), self.stream, flops=4 * B * Nq * Nk * Cc,
+                      tag="attn_small_tc" if not self.prof_detail else "attn_small_tc N%d d%d" % (Nk, Cc))
+            return o
         if (self.use_tc and not self.no_fused_attention and Cc in (64, 128) and Nq % 128 == 0 and Nk % 128 == 0
                 and q.dt == nat.BF16 and k.dt == nat.BF16 and o.dt == nat.BF16 and q.ld % 8 == 0 and k.ld % 8 == 0
                 and o.ld % 8 == 0 and q.ptr % 16 == 0 and k.ptr % 16 == 0 and o.ptr % 16 == 0):

@@ -135,10 +135,17 @@ class UNetPlan:
                 n = r.h * r.w
                 r.rbuf = e.new_act(B, r.h, r.w, r.cout, stats=arena)
                 r.nbuf = e.new_act(B, r.h, r.w, r.cout)
-                r.qk = e.new_act(B, r.h, r.w, 2 * r.cout)
-                r.vT = e.empty((B, r.cout, n))
+                # sampling plans at the low-resolution levels: ONE q | k | v projection, V consumed as pixels x channels by the fused
+                # attention kernel (no V^T GEMM); the train plan keeps q | k + V^T (its backward pass reads them)
+                r.v_nhwc = self._plain_plan() and bf and e.small_attention_takes_nhwc_v(n, n, r.cout)
+                if r.v_nhwc:
+                    r.qkv = e.new_act(B, r.h, r.w, 3 * r.cout)
+                    r.qk, r.vT = r.qkv.slice(0, 2 * r.cout), None
+                else:
+                    r.qk = e.new_act(B, r.h, r.w, 2 * r.cout)
+                    r.vT = e.empty((B, r.cout, n))
+                    max_scores = max(max_scores, B * n * n)
                 r.obuf = e.new_act(B, r.h, r.w, r.cout)
-                max_scores = max(max_scores, B * n * n)
 
         # down path
         hf_i = 0
@@ -158,12 +165,18 @@ class UNetPlan:
                     n = r.h * r.w
                     ca = _L(mod=self.net.hf_ca_list[hf_i], c=r.cout, h=r.h, w=r.w, x=r.y, y=feat_dst[i], level=hf_i)
                     ca.nbuf = e.new_act(B, r.h, r.w, r.cout)
-                    ca.kbuf = e.new_act(B, r.h, r.w, r.cout)
-                    ca.vT = e.empty((B, r.cout, n))
+                    ca.v_nhwc = self._plain_plan() and bf and e.small_attention_takes_nhwc_v(n, n, r.cout)
+                    if ca.v_nhwc:
+                        ca.kv = e.new_act(B, r.h, r.w, 2 * r.cout)           # one k | v projection
+                        ca.kbuf, ca.vT = ca.kv.slice(0, r.cout), None
+                    else:
+                        ca.kbuf = e.new_act(B, r.h, r.w, r.cout)
+                        ca.vT = e.empty((B, r.cout, n))
                     ca.obuf = e.new_act(B, r.h, r.w, r.cout)
                     ca.q = e.new_act(B, r.h, r.w, r.cout)
                     ca.qimg = e.new_act(B, r.h, r.w, self.C_img * (3 if self.kind == "phydiff" else 1), dt=nat.F32)
-                    max_scores = max(max_scores, B * n * n)
+                    if not ca.v_nhwc:
+                        max_scores = max(max_scores, B * n * n)
                     r.ca = ca
                     self.hfca.append(ca)
                     hf_i += 1
@@ -258,8 +271,11 @@ class UNetPlan:
                     r.g3, r.b3 = e.f32(at.norm.weight), e.f32(at.norm.bias)
                     wqkv = at.qkv.weight
                     cc = r.cout
-                    r.wqk = e.pack_conv(wqkv[:2 * cc], None)
-                    r.wv = e.pack_rows(wqkv[2 * cc:].reshape(cc, cc))
+                    if r.v_nhwc:
+                        r.wqkv = e.pack_conv(wqkv, None)
+                    else:
+                        r.wqk = e.pack_conv(wqkv[:2 * cc], None)
+                        r.wv = e.pack_rows(wqkv[2 * cc:].reshape(cc, cc))
                     r.wout = e.pack_conv(at.out.weight, at.out.bias)
 
             for r in self.downs:
@@ -273,8 +289,11 @@ class UNetPlan:
                         ca, m = r.ca, r.ca.mod
                         ca.g, ca.b = e.f32(m.norm.weight), e.f32(m.norm.bias)
                         cc = ca.c
-                        ca.wk = e.pack_conv(m.kv.weight[:cc], None)
-                        ca.wv = e.pack_rows(m.kv.weight[cc:].reshape(cc, cc))
+                        if ca.v_nhwc:
+                            ca.wkv = e.pack_conv(m.kv.weight, None)
+                        else:
+                            ca.wk = e.pack_conv(m.kv.weight[:cc], None)
+                            ca.wv = e.pack_rows(m.kv.weight[cc:].reshape(cc, cc))
                         ca.wout = e.pack_conv(m.out.weight, m.out.bias)
                         ca.wq = self._pack_f32_conv(m.q.weight)
             for r in self.mids:
@@ -463,11 +482,15 @@ class UNetPlan:
             e.conv(a2, r.conv2, dst, res=x, res2=er, gn=gn2)
         if r.attn:
             e.gn_apply(r.rbuf, r.g3, r.b3, G, nat.ACT_NONE, r.nbuf)
-            e.conv(r.nbuf, r.wqk, r.qk, bias=False)
-            self._v_transposed(r.wv, r.nbuf, r.vT)
             n = r.h * r.w
-            e.attention(r.qk.slice(0, r.cout), r.qk.slice(r.cout, r.cout), r.vT, r.obuf,
-                        self.scores[:B * n * n], self.probs[:B * n * n])
+            if r.v_nhwc:
+                e.conv(r.nbuf, r.wqkv, r.qkv, bias=False)
+                e.attention(r.qkv.slice(0, r.cout), r.qkv.slice(r.cout, r.cout), None, r.obuf, None, None, v=r.qkv.slice(2 * r.cout, r.cout))
+            else:
+                e.conv(r.nbuf, r.wqk, r.qk, bias=False)
+                self._v_transposed(r.wv, r.nbuf, r.vT)
+                e.attention(r.qk.slice(0, r.cout), r.qk.slice(r.cout, r.cout), r.vT, r.obuf,
+                            self.scores[:B * n * n], self.probs[:B * n * n])
             e.conv(r.obuf, r.wout, r.y, res=r.rbuf, res2=extra_res)
         return r.y
 
@@ -481,6 +504,11 @@ class UNetPlan:
         cc, n = wv.shape[0], nact.H * nact.W
         e.gemm(wv.data_ptr(), e.dt, (0, cc, 1), nact.ptr, nact.dt, (n * nact.ld, nact.ld, 1),
                vT.data_ptr(), e.dt, (cc * n, n, 1), self.B, cc, n, cc)
+
+    def _plain_plan(self):
+        """The sampling / inference plan (not the train plan, whose backward pass reads q | k and V^T separately)."""
+        import os
+        return type(self) is UNetPlan and os.environ.get("WSR_NO_NHWC_V") is None
 
     def _side_stream(self):
         """The HF-guided cross-attention branches (resdiff/unet.py:156-163: they only produce the SKIP tensors; the main path continues
@@ -507,10 +535,14 @@ class UNetPlan:
     def _hf_ca(self, ca):
         e, B = self.eng, self.B
         e.gn_apply(ca.x, ca.g, ca.b, 32, nat.ACT_NONE, ca.nbuf)       # norm_groups fixed at 32 (guided_cross_attention.py:15)
-        e.conv(ca.nbuf, ca.wk, ca.kbuf, bias=False)
-        self._v_transposed(ca.wv, ca.nbuf, ca.vT)
         n = ca.h * ca.w
-        e.attention(ca.q, ca.kbuf, ca.vT, ca.obuf, self.scores[:B * n * n], self.probs[:B * n * n])
+        if ca.v_nhwc:
+            e.conv(ca.nbuf, ca.wkv, ca.kv, bias=False)
+            e.attention(ca.q, ca.kbuf, None, ca.obuf, None, None, v=ca.kv.slice(ca.c, ca.c))
+        else:
+            e.conv(ca.nbuf, ca.wk, ca.kbuf, bias=False)
+            self._v_transposed(ca.wv, ca.nbuf, ca.vT)
+            e.attention(ca.q, ca.kbuf, ca.vT, ca.obuf, self.scores[:B * n * n], self.probs[:B * n * n])
         e.conv(ca.obuf, ca.wout, ca.y, res=ca.x)
 
     def _stem_input(self, x_t):
