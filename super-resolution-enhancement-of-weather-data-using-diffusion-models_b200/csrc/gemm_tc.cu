@@ -91,9 +91,9 @@ constexpr int kEpiWarps = 8;                      // two warps per TMEM lane qua
 // Fused-GroupNorm kernels: 20 warps = 5 warpgroups.  Warpgroups 0-1 = the 8 epilogue warps, warpgroup 2 = TMA producer (warp 8), MMA
 // issuer (warp 9) and two idle warps, warpgroups 3-4 = 8 transform warps.  All warps of a kernel start with the same register
 // count (65536 / 640 -> 96), which neither fits the 168-register staged epilogue nor is needed by the single-thread roles, so the
-// warpgroups re-balance with setmaxnreg at the top of their role branches: 168 / 32 / 56 registers.  The increase can only be served
+// warpgroups re-balance with setmaxnreg at the top of their role branches: 168 / 40 / 48 registers.  The increase can only be served
 // from registers the CTA itself gives back, so the budget is the LAUNCH allocation, not the register file:
-// 256*168 + 128*32 + 256*56 = 61440 = 640 * 96 exactly (a plan that sums to more than the launch allocation deadlocks in the
+// 256*168 + 128*40 + 256*48 = 60416 <= 640 * 96 = 61440 (a plan that sums to more than the launch allocation deadlocks in the
 // setmaxnreg.inc of the epilogue warps).
 // Round 1 ran 4 transform warps at the common 128-register cap: one warp per scheduler could not hide its own latencies
 // (0.30 ms for the transform alone on the 64->64 @128x256 layer) and the epilogue spilled.
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
   // STG: the epilogue moves residual loads and output stores through a per-warp shared-memory staging buffer (see TcCfg::kStgBytes);
   // the host selects it only when stage_preconditions() hold (bf16 output / residual, unit channel stride, 16-byte aligned rows)
   // register budget: 10 warps = 3 warps on the fullest scheduler, 16384 / 3 / 32 -> 168 registers per thread at most
-  static_assert(256 * 168 + 128 * 32 + 256 * 56 <= kTcThreadsFused * 96, "setmaxnreg plan exceeds the launch allocation");
+  static_assert(256 * 168 + 128 * 40 + 256 * 48 <= kTcThreadsFused * 96, "setmaxnreg plan exceeds the launch allocation");
   static_assert(!FUSE || HALO, "the fused-GroupNorm input path exists in halo mode only");
   static_assert(!VM || (HALO && BLOCK_N == 64), "vertical tap merge: halo mode, N = 64");
   using Cfg = TcCfg<BLOCK_N, HALO, ROWS, VM>;
@@ -176,7 +176,15 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
   uint64_t* tfull_bar = empty_b + kRingB;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* full_raw = tempty_bar + 2;                       // FUSE: TMA landed the raw tile (transform warps wait on it)
-  uint32_t* tmem_slot = (uint32_t*)(full_raw + 2);
+  // FUSE, halo chunks: the stage is handed over ROW BY ROW -- row_raw[stage][h]: halo row h has landed (one TMA box per row);
+  // row_rdy[stage][h]: the transform warps have rewritten it.  With whole-stage barriers a stage went load -> transform -> MMA
+  // strictly one after the other (~5 + 2.4 + 3.5 us per 83 KB stage of the 64->64 layer), and two stages cannot hide three serial
+  // phases: the fused layer ran at the speed of conv + separate GroupNorm pass.  Row by row the three phases overlap inside a stage.
+  constexpr int kRowMax = 6;
+  uint64_t* row_raw = full_raw + 2;                          // [2][kRowMax]
+  uint64_t* row_rdy = row_raw + 2 * kRowMax;                 // [2][kRowMax]
+  uint32_t* tmem_slot = (uint32_t*)(row_rdy + 2 * kRowMax);
+  static_assert(!FUSE || ROWS + 2 <= kRowMax, "row barriers");
   uint8_t* smem_b = smem + Cfg::kAStages * kHaloStage;      // halo mode only
 
   // warp roles: 0..7 epilogue, 8 TMA producer, 9 MMA issuer.  The issue arbiter favours the HIGHEST warp id on an SMSP, so
@@ -203,6 +211,9 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
     for (int s = 0; s < kRingA; ++s) { mbar_init(&full_a[s], FUSE ? kXfWarps : 1); mbar_init(&empty_a[s], 1); }
     for (int s = 0; s < kRingB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); mbar_init(&full_raw[a], 1); }
+    if constexpr (FUSE) {
+      for (int i = 0; i < 2 * kRowMax; ++i) { mbar_init(&row_raw[i], 1); mbar_init(&row_rdy[i], kXfWarps); }
+    }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -223,7 +234,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
 
   if (warp == kProducerWarp) {
     // ===================== TMA producer =====================
-    if constexpr (FUSE) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if constexpr (FUSE) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -257,10 +268,18 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
           const int nch = p.e[0].nchunks;
           for (int c = 0; c < nch; ++c) {
             {
-              uint64_t* fb = FUSE ? &full_raw[sa] : &full_a[sa];
               mbar_wait(&empty_a[sa], pa ^ 1);
-              mbar_expect_tx(fb, (uint32_t)p.halo_bytes);
-              tma_load_4d(smem + sa * kHaloStage, &p.amap[p.e[0].amap], fb, c * kBlockK, c1 - 1, c2 - 1, c3);
+              if constexpr (FUSE) {
+                // one box per halo row (amap[1]: the same tensor, box = one row of t1 + 2 pixels), each on its own barrier
+                const int row_bytes = (p.t1 + 2) * 128;
+                for (int h = 0; h < ROWS + 2; ++h) {
+                  mbar_expect_tx(&row_raw[sa * kRowMax + h], (uint32_t)row_bytes);
+                  tma_load_4d(smem + sa * kHaloStage + h * row_bytes, &p.amap[1], &row_raw[sa * kRowMax + h], c * kBlockK, c1 - 1, c2 - 1 + h, c3);
+                }
+              } else {
+                mbar_expect_tx(&full_a[sa], (uint32_t)p.halo_bytes);
+                tma_load_4d(smem + sa * kHaloStage, &p.amap[p.e[0].amap], &full_a[sa], c * kBlockK, c1 - 1, c2 - 1, c3);
+              }
               if (p.prefetch) {
                 // the box that will land in this stage the NEXT time round (two halo loads ahead) goes to L2 now: with the transform
                 // between load and MMA a stage is refilled only after load + transform + MMA of its previous content, so the refill
@@ -314,9 +333,10 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    if constexpr (FUSE) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if constexpr (FUSE) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      uint32_t ph_row = 0u, ph_x2 = 0u;     // FUSE: per-stage phase bits (bit = stage) of the row barriers / of full_a (x2 uses)
       int it = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
         const int acc = it & 1;
@@ -351,7 +371,17 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
           const int nch = p.e[0].nchunks;
           const int pitch = p.t1 + 2;
           for (int c = 0; c < nch; ++c) {
-            mbar_wait(&full_a[sa], pa);
+            // FUSE: rows become readable one by one (row_rdy); `rows_ok` = halo rows of this stage already waited for
+            int rows_ok = 0;
+            auto need_rows = [&](int upto) {          // make halo rows [0, upto) of the current stage readable
+              if constexpr (FUSE) {
+                if (rows_ok < upto) {
+                  for (; rows_ok < upto; ++rows_ok) mbar_wait(&row_rdy[sa * kRowMax + rows_ok], (ph_row >> sa) & 1u);
+                  tc_fence_after();
+                }
+              }
+            };
+            if constexpr (!FUSE) mbar_wait(&full_a[sa], pa);
             const uint32_t a_lo0 = desc_lo(smem_u32(smem + sa * kHaloStage));
             const uint32_t pitch8 = (uint32_t)pitch * 8u;
             if constexpr (VM) {
@@ -367,15 +397,23 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
                     if (kb == 0 && k == 0) {
                       // very first K step of the tile: every accumulator block starts from zero, which a merged MMA cannot
                       // express (one accumulate flag per instruction) -> nine plain N = 64 MMAs, first touch overwrites
+                      // (issued in halo-row order so that the fused-GroupNorm kernels can start as soon as row 0 is transformed; output
+                      // row rr is still first touched by its dy = -1 tap, halo row rr)
 #pragma unroll
-                      for (int rr = 0; rr < ROWS; ++rr)
+                      for (int hr = 0; hr < ROWS + 2; ++hr) {
+                        need_rows(hr + 1);
 #pragma unroll
-                        for (int dyi = 0; dyi < 3; ++dyi)      // dy = dyi - 1 reads halo row rr + dyi; weights block 2 - dyi
-                          umma_bf16_lo(d_tmem + (uint32_t)(rr * 64), v_lo + (uint32_t)(rr + dyi) * pitch8, b_lo + (uint32_t)(2 - dyi) * 512u,
-                                       kIdBase | (8u << 17), dyi != 0 ? 1u : 0u);
+                        for (int dyi = 0; dyi < 3; ++dyi) {      // dy = dyi - 1 reads halo row rr + dyi; weights block 2 - dyi
+                          const int rr = hr - dyi;
+                          if (rr >= 0 && rr < ROWS)
+                            umma_bf16_lo(d_tmem + (uint32_t)(rr * 64), v_lo + (uint32_t)hr * pitch8, b_lo + (uint32_t)(2 - dyi) * 512u,
+                                         kIdBase | (8u << 17), dyi != 0 ? 1u : 0u);
+                        }
+                      }
                     } else {
 #pragma unroll
                       for (int hr = 0; hr < ROWS + 2; ++hr) {
+                        need_rows(hr + 1);
                         // halo row hr feeds output rows hr-2 (dy=+1, block 0), hr-1 (dy=0, block 1), hr (dy=-1, block 2)
                         const int r_lo = hr - 2 < 0 ? 0 : hr - 2, r_hi = hr < ROWS - 1 ? hr : ROWS - 1;
                         const int nblk = r_hi - r_lo + 1, blk0 = r_lo - (hr - 2);
@@ -398,6 +436,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
               // descriptor's base-offset field stays 0), exactly as for the +32-byte K advance below.
               const uint32_t t_lo = a_lo0 + (uint32_t)((e.d2 + 1) * pitch + (e.d1 + 1)) * 8u;    // 128-byte rows = 8 address units
               const uint32_t b_lo = desc_lo(smem_u32(smem_b + sb * Cfg::kBBytes));
+              need_rows(e.d2 + 1 + ROWS);                  // this tap reads halo rows dy + 1 .. dy + ROWS
               if (!(p.dbg & 2)) {
                 // k outer, row inner: consecutive MMAs accumulate into different TMEM tiles
 #pragma unroll
@@ -412,13 +451,16 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
               if (++sb == kRingB) { sb = 0; pb ^= 1; }
             }
             }
+            need_rows(ROWS + 2);                           // (every row barrier of the stage has been consumed: phases stay in step)
             umma_commit(&empty_a[sa]);
+            if constexpr (FUSE) ph_row ^= 1u << sa;
             if (++sa == kRingA) { sa = 0; pa ^= 1; }
           }
           for (int ei = p.n_taps; ei < p.n_entries; ++ei) {
             const int n2 = p.e[ei].nchunks;
             for (int c = 0; c < n2; ++c, ++kb) {
-              mbar_wait(&full_a[sa], pa);
+              if constexpr (FUSE) { mbar_wait(&full_a[sa], (ph_x2 >> sa) & 1u); ph_x2 ^= 1u << sa; }
+              else mbar_wait(&full_a[sa], pa);
               mbar_wait(&full_b[sb], pb);
               tc_fence_after();
               const uint32_t a_lo = desc_lo(smem_u32(smem + sa * kHaloStage));
@@ -443,7 +485,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
     }
   } else if (FUSE && warp > kMmaWarp && warp < kXfWarp0) {
     // the two spare warps of the producer / MMA warpgroup: give their registers back and leave
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   } else if (FUSE && warp >= kXfWarp0 && warp < kXfWarp0 + kXfWarps) {
     // ===================== transform warps (fused GroupNorm + activation of the input) =====================
     // The raw halo tile has been landed by TMA (zero-filled outside the image); each thread rewrites IN PLACE the 16-byte
@@ -451,14 +493,16 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
     // applies to the normalised tensor), then releases the stage to the MMA issuer.  (Fetching the tile with ordinary
     // loads instead was 4x slower: with 227 KB of shared memory carved out, L1 has almost no lines left for misses in flight.)
     if constexpr (FUSE) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-      constexpr int kXfRows = 4 * kXfWarps;                 // tile rows covered by one pass of the transform warps
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
       const int xt = threadIdx.x - 32 * kXfWarp0;           // 0 .. 32 * kXfWarps - 1
       const int j = xt & 7;                                 // logical 16-byte column (8 channels) owned by this thread
-      const int r0 = xt >> 3;                               // first tile row; rows advance by kXfRows
+      const int slot = xt >> 3;                             // pixel slot inside a halo row; pixels advance by kXfSlots
+      constexpr int kXfSlots = 4 * kXfWarps;                // 32
+      constexpr int U = 3;                                  // loads in flight per thread; 2 x 3 passes cover a halo row of up to 192 pixels
       const int pitch = p.t1 + 2;
-      const int halo_rows = (ROWS + 2) * pitch;
       int sa = 0; uint32_t pa = 0;
+      uint32_t ph_row = 0u, ph_x2 = 0u;                     // per-stage phase bits (bit = stage)
+      const bool swish = p.gn_act == WSR_ACT_SWISH;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         const TileCoord t = decode_tile(p, tile);
         const int c1 = t.i1 * p.t1, c2 = t.i2 * ROWS, c3 = t.i3;
@@ -484,61 +528,66 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
               sc2[q] = *(uint32_t*)&s2; sh2[q] = *(uint32_t*)&h2;
             }
           }
-          mbar_wait(&full_raw[sa], pa);
           const uint32_t st_s = smem_u32(smem + sa * kHaloStage);
-          int hy = r0 / pitch, hx = r0 - hy * pitch;
-          constexpr int U = 4;                              // shared-memory loads in flight per thread
-          const bool swish = p.gn_act == WSR_ACT_SWISH;
-          for (int rb = r0; rb < halo_rows; rb += kXfRows * U) {
-            uint32_t raw[U][4];
-            uint32_t addr[U];
-            bool ok[U];
+          for (int hy = 0; hy < ROWS + 2; ++hy) {
+            // row by row: wait for this row's TMA box, rewrite it in place, hand it to the MMA issuer
+            mbar_wait(&row_raw[sa * kRowMax + hy], (ph_row >> sa) & 1u);
+            if (hy >= hy_lo && hy < hy_hi) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const int r = rb + kXfRows * u;
-              ok[u] = r < halo_rows && hy >= hy_lo && hy < hy_hi && hx >= hx_lo && hx < hx_hi;
-              addr[u] = st_s + (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
-              if (ok[u]) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(raw[u][0]), "=r"(raw[u][1]), "=r"(raw[u][2]), "=r"(raw[u][3]) : "r"(addr[u]));
-              hx += kXfRows;
-              if (hx >= pitch) { hx -= pitch; ++hy; }
-            }
+             for (int u0 = 0; u0 < 6; u0 += U) {             // two batches of three passes: 96 + 96 pixel slots >= t1 + 2
+              uint32_t raw[U][4];
+              uint32_t addr[U];
+              bool ok[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-              if (ok[u]) {
-                uint32_t o[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  uint32_t a;
-                  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(a) : "r"(raw[u][k]), "r"(sc2[k]), "r"(sh2[k]));
-                  if (swish) {
-                    uint32_t h, t;
-                    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(h) : "r"(a), "r"(0x3f003f00u));      // 0.5, 0.5
-                    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t) : "r"(h));
-                    asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(a) : "r"(h), "r"(t));
-                  }
-                  o[k] = a;
-                }
-                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr[u]), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+              for (int u = 0; u < U; ++u) {
+                const int hx = slot + kXfSlots * (u0 + u);
+                const int r = hy * pitch + hx;                 // 128-byte row of the stage
+                ok[u] = hx >= hx_lo && hx < hx_hi;
+                addr[u] = st_s + (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
+                if (ok[u]) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(raw[u][0]), "=r"(raw[u][1]), "=r"(raw[u][2]), "=r"(raw[u][3]) : "r"(addr[u]));
               }
+#pragma unroll
+              for (int u = 0; u < U; ++u) {
+                if (ok[u]) {
+                  uint32_t o[4];
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    uint32_t a;
+                    asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(a) : "r"(raw[u][k]), "r"(sc2[k]), "r"(sh2[k]));
+                    if (swish) {
+                      uint32_t h, tt;
+                      asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(h) : "r"(a), "r"(0x3f003f00u));      // 0.5, 0.5
+                      asm("tanh.approx.bf16x2 %0, %1;" : "=r"(tt) : "r"(h));
+                      asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(a) : "r"(h), "r"(tt));
+                    }
+                    o[k] = a;
+                  }
+                  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr[u]), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                }
+              }
+             }
             }
+            // one arrival per WARP (per-thread arrivals on one shared-memory word serialise)
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&row_rdy[sa * kRowMax + hy]);
           }
-          // one arrival per WARP (256 per-thread arrivals on one shared-memory word serialise: ~1-2 us per stage)
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full_a[sa]);
+          ph_row ^= 1u << sa;
           if (++sa == kRingA) { sa = 0; pa ^= 1; }
         }
         // fused 1x1 segment (ResnetBlock res_conv): the raw x2 tile passes through untouched
         for (int ei = p.n_taps; ei < p.n_entries; ++ei) {
           const int n2 = p.e[ei].nchunks;
           for (int c = 0; c < n2; ++c) {
-            mbar_wait(&full_raw[sa], pa);
+            mbar_wait(&full_raw[sa], (ph_x2 >> sa) & 1u);
+            ph_x2 ^= 1u << sa;
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_a[sa]);
             if (++sa == kRingA) { sa = 0; pa ^= 1; }
           }
         }
       }
+      (void)pa;
     }
   } else {
     // ===================== epilogue (warps 0..7) =====================
@@ -1345,6 +1394,12 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
     rc = encode_map(&p.amap[0], d->x, 4, dims, str, halo ? hbox : abox);
     if (rc) return rc;
     for (int i = 1; i < kNumAMaps; ++i) p.amap[i] = p.amap[0];
+    if (halo && d->gn_table) {
+      // fused GroupNorm input: the halo tile is fetched one row per TMA box (row-by-row hand-over to the transform warps)
+      const uint32_t rbox[4] = {64, (uint32_t)(p.t1 + 2), 1, 1};
+      rc = encode_map(&p.amap[1], d->x, 4, dims, str, rbox);
+      if (rc) return rc;
+    }
   } else {
     // four phase-subsampled views: phase (py, px) starts at pixel (py, px), steps 2 pixels
     for (int py = 0; py < 2; ++py)
