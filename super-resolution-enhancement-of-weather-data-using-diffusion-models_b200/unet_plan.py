@@ -46,13 +46,17 @@ class UNetPlan:
         self.groups = net.norm_groups
         self.time_act = nat.ACT_MISH if net.time_act == "mish" else nat.ACT_SWISH
         self._wver = None
-        # GroupNorm + Swish fused into the consuming convolution's operand path (transform warps rewrite the TMA-landed
-        # tile in shared memory; wsr_conv_tc with WsrConvDesc.gn_table).  Correct and tested, but MEASURED SLOWER on B200
-        # than the separate HBM-bound pass: e.g. 64->64 @128x256, B=64: conv 0.27 ms + gn_apply 0.10 ms unfused vs 0.51 ms
-        # fused (four transform warps cannot keep up with the tensor pipe, and their shared-memory traffic competes with
-        # the operand fetch that already bounds these N=64 layers) -- so it is OFF by default (env WSR_FUSE_GN=1 turns it on).
+        # GroupNorm + Swish fused into the consuming convolution's operand path (transform warps rewrite the TMA-landed halo tile
+        # in shared memory row by row; wsr_conv_tc with WsrConvDesc.gn_table).  Round 2 (8 transform warps on their own register
+        # budget, packed bf16x2 arithmetic, row-by-row hand-over TMA -> transform -> MMA), measured on B200 at B = 64
+        # (profiles/r02_fused_gn_decomposition.txt):  128->128 @64x128: 0.166 ms fused vs 0.141 conv + 0.061 gn_apply;
+        # 384->128: 0.441 vs 0.358 + 0.138;  but 64->64 @128x256: 0.326 vs 0.163 + 0.094 and 192->64: 0.719 vs 0.364 + 0.260 --
+        # the N = 64 layers are bound by the tensor core's own shared-memory operand fetch, and the transform's traffic on the same
+        # banks slows both.  Policy (WSR_FUSE_GN): 1 (default) = fuse where the convolution's column tile is >= 128 wide, 2 = fuse
+        # every eligible layer, 0 = never.
         import os
-        self.fuse_gn = (getattr(self, "fuse_gn", True) and self.eng.mode == "bf16" and os.environ.get("WSR_FUSE_GN", "0") == "1")
+        self.fuse_gn_mode = int(os.environ.get("WSR_FUSE_GN", "1")) if (getattr(self, "fuse_gn", True) and self.eng.mode == "bf16") else 0
+        self.fuse_gn = self.fuse_gn_mode > 0
         self._structure()
         self._buffers()
         self.refresh_weights()
@@ -458,8 +462,9 @@ class UNetPlan:
         e, B, G = self.eng, self.B, self.groups
         SW = nat.ACT_SWISH
         if not hasattr(r, "fuse1"):
-            r.fuse1 = self.fuse_gn and e.conv_can_fuse_gn(x, r.conv1)
-            r.fuse2 = self.fuse_gn and e.conv_can_fuse_gn(r.hbuf, r.conv2, x2=x if r.has_res_conv else None)
+            wide = self.fuse_gn_mode >= 2 or r.cout >= 128
+            r.fuse1 = self.fuse_gn and wide and e.conv_can_fuse_gn(x, r.conv1)
+            r.fuse2 = self.fuse_gn and wide and e.conv_can_fuse_gn(r.hbuf, r.conv2, x2=x if r.has_res_conv else None)
             r.tab1 = e.empty((B, r.cin, 2), torch.float32) if r.fuse1 else None
             r.tab2 = e.empty((B, r.cout, 2), torch.float32) if r.fuse2 else None
         if r.fuse1:
@@ -635,7 +640,7 @@ class UNetPlan:
         """final_conv = GroupNorm -> Swish -> conv3x3 (resdiff/unet.py:119, nn_modules/resnet.py:19-28)."""
         e = self.eng
         if not hasattr(self, "fuse_final"):
-            self.fuse_final = self.fuse_gn and e.conv_can_fuse_gn(x, self.final)
+            self.fuse_final = self.fuse_gn_mode >= 2 and e.conv_can_fuse_gn(x, self.final)
             self.tab_final = e.empty((self.B, self.final_cin, 2), torch.float32) if self.fuse_final else None
         if self.fuse_final:
             e.gn_finalize(x, self.gf, self.bf_, self.groups, self.tab_final)
