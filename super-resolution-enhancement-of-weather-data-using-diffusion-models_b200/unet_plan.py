@@ -311,8 +311,9 @@ class UNetPlan:
             self.gf, self.bf_ = e.f32(fc[0].weight), e.f32(fc[0].bias)
             self.final = e.pack_conv(fc[3].weight, fc[3].bias, rows=64 if e.mode == "bf16" else None)
             # fp32 [9][Cout][Cin] copy of the head's weights for the fused head + reverse-step kernel (wsr_final_conv_sampler_step)
-            self.final_f32 = self._pack_f32_conv(fc[3].weight) if e.mode == "bf16" else None
-            if self.final_f32 is not None and nat.call("wsr_head_sampler_supported", self.final_cin, self.C_img, self.groups):
+            self.final_f32 = self._pack_f32_conv(fc[3].weight) if (e.mode == "bf16" and type(self) is UNetPlan) else None
+            if (type(self) is UNetPlan and self.final_f32 is not None
+                    and nat.call("wsr_head_sampler_supported", self.final_cin, self.C_img, self.groups)):
                 # ldmatrix-ready bf16 blocks of the head's weights for wsr_final_conv_sampler_step
                 key = ("headw", fc[3].weight.data_ptr())
                 self.final_hw = e._pack_cache.get(key)
