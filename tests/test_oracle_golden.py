@@ -204,3 +204,24 @@ def test_srdiff_chain():
         out = process.srdiff_chain(_sd("srdiff", spec["seed"], spec["cfg"]), _sd("rrdb", spec["seed"] + 1), spec["cfg"],
                                    short_schedule(spec["T"]), g["lr"], g["cond"], g["noise"])
     assert rel_l2(out, g["sr_out"]) < TOL
+
+
+def test_oracle_at_benchmark_shape_config4_vs_reference_probe():
+    """The oracle restatement at a BENCHMARK shape against the real reference's output (probe fixture made by
+    oracle/make_golden.py: strided sub-grid of eps_hat + per-sample norms): BASELINE configs[4], 3 variables, inner 128,
+    128x256, the fixture's full batch of 8 (the ResDiff FFT couples the batch; ~40 s on 8 cores)."""
+    from oracle.cases import fields, probe_levels, probe_summary
+    from oracle.weights import seeded_randn
+    name = "resdiff_step_c5_full_b8"
+    g, spec = load_golden(name), CASES[name]
+    cfg, b, seed = spec["cfg"], spec["batch"], spec["seed"]
+    lr, sr, _ = fields(name, b, cfg["image_channels"], cfg["image_height"], cfg["image_width"], seed, scale=spec["scale"])
+    x_t = seeded_randn(name + ".xt", sr.shape, seed)
+    assert torch.equal(lr[:2, :, :2, :8], g["lr_head"]) and torch.equal(x_t[:2, :, :2, :8], g["xt_head"])
+    level = torch.tensor(probe_levels(b), dtype=torch.float32).view(b, 1)
+    sd = _sd("resdiff", seed, cfg)
+    with torch.no_grad():
+        eps = nets.resdiff_unet(sd, torch.cat([sr, x_t], 1), level, cfg)
+    s = probe_summary(eps)
+    assert rel_l2(s["eps_probe"], g["eps_probe"]) < TOL
+    assert float(((s["eps_norm"] - g["eps_norm"]).abs() / g["eps_norm"]).max()) < TOL

@@ -5,7 +5,9 @@ the same inputs.  End to end: the reference-facing classes (ResDiffDiffusion.p_l
 gradients of the REAL reference (tests/golden/resdiff_grad_small.npz) and of the CPU oracle's autograd, per parameter.
 Tolerances: fp32 check mode rel-L2 <= 2e-4 per tensor (atomics / summation order; measured 1.2e-6 over the whole
 gradient).  bf16 mode: 2x the REAL reference's own bf16-autocast drift on this case (oracle/bf16_drift.py: whole gradient
-7.6e-2, median tensor 3.2e-2, worst 0.53 on a 2-element tensor) -> whole gradient <= 1.5e-1, per tensor <= 1.6e-1
+7.6e-2, median tensor 3.2e-2, worst 0.53 on a 2-element tensor) -> per tensor <= 1.6e-1; whole gradient <= 1.5 x the value this
+path measures on B200 (ResDiff 6.8e-2 -> 1.0e-1, PhyDiff 3.0e-2 -> 5e-2, SR3 8.9e-3 -> 2e-2, SRDiff 2.7e-2 -> 5e-2; round 1 used a
+flat 1.5e-1, which a 2x regression would have passed)
 (tensors with fewer than 16 elements: <= 1.0); measured on B200: 6.8e-2 whole gradient."""
 import math
 
@@ -360,7 +362,7 @@ def test_training_step_gradients_with_dropout_on_vs_oracle(precision):
     # the masks really changed the problem: the dropout-free reference loss differs
     assert abs(float(ref_loss) - float(g["loss"])) / float(g["loss"]) > 1e-3
     named = dict(net.named_parameters())
-    tol_t, tol_all = (2e-4, 1e-4) if precision == "fp32" else (1.6e-1, 1.5e-1)
+    tol_t, tol_all = (2e-4, 1e-4) if precision == "fp32" else (1.6e-1, 1.0e-1)
     num = den = 0.0
     bad = []
     for n, p in named.items():
@@ -395,7 +397,7 @@ def test_training_step_gradients_vs_reference(arch, precision):
     rel_loss = abs(loss - float(g["loss"])) / float(g["loss"])
     sd = seeded_state_dict(manifest(arch, cfg), spec["seed"])
     _, oracle_grads = process.arch_param_grads(arch, sd, cfg, g["hr"], g["sr"], g["level"], g["noise"])
-    tol_t, tol_all = (2e-4, 1e-4) if precision == "fp32" else (1.6e-1, 1.5e-1)
+    tol_t, tol_all = (2e-4, 1e-4) if precision == "fp32" else (1.6e-1, {"resdiff": 1.0e-1, "phydiff": 5e-2, "sr3": 2e-2}[arch])
     named = dict(net.named_parameters())
     assert sorted(named) == sorted(str(n) for n in g["names"])
     plan = net.train_plan(g["hr"].shape[0], torch.device("cuda:0"))
@@ -595,7 +597,7 @@ def test_srdiff_training_step_gradients_vs_reference(precision):
     print("\n[parity] srdiff training step %s: loss rel err %.3e, whole-gradient rel-L2 %.3e, cond_proj.weight %.3e, worst tensor %.3e (%s)"
           % (precision, rel_loss, total, cp, worst[0], worst[1]))
     assert rel_loss < (1e-4 if precision == "fp32" else 2e-2)
-    assert total < (1e-4 if precision == "fp32" else 1.5e-1)
+    assert total < (1e-4 if precision == "fp32" else 5e-2)
     assert cp < (2e-4 if precision == "fp32" else 1.6e-1)
     assert worst[0] < (2e-4 if precision == "fp32" else 2.5e-1), worst
 
@@ -656,7 +658,7 @@ def test_srdiff_joint_training_step_vs_reference(precision):
           % (precision, rel_loss, report["unet"][0], report["rrdb"][0], report["unet"][1], report["rrdb"][1]))
     assert rel_loss < (1e-4 if precision == "fp32" else 2e-2)
     for tag in ("unet", "rrdb"):
-        assert report[tag][0] < (2e-4 if precision == "fp32" else 1.5e-1), tag
+        assert report[tag][0] < (2e-4 if precision == "fp32" else 8e-2), tag          # measured 3.9e-2 / 4.8e-2
         assert report[tag][1][0] < (1e-3 if precision == "fp32" else 3e-1), (tag, report[tag][1])
     # one optimizer step over BOTH parameter sets (the encoder's parameters are outside the UNet's flat buffer)
     FusedAdam = wsr.sub("autograd_glue").FusedAdam
