@@ -98,11 +98,15 @@ int wsr_conv_simt(const WsrConvDesc* d, void* stream);
  * Cin2 % 64 == 0, Cout % 16 == 0, W a power of two (>= 2), pitches % 8 == 0, 16-byte aligned bases. */
 int wsr_conv_tc(const WsrConvDesc* d, void* stream);
 int wsr_conv_tc_can_fuse_gn(const WsrConvDesc* d);
-/* test introspection: (column-tile width << 8) | K splits chosen by the most recent wsr_conv_tc / wsr_conv_taps_tc call */
+/* test introspection: (CTA pairs << 20) | (column-tile width << 8) | K splits chosen by the most recent wsr_conv_tc / wsr_conv_taps_tc call */
 int wsr_debug_last_tc_config(void);
 /* split-K of the classic-mode tcgen05 convolution is correct but measured no faster than the unsplit kernel on B200, so
  * it is off unless WSR_SPLITK=1 or this switch is set; returns the previous setting. */
 int wsr_debug_set_splitk(int on);
+/* CTA pairs (tcgen05 cta_group::2: two SMs of a TPC share one 256 x 256 tile, each staging half of the weight columns) for the classic-mode
+ * 256-column convolution tiles: 0 = never, 1 = launches of more than one wave (default; env WSR_PAIR), 2 = every eligible launch (an even
+ * number of row tiles).  Returns the previous mode.  wsr_debug_last_tc_config() reports the choice in bit 20. */
+int wsr_debug_set_pair(int mode);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Tap-table convolution: the same kernels driven by an explicit list of taps instead of (ksize, stride, upsample).

@@ -82,6 +82,7 @@ struct TcParams {
   int ksplit, kb_split;
   float* ws; unsigned* ctr;
   int prefetch;                 // halo mode: L2-prefetch the halo box two loads ahead (see the producer)
+  int pair;                     // classic mode, N = 256: run as CTA pairs (PAIR kernels); the weight map's box is then 128 rows
   const void* xg; int xg_ld, xg_H, xg_W;
   const void* x2g; int x2g_ld;
   const float2* gn_tab; int gn_ld; int gn_act;
@@ -111,13 +112,17 @@ constexpr int next_pow2(int v) { int p = 32; while (p < v) p *= 2; return p; }
 // (halo row, dx) with the weight matrices [dy=+1 | dy=0 | dy=-1] stacked along N (192 columns) updates all three: the
 // 128-pixel activation operand -- whose shared-memory fetch bounds the N = 64 layers -- is read 5 times per 3 output
 // rows instead of 9 times.
-template <int BLOCK_N, bool HALO, int ROWS, bool VM = false> struct TcCfg {
+// PAIR (classic mode, N = 256): two CTAs on one TPC share a 256 x 256 tile through cta_group::2 MMAs -- each CTA stages its own 128 rows
+// of A and only HALF of the B columns, so a K block costs 32 KB of L2 -> SM traffic per SM instead of 48 KB.  At ~70 bytes per clock
+// and SM that is the difference between 690 and 460 cycles against 512 cycles of MMA: the single-CTA kernel is fetch-bound (ncu: tensor
+// pipe 61 % busy on the 32x64 / 16x32 / 8x16 levels), the pair is not.
+template <int BLOCK_N, bool HALO, int ROWS, bool VM = false, bool PAIR = false> struct TcCfg {
   static constexpr int kHaloStage = halo_stage_bytes(ROWS);
-  static constexpr int kBTile = BLOCK_N * kBlockK * 2;                 // one weight tile
+  static constexpr int kBTile = (PAIR ? BLOCK_N / 2 : BLOCK_N) * kBlockK * 2;   // one weight tile (PAIR: this CTA's half of the columns)
   static constexpr int kBBytes = VM ? 3 * kBTile : kBTile;             // one stage of the weight ring
   // classic mode: one ring of {A tile, B tile} stages.  halo mode: a ring of activation halo tiles (one per 64-channel
   // chunk, shared by the 9 taps) and a separate ring of weight tiles.
-  static constexpr int kStages = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+  static constexpr int kStages = PAIR ? 6 : (BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8));
   static constexpr int kAStages = 2;
   static constexpr int kBStages = VM ? 2 : (BLOCK_N >= 256 ? 3 : (BLOCK_N >= 128 ? (ROWS > 1 ? 4 : 6) : (ROWS >= 4 ? 3 : 8)));
   static constexpr int kSmemData = HALO ? kAStages * kHaloStage + kBStages * kBBytes : kStages * (kABytes + kBBytes);
@@ -131,8 +136,8 @@ template <int BLOCK_N, bool HALO, int ROWS, bool VM = false> struct TcCfg {
   static constexpr int kStgBytes = (HALO && ROWS >= 4) ? 0 : 8 * 1024;
   static constexpr int kSmemBytes = kSmemData + 1024 /*align slack*/ + 512 /*barriers*/ + kBsumBytes + kStgBytes;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
-  // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
-  static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+  // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128 (256 across a CTA pair)
+  static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)((PAIR ? 2 : 1) * kBlockM >> 4) << 24);
 };
 
 struct TileCoord { int nt, i1, i2, i3, zb; };
@@ -151,16 +156,17 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
 // ------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------------
-template <int BLOCK_N, bool HALO, int ROWS, bool FUSE = false, bool VM = false, bool STG = false, bool SPLIT = false>
+template <int BLOCK_N, bool HALO, int ROWS, bool FUSE = false, bool VM = false, bool STG = false, bool SPLIT = false, bool PAIR = false>
 __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   static_assert(!SPLIT || (!HALO && STG), "split-K: classic tiles with the staged epilogue only");
+  static_assert(!PAIR || (!HALO && !SPLIT && !FUSE && BLOCK_N == 256), "CTA pairs: classic 256-column tiles only");
   // STG: the epilogue moves residual loads and output stores through a per-warp shared-memory staging buffer (see TcCfg::kStgBytes);
   // the host selects it only when stage_preconditions() hold (bf16 output / residual, unit channel stride, 16-byte aligned rows)
   // register budget: 10 warps = 3 warps on the fullest scheduler, 16384 / 3 / 32 -> 168 registers per thread at most
   static_assert(256 * 168 + 128 * 40 + 256 * 48 <= kTcThreadsFused * 96, "setmaxnreg plan exceeds the launch allocation");
   static_assert(!FUSE || HALO, "the fused-GroupNorm input path exists in halo mode only");
   static_assert(!VM || (HALO && BLOCK_N == 64), "vertical tap merge: halo mode, N = 64");
-  using Cfg = TcCfg<BLOCK_N, HALO, ROWS, VM>;
+  using Cfg = TcCfg<BLOCK_N, HALO, ROWS, VM, PAIR>;
   static_assert(!STG || Cfg::kStgBytes > 0, "no staging buffer in this configuration");
   constexpr int kHaloStage = Cfg::kHaloStage;
   extern __shared__ uint8_t smem_raw[];
@@ -200,8 +206,15 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
   // neighbouring rows (halo re-reads hit L2)
   // SPLIT: the grid is exactly (tiles x ksplit) CTAs, CTA = (tile, split)
   const int split_s = SPLIT ? (int)blockIdx.x % p.ksplit : 0;
-  const int tile_begin = SPLIT ? (int)blockIdx.x / p.ksplit : (int)((long long)blockIdx.x * total_tiles / gridDim.x);
-  const int tile_end = SPLIT ? tile_begin + 1 : (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
+  // PAIR: the grid is a row of 2-CTA clusters; a pair walks "pair tiles" tq = (row-tile pair, column tile) and CTA `rank` of the pair
+  // owns row tile 2 * pair + rank of each (the host guarantees an even number of row tiles)
+  const int pair_rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int n_work = PAIR ? total_tiles / 2 : total_tiles;
+  const int n_cta = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int cta_i = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+  const int tile_begin = SPLIT ? (int)blockIdx.x / p.ksplit : (int)((long long)cta_i * n_work / n_cta);
+  const int tile_end = SPLIT ? tile_begin + 1 : (int)((long long)(cta_i + 1) * n_work / n_cta);
+  auto work_tile = [&](int tq) { return PAIR ? ((tq / p.n_tiles) * 2 + pair_rank) * p.n_tiles + tq % p.n_tiles : tq; };
   const int kb0 = SPLIT ? split_s * p.kb_split : 0;
   const int kb1 = SPLIT ? min(p.total_kb, kb0 + p.kb_split) : p.total_kb;
 
@@ -210,7 +223,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
     for (int i = 0; i < kNumBMaps; ++i) prefetch_tmap(&p.bmap[i]);
     for (int s = 0; s < kRingA; ++s) { mbar_init(&full_a[s], FUSE ? kXfWarps : 1); mbar_init(&empty_a[s], 1); }
     for (int s = 0; s < kRingB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); mbar_init(&full_raw[a], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], (PAIR ? 2 : 1) * kEpiWarps); mbar_init(&full_raw[a], 1); }
     if constexpr (FUSE) {
       for (int i = 0; i < 2 * kRowMax; ++i) { mbar_init(&row_raw[i], 1); mbar_init(&row_rdy[i], kXfWarps); }
     }
@@ -218,11 +231,17 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
     fence_proxy_async();
   }
   if (warp == kMmaWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  // PAIR: the peer must not signal this CTA's barriers (TMA transaction bytes, MMA commits, accumulator hand-back) before they exist
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // FUSE: register re-balancing between the warpgroups (see kXfWarps) -- the setmaxnreg of each role is the FIRST statement of its
@@ -237,7 +256,8 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
     if constexpr (FUSE) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
+      for (int tq = tile_begin; tq < tile_end; ++tq) {
+        const int tile = work_tile(tq);
         const TileCoord t = decode_tile(p, tile);
         const int c1 = t.i1 * p.t1, c2 = t.i2 * (HALO ? ROWS : p.t2), c3 = t.i3 * p.t3 + t.zb * p.a_zmul;
         if constexpr (!HALO) {
@@ -248,6 +268,14 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
               if constexpr (SPLIT) { if (kbi < kb0 || kbi >= kb1) continue; }
               mbar_wait(&empty_a[sa], pa ^ 1);
               uint8_t* st = smem + sa * (kABytes + Cfg::kBBytes);
+              if constexpr (PAIR) {
+                // both CTAs' loads complete on the leader's barrier (the leader's MMA thread is the only consumer)
+                if (pair_rank == 0) mbar_expect_tx(&full_a[sa], (uint32_t)(2 * (p.a_bytes + Cfg::kBBytes)));
+                tma_load_4d_pair(st, &p.amap[e.amap], &full_a[sa], e.a_c0 + c * kBlockK, c1 + e.d1, c2 + e.d2, c3);
+                tma_load_3d_pair(st + kABytes, &p.bmap[e.bmap], &full_a[sa], e.b_k0 + c * kBlockK, t.nt * BLOCK_N + pair_rank * (BLOCK_N / 2), e.b_z);
+                if (++sa == kRingA) { sa = 0; pa ^= 1; }
+                continue;
+              }
               mbar_expect_tx(&full_a[sa], (uint32_t)(p.a_bytes + (p.b_bytes ? p.b_bytes : Cfg::kBBytes)));
               if (!p.a_mn) {
                 tma_load_4d(st, &p.amap[e.amap], &full_a[sa], e.a_c0 + c * kBlockK, c1 + e.d1, c2 + e.d2, c3);
@@ -338,7 +366,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       uint32_t ph_row = 0u, ph_x2 = 0u;     // FUSE: per-stage phase bits (bit = stage) of the row barriers / of full_a (x2 uses)
       int it = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+      for (int tile = tile_begin; tile < ((PAIR && pair_rank != 0) ? tile_begin : tile_end); ++tile, ++it) {   // PAIR: the leader issues for both
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -356,6 +384,16 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
             const uint32_t s_lo = (smem_u32(smem + sa * (kABytes + Cfg::kBBytes)) & 0x3FFFFu) >> 4;
             const uint32_t a_lo = s_lo | a_lbo;
             const uint32_t b_lo = (s_lo + (uint32_t)(kABytes >> 4)) | b_lbo;
+            if constexpr (PAIR) {
+              if (!(p.dbg & 2)) {
+                umma_bf16_lo_pair(d_tmem, a_lo, b_lo, idesc, kb != kb0 ? 1u : 0u);
+                umma_bf16_lo_pair(d_tmem, a_lo + 2u, b_lo + 2u, idesc, 1u);
+                umma_bf16_lo_pair(d_tmem, a_lo + 4u, b_lo + 4u, idesc, 1u);
+                umma_bf16_lo_pair(d_tmem, a_lo + 6u, b_lo + 6u, idesc, 1u);
+              }
+              umma_commit_pair(&empty_a[sa]);                           // frees the stage in both CTAs
+              if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[acc]);     // both epilogues
+            } else {
             if (!(p.dbg & 2)) {
               umma_bf16_lo(d_tmem, a_lo, b_lo, idesc, kb != kb0 ? 1u : 0u);
               umma_bf16_lo(d_tmem, a_lo + a_st, b_lo + b_st, idesc, 1u);
@@ -364,6 +402,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
             }
             umma_commit(&empty_a[sa]);
             if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
+            }
             if (++sa == kRingA) { sa = 0; pa ^= 1; }
           }
         } else {
@@ -672,7 +711,8 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
     // carved out there is almost no L1 left, so the per-row __ldg's of the classic path were L2 round trips)
     float* bs = (float*)(smem + Cfg::kSmemData + 512) + warp * (32 * kChunksPerWarp);
     int it = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+    for (int tq = tile_begin; tq < tile_end; ++tq, ++it) {
+      const int tile = work_tile(tq);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const TileCoord t = decode_tile(p, tile);
@@ -1018,7 +1058,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]); }
       if constexpr (SPLIT) {
         // every CTA of the tile has passed the arrival spin before it gets here, so the last one may restore the zeros
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
@@ -1032,10 +1072,14 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
   }
 
   tc_fence_before();
-  __syncthreads();
+  // PAIR: neither CTA may leave (or free tensor memory) while the other can still signal its barriers or its MMAs read its B half
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
   }
 }
 
@@ -1107,6 +1151,40 @@ static int launch_tc_impl(const TcParams& p, cudaStream_t st) {
   return WSR_OK;
 }
 
+// CTA-pair launch: a row of 2-CTA clusters, at most one pair per TPC the device can co-schedule (asked from the occupancy API once)
+template <bool STG>
+static int launch_tc_pair(const TcParams& p, cudaStream_t st) {
+  using Cfg = TcCfg<256, false, 1, false, true>;
+  auto kern = gemm_tc_kernel<256, false, 1, false, false, STG, false, true>;
+  static int max_pairs = 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = (size_t)Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  if (!max_pairs) {
+    WSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    cfg.gridDim = dim3(sm_count() / 2 * 2);
+    cfg.numAttrs = 1;
+    int n = 0;
+    WSR_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    WSR_REQUIRE(n > 0, WSR_E_CUDA, "gemm_tc: the device cannot co-schedule a CTA pair of the 256-column kernel");
+    max_pairs = n < sm_count() / 2 ? n : sm_count() / 2;
+  }
+  const int total = p.g1 * p.g2 * p.g3 * p.nbatch * p.n_tiles;
+  WSR_REQUIRE(total % 2 == 0 && (p.g1 * p.g2 * p.g3 * p.nbatch) % 2 == 0, WSR_E_INVALID, "gemm_tc: CTA pairs need an even number of row tiles");
+  const int pairs = total / 2 < max_pairs ? total / 2 : max_pairs;
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  WSR_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
+  return WSR_OK;
+}
+
 // Preconditions of the staged epilogue (STG kernels): bf16 output (and residual) with unit channel stride, every row start
 // 16-byte aligned, whole 32-column chunks only.
 static bool stage_preconditions(const TcParams& p, int block_n) {
@@ -1163,6 +1241,9 @@ static int launch_tc(const TcParams& p, cudaStream_t st) {
       return launch_tc_impl<BLOCK_N, false, 1, false, false, true, true>(p, st);
     }
   }
+  if constexpr (BLOCK_N == 256) {
+    if (p.pair) return (sok && (stage_mask() & 4)) ? launch_tc_pair<true>(p, st) : launch_tc_pair<false>(p, st);
+  }
   if (sok && (stage_mask() & 4)) return launch_tc_impl<BLOCK_N, false, 1, false, false, true>(p, st);
   return launch_tc_impl<BLOCK_N, false, 1>(p, st);
 }
@@ -1173,7 +1254,8 @@ static int launch_tc(const TcParams& p, cudaStream_t st) {
 // chosen BN and sets *ksplit (1 = no split).  Split-K needs BN >= 128 (S <= BN / 32 column chunks to distribute), at least 4 K blocks
 // per split, tiles * S <= SMs and the caller's workspace.
 constexpr int kSplitHeader = 32768;               // bytes of counters at the head of the split-K workspace (one 128-byte line per tile)
-static int g_last_ksplit = 1, g_last_bn = 0;
+static int g_last_ksplit = 1, g_last_bn = 0, g_last_pair = 0;
+static int g_pair_mode = -1;                      // -1 = read WSR_PAIR on first use; wsr_debug_set_pair overrides
 static int g_splitk_on = 0;                       // wsr_debug_set_splitk (tests); the environment variable WSR_SPLITK=1 does the same      // introspection for the tests (wsr_debug_last_tc_config)
 
 static int pick_split(int ncols, int m_tiles, int total_kb, long long ws_bytes, int bn_nosplit, int* ksplit) {
@@ -1261,8 +1343,13 @@ using namespace wsr;
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 /* (column-tile width << 8) | K splits of the most recent wsr_conv_tc / wsr_conv_taps_tc launch of this process (tests only) */
-extern "C" int wsr_debug_last_tc_config(void) { return (g_last_bn << 8) | g_last_ksplit; }
+extern "C" int wsr_debug_last_tc_config(void) { return (g_last_pair << 20) | (g_last_bn << 8) | g_last_ksplit; }
 /* enable (1) / disable (0) the split-K plan of wsr_conv_tc / wsr_conv_taps_tc for this process; returns the previous setting */
+// CTA-pair policy of the classic 256-column convolution tiles: 0 never, 1 launches of more than one wave (default), 2 every eligible launch
+extern "C" int wsr_debug_set_pair(int mode) {
+  if (g_pair_mode < 0) g_pair_mode = getenv("WSR_PAIR") ? atoi(getenv("WSR_PAIR")) : 1;
+  const int prev = g_pair_mode; g_pair_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode); return prev;
+}
 extern "C" int wsr_debug_set_splitk(int on) { const int prev = g_splitk_on; g_splitk_on = on ? 1 : 0; return prev; }
 
 extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
@@ -1357,13 +1444,22 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
   static const int dbg_flags = getenv("WSR_TC_DBG") ? atoi(getenv("WSR_TC_DBG")) : 0;
   p.dbg = dbg_flags;
 
+  // CTA pairs (cta_group::2) for the classic 256-column tiles: needs an even number of row tiles; WSR_PAIR=0 switches it off, WSR_PAIR=2
+  // takes every eligible launch (tests)
+  if (g_pair_mode < 0) g_pair_mode = getenv("WSR_PAIR") ? atoi(getenv("WSR_PAIR")) : 1;
+  const int pair_mode = g_pair_mode;
+  const bool pair_on = pair_mode != 0;
+  // (measured on B200, tools/prof_conv.py: +6..7 % on the launches of more than one wave -- 1348 -> 1437, 1416 -> 1496, 1454 -> 1552 TFLOP/s
+  // at B = 64 -- and 3..7 % SLOWER on launches of at most one wave, where neither L2 traffic nor power is the limit and the cluster launch
+  // and the two cluster barriers are pure overhead: pairs only above one wave)
+  p.pair = (pair_on && !halo && bn == 256 && p.ksplit == 1 && m_tiles % 2 == 0 && (pair_mode >= 2 || m_tiles * cdiv(d->Cout, bn) > sm_count())) ? 1 : 0;
+  g_last_pair = p.pair;
   // ---- B maps: weights [tap][Cout][Cin]
   {
     const int wrows = d->w_rows > 0 ? d->w_rows : d->Cout;
-    WSR_REQUIRE(wrows >= bn || wrows % 64 == 0 || true, WSR_E_INVALID, "conv_tc: w_rows");
     uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)wrows, (uint64_t)wtaps};
     uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cin * wrows * 2};
-    uint32_t box[3] = {64, (uint32_t)bn, 1};
+    uint32_t box[3] = {64, (uint32_t)(p.pair ? bn / 2 : bn), 1};
     rc = encode_map(&p.bmap[0], d->w, 3, dims, str, box);
     if (rc) return rc;
     p.bmap[1] = p.bmap[0];

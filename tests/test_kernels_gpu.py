@@ -152,7 +152,32 @@ def test_conv_tc_split_k_vs_simt(case):
         nat.call("wsr_debug_set_splitk", prev)
 
 
-def _split_k_case(N, Cin, Cout, H, W, k, stride, up, Cin2, expect):
+PAIR_CASES = [
+    # N, Cin, Cout, H, W, k, stride, up, Cin2: classic-mode launches with 256-column tiles and an even number of row tiles
+    (64, 512, 512, 8, 16, 3, 1, False, 0),
+    (64, 512, 512, 8, 16, 3, 1, False, 1024),          # fused 1x1 res_conv segment (second weight map)
+    (64, 256, 512, 16, 32, 3, 2, False, 0),            # stride 2 (phase-subsampled activation maps)
+    (64, 512, 512, 8, 16, 3, 1, True, 0),              # nearest-x2 + 3x3, four phase launches
+    (64, 512, 1536, 8, 16, 1, 1, False, 0),            # 1x1 q | k | v projection, 6 column tiles
+    (64, 256, 768, 8, 16, 3, 1, False, 0),             # odd number of column tiles
+    (16, 768, 256, 32, 64, 3, 1, False, 0),            # 64-pixel rows (two image rows per tile), several tiles per pair
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv_tc_cta_pair_vs_simt(case):
+    """CTA pairs (tcgen05 cta_group::2) of the classic-mode 256-column convolution tiles: two CTAs of a 2-wide cluster share one
+    256 x 256 tile, each stages its own 128 rows of activations and HALF of the weight columns, the leader issues the MMAs for both and
+    commits to the barriers of both, both run the epilogue on their own TMEM rows.  By default only launches of more than one wave take
+    this path; the test forces it (wsr_debug_set_pair(2)) and checks that it really ran (bit 20 of wsr_debug_last_tc_config)."""
+    prev = nat.call("wsr_debug_set_pair", 2)
+    try:
+        _split_k_case(*case, expect=False, expect_pair=True)
+    finally:
+        nat.call("wsr_debug_set_pair", prev)
+
+
+def _split_k_case(N, Cin, Cout, H, W, k, stride, up, Cin2, expect, expect_pair=None):
     torch.manual_seed(12)
     dev = _dev()
     eng = Engine(dev, "bf16")
@@ -184,6 +209,8 @@ def _split_k_case(N, Cin, Cout, H, W, k, stride, up, Cin2, expect):
         eng.conv(xa, pc, y_tc, **kw)
         cfg = nat.call("wsr_debug_last_tc_config")
         assert ((cfg & 0xff) > 1) == expect, (cfg >> 8, cfg & 0xff)
+        if expect_pair is not None:
+            assert bool(cfg >> 20) == expect_pair, ((cfg >> 8) & 0xfff, cfg >> 20)
         got = y_tc.to_nchw(eng)
         err = rel_l2(got, ref)
         assert err < (8e-3 if up else 4e-3), (rep, err)          # merged upsample taps are summed before the bf16 rounding

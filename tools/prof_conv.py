@@ -17,8 +17,10 @@ SHAPES = [  # Cin, Cout, H, W, k, stride, up, Cin2
     (512, 512, 16, 32, 3, 1, False, 0), (1024, 512, 16, 32, 3, 1, False, 0), (512, 512, 16, 32, 1, 1, False, 0), (512, 1024, 16, 32, 1, 1, False, 0),
     (256, 256, 32, 64, 3, 1, False, 0), (768, 256, 32, 64, 3, 1, False, 0),
 ]
+if os.environ.get("WSR_PROF_SHAPES"):      # comma-separated indices into SHAPES (ncu captures of one shape)
+    SHAPES = [SHAPES[int(i)] for i in os.environ["WSR_PROF_SHAPES"].split(",")]
 eng = eng_mod.Engine(dev, "bf16")
-R = 20
+R = int(os.environ.get("WSR_PROF_REPS", "20"))
 for (Cin, Cout, H, W, k, stride, up, Cin2) in SHAPES:
     torch.manual_seed(0)
     x = eng.new_act(B, H, W, Cin); x.buf.normal_()
@@ -54,4 +56,4 @@ for (Cin, Cout, H, W, k, stride, up, Cin2) in SHAPES:
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / (5 * R)
     fl = 2 * B * OH * OW * Cout * (k * k * Cin + Cin2)
-    print("B=%d %4d->%4d k%d s%d %3dx%-3d +%4d : bn=%3d S=%d  %7.2f us  %7.1f TFLOP/s" % (B, Cin, Cout, k, stride, H, W, Cin2, cfg >> 8, cfg & 0xff, us, fl / us / 1e6), flush=True)
+    print("B=%d %4d->%4d k%d s%d %3dx%-3d +%4d : bn=%3d S=%d  %7.2f us  %7.1f TFLOP/s" % (B, Cin, Cout, k, stride, H, W, Cin2, (cfg >> 8) & 0xfff, (cfg & 0xff) + 100 * (cfg >> 20), us, fl / us / 1e6), flush=True)
