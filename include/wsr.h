@@ -85,10 +85,8 @@ typedef struct {
    * pixels): [kx][3 * 64 rows][Cin], row block b of slice kx = the 64 (zero-padded) output channels of tap (ky = 2 - b, kx),
    * dtype = x_dtype (wsr_pack_conv_weight_vmerge).  NULL = not available. */
   const void* w_vmerge;
-  /* optional split-K workspace of wsr_conv_tc / wsr_conv_taps_tc (caller-owned, splitk_ws_bytes >= 32768 + tiles * splits * 128 *
-   * BN * 4; its first 32768 bytes are counters that MUST be zero before the first use -- the kernels leave them zero).  When a layer's
-   * tiles do not fill the SMs (deep levels at small batch) the K loop of each tile is cut across several CTAs that exchange fp32
-   * partial tiles through this buffer.  One workspace serves all launches of a stream; NULL = never split. */
+  /* reserved (round 1 exchanged split-K partial tiles through this caller-owned buffer; the split-K kernels now form a thread-block
+   * cluster per tile and exchange the partials through distributed shared memory, so nothing is read or written here).  Pass NULL / 0. */
   void* splitk_ws; long long splitk_ws_bytes;
 } WsrConvDesc;
 
@@ -100,13 +98,19 @@ int wsr_conv_tc(const WsrConvDesc* d, void* stream);
 int wsr_conv_tc_can_fuse_gn(const WsrConvDesc* d);
 /* test introspection: (CTA pairs << 20) | (column-tile width << 8) | K splits chosen by the most recent wsr_conv_tc / wsr_conv_taps_tc call */
 int wsr_debug_last_tc_config(void);
-/* split-K of the classic-mode tcgen05 convolution is correct but measured no faster than the unsplit kernel on B200, so
- * it is off unless WSR_SPLITK=1 or this switch is set; returns the previous setting. */
+/* split-K of the classic-mode tcgen05 convolution (a cluster of 2 / 4 / 8 CTAs per tile, each accumulating a range of the K blocks; partial
+ * tiles exchanged through distributed shared memory) is correct but measured at most 15 % faster per launch and slower for the whole step
+ * on B200, so it is off unless WSR_SPLITK=1 or this switch is set; returns the previous setting. */
 int wsr_debug_set_splitk(int on);
 /* CTA pairs (tcgen05 cta_group::2: two SMs of a TPC share one 256 x 256 tile, each staging half of the weight columns) for the classic-mode
  * 256-column convolution tiles: 0 = never, 1 = launches of more than one wave (default; env WSR_PAIR), 2 = every eligible launch (an even
  * number of row tiles).  Returns the previous mode.  wsr_debug_last_tc_config() reports the choice in bit 20. */
 int wsr_debug_set_pair(int mode);
+/* Programmatic dependent launch for the kernels launched after this call (convolutions, GroupNorm apply, small attention, head): a kernel
+ * may start its prologue while its predecessor drains.  Off by default (no gain at 64 images per GPU, where the device runs under its power
+ * cap; env WSR_PDL=1 switches it on); the sampling loop switches it on around the graph capture of small batches.  Returns the previous
+ * setting (-1 = undecided). */
+int wsr_set_pdl(int on);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Tap-table convolution: the same kernels driven by an explicit list of taps instead of (ksize, stride, upsample).

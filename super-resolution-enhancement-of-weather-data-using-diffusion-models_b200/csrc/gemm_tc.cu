@@ -76,11 +76,10 @@ struct TcParams {
   // write the 128B-swizzled tile themselves (out-of-image pixels stay zero = the convolution's padding of the
   // NORMALISED tensor).  gn_tab: [N][gn_ld] float2 (scale, shift) from wsr_gn_finalize.
   // split-K (SPLIT kernels, classic mode, one work item per CTA): the K blocks of a tile are cut into `ksplit` contiguous ranges of
-  // `kb_split` blocks, CTA (tile, s) accumulates range s; partial tiles go through the fp32 workspace `ws` ([tile][split][128][BN])
-  // and each CTA finishes the 32-column chunks ch with ch % ksplit == s.  ctr: [tile][2] arrival / completion counters, zero
-  // between launches (the last CTA of a tile restores the zeros).
+  // `kb_split` blocks; the `ksplit` CTAs of a tile form a thread-block CLUSTER, CTA s accumulates range s in its own tensor memory, then
+  // the partial tiles are exchanged through distributed shared memory: CTA s finishes the 32-column chunks ch with ch % ksplit == s and
+  // receives the other CTAs' partials of those chunks in its (by then idle) operand ring.
   int ksplit, kb_split;
-  float* ws; unsigned* ctr;
   int prefetch;                 // halo mode: L2-prefetch the halo box two loads ahead (see the producer)
   int pair;                     // classic mode, N = 256: run as CTA pairs (PAIR kernels); the weight map's box is then 128 rows
   const void* xg; int xg_ld, xg_H, xg_W;
@@ -189,7 +188,11 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
   constexpr int kRowMax = 6;
   uint64_t* row_raw = full_raw + 2;                          // [2][kRowMax]
   uint64_t* row_rdy = row_raw + 2 * kRowMax;                 // [2][kRowMax]
-  uint32_t* tmem_slot = (uint32_t*)(row_rdy + 2 * kRowMax);
+  // SPLIT: done_bar -- every CTA of the cluster has finished its K range (its operand ring may be overwritten); recv_bar -- every other
+  // CTA has delivered its partials of this CTA's chunks
+  uint64_t* done_bar = row_rdy + 2 * kRowMax;
+  uint64_t* recv_bar = done_bar + 1;
+  uint32_t* tmem_slot = (uint32_t*)(recv_bar + 1);
   static_assert(!FUSE || ROWS + 2 <= kRowMax, "row barriers");
   uint8_t* smem_b = smem + Cfg::kAStages * kHaloStage;      // halo mode only
 
@@ -227,6 +230,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
     if constexpr (FUSE) {
       for (int i = 0; i < 2 * kRowMax; ++i) { mbar_init(&row_raw[i], 1); mbar_init(&row_rdy[i], kXfWarps); }
     }
+    if constexpr (SPLIT) { mbar_init(done_bar, (uint32_t)p.ksplit); mbar_init(recv_bar, (uint32_t)((p.ksplit - 1) * kEpiWarps)); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -241,7 +245,7 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
   }
   tc_fence_before();
   // PAIR: the peer must not signal this CTA's barriers (TMA transaction bytes, MMA commits, accumulator hand-back) before they exist
-  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
+  if constexpr (PAIR || SPLIT) cluster_sync_all(); else __syncthreads();      // SPLIT: peers arrive on done_bar / recv_bar and write into the ring
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // FUSE: register re-balancing between the warpgroups (see kXfWarps) -- the setmaxnreg of each role is the FIRST statement of its
@@ -744,36 +748,33 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
         __syncwarp();
       }
       if constexpr (SPLIT) {
-        // phase A: the chunks another split finishes go to the workspace as fp32 partials (each lane writes 128 contiguous bytes of
-        // its own row), then every CTA of the tile waits until all partials are there.  All CTAs of the launch are resident (grid
-        // <= number of SMs, one CTA per SM), so spinning on the arrival counter cannot deadlock.
-        float* wsp = p.ws + ((long long)(tile * p.ksplit + split_s) * kBlockM + row) * BLOCK_N;
+        // this CTA's MMAs are complete: its operand ring is dead.  Tell the whole cluster, then wait until every ring is (the
+        // partials land in the rings).
+        const uint32_t S = (uint32_t)p.ksplit;
+        if (warp == 0 && (uint32_t)lane < S) mbar_arrive_remote_release(done_bar, (uint32_t)lane);
+        mbar_wait_cluster(done_bar, 0);
+        // phase A: the chunks another CTA finishes go to that CTA's shared memory as fp32 partials: slot (chunk / S, source), one
+        // 128-byte row per lane, 16-byte pieces XOR-swizzled by the row so that a warp's stores spread over all banks
+        const uint32_t ring = smem_u32(smem);
 #pragma unroll 1
         for (int ci = 0; ci < kChunksPerWarp; ++ci) {
           const int ch = ch_begin + ci;
-          if (ch % p.ksplit == split_s) continue;
+          const uint32_t owner = (uint32_t)ch % S;
+          if (owner == (uint32_t)split_s) continue;
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * Cfg::kAccCols + ch * 32), v);
-          float4* dst = (float4*)(wsp + ch * 32);
+          const uint32_t src_idx = (uint32_t)split_s < owner ? (uint32_t)split_s : (uint32_t)split_s - 1u;
+          const uint32_t slot = ((uint32_t)(ch / (int)S) * (S - 1u) + src_idx) * (uint32_t)(kBlockM * 128) + (uint32_t)row * 128u;
+          const uint32_t dst = dsmem_addr(ring + slot, owner);
           if (!(p.dbg & 16)) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              __stcg(dst + q, make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])));
+            for (int q = 0; q < 8; ++q) dsmem_st4(dst + (uint32_t)((q ^ (row & 7)) << 4), v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
         }
-        __threadfence();
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-        if (threadIdx.x == 0) {
-          // one 128-byte line per tile: arrival counter at [tile * 32], completion counter at [tile * 32 + 1]
-          unsigned* arrive = p.ctr + tile * 32;
-          atomicAdd(arrive, 1u);
-          unsigned seen;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrive) : "memory");
-            if (seen < (unsigned)p.ksplit) __nanosleep(100);
-          } while (seen < (unsigned)p.ksplit && !(p.dbg & 8));
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        fence_acq_rel_cluster();
+        __syncwarp();
+        if ((uint32_t)lane < S && lane != split_s) mbar_arrive_remote_release(recv_bar, (uint32_t)lane);
+        mbar_wait_cluster(recv_bar, 0);
       }
 #pragma unroll 1
       for (int rr = 0; rr < ROWS; ++rr) {
@@ -795,13 +796,13 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * Cfg::kAccCols + rr * BLOCK_N + ch * 32), v);
         if constexpr (SPLIT) {
-          // phase B: this CTA owns the chunk -- add the other splits' partials (L2 reads, never through L1)
-          for (int s2 = 0; s2 < ((p.dbg & 32) ? 0 : p.ksplit); ++s2) {
-            if (s2 == split_s) continue;
-            const float4* src = (const float4*)(p.ws + ((long long)(tile * p.ksplit + s2) * kBlockM + row) * BLOCK_N + ch * 32);
+          // phase B: this CTA owns the chunk -- add the other CTAs' partials out of the ring
+          const int S = p.ksplit;
+          for (int si = 0; si < ((p.dbg & 32) ? 0 : S - 1); ++si) {
+            const uint8_t* src = smem + ((size_t)((ch / S) * (S - 1) + si) * kBlockM + row) * 128;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const float4 t4 = __ldcg(src + q);
+              const float4 t4 = *(const float4*)(src + ((q ^ (row & 7)) << 4));
               v[4 * q] = __float_as_uint(__uint_as_float(v[4 * q]) + t4.x); v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + t4.y);
               v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + t4.z); v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + t4.w);
             }
@@ -1059,14 +1060,6 @@ __global__ void __launch_bounds__(FUSE ? kTcThreadsFused : kTcThreads, 1) gemm_t
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]); }
-      if constexpr (SPLIT) {
-        // every CTA of the tile has passed the arrival spin before it gets here, so the last one may restore the zeros
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-        if (threadIdx.x == 0) {
-          const unsigned done = atomicAdd(p.ctr + tile * 32 + 1, 1u);
-          if (done == (unsigned)p.ksplit - 1) { p.ctr[tile * 32] = 0u; p.ctr[tile * 32 + 1] = 0u; __threadfence(); }
-        }
-      }
     }
     if (p.stats != nullptr) flush_stats();
   }
@@ -1140,14 +1133,28 @@ static int launch_tc_impl(const TcParams& p, cudaStream_t st) {
     WSR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE, VM, STG, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  int total = p.g1 * p.g2 * p.g3 * p.nbatch * p.n_tiles;
-  int grid = total < sm_count() ? total : sm_count();
-  if (SPLIT) {
-    grid = total * p.ksplit;
-    WSR_REQUIRE(p.ksplit >= 2 && grid <= sm_count() && p.ws != nullptr && p.ctr != nullptr, WSR_E_INVALID, "gemm_tc: split-K launch invariants");
+  const int total = p.g1 * p.g2 * p.g3 * p.nbatch * p.n_tiles;
+  if constexpr (SPLIT) {
+    // one cluster of ksplit CTAs per tile (CTA rank in the cluster = K range)
+    WSR_REQUIRE(p.ksplit >= 2 && p.ksplit <= 8 && p.ksplit <= BLOCK_N / 32 && (BLOCK_N / 32) % p.ksplit == 0, WSR_E_INVALID, "gemm_tc: split-K launch invariants");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(total * p.ksplit);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = (size_t)Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)p.ksplit; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    WSR_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE, VM, STG, SPLIT>, p));
+  } else {
+    const int grid = total < sm_count() ? total : sm_count();
+    WSR_CUDA_OK(launch_pdl(gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE, VM, STG, SPLIT>, dim3(grid), dim3(FUSE ? kTcThreadsFused : kTcThreads),
+                           (size_t)Cfg::kSmemBytes, st, p));
   }
-  WSR_CUDA_OK(launch_pdl(gemm_tc_kernel<BLOCK_N, HALO, ROWS, FUSE, VM, STG, SPLIT>, dim3(grid), dim3(FUSE ? kTcThreadsFused : kTcThreads),
-                         (size_t)Cfg::kSmemBytes, st, p));
   return WSR_OK;
 }
 
@@ -1235,11 +1242,9 @@ static int launch_tc(const TcParams& p, cudaStream_t st) {
     }
     return stg ? launch_tc_impl<BLOCK_N, true, 1, false, false, true>(p, st) : launch_tc_impl<BLOCK_N, true, 1>(p, st);
   }
-  if constexpr (BLOCK_N >= 128) {
-    if (p.ksplit > 1) {
-      WSR_REQUIRE(sok, WSR_E_INVALID, "gemm_tc: split-K chosen without the staged-epilogue preconditions");
-      return launch_tc_impl<BLOCK_N, false, 1, false, false, true, true>(p, st);
-    }
+  if (p.ksplit > 1) {
+    WSR_REQUIRE(sok, WSR_E_INVALID, "gemm_tc: split-K chosen without the staged-epilogue preconditions");
+    return launch_tc_impl<BLOCK_N, false, 1, false, false, true, true>(p, st);
   }
   if constexpr (BLOCK_N == 256) {
     if (p.pair) return (sok && (stage_mask() & 4)) ? launch_tc_pair<true>(p, st) : launch_tc_pair<false>(p, st);
@@ -1249,57 +1254,59 @@ static int launch_tc(const TcParams& p, cudaStream_t st) {
 }
 
 // Split-K plan for a classic-mode launch whose tiles do not fill the machine (deep UNet levels at small batch: 8 .. 64 row tiles for
-// 148 SMs).  Cost model in cycles per CTA, from the same B200 measurements as pick_block_n: a 128 x BN x 64 K block costs
-// 4 * (69 + 0.28 BN); a split adds the partial-tile round trip through L2 and one inter-CTA wait (~2000 + 8 BN (S-1)/S).  Returns the
-// chosen BN and sets *ksplit (1 = no split).  Split-K needs BN >= 128 (S <= BN / 32 column chunks to distribute), at least 4 K blocks
-// per split, tiles * S <= SMs and the caller's workspace.
-constexpr int kSplitHeader = 32768;               // bytes of counters at the head of the split-K workspace (one 128-byte line per tile)
-static int g_last_ksplit = 1, g_last_bn = 0, g_last_pair = 0;
+// 148 SMs).  What bounds such a launch is the operand fetch of each CTA -- one SM receives at most ~65 bytes per clock from L2
+// (tools/tma_probe.cu, profiles/r02_tma_probe.txt), and a 128 x BN x 64 K block needs 16 KB + BN * 128 B -- or its MMAs, 4 * (69 + 0.28 BN)
+// cycles; cutting the K loop over the S CTAs of a cluster divides both, at the price of the partial-tile exchange through distributed
+// shared memory (~1500 cycles of barriers + (S-1)/S * BN * 512 B at ~32 B per clock).  Returns the chosen BN and sets *ksplit (1 = no
+// split).  S is a power of two that divides the BN / 32 column chunks; at least 4 K blocks per split; tiles * S <= SMs.
+// MEASURED on B200 (tools/prof_conv.py, profiles/r02_splitk_cluster_sweep.txt; 512->512 3x3 @8x16, 8 images, unsplit BN = 64: 24.7 us):
+// BN 64 / S 2: 21.1 us, BN 128 / S 2 and S 4: 22.9 / 22.7 us, BN 256 / S 2 and S 4: 27.3 us, BN 256 / S 8: 56 us.  The launch is
+// t = 5.3 us + 0.27 us per K block; halving the K loop saves 9.7 us and the cluster launch + two cluster-wide barrier rounds + the
+// exchange give 6 us of it back, and clusters of 8 do not even fit one wave.  Whole step at 8 images per GPU: 3.38 ms without, 3.90 ms
+// with the model's choice.  So split-K stays OFF unless WSR_SPLITK=1 (the round-1 global-memory exchange was worse still: 30 us).
+static int g_last_ksplit = 1, g_last_bn = 0, g_last_pair = 0;      // introspection for the tests (wsr_debug_last_tc_config)
 static int g_pair_mode = -1;                      // -1 = read WSR_PAIR on first use; wsr_debug_set_pair overrides
-static int g_splitk_on = 0;                       // wsr_debug_set_splitk (tests); the environment variable WSR_SPLITK=1 does the same      // introspection for the tests (wsr_debug_last_tc_config)
+static int g_splitk_on = -1;                      // -1 = read WSR_SPLITK on first use (default off); wsr_debug_set_splitk overrides
 
-static int pick_split(int ncols, int m_tiles, int total_kb, long long ws_bytes, int bn_nosplit, int* ksplit) {
+static double kblock_cycles(int bn) {
+  const double fetch = (16384.0 + bn * 128.0) / 65.0, mma = 4.0 * (69.0 + 0.28 * bn);
+  return fetch > mma ? fetch : mma;
+}
+
+static int pick_split(int ncols, int m_tiles, int total_kb, int bn_nosplit, int* ksplit) {
   *ksplit = 1;
-  // MEASURED on B200 (tools/prof_conv.py, profiles/r02_splitk_sweep.txt): at the shapes this was built for (8x16 / 16x32 levels at 8
-  // samples per GPU) the kernel time does not depend on how the work is cut -- 512->512 k3 @8x16, B = 8: 24.5 us with 64 CTAs (BN 64),
-  // 29.7 us with 16 CTAs (BN 256), 30.4 / 29.6 / 33.5 us with 2 / 4 / 8 K splits, and the SAME 31.7 us with the MMA issue disabled:
-  // these launches are bound by the latency of the TMA operand fetch (~190 KB in flight per SM / 1.4 .. 5 us), not by the tensor pipe
-  // or the CTA count, and the partial-tile round trip of a split adds 9 + 5 us.  Split-K is therefore OFF unless WSR_SPLITK=1.
-  static const bool env_on = getenv("WSR_SPLITK") != nullptr && atoi(getenv("WSR_SPLITK")) != 0;
-  static const bool off = getenv("WSR_NO_SPLITK") != nullptr;
+  if (g_splitk_on < 0) g_splitk_on = getenv("WSR_SPLITK") ? (atoi(getenv("WSR_SPLITK")) != 0 ? 1 : 0) : 0;
   static const bool forced = getenv("WSR_SPLITK_FORCE") != nullptr;
-  if ((!env_on && !forced && !g_splitk_on) || off || ws_bytes <= 0) return bn_nosplit;
+  if (!g_splitk_on && !forced) return bn_nosplit;
   const int sms = sm_count();
   // WSR_SPLITK_FORCE="bn,S": measurement override (tools/prof_conv.py); ignored when the plan is not feasible
   static const char* force = getenv("WSR_SPLITK_FORCE");
   if (force) {
     int fbn = 0, fs = 0;
-    if (sscanf(force, "%d,%d", &fbn, &fs) == 2 && (fbn == 128 || fbn == 256) && ncols % fbn == 0) {
+    if (sscanf(force, "%d,%d", &fbn, &fs) == 2 && (fbn == 64 || fbn == 128 || fbn == 256) && ncols % fbn == 0) {
       const int tiles = m_tiles * (ncols / fbn);
       const int per = fs > 0 ? (total_kb + fs - 1) / fs : 0;
-      if (fs >= 2 && fs <= fbn / 32 && tiles * fs <= sms && per >= 1 && (fs - 1) * per < total_kb &&
-          (long long)tiles * fs * kBlockM * fbn * 4 + kSplitHeader <= ws_bytes && tiles * 128 <= kSplitHeader) { *ksplit = fs; return fbn; }
+      if ((fs == 2 || fs == 4 || fs == 8) && fs <= fbn / 32 && tiles * fs <= sms && per >= 1 && (fs - 1) * per < total_kb) { *ksplit = fs; return fbn; }
       if (fs == 1) return fbn;
     }
     return bn_nosplit;
   }
   const double base_tiles = (double)m_tiles * ((ncols + bn_nosplit - 1) / bn_nosplit);
-  const double base = ceil(base_tiles / sms) * total_kb * 4.0 * (69.0 + 0.28 * bn_nosplit);
+  const double base = ceil(base_tiles / sms) * total_kb * kblock_cycles(bn_nosplit);
   double best = base * 0.85;                       // split only for a clear win
   int best_bn = bn_nosplit;
-  const int cand_bn[2] = {256, 128};
-  const int cand_s[7] = {2, 3, 4, 5, 6, 7, 8};
-  for (int i = 0; i < 2; ++i) {
+  const int cand_bn[3] = {256, 128, 64};
+  const int cand_s[3] = {2, 4, 8};
+  for (int i = 0; i < 3; ++i) {
     const int bn = cand_bn[i];
     if (ncols % bn != 0) continue;
     const int tiles = m_tiles * (ncols / bn);
-    for (int j = 0; j < 7; ++j) {
+    for (int j = 0; j < 3; ++j) {
       const int S = cand_s[j];
       if (S > bn / 32 || tiles * S > sms) continue;
       const int per = (total_kb + S - 1) / S;
       if (per < 4 || (S - 1) * per >= total_kb) continue;
-      if ((long long)tiles * S * kBlockM * bn * 4 + kSplitHeader > ws_bytes || tiles * 128 > kSplitHeader) continue;
-      const double cost = per * 4.0 * (69.0 + 0.28 * bn) + 2000.0 + 8.0 * bn * (S - 1) / S;
+      const double cost = per * kblock_cycles(bn) + 1500.0 + 16.0 * bn * (S - 1) / S;
       if (cost < best) { best = cost; best_bn = bn; *ksplit = S; }
     }
   }
@@ -1350,7 +1357,10 @@ extern "C" int wsr_debug_set_pair(int mode) {
   if (g_pair_mode < 0) g_pair_mode = getenv("WSR_PAIR") ? atoi(getenv("WSR_PAIR")) : 1;
   const int prev = g_pair_mode; g_pair_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode); return prev;
 }
-extern "C" int wsr_debug_set_splitk(int on) { const int prev = g_splitk_on; g_splitk_on = on ? 1 : 0; return prev; }
+extern "C" int wsr_debug_set_splitk(int on) {
+  if (g_splitk_on < 0) g_splitk_on = getenv("WSR_SPLITK") ? (atoi(getenv("WSR_SPLITK")) != 0 ? 1 : 0) : 0;
+  const int prev = g_splitk_on; g_splitk_on = on ? 1 : 0; return prev;
+}
 
 extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
   int rc = validate_conv_desc(d);
@@ -1405,14 +1415,13 @@ extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {
   const bool halo = !no_halo && d->ksize == 3 && d->stride == 1 && p.t2 == 1 && p.t3 == 1 && p.t1 + 2 <= 130;
   // split-K (classic tiles that do not fill the machine; needs the caller's workspace and the staged-epilogue preconditions)
   p.ksplit = 1;
-  if (!halo && d->splitk_ws != nullptr && d->gn_table == nullptr && stage_preconditions(p, 128)) {
+  if (!halo && d->gn_table == nullptr && stage_preconditions(p, 64)) {
     const int kb_est = (merged ? 4 : taps) * (d->Cin / 64) + (d->x2 ? d->Cin2 / 64 : 0);
     int ks = 1;
-    const int bn2 = pick_split(d->Cout, m_tiles, kb_est, d->splitk_ws_bytes, bn, &ks);
-    bn = bn2;
-    if (ks > 1) {
-      p.ksplit = ks; p.kb_split = (kb_est + ks - 1) / ks;
-      p.ctr = (unsigned*)d->splitk_ws; p.ws = (float*)((uint8_t*)d->splitk_ws + kSplitHeader);
+    const int bn2 = pick_split(d->Cout, m_tiles, kb_est, bn, &ks);
+    if (ks == 1 || stage_preconditions(p, bn2)) {
+      bn = bn2;
+      if (ks > 1) { p.ksplit = ks; p.kb_split = (kb_est + ks - 1) / ks; }
     }
   }
   // vertical tap merge (N = 64, plain 3x3): three output rows per tile, needs the vmerge weight pack (w_vmerge)
@@ -1620,14 +1629,13 @@ extern "C" int wsr_conv_taps_tc(const WsrConvDesc* d, const WsrTapTable* t, void
   int bn = pick_block_n(d->Cout, m_tiles);
   p.n_taps = 0; p.halo_rows = 1;
   p.ksplit = 1;
-  if (d->splitk_ws != nullptr && stage_preconditions(p, 128)) {
+  if (stage_preconditions(p, 64)) {
     const int kb_est = t->ntaps * (d->Cin / 64);
     int ks = 1;
-    const int bn2 = pick_split(d->Cout, m_tiles, kb_est, d->splitk_ws_bytes, bn, &ks);
-    bn = bn2;
-    if (ks > 1) {
-      p.ksplit = ks; p.kb_split = (kb_est + ks - 1) / ks;
-      p.ctr = (unsigned*)d->splitk_ws; p.ws = (float*)((uint8_t*)d->splitk_ws + kSplitHeader);
+    const int bn2 = pick_split(d->Cout, m_tiles, kb_est, bn, &ks);
+    if (ks == 1 || stage_preconditions(p, bn2)) {
+      bn = bn2;
+      if (ks > 1) { p.ksplit = ks; p.kb_split = (kb_est + ks - 1) / ks; }
     }
   }
   const bool fuse_stats = d->gn_stats != nullptr && (p.t1 * p.t2) % 32 == 0;

@@ -105,9 +105,7 @@ class Engine:
         self.prof = None         # list of (name, flops, bytes, start_event, end_event) when profiling
         self.prof_detail = False
         self.no_fused_attention = False
-        # split-K workspace of the tcgen05 convolutions (WsrConvDesc.splitk_ws): counters (zero) + fp32 partial tiles; one per engine =
-        # one per stream.  148 CTAs x 128 x 256 x 4 bytes = 19.4 MB is the most a launch can use.
-        self.splitk_ws = torch.zeros(32768 + 148 * 128 * 256 * 4, device=self.device, dtype=torch.uint8) if self.use_tc else None
+        self.splitk_ws = None          # WsrConvDesc.splitk_ws is reserved: split-K partials travel through distributed shared memory
 
     # ---- plumbing -------------------------------------------------------------------------------------------------
     def call(self, name, *args, flops=0, nbytes=0, tag=None, xflops=None):

@@ -9,6 +9,7 @@ instead of ~610 eager launches plus a host->device copy (reference diffusion.py:
 from abc import abstractmethod
 
 import numpy as np
+import os
 import torch
 from torch import nn
 
@@ -247,8 +248,16 @@ class ReverseLoop:
     def capture(self):
         torch.cuda.synchronize(self.plan.eng.device)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.step()
+        # small batches (<= 8 images of 128x256 per GPU -- the sharded benchmark): the ~190 launches of a step are short enough for the
+        # gaps between them to show, so the graph is captured with programmatic dependent launch (wsr.h: wsr_set_pdl); WSR_PDL overrides
+        small = self.x.shape[0] * self.x.shape[-2] * self.x.shape[-1] <= 8 * 128 * 256
+        prev = nat.call("wsr_set_pdl", 1) if (small and "WSR_PDL" not in os.environ) else None
+        try:
+            with torch.cuda.graph(self.graph):
+                self.step()
+        finally:
+            if prev is not None:
+                nat.call("wsr_set_pdl", max(prev, 0))
         return self.graph
 
     def replay(self):

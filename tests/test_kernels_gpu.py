@@ -139,11 +139,11 @@ SPLITK_CASES = [
 
 @pytest.mark.parametrize("case", SPLITK_CASES)
 def test_conv_tc_split_k_vs_simt(case):
-    """Split-K of the classic-mode tcgen05 convolution (tiles that do not fill the SMs): fp32 partial tiles through the
-    workspace, distributed fix-up with bias / time-embedding row / residual / GroupNorm statistics in the epilogue; compared
-    with the SIMT kernel on the same bf16 operands, run twice (the arrival counters must be left at zero).  The path is correct
-    but measured no faster than the unsplit kernel on B200, so it is off by default; the test switches it on
-    (wsr_debug_set_splitk) for its own launches only."""
+    """Split-K of the classic-mode tcgen05 convolution (tiles that do not fill the SMs): the CTAs of a thread-block cluster each
+    accumulate a range of the K blocks and exchange fp32 partial tiles through distributed shared memory; distributed fix-up with
+    bias / time-embedding row / residual / GroupNorm statistics in the epilogue; compared with the SIMT kernel on the same bf16
+    operands, run twice.  The path is correct but measured not worth it on B200, so it is off by default; the
+    test switches it on (wsr_debug_set_splitk) for its own launches only."""
     N, Cin, Cout, H, W, k, stride, up, Cin2, expect = case
     prev = nat.call("wsr_debug_set_splitk", 1)
     try:
@@ -218,8 +218,6 @@ def _split_k_case(N, Cin, Cout, H, W, k, stride, up, Cin2, expect, expect_pair=N
         st = arena.tensor.view(N, Cout, 2)
         assert rel_l2(st[..., 0].float(), got.double().sum((2, 3)).float()) < 2e-3
         assert rel_l2(st[..., 1].float(), (got.double() ** 2).sum((2, 3)).float()) < 2e-3
-    ws = eng.splitk_ws[:32768].view(torch.int32)
-    assert int(ws.abs().sum()) == 0                               # counters restored
 
 
 @pytest.mark.parametrize("hw", [(16, 32), (4, 128)])
