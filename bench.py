@@ -511,10 +511,14 @@ def measure_train(ctx, args, steps, warmup, profile=False):
         ms_noar, _, _ = timed(steps, reduce=False)
         plan.on_ready = reducer._on_ready
     if profile and rank == 0:
+        # issued call by call (no launch-list replay): with the per-launch events on, the weight-gradient launches stay on the main
+        # stream (unet_train._on_side), so every kernel is timed alone
+        plan.replay_enabled = False
         plan.eng.prof = []
         step()
         summ = plan.eng.prof_summary()
         plan.eng.prof = None
+        plan.replay_enabled = True
         tot = sum(v[1] for v in summ.values())
         print("# per-op breakdown of one training step (B=%d, %s): name launches ms TFLOP/s" % (B, args.train_precision), file=sys.stderr)
         for name, (n, t, fl, nb, xf) in sorted(summ.items(), key=lambda kv: -kv[1][1]):

@@ -302,6 +302,54 @@ class UNetTrainPlan(UNetPlan):
     # ------------------------------------------------------------------------------------------------------------------
     # backward building blocks
     # ------------------------------------------------------------------------------------------------------------------
+    # ---- weight-gradient side stream ---------------------------------------------------------------------------------
+    # Nothing in the backward chain waits for a weight gradient: dW / db of a layer only feed the optimizer (and the gradient
+    # all-reduce), while the chain itself is data gradient -> GroupNorm backward -> data gradient ...  At the reference's batch of 4
+    # per GPU every one of these ~900 launches is far too small to fill 148 SMs, so the weight-gradient launches (a third of the
+    # step's kernel time) go to a second stream and run BESIDE the chain: fork = the side stream waits for everything the main
+    # stream has issued so far (x and dy of the layer are final by then and are not written again during this backward), join =
+    # the main stream waits for the side stream before a gradient range is handed to the all-reduce / optimizer.  Both are host
+    # callbacks in the recorded launch list, so replays fork and join exactly like the recording run.  WSR_WGRAD_STREAM=0: off.
+    def _wstream(self):
+        if not hasattr(self, "_wside"):
+            on = os.environ.get("WSR_WGRAD_STREAM", "1") != "0" and self.eng.device.type == "cuda"
+            self._wside = torch.cuda.Stream(device=self.eng.device) if on else None
+            self._wev_fork = torch.cuda.Event() if on else None
+            self._wev_join = torch.cuda.Event() if on else None
+            self._wforked = False
+        return self._wside
+
+    def _host(self, fn):
+        """Run a host callback now and at the same place in every replay of the launch list being recorded."""
+        if self.eng.rec is not None:
+            self.eng.rec.append((None, fn, "host"))
+        fn()
+
+    def _wfork_fire(self):
+        self._wev_fork.record(torch.cuda.current_stream(self.eng.device))
+        self._wside.wait_event(self._wev_fork)
+        self._wforked = True
+
+    def _wjoin_fire(self):
+        if self._wforked:
+            self._wev_join.record(self._wside)
+            torch.cuda.current_stream(self.eng.device).wait_event(self._wev_join)
+            self._wforked = False
+
+    def _wjoin(self):
+        if self._wstream() is not None:
+            self._host(self._wjoin_fire)
+
+    def _on_side(self, launch):
+        """Issue ``launch()`` on the weight-gradient stream (after everything the main stream has issued so far)."""
+        side = self._wstream()
+        if side is None or self.eng.prof is not None:      # per-launch event timing brackets launches on the main stream
+            launch()
+            return
+        self._host(self._wfork_fire)
+        with torch.cuda.stream(side):
+            launch()
+
     def _wgrad(self, x, dy, conv_mod, taps, up=1, rows=None, bias=True):
         """Weight (+ bias) gradient of ``conv_mod`` (an nn.Conv2d) straight into its OIHW gradient view.
         rows = (lo, hi): only output channels [lo, hi) of the module (split qkv / kv projections)."""
@@ -315,7 +363,7 @@ class UNetTrainPlan(UNetPlan):
         gb = None
         if bias and conv_mod.bias is not None:
             gb = self.gv(conv_mod.bias)[lo:hi]
-        self.eng.wgrad(xs, dy, taps, view, (1, ci * kh * kw, kh * kw), gb, up)
+        self._on_side(lambda: self.eng.wgrad(xs, dy, taps, view, (1, ci * kh * kw, kh * kw), gb, up))
 
     def _gn_bwd(self, x, gn_mod, act, da, dx, red_off, colsum=0, colsum_ld=0, drop=(0.0, 0, 0), gamma=None, beta=None, groups=None):
         self.eng.gn_bwd(x, gamma, beta, groups or self.groups, act, da, dx, self.red.data_ptr() + 8 * red_off,
@@ -354,9 +402,12 @@ class UNetTrainPlan(UNetPlan):
         e.gemm(dvT.data_ptr(), e.dt, (cc * n, 1, n), wv_packed.data_ptr(), e.dt, (0, 1, cc), dn.ptr, dn.dt, (n * dn.ld, dn.ld, 1),
                B, n, cc, cc, res=(dn.ptr, dn.dt, (n * dn.ld, dn.ld, 1)))
         es = 2 if e.dt == nat.BF16 else 4
-        for b in range(B):
-            e.gemm(dvT.data_ptr() + b * cc * n * es, e.dt, (0, n, 1), nact.ptr + b * n * nact.ld * es, nact.dt, (0, 1, nact.ld),
-                   dw_rows.data_ptr(), nat.F32, (0, cc, 1), 1, cc, cc, n, res=(dw_rows.data_ptr(), nat.F32, (0, cc, 1)))
+
+        def dw_launches():
+            for b in range(B):
+                e.gemm(dvT.data_ptr() + b * cc * n * es, e.dt, (0, n, 1), nact.ptr + b * n * nact.ld * es, nact.dt, (0, 1, nact.ld),
+                       dw_rows.data_ptr(), nat.F32, (0, cc, 1), 1, cc, cc, n, res=(dw_rows.data_ptr(), nat.F32, (0, cc, 1)))
+        self._on_side(dw_launches)
 
     def _res_block_bwd(self, r, x):
         """Backward of UNetPlan._res_block; reads G(r.y), accumulates into G(x)."""
@@ -417,6 +468,7 @@ class UNetTrainPlan(UNetPlan):
         self._gn_bwd(ca.x, m.norm, nat.ACT_NONE, d_n, dx, ca.red, gamma=ca.g, beta=ca.b, groups=32)
 
     def _ready(self, mark):
+        self._wjoin()          # the range's weight gradients were computed on the side stream
         if self.eng.rec is not None:
             self.eng.rec.append((None, functools.partial(self._ready_fire, mark), "on_ready"))
         self._ready_fire(mark)
