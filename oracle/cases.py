@@ -50,6 +50,8 @@ CASES = {
     "resdiff_loss_small": dict(kind="resdiff_loss", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=31, t=400),
     # one training step: loss / numel -> backward (model.py:61-69); fixture = per-parameter gradient summaries
     "resdiff_grad_small": dict(kind="resdiff_grad", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=61, t=400),
+    # the BASELINE configs[2] training step itself: Cfg-A UNet at 128x256, batch 4 (HF_guided_CA at level 0 over 8192 keys)
+    "resdiff_grad_full_b4": dict(kind="resdiff_grad", cfg=unet_cfg(128, 256), batch=4, seed=66, t=400),
     "phydiff_grad_small": dict(kind="phydiff_grad", cfg=unet_cfg(32, 64, attn_res=(4,)), batch=2, seed=62, t=350),
     "sr3_grad_small": dict(kind="sr3_grad", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=2), batch=2, seed=63, t=500),
     "srdiff_chain_small": dict(kind="srdiff_chain", cfg=unet_cfg(32, 64, attn_res=(4,), in_channel=1), batch=2, seed=63, T=4),

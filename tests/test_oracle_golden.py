@@ -139,10 +139,12 @@ def test_phy_stencils_known_answer():
     assert float(st[0, 2, 1, 0]) == 2.0 and float(st[0, 2, 1, 7]) == -2.0 and float(st[0, 2, 1, 3]) == 0.0
 
 
-def test_resdiff_param_grads_match_reference():
-    """Oracle autograd vs the gradient summaries of the real reference's training step (model.py:61-68)."""
+@pytest.mark.parametrize("name", ["resdiff_grad_small", "resdiff_grad_full_b4"])
+def test_resdiff_param_grads_match_reference(name):
+    """Oracle autograd vs the gradient summaries of the real reference's training step (model.py:61-68); the second case is the
+    BASELINE configs[2] shape itself (Cfg-A at 128x256, batch 4)."""
     from oracle.cases import grad_summary
-    g, spec = load_golden("resdiff_grad_small"), CASES["resdiff_grad_small"]
+    g, spec = load_golden(name), CASES[name]
     sd = _sd("resdiff", spec["seed"], spec["cfg"])
     np.testing.assert_allclose(_wsum(sd), g["wsum"].numpy(), rtol=1e-9)
     loss, grads = process.resdiff_param_grads(sd, spec["cfg"], g["hr"], g["sr"], g["level"], g["noise"])

@@ -437,6 +437,52 @@ def test_training_step_gradients_vs_reference(arch, precision):
             assert abs(float(summ["norm/" + n]) - ref_norm) <= tol * ref_norm, n
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_training_step_at_benchmark_shape_vs_reference(precision):
+    """BASELINE configs[2] ITSELF -- ResDiff Cfg-A at 128x256, batch 4, HF_guided_CA over 8192 keys at level 0 -- one p_losses +
+    backward against the REAL reference's gradients (tests/golden/resdiff_grad_full_b4.npz, made by oracle/make_golden.py from the
+    reference's own modules on CPU): per parameter tensor the L2 norm, the dot product with a seeded normal probe (a random projection
+    of the error) and, for tensors below 4096 elements (every bias / GroupNorm / squeeze-excite parameter), the whole gradient.  The
+    tile choices of the backward kernels (row-tile shapes, split of the weight-gradient K loop, images per tile) depend on the batch and
+    the resolution, so the 32x64 fixtures do not cover what bench.py --workload train launches.  Tolerances: fp32 check mode 2e-4 per
+    tensor, bf16 1.6e-1 per tensor and 1e-1 on the projected whole-gradient error."""
+    from oracle.cases import grad_summary
+    g, spec = load_golden("resdiff_grad_full_b4"), CASES["resdiff_grad_full_b4"]
+    cfg = spec["cfg"]
+    net, diff = _build(cfg, spec["seed"], precision, "resdiff")
+    loss = _train_backward(diff, g, spec)
+    rel_loss = abs(loss - float(g["loss"])) / float(g["loss"])
+    named = dict(net.named_parameters())
+    assert sorted(named) == sorted(str(n) for n in g["names"])
+    summ = grad_summary([(n, named[n].grad) for n in named], spec["seed"])
+    tol_t, tol_all = (2e-4, 2e-5) if precision == "fp32" else (1.6e-1, 4.0e-2)      # measured on B200: 1.5e-6 / 1.06e-2
+    gscale = math.sqrt(sum(float(g["norm/" + n]) ** 2 for n in named))
+    bad, num = [], 0.0
+    for n in named:
+        ref_norm, got_norm = float(g["norm/" + n]), float(summ["norm/" + n])
+        # the probe is standard normal, so (dot_got - dot_ref) is a one-dimensional random projection of the error vector: its
+        # magnitude estimates |error|
+        proj = abs(float(summ["dot/" + n]) - float(g["dot/" + n]))
+        num += proj ** 2
+        floor = tol_t * 1e-3 * gscale                       # tensors far below the global gradient scale are judged against it
+        small = named[n].numel() < 16 and precision != "fp32"
+        if abs(got_norm - ref_norm) > (1.0 if small else tol_t) * ref_norm + floor:
+            bad.append("%s: |g| %.4e vs %.4e" % (n, got_norm, ref_norm))
+        elif proj > 4.0 * (1.0 if small else tol_t) * ref_norm + 4.0 * floor:
+            bad.append("%s: probe projection of the error %.3e vs |g| %.3e" % (n, proj, ref_norm))
+        if ("full/" + n) in g:
+            ref_full = torch.as_tensor(g["full/" + n]).double().flatten()
+            err = float((named[n].grad.detach().cpu().double().flatten() - ref_full).norm())
+            if err > (1.0 if small else tol_t) * ref_norm + floor:
+                bad.append("%s: full-tensor error %.3e vs |g| %.3e" % (n, err, ref_norm))
+    total = math.sqrt(num) / gscale
+    print("\n[parity] training step at the configs[2] shape (B=4, 128x256) %s: loss rel err %.3e, projected whole-gradient rel error %.3e, "
+          "%d / %d tensors out" % (precision, rel_loss, total, len(bad), len(named)))
+    assert rel_loss < (1e-4 if precision == "fp32" else 2e-2)
+    assert not bad, bad[:10]
+    assert total < tol_all
+
+
 def test_optimize_parameters_decreases_loss_and_flat_adam():
     """Three optimizer steps on a fixed batch through the flat-buffer path: the loss goes down, the parameters move, and
     the one-launch flat Adam equals per-parameter torch.optim.Adam driven by the same gradients."""
