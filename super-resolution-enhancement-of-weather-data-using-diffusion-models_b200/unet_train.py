@@ -330,15 +330,17 @@ class UNetTrainPlan(UNetPlan):
         self._wside.wait_event(self._wev_fork)
         self._wforked = True
 
-    def _wjoin_fire(self):
-        if self._wforked:
+    def _wjoin_fire(self, final):
+        # a gradient range is only consumed early by the bucketed all-reduce (on_ready); without one the single join at the end of the
+        # backward pass is enough, and the side stream may lag behind the chain as far as it likes
+        if self._wforked and (final or self.on_ready is not None):
             self._wev_join.record(self._wside)
             torch.cuda.current_stream(self.eng.device).wait_event(self._wev_join)
             self._wforked = False
 
-    def _wjoin(self):
+    def _wjoin(self, final):
         if self._wstream() is not None:
-            self._host(self._wjoin_fire)
+            self._host(functools.partial(self._wjoin_fire, final))
 
     def _on_side(self, launch):
         """Issue ``launch()`` on the weight-gradient stream (after everything the main stream has issued so far)."""
@@ -468,7 +470,7 @@ class UNetTrainPlan(UNetPlan):
         self._gn_bwd(ca.x, m.norm, nat.ACT_NONE, d_n, dx, ca.red, gamma=ca.g, beta=ca.b, groups=32)
 
     def _ready(self, mark):
-        self._wjoin()          # the range's weight gradients were computed on the side stream
+        self._wjoin(mark == 2)          # the range's weight gradients were computed on the side stream (mark 2 = end of the backward pass)
         if self.eng.rec is not None:
             self.eng.rec.append((None, functools.partial(self._ready_fire, mark), "on_ready"))
         self._ready_fire(mark)
