@@ -325,8 +325,10 @@ class UNetTrainPlan(UNetPlan):
             self.eng.rec.append((None, fn, "host"))
         fn()
 
-    def _wfork_fire(self):
-        self._wev_fork.record(torch.cuda.current_stream(self.eng.device))
+    def _wfork_fire(self, src=None):
+        # src: the stream the launches being forked from were issued on when that is NOT the caller's current stream (the HF-CA branch
+        # stream below); replays run these callbacks with the main stream current
+        self._wev_fork.record(src if src is not None else torch.cuda.current_stream(self.eng.device))
         self._wside.wait_event(self._wev_fork)
         self._wforked = True
 
@@ -348,9 +350,54 @@ class UNetTrainPlan(UNetPlan):
         if side is None or self.eng.prof is not None:      # per-launch event timing brackets launches on the main stream
             launch()
             return
-        self._host(self._wfork_fire)
+        cur = torch.cuda.current_stream(self.eng.device)
+        src = cur if (getattr(self, "_hside", None) is not None and cur == self._hside) else None
+        self._host(functools.partial(self._wfork_fire, src))
         with torch.cuda.stream(side):
             launch()
+
+    # ---- HF-guided cross-attention backward on a third stream ------------------------------------------------------------
+    # HF_guided_CA only produces SKIP tensors (resdiff/unet.py:156-163), so the gradient of its output is final as soon as the up path
+    # has been walked back, while its own gradient (into the down-path feature it read) is only needed when the backward pass reaches
+    # that Downsample again -- half a pass later.  In between sits the most expensive single piece of the step, the N = 8192 attention
+    # backward through four (B, 8192, 8192) matrices.  The branches therefore run on their own stream from the end of the up path on
+    # (deepest level first, the order in which the chain will ask for them), each into a private dx buffer and private attention
+    # scratch; the chain joins a branch where it used to compute it and adds the private dx.  WSR_HFCA_STREAM=0: off.
+    def _hstream(self):
+        if not hasattr(self, "_hside"):
+            on = (os.environ.get("WSR_HFCA_STREAM", "1") != "0" and self.eng.device.type == "cuda" and self.has_hfca
+                  and self.scores is not None)
+            self._hside = torch.cuda.Stream(device=self.eng.device) if on else None
+            if on:
+                e = self.eng
+                self._hscratch = (torch.empty_like(self.scores), torch.empty_like(self.probs), torch.empty_like(self.dP), torch.empty_like(self.dS))
+                self._hev_fork = torch.cuda.Event()
+                for ca in self.hfca:
+                    ca.dx_side = e.new_act(self.B, ca.h, ca.w, ca.c)
+                    ca.ev_done = torch.cuda.Event()
+        return self._hside
+
+    def _hfork_fire(self):
+        self._hev_fork.record(torch.cuda.current_stream(self.eng.device))
+        self._hside.wait_event(self._hev_fork)
+
+    def _hdone_fire(self, ca):
+        ca.ev_done.record(self._hside)
+
+    def _hjoin_fire(self, ca):
+        torch.cuda.current_stream(self.eng.device).wait_event(ca.ev_done)
+
+    def _hf_ca_bwd_all_on_side(self, order):
+        """Issue the backward of every HF-CA branch in ``order`` on the branch stream; returns False when the stream is off."""
+        side = self._hstream()
+        if side is None or self.eng.prof is not None:
+            return False
+        self._host(self._hfork_fire)
+        with torch.cuda.stream(side):
+            for ca in order:
+                self._hf_ca_bwd(ca, dx=ca.dx_side, scratch=self._hscratch)
+                self._host(functools.partial(self._hdone_fire, ca))
+        return True
 
     def _wgrad(self, x, dy, conv_mod, taps, up=1, rows=None, bias=True):
         """Weight (+ bias) gradient of ``conv_mod`` (an nn.Conv2d) straight into its OIHW gradient view.
@@ -371,14 +418,14 @@ class UNetTrainPlan(UNetPlan):
         self.eng.gn_bwd(x, gamma, beta, groups or self.groups, act, da, dx, self.red.data_ptr() + 8 * red_off,
                         self.gv(gn_mod.weight), self.gv(gn_mod.bias), True, colsum, colsum_ld, drop)
 
-    def _attention_bwd(self, q, k, vT, do, dq, dk, dvT):
+    def _attention_bwd(self, q, k, vT, do, dq, dk, dvT, scratch=None):
         """Backward of o = softmax(q k^T / sqrt(C)) v (nn_modules/resnet.py:90-97, guided_cross_attention.py:34-41).
         q, k, do, dq, dk: Acts (B, ., ., C); vT, dvT: (B, C, Nk) tensors.  dq / dk are written (not accumulated)."""
         e, B = self.eng, self.B
         Nq, Nk, Cc = q.H * q.W, k.H * k.W, q.C
         scale = 1.0 / math.sqrt(Cc)
         n = B * Nq * Nk
-        S, P, dP, dS = self.scores[:n], self.probs[:n], self.dP[:n], self.dS[:n]
+        S, P, dP, dS = (t[:n] for t in (scratch or (self.scores, self.probs, self.dP, self.dS)))
         s_dt = nat.BF16 if S.dtype == torch.bfloat16 else nat.F32
         p_dt = nat.BF16 if P.dtype == torch.bfloat16 else nat.F32
         ds_dt = nat.BF16 if dS.dtype == torch.bfloat16 else nat.F32
@@ -451,18 +498,25 @@ class UNetTrainPlan(UNetPlan):
         self._wgrad(r.a1, d_h, rb.block1.block[3], taps3)
         self._gn_bwd(x, rb.block1.block[0], SW, d_a1, dx, r.red1, gamma=r.g1, beta=r.b1)
 
-    def _hf_ca_bwd(self, ca):
-        """Backward of UNetPlan._hf_ca; reads G(ca.y), accumulates into G(ca.x)."""
+    def _hf_ca_bwd(self, ca, dx=None, scratch=None):
+        """Backward of UNetPlan._hf_ca; reads G(ca.y), accumulates into G(ca.x) -- or, dx given, WRITES the branch's gradient w.r.t.
+        ca.x into that private buffer (branch stream: the chain adds it to G(ca.x) at the join)."""
         e, B, G = self.eng, self.B, self.G
         m = ca.mod
         cc = ca.c
         taps1 = T.forward_taps(1, 1, ca.h, ca.w)
-        dy, dx = G(ca.y), G(ca.x)
+        dy = G(ca.y)
+        private = dx is not None
+        if not private:
+            dx = G(ca.x)
         d_o, d_k, d_q, d_n = G(ca.obuf), G(ca.kbuf), G(ca.q), G(ca.nbuf)
         e.conv(dy, ca.dwout, d_o, bias=False)
         self._wgrad(ca.obuf, dy, m.out, taps1)
-        e.call("wsr_axpby", dy.ptr, dy.dt, dy.ld, 1.0, dx.ptr, dx.dt, dx.ld, 1.0, dx.ptr, dx.dt, dx.ld, B * ca.h * ca.w, cc, e.stream)
-        self._attention_bwd(ca.q, ca.kbuf, ca.vT, d_o, d_q, d_k, ca.dvT)
+        if private:      # dx = dy (z = dy with weight 0: never reads what the private buffer held)
+            e.call("wsr_axpby", dy.ptr, dy.dt, dy.ld, 1.0, dy.ptr, dy.dt, dy.ld, 0.0, dx.ptr, dx.dt, dx.ld, B * ca.h * ca.w, cc, e.stream)
+        else:
+            e.call("wsr_axpby", dy.ptr, dy.dt, dy.ld, 1.0, dx.ptr, dx.dt, dx.ld, 1.0, dx.ptr, dx.dt, dx.ld, B * ca.h * ca.w, cc, e.stream)
+        self._attention_bwd(ca.q, ca.kbuf, ca.vT, d_o, d_q, d_k, ca.dvT, scratch=scratch)
         self._wgrad(ca.qimg, d_q, m.q, taps1, bias=False)
         e.conv(d_k, ca.dwk, d_n, bias=False)
         self._wgrad(ca.nbuf, d_k, m.kv, taps1, rows=(0, cc), bias=False)
@@ -605,6 +659,11 @@ class UNetTrainPlan(UNetPlan):
                 x = self._up_inputs[k]
                 e.conv(G(r.y), r.dconv, G(x), taps=T.dgrad_upsample_taps(x.H, x.W), bias=False, res=G(x))
                 self._wgrad(x, G(r.y), r.mod.conv, T.forward_upsample_taps(x.H, x.W), up=2)
+        # HF-CA branches: their output gradients (skip slots of the up path's concat buffers) are final now
+        hf_on_side = False
+        if self.has_hfca:
+            order = [self.downs[i].ca for i in range(len(self.downs) - 1, 0, -1) if self.downs[i].kind != "res"]
+            hf_on_side = self._hf_ca_bwd_all_on_side(order)
         self._ready(0)
         for i in range(len(self.mids) - 1, -1, -1):
             self._res_block_bwd(self.mids[i], self._mid_inputs[i])
@@ -614,7 +673,12 @@ class UNetTrainPlan(UNetPlan):
             if r.kind == "res":
                 self._res_block_bwd(r, x)
             else:
-                if self.has_hfca:
+                if self.has_hfca and hf_on_side:
+                    ca, gx = r.ca, G(r.ca.x)
+                    self._host(functools.partial(self._hjoin_fire, ca))
+                    e.call("wsr_axpby", ca.dx_side.ptr, ca.dx_side.dt, ca.dx_side.ld, 1.0, gx.ptr, gx.dt, gx.ld, 1.0, gx.ptr, gx.dt, gx.ld,
+                           B * ca.h * ca.w, ca.c, e.stream)
+                elif self.has_hfca:
                     self._hf_ca_bwd(r.ca)
                 dy, dx = G(r.y), G(x)
                 for tp in T.dgrad_down_taps(x.H, x.W):
