@@ -101,7 +101,8 @@ class UNetTrainPlan(UNetPlan):
         self._marks.append(len(order))
         for r in reversed(self.mids):
             res_params(r)
-        for r in reversed(self.downs[1:]):
+        self._marks.append(len(order))    # most parameters sit in the up path, the mid blocks and the two deepest levels: a mark after each
+        for r in reversed(self.downs[1:]):   # lets their all-reduce start while the shallow, parameter-poor levels are still being walked
             if r.kind == "res":
                 res_params(r)
             else:
@@ -109,7 +110,9 @@ class UNetTrainPlan(UNetPlan):
                     m = r.ca.mod
                     add(m.out.weight, m.out.bias, m.kv.weight, m.q.weight, m.norm.weight, m.norm.bias)
                 add(r.mod.conv.weight, r.mod.conv.bias)
-        self._marks.append(len(order))
+                self._marks.append(len(order))
+        if self._marks[-1] != len(order):
+            self._marks.append(len(order))
         stem = self.downs[0].mod
         add(stem.weight, stem.bias)
         if self.kind == "srdiff":
@@ -333,9 +336,9 @@ class UNetTrainPlan(UNetPlan):
         self._wforked = True
 
     def _wjoin_fire(self, final):
-        # a gradient range is only consumed early by the bucketed all-reduce (on_ready); without one the single join at the end of the
-        # backward pass is enough, and the side stream may lag behind the chain as far as it likes
-        if self._wforked and (final or self.on_ready is not None):
+        # the chain itself joins the side stream only at the end of the backward pass; gradient ranges handed to the bucketed all-reduce
+        # earlier are ordered after the side stream without blocking the chain (_ready_fire)
+        if self._wforked and final:
             self._wev_join.record(self._wside)
             torch.cuda.current_stream(self.eng.device).wait_event(self._wev_join)
             self._wforked = False
@@ -523,18 +526,41 @@ class UNetTrainPlan(UNetPlan):
         self._v_bwd(ca.wv, ca.nbuf, ca.dvT, d_n, self.gv(m.kv.weight)[cc:].view(cc, cc))
         self._gn_bwd(ca.x, m.norm, nat.ACT_NONE, d_n, dx, ca.red, gamma=ca.g, beta=ca.b, groups=32)
 
-    def _ready(self, mark):
-        self._wjoin(mark == 2)          # the range's weight gradients were computed on the side stream (mark 2 = end of the backward pass)
+    def _ready(self):
+        """The gradient range that ends at the next mark is final (call order = order of ``self._marks``, then the tail)."""
+        mark = self._mark_i
+        self._mark_i += 1
+        assert mark <= len(self._marks)
+        final = mark == len(self._marks)
+        if final:
+            self._wjoin(True)          # end of the pass: the optimizer reads every gradient
         if self.eng.rec is not None:
-            self.eng.rec.append((None, functools.partial(self._ready_fire, mark), "on_ready"))
-        self._ready_fire(mark)
+            self.eng.rec.append((None, functools.partial(self._ready_fire, mark, final), "on_ready"))
+        self._ready_fire(mark, final)
 
-    def _ready_fire(self, mark):
-        if self.on_ready is not None:
-            lo = 0 if mark == 0 else self._mark_offsets[mark - 1]
-            hi = self._mark_offsets[mark] if mark < len(self._mark_offsets) else self.gflat.numel()
-            if hi > lo:
-                self.on_ready(lo, hi)
+    def _ready_fire(self, mark, final=True):
+        if self.on_ready is None:
+            return
+        lo = 0 if mark == 0 else self._mark_offsets[mark - 1]
+        hi = self._mark_offsets[mark] if mark < len(self._mark_offsets) else self.gflat.numel()
+        if hi <= lo:
+            return
+        side = getattr(self, "_wside", None)
+        if final or side is None or not self._wforked:
+            self.on_ready(lo, hi)
+            return
+        # The range's weight gradients may still be running on the side stream.  Making the chain wait for them here would serialise
+        # the two streams at every mark (measured: 1.3 -> 2.0 ms of exposed all-reduce with 7 marks); instead a third stream waits for
+        # BOTH and the hook -- whose collectives order themselves after the stream they are issued from -- is called on it.
+        if not hasattr(self, "_rsync"):
+            self._rsync = torch.cuda.Stream(device=self.eng.device)
+            self._rev_m, self._rev_s = torch.cuda.Event(), torch.cuda.Event()
+        self._rev_m.record(torch.cuda.current_stream(self.eng.device))
+        self._rev_s.record(side)
+        self._rsync.wait_event(self._rev_m)
+        self._rsync.wait_event(self._rev_s)
+        with torch.cuda.stream(self._rsync):
+            self.on_ready(lo, hi)
 
     # ------------------------------------------------------------------------------------------------------------------
     # the backward pass
@@ -629,6 +655,7 @@ class UNetTrainPlan(UNetPlan):
 
     def _backward_body(self, d_eps):
         e, B, G = self.eng, self.B, self.G
+        self._mark_i = 0
         st = e.stream
         net = self.net
         SW = nat.ACT_SWISH
@@ -664,9 +691,10 @@ class UNetTrainPlan(UNetPlan):
         if self.has_hfca:
             order = [self.downs[i].ca for i in range(len(self.downs) - 1, 0, -1) if self.downs[i].kind != "res"]
             hf_on_side = self._hf_ca_bwd_all_on_side(order)
-        self._ready(0)
+        self._ready()
         for i in range(len(self.mids) - 1, -1, -1):
             self._res_block_bwd(self.mids[i], self._mid_inputs[i])
+        self._ready()
         for i in range(len(self.downs) - 1, 0, -1):
             r = self.downs[i]
             x = self._down_inputs[i]
@@ -684,7 +712,9 @@ class UNetTrainPlan(UNetPlan):
                 for tp in T.dgrad_down_taps(x.H, x.W):
                     e.conv(dy, r.dconv, dx, taps=tp, bias=False, res=dx)
                 self._wgrad(x, dy, r.mod.conv, T.forward_taps(3, 2, x.H, x.W))
-        self._ready(1)
+                self._ready()
+        if self.downs[1].kind == "res":
+            self._ready()
 
         # stem (its input is not a function of any parameter except through ResDiff's FD_Info_Spliter)
         stem = self.downs[0]
@@ -713,7 +743,8 @@ class UNetTrainPlan(UNetPlan):
         e.call("wsr_noise_embed_bwd", self.levels.data_ptr(), B, self.inner, self.mlp_w1.data_ptr(), self.mlp_b1.data_ptr(),
                self.mlp_w2.data_ptr(), self.time_act, self.dtemb.data_ptr(), self.gv(mlp[1].weight).data_ptr(),
                self.gv(mlp[1].bias).data_ptr(), self.gv(mlp[3].weight).data_ptr(), self.gv(mlp[3].bias).data_ptr(), st)
-        self._ready(2)
+        self._ready()
+        assert self._mark_i == len(self._marks) + 1
         return self.gflat
 
     # ------------------------------------------------------------------------------------------------------------------
