@@ -99,8 +99,9 @@ int wsr_conv_tc_can_fuse_gn(const WsrConvDesc* d);
 /* test introspection: (CTA pairs << 20) | (column-tile width << 8) | K splits chosen by the most recent wsr_conv_tc / wsr_conv_taps_tc call */
 int wsr_debug_last_tc_config(void);
 /* split-K of the classic-mode tcgen05 convolution (a cluster of 2 / 4 / 8 CTAs per tile, each accumulating a range of the K blocks; partial
- * tiles exchanged through distributed shared memory) is correct but measured at most 15 % faster per launch and slower for the whole step
- * on B200, so it is off unless WSR_SPLITK=1 or this switch is set; returns the previous setting. */
+ * tiles exchanged through distributed shared memory): mode 0 = never, 1 = the one measured-faster cut (default: 2-CTA clusters for 3x3
+ * convolutions whose tiles fill at most half of the SMs; env WSR_SPLITK), 2 = cost-model search over (column tile, 2 / 4 / 8 splits), measured
+ * slower for the whole step on B200 and kept for the kernel tests.  Returns the previous mode. */
 int wsr_debug_set_splitk(int on);
 /* CTA pairs (tcgen05 cta_group::2: two SMs of a TPC share one 256 x 256 tile, each staging half of the weight columns) for the classic-mode
  * 256-column convolution tiles: 0 = never, 1 = launches of more than one wave (default; env WSR_PAIR), 2 = every eligible launch (an even

@@ -1263,10 +1263,11 @@ static int launch_tc(const TcParams& p, cudaStream_t st) {
 // BN 64 / S 2: 21.1 us, BN 128 / S 2 and S 4: 22.9 / 22.7 us, BN 256 / S 2 and S 4: 27.3 us, BN 256 / S 8: 56 us.  The launch is
 // t = 5.3 us + 0.27 us per K block; halving the K loop saves 9.7 us and the cluster launch + two cluster-wide barrier rounds + the
 // exchange give 6 us of it back, and clusters of 8 do not even fit one wave.  Whole step at 8 images per GPU: 3.38 ms without, 3.90 ms
-// with the model's choice.  So split-K stays OFF unless WSR_SPLITK=1 (the round-1 global-memory exchange was worse still: 30 us).
+// with the model's choice.  So the cost-model search is for tests only (WSR_SPLITK=2 / wsr_debug_set_splitk(2)); the default (1) applies the
+// single cut that measured faster, below; 0 = never.  (The round-1 global-memory exchange was worse still: 30 us.)
 static int g_last_ksplit = 1, g_last_bn = 0, g_last_pair = 0;      // introspection for the tests (wsr_debug_last_tc_config)
 static int g_pair_mode = -1;                      // -1 = read WSR_PAIR on first use; wsr_debug_set_pair overrides
-static int g_splitk_on = -1;                      // -1 = read WSR_SPLITK on first use (default off); wsr_debug_set_splitk overrides
+static int g_splitk_on = -1;                      // -1 = read WSR_SPLITK on first use; 0 off, 1 the measured rule (default), 2 cost-model search (tests)
 
 static double kblock_cycles(int bn) {
   const double fetch = (16384.0 + bn * 128.0) / 65.0, mma = 4.0 * (69.0 + 0.28 * bn);
@@ -1275,7 +1276,7 @@ static double kblock_cycles(int bn) {
 
 static int pick_split(int ncols, int m_tiles, int total_kb, int bn_nosplit, int* ksplit) {
   *ksplit = 1;
-  if (g_splitk_on < 0) g_splitk_on = getenv("WSR_SPLITK") ? (atoi(getenv("WSR_SPLITK")) != 0 ? 1 : 0) : 0;
+  if (g_splitk_on < 0) g_splitk_on = getenv("WSR_SPLITK") ? atoi(getenv("WSR_SPLITK")) : 1;
   static const bool forced = getenv("WSR_SPLITK_FORCE") != nullptr;
   if (!g_splitk_on && !forced) return bn_nosplit;
   const int sms = sm_count();
@@ -1289,6 +1290,14 @@ static int pick_split(int ncols, int m_tiles, int total_kb, int bn_nosplit, int*
       if ((fs == 2 || fs == 4 || fs == 8) && fs <= fbn / 32 && tiles * fs <= sms && per >= 1 && (fs - 1) * per < total_kb) { *ksplit = fs; return fbn; }
       if (fs == 1) return fbn;
     }
+    return bn_nosplit;
+  }
+  if (g_splitk_on == 1) {
+    // the one cut that measured faster (see above): keep the unsplit tile shape and halve its K loop over a 2-CTA cluster, when that
+    // still fits one wave and the K loop is long enough to pay for the exchange (3x3 convolutions with >= 256 input channels: 24.7 ->
+    // 21.1 us, 43.7 -> 33.8 us, 28.8 -> 24.0 us on the 8x16 level at 8 images; 1x1 convolutions get SLOWER, 7.5 -> 9.6 us)
+    const int tiles = m_tiles * ((ncols + bn_nosplit - 1) / bn_nosplit);
+    if (total_kb >= 36 && 2 * tiles <= sms && ncols % bn_nosplit == 0 && (bn_nosplit / 32) % 2 == 0) *ksplit = 2;
     return bn_nosplit;
   }
   const double base_tiles = (double)m_tiles * ((ncols + bn_nosplit - 1) / bn_nosplit);
@@ -1358,8 +1367,8 @@ extern "C" int wsr_debug_set_pair(int mode) {
   const int prev = g_pair_mode; g_pair_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode); return prev;
 }
 extern "C" int wsr_debug_set_splitk(int on) {
-  if (g_splitk_on < 0) g_splitk_on = getenv("WSR_SPLITK") ? (atoi(getenv("WSR_SPLITK")) != 0 ? 1 : 0) : 0;
-  const int prev = g_splitk_on; g_splitk_on = on ? 1 : 0; return prev;
+  if (g_splitk_on < 0) g_splitk_on = getenv("WSR_SPLITK") ? atoi(getenv("WSR_SPLITK")) : 1;
+  const int prev = g_splitk_on; g_splitk_on = on < 0 ? 0 : (on > 2 ? 2 : on); return prev;
 }
 
 extern "C" int wsr_conv_tc(const WsrConvDesc* d, void* stream) {

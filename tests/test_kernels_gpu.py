@@ -145,7 +145,7 @@ def test_conv_tc_split_k_vs_simt(case):
     operands, run twice.  The path is correct but measured not worth it on B200, so it is off by default; the
     test switches it on (wsr_debug_set_splitk) for its own launches only."""
     N, Cin, Cout, H, W, k, stride, up, Cin2, expect = case
-    prev = nat.call("wsr_debug_set_splitk", 1)
+    prev = nat.call("wsr_debug_set_splitk", 2)
     try:
         _split_k_case(N, Cin, Cout, H, W, k, stride, up, Cin2, expect)
     finally:
@@ -175,6 +175,22 @@ def test_conv_tc_cta_pair_vs_simt(case):
         _split_k_case(*case, expect=False, expect_pair=True)
     finally:
         nat.call("wsr_debug_set_pair", prev)
+
+
+@pytest.mark.parametrize("case", [
+    (8, 512, 512, 8, 16, 3, 1, False, 0, True),        # 64 tiles of 64 columns, 72 K blocks: halved over 2-CTA clusters
+    (8, 512, 512, 8, 16, 3, 1, False, 1024, True),     # ... with the fused 1x1 segment
+    (8, 512, 512, 8, 16, 1, 1, False, 0, False),       # 1x1: the K loop is too short to pay for the exchange
+    (8, 512, 512, 16, 32, 3, 1, False, 0, False),      # 128 tiles: no room for a second CTA per tile
+])
+def test_conv_tc_split_k_default_rule(case):
+    """The default split-K policy (mode 1): only the cut that measured faster on B200 -- the unsplit tile shape with its K loop halved over
+    a 2-CTA cluster, for 3x3 convolutions whose tiles fill at most half of the SMs."""
+    prev = nat.call("wsr_debug_set_splitk", 1)
+    try:
+        _split_k_case(*case)
+    finally:
+        nat.call("wsr_debug_set_splitk", prev)
 
 
 def _split_k_case(N, Cin, Cout, H, W, k, stride, up, Cin2, expect, expect_pair=None):
