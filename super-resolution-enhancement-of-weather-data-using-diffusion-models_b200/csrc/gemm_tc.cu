@@ -12,6 +12,12 @@
 // tcgen05.mma issuer (tcgen05.ld -> bias / time-embedding / activation / residual -> global).  Two accumulator
 // buffers in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
 //
+// Variants (template parameters): HALO / ROWS (tiles that are segments of image rows: one halo tile serves the 9 taps), VM (vertical tap
+// merge for 64-column tiles), FUSE (GroupNorm + Swish of the INPUT applied between TMA and MMA by extra transform warps), STG (epilogue
+// stores staged through shared memory), SPLIT (the K loop of a tile cut over the CTAs of a thread-block cluster, fp32 partials exchanged
+// through distributed shared memory) and PAIR (cta_group::2: two CTAs of one TPC share a 256 x 256 tile, each staging its own 128 rows of
+// activations and half of the weight columns; the leader issues the MMAs and commits to the barriers of both).
+//
 // Reference call sites replaced: every nn.Conv2d on the UNet path (nn_modules/resnet.py:24,51,78-79,
 // functional_layers.py:64,79, resdiff/unet.py:68, guided_cross_attention.py:20-22) and the attention einsums
 // (nn_modules/resnet.py:90-97, guided_cross_attention.py:34-41).
