@@ -12,6 +12,7 @@ always runs on one GPU (model.py:79-82).  Here:
     last gradient is ready, i.e. overlapped with the rest of backward.  Loss semantics of the reference are kept:
     every rank contributes sum-loss / GLOBAL numel (model.py:64-66) and gradients are SUM-reduced.
 """
+import os
 import torch
 import torch.distributed as dist
 
@@ -131,7 +132,9 @@ class FlatGradReducer:
     (models/diffusion_models/model.py:64-66) -- so that the SUM of the per-rank gradients is the reference's gradient.
     """
 
-    def __init__(self, plan, bucket_mb=32.0, group=None):
+    def __init__(self, plan, bucket_mb=None, group=None):
+        if bucket_mb is None:
+            bucket_mb = float(os.environ.get("WSR_BUCKET_MB", "32"))
         self.plan, self.group = plan, group
         self.bucket_elems = max(1, int(bucket_mb * (1 << 20)) // 4)
         self._pending = []
