@@ -370,6 +370,11 @@ class UNetTrainPlan(UNetPlan):
         if not hasattr(self, "_hside"):
             on = (os.environ.get("WSR_HFCA_STREAM", "1") != "0" and self.eng.device.type == "cuda" and self.has_hfca
                   and self.scores is not None)
+            if on:
+                # the branch needs its own (B, N, N) scratch set (3.2 GB at batch 4): beyond 8 GB the batch is large enough to fill the
+                # machine without the overlap, and the memory is better left to the activations
+                extra = sum(t.numel() * t.element_size() for t in (self.scores, self.probs, self.dP, self.dS))
+                on = extra <= 8 * (1 << 30)
             self._hside = torch.cuda.Stream(device=self.eng.device) if on else None
             if on:
                 e = self.eng
